@@ -1,0 +1,829 @@
+/*
+ * rnde_oracle.c -- CPU ORACLE (test infrastructure, NOT the product).
+ *
+ * PARITY UNPINNED: the reference's tests hold no golden vectors
+ * (test/test_node.jl:1-89 is @code_warntype only) and no Julia toolchain exists
+ * in this image, so this oracle could not be checked against the reference
+ * itself.  It is a restatement of:
+ *   - src/models/neural_ode.jl:48-144      (problem set-up, return tuple, nfe)
+ *   - src/models/basic.jl:16-28            (TDChain: vcat(x, t) before every layer)
+ *   - experiments/mnist_node.jl:41-54      (MLPDynamics: tanh on both layers)
+ *   - experiments/mnist_node.jl:62-103     (the three regulariser closures)
+ *   - test/test_node.jl:28-89              (func = EEst*dt, abs(eigen_est*dt))
+ *   - OrdinaryDiffEq 5.50.0 / DiffEqBase 6.53.4 / DiffEqCallbacks 2.16.0
+ *     (Manifest.toml:964,242-248,250; un-vendored) as recalled in
+ *     Tsit5 step, RMS norm, PI controller,
+ *     Hairer-Wanner initial dt, FSAL, nf accounting, SavingCallback, eigen_est,
+ *     AutoSwitch.
+ * It is validated against oracle/torch_oracle.py (autograd through the same
+ * algorithm) in FP64, against analytic ODEs and scipy (tests/test_oracle_*.py).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+ * reference legs may load this file's shared objects.
+ *
+ * Build: oracle/Makefile  ->  oracle/_build/liborc_f32.so, liborc_f64.so
+ * Arithmetic: include/regnde_canon.h ("canonical order"); the FP32 build is the
+ * bit-level specification the CUDA kernels are tested against.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+#include "regnde_canon.h"
+
+#ifdef ORC_F64
+typedef double REAL;
+#define R_FMA(a, b, c) __builtin_fma((a), (b), (c))
+#define R_SQRT(a) __builtin_sqrt((a))
+#define R_TANH(a) tanh((a))
+#define R_ABS(a) fabs((a))
+#else
+typedef float REAL;
+#define R_FMA(a, b, c) __builtin_fmaf((a), (b), (c))
+#define R_SQRT(a) __builtin_sqrtf((a))
+#define R_TANH(a) canon_tanhf((a))
+#define R_ABS(a) fabsf((a))
+#endif
+
+#define ORC_OK 0
+#define ORC_ERR_MAXITERS 1
+#define ORC_ERR_DTMIN 2
+#define ORC_ERR_NAN 3
+#define ORC_ERR_ARG 4
+
+enum { ACT_ID = 0, ACT_TANH = 1 };
+enum { ALG_TSIT5 = 0, ALG_AUTO_TSIT5 = 1 };
+enum { REG_NONE = 0, REG_ERR_DT = 1, REG_STIFF_DT_ABS = 2, REG_STIFF_SCALED = 3, REG_ERR_PLUS_STIFF = 4 };
+
+typedef struct {
+    int D, H, B;
+    int act1, act2;
+    int time_dep;
+    int kblock1, kblock2;  /* canonical K blocking of layer 1/2 (<=0: whole K) */
+    int alg;
+    int reg_kind;
+    int max_steps;         /* maxiters */
+    int nthreads;          /* <=0: all */
+    double t0, t1, abstol, reltol;
+    double dtmin;
+    /* forced step sequence (replay): if n_forced>0 the controller is bypassed:
+     * attempt i uses forced_dt[i] and is accepted iff forced_accept[i]. */
+    int n_forced;
+    const double* forced_dt;
+    const int* forced_accept;
+} orc_config;
+
+typedef struct {
+    int nf, naccept, nreject, n_saved, retcode;
+    double t_final, dt_last, dt_init;
+} orc_stats;
+
+typedef struct {
+    orc_config cfg;
+    size_t np;
+    /* tape: per accepted step */
+    int cap, nsteps;
+    REAL* tp_t; REAL* tp_dt; REAL* tp_eest; REAL* tp_eig;
+    REAL** tp_uprev; REAL** tp_k1;
+    REAL* u0; REAL* p;
+    /* attempted-step log */
+    int log_cap, log_n; double* log_dt; int* log_acc; double* log_eest;
+    REAL* saveval; int n_saved;
+    orc_stats st;
+} orc_handle;
+
+static size_t n_params(const orc_config* c) {
+    int td = c->time_dep ? 1 : 0;
+    return (size_t)c->H * (c->D + td) + c->H + (size_t)c->D * (c->H + td) + c->D;
+}
+
+/* ------------------------------------------------------------------ */
+/* canonical reductions                                                */
+/* ------------------------------------------------------------------ */
+/* per-column sum of squares of v[0..D) with row blocking kb: 8-way interleaved
+ * fma chains per block, lanes summed 0..7, blocks summed in order. */
+static REAL col_sumsq(const REAL* v, int D, int kb) {
+    REAL tot = 0; int first = 1;
+    for (int r0 = 0; r0 < D; r0 += kb) {
+        int r1 = r0 + kb < D ? r0 + kb : D;
+        REAL a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int r = r0; r < r1; ++r) { int l = (r - r0) & 7; a[l] = R_FMA(v[r], v[r], a[l]); }
+        REAL s = a[0];
+        for (int l = 1; l < 8; ++l) s = s + a[l];
+        if (first) { tot = s; first = 0; } else tot = tot + s;
+    }
+    return tot;
+}
+/* total over columns: 32-way interleaved chains then xor-butterfly 16,8,4,2,1 */
+static REAL cols_total(const REAL* q, int B) {
+    REAL s[32];
+    for (int l = 0; l < 32; ++l) s[l] = 0;
+    for (int j = 0; j < B; ++j) s[j & 31] = s[j & 31] + q[j];
+    for (int off = 16; off >= 1; off >>= 1) {
+        REAL n[32];
+        for (int l = 0; l < 32; ++l) n[l] = s[l] + s[l ^ off];
+        memcpy(s, n, sizeof(s));
+    }
+    return s[0];
+}
+static REAL rms_from_total(REAL tot, long long count) { return R_SQRT(tot / (REAL)count); }
+
+/* ------------------------------------------------------------------ */
+/* vector field: y = act2(W2*[act1(W1*[z;t]+b1);t]+b2), per column       */
+/* ------------------------------------------------------------------ */
+static REAL act_apply(int act, REAL s) { return act == ACT_TANH ? R_TANH(s) : s; }
+
+/* z: D x B (col-major), out k: D x B, optional hout: H x B */
+static void rhs_eval(const orc_config* c, const REAL* p, const REAL* z, REAL t, REAL* k, REAL* hout) {
+    const int D = c->D, H = c->H, B = c->B, td = c->time_dep ? 1 : 0;
+    const REAL* W1 = p;
+    const REAL* b1 = W1 + (size_t)H * (D + td);
+    const REAL* W2 = b1 + H;
+    const REAL* b2 = W2 + (size_t)D * (H + td);
+    const int kb1 = c->kblock1 > 0 ? c->kblock1 : D;
+    const int kb2 = c->kblock2 > 0 ? c->kblock2 : H;
+#pragma omp parallel
+    {
+        REAL* pacc = (REAL*)malloc(sizeof(REAL) * (size_t)(H > D ? H : D));
+        REAL* s = (REAL*)malloc(sizeof(REAL) * (size_t)(H > D ? H : D));
+        REAL* hh = (REAL*)malloc(sizeof(REAL) * (size_t)H);
+#pragma omp for schedule(static)
+        for (int j = 0; j < B; ++j) {
+            const REAL* zj = z + (size_t)D * j;
+            /* layer 1 */
+            for (int i0 = 0, first = 1; i0 < D; i0 += kb1, first = 0) {
+                int i1 = i0 + kb1 < D ? i0 + kb1 : D;
+                for (int o = 0; o < H; ++o) pacc[o] = 0;
+                for (int i = i0; i < i1; ++i) {
+                    const REAL xv = zj[i];
+                    const REAL* w = W1 + (size_t)H * i;
+                    for (int o = 0; o < H; ++o) pacc[o] = R_FMA(w[o], xv, pacc[o]);
+                }
+                if (first) for (int o = 0; o < H; ++o) s[o] = pacc[o];
+                else for (int o = 0; o < H; ++o) s[o] = s[o] + pacc[o];
+            }
+            for (int o = 0; o < H; ++o) {
+                REAL v = s[o];
+                if (td) v = R_FMA(W1[(size_t)H * D + o], t, v);
+                v = v + b1[o];
+                hh[o] = act_apply(c->act1, v);
+            }
+            if (hout) memcpy(hout + (size_t)H * j, hh, sizeof(REAL) * H);
+            /* layer 2 */
+            for (int i0 = 0, first = 1; i0 < H; i0 += kb2, first = 0) {
+                int i1 = i0 + kb2 < H ? i0 + kb2 : H;
+                for (int o = 0; o < D; ++o) pacc[o] = 0;
+                for (int i = i0; i < i1; ++i) {
+                    const REAL xv = hh[i];
+                    const REAL* w = W2 + (size_t)D * i;
+                    for (int o = 0; o < D; ++o) pacc[o] = R_FMA(w[o], xv, pacc[o]);
+                }
+                if (first) for (int o = 0; o < D; ++o) s[o] = pacc[o];
+                else for (int o = 0; o < D; ++o) s[o] = s[o] + pacc[o];
+            }
+            REAL* kj = k + (size_t)D * j;
+            for (int o = 0; o < D; ++o) {
+                REAL v = s[o];
+                if (td) v = R_FMA(W2[(size_t)D * H + o], t, v);
+                v = v + b2[o];
+                kj[o] = act_apply(c->act2, v);
+            }
+        }
+        free(pacc); free(s); free(hh);
+    }
+}
+
+/* VJP of the field at (z,t) with cotangent kbar: returns zbar, accumulates dp.
+ * Uses saved h (H x B) and k (D x B).  dp accumulators are per-thread.        */
+static void rhs_vjp(const orc_config* c, const REAL* p, const REAL* z, REAL t, const REAL* h, const REAL* k,
+                    const REAL* kbar, REAL* zbar, REAL** dp_thr, REAL* tbar_out) {
+    const int D = c->D, H = c->H, B = c->B, td = c->time_dep ? 1 : 0;
+    const REAL* W1 = p;
+    const REAL* W2 = p + (size_t)H * (D + td) + H;
+    const size_t oW1 = 0, ob1 = (size_t)H * (D + td), oW2 = ob1 + H, ob2 = oW2 + (size_t)D * (H + td);
+    double tbar_tot = 0;
+#pragma omp parallel reduction(+ : tbar_tot)
+    {
+#ifdef _OPENMP
+        REAL* dp = dp_thr[omp_get_thread_num()];
+#else
+        REAL* dp = dp_thr[0];
+#endif
+        REAL* d2 = (REAL*)malloc(sizeof(REAL) * (size_t)D);
+        REAL* d1 = (REAL*)malloc(sizeof(REAL) * (size_t)H);
+#pragma omp for schedule(static)
+        for (int j = 0; j < B; ++j) {
+            const REAL* zj = z + (size_t)D * j;
+            const REAL* hj = h + (size_t)H * j;
+            const REAL* kj = k + (size_t)D * j;
+            const REAL* kb = kbar + (size_t)D * j;
+            REAL* zb = zbar + (size_t)D * j;
+            for (int o = 0; o < D; ++o) d2[o] = c->act2 == ACT_TANH ? kb[o] * (1 - kj[o] * kj[o]) : kb[o];
+            /* dW2 += d2 * [h;t]^T ; db2 += d2 ; hbar = W2[:, :H]^T d2 */
+            for (int i = 0; i < H; ++i) {
+                const REAL* w = W2 + (size_t)D * i;
+                REAL* dw = dp + oW2 + (size_t)D * i;
+                const REAL hv = hj[i];
+                REAL acc = 0;
+                for (int o = 0; o < D; ++o) { dw[o] += d2[o] * hv; acc += w[o] * d2[o]; }
+                d1[i] = c->act1 == ACT_TANH ? acc * (1 - hv * hv) : acc;
+            }
+            if (td) {
+                REAL* dw = dp + oW2 + (size_t)D * H;
+                const REAL* w = W2 + (size_t)D * H;
+                REAL acc = 0;
+                for (int o = 0; o < D; ++o) { dw[o] += d2[o] * t; acc += w[o] * d2[o]; }
+                tbar_tot += (double)acc;
+            }
+            for (int o = 0; o < D; ++o) dp[ob2 + o] += d2[o];
+            /* dW1 += d1 * [z;t]^T ; db1 += d1 ; zbar = W1[:, :D]^T d1 */
+            for (int i = 0; i < D; ++i) {
+                const REAL* w = W1 + (size_t)H * i;
+                REAL* dw = dp + oW1 + (size_t)H * i;
+                const REAL zv = zj[i];
+                REAL acc = 0;
+                for (int o = 0; o < H; ++o) { dw[o] += d1[o] * zv; acc += w[o] * d1[o]; }
+                zb[i] = acc;
+            }
+            if (td) {
+                REAL* dw = dp + oW1 + (size_t)H * D;
+                const REAL* w = W1 + (size_t)H * D;
+                REAL acc = 0;
+                for (int o = 0; o < H; ++o) { dw[o] += d1[o] * t; acc += w[o] * d1[o]; }
+                tbar_tot += (double)acc;
+            }
+            for (int o = 0; o < H; ++o) dp[ob1 + o] += d1[o];
+        }
+        free(d2); free(d1);
+    }
+    if (tbar_out) *tbar_out = (REAL)tbar_tot;
+}
+
+/* ------------------------------------------------------------------ */
+/* one Tsit5 attempt                                                   */
+/* ------------------------------------------------------------------ */
+typedef struct {
+    REAL *k[8];   /* k[1..7] */
+    REAL *z[8];   /* z[2..7]; z[7] = u_new */
+    REAL *h[8];   /* h[2..7] hidden activations of the stage evals (h[1] given by caller when needed) */
+    REAL *utilde, *atmp, *colq;
+} step_ws;
+
+static const double A_[8][7] = {
+    {0}, {0},
+    {0, TS_A21},
+    {0, TS_A31, TS_A32},
+    {0, TS_A41, TS_A42, TS_A43},
+    {0, TS_A51, TS_A52, TS_A53, TS_A54},
+    {0, TS_A61, TS_A62, TS_A63, TS_A64, TS_A65},
+    {0, TS_A71, TS_A72, TS_A73, TS_A74, TS_A75, TS_A76}};
+static const double BT_[8] = {0, TS_BT1, TS_BT2, TS_BT3, TS_BT4, TS_BT5, TS_BT6, TS_BT7};
+static const double C_[8] = {0, 0, TS_C1, TS_C2, TS_C3, TS_C4, 1.0, 1.0};
+
+static REAL stage_time(REAL t, REAL dt, int i) {
+    if (i >= 6) return t + dt;
+    return R_FMA((REAL)C_[i], dt, t);
+}
+
+/* z_i = uprev + dt*(sum_j a_ij k_j): c = a_i1*k1; c = fma(a_ij,k_j,c); z = fma(dt,c,uprev).
+ * stage 2 follows upstream's  a = dt*a21; uprev + a*k1. */
+static void stage_combo(const orc_config* c, int i, REAL dt, const REAL* uprev, REAL* const* k, REAL* z) {
+    const size_t n = (size_t)c->D * c->B;
+    if (i == 2) {
+        const REAL a = dt * (REAL)TS_A21;
+#pragma omp parallel for schedule(static)
+        for (size_t e = 0; e < n; ++e) z[e] = R_FMA(a, k[1][e], uprev[e]);
+        return;
+    }
+    REAL a[7];
+    for (int j = 1; j < i; ++j) a[j] = (REAL)A_[i][j];
+#pragma omp parallel for schedule(static)
+    for (size_t e = 0; e < n; ++e) {
+        REAL s = a[1] * k[1][e];
+        for (int j = 2; j < i; ++j) s = R_FMA(a[j], k[j][e], s);
+        z[e] = R_FMA(dt, s, uprev[e]);
+    }
+}
+
+/* performs the attempt; k[1] must hold fsalfirst.  Returns EEst, eigen_est. */
+static void tsit5_attempt(const orc_config* c, const REAL* p, const REAL* uprev, REAL t, REAL dt, step_ws* w,
+                          REAL* EEst, REAL* eig, int want_h) {
+    const int D = c->D, B = c->B;
+    const size_t n = (size_t)D * B;
+    const long long cnt = (long long)D * B;
+    const int kb = c->kblock1 > 0 ? c->kblock1 : D;
+    for (int i = 2; i <= 7; ++i) {
+        stage_combo(c, i, dt, uprev, w->k, w->z[i]);
+        rhs_eval(c, p, w->z[i], stage_time(t, dt, i), w->k[i], want_h ? w->h[i] : NULL);
+    }
+    if (c->alg == ALG_AUTO_TSIT5) {
+        /* eigen_est = norm(k7-k6)/norm(u-g6)  (Appendix A.2) */
+        REAL tot1, tot2;
+#pragma omp parallel for schedule(static)
+        for (int j = 0; j < B; ++j) {
+            REAL* d = w->atmp + (size_t)D * j;
+            for (int i = 0; i < D; ++i) d[i] = w->k[7][(size_t)D * j + i] - w->k[6][(size_t)D * j + i];
+            w->colq[j] = col_sumsq(d, D, kb);
+        }
+        tot1 = cols_total(w->colq, B);
+#pragma omp parallel for schedule(static)
+        for (int j = 0; j < B; ++j) {
+            REAL* d = w->atmp + (size_t)D * j;
+            for (int i = 0; i < D; ++i) d[i] = w->z[7][(size_t)D * j + i] - w->z[6][(size_t)D * j + i];
+            w->colq[j] = col_sumsq(d, D, kb);
+        }
+        tot2 = cols_total(w->colq, B);
+        *eig = rms_from_total(tot1, cnt) / rms_from_total(tot2, cnt);
+    } else {
+        *eig = 1;
+    }
+    REAL bt[8];
+    for (int i = 1; i <= 7; ++i) bt[i] = (REAL)BT_[i];
+    const REAL atol = (REAL)c->abstol, rtol = (REAL)c->reltol;
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < B; ++j) {
+        for (int i = 0; i < D; ++i) {
+            size_t e = (size_t)D * j + i;
+            REAL s = bt[1] * w->k[1][e];
+            for (int q = 2; q <= 7; ++q) s = R_FMA(bt[q], w->k[q][e], s);
+            REAL ut = dt * s;
+            REAL a0 = R_ABS(uprev[e]), a1 = R_ABS(w->z[7][e]);
+            REAL m = a0 > a1 ? a0 : a1;
+            REAL den = R_FMA(m, rtol, atol);
+            w->utilde[e] = ut;
+            w->atmp[e] = ut / den;
+        }
+        w->colq[j] = col_sumsq(w->atmp + (size_t)D * j, D, kb);
+    }
+    (void)n;
+    *EEst = rms_from_total(cols_total(w->colq, B), cnt);
+}
+
+/* ------------------------------------------------------------------ */
+/* initial dt (Hairer-Wanner, Appendix A.5)                            */
+/* ------------------------------------------------------------------ */
+static REAL initial_dt(const orc_config* c, const REAL* p, const REAL* u0, const REAL* f0, REAL t0, REAL dtmax, REAL* scratch /*3*D*B*/,
+                       REAL* colq) {
+    const int D = c->D, B = c->B;
+    const long long cnt = (long long)D * B;
+    const int kb = c->kblock1 > 0 ? c->kblock1 : D;
+    const REAL atol = (REAL)c->abstol, rtol = (REAL)c->reltol;
+    REAL* tmp = scratch; REAL* u1 = scratch + (size_t)D * B; REAL* f1 = scratch + 2 * (size_t)D * B;
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < B; ++j) {
+        for (int i = 0; i < D; ++i) { size_t e = (size_t)D * j + i; tmp[e] = u0[e] / R_FMA(R_ABS(u0[e]), rtol, atol); }
+        colq[j] = col_sumsq(tmp + (size_t)D * j, D, kb);
+    }
+    REAL d0 = rms_from_total(cols_total(colq, B), cnt);
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < B; ++j) {
+        for (int i = 0; i < D; ++i) { size_t e = (size_t)D * j + i; tmp[e] = f0[e] / R_FMA(R_ABS(u0[e]), rtol, atol); }
+        colq[j] = col_sumsq(tmp + (size_t)D * j, D, kb);
+    }
+    REAL d1 = rms_from_total(cols_total(colq, B), cnt);
+    REAL dt0;
+    if (d0 < (REAL)1e-5 || d1 < (REAL)1e-5) dt0 = (REAL)1e-6;
+    else dt0 = (d0 / d1) / (REAL)100;
+    if (dt0 > dtmax) dt0 = dtmax;
+    const size_t n = (size_t)D * B;
+#pragma omp parallel for schedule(static)
+    for (size_t e = 0; e < n; ++e) u1[e] = R_FMA(dt0, f0[e], u0[e]);
+    rhs_eval(c, p, u1, t0 + dt0, f1, NULL);
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < B; ++j) {
+        for (int i = 0; i < D; ++i) { size_t e = (size_t)D * j + i; tmp[e] = (f1[e] - f0[e]) / R_FMA(R_ABS(u0[e]), rtol, atol); }
+        colq[j] = col_sumsq(tmp + (size_t)D * j, D, kb);
+    }
+    REAL d2 = rms_from_total(cols_total(colq, B), cnt) / dt0;
+    REAL md = d1 > d2 ? d1 : d2;
+    REAL dt1;
+    if (md <= (REAL)1e-15) {
+        REAL a = dt0 * (REAL)1e-3;
+        dt1 = a > (REAL)1e-6 ? a : (REAL)1e-6;
+    } else {
+#ifdef ORC_F64
+        double l10 = canon_log2(md) * 0.30102999566398120;
+        dt1 = canon_exp10(-(2.0 + l10) / 5.0);
+#else
+        float l10 = canon_log10f(md);
+        float ex = -(2.0f + l10) / 5.0f;
+        dt1 = (float)canon_exp10((double)ex);
+#endif
+    }
+    REAL dt = (REAL)100 * dt0;
+    if (dt1 < dt) dt = dt1;
+    if (dtmax < dt) dt = dtmax;
+    if (dt < (REAL)c->dtmin) dt = (REAL)c->dtmin;
+    return dt;
+}
+
+/* ------------------------------------------------------------------ */
+/* saved value (the reference's func closures)                         */
+/* ------------------------------------------------------------------ */
+static REAL saved_value(int kind, REAL EEst, REAL eig, REAL dt) {
+    const REAL stab = (REAL)1 / (REAL)(float)TS_STABILITY_SIZE;
+    switch (kind) {
+        case REG_ERR_DT: return EEst * dt;                        /* neural_ode.jl:116, mnist_node.jl:67 */
+        case REG_STIFF_DT_ABS: return R_ABS(eig * dt);            /* test_node.jl:75 */
+        case REG_STIFF_SCALED: {                                  /* mnist_node.jl:76-79 */
+            REAL s = R_ABS(eig);
+            return stab * ((s == 0 || s != s) ? (REAL)0 : s);
+        }
+        case REG_ERR_PLUS_STIFF: {                                /* mnist_node.jl:88-97 */
+            REAL e = EEst * dt;
+            REAL a = (e == 0 || e != e) ? (REAL)0 : e;
+            REAL b = (eig == 0 || eig != eig) ? (REAL)0 : eig;
+            return (a + ((REAL)0.1f * stab) * b) * (REAL)1;
+        }
+        default: return 0;
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* handle                                                              */
+/* ------------------------------------------------------------------ */
+#ifdef ORC_F64
+#define FN(name) orc64_##name
+#else
+#define FN(name) orc32_##name
+#endif
+
+int FN(create)(const orc_config* cfg, void** out) {
+    if (!cfg || cfg->D <= 0 || cfg->H <= 0 || cfg->B <= 0) return ORC_ERR_ARG;
+    orc_handle* h = (orc_handle*)calloc(1, sizeof(orc_handle));
+    h->cfg = *cfg;
+    if (h->cfg.max_steps <= 0) h->cfg.max_steps = 1000000;
+    if (h->cfg.dtmin <= 0) h->cfg.dtmin = 1e-10;
+    h->np = n_params(cfg);
+    h->cap = 0; h->nsteps = 0;
+    *out = h;
+    return ORC_OK;
+}
+
+static void tape_clear(orc_handle* h) {
+    for (int i = 0; i < h->nsteps; ++i) { free(h->tp_uprev[i]); free(h->tp_k1[i]); }
+    h->nsteps = 0;
+}
+static void tape_push(orc_handle* h, REAL t, REAL dt, REAL eest, REAL eig, const REAL* uprev, const REAL* k1) {
+    if (h->nsteps == h->cap) {
+        int nc = h->cap ? 2 * h->cap : 64;
+        h->tp_t = (REAL*)realloc(h->tp_t, sizeof(REAL) * nc);
+        h->tp_dt = (REAL*)realloc(h->tp_dt, sizeof(REAL) * nc);
+        h->tp_eest = (REAL*)realloc(h->tp_eest, sizeof(REAL) * nc);
+        h->tp_eig = (REAL*)realloc(h->tp_eig, sizeof(REAL) * nc);
+        h->tp_uprev = (REAL**)realloc(h->tp_uprev, sizeof(REAL*) * nc);
+        h->tp_k1 = (REAL**)realloc(h->tp_k1, sizeof(REAL*) * nc);
+        h->saveval = (REAL*)realloc(h->saveval, sizeof(REAL) * (nc + 1));
+        h->cap = nc;
+    }
+    size_t n = (size_t)h->cfg.D * h->cfg.B;
+    int i = h->nsteps++;
+    h->tp_t[i] = t; h->tp_dt[i] = dt; h->tp_eest[i] = eest; h->tp_eig[i] = eig;
+    h->tp_uprev[i] = (REAL*)malloc(sizeof(REAL) * n); memcpy(h->tp_uprev[i], uprev, sizeof(REAL) * n);
+    h->tp_k1[i] = (REAL*)malloc(sizeof(REAL) * n); memcpy(h->tp_k1[i], k1, sizeof(REAL) * n);
+}
+static void log_push(orc_handle* h, double dt, int acc, double eest) {
+    if (h->log_n == h->log_cap) {
+        int nc = h->log_cap ? 2 * h->log_cap : 128;
+        h->log_dt = (double*)realloc(h->log_dt, sizeof(double) * nc);
+        h->log_acc = (int*)realloc(h->log_acc, sizeof(int) * nc);
+        h->log_eest = (double*)realloc(h->log_eest, sizeof(double) * nc);
+        h->log_cap = nc;
+    }
+    h->log_dt[h->log_n] = dt; h->log_acc[h->log_n] = acc; h->log_eest[h->log_n] = eest; h->log_n++;
+}
+
+void FN(destroy)(void* hv) {
+    orc_handle* h = (orc_handle*)hv;
+    if (!h) return;
+    tape_clear(h);
+    free(h->tp_t); free(h->tp_dt); free(h->tp_eest); free(h->tp_eig); free(h->tp_uprev); free(h->tp_k1);
+    free(h->u0); free(h->p); free(h->log_dt); free(h->log_acc); free(h->log_eest); free(h->saveval);
+    free(h);
+}
+
+static step_ws* ws_alloc(const orc_config* c) {
+    step_ws* w = (step_ws*)calloc(1, sizeof(step_ws));
+    size_t n = (size_t)c->D * c->B, nh = (size_t)c->H * c->B;
+    for (int i = 1; i <= 7; ++i) { w->k[i] = (REAL*)malloc(sizeof(REAL) * n); w->z[i] = (REAL*)malloc(sizeof(REAL) * n); w->h[i] = (REAL*)malloc(sizeof(REAL) * nh); }
+    w->utilde = (REAL*)malloc(sizeof(REAL) * n); w->atmp = (REAL*)malloc(sizeof(REAL) * n);
+    w->colq = (REAL*)malloc(sizeof(REAL) * c->B);
+    return w;
+}
+static void ws_free(step_ws* w) {
+    for (int i = 1; i <= 7; ++i) { free(w->k[i]); free(w->z[i]); free(w->h[i]); }
+    free(w->utilde); free(w->atmp); free(w->colq); free(w);
+}
+
+/* forward solve.  u_out: D x B.  saveval_out (may be NULL) gets n_saved values. */
+int FN(forward)(void* hv, const REAL* x, const REAL* p, REAL* u_out, orc_stats* st_out) {
+    orc_handle* h = (orc_handle*)hv;
+    const orc_config* c = &h->cfg;
+#ifdef _OPENMP
+    if (c->nthreads > 0) omp_set_num_threads(c->nthreads);
+#endif
+    const int D = c->D, B = c->B;
+    const size_t n = (size_t)D * B;
+    tape_clear(h);
+    h->log_n = 0;
+    free(h->u0); free(h->p);
+    h->u0 = (REAL*)malloc(sizeof(REAL) * n); memcpy(h->u0, x, sizeof(REAL) * n);
+    h->p = (REAL*)malloc(sizeof(REAL) * h->np); memcpy(h->p, p, sizeof(REAL) * h->np);
+    if (!h->saveval) { h->saveval = (REAL*)malloc(sizeof(REAL) * 65); }
+    step_ws* w = ws_alloc(c);
+    REAL* u = (REAL*)malloc(sizeof(REAL) * n);
+    REAL* scratch = (REAL*)malloc(sizeof(REAL) * 3 * n);
+    memcpy(u, x, sizeof(REAL) * n);
+    orc_stats st; memset(&st, 0, sizeof(st));
+
+    const REAL t0 = (REAL)c->t0, tf = (REAL)c->t1;
+    REAL t = t0;
+    const REAL dtmax = tf - t0;
+    /* controller constants (Appendix A.4), converted once to REAL */
+    const REAL gamma = (REAL)(9.0 / 10.0), qmin = (REAL)(1.0 / 5.0), qmax = (REAL)10;
+    const REAL beta1 = (REAL)(7.0 / 50.0), beta2 = (REAL)(2.0 / 25.0), qoldinit = (REAL)1e-4;
+    REAL qold = qoldinit, q11 = 1;
+    /* SavingCallback initial entry: EEst=1, dt=0, eigen_est=1 (Appendix A.7) */
+    h->n_saved = 0;
+    if (c->reg_kind != REG_NONE) h->saveval[h->n_saved++] = saved_value(c->reg_kind, (REAL)1, (REAL)1, (REAL)0);
+    /* initialize!: fsalfirst */
+    rhs_eval(c, p, u, t, w->k[1], NULL); st.nf += 1;
+    REAL dt;
+    if (c->n_forced > 0) dt = (REAL)c->forced_dt[0];
+    else dt = initial_dt(c, p, u, w->k[1], t, dtmax, scratch, w->colq);
+    st.nf += 2;
+    st.dt_init = dt;
+    /* AutoSwitch state (Appendix A.8) */
+    int as_count = 0, as_stiff = 0;
+    REAL eig_prev = 1;
+    int iter = 0, accept_prev = 1;
+    REAL dtpropose = dt;
+    int rc = ORC_OK;
+    while (t < tf) {
+        if (iter >= c->max_steps) { rc = ORC_ERR_MAXITERS; break; }
+        /* loopheader! */
+        if (iter > 0) {
+            if (accept_prev) dt = dtpropose;
+            else if (c->n_forced == 0) {
+                REAL f = q11 / gamma, lim = (REAL)1 / qmin;
+                dt = dt / (lim < f ? lim : f);
+            }
+        }
+        iter++;
+        if (c->alg == ALG_AUTO_TSIT5 && c->n_forced == 0) {
+            REAL stiffness = R_ABS(eig_prev * dt / (REAL)TS_STABILITY_SIZE);
+            int stiff = stiffness > (REAL)(9.0 / 10.0);
+            as_count = stiff ? (as_count < 0 ? 1 : as_count + 1) : (as_count > 0 ? -1 : as_count - 1);
+            if (!as_stiff && as_count > 10) { dt = dt * (REAL)2; as_stiff = 1; st.nf += 1; }
+            else if (as_stiff && as_count < -3) { dt = dt / (REAL)2; as_stiff = 0; st.nf += 1; }
+        }
+        if (c->n_forced > 0) {
+            if (iter - 1 >= c->n_forced) { rc = ORC_ERR_ARG; break; }
+            dt = (REAL)c->forced_dt[iter - 1];
+        } else {
+            /* fix_dt_at_bounds!, modify_dt_for_tstops! */
+            if (dt > dtmax) dt = dtmax;
+            if (dt < (REAL)c->dtmin) dt = (REAL)c->dtmin;
+            REAL rem = tf - t;
+            if (rem < dt) dt = rem;
+        }
+        REAL EEst, eig;
+        tsit5_attempt(c, p, u, t, dt, w, &EEst, &eig, 0);
+        st.nf += 6;
+        if (EEst != EEst) { rc = ORC_ERR_NAN; log_push(h, dt, 0, EEst); break; }
+        /* loopfooter!: stepsize_controller! */
+        REAL q;
+        if (EEst == 0) q = (REAL)1 / qmax;
+        else {
+#ifdef ORC_F64
+            q11 = canon_pow(EEst, beta1);
+            q = q11 / canon_pow(qold, beta2);
+#else
+            q11 = canon_powf(EEst, beta1);
+            q = q11 / canon_powf(qold, beta2);
+#endif
+            REAL qq = q / gamma, hi = (REAL)1 / qmin, lo = (REAL)1 / qmax;
+            qq = hi < qq ? hi : qq;
+            q = lo > qq ? lo : qq;
+        }
+        int accept = c->n_forced > 0 ? c->forced_accept[iter - 1] : (EEst <= (REAL)1);
+        log_push(h, dt, accept, EEst);
+        if (c->alg == ALG_AUTO_TSIT5) eig_prev = eig;
+        if (accept) {
+            st.naccept++;
+            tape_push(h, t, dt, EEst, eig, u, w->k[1]);
+            if (q >= (REAL)1 && q <= (REAL)1) q = 1;   /* qsteady_min = qsteady_max = 1 */
+            qold = EEst > qoldinit ? EEst : qoldinit;
+            REAL dtnew = dt / q;
+            t = t + dt;
+            dtpropose = dtnew < dtmax ? dtnew : dtmax;
+            if (dtpropose < (REAL)c->dtmin) dtpropose = (REAL)c->dtmin;
+            memcpy(u, w->z[7], sizeof(REAL) * n);
+            REAL* tmp = w->k[1]; w->k[1] = w->k[7]; w->k[7] = tmp;   /* FSAL */
+            if (c->reg_kind != REG_NONE) h->saveval[h->n_saved++] = saved_value(c->reg_kind, EEst, eig, dt);
+            st.dt_last = dt;
+        } else {
+            st.nreject++;
+            if (dt <= (REAL)c->dtmin) { rc = ORC_ERR_DTMIN; break; }
+        }
+        accept_prev = accept;
+    }
+    memcpy(u_out, u, sizeof(REAL) * n);
+    st.t_final = t; st.n_saved = h->n_saved; st.retcode = rc;
+    h->st = st;
+    if (st_out) *st_out = st;
+    ws_free(w); free(u); free(scratch);
+    return rc;
+}
+
+int FN(get_saveval)(void* hv, REAL* out, int cap) {
+    orc_handle* h = (orc_handle*)hv;
+    int n = h->n_saved < cap ? h->n_saved : cap;
+    memcpy(out, h->saveval, sizeof(REAL) * n);
+    return h->n_saved;
+}
+int FN(get_log)(void* hv, double* dt, int* acc, double* eest, int cap) {
+    orc_handle* h = (orc_handle*)hv;
+    int n = h->log_n < cap ? h->log_n : cap;
+    if (dt) memcpy(dt, h->log_dt, sizeof(double) * n);
+    if (acc) memcpy(acc, h->log_acc, sizeof(int) * n);
+    if (eest) memcpy(eest, h->log_eest, sizeof(double) * n);
+    return h->log_n;
+}
+int FN(get_step)(void* hv, int j, double* t, double* dt, double* eest, double* eig) {
+    orc_handle* h = (orc_handle*)hv;
+    if (j < 0 || j >= h->nsteps) return ORC_ERR_ARG;
+    *t = h->tp_t[j]; *dt = h->tp_dt[j]; *eest = h->tp_eest[j]; *eig = h->tp_eig[j];
+    return ORC_OK;
+}
+
+/* field evaluation exported for unit tests */
+int FN(rhs)(const orc_config* cfg, const REAL* p, const REAL* z, double t, REAL* k, REAL* hout) {
+    rhs_eval(cfg, p, z, (REAL)t, k, hout);
+    return ORC_OK;
+}
+
+/* ------------------------------------------------------------------ */
+/* backward: discrete adjoint of the recorded accepted steps, frozen dt */
+/* (SURVEY.md section 3.2 / Appendix A.6 with detach_dt = all)          */
+/*   du_out   : dL/du(t_f)             (D x B)                          */
+/*   dsaveval : dL/dsaveval[i], i in [0,n_saved)                        */
+/*   dp (np), dx (D x B) are overwritten.                               */
+/*   dtbar_steps/tbar_steps (may be NULL, length naccept): per accepted  */
+/*   step j the partial derivatives dL/d(dt_j) (t_j held fixed) and      */
+/*   dL/d(t_j) (dt_j held fixed) -- the scalar adjoints the              */
+/*   all_but_first mode composes in oracle/orc.py.                       */
+/* ------------------------------------------------------------------ */
+int FN(backward)(void* hv, const REAL* du_out, const REAL* dsaveval, REAL* dp_out, REAL* dx_out, double* dtbar_steps,
+                 double* tbar_steps) {
+    orc_handle* h = (orc_handle*)hv;
+    const orc_config* c = &h->cfg;
+    const int D = c->D, B = c->B;
+    const size_t n = (size_t)D * B;
+    const long long cnt = (long long)D * B;
+    const REAL* p = h->p;
+#ifdef _OPENMP
+    if (c->nthreads > 0) omp_set_num_threads(c->nthreads);
+    int nthr = omp_get_max_threads();
+#else
+    int nthr = 1;
+#endif
+    REAL** dp_thr = (REAL**)malloc(sizeof(REAL*) * nthr);
+    for (int i = 0; i < nthr; ++i) dp_thr[i] = (REAL*)calloc(h->np, sizeof(REAL));
+    step_ws* w = ws_alloc(c);
+    REAL* ubar = (REAL*)malloc(sizeof(REAL) * n);      /* cotangent of u_new */
+    REAL* uprevbar = (REAL*)malloc(sizeof(REAL) * n);
+    REAL* kbar[8];
+    for (int i = 1; i <= 7; ++i) kbar[i] = (REAL*)calloc(n, sizeof(REAL));
+    REAL* zbar = (REAL*)malloc(sizeof(REAL) * n);
+    REAL* k7bar_in = (REAL*)calloc(n, sizeof(REAL));   /* from the next step's k1 */
+    REAL* h1 = (REAL*)malloc(sizeof(REAL) * (size_t)c->H * B);
+    memcpy(ubar, du_out, sizeof(REAL) * n);
+    const REAL atol = (REAL)c->abstol, rtol = (REAL)c->reltol;
+    const int has_reg = c->reg_kind != REG_NONE;
+
+    for (int s = h->nsteps - 1; s >= 0; --s) {
+        const REAL t = h->tp_t[s], dt = h->tp_dt[s];
+        const REAL* uprev = h->tp_uprev[s];
+        memcpy(w->k[1], h->tp_k1[s], sizeof(REAL) * n);
+        REAL EEst, eig;
+        tsit5_attempt(c, p, uprev, t, dt, w, &EEst, &eig, 1);
+        double dtbar = 0, tbar = 0;
+        /* cotangents entering this step */
+        for (int i = 1; i <= 6; ++i) memset(kbar[i], 0, sizeof(REAL) * n);
+        memcpy(kbar[7], k7bar_in, sizeof(REAL) * n);
+        memset(uprevbar, 0, sizeof(REAL) * n);
+        REAL* z6bar_extra = NULL;
+        /* saved value cotangent */
+        REAL sbar = has_reg ? dsaveval[s + 1] : (REAL)0;
+        REAL eestbar = 0, eigbar = 0;
+        if (sbar != 0) {
+            const REAL stab = (REAL)1 / (REAL)(float)TS_STABILITY_SIZE;
+            switch (c->reg_kind) {
+                case REG_ERR_DT: eestbar = sbar * dt; dtbar += (double)(sbar * EEst); break;
+                case REG_STIFF_DT_ABS: {
+                    REAL sg = (eig * dt) >= 0 ? (REAL)1 : (REAL)-1;
+                    eigbar = sbar * sg * dt; dtbar += (double)(sbar * sg * eig); break;
+                }
+                case REG_STIFF_SCALED: {
+                    REAL a = R_ABS(eig);
+                    if (!(a == 0 || a != a)) eigbar = sbar * stab * (eig >= 0 ? (REAL)1 : (REAL)-1);
+                    break;
+                }
+                case REG_ERR_PLUS_STIFF: {
+                    REAL e = EEst * dt;
+                    if (!(e == 0 || e != e)) { eestbar = sbar * dt; dtbar += (double)(sbar * EEst); }
+                    if (!(eig == 0 || eig != eig)) eigbar = sbar * ((REAL)0.1f * stab);
+                    break;
+                }
+            }
+        }
+        if (eestbar != 0 && EEst > 0) {
+            /* EEst = sqrt(sum(atmp^2)/N); atmp = utilde/den; den = atol + max(|uprev|,|u|)*rtol */
+            const REAL g = eestbar / ((REAL)cnt * EEst);
+            REAL bt[8];
+            for (int i = 1; i <= 7; ++i) bt[i] = (REAL)BT_[i];
+            double dtb = 0;
+#pragma omp parallel for schedule(static) reduction(+ : dtb)
+            for (size_t e = 0; e < n; ++e) {
+                REAL a0 = R_ABS(uprev[e]), a1 = R_ABS(w->z[7][e]);
+                REAL m = a0 > a1 ? a0 : a1;
+                REAL den = R_FMA(m, rtol, atol);
+                REAL ab = g * w->atmp[e];
+                REAL utb = ab / den;
+                REAL denb = -ab * w->atmp[e] / den;
+                REAL mb = denb * rtol;
+                if (a0 > a1) uprevbar[e] += mb * (uprev[e] >= 0 ? (REAL)1 : (REAL)-1);
+                else if (a1 > a0) ubar[e] += mb * (w->z[7][e] >= 0 ? (REAL)1 : (REAL)-1);
+                else { uprevbar[e] += (REAL)0.5 * mb * (uprev[e] > 0 ? 1 : (uprev[e] < 0 ? -1 : 0));
+                       ubar[e] += (REAL)0.5 * mb * (w->z[7][e] > 0 ? 1 : (w->z[7][e] < 0 ? -1 : 0)); }
+                REAL ssum = 0;
+                for (int i = 1; i <= 7; ++i) { kbar[i][e] += dt * bt[i] * utb; ssum += bt[i] * w->k[i][e]; }
+                dtb += (double)(utb * ssum);
+            }
+            dtbar += dtb;
+        }
+        if (eigbar != 0 && c->alg == ALG_AUTO_TSIT5) {
+            /* eig = n1/n2; n1 = rms(k7-k6); n2 = rms(u - g6) */
+            double s1 = 0, s2 = 0;
+            for (size_t e = 0; e < n; ++e) { double a = (double)w->k[7][e] - w->k[6][e], b = (double)w->z[7][e] - w->z[6][e]; s1 += a * a; s2 += b * b; }
+            REAL n1 = (REAL)sqrt(s1 / (double)cnt), n2 = (REAL)sqrt(s2 / (double)cnt);
+            REAL n1b = eigbar / n2, n2b = -eigbar * n1 / (n2 * n2);
+            z6bar_extra = (REAL*)calloc(n, sizeof(REAL));
+            for (size_t e = 0; e < n; ++e) {
+                REAL a = w->k[7][e] - w->k[6][e], b = w->z[7][e] - w->z[6][e];
+                REAL ga = n1 > 0 ? n1b * a / ((REAL)cnt * n1) : (REAL)0;
+                REAL gb = n2 > 0 ? n2b * b / ((REAL)cnt * n2) : (REAL)0;
+                kbar[7][e] += ga; kbar[6][e] -= ga;
+                ubar[e] += gb; z6bar_extra[e] -= gb;
+            }
+        }
+        /* stages in reverse */
+        for (int i = 7; i >= 2; --i) {
+            REAL tb_stage = 0;
+            rhs_vjp(c, p, w->z[i], stage_time(t, dt, i), w->h[i], w->k[i], kbar[i], zbar, dp_thr, &tb_stage);
+            tbar += (double)tb_stage;
+            dtbar += (double)C_[i] * (double)tb_stage;
+            REAL* zb = zbar;
+            if (i == 7) {
+                /* z7 = u_new: total cotangent ubar + zbar */
+#pragma omp parallel for schedule(static)
+                for (size_t e = 0; e < n; ++e) ubar[e] += zbar[e];
+                zb = ubar;
+            } else if (i == 6 && z6bar_extra) {
+                for (size_t e = 0; e < n; ++e) zbar[e] += z6bar_extra[e];
+            }
+            double dtb = 0;
+#pragma omp parallel for schedule(static) reduction(+ : dtb)
+            for (size_t e = 0; e < n; ++e) {
+                REAL g = zb[e];
+                REAL ssum = 0;
+                for (int j = 1; j < i; ++j) { kbar[j][e] += dt * (REAL)A_[i][j] * g; ssum += (REAL)A_[i][j] * w->k[j][e]; }
+                uprevbar[e] += g;
+                dtb += (double)(g * ssum);
+            }
+            dtbar += dtb;
+        }
+        if (z6bar_extra) { free(z6bar_extra); }
+        /* hand over to the previous step: u_new(prev) = uprev, k7(prev) = k1 */
+        memcpy(ubar, uprevbar, sizeof(REAL) * n);
+        memcpy(k7bar_in, kbar[1], sizeof(REAL) * n);
+        if (dtbar_steps) dtbar_steps[s] = dtbar;
+        if (tbar_steps) tbar_steps[s] = tbar;
+    }
+    /* initial fsalfirst = f(u0,t0): VJP with k7bar_in */
+    rhs_eval(c, p, h->u0, (REAL)c->t0, w->k[1], h1);
+    rhs_vjp(c, p, h->u0, (REAL)c->t0, h1, w->k[1], k7bar_in, zbar, dp_thr, NULL);
+    for (size_t e = 0; e < n; ++e) dx_out[e] = ubar[e] + zbar[e];
+    for (size_t q = 0; q < h->np; ++q) { double a = 0; for (int i = 0; i < nthr; ++i) a += (double)dp_thr[i][q]; dp_out[q] = (REAL)a; }
+    for (int i = 0; i < nthr; ++i) free(dp_thr[i]);
+    free(dp_thr); ws_free(w); free(ubar); free(uprevbar);
+    for (int i = 1; i <= 7; ++i) free(kbar[i]);
+    free(zbar); free(k7bar_in); free(h1);
+    return ORC_OK;
+}
+
+int FN(sizeof_real)(void) { return (int)sizeof(REAL); }
