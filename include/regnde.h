@@ -1,0 +1,163 @@
+/*
+ * regnde.h -- C ABI of libregnde.so: the B200-native replacement for the body of
+ * the reference's neural-ODE layer call and everything below it.
+ *
+ * The reference has no FFI; its hot path sits behind Julia callable structs.
+ * Each entry point below names the reference interface it replaces:
+ *
+ *   rnde_create        TrackedNeuralODE(model, tspan, time_dep, regularize, solver...; kwargs...)
+ *                      src/models/neural_ode.jl:10-32   (constructor: shapes, solver args, kwargs)
+ *   rnde_forward       (n::TrackedNeuralODE{R,false})(x, p; func, tspan)  ->  (res, nfe, sv)
+ *                      src/models/neural_ode.jl:48-77 (R=false), :110-144 (R=true);
+ *                      solve(prob, Tsit5()|AutoTsit5(Tsit5()); callback=SavingCallback(func, sv), ...) :131-137
+ *   rnde_backward      Tracker.gradient(...) through that call
+ *                      experiments/mnist_node.jl:229-232, test/test_node.jl:25,47-57,79-89
+ *   rnde_head_*        ClassifierNODE post-net Dense(784,10) + logitcrossentropy
+ *                      src/models/supervised_classification.jl:44-45, experiments/mnist_node.jl:135
+ *   rnde_stats         sol.destats.nf (neural_ode.jl:142) and length(sv.saveval)
+ *
+ * Conventions
+ *   - All arrays are Float32, COLUMN-MAJOR features x batch (a Julia CuArray /
+ *     Array passes its pointer unchanged); `p` is the Flux.destructure vector
+ *     of the 2-layer time-concatenated field: W1 (H x (D+1)), b1 (H),
+ *     W2 (D x (H+1)), b2 (D)   [src/models/basic.jl:16-28, experiments/mnist_node.jl:41-54].
+ *   - *_dev pointers are device pointers owned by the caller; `stream` is a
+ *     cudaStream_t passed as void*.  The *_host entry points take host pointers
+ *     and do the H2D/D2H copies themselves (the end-to-end path).
+ *   - Every function returns an rnde_status; nothing throws across the ABI.
+ *     Solver failures (maxiters, dt<=dtmin, NaN) are reported in the return
+ *     code AND in rnde_stats.retcode, mirroring upstream retcodes.
+ *   - A handle is not thread-safe; distinct handles are independent.
+ *   - There is NO CPU fallback: with no CUDA device every call returns
+ *     RNDE_ERR_CUDA.
+ */
+#ifndef REGNDE_H
+#define REGNDE_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RNDE_VERSION 100
+
+typedef enum {
+    RNDE_OK = 0,
+    RNDE_ERR_MAXITERS = 1,     /* retcode :MaxIters   */
+    RNDE_ERR_DTMIN = 2,        /* retcode :DtLessThanMin */
+    RNDE_ERR_NAN = 3,          /* retcode :DtNaN / unstable */
+    RNDE_ERR_ARG = 4,
+    RNDE_ERR_UNSUPPORTED = 5,  /* shape does not fit any kernel variant */
+    RNDE_ERR_CUDA = 6,
+    RNDE_ERR_TAPE_FULL = 7,    /* more accepted steps than tape_capacity */
+    RNDE_ERR_STATE = 8         /* backward without a taped forward */
+} rnde_status;
+
+enum { RNDE_ACT_IDENTITY = 0, RNDE_ACT_TANH = 1 };
+/* solver_args... of the constructor: Tsit5() or AutoTsit5(Tsit5()) */
+enum { RNDE_ALG_TSIT5 = 0, RNDE_ALG_AUTO_TSIT5 = 1 };
+/* the `func` closures the reference passes to SavingCallback:
+ *   ERR_DT         integrator.EEst * integrator.dt          neural_ode.jl:116, mnist_node.jl:67
+ *   STIFF_DT_ABS   abs(integrator.eigen_est*integrator.dt)  test/test_node.jl:75
+ *   STIFF_SCALED   stability_size*|eigen_est| (0/NaN guard)  mnist_node.jl:76-79
+ *   ERR_PLUS_STIFF EEst*dt + 0.1*stability_size*eigen_est   mnist_node.jl:88-97 */
+enum { RNDE_REG_NONE = 0, RNDE_REG_ERR_DT = 1, RNDE_REG_STIFF_DT_ABS = 2, RNDE_REG_STIFF_SCALED = 3, RNDE_REG_ERR_PLUS_STIFF = 4 };
+enum { RNDE_KERNEL_AUTO = 0, RNDE_KERNEL_CTA = 1, RNDE_KERNEL_STREAM = 2, RNDE_KERNEL_CLUSTER = 3 };
+enum { RNDE_DIST_SINGLE = 0, RNDE_DIST_EXACT = 1, RNDE_DIST_INDEPENDENT = 2 };
+
+typedef struct rnde_config {
+    int32_t struct_bytes;     /* sizeof(rnde_config), for versioning */
+    int32_t state_dim;        /* D */
+    int32_t hidden_dim;       /* H */
+    int32_t batch;            /* B: columns held by this handle (this rank) */
+    int32_t act_hidden;       /* RNDE_ACT_* of layer 1 */
+    int32_t act_out;          /* RNDE_ACT_* of layer 2 (identity: TDChain test; tanh: MLPDynamics) */
+    int32_t time_dep;         /* time_dep::Bool of the constructor (neural_ode.jl:8) */
+    int32_t kblock;           /* canonical K-blocking of layer 1; 0 = library default */
+    int32_t alg;              /* RNDE_ALG_* */
+    int32_t reg_kind;         /* RNDE_REG_* ; NONE == regularize=false */
+    int32_t max_steps;        /* maxiters; 0 = 1000000 */
+    int32_t tape_capacity;    /* accepted steps the backward tape can hold; 0 = 256 */
+    int32_t need_backward;    /* record the tape during forward */
+    int32_t kernel_variant;   /* RNDE_KERNEL_* */
+    int32_t dist_mode;        /* RNDE_DIST_* */
+    int32_t rank, nranks;     /* data-parallel position (columns sharded by rank) */
+    float t0, t1;             /* tspan */
+    float abstol, reltol;     /* solver kwargs */
+    float dtmin;              /* 0 = 1e-10 */
+    int64_t global_batch;     /* columns over all ranks (EXACT mode); 0 = batch */
+} rnde_config;
+
+typedef struct rnde_stats {
+    int32_t nf;        /* sol.destats.nf */
+    int32_t naccept;
+    int32_t nreject;
+    int32_t n_saved;   /* length(sv.saveval) = naccept + 1 when regularize */
+    int32_t retcode;   /* rnde_status of the solve */
+    float t_final;
+    float dt_last;
+    float dt_init;
+} rnde_stats;
+
+typedef struct rnde_handle rnde_handle;
+
+int rnde_version(void);
+const char* rnde_status_string(int status);
+/* device query used by the host layer to fail loudly: number of visible CUDA devices */
+int rnde_device_count(void);
+
+int rnde_create(const rnde_config* cfg, rnde_handle** out);
+void rnde_destroy(rnde_handle* h);
+const char* rnde_last_error(const rnde_handle* h);
+/* number of parameters of the field (length of p) and default kblock for (D, variant) */
+int64_t rnde_num_params(const rnde_config* cfg);
+int rnde_default_kblock(const rnde_config* cfg);
+/* which kernel variant the handle resolved to (RNDE_KERNEL_*) and how many of
+ * this library's kernels it has launched so far (bench.py's gpu_launches) */
+int rnde_kernel_variant(const rnde_handle* h);
+int64_t rnde_launch_count(const rnde_handle* h);
+
+/* tspan override per call (the functor's `tspan` keyword, neural_ode.jl:53,58) */
+int rnde_set_tspan(rnde_handle* h, float t0, float t1);
+
+/* Forward solve.  x_dev (D x B), p_dev (num_params), u_out_dev (D x B),
+ * saveval_dev (>= tape_capacity+1 floats, may be NULL when reg_kind==NONE).
+ * stats_host may be NULL (fully asynchronous); otherwise the stream is
+ * synchronised and the stats are filled in. */
+int rnde_forward(rnde_handle* h, const float* x_dev, const float* p_dev, float* u_out_dev, float* saveval_dev,
+                 rnde_stats* stats_host, void* stream);
+
+/* Backward (discrete adjoint of the recorded accepted steps).
+ * du_dev: dL/d res (D x B); dsaveval_dev: dL/d sv.saveval[i] (n_saved floats, may be NULL);
+ * dp_dev (num_params) and dx_dev (D x B, may be NULL) are OVERWRITTEN. */
+int rnde_backward(rnde_handle* h, const float* du_dev, const float* dsaveval_dev, float* dp_dev, float* dx_dev, void* stream);
+
+/* Host-buffer variants (end-to-end path: copies inside the call). */
+int rnde_forward_host(rnde_handle* h, const float* x_host, const float* p_host, float* u_out_host, float* saveval_host,
+                      rnde_stats* stats_host);
+int rnde_backward_host(rnde_handle* h, const float* du_host, const float* dsaveval_host, float* dp_host, float* dx_host);
+
+/* Classifier head of ClassifierNODE (supervised_classification.jl:44-45) with the
+ * experiment's loss (mnist_node.jl:135): logits = W3*u + b3 (C x B),
+ * loss = mean_j logitcrossentropy(logits[:,j], y[:,j]).  p3 = [W3 (C x D) col-major; b3 (C)].
+ * Writes loss (1 float), logits (C x B, may be NULL), du = dloss/du (D x B), dp3 (C*D + C). */
+int rnde_head_loss_grad(rnde_handle* h, const float* u_dev, const float* p3_dev, const float* y_onehot_dev, int32_t n_classes,
+                        float loss_scale, float* loss_dev, float* logits_dev, float* du_dev, float* dp3_dev, void* stream);
+
+/* update_parameters!(ps, gs, opt) with opt = Optimiser(InvDecay(gamma), Momentum(eta, rho))
+ * (src/utils.jl:149-156, experiments/mnist_node.jl:130), in place on raw arrays:
+ *   delta = g * inv_decay_scale   [InvDecay: 1/(1 + gamma*n), n = 1-based update count]
+ *   v = rho*v - eta*delta ; p = p + v                        [Flux 0.11.6 Momentum]
+ * `h` may be NULL (no handle state is used). */
+int rnde_opt_update(rnde_handle* h, float* p_dev, const float* g_dev, float* v_dev, int64_t n, float inv_decay_scale, float eta, float rho,
+                    void* stream);
+
+/* introspection for tests: per accepted step (t, dt, EEst, eigen_est), host arrays of length naccept */
+int rnde_get_steps(rnde_handle* h, float* t, float* dt, float* eest, float* eig, int32_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REGNDE_H */

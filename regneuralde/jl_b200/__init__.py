@@ -1,0 +1,18 @@
+"""regneuralde.jl_b200 -- B200-native hot path of avik-pal/RegNeuralDE.jl.
+
+Batched adaptive Tsit5 integration of a small neural-network vector field with the
+solver-heuristic regularisers and the discrete-adjoint backward pass, in hand-written
+sm_100a CUDA kernels behind a C ABI (include/regnde.h, libregnde.so).  This package is
+the host-side mirror of the reference's Julia surface for that path.  No CPU fallback.
+"""
+from . import _lib
+from ._lib import RndeError, build, lib
+from .node import (AutoTsit5, Dense, ERROR_ESTIMATE, ERROR_PLUS_STIFFNESS, MLPDynamics, STIFFNESS_ESTIMATE, STIFFNESS_SCALED,
+                   SavedValues, SaveFunc, TDChain, TrackedNeuralODE, Tsit5, colmajor, from_colmajor, track, untrack)
+from .classifier import ClassifierNODE, Optimiser, update_parameters_
+
+__all__ = [
+    "RndeError", "build", "lib", "AutoTsit5", "Tsit5", "Dense", "TDChain", "MLPDynamics", "TrackedNeuralODE", "SavedValues", "SaveFunc",
+    "ERROR_ESTIMATE", "STIFFNESS_ESTIMATE", "STIFFNESS_SCALED", "ERROR_PLUS_STIFFNESS", "ClassifierNODE", "Optimiser",
+    "update_parameters_", "track", "untrack", "colmajor", "from_colmajor",
+]

@@ -1,0 +1,141 @@
+"""ctypes binding of libregnde.so (include/regnde.h) + the in-tree nvcc build.
+
+The product path has NO fallback: if the shared library is missing, or no CUDA
+device is visible, every entry point raises.  Nothing in this package imports
+``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+_ROOT = _PKG.parent.parent
+_CSRC = _PKG / "csrc"
+_INCLUDE = _ROOT / "include"
+LIB_PATH = _PKG / "libregnde.so"
+
+NVCC_FLAGS = [
+    "-shared", "-Xcompiler", "-fPIC", "-std=c++17", "-O3",
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    "-fmad=false",            # canonical arithmetic: no implicit contraction (include/regnde_canon.h)
+]
+
+# status codes / enums (mirror include/regnde.h)
+OK, ERR_MAXITERS, ERR_DTMIN, ERR_NAN, ERR_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_TAPE_FULL, ERR_STATE = range(9)
+ACT_IDENTITY, ACT_TANH = 0, 1
+ALG_TSIT5, ALG_AUTO_TSIT5 = 0, 1
+REG_NONE, REG_ERR_DT, REG_STIFF_DT_ABS, REG_STIFF_SCALED, REG_ERR_PLUS_STIFF = range(5)
+KERNEL_AUTO, KERNEL_CTA, KERNEL_STREAM, KERNEL_CLUSTER = range(4)
+DIST_SINGLE, DIST_EXACT, DIST_INDEPENDENT = range(3)
+
+EXPORTS = [
+    "rnde_version", "rnde_status_string", "rnde_device_count", "rnde_create", "rnde_destroy", "rnde_last_error",
+    "rnde_num_params", "rnde_default_kblock", "rnde_kernel_variant", "rnde_launch_count", "rnde_set_tspan",
+    "rnde_forward", "rnde_backward", "rnde_forward_host", "rnde_backward_host", "rnde_head_loss_grad", "rnde_get_steps",
+    "rnde_opt_update",
+]
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("struct_bytes", C.c_int32), ("state_dim", C.c_int32), ("hidden_dim", C.c_int32), ("batch", C.c_int32),
+        ("act_hidden", C.c_int32), ("act_out", C.c_int32), ("time_dep", C.c_int32), ("kblock", C.c_int32),
+        ("alg", C.c_int32), ("reg_kind", C.c_int32), ("max_steps", C.c_int32), ("tape_capacity", C.c_int32),
+        ("need_backward", C.c_int32), ("kernel_variant", C.c_int32), ("dist_mode", C.c_int32),
+        ("rank", C.c_int32), ("nranks", C.c_int32),
+        ("t0", C.c_float), ("t1", C.c_float), ("abstol", C.c_float), ("reltol", C.c_float), ("dtmin", C.c_float),
+        ("global_batch", C.c_int64),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("nf", C.c_int32), ("naccept", C.c_int32), ("nreject", C.c_int32), ("n_saved", C.c_int32), ("retcode", C.c_int32),
+        ("t_final", C.c_float), ("dt_last", C.c_float), ("dt_init", C.c_float),
+    ]
+
+
+def sources() -> list[Path]:
+    return [_CSRC / "regnde.cu"]
+
+
+def _stale() -> bool:
+    if not LIB_PATH.exists():
+        return True
+    t = LIB_PATH.stat().st_mtime
+    deps = list(_CSRC.glob("*.cu")) + list(_CSRC.glob("*.cuh")) + list(_INCLUDE.glob("*.h"))
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile csrc/ for sm_100a with nvcc into regneuralde/jl_b200/libregnde.so (in-tree)."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not Path(nvcc).exists():
+        if LIB_PATH.exists():
+            return LIB_PATH          # GPU box without nvcc on PATH: use the prebuilt library that travelled
+        raise RuntimeError("nvcc not found and no prebuilt libregnde.so")
+    cmd = [nvcc, *NVCC_FLAGS, f"-I{_INCLUDE}", "-o", str(LIB_PATH)] + [str(s) for s in sources()]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libregnde.so (building it first if nvcc is available and it is stale)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        build()
+    L = C.CDLL(str(LIB_PATH))
+    vp, fp, ip = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)
+    L.rnde_version.restype = C.c_int
+    L.rnde_status_string.restype = C.c_char_p
+    L.rnde_status_string.argtypes = [C.c_int]
+    L.rnde_device_count.restype = C.c_int
+    L.rnde_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.rnde_destroy.argtypes = [vp]
+    L.rnde_destroy.restype = None
+    L.rnde_last_error.argtypes = [vp]
+    L.rnde_last_error.restype = C.c_char_p
+    L.rnde_num_params.argtypes = [C.POINTER(Config)]
+    L.rnde_num_params.restype = C.c_int64
+    L.rnde_default_kblock.argtypes = [C.POINTER(Config)]
+    L.rnde_kernel_variant.argtypes = [vp]
+    L.rnde_launch_count.argtypes = [vp]
+    L.rnde_launch_count.restype = C.c_int64
+    L.rnde_set_tspan.argtypes = [vp, C.c_float, C.c_float]
+    L.rnde_forward.argtypes = [vp, vp, vp, vp, vp, C.POINTER(Stats), vp]
+    L.rnde_backward.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.rnde_forward_host.argtypes = [vp, vp, vp, vp, vp, C.POINTER(Stats)]
+    L.rnde_backward_host.argtypes = [vp, vp, vp, vp, vp]
+    L.rnde_head_loss_grad.argtypes = [vp, vp, vp, vp, C.c_int32, C.c_float, vp, vp, vp, vp, vp]
+    L.rnde_get_steps.argtypes = [vp, vp, vp, vp, vp, C.c_int32]
+    L.rnde_opt_update.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, vp]
+    _lib = L
+    return L
+
+
+class RndeError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"regnde error {code} ({lib().rnde_status_string(code).decode()}): {msg}")
+        self.code = code
+
+
+def require_device() -> None:
+    if lib().rnde_device_count() <= 0:
+        raise RuntimeError("regneuralde.jl_b200 needs a CUDA device (sm_100a); there is no CPU fallback")

@@ -1,0 +1,338 @@
+// bwd_kernel.cuh -- persistent reverse sweep over the recorded accepted steps.
+//
+// This is the discrete adjoint of the exact step sequence the forward kernel took
+// (what Tracker.gradient through solve(...; sensealg=SensitivityADPassThrough()) computes:
+// /root/reference/src/models/neural_ode.jl:134, experiments/mnist_node.jl:229-232,
+// SURVEY.md 3.2 / Appendix A.6 with the step sizes frozen).  Cotangents enter from the
+// final state and from every saved value EEst_j*dt_j / eigen_est_j (through norm ->
+// residual -> utilde, u0, u1).  The same cluster decomposition as the forward kernel is
+// used: each CTA owns R state rows of NP columns; per stage it needs one H x NP exchange
+// (W2^T delta2 is a split-K over the CTA's rows).  The per-stage deltas are written back
+// over the tape so that the parameter gradients become two large batched contractions
+// (wgrad_kernel.cuh) instead of rank-NP updates inside this latency-bound sweep.
+#pragma once
+#include "common.cuh"
+
+namespace rnde {
+
+struct BwdLayout {
+    int HP, RP;
+    int oW2T, oW1T, oUb, oUpb, oKb, oPart, oD1, total;
+};
+
+__host__ __device__ inline BwdLayout make_bwd_layout(int G, int NP, bool WS, int D, int H, int R, int HS) {
+    BwdLayout L;
+    L.HP = round_up(H, 4);
+    L.RP = round_up(R, 4);
+    int o = 0;
+    L.oW2T = o; o += WS ? R * L.HP : 0;     // [k = local row][m = hidden]
+    L.oW1T = o; o += WS ? H * L.RP : 0;     // [k = hidden][m = local row]
+    L.oUb = o; o += L.RP * NP;
+    L.oUpb = o; o += L.RP * NP;
+    L.oKb = o; o += 7 * L.RP * NP;
+    L.oPart = o; o += G * HS * NP;
+    L.oD1 = o; o += L.HP * NP;
+    L.total = o;
+    return L;
+}
+
+template <int G, int NP, int TM, bool WS, int NT>
+__global__ void __launch_bounds__(NT, 1) bwd_kernel(const KParams P) {
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = NT / 32;
+    constexpr int LN = NP / 4;
+    constexpr int LM = 32 / LN;
+    constexpr int TMW = LM * TM;
+    const int rank = (G > 1) ? (int)cluster_ctarank() : 0;
+    const int q = blockIdx.x / G;
+    const int D = P.D, H = P.H, R = P.R, HS = P.HS, td = P.td;
+    const int r0 = rank * R;
+    const int Rloc = max(0, min(R, D - r0));
+    const int c0 = q * NP;
+    const int Nloc = max(0, min(NP, P.B - c0));
+    const int HSloc = max(0, min(HS, H - rank * HS));
+    const BwdLayout L = make_bwd_layout(G, NP, WS, D, H, R, HS);
+    const int HP = L.HP, RP = L.RP;
+    float* sW2T = smem + L.oW2T; float* sW1T = smem + L.oW1T;
+    float* sUb = smem + L.oUb; float* sUpb = smem + L.oUpb;
+    float* sPart = smem + L.oPart; float* sD1 = smem + L.oD1;
+    float* const sKb = smem + L.oKb;
+    const int kstride = RP * NP;
+    int flipK = 0;
+    auto Kb = [&](const int j) -> float* {
+        int slot = j - 1;
+        if (j == 1) slot = flipK ? 6 : 0;
+        if (j == 7) slot = flipK ? 0 : 6;
+        return sKb + slot * kstride;
+    };
+    const float* gW1 = P.p;
+    const float* gW2 = gW1 + (size_t)H * (D + td) + H;
+    const size_t tileD = (size_t)D * NP, tileH = (size_t)H * NP;
+    auto tile_off_D = [&](int rec) -> size_t { return ((size_t)rec * P.Q + q) * tileD + (size_t)r0 * NP; };
+    auto tile_off_H = [&](int rec) -> size_t { return ((size_t)rec * P.Q + q) * tileH; };
+
+    if constexpr (WS) {
+        for (int e = tid; e < R * HP; e += NT) {       // W2T[k][m] = W2[r0+k, m]
+            const int k = e / HP, m = e - k * HP;
+            sW2T[e] = (k < Rloc && m < H) ? __ldg(gW2 + (size_t)D * m + r0 + k) : 0.f;
+        }
+        for (int e = tid; e < H * RP; e += NT) {       // W1T[k][m] = W1[k, r0+m]
+            const int k = e / RP, m = e - k * RP;
+            sW1T[e] = (m < Rloc) ? __ldg(gW1 + (size_t)H * (r0 + m) + k) : 0.f;
+        }
+    }
+    for (int e = tid; e < RP * NP; e += NT) {
+        const int n = e / RP, m = e - n * RP;
+        sUb[m * NP + n] = (m < Rloc && n < Nloc) ? __ldg(P.du + (size_t)D * (c0 + n) + r0 + m) : 0.f;
+        sUpb[m * NP + n] = 0.f;
+    }
+    for (int e = tid; e < 7 * kstride; e += NT) sKb[e] = 0.f;
+    __syncthreads();
+    if constexpr (G > 1) cluster_sync_all();
+
+    const int ln = lane % LN, lm = lane / LN, n0 = ln * 4;
+
+    // VJP of one field evaluation (record `rec`).  On entry Kb(i) holds kbar_i; it is
+    // turned into delta2 in place.  `epi(m, n0, zbar[4])` consumes zbar = W1^T delta1.
+    auto vjp = [&](float* sKbar, const int rec, auto epi) {
+        const size_t offD = tile_off_D(rec), offH = tile_off_H(rec);
+        for (int e = tid; e < Rloc * NP; e += NT) {
+            const float kb = sKbar[e];
+            float d2 = kb;
+            if (P.act2 == RNDE_ACT_TANH) { const float kv = __ldcg(P.tapeK + offD + e); d2 = kb * (1.f - kv * kv); }
+            sKbar[e] = d2;
+            P.tapeK[offD + e] = d2;       // delta2 replaces k in the tape (consumed by wgrad)
+        }
+        __syncthreads();
+        // phase A': hbar partial = W2[rows, :H]^T delta2   (split-K over this CTA's rows)
+        for (int mt = warp; mt * TMW < H; mt += NW) {
+            const int m0 = mt * TMW + lm * TM;
+            if (m0 < H) {
+                float acc[TM][4];
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+                for (int k = 0; k < Rloc; ++k) {
+                    float w[TM];
+                    if constexpr (TM == 4) {
+                        if constexpr (WS) {
+                            const float4 w4 = *reinterpret_cast<const float4*>(sW2T + k * HP + m0);
+                            w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[3] = w4.w;
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < TM; ++i) w[i] = (m0 + i < H) ? __ldg(gW2 + (size_t)D * (m0 + i) + r0 + k) : 0.f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < TM; ++i) {
+                            if constexpr (WS) w[i] = sW2T[k * HP + min(m0 + i, HP - 1)];
+                            else w[i] = (m0 + i < H) ? __ldg(gW2 + (size_t)D * (m0 + i) + r0 + k) : 0.f;
+                        }
+                    }
+                    const float4 x4 = *reinterpret_cast<const float4*>(sKbar + k * NP + n0);
+                    const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+                    for (int i = 0; i < TM; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[i][j] = rn_fmaf(w[i], xv[j], acc[i][j]);
+                }
+#pragma unroll
+                for (int i = 0; i < TM; ++i) {
+                    const int m = m0 + i;
+                    if (m < H) {
+                        const float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+                        if constexpr (G > 1) {
+                            const int d = m / HS, ml = m - d * HS;
+                            st_cluster_f4(mapa_u32(smem_u32(sPart + (rank * HS + ml) * NP + n0), d), v);
+                        } else {
+                            *reinterpret_cast<float4*>(sPart + m * NP + n0) = v;
+                        }
+                    }
+                }
+            }
+        }
+        group_sync<G>();
+        // phase B': reduce over the cluster, delta1 = hbar * act1'(h), broadcast
+        for (int e = tid; e < HSloc * NP; e += NT) {
+            const int ml = e / NP, n = e - ml * NP;
+            const int m = rank * HS + ml;
+            float s = sPart[ml * NP + n];
+#pragma unroll
+            for (int c = 1; c < G; ++c) s = s + sPart[(c * HS + ml) * NP + n];
+            float d1 = s;
+            if (P.act1 == RNDE_ACT_TANH) { const float hv = __ldcg(P.tapeH + offH + (size_t)m * NP + n); d1 = s * (1.f - hv * hv); }
+            if constexpr (G > 1) {
+                const uint32_t a = smem_u32(sD1 + m * NP + n);
+#pragma unroll
+                for (int d = 0; d < G; ++d) st_cluster_f32(mapa_u32(a, d), d1);
+            } else {
+                sD1[m * NP + n] = d1;
+            }
+            P.tapeD1[offH + (size_t)m * NP + n] = d1;
+        }
+        group_sync<G>();
+        // phase C': zbar = W1[:, rows]^T delta1  for this CTA's rows
+        for (int mt = warp; mt * TMW < Rloc; mt += NW) {
+            const int m0 = mt * TMW + lm * TM;
+            if (m0 < Rloc) {
+                float acc[TM][4];
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+                for (int k = 0; k < H; ++k) {
+                    float w[TM];
+                    if constexpr (TM == 4) {
+                        if constexpr (WS) {
+                            const float4 w4 = *reinterpret_cast<const float4*>(sW1T + k * RP + m0);
+                            w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[3] = w4.w;
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < TM; ++i) w[i] = (m0 + i < Rloc) ? __ldg(gW1 + (size_t)H * (r0 + m0 + i) + k) : 0.f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < TM; ++i) {
+                            if constexpr (WS) w[i] = sW1T[k * RP + min(m0 + i, RP - 1)];
+                            else w[i] = (m0 + i < Rloc) ? __ldg(gW1 + (size_t)H * (r0 + m0 + i) + k) : 0.f;
+                        }
+                    }
+                    const float4 x4 = *reinterpret_cast<const float4*>(sD1 + k * NP + n0);
+                    const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+                    for (int i = 0; i < TM; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[i][j] = rn_fmaf(w[i], xv[j], acc[i][j]);
+                }
+#pragma unroll
+                for (int i = 0; i < TM; ++i) {
+                    const int m = m0 + i;
+                    if (m < Rloc) epi(m, n0, acc[i]);
+                }
+            }
+        }
+        __syncthreads();
+    };
+
+    const float atol = P.abstol, rtol = P.reltol;
+    const float cntf = (float)P.norm_count;
+    const float stab = rn_divf(1.0f, (float)TS_STABILITY_SIZE);
+
+    for (int s = P.nsteps - 1; s >= 0; --s) {
+        const StepRec sr = P.steps[s];
+        const float dt = sr.dt, EEst = sr.eest, eig = sr.eig, n1 = sr.n1, n2 = sr.n2;
+        // cotangents of this step's saved value
+        const float sbar = P.dsaveval ? __ldg(P.dsaveval + s + 1) : 0.f;
+        float eestbar = 0.f, eigbar = 0.f;
+        if (sbar != 0.f) {
+            switch (P.reg_kind) {
+                case RNDE_REG_ERR_DT: eestbar = sbar * dt; break;
+                case RNDE_REG_STIFF_DT_ABS: eigbar = sbar * ((eig * dt) >= 0.f ? 1.f : -1.f) * dt; break;
+                case RNDE_REG_STIFF_SCALED: { const float a = fabsf(eig); if (!(a == 0.f || a != a)) eigbar = sbar * stab * (eig >= 0.f ? 1.f : -1.f); break; }
+                case RNDE_REG_ERR_PLUS_STIFF: {
+                    const float e = EEst * dt;
+                    if (!(e == 0.f || e != e)) eestbar = sbar * dt;
+                    if (!(eig == 0.f || eig != eig)) eigbar = sbar * (0.1f * stab);
+                    break;
+                }
+                default: break;
+            }
+        }
+        if (P.alg != RNDE_ALG_AUTO_TSIT5) eigbar = 0.f;
+        const bool use_eest = (eestbar != 0.f) && (EEst > 0.f);
+        const bool use_eig = (eigbar != 0.f) && (n1 > 0.f) && (n2 > 0.f);
+        const float gE = use_eest ? eestbar / (cntf * EEst) : 0.f;
+        const float n1b = use_eig ? eigbar / n2 : 0.f;
+        const float n2b = use_eig ? -eigbar * n1 / (n2 * n2) : 0.f;
+        const float gA = use_eig ? n1b / (cntf * n1) : 0.f;    // multiplies (k7-k6)
+        const float gB = use_eig ? n2b / (cntf * n2) : 0.f;    // multiplies (u-g6)
+        const int recU0 = 6 * s, recU1 = 6 * s + 6, recG6 = 6 * s + 5;
+
+        // reset the per-step cotangents (Kb(7) carries k7bar from the following step)
+        for (int e = tid; e < Rloc * NP; e += NT) {
+            sUpb[e] = 0.f;
+#pragma unroll
+            for (int j = 1; j <= 6; ++j) Kb(j)[e] = 0.f;
+        }
+        __syncthreads();
+        if (use_eest || use_eig) {
+            for (int e = tid; e < Rloc * NP; e += NT) {
+                const int n = e % NP;
+                if (n >= Nloc) continue;
+                const float up = __ldcg(P.tapeZ + tile_off_D(recU0) + e);
+                const float un = __ldcg(P.tapeZ + tile_off_D(recU1) + e);
+                float kv[8];
+#pragma unroll
+                for (int j = 1; j <= 7; ++j) kv[j] = __ldcg(P.tapeK + tile_off_D(6 * s + j - 1) + e);
+                if (use_eest) {
+                    float ssum = ts_bt(1) * kv[1];
+#pragma unroll
+                    for (int j = 2; j <= 7; ++j) ssum = rn_fmaf(ts_bt(j), kv[j], ssum);
+                    const float ut = dt * ssum;
+                    const float a0 = fabsf(up), a1 = fabsf(un);
+                    const float mx = a0 > a1 ? a0 : a1;
+                    const float den = rn_fmaf(mx, rtol, atol);
+                    const float at = ut / den;
+                    const float ab = gE * at;
+                    const float utb = ab / den;
+                    const float mb = (-ab * at / den) * rtol;
+                    if (a0 > a1) sUpb[e] += mb * (up >= 0.f ? 1.f : -1.f);
+                    else if (a1 > a0) sUb[e] += mb * (un >= 0.f ? 1.f : -1.f);
+                    else {
+                        sUpb[e] += 0.5f * mb * (up > 0.f ? 1.f : (up < 0.f ? -1.f : 0.f));
+                        sUb[e] += 0.5f * mb * (un > 0.f ? 1.f : (un < 0.f ? -1.f : 0.f));
+                    }
+#pragma unroll
+                    for (int j = 1; j <= 7; ++j) Kb(j)[e] += dt * ts_bt(j) * utb;
+                }
+                if (use_eig) {
+                    const float g6 = __ldcg(P.tapeZ + tile_off_D(recG6) + e);
+                    const float ga = gA * (kv[7] - kv[6]);
+                    const float gb = gB * (un - g6);
+                    Kb(7)[e] += ga; Kb(6)[e] -= ga;
+                    sUb[e] += gb;            // the matching -gb on g6 is applied in stage 6's epilogue
+                }
+            }
+            __syncthreads();
+        }
+        for (int i = 7; i >= 2; --i) {
+            const int rec = 6 * s + i - 1;
+            vjp(Kb(i), rec, [&](const int m, const int nn, const float* zb) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int e = m * NP + nn + j;
+                    float g = zb[j];
+                    if (i == 7) g += sUb[e];
+                    if (i == 6 && use_eig && (nn + j) < Nloc) {
+                        const float un = __ldcg(P.tapeZ + tile_off_D(recU1) + e);
+                        const float g6 = __ldcg(P.tapeZ + tile_off_D(recG6) + e);
+                        g -= gB * (un - g6);
+                    }
+                    for (int jj = 1; jj < i; ++jj) Kb(jj)[e] = rn_fmaf(dt * ts_a(i, jj), g, Kb(jj)[e]);
+                    sUpb[e] += g;
+                }
+            });
+        }
+        // hand over: u_new(prev step) = uprev, k7(prev step) = k1
+        { float* tmp = sUb; sUb = sUpb; sUpb = tmp; }
+        flipK ^= 1;
+        __syncthreads();
+    }
+    // initial fsalfirst = f(u0, t0): record 0, cotangent carried in Kb(7)
+    vjp(Kb(7), 0, [&](const int m, const int nn, const float* zb) {
+        if (P.dx) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = nn + j;
+                if (n < Nloc) P.dx[(size_t)D * (c0 + n) + r0 + m] = sUb[m * NP + n] + zb[j];
+            }
+        }
+    });
+    if constexpr (G > 1) cluster_sync_all();
+}
+
+}  // namespace rnde

@@ -1,0 +1,116 @@
+// common.cuh -- shared device-side helpers for the regnde sm_100a kernels.
+// Arithmetic follows include/regnde_canon.h (canonical order): every fused
+// multiply-add is an explicit rn_fmaf; the translation unit is built with
+// -fmad=false so nothing else is contracted.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "regnde.h"
+#include "regnde_canon.h"
+
+namespace rnde {
+
+struct StepRec { float t, dt, eest, eig, n1, n2, pad0, pad1; };   // n1/n2: rms(k7-k6), rms(u-g6)
+
+struct DevStats {
+    int nf, naccept, nreject, n_saved, retcode;
+    float t_final, dt_last, dt_init;
+};
+
+// Kernel parameters shared by the forward and backward steppers.
+struct KParams {
+    int D, H, B;        // state dim, hidden dim, local columns
+    int R;              // rows owned by one CTA (G*R >= D)
+    int kblock;         // canonical K-block of layer 1 and of the norms
+    int HS;             // hidden rows reduced by one CTA of the cluster
+    int Q;              // number of column tiles (= clusters)
+    int act1, act2, td;
+    int alg, reg_kind, max_steps, tape_cap, need_tape;
+    float t0, t1, abstol, reltol, dtmin;
+    long long norm_count;   // D * global batch
+    int Bglobal;            // columns entering the norm (== B unless distributed)
+    int col_offset;         // first global column of this rank
+    const float* x; const float* p; float* u_out; float* saveval;
+    float* colsum;          // [2 slots][3][Bpad_global]
+    int colsum_stride;      // Bpad_global
+    unsigned int* bar;      // grid barrier {count, generation}
+    StepRec* steps; DevStats* stats;
+    float* tapeZ; float* tapeK; float* tapeH; float* tapeD1;   // [rec][tile][rows][NP]
+    // backward only
+    const float* du; const float* dsaveval; float* dx;
+    float* scal;            // per-step scalar adjoints (dtbar, tbar) [2*tape_cap]
+    int nsteps;
+};
+
+// ---- small PTX wrappers ----------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_cluster_f4(uint32_t addr, float4 v) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+
+template <int G>
+__device__ __forceinline__ void group_sync() {
+    if constexpr (G > 1) cluster_sync_all(); else __syncthreads();
+}
+
+// Sense-reversing grid barrier over all CTAs of a co-resident persistent grid.
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned nblocks, unsigned& gen) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned prev = atomicAdd(&bar[0], 1u);
+        if (prev == nblocks - 1) {
+            atomicExch(&bar[0], 0u);
+            __threadfence();
+            atomicAdd(&bar[1], 1u);
+        } else {
+            while (ld_acquire_gpu(&bar[1]) == gen) { }
+        }
+        __threadfence();
+    }
+    gen += 1;
+    __syncthreads();
+}
+
+__device__ __forceinline__ float act_apply(int act, float s) { return act == RNDE_ACT_TANH ? canon_tanhf(s) : s; }
+
+// 4 consecutive floats from global memory; vector load when 16B aligned and in range.
+__device__ __forceinline__ float4 ldg4(const float* __restrict__ ptr, int remaining) {
+    if (remaining >= 4 && ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0)) return __ldg(reinterpret_cast<const float4*>(ptr));
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (remaining > 0) v.x = __ldg(ptr);
+    if (remaining > 1) v.y = __ldg(ptr + 1);
+    if (remaining > 2) v.z = __ldg(ptr + 2);
+    if (remaining > 3) v.w = __ldg(ptr + 3);
+    return v;
+}
+
+__host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// Tsit5 coefficients in Float32 (each converted once from its Float64 literal on the host,
+// exactly like the oracle's (REAL)TS_xx casts); filled by init_constants() in regnde.cu.
+__constant__ float c_A[8][8];
+__constant__ float c_BT[8];
+__constant__ float c_C[8];
+__device__ __forceinline__ float ts_a(int i, int j) { return c_A[i][j]; }
+__device__ __forceinline__ float ts_bt(int i) { return c_BT[i]; }
+__device__ __forceinline__ float ts_c(int i) { return c_C[i]; }
+__device__ __forceinline__ float stage_time(float t, float dt, int i) {
+    if (i >= 6) return t + dt;
+    return rn_fmaf(ts_c(i), dt, t);
+}
+
+}  // namespace rnde

@@ -1,0 +1,461 @@
+// regnde.cu -- C ABI of libregnde.so (include/regnde.h): handle management, kernel
+// variant selection, workspace / tape allocation in HBM, launches.
+// No torch, no CPU fallback: every entry point needs a CUDA device.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <cuda_runtime.h>
+#include "regnde.h"
+#include "common.cuh"
+#include "fwd_kernel.cuh"
+#include "bwd_kernel.cuh"
+#include "wgrad_kernel.cuh"
+#include "head_kernel.cuh"
+
+using namespace rnde;
+
+struct rnde_handle {
+    rnde_config cfg;
+    int variant = 0;
+    int G = 1, NP = 32, R = 0, HS = 0, Q = 0, kblock = 0;
+    int num_sms = 0, device = 0;
+    size_t smem_fwd = 0, smem_bwd = 0;
+    int64_t np = 0;
+    // device workspace
+    float* colsum = nullptr; int colsum_stride = 0;
+    unsigned int* bar = nullptr;
+    StepRec* steps = nullptr;
+    DevStats* stats = nullptr;
+    float* tapeZ = nullptr; float* tapeK = nullptr; float* tapeH = nullptr; float* tapeD1 = nullptr;
+    float* wg_ws = nullptr; size_t wg_ws_floats = 0;
+    float* scal = nullptr;
+    float* saveval_int = nullptr;       // used when the caller passes no saveval buffer
+    float* dtile = nullptr;             // dx staging in tile layout
+    float* head_ws = nullptr;
+    // host-path staging
+    float *hx = nullptr, *hp = nullptr, *hu = nullptr, *hsv = nullptr, *hdu = nullptr, *hdsv = nullptr, *hdp = nullptr, *hdx = nullptr;
+    DevStats* stats_pinned = nullptr;
+    const float* last_p = nullptr;
+    rnde_stats last_stats{};
+    bool have_tape = false;
+    int64_t launches = 0;
+    std::string err;
+};
+
+static bool g_const_init[64] = {false};
+
+static int set_err(rnde_handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    return code;
+}
+#define CUDA_TRY(h, expr)                                                                         \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            return set_err((h), RNDE_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+        }                                                                                         \
+    } while (0)
+
+static int init_constants(rnde_handle* h) {
+    int dev = 0;
+    CUDA_TRY(h, cudaGetDevice(&dev));
+    if (dev < 64 && g_const_init[dev]) return RNDE_OK;
+    float A[8][8]; float BT[8]; float C[8];
+    memset(A, 0, sizeof(A)); memset(BT, 0, sizeof(BT)); memset(C, 0, sizeof(C));
+    A[2][1] = (float)TS_A21;
+    A[3][1] = (float)TS_A31; A[3][2] = (float)TS_A32;
+    A[4][1] = (float)TS_A41; A[4][2] = (float)TS_A42; A[4][3] = (float)TS_A43;
+    A[5][1] = (float)TS_A51; A[5][2] = (float)TS_A52; A[5][3] = (float)TS_A53; A[5][4] = (float)TS_A54;
+    A[6][1] = (float)TS_A61; A[6][2] = (float)TS_A62; A[6][3] = (float)TS_A63; A[6][4] = (float)TS_A64; A[6][5] = (float)TS_A65;
+    A[7][1] = (float)TS_A71; A[7][2] = (float)TS_A72; A[7][3] = (float)TS_A73; A[7][4] = (float)TS_A74; A[7][5] = (float)TS_A75;
+    A[7][6] = (float)TS_A76;
+    BT[1] = (float)TS_BT1; BT[2] = (float)TS_BT2; BT[3] = (float)TS_BT3; BT[4] = (float)TS_BT4; BT[5] = (float)TS_BT5;
+    BT[6] = (float)TS_BT6; BT[7] = (float)TS_BT7;
+    C[2] = (float)TS_C1; C[3] = (float)TS_C2; C[4] = (float)TS_C3; C[5] = (float)TS_C4; C[6] = 1.f; C[7] = 1.f;
+    CUDA_TRY(h, cudaMemcpyToSymbol(c_A, A, sizeof(A)));
+    CUDA_TRY(h, cudaMemcpyToSymbol(c_BT, BT, sizeof(BT)));
+    CUDA_TRY(h, cudaMemcpyToSymbol(c_C, C, sizeof(C)));
+    if (dev < 64) g_const_init[dev] = true;
+    return RNDE_OK;
+}
+
+// ---- kernel variants --------------------------------------------------------
+constexpr int NT_FWD = 256;
+typedef void (*kern_t)(const KParams);
+
+static kern_t fwd_kernel_for(int variant) {
+    switch (variant) {
+        case RNDE_KERNEL_CTA: return fwd_kernel<1, 32, 4, true, NT_FWD>;
+        case RNDE_KERNEL_STREAM: return fwd_kernel<1, 4, 1, false, NT_FWD>;
+        case RNDE_KERNEL_CLUSTER: return fwd_kernel<8, 32, 4, true, NT_FWD>;
+        default: return nullptr;
+    }
+}
+static kern_t bwd_kernel_for(int variant) {
+    switch (variant) {
+        case RNDE_KERNEL_CTA: return bwd_kernel<1, 32, 4, true, NT_FWD>;
+        case RNDE_KERNEL_STREAM: return bwd_kernel<1, 4, 1, false, NT_FWD>;
+        case RNDE_KERNEL_CLUSTER: return bwd_kernel<8, 32, 4, true, NT_FWD>;
+        default: return nullptr;
+    }
+}
+static void variant_shape(int variant, int* G, int* NP, bool* WS) {
+    switch (variant) {
+        case RNDE_KERNEL_CTA: *G = 1; *NP = 32; *WS = true; break;
+        case RNDE_KERNEL_STREAM: *G = 1; *NP = 4; *WS = false; break;
+        default: *G = 8; *NP = 32; *WS = true; break;
+    }
+}
+
+extern "C" int rnde_version(void) { return RNDE_VERSION; }
+
+extern "C" const char* rnde_status_string(int s) {
+    switch (s) {
+        case RNDE_OK: return "ok";
+        case RNDE_ERR_MAXITERS: return "maxiters reached";
+        case RNDE_ERR_DTMIN: return "dt <= dtmin";
+        case RNDE_ERR_NAN: return "NaN in error estimate";
+        case RNDE_ERR_ARG: return "invalid argument";
+        case RNDE_ERR_UNSUPPORTED: return "shape not supported by any kernel variant";
+        case RNDE_ERR_CUDA: return "CUDA error";
+        case RNDE_ERR_TAPE_FULL: return "tape capacity exceeded";
+        case RNDE_ERR_STATE: return "backward requires a taped forward";
+        default: return "unknown";
+    }
+}
+
+extern "C" int rnde_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int64_t rnde_num_params(const rnde_config* c) {
+    const int td = c->time_dep ? 1 : 0;
+    return (int64_t)c->hidden_dim * (c->state_dim + td) + c->hidden_dim + (int64_t)c->state_dim * (c->hidden_dim + td) + c->state_dim;
+}
+
+extern "C" int rnde_default_kblock(const rnde_config* c) {
+    // canonical K-blocking of layer 1 (DESIGN.md "canonical arithmetic"): large states are
+    // summed in 8 blocks (one per CTA of the cluster kernel), small ones in a single chain.
+    const int D = c->state_dim;
+    return D >= 128 ? (D + 7) / 8 : D;
+}
+
+extern "C" const char* rnde_last_error(const rnde_handle* h) { return h ? h->err.c_str() : "null handle"; }
+extern "C" int rnde_kernel_variant(const rnde_handle* h) { return h ? h->variant : 0; }
+extern "C" int64_t rnde_launch_count(const rnde_handle* h) { return h ? h->launches : 0; }
+
+static size_t smem_bytes_fwd(int variant, int D, int H, int R, int HS, int kblock) {
+    int G, NP; bool WS;
+    variant_shape(variant, &G, &NP, &WS);
+    return (size_t)make_layout(G, NP, WS, D, H, R, HS, kblock).total * sizeof(float);
+}
+static size_t smem_bytes_bwd(int variant, int D, int H, int R, int HS, int kblock) {
+    int G, NP; bool WS;
+    variant_shape(variant, &G, &NP, &WS);
+    return (size_t)make_bwd_layout(G, NP, WS, D, H, R, HS).total * sizeof(float);
+}
+
+static void free_all(rnde_handle* h) {
+    cudaFree(h->colsum); cudaFree(h->bar); cudaFree(h->steps); cudaFree(h->stats);
+    cudaFree(h->tapeZ); cudaFree(h->tapeK); cudaFree(h->tapeH); cudaFree(h->tapeD1); cudaFree(h->wg_ws); cudaFree(h->scal); cudaFree(h->saveval_int);
+    cudaFree(h->dtile); cudaFree(h->head_ws);
+    cudaFree(h->hx); cudaFree(h->hp); cudaFree(h->hu); cudaFree(h->hsv); cudaFree(h->hdu); cudaFree(h->hdsv); cudaFree(h->hdp); cudaFree(h->hdx);
+    if (h->stats_pinned) cudaFreeHost(h->stats_pinned);
+}
+
+extern "C" void rnde_destroy(rnde_handle* h) {
+    if (!h) return;
+    free_all(h);
+    delete h;
+}
+
+static int try_variant(rnde_handle* h, int variant, size_t smem_limit, std::string* why) {
+    const rnde_config& c = h->cfg;
+    const int D = c.state_dim, H = c.hidden_dim, B = c.batch;
+    int G, NP; bool WS;
+    variant_shape(variant, &G, &NP, &WS);
+    const int R = (D + G - 1) / G;
+    const int HS = (H + G - 1) / G;
+    const int Q = (B + NP - 1) / NP;
+    if (G > 1 && h->kblock != R) { *why = "cluster variant needs kblock == ceil(D/8)"; return 0; }
+    if (G > 1 && (D < 64 || (G - 1) * R >= D)) { *why = "state too small for the cluster variant"; return 0; }
+    const int nbl = (D + h->kblock - 1) / h->kblock;
+    if (G == 1 && nbl > 32) { *why = "more than 32 canonical K-blocks"; return 0; }
+    const size_t sf = smem_bytes_fwd(variant, D, H, R, HS, h->kblock);
+    const size_t sb = c.need_backward ? smem_bytes_bwd(variant, D, H, R, HS, h->kblock) : 0;
+    if (sf > smem_limit || sb > smem_limit) { *why = "shared memory: need " + std::to_string(std::max(sf, sb)) + " B"; return 0; }
+    // all CTAs must be co-resident (persistent grid with a grid barrier)
+    kern_t kf = fwd_kernel_for(variant);
+    if (cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sf) != cudaSuccess) { cudaGetLastError(); *why = "cudaFuncSetAttribute(fwd) failed"; return 0; }
+    if (c.need_backward) {
+        kern_t kb = bwd_kernel_for(variant);
+        if (cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb) != cudaSuccess) { cudaGetLastError(); *why = "cudaFuncSetAttribute(bwd) failed"; return 0; }
+    }
+    int max_cta = 0;
+    if (G == 1) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kf, NT_FWD, sf) != cudaSuccess) { cudaGetLastError(); *why = "occupancy query failed"; return 0; }
+        max_cta = per_sm * h->num_sms;
+        if (c.need_backward) {
+            int per_sm_b = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, bwd_kernel_for(variant), NT_FWD, sb);
+            max_cta = std::min(max_cta, per_sm_b * h->num_sms);
+        }
+    } else {
+        cudaLaunchConfig_t lc{};
+        lc.gridDim = dim3(Q * G); lc.blockDim = dim3(NT_FWD); lc.dynamicSmemBytes = sf;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = G; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        lc.attrs = at; lc.numAttrs = 1;
+        int ncl = 0;
+        if (cudaOccupancyMaxActiveClusters(&ncl, kf, &lc) != cudaSuccess) { cudaGetLastError(); *why = "cluster occupancy query failed"; return 0; }
+        max_cta = ncl * G;
+        if (c.need_backward) {
+            lc.dynamicSmemBytes = sb;
+            int nclb = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclb, bwd_kernel_for(variant), &lc) == cudaSuccess) max_cta = std::min(max_cta, nclb * G);
+            else cudaGetLastError();
+        }
+    }
+    if (Q * G > max_cta) { *why = "grid of " + std::to_string(Q * G) + " CTAs exceeds co-resident capacity " + std::to_string(max_cta); return 0; }
+    h->variant = variant; h->G = G; h->NP = NP; h->R = R; h->HS = HS; h->Q = Q; h->smem_fwd = sf; h->smem_bwd = sb;
+    return 1;
+}
+
+extern "C" int rnde_create(const rnde_config* cfg, rnde_handle** out) {
+    if (!cfg || !out) return RNDE_ERR_ARG;
+    *out = nullptr;
+    if (cfg->struct_bytes != (int32_t)sizeof(rnde_config)) return RNDE_ERR_ARG;
+    if (cfg->state_dim <= 0 || cfg->hidden_dim <= 0 || cfg->batch <= 0) return RNDE_ERR_ARG;
+    if (cfg->act_hidden < 0 || cfg->act_hidden > 1 || cfg->act_out < 0 || cfg->act_out > 1) return RNDE_ERR_ARG;
+    if (cfg->reg_kind < 0 || cfg->reg_kind > RNDE_REG_ERR_PLUS_STIFF || cfg->alg < 0 || cfg->alg > 1) return RNDE_ERR_ARG;
+    if (!(cfg->t1 > cfg->t0) || !(cfg->abstol > 0.f) || !(cfg->reltol > 0.f)) return RNDE_ERR_ARG;
+    if (cfg->dist_mode != RNDE_DIST_SINGLE && cfg->dist_mode != RNDE_DIST_INDEPENDENT) return RNDE_ERR_UNSUPPORTED;
+    if (rnde_device_count() <= 0) return RNDE_ERR_CUDA;
+    rnde_handle* h = new rnde_handle();
+    h->cfg = *cfg;
+    if (h->cfg.max_steps <= 0) h->cfg.max_steps = 1000000;
+    if (h->cfg.tape_capacity <= 0) h->cfg.tape_capacity = 256;
+    if (h->cfg.dtmin <= 0.f) h->cfg.dtmin = 1e-10f;
+    if (h->cfg.global_batch <= 0) h->cfg.global_batch = h->cfg.batch;
+    h->kblock = cfg->kblock > 0 ? std::min(cfg->kblock, cfg->state_dim) : rnde_default_kblock(cfg);
+    h->np = rnde_num_params(cfg);
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&h->device) != cudaSuccess || cudaGetDeviceProperties(&prop, h->device) != cudaSuccess) { delete h; return RNDE_ERR_CUDA; }
+    h->num_sms = prop.multiProcessorCount;
+    const size_t smem_limit = prop.sharedMemPerBlockOptin;
+    int rc = init_constants(h);
+    if (rc != RNDE_OK) { delete h; return rc; }
+    std::string why, all;
+    int ok = 0;
+    if (cfg->kernel_variant != RNDE_KERNEL_AUTO) {
+        ok = try_variant(h, cfg->kernel_variant, smem_limit, &why);
+        all = why;
+    } else {
+        const int order[3] = {RNDE_KERNEL_CTA, RNDE_KERNEL_CLUSTER, RNDE_KERNEL_STREAM};
+        for (int i = 0; i < 3 && !ok; ++i) {
+            ok = try_variant(h, order[i], smem_limit, &why);
+            if (!ok) all += "[variant " + std::to_string(order[i]) + ": " + why + "] ";
+        }
+    }
+    if (!ok) {
+        fprintf(stderr, "regnde: no kernel variant fits D=%d H=%d B=%d: %s\n", cfg->state_dim, cfg->hidden_dim, cfg->batch, all.c_str());
+        delete h;
+        return RNDE_ERR_UNSUPPORTED;
+    }
+    // ---- workspace in HBM ----
+    const rnde_config& c = h->cfg;
+    const int D = c.state_dim, H = c.hidden_dim;
+    h->colsum_stride = round_up((int)c.global_batch, 32);
+    auto fail = [&](const char* what) { h->err = what; free_all(h); delete h; return RNDE_ERR_CUDA; };
+    if (cudaMalloc(&h->colsum, sizeof(float) * 2 * 3 * h->colsum_stride) != cudaSuccess) return fail("cudaMalloc colsum");
+    if (cudaMalloc(&h->bar, sizeof(unsigned) * 4) != cudaSuccess) return fail("cudaMalloc bar");
+    if (cudaMalloc(&h->steps, sizeof(StepRec) * c.tape_capacity) != cudaSuccess) return fail("cudaMalloc steps");
+    if (cudaMalloc(&h->stats, sizeof(DevStats)) != cudaSuccess) return fail("cudaMalloc stats");
+    if (cudaMalloc(&h->saveval_int, sizeof(float) * (c.tape_capacity + 1)) != cudaSuccess) return fail("cudaMalloc saveval");
+    if (cudaMallocHost(&h->stats_pinned, sizeof(DevStats)) != cudaSuccess) return fail("cudaMallocHost stats");
+    if (c.need_backward) {
+        const size_t nrec = 1 + (size_t)6 * c.tape_capacity;
+        const size_t tile = (size_t)h->Q * h->NP;
+        if (cudaMalloc(&h->tapeZ, sizeof(float) * nrec * tile * D) != cudaSuccess) return fail("cudaMalloc tapeZ (lower tape_capacity?)");
+        if (cudaMalloc(&h->tapeK, sizeof(float) * nrec * tile * D) != cudaSuccess) return fail("cudaMalloc tapeK (lower tape_capacity?)");
+        if (cudaMalloc(&h->tapeH, sizeof(float) * nrec * tile * H) != cudaSuccess) return fail("cudaMalloc tapeH");
+        if (cudaMalloc(&h->tapeD1, sizeof(float) * nrec * tile * H) != cudaSuccess) return fail("cudaMalloc tapeD1");
+        h->wg_ws_floats = wgrad_workspace_floats(D, H);
+        if (cudaMalloc(&h->wg_ws, sizeof(float) * h->wg_ws_floats) != cudaSuccess) return fail("cudaMalloc wgrad workspace");
+        if (cudaMalloc(&h->scal, sizeof(float) * 2 * c.tape_capacity) != cudaSuccess) return fail("cudaMalloc scal");
+    }
+    *out = h;
+    return RNDE_OK;
+}
+
+extern "C" int rnde_set_tspan(rnde_handle* h, float t0, float t1) {
+    if (!h || !(t1 > t0)) return RNDE_ERR_ARG;
+    h->cfg.t0 = t0; h->cfg.t1 = t1;
+    return RNDE_OK;
+}
+
+static void fill_params(const rnde_handle* h, KParams& P) {
+    const rnde_config& c = h->cfg;
+    memset(&P, 0, sizeof(P));
+    P.D = c.state_dim; P.H = c.hidden_dim; P.B = c.batch;
+    P.R = h->R; P.kblock = h->kblock; P.HS = h->HS; P.Q = h->Q;
+    P.act1 = c.act_hidden; P.act2 = c.act_out; P.td = c.time_dep ? 1 : 0;
+    P.alg = c.alg; P.reg_kind = c.reg_kind; P.max_steps = c.max_steps; P.tape_cap = c.tape_capacity; P.need_tape = c.need_backward ? 1 : 0;
+    P.t0 = c.t0; P.t1 = c.t1; P.abstol = c.abstol; P.reltol = c.reltol; P.dtmin = c.dtmin;
+    P.norm_count = (long long)c.state_dim * (long long)c.batch;   // SINGLE / INDEPENDENT: the local batch is the whole problem
+    P.Bglobal = c.batch; P.col_offset = 0;
+    P.colsum = h->colsum; P.colsum_stride = h->colsum_stride; P.bar = h->bar; P.steps = h->steps; P.stats = h->stats;
+    P.tapeZ = h->tapeZ; P.tapeK = h->tapeK; P.tapeH = h->tapeH; P.tapeD1 = h->tapeD1; P.scal = h->scal;
+}
+
+static int launch(rnde_handle* h, kern_t k, const KParams& P, size_t smem, cudaStream_t st) {
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(h->Q * h->G); lc.blockDim = dim3(NT_FWD); lc.dynamicSmemBytes = smem; lc.stream = st;
+    cudaLaunchAttribute at[1];
+    int na = 0;
+    if (h->G > 1) {
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = h->G; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+        na++;
+    }
+    lc.attrs = at; lc.numAttrs = na;
+    CUDA_TRY(h, cudaLaunchKernelEx(&lc, k, P));
+    h->launches += 1;
+    return RNDE_OK;
+}
+
+extern "C" int rnde_forward(rnde_handle* h, const float* x_dev, const float* p_dev, float* u_out_dev, float* saveval_dev,
+                            rnde_stats* stats_host, void* stream) {
+    if (!h || !x_dev || !p_dev || !u_out_dev) return RNDE_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    KParams P;
+    fill_params(h, P);
+    P.x = x_dev; P.p = p_dev; P.u_out = u_out_dev;
+    P.saveval = saveval_dev ? saveval_dev : h->saveval_int;
+    CUDA_TRY(h, cudaMemsetAsync(h->bar, 0, sizeof(unsigned) * 4, st));
+    int rc = launch(h, fwd_kernel_for(h->variant), P, h->smem_fwd, st);
+    if (rc != RNDE_OK) return rc;
+    h->last_p = p_dev;
+    h->have_tape = h->cfg.need_backward != 0;
+    CUDA_TRY(h, cudaMemcpyAsync(h->stats_pinned, h->stats, sizeof(DevStats), cudaMemcpyDeviceToHost, st));
+    if (stats_host) {
+        CUDA_TRY(h, cudaStreamSynchronize(st));
+        const DevStats& s = *h->stats_pinned;
+        stats_host->nf = s.nf; stats_host->naccept = s.naccept; stats_host->nreject = s.nreject; stats_host->n_saved = s.n_saved;
+        stats_host->retcode = s.retcode; stats_host->t_final = s.t_final; stats_host->dt_last = s.dt_last; stats_host->dt_init = s.dt_init;
+        h->last_stats = *stats_host;
+        if (s.retcode != RNDE_OK) return set_err(h, s.retcode, rnde_status_string(s.retcode));
+    }
+    return RNDE_OK;
+}
+
+extern "C" int rnde_get_steps(rnde_handle* h, float* t, float* dt, float* eest, float* eig, int32_t cap) {
+    if (!h) return RNDE_ERR_ARG;
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    DevStats s;
+    CUDA_TRY(h, cudaMemcpy(&s, h->stats, sizeof(s), cudaMemcpyDeviceToHost));
+    const int n = std::min(std::min(s.naccept, (int)cap), h->cfg.tape_capacity);
+    std::vector<StepRec> r(std::max(n, 1));
+    if (n > 0) CUDA_TRY(h, cudaMemcpy(r.data(), h->steps, sizeof(StepRec) * n, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) {
+        if (t) t[i] = r[i].t;
+        if (dt) dt[i] = r[i].dt;
+        if (eest) eest[i] = r[i].eest;
+        if (eig) eig[i] = r[i].eig;
+    }
+    return RNDE_OK;
+}
+
+// ---- backward -----------------------------------------------------------------
+extern "C" int rnde_backward(rnde_handle* h, const float* du_dev, const float* dsaveval_dev, float* dp_dev, float* dx_dev, void* stream) {
+    if (!h || !du_dev || !dp_dev) return RNDE_ERR_ARG;
+    if (!h->have_tape || !h->cfg.need_backward) return set_err(h, RNDE_ERR_STATE, "rnde_backward needs a preceding rnde_forward on a handle created with need_backward=1");
+    cudaStream_t st = (cudaStream_t)stream;
+    // number of accepted steps of the forward on this handle (already copied to pinned memory)
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    const DevStats s = *h->stats_pinned;
+    if (s.retcode != RNDE_OK) return set_err(h, RNDE_ERR_STATE, "forward solve failed; nothing to differentiate");
+    KParams P;
+    fill_params(h, P);
+    P.p = h->last_p; P.du = du_dev; P.dsaveval = (h->cfg.reg_kind != RNDE_REG_NONE) ? dsaveval_dev : nullptr; P.dx = dx_dev;
+    P.nsteps = s.naccept;
+    CUDA_TRY(h, cudaMemsetAsync(h->bar, 0, sizeof(unsigned) * 4, st));
+    int rc = launch(h, bwd_kernel_for(h->variant), P, h->smem_bwd, st);
+    if (rc != RNDE_OK) return rc;
+    // parameter gradients: two batched contractions over (record, column) -- see wgrad_kernel.cuh
+    const int nrec = 1 + 6 * s.naccept;
+    rc = launch_wgrad(h->cfg.state_dim, h->cfg.hidden_dim, h->cfg.time_dep ? 1 : 0, nrec, h->Q, h->NP, h->cfg.batch,
+                      h->tapeZ, h->tapeK, h->tapeH, h->tapeD1, h->steps, h->cfg.t0, h->wg_ws, dp_dev, st, &h->launches);
+    if (rc != 0) return set_err(h, RNDE_ERR_CUDA, std::string("wgrad launch: ") + cudaGetErrorString((cudaError_t)rc));
+    return RNDE_OK;
+}
+
+// ---- host-buffer (end-to-end) variants ------------------------------------------
+static int ensure(rnde_handle* h, float** p, size_t n) {
+    if (*p) return RNDE_OK;
+    CUDA_TRY(h, cudaMalloc(p, sizeof(float) * n));
+    return RNDE_OK;
+}
+
+extern "C" int rnde_forward_host(rnde_handle* h, const float* x_host, const float* p_host, float* u_out_host, float* saveval_host,
+                                 rnde_stats* stats_host) {
+    if (!h || !x_host || !p_host || !u_out_host) return RNDE_ERR_ARG;
+    const size_t n = (size_t)h->cfg.state_dim * h->cfg.batch;
+    int rc;
+    if ((rc = ensure(h, &h->hx, n)) || (rc = ensure(h, &h->hp, (size_t)h->np)) || (rc = ensure(h, &h->hu, n)) ||
+        (rc = ensure(h, &h->hsv, (size_t)h->cfg.tape_capacity + 1))) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(h->hx, x_host, sizeof(float) * n, cudaMemcpyHostToDevice, 0));
+    CUDA_TRY(h, cudaMemcpyAsync(h->hp, p_host, sizeof(float) * h->np, cudaMemcpyHostToDevice, 0));
+    rnde_stats st;
+    rc = rnde_forward(h, h->hx, h->hp, h->hu, h->hsv, &st, 0);
+    if (stats_host) *stats_host = st;
+    if (rc != RNDE_OK) return rc;
+    CUDA_TRY(h, cudaMemcpy(u_out_host, h->hu, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    if (saveval_host && st.n_saved > 0) CUDA_TRY(h, cudaMemcpy(saveval_host, h->hsv, sizeof(float) * st.n_saved, cudaMemcpyDeviceToHost));
+    return RNDE_OK;
+}
+
+extern "C" int rnde_backward_host(rnde_handle* h, const float* du_host, const float* dsaveval_host, float* dp_host, float* dx_host) {
+    if (!h || !du_host || !dp_host) return RNDE_ERR_ARG;
+    const size_t n = (size_t)h->cfg.state_dim * h->cfg.batch;
+    int rc;
+    if ((rc = ensure(h, &h->hdu, n)) || (rc = ensure(h, &h->hdsv, (size_t)h->cfg.tape_capacity + 1)) || (rc = ensure(h, &h->hdp, (size_t)h->np)) ||
+        (rc = ensure(h, &h->hdx, n))) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(h->hdu, du_host, sizeof(float) * n, cudaMemcpyHostToDevice, 0));
+    const int nsv = h->last_stats.n_saved;
+    if (dsaveval_host && nsv > 0) CUDA_TRY(h, cudaMemcpyAsync(h->hdsv, dsaveval_host, sizeof(float) * nsv, cudaMemcpyHostToDevice, 0));
+    else CUDA_TRY(h, cudaMemsetAsync(h->hdsv, 0, sizeof(float) * ((size_t)h->cfg.tape_capacity + 1), 0));
+    rc = rnde_backward(h, h->hdu, h->hdsv, h->hdp, h->hdx, 0);
+    if (rc != RNDE_OK) return rc;
+    CUDA_TRY(h, cudaMemcpy(dp_host, h->hdp, sizeof(float) * h->np, cudaMemcpyDeviceToHost));
+    if (dx_host) CUDA_TRY(h, cudaMemcpy(dx_host, h->hdx, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    return RNDE_OK;
+}
+
+extern "C" int rnde_head_loss_grad(rnde_handle* h, const float* u_dev, const float* p3_dev, const float* y_onehot_dev, int32_t n_classes,
+                                   float loss_scale, float* loss_dev, float* logits_dev, float* du_dev, float* dp3_dev, void* stream) {
+    if (!h || !u_dev || !p3_dev || !y_onehot_dev || !loss_dev || !du_dev || !dp3_dev || n_classes <= 0 || n_classes > 32) return RNDE_ERR_ARG;
+    const int D = h->cfg.state_dim, B = h->cfg.batch;
+    if (!h->head_ws) CUDA_TRY(h, cudaMalloc(&h->head_ws, sizeof(float) * ((size_t)n_classes * B + B + 4)));
+    int rc = launch_head(D, B, n_classes, u_dev, p3_dev, y_onehot_dev, loss_scale, loss_dev, logits_dev, du_dev, dp3_dev, h->head_ws,
+                         (cudaStream_t)stream, &h->launches);
+    if (rc != 0) return set_err(h, RNDE_ERR_CUDA, std::string("head launch: ") + cudaGetErrorString((cudaError_t)rc));
+    return RNDE_OK;
+}
+
+extern "C" int rnde_opt_update(rnde_handle* h, float* p_dev, const float* g_dev, float* v_dev, int64_t n, float inv_decay_scale, float eta,
+                               float rho, void* stream) {
+    if (!p_dev || !g_dev || !v_dev || n < 0) return RNDE_ERR_ARG;
+    if (n == 0) return RNDE_OK;   // update_parameters! skips empty parameter vectors (src/utils.jl:151)
+    opt_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p_dev, g_dev, v_dev, (long long)n, inv_decay_scale, eta, rho);
+    if (h) h->launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_err(h, RNDE_ERR_CUDA, std::string("opt_update: ") + cudaGetErrorString(e));
+    return RNDE_OK;
+}

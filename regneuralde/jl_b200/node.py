@@ -1,0 +1,293 @@
+"""Host-side mirror of the reference's neural-ODE layer surface over libregnde.so.
+
+Same names, argument meaning and return tuples as the Julia reference, so the
+parity tests read like the reference's own test script (test/test_node.jl):
+
+    TDChain(Dense(3, 10, tanh), Dense(11, 2))            src/models/basic.jl:2-28
+    MLPDynamics(784, 100)                                experiments/mnist_node.jl:41-54
+    TrackedNeuralODE(model, tspan, time_dep, regularize, solver; reltol, abstol, ...)
+                                                         src/models/neural_ode.jl:10-32
+    node(x, p; func=..., tspan=...) -> (res, nfe, sv)    src/models/neural_ode.jl:48-144
+    track / untrack                                      src/RegNeuralDE.jl:24-25
+
+Arrays are torch CUDA tensors used as device buffers only (PyTorch is plumbing:
+memory, streams, autograd glue).  A state of shape (D, B) is held column-major
+(feature index fastest), i.e. the memory of a Julia ``D x B`` CuArray; helpers
+``colmajor``/``from_colmajor`` convert.  All arithmetic runs in the CUDA library;
+there is no CPU or eager fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+
+# ---- solver / regulariser selectors (the reference passes Julia objects/closures) ----
+@dataclass(frozen=True)
+class Tsit5:
+    """OrdinaryDiffEq.Tsit5()"""
+    alg: int = L.ALG_TSIT5
+
+
+@dataclass(frozen=True)
+class AutoTsit5:
+    """OrdinaryDiffEq.AutoTsit5(Tsit5()) -- composite algorithm exposing eigen_est"""
+    inner: Tsit5 = Tsit5()
+    alg: int = L.ALG_AUTO_TSIT5
+
+
+@dataclass(frozen=True)
+class SaveFunc:
+    """One of the `func(u, t, integrator)` closures the reference hands to SavingCallback.
+    Closures cannot cross a C ABI, so the ones the reference uses are enumerated."""
+    kind: int
+    name: str
+
+
+#: (u, t, integrator) -> integrator.EEst * integrator.dt      neural_ode.jl:116, mnist_node.jl:67
+ERROR_ESTIMATE = SaveFunc(L.REG_ERR_DT, "error_estimate")
+#: (u, t, integrator) -> abs(integrator.eigen_est * integrator.dt)      test/test_node.jl:75
+STIFFNESS_ESTIMATE = SaveFunc(L.REG_STIFF_DT_ABS, "stiffness_estimate")
+#: stability_size * |eigen_est| with the iszero/isnan guard              mnist_node.jl:76-79
+STIFFNESS_SCALED = SaveFunc(L.REG_STIFF_SCALED, "stiff_est")
+#: EEst*dt + 0.1*stability_size*eigen_est                               mnist_node.jl:88-97
+ERROR_PLUS_STIFFNESS = SaveFunc(L.REG_ERR_PLUS_STIFF, "error_stiff_est")
+
+
+def colmajor(x: torch.Tensor) -> torch.Tensor:
+    """(D, B) tensor -> flat device buffer in Julia (column-major) order."""
+    return x.t().contiguous().view(-1)
+
+
+def from_colmajor(buf: torch.Tensor, D: int, B: int) -> torch.Tensor:
+    """flat column-major buffer -> (D, B) tensor view (no copy)."""
+    return buf.view(B, D).t()
+
+
+# ---- layers (only what the hot path's vector fields need) ----------------------
+class Dense:
+    """Flux.Dense(in, out, σ): weight (out, in) glorot_uniform, zero bias (Flux 0.11.6)."""
+
+    def __init__(self, inp: int, out: int, act=None, *, generator: Optional[torch.Generator] = None):
+        self.inp, self.out = inp, out
+        self.act = L.ACT_TANH if act in (torch.tanh, math.tanh, "tanh") else L.ACT_IDENTITY
+        if act not in (None, "identity", torch.tanh, math.tanh, "tanh"):
+            raise ValueError("only identity and tanh activations are supported by the CUDA field kernels")
+        s = math.sqrt(6.0 / (inp + out))
+        self.W = (torch.rand(out, inp, generator=generator, dtype=torch.float32) * 2 - 1) * s
+        self.b = torch.zeros(out, dtype=torch.float32)
+
+    def destructure(self) -> torch.Tensor:
+        # Flux.destructure: vec(W) column-major, then b
+        return torch.cat([self.W.t().contiguous().view(-1), self.b])
+
+
+class TDChain:
+    """Time-conditioned MLP: a 1xB row holding t is vcat'd onto the input of EVERY layer
+    (src/models/basic.jl:16-28).  The CUDA kernels implement the 2-layer case."""
+
+    def __init__(self, *layers: Dense):
+        if len(layers) != 2:
+            raise NotImplementedError("the fused field kernels implement 2-layer time-concatenated chains")
+        l1, l2 = layers
+        if l2.inp != l1.out + 1 or l2.out != l1.inp - 1:
+            raise ValueError("TDChain(Dense(D+1,H,σ), Dense(H+1,D)) expected")
+        self.layers = layers
+        self.D, self.H = l2.out, l1.out
+
+    def destructure(self) -> torch.Tensor:
+        return torch.cat([l.destructure() for l in self.layers])
+
+
+def MLPDynamics(inp: int, hidden: int, *, generator: Optional[torch.Generator] = None) -> TDChain:
+    """experiments/mnist_node.jl:41-54: Dense(in+1, hidden, tanh), Dense(hidden+1, in, tanh)."""
+    return TDChain(Dense(inp + 1, hidden, "tanh", generator=generator), Dense(hidden + 1, inp, "tanh", generator=generator))
+
+
+def track(p: torch.Tensor) -> torch.Tensor:
+    """RegNeuralDE.track: mark an array as a differentiable parameter (Tracker.param)."""
+    return p.detach().clone().requires_grad_(True)
+
+
+def untrack(p: torch.Tensor) -> torch.Tensor:
+    """RegNeuralDE.untrack: Tracker.data"""
+    return p.detach()
+
+
+class SavedValues:
+    """DiffEqCallbacks.SavedValues as returned by the regularised functor: .t, .saveval"""
+
+    def __init__(self, t: torch.Tensor, saveval: torch.Tensor):
+        self.t = t
+        self.saveval = saveval
+
+    def __len__(self):
+        return int(self.saveval.numel())
+
+
+class _Handle:
+    """Owns one rnde_handle (fixed batch size / regulariser / solver)."""
+
+    def __init__(self, cfg: L.Config):
+        L.require_device()
+        self.lib = L.lib()
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        rc = self.lib.rnde_create(C.byref(cfg), C.byref(self.h))
+        if rc != L.OK:
+            raise L.RndeError(rc, f"rnde_create(D={cfg.state_dim}, H={cfg.hidden_dim}, B={cfg.batch})")
+
+    def check(self, rc: int, what: str):
+        if rc != L.OK:
+            raise L.RndeError(rc, what + ": " + self.lib.rnde_last_error(self.h).decode())
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.rnde_destroy(self.h)
+                self.h = C.c_void_p()
+        except Exception:
+            pass
+
+
+def _stream_ptr() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class _Solve(torch.autograd.Function):
+    """Glue between torch autograd and rnde_forward / rnde_backward (the role Tracker's
+    custom-gradient hook plays in the Julia wrapper, julia/RegNeuralDEB200.jl)."""
+
+    @staticmethod
+    def forward(ctx, xbuf: torch.Tensor, p: torch.Tensor, node: "TrackedNeuralODE", hd: _Handle):
+        cfg = hd.cfg
+        D, B = cfg.state_dim, cfg.batch
+        u = torch.empty(D * B, device=xbuf.device, dtype=torch.float32)
+        sv = torch.zeros(cfg.tape_capacity + 1 if cfg.tape_capacity > 0 else 257, device=xbuf.device, dtype=torch.float32)
+        st = L.Stats()
+        rc = hd.lib.rnde_forward(hd.h, xbuf.data_ptr(), p.data_ptr(), u.data_ptr(), sv.data_ptr(), C.byref(st), _stream_ptr())
+        node.last_stats = st
+        hd.check(rc, "rnde_forward")
+        ctx.hd = hd
+        ctx.n_saved = st.n_saved
+        ctx.p_ref = p            # keeps the parameter buffer alive until backward
+        return u, sv[: st.n_saved]
+
+    @staticmethod
+    def backward(ctx, du: torch.Tensor, dsv: torch.Tensor):
+        hd = ctx.hd
+        cfg = hd.cfg
+        D, B = cfg.state_dim, cfg.batch
+        du = du.contiguous() if du is not None else torch.zeros(D * B, device=ctx.p_ref.device)
+        dsv_full = torch.zeros(cfg.tape_capacity + 1, device=du.device, dtype=torch.float32)
+        if dsv is not None and ctx.n_saved > 0:
+            dsv_full[: ctx.n_saved] = dsv
+        dp = torch.empty(ctx.p_ref.numel(), device=du.device, dtype=torch.float32)
+        dx = torch.empty(D * B, device=du.device, dtype=torch.float32)
+        rc = hd.lib.rnde_backward(hd.h, du.data_ptr(), dsv_full.data_ptr(), dp.data_ptr(), dx.data_ptr(), _stream_ptr())
+        hd.check(rc, "rnde_backward")
+        return dx, dp, None, None
+
+
+class TrackedNeuralODE:
+    """src/models/neural_ode.jl:1-33.  ``TrackedNeuralODE(model, tspan, time_dep, regularize,
+    solver; reltol, abstol, save_everystep=false, save_start=false)``."""
+
+    def __init__(self, model: TDChain, tspan: Sequence[float], time_dep: bool, regularize: bool, solver=Tsit5(), *,
+                 reltol: float = 1.4e-8, abstol: float = 1.4e-8, save_everystep: bool = False, save_start: bool = False,
+                 saveat=None, maxiters: int = 0, tape_capacity: int = 256, kernel_variant: int = L.KERNEL_AUTO,
+                 kblock: int = 0, device: str = "cuda"):
+        if save_everystep or saveat is not None:
+            raise NotImplementedError("return_multiple (save_everystep/saveat) is a NEXT row (SURVEY.md 8f N1)")
+        if not time_dep:
+            raise NotImplementedError("the reference's fields on this path are all time dependent")
+        L.require_device()
+        self.model = model
+        self.device = torch.device(device)
+        self.p = model.destructure().to(self.device)
+        self.tspan = (float(tspan[0]), float(tspan[1]))
+        self.time_dep, self.regularize = bool(time_dep), bool(regularize)
+        self.solver = solver
+        self.reltol, self.abstol = float(reltol), float(abstol)
+        self.maxiters, self.tape_capacity = maxiters, tape_capacity
+        self.kernel_variant, self.kblock = kernel_variant, kblock
+        self._handles: dict = {}
+        self.last_stats: Optional[L.Stats] = None
+
+    # Flux.trainable-style access
+    def parameters(self) -> torch.Tensor:
+        return self.p
+
+    def _handle(self, B: int, reg_kind: int, need_backward: bool) -> _Handle:
+        key = (B, reg_kind, need_backward)
+        if key not in self._handles:
+            cfg = L.Config()
+            cfg.struct_bytes = C.sizeof(L.Config)
+            cfg.state_dim, cfg.hidden_dim, cfg.batch = self.model.D, self.model.H, B
+            cfg.act_hidden, cfg.act_out = self.model.layers[0].act, self.model.layers[1].act
+            cfg.time_dep = 1
+            cfg.kblock = self.kblock
+            cfg.alg = self.solver.alg
+            cfg.reg_kind = reg_kind
+            cfg.max_steps = self.maxiters
+            cfg.tape_capacity = self.tape_capacity
+            cfg.need_backward = 1 if need_backward else 0
+            cfg.kernel_variant = self.kernel_variant
+            cfg.dist_mode, cfg.rank, cfg.nranks = L.DIST_SINGLE, 0, 1
+            cfg.t0, cfg.t1 = self.tspan
+            cfg.abstol, cfg.reltol, cfg.dtmin = self.abstol, self.reltol, 0.0
+            cfg.global_batch = B
+            self._handles[key] = _Handle(cfg)
+        return self._handles[key]
+
+    def __call__(self, x: torch.Tensor, p: Optional[torch.Tensor] = None, *, func: Optional[SaveFunc] = None, tspan=None,
+                 saveat=None):
+        """-> (res, nfe, sv): final state (D, B), sol.destats.nf, SavedValues or None."""
+        if saveat is not None:
+            raise NotImplementedError("saveat is a NEXT row (SURVEY.md 8f N1)")
+        p = self.p if p is None else p
+        D = self.model.D
+        if x.dim() != 2 or x.shape[0] != D:
+            raise ValueError(f"x must be ({D}, B)")
+        if not x.is_cuda or not p.is_cuda:
+            raise RuntimeError("regneuralde.jl_b200 runs on CUDA tensors only (no CPU fallback)")
+        B = x.shape[1]
+        if self.regularize:
+            func = ERROR_ESTIMATE if func is None else func     # default of neural_ode.jl:116
+            reg_kind = func.kind
+        else:
+            reg_kind = L.REG_NONE                               # {false,*}: func is ignored (neural_ode.jl:51)
+        need_bwd = torch.is_grad_enabled() and (x.requires_grad or p.requires_grad)
+        hd = self._handle(B, reg_kind, need_bwd)
+        t0, t1 = self.tspan if tspan is None else (float(tspan[0]), float(tspan[1]))
+        hd.check(hd.lib.rnde_set_tspan(hd.h, t0, t1), "rnde_set_tspan")
+        xbuf = colmajor(x.to(torch.float32))
+        ubuf, saveval = _Solve.apply(xbuf, p.contiguous(), self, hd)
+        res = from_colmajor(ubuf, D, B)
+        nfe = int(self.last_stats.nf)
+        if not self.regularize:
+            return res, nfe, None
+        n = int(self.last_stats.naccept)
+        # times of the saved values: t0, then t after each accepted step
+        tcpu = (C.c_float * max(n, 1))()
+        dcpu = (C.c_float * max(n, 1))()
+        hd.check(hd.lib.rnde_get_steps(hd.h, tcpu, dcpu, None, None, n), "rnde_get_steps")
+        ts = [t0] + [tcpu[i] + dcpu[i] for i in range(n)]
+        return res, nfe, SavedValues(torch.tensor(ts, dtype=torch.float32), saveval)
+
+    def steps(self, B: int, reg_kind: int = L.REG_NONE, need_backward: bool = False):
+        """(t, dt, EEst, eigen_est) of every accepted step of the last solve on that handle."""
+        hd = self._handles[(B, reg_kind, need_backward)]
+        n = int(self.last_stats.naccept)
+        arrs = [(C.c_float * max(n, 1))() for _ in range(4)]
+        hd.check(hd.lib.rnde_get_steps(hd.h, *arrs, n), "rnde_get_steps")
+        return [list(a)[:n] for a in arrs]
+
+    def launch_count(self) -> int:
+        return sum(int(h.lib.rnde_launch_count(h.h)) for h in self._handles.values())
