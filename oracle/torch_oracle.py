@@ -131,7 +131,7 @@ def solve(x, p, *, D, H, act2_tanh=True, time_dep=True, t0=0.0, t1=1.0, abstol=1
         sk = abstol + torch.abs(u) * reltol
         d0 = rms(u / sk)
         d1 = rms(k1 / sk)
-        if float(d0) < 1e-5 or float(d1) < 1e-5:
+        if float(d0.detach()) < 1e-5 or float(d1.detach()) < 1e-5:
             dt0 = c(1e-6)
         else:
             dt0 = (d0 / d1) / 100

@@ -1,0 +1,79 @@
+"""The hand-written adjoint of the C oracle against torch autograd through the same algorithm (FP64).
+This is what pins the oracle's MATH (the reference's own tests pin nothing: test/test_node.jl is
+@code_warntype only).  Shapes follow test/test_node.jl:4-6 (TDChain(Dense(3,10,tanh), Dense(11,2)), x 2x1)
+plus larger ones for the canonical K-blocking and every regulariser closure of experiments/mnist_node.jl:62-103."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import orc, torch_oracle as to
+
+CASES = [
+    # D, H, B, act2, alg, reg, kblock
+    (2, 10, 1, orc.ACT_ID, orc.ALG_TSIT5, orc.REG_NONE, 0),            # test_node.jl:9-25
+    (2, 10, 1, orc.ACT_ID, orc.ALG_TSIT5, orc.REG_ERR_DT, 0),          # test_node.jl:28-57
+    (2, 10, 1, orc.ACT_ID, orc.ALG_AUTO_TSIT5, orc.REG_STIFF_DT_ABS, 0),  # test_node.jl:60-89
+    (2, 10, 3, orc.ACT_ID, orc.ALG_TSIT5, orc.REG_ERR_DT, 0),
+    (16, 12, 5, orc.ACT_TANH, orc.ALG_AUTO_TSIT5, orc.REG_ERR_PLUS_STIFF, 4),   # mnist_node.jl:82-99
+    (16, 12, 5, orc.ACT_TANH, orc.ALG_AUTO_TSIT5, orc.REG_STIFF_SCALED, 4),     # mnist_node.jl:70-81
+    (24, 9, 4, orc.ACT_TANH, orc.ALG_TSIT5, orc.REG_ERR_DT, 3),                 # mnist_node.jl:62-69
+]
+
+
+@pytest.mark.parametrize("D,H,B,act2,alg,reg,kb", CASES)
+def test_c_oracle_matches_autograd_fp64(oracle_built, D, H, B, act2, alg, reg, kb):
+    torch.set_default_dtype(torch.float64)
+    try:
+        rng = np.random.default_rng(7 + D + 10 * reg)
+        cfg = orc.OracleConfig(D=D, H=H, B=B, act2=act2, alg=alg, reg_kind=reg, kblock1=kb, abstol=1.4e-8, reltol=1.4e-8)
+        p = orc.glorot_params(rng, D, H, dtype=np.float64) * 1.5 + 0.05 * rng.standard_normal(cfg.n_params)
+        x = rng.random((D, B))
+        o = orc.Oracle(cfg, f64=True)
+        r = o.forward(x, p)
+        pt = torch.tensor(p, requires_grad=True)
+        xt = torch.tensor(x, requires_grad=True)
+        tr = to.solve(xt, pt, D=D, H=H, act2_tanh=(act2 == 1), auto_tsit5=(alg == 1), reg_kind=reg, detach="all")
+        # identical step sequence / NFE accounting (nf = 3 + 6*(naccept+nreject))
+        assert (r.nf, r.naccept, r.nreject) == (tr.nf, tr.naccept, tr.nreject)
+        assert r.nf == 3 + 6 * (r.naccept + r.nreject)
+        assert np.allclose(r.u, tr.u.detach().numpy(), rtol=0, atol=1e-12)
+        assert np.allclose(r.dt_log, tr.dt_log, rtol=1e-5, atol=1e-6)   # the last step is tf - t: absolute, not relative
+        sv_t = torch.stack(tr.saveval) if tr.saveval else torch.zeros(0)
+        if reg:
+            assert len(r.saveval) == r.naccept + 1          # SavingCallback: initial entry + one per accepted step (A.7)
+            assert np.allclose(r.saveval, sv_t.detach().numpy(), rtol=2e-4, atol=1e-9)
+        w = rng.standard_normal((D, B))
+        ws = rng.standard_normal(max(len(r.saveval), 1))
+        loss = (tr.u * torch.tensor(w)).sum()
+        if reg:
+            loss = loss + (sv_t * torch.tensor(ws[: len(r.saveval)])).sum()
+        gp, gx = torch.autograd.grad(loss, [pt, xt])
+        dp, dx, dtb, tb = o.backward(w, ws)
+        assert np.abs(dp - gp.numpy()).max() <= 1e-6 * np.abs(gp.numpy()).max()
+        assert np.abs(dx - gx.numpy()).max() <= 1e-6 * np.abs(gx.numpy()).max()
+        # scalar adjoints w.r.t. every accepted dt (direct + time-shift paths) via replay with leaf dts
+        dts = torch.tensor(r.dt_log, requires_grad=True)
+        tr2 = to.solve(xt, pt, D=D, H=H, act2_tanh=(act2 == 1), auto_tsit5=(alg == 1), reg_kind=reg, detach="all",
+                       forced_dt=r.dt_log, forced_accept=r.accept_log, dt_leaf=dts)
+        sv2 = torch.stack(tr2.saveval) if tr2.saveval else torch.zeros(0)
+        loss2 = (tr2.u * torch.tensor(w)).sum() + ((sv2 * torch.tensor(ws[: len(r.saveval)])).sum() if reg else 0)
+        gdt, = torch.autograd.grad(loss2, [dts])
+        gdt = gdt.numpy()[r.accept_log == 1]
+        mine = dtb + np.concatenate([np.cumsum(tb[::-1])[::-1][1:], [0.0]])
+        assert np.abs(mine - gdt).max() <= 1e-5 * np.abs(gdt).max()
+    finally:
+        torch.set_default_dtype(torch.float32)
+
+
+def test_first_saved_value_conventions(oracle_built):
+    """Appendix A.7: the entry recorded at callback initialisation uses EEst=1, dt=0, eigen_est=1."""
+    rng = np.random.default_rng(3)
+    p = orc.glorot_params(rng, 2, 10); x = rng.random((2, 1), dtype=np.float32)
+    first = {}
+    for reg, alg in ((orc.REG_ERR_DT, 0), (orc.REG_STIFF_DT_ABS, 1), (orc.REG_STIFF_SCALED, 1), (orc.REG_ERR_PLUS_STIFF, 1)):
+        r = orc.Oracle(orc.OracleConfig(D=2, H=10, B=1, act2=0, alg=alg, reg_kind=reg)).forward(x, p)
+        first[reg] = r.saveval[0]
+    assert first[orc.REG_ERR_DT] == 0 and first[orc.REG_STIFF_DT_ABS] == 0
+    stab = np.float32(1) / np.float32(3.5068)
+    assert first[orc.REG_STIFF_SCALED] == stab
+    assert first[orc.REG_ERR_PLUS_STIFF] == np.float32(0.1) * stab

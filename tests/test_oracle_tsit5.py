@@ -1,0 +1,104 @@
+"""Independent checks of the oracle's integrator (no Julia available): analytic linear ODE,
+convergence order of the 5(4) pair, scipy cross-check, FP32 invariants and thread-count determinism."""
+import numpy as np
+import pytest
+from scipy.integrate import solve_ivp
+from scipy.linalg import expm
+
+from oracle import orc
+
+
+def linear_field_params(rng, D, H):
+    """identity activations => u' = W2[:, :H] (W1[:, :D] u + w1t t + b1) + w2t t + b2 = A u + c0 + c1 t"""
+    W1 = rng.standard_normal((H, D + 1)) * 0.4
+    W2 = rng.standard_normal((D, H + 1)) * 0.4
+    b1 = rng.standard_normal(H) * 0.1
+    b2 = rng.standard_normal(D) * 0.1
+    p = np.concatenate([W1.flatten(order="F"), b1, W2.flatten(order="F"), b2])
+    A = W2[:, :H] @ W1[:, :D]
+    c0 = W2[:, :H] @ b1 + b2
+    c1 = W2[:, :H] @ W1[:, D] + W2[:, H]
+    return p, A, c0, c1
+
+
+def exact_linear(A, c0, c1, u0, T):
+    # augment: d/dt [u; 1; t] = [[A, c0, c1], [0,0,0], [0,1,0]] [u; 1; t]
+    D = len(u0)
+    M = np.zeros((D + 2, D + 2))
+    M[:D, :D] = A; M[:D, D] = c0; M[:D, D + 1] = c1; M[D + 1, D] = 1.0
+    return (expm(M * T) @ np.concatenate([u0, [1.0, 0.0]]))[:D]
+
+
+def test_fifth_order_convergence_and_estimator_order(oracle_built):
+    rng = np.random.default_rng(5)
+    D, H = 3, 4
+    p, A, c0, c1 = linear_field_params(rng, D, H)
+    u0 = rng.standard_normal((D, 1))
+    ref = exact_linear(A, c0, c1, u0[:, 0], 1.0)
+    errs, ests = [], []
+    ns = [4, 8, 16, 32]
+    for n in ns:
+        dt = np.full(n, 1.0 / n)
+        cfg = orc.OracleConfig(D=D, H=H, B=1, act1=orc.ACT_ID, act2=orc.ACT_ID, reg_kind=orc.REG_ERR_DT, forced_dt=dt,
+                               forced_accept=np.ones(n, np.int32))
+        r = orc.Oracle(cfg, f64=True).forward(u0, p)
+        assert r.naccept == n and abs(r.t_final - 1.0) < 1e-12
+        errs.append(np.abs(r.u[:, 0] - ref).max())
+        ests.append(np.mean(r.eest_log))
+    rate = np.log2(np.array(errs[:-1]) / np.array(errs[1:]))
+    assert np.all(rate > 4.6) and np.all(rate < 5.6), rate          # global order 5
+    erate = np.log2(np.array(ests[:-1]) / np.array(ests[1:]))
+    assert np.all(erate > 4.5) and np.all(erate < 5.6), erate       # local estimate of the embedded 4th-order solution ~ dt^5
+
+
+def test_adaptive_solution_matches_scipy(oracle_built):
+    rng = np.random.default_rng(11)
+    D, H, B = 6, 16, 3
+    p = orc.glorot_params(rng, D, H, dtype=np.float64) * 2.0
+    x = rng.random((D, B))
+    cfg = orc.OracleConfig(D=D, H=H, B=B, act2=orc.ACT_TANH, abstol=1e-10, reltol=1e-10)
+    o = orc.Oracle(cfg, f64=True)
+    r = o.forward(x, p)
+    assert r.retcode == 0 and r.nf == 3 + 6 * (r.naccept + r.nreject)
+
+    def f(t, y):
+        k, _ = orc.Oracle(orc.OracleConfig(D=D, H=H, B=B, act2=orc.ACT_TANH), f64=True).rhs(p, y.reshape(B, D).T, t)
+        return k.T.reshape(-1)
+
+    s = solve_ivp(f, (0.0, 1.0), x.T.reshape(-1), method="DOP853", rtol=1e-12, atol=1e-12)
+    assert np.abs(s.y[:, -1].reshape(B, D).T - r.u).max() < 1e-8
+
+
+def test_fp32_invariants_and_determinism(oracle_built):
+    rng = np.random.default_rng(1999)
+    D, H, B = 64, 20, 9
+    p = orc.glorot_params(rng, D, H); x = rng.random((D, B), dtype=np.float32)
+    base = None
+    for nthreads in (1, 2, 8):
+        cfg = orc.OracleConfig(D=D, H=H, B=B, kblock1=8, reg_kind=orc.REG_ERR_DT, nthreads=nthreads)
+        r = orc.Oracle(cfg).forward(x, p)
+        assert r.retcode == 0
+        assert r.nf == 3 + 6 * (r.naccept + r.nreject)
+        assert len(r.saveval) == r.naccept + 1
+        assert r.t_final == 1.0
+        key = (r.u.tobytes(), r.saveval.tobytes(), r.nf)
+        base = base or key
+        assert key == base      # bit-identical for any thread count: the order of operations is pinned
+    # the canonical K-blocking is part of the arithmetic: a different kblock may change low-order bits
+    r2 = orc.Oracle(orc.OracleConfig(D=D, H=H, B=B, kblock1=64, reg_kind=orc.REG_ERR_DT)).forward(x, p)
+    assert np.abs(r2.u - np.frombuffer(base[0], np.float32).reshape(D, B)).max() < 1e-4
+
+
+def test_rejections_and_failure_codes(oracle_built):
+    rng = np.random.default_rng(2)
+    D, H, B = 4, 8, 2
+    p = orc.glorot_params(rng, D, H) * 30.0     # stiff-ish field: forces rejected steps
+    x = rng.random((D, B), dtype=np.float32)
+    r = orc.Oracle(orc.OracleConfig(D=D, H=H, B=B, reg_kind=orc.REG_ERR_DT, abstol=1e-6, reltol=1e-6)).forward(x, p)
+    assert r.retcode == 0 and r.nf == 3 + 6 * (r.naccept + r.nreject) and r.nreject > 0
+    assert np.sum(r.accept_log == 0) == r.nreject
+    r = orc.Oracle(orc.OracleConfig(D=D, H=H, B=B, max_steps=3)).forward(x, p)
+    assert r.retcode == 1      # maxiters
+    pn = p.copy(); pn[0] = np.nan
+    r = orc.Oracle(orc.OracleConfig(D=D, H=H, B=B)).forward(x, pn)
+    assert r.retcode == 3      # NaN
