@@ -166,6 +166,12 @@ if __name__ == "__main__":
                 compare_bwd("bwd mid stiff", 20, 50, 37, 1, 1, 2, VAR["auto"])
                 compare_bwd("bwd mnist B=32 cluster", 784, 100, 32, 1, 0, 1, VAR["cluster"])
                 compare_bwd("bwd mnist B=32 stream", 784, 100, 32, 1, 0, 1, VAR["stream"])
+            elif cs == "prof":
+                x, p = make(784, 100, 480, 1999, 1)
+                for _ in range(2):
+                    c = run_cuda(784, 100, 480, x, p, 1, 0, 1, VAR["cluster"])
+                    print("prof fwd", c["time"] * 1e3, "ms nf", c["st"].nf)
+                    c["lib"].rnde_destroy(c["h"])
             elif cs == "timing":
                 timing(512, VAR["cluster"])
                 timing(512, VAR["stream"], reps=2)
