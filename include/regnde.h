@@ -64,7 +64,10 @@ enum { RNDE_ALG_TSIT5 = 0, RNDE_ALG_AUTO_TSIT5 = 1 };
  *   STIFF_SCALED   stability_size*|eigen_est| (0/NaN guard)  mnist_node.jl:76-79
  *   ERR_PLUS_STIFF EEst*dt + 0.1*stability_size*eigen_est   mnist_node.jl:88-97 */
 enum { RNDE_REG_NONE = 0, RNDE_REG_ERR_DT = 1, RNDE_REG_STIFF_DT_ABS = 2, RNDE_REG_STIFF_SCALED = 3, RNDE_REG_ERR_PLUS_STIFF = 4 };
-enum { RNDE_KERNEL_AUTO = 0, RNDE_KERNEL_CTA = 1, RNDE_KERNEL_STREAM = 2, RNDE_KERNEL_CLUSTER = 3 };
+/* CTA: weights + state of a column tile in one CTA's shared memory (small fields);
+ * STREAM: weights streamed from L2 (any size, slow fallback); CLUSTER: 8-CTA clusters, state in
+ * distributed shared memory; CLUSTER4: 4-CTA clusters, state in registers (MNIST-shaped fields). */
+enum { RNDE_KERNEL_AUTO = 0, RNDE_KERNEL_CTA = 1, RNDE_KERNEL_STREAM = 2, RNDE_KERNEL_CLUSTER = 3, RNDE_KERNEL_CLUSTER4 = 4 };
 enum { RNDE_DIST_SINGLE = 0, RNDE_DIST_EXACT = 1, RNDE_DIST_INDEPENDENT = 2 };
 
 typedef struct rnde_config {
@@ -156,6 +159,13 @@ int rnde_opt_update(rnde_handle* h, float* p_dev, const float* g_dev, float* v_d
 
 /* introspection for tests: per accepted step (t, dt, EEst, eigen_est), host arrays of length naccept */
 int rnde_get_steps(rnde_handle* h, float* t, float* dt, float* eest, float* eig, int32_t cap);
+
+/* test hooks: canonical device math (include/regnde_canon.h) evaluated on the GPU, for bit-level
+ * comparison with the CPU build of the same header */
+int rnde_test_tanh(const float* x_dev, float* y_dev, int64_t n, void* stream);
+int rnde_test_tanh_bits(uint32_t first_bits, int64_t n, float* y_dev, void* stream);
+int rnde_test_pow(const float* x_dev, float e, float* y_dev, float* l10_dev, int64_t n, void* stream);
+int rnde_debug_timeline(rnde_handle* h, long long* out, int n);
 
 #ifdef __cplusplus
 }

@@ -103,19 +103,34 @@ static size_t n_params(const orc_config* c) {
 /* ------------------------------------------------------------------ */
 /* canonical reductions                                                */
 /* ------------------------------------------------------------------ */
-/* per-column sum of squares of v[0..D) with row blocking kb: 8-way interleaved
- * fma chains per block, lanes summed 0..7, blocks summed in order. */
-static REAL col_sumsq(const REAL* v, int D, int kb) {
-    REAL tot = 0; int first = 1;
-    for (int r0 = 0; r0 < D; r0 += kb) {
-        int r1 = r0 + kb < D ? r0 + kb : D;
-        REAL a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int r = r0; r < r1; ++r) { int l = (r - r0) & 7; a[l] = R_FMA(v[r], v[r], a[l]); }
-        REAL s = a[0];
-        for (int l = 1; l < 8; ++l) s = s + a[l];
-        if (first) { tot = s; first = 0; } else tot = tot + s;
+/* Canonical combination of per-block partial sums p[0..n): adjacent blocks are paired
+ * first, pairs are then accumulated left to right:  ((p0+p1) + (p2+p3)) + (p4+p5) ...
+ * (one CTA of the cluster-4 kernel owns two adjacent blocks). */
+static REAL combine_blocks(const REAL* p, int n) {
+    REAL tot = 0;
+    for (int b = 0; b < n; b += 2) {
+        REAL pair = (b + 1 < n) ? p[b] + p[b + 1] : p[b];
+        tot = (b == 0) ? pair : tot + pair;
     }
     return tot;
+}
+/* per-column sum of squares of v[0..D) with row blocking kb: inside a block, groups of 4
+ * consecutive rows form one fma chain (acc = fma(v,v,acc) from 0), group sums are added in
+ * order, block sums are combined by combine_blocks. */
+static REAL col_sumsq(const REAL* v, int D, int kb) {
+    REAL part[64]; int nb = 0;
+    for (int r0 = 0; r0 < D; r0 += kb) {
+        int r1 = r0 + kb < D ? r0 + kb : D;
+        REAL s = 0;
+        for (int g0 = r0; g0 < r1; g0 += 4) {
+            int g1 = g0 + 4 < r1 ? g0 + 4 : r1;
+            REAL q = 0;
+            for (int r = g0; r < g1; ++r) q = R_FMA(v[r], v[r], q);
+            s = (g0 == r0) ? q : s + q;
+        }
+        part[nb++] = s;
+    }
+    return combine_blocks(part, nb);
 }
 /* total over columns: 32-way interleaved chains then xor-butterfly 16,8,4,2,1 */
 static REAL cols_total(const REAL* q, int B) {
@@ -149,12 +164,14 @@ static void rhs_eval(const orc_config* c, const REAL* p, const REAL* z, REAL t, 
     {
         REAL* pacc = (REAL*)malloc(sizeof(REAL) * (size_t)(H > D ? H : D));
         REAL* s = (REAL*)malloc(sizeof(REAL) * (size_t)(H > D ? H : D));
+        REAL* pairb = (REAL*)malloc(sizeof(REAL) * (size_t)(H > D ? H : D));
         REAL* hh = (REAL*)malloc(sizeof(REAL) * (size_t)H);
 #pragma omp for schedule(static)
         for (int j = 0; j < B; ++j) {
             const REAL* zj = z + (size_t)D * j;
             /* layer 1 */
-            for (int i0 = 0, first = 1; i0 < D; i0 += kb1, first = 0) {
+            /* blocks of kb1 inputs: fma chain per block; blocks combined pairwise-then-sequentially */
+            for (int i0 = 0, b = 0; i0 < D; i0 += kb1, ++b) {
                 int i1 = i0 + kb1 < D ? i0 + kb1 : D;
                 for (int o = 0; o < H; ++o) pacc[o] = 0;
                 for (int i = i0; i < i1; ++i) {
@@ -162,8 +179,12 @@ static void rhs_eval(const orc_config* c, const REAL* p, const REAL* z, REAL t, 
                     const REAL* w = W1 + (size_t)H * i;
                     for (int o = 0; o < H; ++o) pacc[o] = R_FMA(w[o], xv, pacc[o]);
                 }
-                if (first) for (int o = 0; o < H; ++o) s[o] = pacc[o];
-                else for (int o = 0; o < H; ++o) s[o] = s[o] + pacc[o];
+                if ((b & 1) == 0) for (int o = 0; o < H; ++o) pairb[o] = pacc[o];
+                else for (int o = 0; o < H; ++o) pairb[o] = pairb[o] + pacc[o];
+                if ((b & 1) == 1 || i1 == D) {
+                    if (b < 2) for (int o = 0; o < H; ++o) s[o] = pairb[o];
+                    else for (int o = 0; o < H; ++o) s[o] = s[o] + pairb[o];
+                }
             }
             for (int o = 0; o < H; ++o) {
                 REAL v = s[o];
@@ -173,7 +194,7 @@ static void rhs_eval(const orc_config* c, const REAL* p, const REAL* z, REAL t, 
             }
             if (hout) memcpy(hout + (size_t)H * j, hh, sizeof(REAL) * H);
             /* layer 2 */
-            for (int i0 = 0, first = 1; i0 < H; i0 += kb2, first = 0) {
+            for (int i0 = 0, b = 0; i0 < H; i0 += kb2, ++b) {
                 int i1 = i0 + kb2 < H ? i0 + kb2 : H;
                 for (int o = 0; o < D; ++o) pacc[o] = 0;
                 for (int i = i0; i < i1; ++i) {
@@ -181,8 +202,12 @@ static void rhs_eval(const orc_config* c, const REAL* p, const REAL* z, REAL t, 
                     const REAL* w = W2 + (size_t)D * i;
                     for (int o = 0; o < D; ++o) pacc[o] = R_FMA(w[o], xv, pacc[o]);
                 }
-                if (first) for (int o = 0; o < D; ++o) s[o] = pacc[o];
-                else for (int o = 0; o < D; ++o) s[o] = s[o] + pacc[o];
+                if ((b & 1) == 0) for (int o = 0; o < D; ++o) pairb[o] = pacc[o];
+                else for (int o = 0; o < D; ++o) pairb[o] = pairb[o] + pacc[o];
+                if ((b & 1) == 1 || i1 == H) {
+                    if (b < 2) for (int o = 0; o < D; ++o) s[o] = pairb[o];
+                    else for (int o = 0; o < D; ++o) s[o] = s[o] + pairb[o];
+                }
             }
             REAL* kj = k + (size_t)D * j;
             for (int o = 0; o < D; ++o) {
@@ -192,7 +217,7 @@ static void rhs_eval(const orc_config* c, const REAL* p, const REAL* z, REAL t, 
                 kj[o] = act_apply(c->act2, v);
             }
         }
-        free(pacc); free(s); free(hh);
+        free(pacc); free(s); free(pairb); free(hh);
     }
 }
 
@@ -453,6 +478,7 @@ static REAL saved_value(int kind, REAL EEst, REAL eig, REAL dt) {
 
 int FN(create)(const orc_config* cfg, void** out) {
     if (!cfg || cfg->D <= 0 || cfg->H <= 0 || cfg->B <= 0) return ORC_ERR_ARG;
+    if (cfg->kblock1 > 0 && (cfg->D + cfg->kblock1 - 1) / cfg->kblock1 > 64) return ORC_ERR_ARG;   /* col_sumsq part[64] */
     orc_handle* h = (orc_handle*)calloc(1, sizeof(orc_handle));
     h->cfg = *cfg;
     if (h->cfg.max_steps <= 0) h->cfg.max_steps = 1000000;

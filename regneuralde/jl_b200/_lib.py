@@ -29,14 +29,14 @@ OK, ERR_MAXITERS, ERR_DTMIN, ERR_NAN, ERR_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_TA
 ACT_IDENTITY, ACT_TANH = 0, 1
 ALG_TSIT5, ALG_AUTO_TSIT5 = 0, 1
 REG_NONE, REG_ERR_DT, REG_STIFF_DT_ABS, REG_STIFF_SCALED, REG_ERR_PLUS_STIFF = range(5)
-KERNEL_AUTO, KERNEL_CTA, KERNEL_STREAM, KERNEL_CLUSTER = range(4)
+KERNEL_AUTO, KERNEL_CTA, KERNEL_STREAM, KERNEL_CLUSTER, KERNEL_CLUSTER4 = range(5)
 DIST_SINGLE, DIST_EXACT, DIST_INDEPENDENT = range(3)
 
 EXPORTS = [
     "rnde_version", "rnde_status_string", "rnde_device_count", "rnde_create", "rnde_destroy", "rnde_last_error",
     "rnde_num_params", "rnde_default_kblock", "rnde_kernel_variant", "rnde_launch_count", "rnde_set_tspan",
     "rnde_forward", "rnde_backward", "rnde_forward_host", "rnde_backward_host", "rnde_head_loss_grad", "rnde_get_steps",
-    "rnde_opt_update",
+    "rnde_opt_update", "rnde_test_tanh", "rnde_test_tanh_bits", "rnde_test_pow", "rnde_debug_timeline",
 ]
 
 
@@ -126,6 +126,10 @@ def lib() -> C.CDLL:
     L.rnde_head_loss_grad.argtypes = [vp, vp, vp, vp, C.c_int32, C.c_float, vp, vp, vp, vp, vp]
     L.rnde_get_steps.argtypes = [vp, vp, vp, vp, vp, C.c_int32]
     L.rnde_opt_update.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, vp]
+    L.rnde_test_tanh.argtypes = [vp, vp, C.c_int64, vp]
+    L.rnde_test_tanh_bits.argtypes = [C.c_uint32, C.c_int64, vp, vp]
+    L.rnde_test_pow.argtypes = [vp, C.c_float, vp, vp, C.c_int64, vp]
+    L.rnde_debug_timeline.argtypes = [vp, vp, C.c_int]
     _lib = L
     return L
 

@@ -1,0 +1,401 @@
+// bwd4_kernel.cuh -- reverse sweep for the cluster-4 / register-resident decomposition
+// (the adjoint counterpart of fwd4_kernel.cuh; same maths as bwd_kernel.cuh).
+//
+// Every thread owns the same 4x4 state tile as in the forward kernel and keeps the cotangents of
+// u_new, u_prev and k1..k7 for that tile in registers.  Per field evaluation on the tape (newest
+// first): delta2 = kbar * act2'(k) (thread local, written back over k in the tape) ->
+// [A'] hbar partial = W2[rows,:]^T delta2, one thread tile per (K-block, 4 hidden, 4 cols), block
+// pair-sum, st.async scatter to the reducer CTA -> [B'] sum over the 4 CTAs, delta1 = hbar*act1'(h),
+// st.async all-gather, delta1 to the tape -> [C'] zbar = W1[:,rows]^T delta1 for the thread's tile,
+// distributed into the k-cotangents with the Tsit5 coefficients.  Clusters never synchronise with
+// each other.  Weight gradients are left to wgrad_kernel.cuh.
+#pragma once
+#include "common.cuh"
+#include "fwd4_kernel.cuh"
+
+namespace rnde {
+
+struct B4Layout {
+    int KB, KBP, R, RPAD, HP, HS, NGC, NGH;
+    int oW2T, oW1T, oD2, oP1, oPart, oD1, oBar, total;
+};
+
+__host__ __device__ inline B4Layout make_b4_layout(int D, int H) {
+    B4Layout L;
+    L.KB = D / 8;
+    L.KBP = round_up(L.KB, 4);
+    L.R = 2 * L.KB;
+    L.RPAD = 2 * L.KBP;
+    L.HP = round_up(H, 4);
+    L.HS = (H + V2_G - 1) / V2_G;
+    L.NGC = (L.KB + 3) / 4;
+    L.NGH = (H + 3) / 4;
+    int o = 0;
+    L.oW2T = o; o += L.R * L.HP;           // [k = dense local row][m = hidden]
+    L.oW1T = o; o += H * L.RPAD;           // [k = hidden][m = padded local row]
+    L.oD2 = o; o += L.R * V2_NP;
+    L.oP1 = o; o += L.HP * V2_NP;
+    L.oPart = o; o += V2_G * L.HS * V2_NP;
+    L.oD1 = o; o += L.HP * V2_NP;
+    L.oBar = o; o += 8;
+    L.total = o;
+    return L;
+}
+
+// kbar_j += dt * a_Ij * g for j < I (cotangent of z_I = uprev + dt * sum_j a_Ij k_j)
+template <int I>
+__device__ __forceinline__ void bwd_distribute(float (&kb)[7][16], const float (&g)[16], const float dt) {
+#pragma unroll
+    for (int j = 1; j < I; ++j) {
+        const float c = dt * c_A[I][j];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) kb[j - 1][e] = rn_fmaf(c, g[e], kb[j - 1][e]);
+    }
+}
+
+template <int HC, int KBC>
+__global__ void __launch_bounds__(V2_NT, 1) bwd4_kernel(const KParams P) {
+    constexpr int G = V2_G, NP = V2_NP, NT = V2_NT;
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x;
+    const int rank = (int)cluster_ctarank();
+    const int q = blockIdx.x / G;
+    const int D = P.D, td = P.td;
+    const int H = (HC > 0) ? HC : P.H;
+    const B4Layout L = make_b4_layout(D, H);
+    const int KB = (KBC > 0) ? KBC : L.KB;
+    const int KBP = (KBC > 0) ? ((KBC + 3) / 4 * 4) : L.KBP;
+    const int R = 2 * KB, RPAD = 2 * KBP;
+    const int HP = (HC > 0) ? ((HC + 3) / 4 * 4) : L.HP;
+    const int HS = L.HS, NGC = (KB + 3) / 4, NGH = (H + 3) / 4;
+    const int r0 = rank * R;
+    const int c0 = q * NP;
+    const int Nloc = max(0, min(NP, P.B - c0));
+    const int HSloc = max(0, min(HS, H - rank * HS));
+    float* sW2T = smem + L.oW2T; float* sW1T = smem + L.oW1T;
+    float* sD2 = smem + L.oD2; float* sP1 = smem + L.oP1; float* sPart = smem + L.oPart; float* sD1 = smem + L.oD1;
+    const uint32_t barP = smem_u32(smem + L.oBar), barH = barP + 8;
+    const float* gW1 = P.p;
+    const float* gW2 = gW1 + (size_t)H * (D + td) + H;
+
+    const bool own = tid < 2 * NGC * 4;
+    const int cblk = tid / (NGC * 4), ctile = tid % (NGC * 4);
+    const int cmt = ctile >> 2, cn0 = (ctile & 3) * 4;
+    const int crow0 = cblk * KB + cmt * 4;
+    const int cprow0 = cblk * KBP + cmt * 4;
+    const int cvalid = own ? min(4, KB - cmt * 4) : 0;
+    const bool actA = tid < 2 * NGH * 4;
+    const int akh = tid / (NGH * 4), atile = tid % (NGH * 4);
+    const int am0 = (atile >> 2) * 4, an0 = (atile & 3) * 4;
+
+    for (int e = tid; e < R * HP; e += NT) {        // W2T[k][m] = W2[r0 + k, m]
+        const int k = e / HP, m = e - k * HP;
+        sW2T[e] = (m < H) ? __ldg(gW2 + (size_t)D * m + r0 + k) : 0.f;
+    }
+    for (int e = tid; e < H * RPAD; e += NT) {      // W1T[k][mp] = W1[k, r0 + row(mp)]
+        const int k = e / RPAD, mp = e - k * RPAD;
+        const int b = mp / KBP, i = mp - b * KBP;
+        sW1T[e] = (i < KB) ? __ldg(gW1 + (size_t)H * (r0 + b * KB + i) + k) : 0.f;
+    }
+    if (tid == 0) {
+        mbar_init(barP, 1);
+        mbar_init(barH, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // cotangents in registers
+    float ubar[16], upb[16], kb[7][16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = cn0 + j;
+            ubar[i * 4 + j] = (i < cvalid && n < Nloc) ? __ldg(P.du + (size_t)D * (c0 + n) + r0 + crow0 + i) : 0.f;
+            upb[i * 4 + j] = 0.f;
+        }
+#pragma unroll
+    for (int a = 0; a < 7; ++a)
+#pragma unroll
+        for (int e = 0; e < 16; ++e) kb[a][e] = 0.f;
+    __syncthreads();
+    cluster_sync_all();
+
+    uint32_t ev_parity = 0;
+    const uint32_t bytesP = (uint32_t)((G - 1) * HSloc * NP * 4);
+    const uint32_t bytesH = (uint32_t)((H - HSloc) * NP * 4);
+    const size_t tileD = (size_t)D * NP, tileH = (size_t)H * NP;
+    // offset of this thread's tile row i inside record rec of the [rec][q][row][NP] tapes
+    auto offD = [&](int rec, int i) -> size_t { return ((size_t)rec * P.Q + q) * tileD + (size_t)(r0 + crow0 + i) * NP + cn0; };
+
+    // VJP of record `rec`: cur = kbar of that evaluation (in), zb = W1^T delta1 for the tile (out)
+    auto vjp = [&](const float (&cur)[16], float (&zb)[16], const int rec) {
+        if (tid == 0) { mbar_expect_tx(barP, bytesP); mbar_expect_tx(barH, bytesH); }
+        if (own) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (i < cvalid) {
+                    float4 d2 = make_float4(cur[i * 4], cur[i * 4 + 1], cur[i * 4 + 2], cur[i * 4 + 3]);
+                    float* tp = P.tapeK + offD(rec, i);
+                    if (P.act2 == RNDE_ACT_TANH) {
+                        const float4 kv = __ldcg(reinterpret_cast<const float4*>(tp));
+                        d2.x = d2.x * (1.f - kv.x * kv.x); d2.y = d2.y * (1.f - kv.y * kv.y);
+                        d2.z = d2.z * (1.f - kv.z * kv.z); d2.w = d2.w * (1.f - kv.w * kv.w);
+                    }
+                    *reinterpret_cast<float4*>(sD2 + (crow0 + i) * NP + cn0) = d2;
+                    *reinterpret_cast<float4*>(tp) = d2;      // delta2 replaces k in the tape (wgrad operand)
+                }
+            }
+        }
+        __syncthreads();
+        float acc[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+        if (actA) {     // phase A': hbar partial over one K-block of this CTA's rows
+            const float* wp = sW2T + (akh * KB) * HP + am0;
+            const float* xp = sD2 + (akh * KB) * NP + an0;
+            float4 w = *reinterpret_cast<const float4*>(wp), x = *reinterpret_cast<const float4*>(xp);
+#pragma unroll (KBC > 0 ? 7 : 4)
+            for (int k = 0; k < KB; ++k) {
+                const int kn = (k + 1 < KB) ? k + 1 : k;
+                const float4 wn = *reinterpret_cast<const float4*>(wp + kn * HP);
+                const float4 xn = *reinterpret_cast<const float4*>(xp + kn * NP);
+                const float wv[4] = {w.x, w.y, w.z, w.w}, xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i * 4 + j] = rn_fmaf(wv[i], xv[j], acc[i * 4 + j]);
+                w = wn; x = xn;
+            }
+            if (akh == 1) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    *reinterpret_cast<float4*>(sP1 + (am0 + i) * NP + an0) = make_float4(acc[i * 4], acc[i * 4 + 1], acc[i * 4 + 2], acc[i * 4 + 3]);
+            }
+        }
+        __syncthreads();
+        if (actA && akh == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int m = am0 + i;
+                if (m < H) {
+                    const float4 o = *reinterpret_cast<const float4*>(sP1 + m * NP + an0);
+                    const float4 v = make_float4(acc[i * 4] + o.x, acc[i * 4 + 1] + o.y, acc[i * 4 + 2] + o.z, acc[i * 4 + 3] + o.w);
+                    const int d = m / HS, ml = m - d * HS;
+                    float* dst = sPart + (rank * HS + ml) * NP + an0;
+                    if (d == rank) *reinterpret_cast<float4*>(dst) = v;
+                    else st_async_f4(mapa_u32(smem_u32(dst), d), v, mapa_u32(barP, d));
+                }
+            }
+        }
+        __syncthreads();
+        mbar_wait(barP, ev_parity);
+        if (tid < HSloc * 4) {      // phase B'
+            const int ml = tid >> 2, n4 = (tid & 3) * 4;
+            const int m = rank * HS + ml;
+            float4 s = *reinterpret_cast<const float4*>(sPart + ml * NP + n4);
+#pragma unroll
+            for (int c = 1; c < G; ++c) {
+                const float4 pc = *reinterpret_cast<const float4*>(sPart + (c * HS + ml) * NP + n4);
+                s.x += pc.x; s.y += pc.y; s.z += pc.z; s.w += pc.w;
+            }
+            const size_t oh = ((size_t)rec * P.Q + q) * tileH + (size_t)m * NP + n4;
+            if (P.act1 == RNDE_ACT_TANH) {
+                const float4 hv = __ldcg(reinterpret_cast<const float4*>(P.tapeH + oh));
+                s.x *= (1.f - hv.x * hv.x); s.y *= (1.f - hv.y * hv.y); s.z *= (1.f - hv.z * hv.z); s.w *= (1.f - hv.w * hv.w);
+            }
+            float* dst = sD1 + m * NP + n4;
+            *reinterpret_cast<float4*>(dst) = s;
+            const uint32_t da = smem_u32(dst);
+#pragma unroll
+            for (int d = 1; d < G; ++d) {
+                const int peer = (rank + d) & (G - 1);
+                st_async_f4(mapa_u32(da, peer), s, mapa_u32(barH, peer));
+            }
+            *reinterpret_cast<float4*>(P.tapeD1 + oh) = s;
+        }
+        __syncthreads();
+        mbar_wait(barH, ev_parity);
+        ev_parity ^= 1u;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) zb[e] = 0.f;
+        if (own) {      // phase C'
+            const float* wp = sW1T + cprow0;
+            const float* xp = sD1 + cn0;
+            float4 w = *reinterpret_cast<const float4*>(wp), x = *reinterpret_cast<const float4*>(xp);
+#pragma unroll (HC > 0 ? 5 : 4)
+            for (int k = 0; k < H; ++k) {
+                const int kn = (k + 1 < H) ? k + 1 : k;
+                const float4 wn = *reinterpret_cast<const float4*>(wp + kn * RPAD);
+                const float4 xn = *reinterpret_cast<const float4*>(xp + kn * NP);
+                const float wv[4] = {w.x, w.y, w.z, w.w}, xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) zb[i * 4 + j] = rn_fmaf(wv[i], xv[j], zb[i * 4 + j]);
+                w = wn; x = xn;
+            }
+        }
+    };
+
+    const float atol = P.abstol, rtol = P.reltol;
+    const float cntf = (float)P.norm_count;
+    const float stab = rn_divf(1.0f, (float)TS_STABILITY_SIZE);
+
+    // task list, newest evaluation first: for s = nsteps-1..0: stages 7..2; then the initial record 0
+    const int ntask = 6 * P.nsteps + 1;
+    float dt = 0.f, gB = 0.f;
+    bool use_eig = false;
+    int recU1 = 0, recG6 = 0;
+    for (int task = 0; task < ntask; ++task) {
+        const bool last = (task == ntask - 1);
+        const int s = last ? 0 : P.nsteps - 1 - task / 6;
+        const int i = last ? 7 : 7 - task % 6;
+        const int rec = last ? 0 : 6 * s + i - 1;
+        if (!last && i == 7) {
+            // ---- entering step s: reset per-step cotangents, add the saved-value cotangents --------
+            const StepRec sr = P.steps[s];
+            dt = sr.dt;
+            const float EEst = sr.eest, eig = sr.eig, n1 = sr.n1, n2 = sr.n2;
+            const float sbar = P.dsaveval ? __ldg(P.dsaveval + s + 1) : 0.f;
+            float eestbar = 0.f, eigbar = 0.f;
+            if (sbar != 0.f) {
+                switch (P.reg_kind) {
+                    case RNDE_REG_ERR_DT: eestbar = sbar * dt; break;
+                    case RNDE_REG_STIFF_DT_ABS: eigbar = sbar * ((eig * dt) >= 0.f ? 1.f : -1.f) * dt; break;
+                    case RNDE_REG_STIFF_SCALED: { const float a = fabsf(eig); if (!(a == 0.f || a != a)) eigbar = sbar * stab * (eig >= 0.f ? 1.f : -1.f); break; }
+                    case RNDE_REG_ERR_PLUS_STIFF: {
+                        const float e = EEst * dt;
+                        if (!(e == 0.f || e != e)) eestbar = sbar * dt;
+                        if (!(eig == 0.f || eig != eig)) eigbar = sbar * (0.1f * stab);
+                        break;
+                    }
+                    default: break;
+                }
+            }
+            if (P.alg != RNDE_ALG_AUTO_TSIT5) eigbar = 0.f;
+            const bool use_eest = (eestbar != 0.f) && (EEst > 0.f);
+            use_eig = (eigbar != 0.f) && (n1 > 0.f) && (n2 > 0.f);
+            const float gE = use_eest ? eestbar / (cntf * EEst) : 0.f;
+            const float n1b = use_eig ? eigbar / n2 : 0.f;
+            const float n2b = use_eig ? -eigbar * n1 / (n2 * n2) : 0.f;
+            const float gA = use_eig ? n1b / (cntf * n1) : 0.f;
+            gB = use_eig ? n2b / (cntf * n2) : 0.f;
+            recU1 = 6 * s + 6; recG6 = 6 * s + 5;
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                for (int e = 0; e < 16; ++e) kb[a][e] = 0.f;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) upb[e] = 0.f;
+            if ((use_eest || use_eig) && own) {
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii) {
+                    if (ii < cvalid) {
+                        const float4 up4 = __ldcg(reinterpret_cast<const float4*>(P.tapeZ + offD(6 * s, ii)));
+                        const float4 un4 = __ldcg(reinterpret_cast<const float4*>(P.tapeZ + offD(recU1, ii)));
+                        float kv[7][4];
+#pragma unroll
+                        for (int j = 0; j < 7; ++j) {
+                            const float4 k4 = __ldcg(reinterpret_cast<const float4*>(P.tapeK + offD(6 * s + j, ii)));
+                            kv[j][0] = k4.x; kv[j][1] = k4.y; kv[j][2] = k4.z; kv[j][3] = k4.w;
+                        }
+                        float4 g64 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (use_eig) g64 = __ldcg(reinterpret_cast<const float4*>(P.tapeZ + offD(recG6, ii)));
+                        const float upv[4] = {up4.x, up4.y, up4.z, up4.w}, unv[4] = {un4.x, un4.y, un4.z, un4.w};
+                        const float g6v[4] = {g64.x, g64.y, g64.z, g64.w};
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            if (cn0 + jj >= Nloc) continue;
+                            const int e = ii * 4 + jj;
+                            const float up = upv[jj], un = unv[jj];
+                            if (use_eest) {
+                                float ssum = c_BT[1] * kv[0][jj];
+#pragma unroll
+                                for (int j = 2; j <= 7; ++j) ssum = rn_fmaf(c_BT[j], kv[j - 1][jj], ssum);
+                                const float ut = dt * ssum;
+                                const float a0 = fabsf(up), a1 = fabsf(un);
+                                const float mx = a0 > a1 ? a0 : a1;
+                                const float den = rn_fmaf(mx, rtol, atol);
+                                const float at = ut / den;
+                                const float ab = gE * at;
+                                const float utb = ab / den;
+                                const float mb = (-ab * at / den) * rtol;
+                                if (a0 > a1) upb[e] += mb * (up >= 0.f ? 1.f : -1.f);
+                                else if (a1 > a0) ubar[e] += mb * (un >= 0.f ? 1.f : -1.f);
+                                else {
+                                    upb[e] += 0.5f * mb * (up > 0.f ? 1.f : (up < 0.f ? -1.f : 0.f));
+                                    ubar[e] += 0.5f * mb * (un > 0.f ? 1.f : (un < 0.f ? -1.f : 0.f));
+                                }
+#pragma unroll
+                                for (int j = 1; j <= 7; ++j) kb[j - 1][e] += dt * c_BT[j] * utb;
+                            }
+                            if (use_eig) {
+                                const float ga = gA * (kv[6][jj] - kv[5][jj]);
+                                const float gb = gB * (un - g6v[jj]);
+                                kb[6][e] += ga; kb[5][e] -= ga;
+                                ubar[e] += gb;       // the matching -gb on g6 is applied after stage 6's VJP
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        // kbar of this evaluation
+        float cur[16], zb[16];
+        switch (i) {
+#define RNDE_CUR(J) case J: _Pragma("unroll") for (int e = 0; e < 16; ++e) cur[e] = kb[J - 1][e]; break;
+            RNDE_CUR(2) RNDE_CUR(3) RNDE_CUR(4) RNDE_CUR(5) RNDE_CUR(6)
+            default: _Pragma("unroll") for (int e = 0; e < 16; ++e) cur[e] = kb[6][e]; break;
+#undef RNDE_CUR
+        }
+        vjp(cur, zb, rec);
+        if (last) {
+            // initial fsalfirst = f(u0, t0): dx = ubar + zbar
+            if (P.dx && own) {
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int n = cn0 + jj;
+                        if (ii < cvalid && n < Nloc) P.dx[(size_t)D * (c0 + n) + r0 + crow0 + ii] = ubar[ii * 4 + jj] + zb[ii * 4 + jj];
+                    }
+            }
+            break;
+        }
+        // cotangent of the stage input z_i
+        if (i == 7) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) zb[e] += ubar[e];
+        }
+        if (i == 6 && use_eig && own) {
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii) {
+                if (ii < cvalid) {
+                    const float4 un4 = __ldcg(reinterpret_cast<const float4*>(P.tapeZ + offD(recU1, ii)));
+                    const float4 g64 = __ldcg(reinterpret_cast<const float4*>(P.tapeZ + offD(recG6, ii)));
+                    const float unv[4] = {un4.x, un4.y, un4.z, un4.w}, g6v[4] = {g64.x, g64.y, g64.z, g64.w};
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj)
+                        if (cn0 + jj < Nloc) zb[ii * 4 + jj] -= gB * (unv[jj] - g6v[jj]);
+                }
+            }
+        }
+        switch (i) {
+            case 2: bwd_distribute<2>(kb, zb, dt); break;
+            case 3: bwd_distribute<3>(kb, zb, dt); break;
+            case 4: bwd_distribute<4>(kb, zb, dt); break;
+            case 5: bwd_distribute<5>(kb, zb, dt); break;
+            case 6: bwd_distribute<6>(kb, zb, dt); break;
+            default: bwd_distribute<7>(kb, zb, dt); break;
+        }
+#pragma unroll
+        for (int e = 0; e < 16; ++e) upb[e] += zb[e];
+        if (i == 2) {
+            // hand over to the previous step: u_new(prev) = uprev, k7(prev) = k1
+#pragma unroll
+            for (int e = 0; e < 16; ++e) { ubar[e] = upb[e]; kb[6][e] = kb[0][e]; }
+        }
+    }
+    cluster_sync_all();
+}
+
+}  // namespace rnde

@@ -40,6 +40,7 @@ struct KParams {
     const float* du; const float* dsaveval; float* dx;
     float* scal;            // per-step scalar adjoints (dtbar, tbar) [2*tape_cap]
     int nsteps;
+    long long* dbg;         // optional phase timeline (clock64 stamps), developer diagnostics only
 };
 
 // ---- small PTX wrappers ----------------------------------------------------

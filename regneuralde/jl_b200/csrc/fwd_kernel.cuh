@@ -29,7 +29,7 @@
 namespace rnde {
 
 struct SmemLayout {
-    int HP, RP, nbl;
+    int HP, RP, nbl, ngmax;
     int oW1, oW1t, ob1, oW2, oW2t, ob2, oU, oZ, oK, oPart, oH, oRed, oCP, oTot, oCtl, total;
 };
 
@@ -43,6 +43,7 @@ __host__ __device__ inline SmemLayout make_layout(int G, int NP, bool WS, int D,
     L.HP = round_up(H, 4);
     L.RP = round_up(R, 4);
     L.nbl = (G > 1) ? 1 : (D + kblock - 1) / kblock;
+    L.ngmax = (kblock + 3) / 4;
     int o = 0;
     L.oW1 = o; o += WS ? R * L.HP : 0;
     L.oW1t = o; o += L.HP;
@@ -53,9 +54,14 @@ __host__ __device__ inline SmemLayout make_layout(int G, int NP, bool WS, int D,
     L.oU = o; o += L.RP * NP;
     L.oZ = o; o += L.RP * NP;
     L.oK = o; o += 7 * L.RP * NP;
-    L.oPart = o; o += G * round_up(HS, 1) * NP;
-    L.oH = o; o += L.HP * NP;
-    L.oRed = o; o += 3 * L.nbl * 8 * NP;
+    // the norm scratch (sRed) is only live between field evaluations, the exchange buffers
+    // (sPart, sH) only inside one: they share storage.
+    const int xchg = G * round_up(HS, 1) * NP + L.HP * NP;
+    const int red = 3 * L.nbl * L.ngmax * NP;
+    L.oPart = o;
+    L.oH = o + G * round_up(HS, 1) * NP;
+    L.oRed = o;
+    o += (xchg > red ? xchg : red);
     L.oCP = o; o += 3 * G * NP;
     L.oTot = o; o += 4;
     L.oCtl = o; o += 32;
@@ -63,11 +69,23 @@ __host__ __device__ inline SmemLayout make_layout(int G, int NP, bool WS, int D,
     return L;
 }
 
+// Canonical combination of per-block partials: adjacent blocks paired first, pairs accumulated
+// left to right (oracle/rnde_oracle.c combine_blocks).
+template <class F>
+__device__ __forceinline__ float combine_blocks(int n, F part) {
+    float tot = 0.f;
+    for (int b = 0; b < n; b += 2) {
+        const float pair = (b + 1 < n) ? part(b) + part(b + 1) : part(b);
+        tot = (b == 0) ? pair : tot + pair;
+    }
+    return tot;
+}
+
 // Canonical RMS norms of up to NV fields at once.
 //   val(ml, n, out[NV]) gives the field values at local row ml, column n.
-// Order: per column, per kblock: 8 row-interleaved fma chains, lanes summed 0..7,
-// blocks (== CTAs of the cluster when G>1) summed in order; columns folded by 32
-// interleaved chains + xor butterfly.  Identical to oracle/rnde_oracle.c col_sumsq/cols_total.
+// Order: per column, per kblock: groups of 4 consecutive rows are fma chains, group sums are
+// added in order, blocks (== CTAs of the cluster when G>1) combined by combine_blocks; columns
+// folded by 32 interleaved chains + xor butterfly.  Identical to oracle col_sumsq/cols_total.
 template <int G, int NP, int NV, int NT, class F>
 __device__ __forceinline__ void grid_rms(const KParams& P, const SmemLayout& L, float* smem, int rank, int q, int Rloc, int Nloc,
                                          unsigned& norm_seq, unsigned& bar_gen, F val, float* out) {
@@ -75,23 +93,27 @@ __device__ __forceinline__ void grid_rms(const KParams& P, const SmemLayout& L, 
     float* sRed = smem + L.oRed;
     float* sCP = smem + L.oCP;
     float* sTot = smem + L.oTot;
-    const int nbl = L.nbl;
-    if (tid < 8 * NP) {
+    const int nbl = L.nbl, ngmax = L.ngmax;
+    constexpr int NL = NT / NP;       // group lanes per column
+    {
         const int n = tid % NP, l = tid / NP;
         for (int b = 0; b < nbl; ++b) {
             const int rb0 = (G > 1) ? 0 : b * P.kblock;
             const int rb1 = (G > 1) ? Rloc : min(rb0 + P.kblock, Rloc);
-            float acc[NV];
+            for (int g = l; rb0 + 4 * g < rb1; g += NL) {
+                const int g0 = rb0 + 4 * g, g1 = min(g0 + 4, rb1);
+                float acc[NV];
 #pragma unroll
-            for (int v = 0; v < NV; ++v) acc[v] = 0.f;
-            for (int r = rb0 + l; r < rb1; r += 8) {
-                float vv[NV];
-                val(r, n, vv);
+                for (int v = 0; v < NV; ++v) acc[v] = 0.f;
+                for (int r = g0; r < g1; ++r) {
+                    float vv[NV];
+                    val(r, n, vv);
 #pragma unroll
-                for (int v = 0; v < NV; ++v) acc[v] = rn_fmaf(vv[v], vv[v], acc[v]);
+                    for (int v = 0; v < NV; ++v) acc[v] = rn_fmaf(vv[v], vv[v], acc[v]);
+                }
+#pragma unroll
+                for (int v = 0; v < NV; ++v) sRed[((v * nbl + b) * ngmax + g) * NP + n] = acc[v];
             }
-#pragma unroll
-            for (int v = 0; v < NV; ++v) sRed[((v * nbl + b) * 8 + l) * NP + n] = acc[v];
         }
     }
     __syncthreads();
@@ -99,14 +121,15 @@ __device__ __forceinline__ void grid_rms(const KParams& P, const SmemLayout& L, 
     float* gcol = P.colsum + (size_t)slot * 3 * P.colsum_stride;
     if (tid < NP * NV) {
         const int n = tid % NP, v = tid / NP;
-        float tot = 0.f;
-        for (int b = 0; b < nbl; ++b) {
-            const float* rp = sRed + ((v * nbl + b) * 8) * NP + n;
-            float s = rp[0];
-#pragma unroll
-            for (int l = 1; l < 8; ++l) s = s + rp[l * NP];
-            tot = (b == 0) ? s : tot + s;
-        }
+        const float tot = combine_blocks(nbl, [&](int b) {
+            const int rb0 = (G > 1) ? 0 : b * P.kblock;
+            const int rb1 = (G > 1) ? Rloc : min(rb0 + P.kblock, Rloc);
+            const int ng = (rb1 - rb0 + 3) / 4;
+            const float* rp = sRed + ((v * nbl + b) * ngmax) * NP + n;
+            float s = 0.f;
+            for (int g = 0; g < ng; ++g) s = (g == 0) ? rp[0] : s + rp[g * NP];
+            return s;
+        });
         if constexpr (G > 1) {
             st_cluster_f32(mapa_u32(smem_u32(sCP + (v * G + rank) * NP + n), 0), tot);
         } else {
@@ -117,9 +140,7 @@ __device__ __forceinline__ void grid_rms(const KParams& P, const SmemLayout& L, 
         cluster_sync_all();
         if (rank == 0 && tid < NP * NV) {
             const int n = tid % NP, v = tid / NP;
-            float tot = sCP[(v * G + 0) * NP + n];
-#pragma unroll
-            for (int c = 1; c < G; ++c) tot = tot + sCP[(v * G + c) * NP + n];
+            const float tot = combine_blocks(G, [&](int c) { return sCP[(v * G + c) * NP + n]; });
             if (n < Nloc) gcol[(size_t)v * P.colsum_stride + P.col_offset + q * NP + n] = tot;
         }
     }
@@ -245,8 +266,9 @@ __global__ void __launch_bounds__(NT, 1) fwd_kernel(const KParams P) {
             float tot[TM][4];
             const bool active = m0 < H;
             if (active) {
-                bool first = true;
-                for (int kb0 = 0; kb0 < Rloc; kb0 += P.kblock) {
+                int blk = 0;
+                float pairv[TM][4];
+                for (int kb0 = 0; kb0 < Rloc; kb0 += P.kblock, ++blk) {
                     const int kb1 = min(kb0 + P.kblock, Rloc);
                     float acc[TM][4];
 #pragma unroll
@@ -275,13 +297,17 @@ __global__ void __launch_bounds__(NT, 1) fwd_kernel(const KParams P) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) acc[i][j] = rn_fmaf(w[i], xv[j], acc[i][j]);
                     }
+                    // canonical block combination: adjacent blocks paired, pairs accumulated in order
+                    const bool odd = (blk & 1) != 0, flush = odd || kb1 == Rloc;
 #pragma unroll
                     for (int i = 0; i < TM; ++i)
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) tot[i][j] = first ? acc[i][j] : tot[i][j] + acc[i][j];
-                    first = false;
+                        for (int j = 0; j < 4; ++j) {
+                            pairv[i][j] = odd ? pairv[i][j] + acc[i][j] : acc[i][j];
+                            if (flush) tot[i][j] = (blk < 2) ? pairv[i][j] : tot[i][j] + pairv[i][j];
+                        }
                 }
-                if (first) {
+                if (blk == 0) {
 #pragma unroll
                     for (int i = 0; i < TM; ++i)
 #pragma unroll
@@ -307,9 +333,7 @@ __global__ void __launch_bounds__(NT, 1) fwd_kernel(const KParams P) {
         for (int e = tid; e < HSloc * NP; e += NT) {
             const int ml = e / NP, n = e - ml * NP;
             const int m = rank * HS + ml;
-            float s = sPart[ml * NP + n];
-#pragma unroll
-            for (int c = 1; c < G; ++c) s = s + sPart[(c * HS + ml) * NP + n];
+            float s = combine_blocks(G, [&](int c) { return sPart[(c * HS + ml) * NP + n]; });
             if (td) s = rn_fmaf(sW1t[m], tstage, s);
             s = s + sb1[m];
             const float hv = act_apply(P.act1, s);

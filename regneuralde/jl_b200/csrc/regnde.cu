@@ -11,7 +11,9 @@
 #include "regnde.h"
 #include "common.cuh"
 #include "fwd_kernel.cuh"
+#include "fwd4_kernel.cuh"
 #include "bwd_kernel.cuh"
+#include "bwd4_kernel.cuh"
 #include "wgrad_kernel.cuh"
 #include "head_kernel.cuh"
 
@@ -35,6 +37,7 @@ struct rnde_handle {
     float* saveval_int = nullptr;       // used when the caller passes no saveval buffer
     float* dtile = nullptr;             // dx staging in tile layout
     float* head_ws = nullptr;
+    long long* dbg = nullptr;
     // host-path staging
     float *hx = nullptr, *hp = nullptr, *hu = nullptr, *hsv = nullptr, *hdu = nullptr, *hdsv = nullptr, *hdp = nullptr, *hdx = nullptr;
     DevStats* stats_pinned = nullptr;
@@ -86,19 +89,21 @@ static int init_constants(rnde_handle* h) {
 constexpr int NT_FWD = 256;
 typedef void (*kern_t)(const KParams);
 
-static kern_t fwd_kernel_for(int variant) {
+static kern_t fwd_kernel_for(int variant, int D = 0, int H = 0) {
     switch (variant) {
         case RNDE_KERNEL_CTA: return fwd_kernel<1, 32, 4, true, NT_FWD>;
         case RNDE_KERNEL_STREAM: return fwd_kernel<1, 4, 1, false, NT_FWD>;
         case RNDE_KERNEL_CLUSTER: return fwd_kernel<8, 32, 4, true, NT_FWD>;
+        case RNDE_KERNEL_CLUSTER4: return (H == 100 && D == 784) ? fwd4_kernel<100, 98> : fwd4_kernel<0, 0>;
         default: return nullptr;
     }
 }
-static kern_t bwd_kernel_for(int variant) {
+static kern_t bwd_kernel_for(int variant, int D = 0, int H = 0) {
     switch (variant) {
         case RNDE_KERNEL_CTA: return bwd_kernel<1, 32, 4, true, NT_FWD>;
         case RNDE_KERNEL_STREAM: return bwd_kernel<1, 4, 1, false, NT_FWD>;
         case RNDE_KERNEL_CLUSTER: return bwd_kernel<8, 32, 4, true, NT_FWD>;
+        case RNDE_KERNEL_CLUSTER4: return (H == 100 && D == 784) ? bwd4_kernel<100, 98> : bwd4_kernel<0, 0>;
         default: return nullptr;
     }
 }
@@ -106,6 +111,7 @@ static void variant_shape(int variant, int* G, int* NP, bool* WS) {
     switch (variant) {
         case RNDE_KERNEL_CTA: *G = 1; *NP = 32; *WS = true; break;
         case RNDE_KERNEL_STREAM: *G = 1; *NP = 4; *WS = false; break;
+        case RNDE_KERNEL_CLUSTER4: *G = V2_G; *NP = V2_NP; *WS = true; break;
         default: *G = 8; *NP = 32; *WS = true; break;
     }
 }
@@ -150,11 +156,13 @@ extern "C" int rnde_kernel_variant(const rnde_handle* h) { return h ? h->variant
 extern "C" int64_t rnde_launch_count(const rnde_handle* h) { return h ? h->launches : 0; }
 
 static size_t smem_bytes_fwd(int variant, int D, int H, int R, int HS, int kblock) {
+    if (variant == RNDE_KERNEL_CLUSTER4) return (size_t)make_v2_layout(D, H).total * sizeof(float);
     int G, NP; bool WS;
     variant_shape(variant, &G, &NP, &WS);
     return (size_t)make_layout(G, NP, WS, D, H, R, HS, kblock).total * sizeof(float);
 }
 static size_t smem_bytes_bwd(int variant, int D, int H, int R, int HS, int kblock) {
+    if (variant == RNDE_KERNEL_CLUSTER4) return (size_t)make_b4_layout(D, H).total * sizeof(float);
     int G, NP; bool WS;
     variant_shape(variant, &G, &NP, &WS);
     return (size_t)make_bwd_layout(G, NP, WS, D, H, R, HS).total * sizeof(float);
@@ -163,7 +171,7 @@ static size_t smem_bytes_bwd(int variant, int D, int H, int R, int HS, int kbloc
 static void free_all(rnde_handle* h) {
     cudaFree(h->colsum); cudaFree(h->bar); cudaFree(h->steps); cudaFree(h->stats);
     cudaFree(h->tapeZ); cudaFree(h->tapeK); cudaFree(h->tapeH); cudaFree(h->tapeD1); cudaFree(h->wg_ws); cudaFree(h->scal); cudaFree(h->saveval_int);
-    cudaFree(h->dtile); cudaFree(h->head_ws);
+    cudaFree(h->dtile); cudaFree(h->head_ws); cudaFree(h->dbg);
     cudaFree(h->hx); cudaFree(h->hp); cudaFree(h->hu); cudaFree(h->hsv); cudaFree(h->hdu); cudaFree(h->hdsv); cudaFree(h->hdp); cudaFree(h->hdx);
     if (h->stats_pinned) cudaFreeHost(h->stats_pinned);
 }
@@ -182,18 +190,21 @@ static int try_variant(rnde_handle* h, int variant, size_t smem_limit, std::stri
     const int R = (D + G - 1) / G;
     const int HS = (H + G - 1) / G;
     const int Q = (B + NP - 1) / NP;
-    if (G > 1 && h->kblock != R) { *why = "cluster variant needs kblock == ceil(D/8)"; return 0; }
+    if (variant == RNDE_KERNEL_CLUSTER4) {
+        if (!v2_shape_ok(D, H) || h->kblock != D / 8) { *why = "cluster-4 variant needs D % 8 == 0, kblock == D/8, H <= 128, D <= 1024"; return 0; }
+        if (c.need_backward && !bwd_kernel_for(variant)) { *why = "cluster-4 backward not available"; return 0; }
+    } else if (G > 1 && h->kblock != R) { *why = "cluster variant needs kblock == ceil(D/8)"; return 0; }
     if (G > 1 && (D < 64 || (G - 1) * R >= D)) { *why = "state too small for the cluster variant"; return 0; }
     const int nbl = (D + h->kblock - 1) / h->kblock;
-    if (G == 1 && nbl > 32) { *why = "more than 32 canonical K-blocks"; return 0; }
+    if (nbl > 64) { *why = "more than 64 canonical K-blocks"; return 0; }
     const size_t sf = smem_bytes_fwd(variant, D, H, R, HS, h->kblock);
     const size_t sb = c.need_backward ? smem_bytes_bwd(variant, D, H, R, HS, h->kblock) : 0;
     if (sf > smem_limit || sb > smem_limit) { *why = "shared memory: need " + std::to_string(std::max(sf, sb)) + " B"; return 0; }
     // all CTAs must be co-resident (persistent grid with a grid barrier)
-    kern_t kf = fwd_kernel_for(variant);
+    kern_t kf = fwd_kernel_for(variant, D, H);
     if (cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sf) != cudaSuccess) { cudaGetLastError(); *why = "cudaFuncSetAttribute(fwd) failed"; return 0; }
     if (c.need_backward) {
-        kern_t kb = bwd_kernel_for(variant);
+        kern_t kb = bwd_kernel_for(variant, D, H);
         if (cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb) != cudaSuccess) { cudaGetLastError(); *why = "cudaFuncSetAttribute(bwd) failed"; return 0; }
     }
     int max_cta = 0;
@@ -203,7 +214,7 @@ static int try_variant(rnde_handle* h, int variant, size_t smem_limit, std::stri
         max_cta = per_sm * h->num_sms;
         if (c.need_backward) {
             int per_sm_b = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, bwd_kernel_for(variant), NT_FWD, sb);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, bwd_kernel_for(variant, D, H), NT_FWD, sb);
             max_cta = std::min(max_cta, per_sm_b * h->num_sms);
         }
     } else {
@@ -218,7 +229,7 @@ static int try_variant(rnde_handle* h, int variant, size_t smem_limit, std::stri
         if (c.need_backward) {
             lc.dynamicSmemBytes = sb;
             int nclb = 0;
-            if (cudaOccupancyMaxActiveClusters(&nclb, bwd_kernel_for(variant), &lc) == cudaSuccess) max_cta = std::min(max_cta, nclb * G);
+            if (cudaOccupancyMaxActiveClusters(&nclb, bwd_kernel_for(variant, D, H), &lc) == cudaSuccess) max_cta = std::min(max_cta, nclb * G);
             else cudaGetLastError();
         }
     }
@@ -257,8 +268,8 @@ extern "C" int rnde_create(const rnde_config* cfg, rnde_handle** out) {
         ok = try_variant(h, cfg->kernel_variant, smem_limit, &why);
         all = why;
     } else {
-        const int order[3] = {RNDE_KERNEL_CTA, RNDE_KERNEL_CLUSTER, RNDE_KERNEL_STREAM};
-        for (int i = 0; i < 3 && !ok; ++i) {
+        const int order[4] = {RNDE_KERNEL_CTA, RNDE_KERNEL_CLUSTER4, RNDE_KERNEL_CLUSTER, RNDE_KERNEL_STREAM};
+        for (int i = 0; i < 4 && !ok; ++i) {
             ok = try_variant(h, order[i], smem_limit, &why);
             if (!ok) all += "[variant " + std::to_string(order[i]) + ": " + why + "] ";
         }
@@ -290,7 +301,15 @@ extern "C" int rnde_create(const rnde_config* cfg, rnde_handle** out) {
         if (cudaMalloc(&h->wg_ws, sizeof(float) * h->wg_ws_floats) != cudaSuccess) return fail("cudaMalloc wgrad workspace");
         if (cudaMalloc(&h->scal, sizeof(float) * 2 * c.tape_capacity) != cudaSuccess) return fail("cudaMalloc scal");
     }
+    if (getenv("RNDE_DEBUG_TIMELINE")) { cudaMalloc(&h->dbg, sizeof(long long) * 8000); cudaMemset(h->dbg, 0, sizeof(long long) * 8000); }
     *out = h;
+    return RNDE_OK;
+}
+
+extern "C" int rnde_debug_timeline(rnde_handle* h, long long* out, int n) {
+    if (!h || !h->dbg) return RNDE_ERR_STATE;
+    cudaDeviceSynchronize();
+    cudaMemcpy(out, h->dbg, sizeof(long long) * n, cudaMemcpyDeviceToHost);
     return RNDE_OK;
 }
 
@@ -311,6 +330,7 @@ static void fill_params(const rnde_handle* h, KParams& P) {
     P.norm_count = (long long)c.state_dim * (long long)c.batch;   // SINGLE / INDEPENDENT: the local batch is the whole problem
     P.Bglobal = c.batch; P.col_offset = 0;
     P.colsum = h->colsum; P.colsum_stride = h->colsum_stride; P.bar = h->bar; P.steps = h->steps; P.stats = h->stats;
+    P.dbg = h->dbg;
     P.tapeZ = h->tapeZ; P.tapeK = h->tapeK; P.tapeH = h->tapeH; P.tapeD1 = h->tapeD1; P.scal = h->scal;
 }
 
@@ -339,7 +359,7 @@ extern "C" int rnde_forward(rnde_handle* h, const float* x_dev, const float* p_d
     P.x = x_dev; P.p = p_dev; P.u_out = u_out_dev;
     P.saveval = saveval_dev ? saveval_dev : h->saveval_int;
     CUDA_TRY(h, cudaMemsetAsync(h->bar, 0, sizeof(unsigned) * 4, st));
-    int rc = launch(h, fwd_kernel_for(h->variant), P, h->smem_fwd, st);
+    int rc = launch(h, fwd_kernel_for(h->variant, h->cfg.state_dim, h->cfg.hidden_dim), P, h->smem_fwd, st);
     if (rc != RNDE_OK) return rc;
     h->last_p = p_dev;
     h->have_tape = h->cfg.need_backward != 0;
@@ -386,7 +406,7 @@ extern "C" int rnde_backward(rnde_handle* h, const float* du_dev, const float* d
     P.p = h->last_p; P.du = du_dev; P.dsaveval = (h->cfg.reg_kind != RNDE_REG_NONE) ? dsaveval_dev : nullptr; P.dx = dx_dev;
     P.nsteps = s.naccept;
     CUDA_TRY(h, cudaMemsetAsync(h->bar, 0, sizeof(unsigned) * 4, st));
-    int rc = launch(h, bwd_kernel_for(h->variant), P, h->smem_bwd, st);
+    int rc = launch(h, bwd_kernel_for(h->variant, h->cfg.state_dim, h->cfg.hidden_dim), P, h->smem_bwd, st);
     if (rc != RNDE_OK) return rc;
     // parameter gradients: two batched contractions over (record, column) -- see wgrad_kernel.cuh
     const int nrec = 1 + 6 * s.naccept;
@@ -458,4 +478,30 @@ extern "C" int rnde_opt_update(rnde_handle* h, float* p_dev, const float* g_dev,
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_err(h, RNDE_ERR_CUDA, std::string("opt_update: ") + cudaGetErrorString(e));
     return RNDE_OK;
+}
+
+// ---- test hooks (bit-level checks of the canonical device math against the CPU) -----------------
+__global__ void canon_tanh_test_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = canon_tanhf(x[i]);
+}
+__global__ void canon_tanh_range_kernel(unsigned int first_bits, long long n, float* __restrict__ y) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = canon_tanhf(__uint_as_float(first_bits + (unsigned int)i));
+}
+__global__ void canon_pow_test_kernel(const float* __restrict__ x, float e, float* __restrict__ y, float* __restrict__ l10, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { y[i] = canon_powf(x[i], e); l10[i] = canon_log10f(x[i]); }
+}
+extern "C" int rnde_test_tanh(const float* x_dev, float* y_dev, int64_t n, void* stream) {
+    canon_tanh_test_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x_dev, y_dev, (long long)n);
+    return cudaGetLastError() == cudaSuccess ? RNDE_OK : RNDE_ERR_CUDA;
+}
+extern "C" int rnde_test_tanh_bits(uint32_t first_bits, int64_t n, float* y_dev, void* stream) {
+    canon_tanh_range_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(first_bits, (long long)n, y_dev);
+    return cudaGetLastError() == cudaSuccess ? RNDE_OK : RNDE_ERR_CUDA;
+}
+extern "C" int rnde_test_pow(const float* x_dev, float e, float* y_dev, float* l10_dev, int64_t n, void* stream) {
+    canon_pow_test_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x_dev, e, y_dev, l10_dev, (long long)n);
+    return cudaGetLastError() == cudaSuccess ? RNDE_OK : RNDE_ERR_CUDA;
 }

@@ -15,7 +15,7 @@ from oracle import orc  # noqa: E402  (diagnostic tool: oracle as checker)
 import regneuralde.jl_b200 as R  # noqa: E402
 from regneuralde.jl_b200 import _lib as L  # noqa: E402
 
-VAR = {"auto": 0, "cta": 1, "stream": 2, "cluster": 3}
+VAR = {"auto": 0, "cta": 1, "stream": 2, "cluster": 3, "cluster4": 4}
 
 
 def make(D, H, B, seed, act2, scale=1.0):
@@ -166,12 +166,56 @@ if __name__ == "__main__":
                 compare_bwd("bwd mid stiff", 20, 50, 37, 1, 1, 2, VAR["auto"])
                 compare_bwd("bwd mnist B=32 cluster", 784, 100, 32, 1, 0, 1, VAR["cluster"])
                 compare_bwd("bwd mnist B=32 stream", 784, 100, 32, 1, 0, 1, VAR["stream"])
+            elif cs == "c4":
+                compare_fwd("mnist B=16 cluster4", 784, 100, 16, 1, 0, 1, VAR["cluster4"])
+                compare_fwd("mnist B=40 cluster4 auto-tsit5 combined", 784, 100, 40, 1, 1, 4, VAR["cluster4"])
+                compare_fwd("mnist B=512 cluster4", 784, 100, 512, 1, 0, 1, VAR["cluster4"])
+                compare_fwd("D=64 H=20 B=100 cluster4", 64, 20, 100, 1, 0, 1, VAR["cluster4"], kblock=8)
+                compare_fwd("D=200 H=37 B=33 cluster4 stiff", 200, 37, 33, 0, 1, 2, VAR["cluster4"], kblock=25)
+            elif cs == "c4time":
+                x, p = make(784, 100, 512, 1999, 1)
+                for _ in range(3):
+                    c = run_cuda(784, 100, 512, x, p, 1, 0, 1, VAR["cluster4"])
+                    print("cluster4 fwd B=512", c["time"] * 1e3, "ms nf", c["st"].nf, "variant", c["variant"])
+                    c["lib"].rnde_destroy(c["h"])
+            elif cs == "timeline":
+                import os
+                os.environ["RNDE_DEBUG_TIMELINE"] = "1"
+                for (D_, H_, kb_) in ((784, 100, 0), (64, 20, 8)):
+                    x, p = make(D_, H_, 512, 1999, 1)
+                    c = run_cuda(D_, H_, 512, x, p, 1, 0, 1, VAR["cluster4"], kblock=kb_)
+                    buf = (C.c_longlong * 8000)()
+                    c["lib"].rnde_debug_timeline(c["h"], buf, 8000)
+                    a = np.array(list(buf)).reshape(-1, 2)
+                    a = a[: np.nonzero(a[:, 1])[0].max() + 1]
+                    ids, ts = a[:, 0], a[:, 1]
+                    # per-eval phase durations: average over evals 5..60
+                    starts = np.nonzero(ids == 0)[0]
+                    names = {1: "stageZ+sync", 2: "phaseA", 3: "syncA", 4: "pair+scatter", 5: "sync", 6: "waitP", 7: "phaseB", 8: "sync", 9: "waitH", 10: "phaseC"}
+                    durs = {k: [] for k in names}
+                    between = []
+                    for si in range(5, min(60, len(starts) - 1)):
+                        s0 = starts[si]
+                        for k in range(1, 11):
+                            durs[k].append(ts[s0 + k] - ts[s0 + k - 1])
+                        between.append(ts[starts[si + 1]] - ts[s0 + 10])
+                    print(f"timeline D={D_} H={H_}: total/eval {np.mean([ts[starts[i+1]]-ts[starts[i]] for i in range(5, min(60, len(starts)-1))]):.0f} cycles")
+                    for k in range(1, 11):
+                        print(f"   {names[k]:14s} {np.mean(durs[k]):8.0f}")
+                    print(f"   between evals  {np.mean(between):8.0f}  (median {np.median(between):.0f})")
+                    c["lib"].rnde_destroy(c["h"])
             elif cs == "prof":
                 x, p = make(784, 100, 480, 1999, 1)
                 for _ in range(2):
                     c = run_cuda(784, 100, 480, x, p, 1, 0, 1, VAR["cluster"])
                     print("prof fwd", c["time"] * 1e3, "ms nf", c["st"].nf)
                     c["lib"].rnde_destroy(c["h"])
+            elif cs == "c4bwd":
+                compare_bwd("bwd mnist B=32 cluster4", 784, 100, 32, 1, 0, 1, VAR["cluster4"])
+                compare_bwd("bwd mnist B=40 cluster4 auto combined", 784, 100, 40, 1, 1, 4, VAR["cluster4"])
+                compare_bwd("bwd mnist B=24 cluster4 stiff identity-out", 784, 100, 24, 0, 1, 2, VAR["cluster4"])
+                compare_bwd("bwd mnist B=512 cluster4", 784, 100, 512, 1, 0, 1, VAR["cluster4"])
+                timing(512, VAR["cluster4"], reps=4)
             elif cs == "timing":
                 timing(512, VAR["cluster"])
                 timing(512, VAR["stream"], reps=2)
