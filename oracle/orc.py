@@ -44,7 +44,7 @@ class _Stats(C.Structure):
 def build(force: bool = False) -> None:
     """Compile the oracle with its Makefile (gcc; a few seconds)."""
     if force or not ((_BUILD / "liborc_f32.so").exists() and (_BUILD / "liborc_f64.so").exists()) or \
-            (_BUILD / "liborc_f32.so").stat().st_mtime < max((_HERE / "rnde_oracle.c").stat().st_mtime,
+            (_BUILD / "liborc_f32.so").stat().st_mtime < max((_HERE / "rnde_oracle.c").stat().st_mtime, (_HERE / "rnde_oracle_bwd.inc").stat().st_mtime,
                                                              (_HERE.parent / "include" / "regnde_canon.h").stat().st_mtime):
         subprocess.run(["make", "-C", str(_HERE), "-s"], check=True)
 
@@ -196,8 +196,10 @@ class Oracle:
                             dt_log=dts[:n], accept_log=acc[:n], eest_log=ee[:n], dt_init=st.dt_init,
                             t_final=st.t_final, steps=steps)
 
-    def backward(self, du, dsaveval=None):
-        """Discrete adjoint with frozen dt.  Returns dp, dx, dtbar[naccept], tbar[naccept]."""
+    def backward(self, du, dsaveval=None, hi: bool = False):
+        """Discrete adjoint with frozen dt.  Returns dp, dx, dtbar[naccept], tbar[naccept].
+        hi=True (FP32 oracle only): cotangents and accumulations in Float64 over the same FP32
+        forward values -- the reference for judging the accuracy of FP32 adjoints."""
         D, B = self.cfg.D, self.cfg.B
         du = np.asfortranarray(du, dtype=self.dtype)
         if dsaveval is None:
@@ -208,7 +210,7 @@ class Oracle:
         nacc = max(self._naccept, 1)
         dtbar = np.zeros(nacc, dtype=np.float64)
         tbar = np.zeros(nacc, dtype=np.float64)
-        f = self._fn("backward")
+        f = self._fn("backward_hi" if (hi and not self.f64) else "backward")
         f.argtypes = [C.c_void_p] * 7
         rc = f(self.h, self._ptr(du), self._ptr(dsaveval), self._ptr(dp), self._ptr(dx), self._ptr(dtbar), self._ptr(tbar))
         if rc != 0:

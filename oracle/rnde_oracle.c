@@ -221,72 +221,6 @@ static void rhs_eval(const orc_config* c, const REAL* p, const REAL* z, REAL t, 
     }
 }
 
-/* VJP of the field at (z,t) with cotangent kbar: returns zbar, accumulates dp.
- * Uses saved h (H x B) and k (D x B).  dp accumulators are per-thread.        */
-static void rhs_vjp(const orc_config* c, const REAL* p, const REAL* z, REAL t, const REAL* h, const REAL* k,
-                    const REAL* kbar, REAL* zbar, REAL** dp_thr, REAL* tbar_out) {
-    const int D = c->D, H = c->H, B = c->B, td = c->time_dep ? 1 : 0;
-    const REAL* W1 = p;
-    const REAL* W2 = p + (size_t)H * (D + td) + H;
-    const size_t oW1 = 0, ob1 = (size_t)H * (D + td), oW2 = ob1 + H, ob2 = oW2 + (size_t)D * (H + td);
-    double tbar_tot = 0;
-#pragma omp parallel reduction(+ : tbar_tot)
-    {
-#ifdef _OPENMP
-        REAL* dp = dp_thr[omp_get_thread_num()];
-#else
-        REAL* dp = dp_thr[0];
-#endif
-        REAL* d2 = (REAL*)malloc(sizeof(REAL) * (size_t)D);
-        REAL* d1 = (REAL*)malloc(sizeof(REAL) * (size_t)H);
-#pragma omp for schedule(static)
-        for (int j = 0; j < B; ++j) {
-            const REAL* zj = z + (size_t)D * j;
-            const REAL* hj = h + (size_t)H * j;
-            const REAL* kj = k + (size_t)D * j;
-            const REAL* kb = kbar + (size_t)D * j;
-            REAL* zb = zbar + (size_t)D * j;
-            for (int o = 0; o < D; ++o) d2[o] = c->act2 == ACT_TANH ? kb[o] * (1 - kj[o] * kj[o]) : kb[o];
-            /* dW2 += d2 * [h;t]^T ; db2 += d2 ; hbar = W2[:, :H]^T d2 */
-            for (int i = 0; i < H; ++i) {
-                const REAL* w = W2 + (size_t)D * i;
-                REAL* dw = dp + oW2 + (size_t)D * i;
-                const REAL hv = hj[i];
-                REAL acc = 0;
-                for (int o = 0; o < D; ++o) { dw[o] += d2[o] * hv; acc += w[o] * d2[o]; }
-                d1[i] = c->act1 == ACT_TANH ? acc * (1 - hv * hv) : acc;
-            }
-            if (td) {
-                REAL* dw = dp + oW2 + (size_t)D * H;
-                const REAL* w = W2 + (size_t)D * H;
-                REAL acc = 0;
-                for (int o = 0; o < D; ++o) { dw[o] += d2[o] * t; acc += w[o] * d2[o]; }
-                tbar_tot += (double)acc;
-            }
-            for (int o = 0; o < D; ++o) dp[ob2 + o] += d2[o];
-            /* dW1 += d1 * [z;t]^T ; db1 += d1 ; zbar = W1[:, :D]^T d1 */
-            for (int i = 0; i < D; ++i) {
-                const REAL* w = W1 + (size_t)H * i;
-                REAL* dw = dp + oW1 + (size_t)H * i;
-                const REAL zv = zj[i];
-                REAL acc = 0;
-                for (int o = 0; o < H; ++o) { dw[o] += d1[o] * zv; acc += w[o] * d1[o]; }
-                zb[i] = acc;
-            }
-            if (td) {
-                REAL* dw = dp + oW1 + (size_t)H * D;
-                const REAL* w = W1 + (size_t)H * D;
-                REAL acc = 0;
-                for (int o = 0; o < H; ++o) { dw[o] += d1[o] * t; acc += w[o] * d1[o]; }
-                tbar_tot += (double)acc;
-            }
-            for (int o = 0; o < H; ++o) dp[ob1 + o] += d1[o];
-        }
-        free(d2); free(d1);
-    }
-    if (tbar_out) *tbar_out = (REAL)tbar_tot;
-}
-
 /* ------------------------------------------------------------------ */
 /* one Tsit5 attempt                                                   */
 /* ------------------------------------------------------------------ */
@@ -692,164 +626,24 @@ int FN(rhs)(const orc_config* cfg, const REAL* p, const REAL* z, double t, REAL*
     return ORC_OK;
 }
 
-/* ------------------------------------------------------------------ */
-/* backward: discrete adjoint of the recorded accepted steps, frozen dt */
-/* (SURVEY.md section 3.2 / Appendix A.6 with detach_dt = all)          */
-/*   du_out   : dL/du(t_f)             (D x B)                          */
-/*   dsaveval : dL/dsaveval[i], i in [0,n_saved)                        */
-/*   dp (np), dx (D x B) are overwritten.                               */
-/*   dtbar_steps/tbar_steps (may be NULL, length naccept): per accepted  */
-/*   step j the partial derivatives dL/d(dt_j) (t_j held fixed) and      */
-/*   dL/d(t_j) (dt_j held fixed) -- the scalar adjoints the              */
-/*   all_but_first mode composes in oracle/orc.py.                       */
-/* ------------------------------------------------------------------ */
-int FN(backward)(void* hv, const REAL* du_out, const REAL* dsaveval, REAL* dp_out, REAL* dx_out, double* dtbar_steps,
-                 double* tbar_steps) {
-    orc_handle* h = (orc_handle*)hv;
-    const orc_config* c = &h->cfg;
-    const int D = c->D, B = c->B;
-    const size_t n = (size_t)D * B;
-    const long long cnt = (long long)D * B;
-    const REAL* p = h->p;
-#ifdef _OPENMP
-    if (c->nthreads > 0) omp_set_num_threads(c->nthreads);
-    int nthr = omp_get_max_threads();
-#else
-    int nthr = 1;
+/* The adjoint is compiled twice: with cotangents in REAL (the plain FP32/FP64 adjoint) and, for
+ * the FP32 build, with cotangents in double over the SAME FP32 forward values ("truth" for
+ * judging FP32 adjoints: the regulariser gradient cancels ~1e7-sized cotangents). */
+#define ADJ REAL
+#define VJP_FN rhs_vjp
+#define BWD_FN FN(backward)
+#include "rnde_oracle_bwd.inc"
+#undef ADJ
+#undef VJP_FN
+#undef BWD_FN
+#ifndef ORC_F64
+#define ADJ double
+#define VJP_FN rhs_vjp_hi
+#define BWD_FN FN(backward_hi)
+#include "rnde_oracle_bwd.inc"
+#undef ADJ
+#undef VJP_FN
+#undef BWD_FN
 #endif
-    REAL** dp_thr = (REAL**)malloc(sizeof(REAL*) * nthr);
-    for (int i = 0; i < nthr; ++i) dp_thr[i] = (REAL*)calloc(h->np, sizeof(REAL));
-    step_ws* w = ws_alloc(c);
-    REAL* ubar = (REAL*)malloc(sizeof(REAL) * n);      /* cotangent of u_new */
-    REAL* uprevbar = (REAL*)malloc(sizeof(REAL) * n);
-    REAL* kbar[8];
-    for (int i = 1; i <= 7; ++i) kbar[i] = (REAL*)calloc(n, sizeof(REAL));
-    REAL* zbar = (REAL*)malloc(sizeof(REAL) * n);
-    REAL* k7bar_in = (REAL*)calloc(n, sizeof(REAL));   /* from the next step's k1 */
-    REAL* h1 = (REAL*)malloc(sizeof(REAL) * (size_t)c->H * B);
-    memcpy(ubar, du_out, sizeof(REAL) * n);
-    const REAL atol = (REAL)c->abstol, rtol = (REAL)c->reltol;
-    const int has_reg = c->reg_kind != REG_NONE;
-
-    for (int s = h->nsteps - 1; s >= 0; --s) {
-        const REAL t = h->tp_t[s], dt = h->tp_dt[s];
-        const REAL* uprev = h->tp_uprev[s];
-        memcpy(w->k[1], h->tp_k1[s], sizeof(REAL) * n);
-        REAL EEst, eig;
-        tsit5_attempt(c, p, uprev, t, dt, w, &EEst, &eig, 1);
-        double dtbar = 0, tbar = 0;
-        /* cotangents entering this step */
-        for (int i = 1; i <= 6; ++i) memset(kbar[i], 0, sizeof(REAL) * n);
-        memcpy(kbar[7], k7bar_in, sizeof(REAL) * n);
-        memset(uprevbar, 0, sizeof(REAL) * n);
-        REAL* z6bar_extra = NULL;
-        /* saved value cotangent */
-        REAL sbar = has_reg ? dsaveval[s + 1] : (REAL)0;
-        REAL eestbar = 0, eigbar = 0;
-        if (sbar != 0) {
-            const REAL stab = (REAL)1 / (REAL)(float)TS_STABILITY_SIZE;
-            switch (c->reg_kind) {
-                case REG_ERR_DT: eestbar = sbar * dt; dtbar += (double)(sbar * EEst); break;
-                case REG_STIFF_DT_ABS: {
-                    REAL sg = (eig * dt) >= 0 ? (REAL)1 : (REAL)-1;
-                    eigbar = sbar * sg * dt; dtbar += (double)(sbar * sg * eig); break;
-                }
-                case REG_STIFF_SCALED: {
-                    REAL a = R_ABS(eig);
-                    if (!(a == 0 || a != a)) eigbar = sbar * stab * (eig >= 0 ? (REAL)1 : (REAL)-1);
-                    break;
-                }
-                case REG_ERR_PLUS_STIFF: {
-                    REAL e = EEst * dt;
-                    if (!(e == 0 || e != e)) { eestbar = sbar * dt; dtbar += (double)(sbar * EEst); }
-                    if (!(eig == 0 || eig != eig)) eigbar = sbar * ((REAL)0.1f * stab);
-                    break;
-                }
-            }
-        }
-        if (eestbar != 0 && EEst > 0) {
-            /* EEst = sqrt(sum(atmp^2)/N); atmp = utilde/den; den = atol + max(|uprev|,|u|)*rtol */
-            const REAL g = eestbar / ((REAL)cnt * EEst);
-            REAL bt[8];
-            for (int i = 1; i <= 7; ++i) bt[i] = (REAL)BT_[i];
-            double dtb = 0;
-#pragma omp parallel for schedule(static) reduction(+ : dtb)
-            for (size_t e = 0; e < n; ++e) {
-                REAL a0 = R_ABS(uprev[e]), a1 = R_ABS(w->z[7][e]);
-                REAL m = a0 > a1 ? a0 : a1;
-                REAL den = R_FMA(m, rtol, atol);
-                REAL ab = g * w->atmp[e];
-                REAL utb = ab / den;
-                REAL denb = -ab * w->atmp[e] / den;
-                REAL mb = denb * rtol;
-                if (a0 > a1) uprevbar[e] += mb * (uprev[e] >= 0 ? (REAL)1 : (REAL)-1);
-                else if (a1 > a0) ubar[e] += mb * (w->z[7][e] >= 0 ? (REAL)1 : (REAL)-1);
-                else { uprevbar[e] += (REAL)0.5 * mb * (uprev[e] > 0 ? 1 : (uprev[e] < 0 ? -1 : 0));
-                       ubar[e] += (REAL)0.5 * mb * (w->z[7][e] > 0 ? 1 : (w->z[7][e] < 0 ? -1 : 0)); }
-                REAL ssum = 0;
-                for (int i = 1; i <= 7; ++i) { kbar[i][e] += dt * bt[i] * utb; ssum += bt[i] * w->k[i][e]; }
-                dtb += (double)(utb * ssum);
-            }
-            dtbar += dtb;
-        }
-        if (eigbar != 0 && c->alg == ALG_AUTO_TSIT5) {
-            /* eig = n1/n2; n1 = rms(k7-k6); n2 = rms(u - g6) */
-            double s1 = 0, s2 = 0;
-            for (size_t e = 0; e < n; ++e) { double a = (double)w->k[7][e] - w->k[6][e], b = (double)w->z[7][e] - w->z[6][e]; s1 += a * a; s2 += b * b; }
-            REAL n1 = (REAL)sqrt(s1 / (double)cnt), n2 = (REAL)sqrt(s2 / (double)cnt);
-            REAL n1b = eigbar / n2, n2b = -eigbar * n1 / (n2 * n2);
-            z6bar_extra = (REAL*)calloc(n, sizeof(REAL));
-            for (size_t e = 0; e < n; ++e) {
-                REAL a = w->k[7][e] - w->k[6][e], b = w->z[7][e] - w->z[6][e];
-                REAL ga = n1 > 0 ? n1b * a / ((REAL)cnt * n1) : (REAL)0;
-                REAL gb = n2 > 0 ? n2b * b / ((REAL)cnt * n2) : (REAL)0;
-                kbar[7][e] += ga; kbar[6][e] -= ga;
-                ubar[e] += gb; z6bar_extra[e] -= gb;
-            }
-        }
-        /* stages in reverse */
-        for (int i = 7; i >= 2; --i) {
-            REAL tb_stage = 0;
-            rhs_vjp(c, p, w->z[i], stage_time(t, dt, i), w->h[i], w->k[i], kbar[i], zbar, dp_thr, &tb_stage);
-            tbar += (double)tb_stage;
-            dtbar += (double)C_[i] * (double)tb_stage;
-            REAL* zb = zbar;
-            if (i == 7) {
-                /* z7 = u_new: total cotangent ubar + zbar */
-#pragma omp parallel for schedule(static)
-                for (size_t e = 0; e < n; ++e) ubar[e] += zbar[e];
-                zb = ubar;
-            } else if (i == 6 && z6bar_extra) {
-                for (size_t e = 0; e < n; ++e) zbar[e] += z6bar_extra[e];
-            }
-            double dtb = 0;
-#pragma omp parallel for schedule(static) reduction(+ : dtb)
-            for (size_t e = 0; e < n; ++e) {
-                REAL g = zb[e];
-                REAL ssum = 0;
-                for (int j = 1; j < i; ++j) { kbar[j][e] += dt * (REAL)A_[i][j] * g; ssum += (REAL)A_[i][j] * w->k[j][e]; }
-                uprevbar[e] += g;
-                dtb += (double)(g * ssum);
-            }
-            dtbar += dtb;
-        }
-        if (z6bar_extra) { free(z6bar_extra); }
-        /* hand over to the previous step: u_new(prev) = uprev, k7(prev) = k1 */
-        memcpy(ubar, uprevbar, sizeof(REAL) * n);
-        memcpy(k7bar_in, kbar[1], sizeof(REAL) * n);
-        if (dtbar_steps) dtbar_steps[s] = dtbar;
-        if (tbar_steps) tbar_steps[s] = tbar;
-    }
-    /* initial fsalfirst = f(u0,t0): VJP with k7bar_in */
-    rhs_eval(c, p, h->u0, (REAL)c->t0, w->k[1], h1);
-    rhs_vjp(c, p, h->u0, (REAL)c->t0, h1, w->k[1], k7bar_in, zbar, dp_thr, NULL);
-    for (size_t e = 0; e < n; ++e) dx_out[e] = ubar[e] + zbar[e];
-    for (size_t q = 0; q < h->np; ++q) { double a = 0; for (int i = 0; i < nthr; ++i) a += (double)dp_thr[i][q]; dp_out[q] = (REAL)a; }
-    for (int i = 0; i < nthr; ++i) free(dp_thr[i]);
-    free(dp_thr); ws_free(w); free(ubar); free(uprevbar);
-    for (int i = 1; i <= 7; ++i) free(kbar[i]);
-    free(zbar); free(k7bar_in); free(h1);
-    return ORC_OK;
-}
 
 int FN(sizeof_real)(void) { return (int)sizeof(REAL); }

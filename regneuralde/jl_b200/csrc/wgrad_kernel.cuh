@@ -2,28 +2,35 @@
 //
 //   dW1aug[h][d] = sum_{rec, col} delta1[rec][h][col] * [Z; t; 1][rec][d][col]      (H x (D+2))
 //   dW2aug[d][h] = sum_{rec, col} delta2[rec][d][col] * [Hact; t; 1][rec][h][col]   (D x (H+2))
-// where rec runs over every field evaluation on the tape (1 + 6*naccept records) and col
-// over the batch: a contraction of length nrec*B (~1e5 for the MNIST config), i.e. a real
-// dense GEMM instead of ~200 rank-32 updates inside the latency-bound reverse sweep.
-// The "t" and "1" rows give the time-column and bias gradients for free.
-// Replaces the weight-gradient part of Tracker's back-propagation through
-// Flux.Dense inside dudt_ (/root/reference/src/models/neural_ode.jl:120,
-// experiments/mnist_node.jl:51-54).
+// where rec runs over every field evaluation on the tape (1 + 6*naccept records) and col over the
+// batch: a contraction of length nrec*B (~1e5 for the MNIST config), i.e. a real dense GEMM
+// instead of ~200 rank-16 updates inside the latency-bound reverse sweep.  The "t" and "1" rows
+// give the time-column and bias gradients for free.
+// Replaces the weight-gradient part of Tracker's back-propagation through Flux.Dense inside dudt_
+// (/root/reference/src/models/neural_ode.jl:120, experiments/mnist_node.jl:51-54).
 //
-// Both operands are stored [tile][row][NP] (NP contiguous contraction entries per row), so a
-// 64-row x NP tile is one contiguous block.  Split-K over tiles with a deterministic two-pass
-// reduction (no atomics): partials[split][M][Naug] then a fixed-order sum.
+// Layout: both operands are stored [tile][row][NP] (NP contiguous contraction entries per row).
+// Kernel: 64x64 output tile per CTA, 64 contraction entries per pipeline stage copied straight
+// into shared memory with cp.async (double buffered, no transposition: threads own interleaved
+// rows so the k-contiguous float4 reads are bank-conflict free), 4x4 accumulators per thread.
+// Accuracy: the regulariser part of the gradient is a sum of large cancelling terms (adjacent
+// stages of one step carry +-O(10) cotangents, DESIGN.md "gradient conditioning"), so
+//   * split-K assigns CONTIGUOUS record ranges to a split (cancelling records meet early),
+//   * FP32 accumulators are flushed into FP64 every stage, partials are FP64, the final fixed-order
+//     reduction over splits is FP64 (deterministic, no atomics).
 #pragma once
 #include "common.cuh"
 
 namespace rnde {
 
 constexpr int WG_TILE = 64;
+constexpr int WG_KC = 64;            // contraction entries per stage
+constexpr int WG_LD = WG_KC + 4;     // padded row stride (floats)
 constexpr int WG_SPLITS = 24;
 
 __host__ inline size_t wgrad_workspace_floats(int D, int H) {
     const size_t a = (size_t)H * (D + 2), b = (size_t)D * (H + 2);
-    return (size_t)WG_SPLITS * (a > b ? a : b);
+    return 2 * (size_t)WG_SPLITS * (a > b ? a : b);      // doubles
 }
 
 __device__ __forceinline__ float rec_time(const StepRec* steps, float t0, int rec) {
@@ -33,103 +40,156 @@ __device__ __forceinline__ float rec_time(const StepRec* steps, float t0, int re
     return stage_time(sr.t, sr.dt, i);
 }
 
-// A: [ntiles][M][NP], Bm: [ntiles][Nrows][NP]; out partial[split][M][Naug], Naug = Nrows + 2
-__global__ void __launch_bounds__(256) wgrad_gemm_kernel(const float* __restrict__ A, int M, const float* __restrict__ Bm, int Nrows, int NP,
-                                                        int ntiles, int Q, const StepRec* __restrict__ steps, float t0, int td,
-                                                        float* __restrict__ partial) {
-    constexpr int LD = WG_TILE + 4;
-    __shared__ __align__(16) float As[32 * LD];
-    __shared__ __align__(16) float Bs[32 * LD];
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// A: [ntiles][M][NP], Bm: [ntiles][Nrows][NP]; out partial[split][M][Naug] (double), Naug = Nrows + 2
+template <int NP>
+__global__ void __launch_bounds__(256, 2) wgrad_gemm_kernel(const float* __restrict__ A, int M, const float* __restrict__ Bm, int Nrows,
+                                                           int ntiles, int Q, const StepRec* __restrict__ steps, float t0, int td,
+                                                           double* __restrict__ partial) {
+    extern __shared__ __align__(16) float wsm[];
+    float* As[2] = {wsm, wsm + 2 * WG_TILE * WG_LD};
+    float* Bs[2] = {wsm + WG_TILE * WG_LD, wsm + 3 * WG_TILE * WG_LD};
     const int tid = threadIdx.x;
-    const int tx = tid & 15, ty = tid >> 4;
+    const int tx = tid & 15, ty = tid >> 4;       // thread owns A rows ty+16i, B rows tx+16j
     const int m_base = blockIdx.x * WG_TILE, n_base = blockIdx.y * WG_TILE;
     const int Naug = Nrows + 2;
-    float acc[4][4];
+    constexpr int tps = WG_KC / NP;               // (rec,q) tiles per stage
+    // contiguous tile range of this split
+    const int per = (ntiles + gridDim.z - 1) / gridDim.z;
+    const int tile0 = blockIdx.z * per, tile1 = min(ntiles, tile0 + per);
+    const int nstage = (tile1 - tile0 + tps - 1) / tps;
+    constexpr int vpr = NP / 4;                   // float4 per row per tile
+
+    auto issue = [&](int stage, int buf) {
+        // copy rows x (tps tiles x NP) for A and B; zero-fill out-of-range rows / tiles; synthesize aug rows
+        constexpr int nvec = WG_TILE * tps * vpr;
+#pragma unroll
+        for (int e = tid; e < nvec; e += 256) {
+            const int row = e / (tps * vpr), rem = e - row * (tps * vpr);
+            const int sub = rem / vpr, k4 = rem - sub * vpr;
+            const int tt = tile0 + stage * tps + sub;
+            const int kcol = sub * NP + k4 * 4;
+            float* da = As[buf] + row * WG_LD + kcol;
+            float* db = Bs[buf] + row * WG_LD + kcol;
+            const int m = m_base + row, n = n_base + row;
+            if (tt < tile1 && m < M) cp_async16(da, A + ((size_t)tt * M + m) * NP + k4 * 4);
+            else *reinterpret_cast<float4*>(da) = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tt < tile1 && n < Nrows) cp_async16(db, Bm + ((size_t)tt * Nrows + n) * NP + k4 * 4);
+            else {
+                float v = 0.f;
+                if (tt < tile1 && n == Nrows) v = td ? rec_time(steps, t0, tt / Q) : 0.f;
+                else if (tt < tile1 && n == Nrows + 1) v = 1.f;
+                *reinterpret_cast<float4*>(db) = make_float4(v, v, v, v);
+            }
+        }
+        cp_async_commit();
+    };
+
+    double accd[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    const int vec_per_row = NP / 4;
-    const int nvec = WG_TILE * vec_per_row;
-    for (int tt = blockIdx.z; tt < ntiles; tt += gridDim.z) {
-        const float trec = td ? rec_time(steps, t0, tt / Q) : 0.f;
-        for (int e = tid; e < nvec; e += 256) {
-            const int row = e / vec_per_row, k4 = e - row * vec_per_row;
-            const int m = m_base + row;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m < M) v = __ldg(reinterpret_cast<const float4*>(A + ((size_t)tt * M + m) * NP + k4 * 4));
-            As[(k4 * 4 + 0) * LD + row] = v.x; As[(k4 * 4 + 1) * LD + row] = v.y;
-            As[(k4 * 4 + 2) * LD + row] = v.z; As[(k4 * 4 + 3) * LD + row] = v.w;
-            const int n = n_base + row;
-            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (n < Nrows) w = __ldg(reinterpret_cast<const float4*>(Bm + ((size_t)tt * Nrows + n) * NP + k4 * 4));
-            else if (n == Nrows) w = make_float4(trec, trec, trec, trec);
-            else if (n == Nrows + 1) w = make_float4(1.f, 1.f, 1.f, 1.f);
-            Bs[(k4 * 4 + 0) * LD + row] = w.x; Bs[(k4 * 4 + 1) * LD + row] = w.y;
-            Bs[(k4 * 4 + 2) * LD + row] = w.z; Bs[(k4 * 4 + 3) * LD + row] = w.w;
-        }
+        for (int j = 0; j < 4; ++j) accd[i][j] = 0.0;
+
+    if (nstage > 0) issue(0, 0);
+    for (int s = 0; s < nstage; ++s) {
+        const int buf = s & 1;
+        if (s + 1 < nstage) { issue(s + 1, buf ^ 1); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
         __syncthreads();
-#pragma unroll 8
-        for (int k = 0; k < NP; ++k) {
-            const float4 a4 = *reinterpret_cast<const float4*>(As + k * LD + ty * 4);
-            const float4 b4 = *reinterpret_cast<const float4*>(Bs + k * LD + tx * 4);
-            const float av[4] = {a4.x, a4.y, a4.z, a4.w};
-            const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        const float* ap = As[buf] + ty * WG_LD;
+        const float* bp = Bs[buf] + tx * WG_LD;
+#pragma unroll 4
+        for (int k = 0; k < WG_KC; k += 4) {
+            float4 a4[4], b4[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a4[i] = *reinterpret_cast<const float4*>(ap + i * 16 * WG_LD + k);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b4[j] = *reinterpret_cast<const float4*>(bp + j * 16 * WG_LD + k);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = rn_fmaf(av[i], bv[j], acc[i][j]);
+                for (int j = 0; j < 4; ++j) {
+                    acc[i][j] = rn_fmaf(a4[i].x, b4[j].x, acc[i][j]);
+                    acc[i][j] = rn_fmaf(a4[i].y, b4[j].y, acc[i][j]);
+                    acc[i][j] = rn_fmaf(a4[i].z, b4[j].z, acc[i][j]);
+                    acc[i][j] = rn_fmaf(a4[i].w, b4[j].w, acc[i][j]);
+                }
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) accd[i][j] += (double)acc[i][j];
         __syncthreads();
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const int m = m_base + ty * 4 + i;
+        const int m = m_base + ty + 16 * i;
         if (m >= M) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int n = n_base + tx * 4 + j;
-            if (n < Naug) partial[((size_t)blockIdx.z * M + m) * Naug + n] = acc[i][j];
+            const int n = n_base + tx + 16 * j;
+            if (n < Naug) partial[((size_t)blockIdx.z * M + m) * Naug + n] = accd[i][j];
         }
     }
 }
 
-// fixed-order sum over splits; scatter into Flux.destructure layout:
+// fixed-order FP64 sum over splits; scatter into Flux.destructure layout:
 //   outW[m + M*n] for n < Nrows (+ the time column n == Nrows when td), outb[m] from n == Nrows+1
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int nsplit, int M, int Nrows, int td, float* __restrict__ outW,
+__global__ void wgrad_reduce_kernel(const double* __restrict__ partial, int nsplit, int M, int Nrows, int td, float* __restrict__ outW,
                                     float* __restrict__ outb) {
     const int Naug = Nrows + 2;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= M * Naug) return;
     const int n = idx / M, m = idx - n * M;     // m fastest: coalesced writes of the column-major W
-    float s = 0.f;
+    double s = 0.0;
     for (int sp = 0; sp < nsplit; ++sp) s += partial[((size_t)sp * M + m) * Naug + n];
-    if (n < Nrows) outW[(size_t)M * n + m] = s;
-    else if (n == Nrows) { if (td) outW[(size_t)M * Nrows + m] = s; }
-    else outb[m] = s;
+    if (n < Nrows) outW[(size_t)M * n + m] = (float)s;
+    else if (n == Nrows) { if (td) outW[(size_t)M * Nrows + m] = (float)s; }
+    else outb[m] = (float)s;
 }
+
+constexpr size_t WG_SMEM = sizeof(float) * 4 * WG_TILE * WG_LD;
 
 // dp layout: W1 (H x (D+td)), b1 (H), W2 (D x (H+td)), b2 (D)
 static int launch_wgrad(int D, int H, int td, int nrec, int Q, int NP, int B, const float* tapeZ, const float* tapeD2, const float* tapeH,
                         const float* tapeD1, const StepRec* steps, float t0, float* ws, float* dp, cudaStream_t st, int64_t* launches) {
     (void)B;
+    typedef void (*gemm_t)(const float*, int, const float*, int, int, int, const StepRec*, float, int, double*);
+    gemm_t gemm = NP == 16 ? wgrad_gemm_kernel<16> : (NP == 32 ? wgrad_gemm_kernel<32> : wgrad_gemm_kernel<4>);
+    cudaFuncSetAttribute(gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM);
     const int ntiles = nrec * Q;
-    const int nsplit = ntiles < WG_SPLITS ? ntiles : WG_SPLITS;
+    const int tps = WG_KC / NP;
+    int nsplit = WG_SPLITS;
+    if (ntiles < nsplit * tps) nsplit = (ntiles + tps - 1) / tps;
+    if (nsplit < 1) nsplit = 1;
+    double* wsd = reinterpret_cast<double*>(ws);
     float* dW1 = dp;
     float* db1 = dW1 + (size_t)H * (D + td);
     float* dW2 = db1 + H;
     float* db2 = dW2 + (size_t)D * (H + td);
     {   // dW1aug = delta1 . [Z; t; 1]^T
         dim3 grid((H + WG_TILE - 1) / WG_TILE, (D + 2 + WG_TILE - 1) / WG_TILE, nsplit);
-        wgrad_gemm_kernel<<<grid, 256, 0, st>>>(tapeD1, H, tapeZ, D, NP, ntiles, Q, steps, t0, td, ws);
+        gemm<<<grid, 256, WG_SMEM, st>>>(tapeD1, H, tapeZ, D, ntiles, Q, steps, t0, td, wsd);
         const int tot = H * (D + 2);
-        wgrad_reduce_kernel<<<(tot + 255) / 256, 256, 0, st>>>(ws, nsplit, H, D, td, dW1, db1);
+        wgrad_reduce_kernel<<<(tot + 255) / 256, 256, 0, st>>>(wsd, nsplit, H, D, td, dW1, db1);
     }
     {   // dW2aug = delta2 . [Hact; t; 1]^T
         dim3 grid((D + WG_TILE - 1) / WG_TILE, (H + 2 + WG_TILE - 1) / WG_TILE, nsplit);
-        wgrad_gemm_kernel<<<grid, 256, 0, st>>>(tapeD2, D, tapeH, H, NP, ntiles, Q, steps, t0, td, ws);
+        gemm<<<grid, 256, WG_SMEM, st>>>(tapeD2, D, tapeH, H, ntiles, Q, steps, t0, td, wsd);
         const int tot = D * (H + 2);
-        wgrad_reduce_kernel<<<(tot + 255) / 256, 256, 0, st>>>(ws, nsplit, D, H, td, dW2, db2);
+        wgrad_reduce_kernel<<<(tot + 255) / 256, 256, 0, st>>>(wsd, nsplit, D, H, td, dW2, db2);
     }
     if (launches) *launches += 4;
     return (int)cudaGetLastError();
