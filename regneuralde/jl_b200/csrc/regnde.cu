@@ -15,6 +15,7 @@
 #include "bwd_kernel.cuh"
 #include "bwd4_kernel.cuh"
 #include "wgrad_kernel.cuh"
+#include "wgrad_tc_kernel.cuh"
 #include "head_kernel.cuh"
 
 using namespace rnde;
@@ -410,6 +411,14 @@ extern "C" int rnde_backward(rnde_handle* h, const float* du_dev, const float* d
     if (rc != RNDE_OK) return rc;
     // parameter gradients: two batched contractions over (record, column) -- see wgrad_kernel.cuh
     const int nrec = 1 + 6 * s.naccept;
+    // tensor-core (tcgen05 3xTF32) contraction for the 16-column tape layout; RNDE_WGRAD_FFMA=1 selects the FFMA kernel
+    static const bool force_ffma = getenv("RNDE_WGRAD_FFMA") != nullptr;
+    if (h->NP == 16 && !force_ffma) {
+        rc = launch_wgrad_tc(h->cfg.state_dim, h->cfg.hidden_dim, h->cfg.time_dep ? 1 : 0, nrec, h->Q, h->tapeZ, h->tapeK, h->tapeH, h->tapeD1,
+                             h->steps, h->cfg.t0, h->wg_ws, dp_dev, st, &h->launches);
+        if (rc != 0) return set_err(h, RNDE_ERR_CUDA, std::string("wgrad (tcgen05) launch: ") + cudaGetErrorString((cudaError_t)rc));
+        return RNDE_OK;
+    }
     rc = launch_wgrad(h->cfg.state_dim, h->cfg.hidden_dim, h->cfg.time_dep ? 1 : 0, nrec, h->Q, h->NP, h->cfg.batch,
                       h->tapeZ, h->tapeK, h->tapeH, h->tapeD1, h->steps, h->cfg.t0, h->wg_ws, dp_dev, st, &h->launches);
     if (rc != 0) return set_err(h, RNDE_ERR_CUDA, std::string("wgrad launch: ") + cudaGetErrorString((cudaError_t)rc));

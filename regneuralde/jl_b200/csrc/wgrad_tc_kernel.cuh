@@ -1,0 +1,284 @@
+// wgrad_tc_kernel.cuh -- the weight-gradient contractions on the 5th-gen tensor cores (tcgen05),
+// Float32 accuracy preserved by the 3xTF32 split  a*b ~= ah*bh + ah*bl + al*bh  (north_star item 2:
+// "tensor cores only where batch x hidden makes a real dense contraction": here the contraction
+// length is nrec*B ~ 1e5).  Same operands, ordering and FP64 partial sums as wgrad_kernel.cuh.
+//
+// One CTA = one 128 x 128 output tile x one contiguous range of the contraction (split-K).
+// Warp roles (416 threads):
+//   warps 0-7  load + split: cp.async the raw FP32 operand chunks of a stage (32 contraction entries)
+//              straight into the UMMA K-major no-swizzle core-matrix layout, then write the low parts
+//              lo = x - tf32_trunc(x) next to them (the tensor core itself truncates the raw tile to
+//              its high part), fence.proxy.async, arrive on ready[stage].
+//   warp 8     one elected lane issues 4 K-blocks x 3 tcgen05.mma.kind::tf32 (M128 N128 K8) per stage
+//              into a TMEM accumulator, tcgen05.commit -> empty[stage]; every WGT_FLUSH stages the
+//              accumulator buffer is committed to the epilogue and the other TMEM buffer is used.
+//   warps 9-12 epilogue: tcgen05.ld the 128 x 128 FP32 accumulator (lane = output row) and add it
+//              into the CTA's private FP64 partial tile in global memory (exclusive owner: plain
+//              read-modify-write, deterministic), release the TMEM buffer.
+//              [now: every chunk is stored to its own FP32 slot; the FP64 summation over
+//               (split, chunk) happens in the fixed-order reduce kernel -- no read-modify-write]
+// Shared memory: 3 stages x (A_hi, A_lo, B_hi, B_lo) x 16 KB = 192 KB.  TMEM: 2 x 128 columns.
+#pragma once
+#include "common.cuh"
+#include "fwd4_kernel.cuh"      // mbarrier wrappers
+#include "wgrad_kernel.cuh"     // tile_of, rec_time, cp_async helpers
+
+namespace rnde {
+
+constexpr int WGT_M = 128, WGT_N = 128;
+constexpr int WGT_KC = 32;                 // contraction entries per stage (4 UMMA K-blocks of 8)
+constexpr int WGT_STAGES = 3;
+constexpr int WGT_FLUSH_MIN = 16;          // stages per FP32 accumulation chunk (>= 512 entries)
+constexpr int WGT_MAXCHUNK = 16;           // chunks per split (bounds the partial workspace)
+constexpr int WGT_LOADERS = 256;
+constexpr int WGT_THREADS = 32 * (8 + 1 + 4);
+constexpr int WGT_PART_BYTES = 128 * WGT_KC * 4;                  // one operand part of a stage: 16 KB
+constexpr int WGT_STAGE_BYTES = 4 * WGT_PART_BYTES;               // A_hi, A_lo, B_hi, B_lo
+constexpr size_t WGT_SMEM = (size_t)WGT_STAGES * WGT_STAGE_BYTES + 256;
+constexpr int WGT_SPLITS = 21;             // 7 tiles x 21 splits = 147 CTAs: one wave on 148 SMs
+
+// ---- tcgen05 wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, SWIZZLE_NONE canonical layout: 8-row x 16-byte core matrices; K-adjacent core matrices
+// LBO bytes apart, 8-row groups SBO bytes apart (cute/arch/mma_sm100_desc.hpp SmemDescriptor).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;        // descriptor version 1 (Blackwell)
+    return d;                       // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
+}
+__device__ __forceinline__ void mbar_arrive_local(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+
+// A: [tiles][M][16], Bm: [tiles][Nrows][16] (physical tile = rec*Q + q); partial: [split][chunk][Naug][M] floats
+__global__ void __launch_bounds__(WGT_THREADS, 1) wgrad_tc_kernel(const float* __restrict__ A, int M, const float* __restrict__ Bm, int Nrows,
+                                                                 int ntiles, int Q, const StepRec* __restrict__ steps, float t0, int td,
+                                                                 int flush, float* __restrict__ partial) {
+    constexpr int NP = 16;
+    constexpr int TPS = WGT_KC / NP;              // tiles per stage = 2
+    extern __shared__ __align__(1024) unsigned char tsm[];
+    const uint32_t sbase = smem_u32(tsm);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tsm + (size_t)WGT_STAGES * WGT_STAGE_BYTES);
+    const uint32_t bar0 = sbase + WGT_STAGES * WGT_STAGE_BYTES;
+    auto bar_ready = [&](int s) { return bar0 + 8 * s; };
+    auto bar_empty = [&](int s) { return bar0 + 8 * (WGT_STAGES + s); };
+    auto bar_accfull = [&](int a) { return bar0 + 8 * (2 * WGT_STAGES + a); };
+    auto bar_accempty = [&](int a) { return bar0 + 8 * (2 * WGT_STAGES + 2 + a); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WGT_STAGES + 4);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m_base = blockIdx.x * WGT_M, n_base = blockIdx.y * WGT_N;
+    const int Naug = Nrows + 2;
+    const int per = (ntiles + gridDim.z - 1) / gridDim.z;
+    const int tile0 = blockIdx.z * per, tile1 = min(ntiles, tile0 + per);
+    const int nstage = (tile1 - tile0 + TPS - 1) / TPS;
+    const int nchunk = (nstage + flush - 1) / flush;
+
+    if (tid == 0) {
+        for (int s = 0; s < WGT_STAGES; ++s) { mbar_init(bar_ready(s), WGT_LOADERS); mbar_init(bar_empty(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_accfull(a), 1); mbar_init(bar_accempty(a), 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {        // TMEM allocation: 256 columns (two 128-column FP32 accumulators)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 8) {
+        // ================= loaders / splitters =================
+        // warp w owns (operand = w>>2, tile-in-stage = (w>>1)&1, row groups [8*(w&1), 8*(w&1)+8)); inside a row group
+        // lane -> (row r8 = lane & 7, 16-byte chunk k4 = lane >> 3): the warp reads 8 rows x 64 B = 512 contiguous bytes
+        // of the tape and writes four conflict-free 128-byte core-matrix rows.  No index arithmetic in the loop.
+        const int r8 = lane & 7, k4 = lane >> 3;
+        const int opnd = warp >> 2, sub = (warp >> 1) & 1, rg0 = (warp & 1) * 8;
+        const float* gsrc = opnd ? Bm : A;
+        const int nrows_src = opnd ? Nrows : M;                  // rows that exist in the tape operand
+        const int row_base = (opnd ? n_base : m_base) + rg0 * 8 + r8;
+        const uint32_t lane_dst = (uint32_t)((opnd ? 2 * WGT_PART_BYTES : 0) + rg0 * 1024 + (sub * 4 + k4) * 128 + r8 * 16);
+        auto issue = [&](int g) {
+            unsigned char* stage = tsm + (size_t)(g % WGT_STAGES) * WGT_STAGE_BYTES;
+            const int tt = tile0 + g * TPS + sub;
+            const bool live = tt < tile1;
+            int rec = 0, q = 0;
+            if (live) tile_of(tt, Q, rec, q);
+            const float* src = gsrc + (((size_t)rec * Q + q) * nrows_src + row_base) * NP + k4 * 4;
+            float augv = 0.f, onev = 0.f;
+            if (opnd && live) { augv = td ? rec_time(steps, t0, rec) : 0.f; onev = 1.f; }
+            unsigned char* dst = stage + lane_dst;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int row = row_base + i * 8;
+                if (live && row < nrows_src) cp_async16(dst + i * 1024, src + (size_t)i * 8 * NP);
+                else {
+                    float v = 0.f;
+                    if (opnd && row == Nrows) v = augv;
+                    else if (opnd && row == Nrows + 1) v = onev;
+                    *reinterpret_cast<float4*>(dst + i * 1024) = make_float4(v, v, v, v);
+                }
+            }
+            cp_async_commit();
+        };
+        auto split = [&](int g) {
+            unsigned char* hi = tsm + (size_t)(g % WGT_STAGES) * WGT_STAGE_BYTES + lane_dst;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 x = *reinterpret_cast<const float4*>(hi + i * 1024);
+                float4 lo;
+                lo.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+                lo.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+                lo.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+                lo.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+                *reinterpret_cast<float4*>(hi + i * 1024 + WGT_PART_BYTES) = lo;
+            }
+        };
+        // software pipeline: loads of stage g+1 are in flight while stage g is split and published
+        if (nstage > 0) issue(0);
+        for (int g = 0; g < nstage; ++g) {
+            if (g + 1 < nstage) {
+                const int bn = (g + 1) % WGT_STAGES;
+                if (g + 1 >= WGT_STAGES) mbar_wait(bar_empty(bn), (uint32_t)(((g + 1) / WGT_STAGES - 1) & 1));
+                issue(g + 1);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            split(g);        // each lane splits exactly the chunks it loaded itself
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive_local(bar_ready(g % WGT_STAGES));
+        }
+    } else if (warp == 8) {
+        // ================= MMA issuer =================
+        // instruction descriptor: D=F32, A=B=TF32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(WGT_N >> 3) << 17) | ((uint32_t)(WGT_M >> 4) << 24);
+        for (int g = 0; g < nstage; ++g) {
+            const int b = g % WGT_STAGES;
+            const int chunk = g / flush, acc = chunk & 1;
+            const bool first_in_chunk = (g % flush) == 0;
+            if (first_in_chunk && chunk >= 2) mbar_wait(bar_accempty(acc), (uint32_t)((chunk / 2 - 1) & 1));
+            mbar_wait(bar_ready(b), (uint32_t)((g / WGT_STAGES) & 1));
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t st = sbase + b * WGT_STAGE_BYTES;
+                const uint32_t d_tmem = tmem_base + acc * 128;
+#pragma unroll
+                for (int kb = 0; kb < WGT_KC / 8; ++kb) {
+                    const uint64_t a_hi = umma_desc(st + kb * 256, 128, 1024);
+                    const uint64_t a_lo = umma_desc(st + WGT_PART_BYTES + kb * 256, 128, 1024);
+                    const uint64_t b_hi = umma_desc(st + 2 * WGT_PART_BYTES + kb * 256, 128, 1024);
+                    const uint64_t b_lo = umma_desc(st + 3 * WGT_PART_BYTES + kb * 256, 128, 1024);
+                    tc_mma_tf32(d_tmem, a_hi, b_hi, idesc, (first_in_chunk && kb == 0) ? 0u : 1u);
+                    tc_mma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
+                    tc_mma_tf32(d_tmem, a_lo, b_hi, idesc, 1u);
+                }
+                tc_commit(bar_empty(b));                                  // stage buffer free when these MMAs retire
+                if ((g % flush) == flush - 1 || g == nstage - 1) tc_commit(bar_accfull(acc));
+            }
+            __syncwarp();
+        }
+    } else {
+        // ================= epilogue: TMEM -> FP64 partial tile in global memory =================
+        const int quad = warp & 3;                    // TMEM lanes [32*quad, 32*quad+32) are this warp's
+        const int row = quad * 32 + lane;
+        const int m = m_base + row;
+        for (int chunk = 0; chunk < WGT_MAXCHUNK; ++chunk) {
+            float* prow = partial + ((size_t)blockIdx.z * WGT_MAXCHUNK + chunk) * Naug * M;     // [n][m], m fastest
+            if (chunk >= nchunk) {      // unused slots are zeroed so the reduce needs no bookkeeping
+                if (m < M) for (int n = n_base; n < min(n_base + WGT_N, Naug); ++n) prow[(size_t)n * M + m] = 0.f;
+                continue;
+            }
+            const int acc = chunk & 1;
+            mbar_wait(bar_accfull(acc), (uint32_t)((chunk / 2) & 1));
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < WGT_N / 16; ++c) {
+                uint32_t v[16];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 128 + c * 16);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                      "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                    : "r"(taddr) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (m < M) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int n = n_base + c * 16 + j;
+                        if (n < Naug) prow[(size_t)n * M + m] = __uint_as_float(v[j]);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive_local(bar_accempty(acc));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
+    }
+}
+
+// fixed-order FP64 sum over splits of the [split][n][m] partials; scatter into Flux.destructure layout
+__global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, int nslots, int M, int Nrows, int td, float* __restrict__ outW,
+                                       float* __restrict__ outb) {
+    const int Naug = Nrows + 2;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M * Naug) return;
+    const int n = idx / M, m = idx - n * M;
+    double s = 0.0;
+    for (int sp = 0; sp < nslots; ++sp) s += (double)partial[((size_t)sp * Naug + n) * M + m];
+    if (n < Nrows) outW[(size_t)M * n + m] = (float)s;
+    else if (n == Nrows) { if (td) outW[(size_t)M * Nrows + m] = (float)s; }
+    else outb[m] = (float)s;
+}
+
+static int launch_wgrad_tc(int D, int H, int td, int nrec, int Q, const float* tapeZ, const float* tapeD2, const float* tapeH,
+                           const float* tapeD1, const StepRec* steps, float t0, float* ws, float* dp, cudaStream_t st, int64_t* launches) {
+    cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WGT_SMEM);
+    const int ntiles = nrec * Q;
+    int nsplit = WGT_SPLITS;
+    if (ntiles < nsplit * 2) nsplit = (ntiles + 1) / 2;
+    if (nsplit < 1) nsplit = 1;
+    const int per = (ntiles + nsplit - 1) / nsplit, nstage = (per + 1) / 2;
+    int flush = (nstage + WGT_MAXCHUNK - 1) / WGT_MAXCHUNK;
+    if (flush < WGT_FLUSH_MIN) flush = WGT_FLUSH_MIN;
+    float* wsd = ws;
+    const int nslots = nsplit * WGT_MAXCHUNK;
+    float* dW1 = dp;
+    float* db1 = dW1 + (size_t)H * (D + td);
+    float* dW2 = db1 + H;
+    float* db2 = dW2 + (size_t)D * (H + td);
+    {   // dW1aug = delta1 . [Z; t; 1]^T      (M = H, N = D + 2)
+        dim3 grid((H + WGT_M - 1) / WGT_M, (D + 2 + WGT_N - 1) / WGT_N, nsplit);
+        wgrad_tc_kernel<<<grid, WGT_THREADS, WGT_SMEM, st>>>(tapeD1, H, tapeZ, D, ntiles, Q, steps, t0, td, flush, wsd);
+        const int tot = H * (D + 2);
+        wgrad_tc_reduce_kernel<<<(tot + 255) / 256, 256, 0, st>>>(wsd, nslots, H, D, td, dW1, db1);
+    }
+    {   // dW2aug = delta2 . [Hact; t; 1]^T   (M = D, N = H + 2)
+        dim3 grid((D + WGT_M - 1) / WGT_M, (H + 2 + WGT_N - 1) / WGT_N, nsplit);
+        wgrad_tc_kernel<<<grid, WGT_THREADS, WGT_SMEM, st>>>(tapeD2, D, tapeH, H, ntiles, Q, steps, t0, td, flush, wsd);
+        const int tot = D * (H + 2);
+        wgrad_tc_reduce_kernel<<<(tot + 255) / 256, 256, 0, st>>>(wsd, nslots, D, H, td, dW2, db2);
+    }
+    if (launches) *launches += 4;
+    return (int)cudaGetLastError();
+}
+
+}  // namespace rnde

@@ -216,6 +216,8 @@ if __name__ == "__main__":
                 compare_bwd("bwd mnist B=24 cluster4 stiff identity-out", 784, 100, 24, 0, 1, 2, VAR["cluster4"])
                 compare_bwd("bwd mnist B=512 cluster4", 784, 100, 512, 1, 0, 1, VAR["cluster4"])
                 timing(512, VAR["cluster4"], reps=4)
+            elif cs == "prof4":
+                timing(512, VAR["cluster4"], reps=2)
             elif cs == "timing":
                 timing(512, VAR["cluster"])
                 timing(512, VAR["stream"], reps=2)
