@@ -157,6 +157,16 @@ int rnde_head_loss_grad(rnde_handle* h, const float* u_dev, const float* p3_dev,
 int rnde_opt_update(rnde_handle* h, float* p_dev, const float* g_dev, float* v_dev, int64_t n, float inv_decay_scale, float eta, float rho,
                     void* stream);
 
+/* Reference-exact data-parallel mode (RNDE_DIST_EXACT): all ranks take the step sequence of the single batched
+ * solve over the global batch.  The per-column sums of squares of every norm are written by each rank straight into
+ * every peer's exchange buffer (CUDA IPC peer memory over NVLink) from inside the persistent kernel, followed by a
+ * flag barrier; the fold over columns uses the GLOBAL column order, so results are bit-identical to one GPU.
+ * Protocol: every rank calls rnde_dist_export, the 64-byte handles are all-gathered by the host layer
+ * (torch.distributed / MPI / files), then every rank calls rnde_dist_import with all of them (rank order). */
+#define RNDE_IPC_HANDLE_BYTES 64
+int rnde_dist_export(rnde_handle* h, void* ipc_handle_out);
+int rnde_dist_import(rnde_handle* h, const void* ipc_handles, int32_t nranks);
+
 /* introspection for tests: per accepted step (t, dt, EEst, eigen_est), host arrays of length naccept */
 int rnde_get_steps(rnde_handle* h, float* t, float* dt, float* eest, float* eig, int32_t cap);
 

@@ -51,9 +51,12 @@ class ClassifierNODE:
 
     # ---- fused training-step path -------------------------------------------------
     def loss_and_gradient(self, x: torch.Tensor, y_onehot: torch.Tensor, *, lam: float = 1.0e2, func: Optional[SaveFunc] = None,
-                          agg: str = "mean", tspan=None):
+                          agg: str = "mean", tspan=None, ce_scale: float = 1.0, reg_scale: float = 1.0):
         """loss = logitcrossentropy(model(x), y) + λ*agg(sv.saveval) and its gradient w.r.t. (p2, p3).
-        Returns dict(loss, ce, reg, nfe, naccept, g2, g3, logits)."""
+        Returns dict(loss, ce, reg, nfe, naccept, g2, g3, logits).
+        ce_scale / reg_scale: weights of this rank's shard in a data-parallel global loss (exact mode: the cross-entropy
+        mean runs over world*B samples -> ce_scale = 1/world; the regulariser is global, every rank back-propagates the
+        full cotangent through its own columns -> reg_scale = 1; gradients are then SUMMED over ranks)."""
         node = self.node
         D, Cn = node.model.D, self.n_classes
         x = self.preode(x) if self.preode is not None else x
@@ -72,7 +75,7 @@ class ClassifierNODE:
         hd.check(lib.rnde_forward(hd.h, xbuf.data_ptr(), self.p2.data_ptr(), ws["u"].data_ptr(), ws["sv"].data_ptr(), C.byref(st), stream),
                  "rnde_forward")
         node.last_stats = st
-        hd.check(lib.rnde_head_loss_grad(hd.h, ws["u"].data_ptr(), self.p3.data_ptr(), ybuf.data_ptr(), Cn, 1.0, ws["loss"].data_ptr(),
+        hd.check(lib.rnde_head_loss_grad(hd.h, ws["u"].data_ptr(), self.p3.data_ptr(), ybuf.data_ptr(), Cn, float(ce_scale), ws["loss"].data_ptr(),
                                          ws["logits"].data_ptr(), ws["du"].data_ptr(), ws["g3"].data_ptr(), stream), "rnde_head_loss_grad")
         n_saved = int(st.n_saved)
         dsv = ws["dsv"]
@@ -80,14 +83,14 @@ class ClassifierNODE:
         if n_saved > 0:
             sv = ws["sv"][:n_saved]
             if agg == "mean":           # mnist_node.jl:69,98
-                dsv.zero_(); dsv[:n_saved] = lam / n_saved
+                dsv.zero_(); dsv[:n_saved] = reg_scale * lam / n_saved
                 reg = lam * sv.mean()
             elif agg == "maximum":      # mnist_node.jl:80
                 k = int(torch.argmax(sv))
-                dsv.zero_(); dsv[k] = lam
+                dsv.zero_(); dsv[k] = reg_scale * lam
                 reg = lam * sv[k]
             elif agg == "sum":          # test/test_node.jl:55
-                dsv.zero_(); dsv[:n_saved] = lam
+                dsv.zero_(); dsv[:n_saved] = reg_scale * lam
                 reg = lam * sv.sum()
             else:
                 raise ValueError(agg)

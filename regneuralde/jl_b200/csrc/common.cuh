@@ -41,6 +41,10 @@ struct KParams {
     float* scal;            // per-step scalar adjoints (dtbar, tbar) [2*tape_cap]
     int nsteps;
     long long* dbg;         // optional phase timeline (clock64 stamps), developer diagnostics only
+    // reference-exact data parallel mode: every rank's exchange buffer (IPC-mapped peer memory over NVLink)
+    int nranks, rank;
+    unsigned long long peers[8];    // base of rank r's exchange buffer: [colsum 2x3xstride floats][flags 64 u32][seq u32]
+    unsigned int flag_off;          // offset (in 4-byte words) of the flag array inside an exchange buffer
 };
 
 // ---- small PTX wrappers ----------------------------------------------------
@@ -84,6 +88,35 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned nblocks
     }
     gen += 1;
     __syncthreads();
+}
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Cross-GPU barrier of the exact data-parallel mode.  Called after the local grid barrier: block 0 publishes
+// "rank r reached norm `seq`" into every peer's flag array (peer memory, st.release.sys makes this rank's column
+// sums -- already written into the peers' buffers -- visible first); every CTA then waits for all ranks' flags.
+__device__ __forceinline__ void xrank_barrier(const KParams& P, unsigned seq) {
+    if (P.nranks <= 1) return;
+    if (threadIdx.x == 0) {
+        if (blockIdx.x == 0) {
+            __threadfence_system();
+            for (int r = 0; r < P.nranks; ++r)
+                st_release_sys(reinterpret_cast<unsigned*>(P.peers[r]) + P.flag_off + P.rank, seq);
+        }
+        const unsigned* mine = reinterpret_cast<const unsigned*>(P.peers[P.rank]) + P.flag_off;
+        for (int r = 0; r < P.nranks; ++r)
+            while ((int)(ld_acquire_sys(mine + r) - seq) < 0) { }
+    }
+    __syncthreads();
+}
+// write one per-column sum into every rank's exchange buffer (own buffer included)
+__device__ __forceinline__ void publish_colsum(const KParams& P, size_t word_off, float v) {
+    if (P.nranks <= 1) { P.colsum[word_off] = v; return; }
+    for (int r = 0; r < P.nranks; ++r) reinterpret_cast<float*>(P.peers[r])[word_off] = v;
 }
 
 __device__ __forceinline__ float act_apply(int act, float s) { return act == RNDE_ACT_TANH ? canon_tanhf(s) : s; }

@@ -208,6 +208,9 @@ __global__ void __launch_bounds__(V2_NT, 1) fwd4_kernel(const KParams P) {
     cluster_sync_all();     // weights staged, mbarriers initialised and visible cluster-wide
 
     unsigned norm_seq = 0, bar_gen = 0;
+    // exact mode: norms are numbered consecutively across launches (same count on every rank)
+    unsigned* xseq_ptr = reinterpret_cast<unsigned*>(P.peers[P.rank]) + P.flag_off + 32;
+    const unsigned xseq_base = (P.nranks > 1) ? *xseq_ptr : 0u;
     uint32_t ev_parity = 0;
     int dbg_n = 0;
     auto mark = [&](int id) {
@@ -398,9 +401,11 @@ __global__ void __launch_bounds__(V2_NT, 1) fwd4_kernel(const KParams P) {
             float tot = sCP[(v * G) * NP + n];
 #pragma unroll
             for (int c = 1; c < G; ++c) tot = tot + sCP[(v * G + c) * NP + n];
-            if (n < Nloc) gcol[(size_t)v * P.colsum_stride + P.col_offset + q * NP + n] = tot;
+            if (n < Nloc) publish_colsum(P, (size_t)slot * 3 * P.colsum_stride + (size_t)v * P.colsum_stride + P.col_offset + q * NP + n, tot);
+            if (P.nranks > 1) __threadfence_system();
         }
         grid_barrier(P.bar, gridDim.x, bar_gen);
+        xrank_barrier(P, xseq_base + norm_seq + 1u);
         const int warp = tid >> 5, lane = tid & 31;
         if (warp < NV) {
             const float* g = gcol + (size_t)warp * P.colsum_stride;
@@ -649,6 +654,7 @@ __global__ void __launch_bounds__(V2_NT, 1) fwd4_kernel(const KParams P) {
         s.nf = ctl->nf; s.naccept = ctl->naccept; s.nreject = ctl->nreject; s.n_saved = ctl->n_saved; s.retcode = ctl->retcode;
         s.t_final = ctl->t; s.dt_last = ctl->dt_last; s.dt_init = ctl->dt_init;
         *P.stats = s;
+        if (P.nranks > 1) *xseq_ptr = xseq_base + norm_seq;
     }
     cluster_sync_all();
 }

@@ -88,7 +88,7 @@ __device__ __forceinline__ float combine_blocks(int n, F part) {
 // folded by 32 interleaved chains + xor butterfly.  Identical to oracle col_sumsq/cols_total.
 template <int G, int NP, int NV, int NT, class F>
 __device__ __forceinline__ void grid_rms(const KParams& P, const SmemLayout& L, float* smem, int rank, int q, int Rloc, int Nloc,
-                                         unsigned& norm_seq, unsigned& bar_gen, F val, float* out) {
+                                         unsigned& norm_seq, unsigned& bar_gen, F val, float* out, unsigned xseq_base = 0) {
     const int tid = threadIdx.x;
     float* sRed = smem + L.oRed;
     float* sCP = smem + L.oCP;
@@ -133,7 +133,8 @@ __device__ __forceinline__ void grid_rms(const KParams& P, const SmemLayout& L, 
         if constexpr (G > 1) {
             st_cluster_f32(mapa_u32(smem_u32(sCP + (v * G + rank) * NP + n), 0), tot);
         } else {
-            if (n < Nloc) gcol[(size_t)v * P.colsum_stride + P.col_offset + q * NP + n] = tot;
+            if (n < Nloc) publish_colsum(P, (size_t)slot * 3 * P.colsum_stride + (size_t)v * P.colsum_stride + P.col_offset + q * NP + n, tot);
+            if (P.nranks > 1) __threadfence_system();
         }
     }
     if constexpr (G > 1) {
@@ -141,10 +142,12 @@ __device__ __forceinline__ void grid_rms(const KParams& P, const SmemLayout& L, 
         if (rank == 0 && tid < NP * NV) {
             const int n = tid % NP, v = tid / NP;
             const float tot = combine_blocks(G, [&](int c) { return sCP[(v * G + c) * NP + n]; });
-            if (n < Nloc) gcol[(size_t)v * P.colsum_stride + P.col_offset + q * NP + n] = tot;
+            if (n < Nloc) publish_colsum(P, (size_t)slot * 3 * P.colsum_stride + (size_t)v * P.colsum_stride + P.col_offset + q * NP + n, tot);
+            if (P.nranks > 1) __threadfence_system();
         }
     }
     grid_barrier(P.bar, gridDim.x, bar_gen);
+    xrank_barrier(P, xseq_base + norm_seq + 1u);
     const int warp = tid >> 5, lane = tid & 31;
     if (warp < NV) {
         const float* g = gcol + (size_t)warp * P.colsum_stride;
@@ -256,6 +259,8 @@ __global__ void __launch_bounds__(NT, 1) fwd_kernel(const KParams P) {
     if constexpr (G > 1) cluster_sync_all();   // peers' shared memory is live before any DSMEM store
 
     unsigned norm_seq = 0, bar_gen = 0;
+    unsigned* xseq_ptr = reinterpret_cast<unsigned*>(P.peers[P.rank]) + P.flag_off + 32;
+    const unsigned xseq_base = (P.nranks > 1) ? *xseq_ptr : 0u;
 
     // ---- one evaluation of the vector field: sOut = f(sIn, tstage) --------
     auto rhs = [&](const float* sIn, float* sOut, const float tstage, const int rec) {
@@ -424,7 +429,7 @@ __global__ void __launch_bounds__(NT, 1) fwd_kernel(const KParams P) {
                 const float sk = rn_fmaf(fabsf(u), P.reltol, P.abstol);
                 o[0] = rn_divf(u, sk);
                 o[1] = rn_divf(K(1)[r * NP + n], sk);
-            }, d01);
+            }, d01, xseq_base);
         const float d0 = d01[0], d1 = d01[1];
         float dt0;
         if (d0 < (float)1e-5 || d1 < (float)1e-5) dt0 = (float)1e-6;
@@ -439,7 +444,7 @@ __global__ void __launch_bounds__(NT, 1) fwd_kernel(const KParams P) {
                 const float u = sU[r * NP + n];
                 const float sk = rn_fmaf(fabsf(u), P.reltol, P.abstol);
                 o[0] = rn_divf(K(2)[r * NP + n] - K(1)[r * NP + n], sk);
-            }, d2v);
+            }, d2v, xseq_base);
         if (tid == 0) {
             const float d2 = rn_divf(d2v[0], dt0);
             const float md = d1 > d2 ? d1 : d2;
@@ -528,13 +533,13 @@ __global__ void __launch_bounds__(NT, 1) fwd_kernel(const KParams P) {
                     o[0] = K(7)[e] - K(6)[e];
                     o[1] = sZ[e] - combo_val(6, dt, a2, e);
                     o[2] = atmp_val(r, n);
-                }, o3);
+                }, o3, xseq_base);
             eig = rn_divf(o3[0], o3[1]); en1 = o3[0]; en2 = o3[1];
             EEst = o3[2];
         } else {
             float o1[1];
             grid_rms<G, NP, 1, NT>(P, L, smem, rank, q, Rloc, Nloc, norm_seq, bar_gen,
-                [&](int r, int n, float* o) { o[0] = atmp_val(r, n); }, o1);
+                [&](int r, int n, float* o) { o[0] = atmp_val(r, n); }, o1, xseq_base);
             EEst = o1[0];
         }
         if (tid == 0) {   // loopfooter!
@@ -597,6 +602,7 @@ __global__ void __launch_bounds__(NT, 1) fwd_kernel(const KParams P) {
         s.nf = ctl->nf; s.naccept = ctl->naccept; s.nreject = ctl->nreject; s.n_saved = ctl->n_saved; s.retcode = ctl->retcode;
         s.t_final = ctl->t; s.dt_last = ctl->dt_last; s.dt_init = ctl->dt_init;
         *P.stats = s;
+        if (P.nranks > 1) *xseq_ptr = xseq_base + norm_seq;
     }
     if constexpr (G > 1) cluster_sync_all();   // no CTA exits while peers may still address its shared memory
 }

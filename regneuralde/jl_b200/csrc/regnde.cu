@@ -28,7 +28,10 @@ struct rnde_handle {
     size_t smem_fwd = 0, smem_bwd = 0;
     int64_t np = 0;
     // device workspace
-    float* colsum = nullptr; int colsum_stride = 0;
+    float* colsum = nullptr; int colsum_stride = 0;     // exchange buffer: [colsum 2x3xstride][flags 64][seq...]
+    unsigned long long peers[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bool peers_open[8] = {false, false, false, false, false, false, false, false};
+    bool dist_ready = false;
     unsigned int* bar = nullptr;
     StepRec* steps = nullptr;
     DevStats* stats = nullptr;
@@ -170,6 +173,7 @@ static size_t smem_bytes_bwd(int variant, int D, int H, int R, int HS, int kbloc
 }
 
 static void free_all(rnde_handle* h) {
+    for (int i = 0; i < 8; ++i) if (h->peers_open[i]) cudaIpcCloseMemHandle((void*)h->peers[i]);
     cudaFree(h->colsum); cudaFree(h->bar); cudaFree(h->steps); cudaFree(h->stats);
     cudaFree(h->tapeZ); cudaFree(h->tapeK); cudaFree(h->tapeH); cudaFree(h->tapeD1); cudaFree(h->wg_ws); cudaFree(h->scal); cudaFree(h->saveval_int);
     cudaFree(h->dtile); cudaFree(h->head_ws); cudaFree(h->dbg);
@@ -247,14 +251,16 @@ extern "C" int rnde_create(const rnde_config* cfg, rnde_handle** out) {
     if (cfg->act_hidden < 0 || cfg->act_hidden > 1 || cfg->act_out < 0 || cfg->act_out > 1) return RNDE_ERR_ARG;
     if (cfg->reg_kind < 0 || cfg->reg_kind > RNDE_REG_ERR_PLUS_STIFF || cfg->alg < 0 || cfg->alg > 1) return RNDE_ERR_ARG;
     if (!(cfg->t1 > cfg->t0) || !(cfg->abstol > 0.f) || !(cfg->reltol > 0.f)) return RNDE_ERR_ARG;
-    if (cfg->dist_mode != RNDE_DIST_SINGLE && cfg->dist_mode != RNDE_DIST_INDEPENDENT) return RNDE_ERR_UNSUPPORTED;
+    if (cfg->dist_mode < RNDE_DIST_SINGLE || cfg->dist_mode > RNDE_DIST_INDEPENDENT) return RNDE_ERR_ARG;
+    if (cfg->dist_mode == RNDE_DIST_EXACT && (cfg->nranks < 1 || cfg->nranks > 8 || cfg->rank < 0 || cfg->rank >= cfg->nranks)) return RNDE_ERR_ARG;
     if (rnde_device_count() <= 0) return RNDE_ERR_CUDA;
     rnde_handle* h = new rnde_handle();
     h->cfg = *cfg;
     if (h->cfg.max_steps <= 0) h->cfg.max_steps = 1000000;
     if (h->cfg.tape_capacity <= 0) h->cfg.tape_capacity = 256;
     if (h->cfg.dtmin <= 0.f) h->cfg.dtmin = 1e-10f;
-    if (h->cfg.global_batch <= 0) h->cfg.global_batch = h->cfg.batch;
+    if (h->cfg.dist_mode != RNDE_DIST_EXACT) { h->cfg.global_batch = h->cfg.batch; h->cfg.nranks = 1; h->cfg.rank = 0; }
+    else h->cfg.global_batch = (int64_t)h->cfg.batch * h->cfg.nranks;     // equal shards
     h->kblock = cfg->kblock > 0 ? std::min(cfg->kblock, cfg->state_dim) : rnde_default_kblock(cfg);
     h->np = rnde_num_params(cfg);
     cudaDeviceProp prop;
@@ -285,7 +291,11 @@ extern "C" int rnde_create(const rnde_config* cfg, rnde_handle** out) {
     const int D = c.state_dim, H = c.hidden_dim;
     h->colsum_stride = round_up((int)c.global_batch, 32);
     auto fail = [&](const char* what) { h->err = what; free_all(h); delete h; return RNDE_ERR_CUDA; };
-    if (cudaMalloc(&h->colsum, sizeof(float) * 2 * 3 * h->colsum_stride) != cudaSuccess) return fail("cudaMalloc colsum");
+    const size_t xwords = (size_t)2 * 3 * h->colsum_stride + 128;
+    if (cudaMalloc(&h->colsum, sizeof(float) * xwords) != cudaSuccess) return fail("cudaMalloc colsum");
+    if (cudaMemset(h->colsum, 0, sizeof(float) * xwords) != cudaSuccess) return fail("cudaMemset colsum");
+    h->peers[h->cfg.rank] = (unsigned long long)h->colsum;
+    h->dist_ready = h->cfg.dist_mode != RNDE_DIST_EXACT || h->cfg.nranks == 1;
     if (cudaMalloc(&h->bar, sizeof(unsigned) * 4) != cudaSuccess) return fail("cudaMalloc bar");
     if (cudaMalloc(&h->steps, sizeof(StepRec) * c.tape_capacity) != cudaSuccess) return fail("cudaMalloc steps");
     if (cudaMalloc(&h->stats, sizeof(DevStats)) != cudaSuccess) return fail("cudaMalloc stats");
@@ -314,6 +324,31 @@ extern "C" int rnde_debug_timeline(rnde_handle* h, long long* out, int n) {
     return RNDE_OK;
 }
 
+extern "C" int rnde_dist_export(rnde_handle* h, void* ipc_handle_out) {
+    if (!h || !ipc_handle_out) return RNDE_ERR_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == RNDE_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t mh;
+    CUDA_TRY(h, cudaIpcGetMemHandle(&mh, h->colsum));
+    memcpy(ipc_handle_out, &mh, sizeof(mh));
+    return RNDE_OK;
+}
+
+extern "C" int rnde_dist_import(rnde_handle* h, const void* ipc_handles, int32_t nranks) {
+    if (!h || !ipc_handles || nranks != h->cfg.nranks) return RNDE_ERR_ARG;
+    const unsigned char* p = (const unsigned char*)ipc_handles;
+    for (int r = 0; r < nranks; ++r) {
+        if (r == h->cfg.rank) continue;
+        cudaIpcMemHandle_t mh;
+        memcpy(&mh, p + (size_t)r * RNDE_IPC_HANDLE_BYTES, sizeof(mh));
+        void* ptr = nullptr;
+        CUDA_TRY(h, cudaIpcOpenMemHandle(&ptr, mh, cudaIpcMemLazyEnablePeerAccess));
+        h->peers[r] = (unsigned long long)ptr;
+        h->peers_open[r] = true;
+    }
+    h->dist_ready = true;
+    return RNDE_OK;
+}
+
 extern "C" int rnde_set_tspan(rnde_handle* h, float t0, float t1) {
     if (!h || !(t1 > t0)) return RNDE_ERR_ARG;
     h->cfg.t0 = t0; h->cfg.t1 = t1;
@@ -328,8 +363,10 @@ static void fill_params(const rnde_handle* h, KParams& P) {
     P.act1 = c.act_hidden; P.act2 = c.act_out; P.td = c.time_dep ? 1 : 0;
     P.alg = c.alg; P.reg_kind = c.reg_kind; P.max_steps = c.max_steps; P.tape_cap = c.tape_capacity; P.need_tape = c.need_backward ? 1 : 0;
     P.t0 = c.t0; P.t1 = c.t1; P.abstol = c.abstol; P.reltol = c.reltol; P.dtmin = c.dtmin;
-    P.norm_count = (long long)c.state_dim * (long long)c.batch;   // SINGLE / INDEPENDENT: the local batch is the whole problem
-    P.Bglobal = c.batch; P.col_offset = 0;
+    P.norm_count = (long long)c.state_dim * (long long)c.global_batch;   // SINGLE / INDEPENDENT: global_batch == batch
+    P.Bglobal = (int)c.global_batch; P.col_offset = c.rank * c.batch;
+    P.nranks = c.nranks; P.rank = c.rank; P.flag_off = (unsigned)(2 * 3 * h->colsum_stride);
+    for (int i = 0; i < 8; ++i) P.peers[i] = h->peers[i];
     P.colsum = h->colsum; P.colsum_stride = h->colsum_stride; P.bar = h->bar; P.steps = h->steps; P.stats = h->stats;
     P.dbg = h->dbg;
     P.tapeZ = h->tapeZ; P.tapeK = h->tapeK; P.tapeH = h->tapeH; P.tapeD1 = h->tapeD1; P.scal = h->scal;
@@ -354,6 +391,7 @@ static int launch(rnde_handle* h, kern_t k, const KParams& P, size_t smem, cudaS
 extern "C" int rnde_forward(rnde_handle* h, const float* x_dev, const float* p_dev, float* u_out_dev, float* saveval_dev,
                             rnde_stats* stats_host, void* stream) {
     if (!h || !x_dev || !p_dev || !u_out_dev) return RNDE_ERR_ARG;
+    if (!h->dist_ready) return set_err(h, RNDE_ERR_STATE, "RNDE_DIST_EXACT: call rnde_dist_export / rnde_dist_import on every rank first");
     cudaStream_t st = (cudaStream_t)stream;
     KParams P;
     fill_params(h, P);

@@ -202,7 +202,7 @@ class TrackedNeuralODE:
     def __init__(self, model: TDChain, tspan: Sequence[float], time_dep: bool, regularize: bool, solver=Tsit5(), *,
                  reltol: float = 1.4e-8, abstol: float = 1.4e-8, save_everystep: bool = False, save_start: bool = False,
                  saveat=None, maxiters: int = 0, tape_capacity: int = 256, kernel_variant: int = L.KERNEL_AUTO,
-                 kblock: int = 0, device: str = "cuda"):
+                 kblock: int = 0, device: str = "cuda", dist_mode: int = L.DIST_SINGLE, rank: int = 0, world: int = 1):
         if save_everystep or saveat is not None:
             raise NotImplementedError("return_multiple (save_everystep/saveat) is a NEXT row (SURVEY.md 8f N1)")
         if not time_dep:
@@ -217,6 +217,9 @@ class TrackedNeuralODE:
         self.reltol, self.abstol = float(reltol), float(abstol)
         self.maxiters, self.tape_capacity = maxiters, tape_capacity
         self.kernel_variant, self.kblock = kernel_variant, kblock
+        # data parallel: DIST_EXACT shares the step sequence of the global batched solve across ranks (x holds this
+        # rank's columns, all shards equal); DIST_INDEPENDENT / DIST_SINGLE integrate the local columns on their own
+        self.dist_mode, self.rank, self.world = dist_mode, rank, world
         self._handles: dict = {}
         self.last_stats: Optional[L.Stats] = None
 
@@ -239,11 +242,19 @@ class TrackedNeuralODE:
             cfg.tape_capacity = self.tape_capacity
             cfg.need_backward = 1 if need_backward else 0
             cfg.kernel_variant = self.kernel_variant
-            cfg.dist_mode, cfg.rank, cfg.nranks = L.DIST_SINGLE, 0, 1
+            cfg.dist_mode, cfg.rank, cfg.nranks = self.dist_mode, self.rank, self.world
             cfg.t0, cfg.t1 = self.tspan
             cfg.abstol, cfg.reltol, cfg.dtmin = self.abstol, self.reltol, 0.0
-            cfg.global_batch = B
-            self._handles[key] = _Handle(cfg)
+            cfg.global_batch = B * (self.world if self.dist_mode == L.DIST_EXACT else 1)
+            hd = _Handle(cfg)
+            if self.dist_mode == L.DIST_EXACT and self.world > 1:
+                from .parallel import exchange_ipc_handles
+                mine = (C.c_ubyte * 64)()
+                hd.check(hd.lib.rnde_dist_export(hd.h, mine), "rnde_dist_export")
+                allh = exchange_ipc_handles(bytes(mine), self.world)
+                buf = (C.c_ubyte * (64 * self.world)).from_buffer_copy(b"".join(allh))
+                hd.check(hd.lib.rnde_dist_import(hd.h, buf, self.world), "rnde_dist_import")
+            self._handles[key] = hd
         return self._handles[key]
 
     def __call__(self, x: torch.Tensor, p: Optional[torch.Tensor] = None, *, func: Optional[SaveFunc] = None, tspan=None,

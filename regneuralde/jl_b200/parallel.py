@@ -34,3 +34,11 @@ def max_over_ranks(value: float, device=None) -> float:
     t = torch.tensor([value], device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t)
+
+
+def exchange_ipc_handles(mine: bytes, world: int) -> list[bytes]:
+    """All-gather the 64-byte CUDA IPC handles of the ranks' exchange buffers (rnde_dist_export ->
+    rnde_dist_import).  Plumbing only: a collective on host bytes."""
+    out = [None] * world
+    dist.all_gather_object(out, mine)
+    return out

@@ -264,3 +264,48 @@ def test_rejected_steps_path(oracle_built):
     assert ref.nreject > 0 and node.last_stats.nreject == ref.nreject and nfe == ref.nf
     assert np.array_equal(bits(res.cpu().numpy()), bits(ref.u))
     assert np.array_equal(bits(sv.saveval.cpu().numpy()), bits(ref.saveval))
+
+
+def _exact_worker(rank, world, port, q):
+    import os
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import regneuralde.jl_b200 as r
+    from regneuralde.jl_b200 import _lib as L
+    D, H, Bg = 784, 100, 96
+    Bl = Bg // world
+    rng = np.random.default_rng(1999)
+    p_np = orc.glorot_params(rng, D, H); x_np = rng.random((D, Bg), dtype=np.float32)
+    node = r.TrackedNeuralODE(r.MLPDynamics(D, H), [0.0, 1.0], True, True, r.Tsit5(), reltol=1.4e-8, abstol=1.4e-8,
+                              dist_mode=L.DIST_EXACT, rank=rank, world=world)
+    with torch.no_grad():
+        res, nfe, sv = node(torch.from_numpy(np.ascontiguousarray(x_np[:, rank * Bl:(rank + 1) * Bl])).cuda(), torch.from_numpy(p_np).cuda())
+    q.put((rank, res.cpu().numpy(), sv.saveval.cpu().numpy(), nfe))
+    dist.destroy_process_group()
+
+
+def test_exact_data_parallel_matches_single_solve(oracle_built):
+    """SURVEY.md 8e reference-exact mode: 2 ranks sharing the step sequence == one batched solve, bit for bit."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (tools/dist_exact_check.py is the torchrun version; result in profiles/)")
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    qq = ctx.Queue()
+    procs = [ctx.Process(target=_exact_worker, args=(rk, 2, port, qq)) for rk in range(2)]
+    for p in procs:
+        p.start()
+    outs = sorted((qq.get(timeout=300) for _ in procs), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    D, H, Bg = 784, 100, 96
+    rng = np.random.default_rng(1999)
+    p_np = orc.glorot_params(rng, D, H); x_np = rng.random((D, Bg), dtype=np.float32)
+    ref = orc.Oracle(oracle_cfg(D, H, Bg, 1, 0, orc.REG_ERR_DT)).forward(x_np, p_np)
+    u = np.concatenate([o[1] for o in outs], axis=1)
+    assert outs[0][3] == ref.nf and outs[1][3] == ref.nf
+    assert np.array_equal(bits(u), bits(ref.u))
+    assert np.array_equal(bits(outs[0][2]), bits(ref.saveval)) and np.array_equal(bits(outs[1][2]), bits(ref.saveval))
