@@ -127,8 +127,18 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4_kernel(const KParams P) {
     auto offD = [&](int rec, int i) -> size_t { return ((size_t)rec * P.Q + q) * tileD + (size_t)(r0 + crow0 + i) * NP + cn0; };
 
     // VJP of record `rec`: cur = kbar of that evaluation (in), zb = W1^T delta1 for the tile (out)
-    auto vjp = [&](const float (&cur)[16], float (&zb)[16], const int rec) {
+    auto vjp = [&](const float (&cur)[16], float (&zb)[16], const int rec, const int rec_next) {
         if (tid == 0) { mbar_expect_tx(barP, bytesP); mbar_expect_tx(barH, bytesH); }
+        // the tape is HBM resident (0.75 GB): pull the NEXT record's k / h tiles towards L2 while this record is processed
+        if (rec_next >= 0) {
+            if (own) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (i < cvalid) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.tapeK + offD(rec_next, i)));
+            }
+            if (tid < HSloc * 4)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(P.tapeH + ((size_t)rec_next * P.Q + q) * tileH + (size_t)(rank * HS + (tid >> 2)) * NP + (tid & 3) * 4));
+        }
         if (own) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -347,7 +357,13 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4_kernel(const KParams P) {
             default: _Pragma("unroll") for (int e = 0; e < 16; ++e) cur[e] = kb[6][e]; break;
 #undef RNDE_CUR
         }
-        vjp(cur, zb, rec);
+        int rec_next = -1;
+        if (!last) {
+            const int t2 = task + 1;
+            if (t2 == ntask - 1) rec_next = 0;
+            else { const int s2 = P.nsteps - 1 - t2 / 6, i2 = 7 - t2 % 6; rec_next = 6 * s2 + i2 - 1; }
+        }
+        vjp(cur, zb, rec, rec_next);
         if (last) {
             // initial fsalfirst = f(u0, t0): dx = ubar + zbar
             if (P.dx && own) {

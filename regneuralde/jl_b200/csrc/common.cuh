@@ -71,20 +71,15 @@ __device__ __forceinline__ void group_sync() {
     if constexpr (G > 1) cluster_sync_all(); else __syncthreads();
 }
 
-// Sense-reversing grid barrier over all CTAs of a co-resident persistent grid.
+// Grid barrier over all CTAs of a co-resident persistent grid: one release-add on a monotonically
+// increasing arrival counter, then acquire-polling until it reaches nblocks*(generation+1).
+// (bar[0] is zeroed by the host before every launch.)
 __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned nblocks, unsigned& gen) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned prev = atomicAdd(&bar[0], 1u);
-        if (prev == nblocks - 1) {
-            atomicExch(&bar[0], 0u);
-            __threadfence();
-            atomicAdd(&bar[1], 1u);
-        } else {
-            while (ld_acquire_gpu(&bar[1]) == gen) { }
-        }
-        __threadfence();
+        const unsigned target = nblocks * (gen + 1u);
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+        while ((int)(ld_acquire_gpu(bar) - target) < 0) { }
     }
     gen += 1;
     __syncthreads();

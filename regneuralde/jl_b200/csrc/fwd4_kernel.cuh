@@ -214,7 +214,11 @@ __global__ void __launch_bounds__(V2_NT, 1) fwd4_kernel(const KParams P) {
     uint32_t ev_parity = 0;
     int dbg_n = 0;
     auto mark = [&](int id) {
+#ifdef RNDE_TIMELINE      // phase timeline for tools/gpu_check.py timeline; compiled out of the product build
         if (P.dbg && blockIdx.x == 0 && tid == 0 && dbg_n < 4000) { P.dbg[dbg_n * 2] = id; P.dbg[dbg_n * 2 + 1] = clock64(); dbg_n++; }
+#else
+        (void)id; (void)dbg_n;
+#endif
     };
     const uint32_t bytesP = (uint32_t)((G - 1) * HSloc * NP * 4);
     const uint32_t bytesH = (uint32_t)((H - HSloc) * NP * 4);
