@@ -38,6 +38,22 @@ SEED = 1999
 LAMBDA = 1.0e2
 
 
+def stepper_dram_traffic() -> float | None:
+    """dram__bytes_read.sum + dram__bytes_write.sum of the forward stepper per launch, from the committed
+    `ncu --set full` capture (profiles/r1h_steppers_ncu_raw_metrics.json)."""
+    f = ROOT / "profiles" / "r1h_steppers_ncu_raw_metrics.json"
+    try:
+        d = json.loads(f.read_text())
+        k = next(v for n, v in d.items() if "fwd4" in n)
+        tot = 0.0
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            val, unit = k[key]
+            tot += float(val) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+        return tot
+    except Exception:
+        return None
+
+
 def ffma_peak_tflops() -> tuple[float, str]:
     """FP32 FFMA peak of this pool's B200 (not in MEASURED_PEAKS.json): measured by tools/microbench.cu,
     committed in profiles/ffma_peak.json."""
@@ -325,7 +341,7 @@ def run_ours(args):
             "gpu_launches": int(nlaunch),
             "clocks": clocks,
             "roofline": {"bound": "fp32_ffma", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": fwd_ms, "nfe": nf,
+                         "frac": achieved / peak, "traffic": stepper_dram_traffic(), "traffic_unit": "bytes/launch (ncu, tape writes; algorithmic = 3.416 MB x records)", "peak_source": peak_src, "kernel_ms": fwd_ms, "nfe": nf,
                          "flop_per_launch": nf * F_RHS * B,
                          "train_step_frac": flop_per_sample * B * world * K / (ms * 1e-3) / 1e12 / (peak * world)},
         }
@@ -339,7 +355,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=512, help="samples per GPU")
