@@ -31,6 +31,7 @@ class _Cfg(C.Structure):
         ("t0", C.c_double), ("t1", C.c_double), ("abstol", C.c_double), ("reltol", C.c_double),
         ("dtmin", C.c_double),
         ("n_forced", C.c_int), ("forced_dt", C.POINTER(C.c_double)), ("forced_accept", C.POINTER(C.c_int)),
+        ("n_saveat", C.c_int), ("saveat", C.POINTER(C.c_double)),
     ]
 
 
@@ -83,6 +84,7 @@ class OracleConfig:
     dtmin: float = 0.0
     forced_dt: np.ndarray | None = None
     forced_accept: np.ndarray | None = None
+    saveat: np.ndarray | None = None
 
     @property
     def n_params(self) -> int:
@@ -104,6 +106,7 @@ class OracleResult:
     dt_init: float
     t_final: float
     steps: list = field(default_factory=list)   # (t, dt, EEst, eigen_est) per accepted step
+    usave: np.ndarray | None = None              # (n_saveat, D, B) states at the saveat times
 
 
 class Oracle:
@@ -128,6 +131,11 @@ class Oracle:
             c.n_forced = len(fd)
             c.forced_dt = fd.ctypes.data_as(C.POINTER(C.c_double))
             c.forced_accept = fa.ctypes.data_as(C.POINTER(C.c_int))
+        if cfg.saveat is not None:
+            sa = np.ascontiguousarray(cfg.saveat, dtype=np.float64)
+            self._keep.append(sa)
+            c.n_saveat = len(sa)
+            c.saveat = sa.ctypes.data_as(C.POINTER(C.c_double))
         self._c = c
         self.h = C.c_void_p()
         rc = self._fn("create")(C.byref(c), C.byref(self.h))
@@ -192,11 +200,20 @@ class Oracle:
             a = [C.c_double() for _ in range(4)]
             gs(self.h, j, *[C.byref(v) for v in a])
             steps.append(tuple(v.value for v in a))
-        return OracleResult(u=u, nf=st.nf, naccept=st.naccept, nreject=st.nreject, retcode=st.retcode, saveval=sv,
+        usave = None
+        if self.cfg.saveat is not None:
+            nsv = len(self.cfg.saveat)
+            buf = np.zeros((nsv, B, D), dtype=self.dtype)
+            gu = self._fn("get_usave"); gu.argtypes = [C.c_void_p, C.c_void_p]
+            got = gu(self.h, self._ptr(buf))
+            usave = np.ascontiguousarray(buf[:got].transpose(0, 2, 1))
+        res = OracleResult(u=u, nf=st.nf, naccept=st.naccept, nreject=st.nreject, retcode=st.retcode, saveval=sv,
                             dt_log=dts[:n], accept_log=acc[:n], eest_log=ee[:n], dt_init=st.dt_init,
                             t_final=st.t_final, steps=steps)
+        res.usave = usave
+        return res
 
-    def backward(self, du, dsaveval=None, hi: bool = False):
+    def backward(self, du, dsaveval=None, hi: bool = False, dusave=None):
         """Discrete adjoint with frozen dt.  Returns dp, dx, dtbar[naccept], tbar[naccept].
         hi=True (FP32 oracle only): cotangents and accumulations in Float64 over the same FP32
         forward values -- the reference for judging the accuracy of FP32 adjoints."""
@@ -211,8 +228,12 @@ class Oracle:
         dtbar = np.zeros(nacc, dtype=np.float64)
         tbar = np.zeros(nacc, dtype=np.float64)
         f = self._fn("backward_hi" if (hi and not self.f64) else "backward")
-        f.argtypes = [C.c_void_p] * 7
-        rc = f(self.h, self._ptr(du), self._ptr(dsaveval), self._ptr(dp), self._ptr(dx), self._ptr(dtbar), self._ptr(tbar))
+        f.argtypes = [C.c_void_p] * 8
+        dus = None
+        if dusave is not None:      # (n_saveat, D, B) -> per save a column-major D x B block
+            dus = np.ascontiguousarray(np.asarray(dusave, dtype=self.dtype).transpose(0, 2, 1))
+        rc = f(self.h, self._ptr(du), self._ptr(dsaveval), self._ptr(dp), self._ptr(dx), self._ptr(dtbar), self._ptr(tbar),
+               self._ptr(dus) if dus is not None else None)
         if rc != 0:
             raise RuntimeError(f"oracle backward rc={rc}")
         return dp, dx, dtbar[: self._naccept], tbar[: self._naccept]

@@ -74,6 +74,10 @@ typedef struct {
     int n_forced;
     const double* forced_dt;
     const int* forced_accept;
+    /* saveat (neural_ode.jl:79-108,146-180; DiffEqBase saveat semantics): sorted times in
+     * [t0,t1]; a time equal to a step end copies u, others use the Tsit5 free interpolant; t0 in saveat saves u0 */
+    int n_saveat;
+    const double* saveat;
 } orc_config;
 
 typedef struct {
@@ -92,6 +96,10 @@ typedef struct {
     /* attempted-step log */
     int log_cap, log_n; double* log_dt; int* log_acc; double* log_eest;
     REAL* saveval; int n_saved;
+    REAL* usave;            /* n_saveat x (D*B) saved states */
+    int* save_step;         /* accepted-step index each save belongs to (-1: t0) */
+    REAL* save_theta;       /* theta of the save inside its step (1 = copied end state) */
+    int n_usaved;
     orc_stats st;
 } orc_handle;
 
@@ -321,6 +329,18 @@ static void tsit5_attempt(const orc_config* c, const REAL* p, const REAL* uprev,
     *EEst = rms_from_total(cols_total(w->colq, B), cnt);
 }
 
+/* Tsit5 free interpolant weights b_i(theta), i = 1..7 (Appendix A.9), Horner with fma */
+static void interp_weights(REAL th, REAL* b) {
+    const REAL th2 = th * th;
+    b[1] = th * R_FMA(th, R_FMA(th, R_FMA(th, (REAL)TS_R14, (REAL)TS_R13), (REAL)TS_R12), (REAL)TS_R11);
+    b[2] = th2 * R_FMA(th, R_FMA(th, (REAL)TS_R24, (REAL)TS_R23), (REAL)TS_R22);
+    b[3] = th2 * R_FMA(th, R_FMA(th, (REAL)TS_R34, (REAL)TS_R33), (REAL)TS_R32);
+    b[4] = th2 * R_FMA(th, R_FMA(th, (REAL)TS_R44, (REAL)TS_R43), (REAL)TS_R42);
+    b[5] = th2 * R_FMA(th, R_FMA(th, (REAL)TS_R54, (REAL)TS_R53), (REAL)TS_R52);
+    b[6] = th2 * R_FMA(th, R_FMA(th, (REAL)TS_R64, (REAL)TS_R63), (REAL)TS_R62);
+    b[7] = th2 * R_FMA(th, R_FMA(th, (REAL)TS_R74, (REAL)TS_R73), (REAL)TS_R72);
+}
+
 /* ------------------------------------------------------------------ */
 /* initial dt (Hairer-Wanner, Appendix A.5)                            */
 /* ------------------------------------------------------------------ */
@@ -462,6 +482,7 @@ void FN(destroy)(void* hv) {
     tape_clear(h);
     free(h->tp_t); free(h->tp_dt); free(h->tp_eest); free(h->tp_eig); free(h->tp_uprev); free(h->tp_k1);
     free(h->u0); free(h->p); free(h->log_dt); free(h->log_acc); free(h->log_eest); free(h->saveval);
+    free(h->usave); free(h->save_step); free(h->save_theta);
     free(h);
 }
 
@@ -501,6 +522,18 @@ int FN(forward)(void* hv, const REAL* x, const REAL* p, REAL* u_out, orc_stats* 
 
     const REAL t0 = (REAL)c->t0, tf = (REAL)c->t1;
     REAL t = t0;
+    free(h->usave); free(h->save_step); free(h->save_theta);
+    h->usave = NULL; h->save_step = NULL; h->save_theta = NULL; h->n_usaved = 0;
+    int save_idx = 0;
+    if (c->n_saveat > 0) {
+        h->usave = (REAL*)calloc((size_t)c->n_saveat * n, sizeof(REAL));
+        h->save_step = (int*)malloc(sizeof(int) * c->n_saveat);
+        h->save_theta = (REAL*)malloc(sizeof(REAL) * c->n_saveat);
+        while (save_idx < c->n_saveat && (REAL)c->saveat[save_idx] <= t0) {
+            memcpy(h->usave + (size_t)save_idx * n, x, sizeof(REAL) * n);
+            h->save_step[save_idx] = -1; h->save_theta[save_idx] = 0; save_idx++;
+        }
+    }
     const REAL dtmax = tf - t0;
     /* controller constants (Appendix A.4), converted once to REAL */
     const REAL gamma = (REAL)(9.0 / 10.0), qmin = (REAL)(1.0 / 5.0), qmax = (REAL)10;
@@ -578,7 +611,27 @@ int FN(forward)(void* hv, const REAL* x, const REAL* p, REAL* u_out, orc_stats* 
             if (q >= (REAL)1 && q <= (REAL)1) q = 1;   /* qsteady_min = qsteady_max = 1 */
             qold = EEst > qoldinit ? EEst : qoldinit;
             REAL dtnew = dt / q;
+            const REAL tprev = t;
             t = t + dt;
+            /* savevalues!: every pending saveat time <= t */
+            while (save_idx < c->n_saveat && (REAL)c->saveat[save_idx] <= t) {
+                const REAL tau = (REAL)c->saveat[save_idx];
+                REAL* dst = h->usave + (size_t)save_idx * n;
+                h->save_step[save_idx] = st.naccept - 1;
+                if (tau == t) { memcpy(dst, w->z[7], sizeof(REAL) * n); h->save_theta[save_idx] = 1; }
+                else {
+                    const REAL th = (tau - tprev) / dt;
+                    REAL b[8]; interp_weights(th, b);
+                    h->save_theta[save_idx] = th;
+#pragma omp parallel for schedule(static)
+                    for (size_t e = 0; e < n; ++e) {
+                        REAL sacc = b[1] * w->k[1][e];
+                        for (int i = 2; i <= 7; ++i) sacc = R_FMA(b[i], w->k[i][e], sacc);
+                        dst[e] = R_FMA(dt, sacc, u[e]);
+                    }
+                }
+                save_idx++;
+            }
             dtpropose = dtnew < dtmax ? dtnew : dtmax;
             if (dtpropose < (REAL)c->dtmin) dtpropose = (REAL)c->dtmin;
             memcpy(u, w->z[7], sizeof(REAL) * n);
@@ -592,6 +645,7 @@ int FN(forward)(void* hv, const REAL* x, const REAL* p, REAL* u_out, orc_stats* 
         accept_prev = accept;
     }
     memcpy(u_out, u, sizeof(REAL) * n);
+    h->n_usaved = save_idx;
     st.t_final = t; st.n_saved = h->n_saved; st.retcode = rc;
     h->st = st;
     if (st_out) *st_out = st;
@@ -604,6 +658,12 @@ int FN(get_saveval)(void* hv, REAL* out, int cap) {
     int n = h->n_saved < cap ? h->n_saved : cap;
     memcpy(out, h->saveval, sizeof(REAL) * n);
     return h->n_saved;
+}
+/* saved states: out is n_saveat x (D*B); returns the number actually saved */
+int FN(get_usave)(void* hv, REAL* out) {
+    orc_handle* h = (orc_handle*)hv;
+    if (h->n_usaved > 0) memcpy(out, h->usave, sizeof(REAL) * (size_t)h->n_usaved * h->cfg.D * h->cfg.B);
+    return h->n_usaved;
 }
 int FN(get_log)(void* hv, double* dt, int* acc, double* eest, int cap) {
     orc_handle* h = (orc_handle*)hv;

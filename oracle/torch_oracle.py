@@ -78,6 +78,20 @@ def field(p, z, t, D, H, act2_tanh=True, time_dep=True):
     return torch.tanh(y) if act2_tanh else y
 
 
+R = [[1.0, -2.763706197274826, 2.9132554618219126, -1.0530884977290216],
+     [0.13169999999999998, -0.2234, 0.1017], [3.9302962368947516, -5.941033872131505, 2.490627285651253],
+     [-12.411077166933676, 30.33818863028232, -16.548102889244902], [37.50931341651104, -88.1789048947664, 47.37952196281928],
+     [-27.896526289197286, 65.09189467479366, -34.87065786149661], [1.5, -4.0, 2.5]]
+
+
+def interp_weights(th):
+    """Tsit5 free interpolant b_i(theta)."""
+    b = [th * (R[0][0] + th * (R[0][1] + th * (R[0][2] + th * R[0][3])))]
+    for i in range(1, 7):
+        b.append(th * th * (R[i][0] + th * (R[i][1] + th * R[i][2])))
+    return b
+
+
 def rms(x):
     return torch.sqrt(torch.sum(x * x) / x.numel())
 
@@ -101,7 +115,7 @@ def saved_value(kind, EEst, eig, dt, dtype):
 
 def solve(x, p, *, D, H, act2_tanh=True, time_dep=True, t0=0.0, t1=1.0, abstol=1.4e-8, reltol=1.4e-8,
           auto_tsit5=False, reg_kind=REG_NONE, detach="all", forced_dt=None, forced_accept=None,
-          dt_leaf=None, max_steps=100000) -> TorchResult:
+          dt_leaf=None, max_steps=100000, saveat=None) -> TorchResult:
     """x: (D,B) tensor, p: flat parameter tensor (Flux.destructure order).
 
     forced_dt/forced_accept replay a recorded attempt sequence (controller
@@ -121,6 +135,11 @@ def solve(x, p, *, D, H, act2_tanh=True, time_dep=True, t0=0.0, t1=1.0, abstol=1
     saveval = []
     if reg_kind != REG_NONE:
         saveval.append(saved_value(reg_kind, c(1.0), c(1.0), c(0.0), dtype))
+    usave = []
+    save_idx = 0
+    if saveat is not None:
+        while save_idx < len(saveat) and float(saveat[save_idx]) <= t0:
+            usave.append(u); save_idx += 1
     k1 = f(u, t)
     nf = 1
     forced = forced_dt is not None
@@ -220,7 +239,20 @@ def solve(x, p, *, D, H, act2_tanh=True, time_dep=True, t0=0.0, t1=1.0, abstol=1
             qold = max(ee, qoldinit)
             dtnew = float(dt) / q
             dt_list.append(dt); t_list.append(t)
+            tprev = t
             t = t + dt
+            while saveat is not None and save_idx < len(saveat) and float(saveat[save_idx]) <= float(t):
+                tau = float(saveat[save_idx])
+                if tau == float(t):
+                    usave.append(unew)
+                else:
+                    th = (tau - float(tprev)) / float(dt)       # theta is not differentiated (frozen step sequence)
+                    bw = interp_weights(th)
+                    acc = bw[0] * ks[1]
+                    for j in range(2, 8):
+                        acc = acc + bw[j - 1] * ks[j]
+                    usave.append(u + dt * acc)
+                save_idx += 1
             dtpropose = c(min(dtmax, dtnew))     # DiffEqBase.value(...): detached (Appendix A.6)
             u = unew
             k1 = ks[7]
@@ -232,4 +264,5 @@ def solve(x, p, *, D, H, act2_tanh=True, time_dep=True, t0=0.0, t1=1.0, abstol=1
     res = TorchResult(u=u, nf=nf, naccept=naccept, nreject=nreject, saveval=saveval, dt_log=dt_log,
                       accept_log=accept_log, eest_log=eest_log, dt_list=dt_list, t_list=t_list)
     res.dt_init = dt_init
+    res.usave = usave
     return res
