@@ -90,6 +90,8 @@ typedef struct rnde_config {
     float t0, t1;             /* tspan */
     float abstol, reltol;     /* solver kwargs */
     float dtmin;              /* 0 = 1e-10 */
+    int32_t max_saveat;       /* > 0: the handle serves the multi-save functors (saveat keyword); sizes the saveat buffer */
+    int32_t reserved0;
     int64_t global_batch;     /* columns over all ranks (EXACT mode); 0 = batch */
 } rnde_config;
 
@@ -136,6 +138,21 @@ int rnde_forward(rnde_handle* h, const float* x_dev, const float* p_dev, float* 
  * du_dev: dL/d res (D x B); dsaveval_dev: dL/d sv.saveval[i] (n_saved floats, may be NULL);
  * dp_dev (num_params) and dx_dev (D x B, may be NULL) are OVERWRITTEN. */
 int rnde_backward(rnde_handle* h, const float* du_dev, const float* dsaveval_dev, float* dp_dev, float* dx_dev, void* stream);
+
+/* Multi-save functors  (n::TrackedNeuralODE{R,true})(x, p; func)  (neural_ode.jl:79-108 unregularised, :146-180
+ * regularised; latent-ODE call site time_series.jl:51).  rnde_set_saveat installs the sorted save times (host
+ * array, n <= max_saveat, all inside tspan; n = 0 switches back to the single-save functors) -- the counterpart of
+ * update_saveat! (neural_ode.jl:41-45).  Semantics follow solve(...; saveat) of OrdinaryDiffEq 5.50 (SURVEY.md
+ * Appendix A.9): no tstops are added; after every accepted step each pending time <= t is produced, by copying u when
+ * it equals the step end and by the Tsit5 free interpolant otherwise; a time equal to tspan[1] saves the input.
+ * usave_dev is the reference's `res`: feat x nsave x batch, column-major (D*n*B floats); u_out_dev (final state,
+ * D x B) may be NULL.  Backward: dusave_dev has the shape of usave_dev, du_dev (cotangent of the final state) may
+ * be NULL. */
+int rnde_set_saveat(rnde_handle* h, const float* saveat_host, int32_t n);
+int rnde_forward_saveat(rnde_handle* h, const float* x_dev, const float* p_dev, float* u_out_dev, float* usave_dev, float* saveval_dev,
+                        rnde_stats* stats_host, void* stream);
+int rnde_backward_saveat(rnde_handle* h, const float* du_dev, const float* dusave_dev, const float* dsaveval_dev, float* dp_dev,
+                         float* dx_dev, void* stream);
 
 /* Host-buffer variants (end-to-end path: copies inside the call). */
 int rnde_forward_host(rnde_handle* h, const float* x_host, const float* p_host, float* u_out_host, float* saveval_host,

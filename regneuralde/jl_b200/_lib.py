@@ -37,6 +37,7 @@ EXPORTS = [
     "rnde_num_params", "rnde_default_kblock", "rnde_kernel_variant", "rnde_launch_count", "rnde_set_tspan",
     "rnde_forward", "rnde_backward", "rnde_forward_host", "rnde_backward_host", "rnde_head_loss_grad", "rnde_get_steps",
     "rnde_opt_update", "rnde_test_tanh", "rnde_test_tanh_bits", "rnde_test_pow", "rnde_debug_timeline", "rnde_dist_export", "rnde_dist_import",
+    "rnde_set_saveat", "rnde_forward_saveat", "rnde_backward_saveat",
 ]
 
 
@@ -48,6 +49,7 @@ class Config(C.Structure):
         ("need_backward", C.c_int32), ("kernel_variant", C.c_int32), ("dist_mode", C.c_int32),
         ("rank", C.c_int32), ("nranks", C.c_int32),
         ("t0", C.c_float), ("t1", C.c_float), ("abstol", C.c_float), ("reltol", C.c_float), ("dtmin", C.c_float),
+        ("max_saveat", C.c_int32), ("reserved0", C.c_int32),
         ("global_batch", C.c_int64),
     ]
 
@@ -132,6 +134,9 @@ def lib() -> C.CDLL:
     L.rnde_debug_timeline.argtypes = [vp, vp, C.c_int]
     L.rnde_dist_export.argtypes = [vp, vp]
     L.rnde_dist_import.argtypes = [vp, vp, C.c_int32]
+    L.rnde_set_saveat.argtypes = [vp, vp, C.c_int32]
+    L.rnde_forward_saveat.argtypes = [vp, vp, vp, vp, vp, vp, C.POINTER(Stats), vp]
+    L.rnde_backward_saveat.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     _lib = L
     return L
 

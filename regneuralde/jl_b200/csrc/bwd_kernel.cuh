@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(NT, 1) bwd_kernel(const KParams P) {
     }
     for (int e = tid; e < RP * NP; e += NT) {
         const int n = e / RP, m = e - n * RP;
-        sUb[m * NP + n] = (m < Rloc && n < Nloc) ? __ldg(P.du + (size_t)D * (c0 + n) + r0 + m) : 0.f;
+        sUb[m * NP + n] = (P.du && m < Rloc && n < Nloc) ? __ldg(P.du + (size_t)D * (c0 + n) + r0 + m) : 0.f;
         sUpb[m * NP + n] = 0.f;
     }
     for (int e = tid; e < 7 * kstride; e += NT) sKb[e] = 0.f;
@@ -222,6 +222,17 @@ __global__ void __launch_bounds__(NT, 1) bwd_kernel(const KParams P) {
     const float cntf = (float)P.norm_count;
     const float stab = rn_divf(1.0f, (float)TS_STABILITY_SIZE);
 
+    // saveat cotangents are consumed newest first; times beyond the last accepted step were never saved
+    int sidx = P.dusave ? P.n_saveat - 1 : -1;
+    if (sidx >= 0) {
+        const float tend = P.nsteps > 0 ? P.steps[P.nsteps - 1].t + P.steps[P.nsteps - 1].dt : P.t0;
+        while (sidx >= 0 && __ldg(P.saveat + sidx) > tend) --sidx;
+    }
+    auto gsave = [&](const int si, const int e) -> float {
+        const int m = e / NP, n = e - m * NP;
+        return (n < Nloc) ? __ldg(P.dusave + (size_t)D * (si + (size_t)P.n_saveat * (c0 + n)) + r0 + m) : 0.f;
+    };
+
     for (int s = P.nsteps - 1; s >= 0; --s) {
         const StepRec sr = P.steps[s];
         const float dt = sr.dt, EEst = sr.eest, eig = sr.eig, n1 = sr.n1, n2 = sr.n2;
@@ -259,6 +270,23 @@ __global__ void __launch_bounds__(NT, 1) bwd_kernel(const KParams P) {
             for (int j = 1; j <= 6; ++j) Kb(j)[e] = 0.f;
         }
         __syncthreads();
+        // states saved inside this step: u(theta) = uprev + dt * sum_j b_j(theta) k_j   (theta frozen)
+        while (sidx >= 0 && __ldg(P.saveat + sidx) > sr.t) {
+            const float tau = __ldg(P.saveat + sidx);
+            if (tau == sr.t + dt) {
+                for (int e = tid; e < Rloc * NP; e += NT) sUb[e] += gsave(sidx, e);
+            } else {
+                float bw[8];
+                interp_weights(rn_divf(tau - sr.t, dt), bw);
+                for (int e = tid; e < Rloc * NP; e += NT) {
+                    const float g = gsave(sidx, e);
+                    sUpb[e] += g;
+#pragma unroll
+                    for (int j = 1; j <= 7; ++j) Kb(j)[e] += (dt * bw[j]) * g;
+                }
+            }
+            --sidx;
+        }
         if (use_eest || use_eig) {
             for (int e = tid; e < Rloc * NP; e += NT) {
                 const int n = e % NP;
@@ -328,7 +356,11 @@ __global__ void __launch_bounds__(NT, 1) bwd_kernel(const KParams P) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int n = nn + j;
-                if (n < Nloc) P.dx[(size_t)D * (c0 + n) + r0 + m] = sUb[m * NP + n] + zb[j];
+                if (n < Nloc) {
+                    float g = sUb[m * NP + n] + zb[j];
+                    for (int si = sidx; si >= 0; --si) g += gsave(si, m * NP + n);     // saves at t0 are the input itself
+                    P.dx[(size_t)D * (c0 + n) + r0 + m] = g;
+                }
             }
         }
     });

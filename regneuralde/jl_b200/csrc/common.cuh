@@ -45,7 +45,22 @@ struct KParams {
     int nranks, rank;
     unsigned long long peers[8];    // base of rank r's exchange buffer: [colsum 2x3xstride floats][flags 64 u32][seq u32]
     unsigned int flag_off;          // offset (in 4-byte words) of the flag array inside an exchange buffer
+    // saveat (multi-save functors, neural_ode.jl:79-108,146-180): sorted times, states written as feat x nsave x batch
+    const float* saveat; int n_saveat;
+    float* usave; const float* dusave;
 };
+
+// Tsit5 free interpolant weights b_1..b_7(theta); same Horner/fma order as the oracle's interp_weights
+__device__ __forceinline__ void interp_weights(const float th, float* b) {
+    const float th2 = th * th;
+    b[1] = th * rn_fmaf(th, rn_fmaf(th, rn_fmaf(th, (float)TS_R14, (float)TS_R13), (float)TS_R12), (float)TS_R11);
+    b[2] = th2 * rn_fmaf(th, rn_fmaf(th, (float)TS_R24, (float)TS_R23), (float)TS_R22);
+    b[3] = th2 * rn_fmaf(th, rn_fmaf(th, (float)TS_R34, (float)TS_R33), (float)TS_R32);
+    b[4] = th2 * rn_fmaf(th, rn_fmaf(th, (float)TS_R44, (float)TS_R43), (float)TS_R42);
+    b[5] = th2 * rn_fmaf(th, rn_fmaf(th, (float)TS_R54, (float)TS_R53), (float)TS_R52);
+    b[6] = th2 * rn_fmaf(th, rn_fmaf(th, (float)TS_R64, (float)TS_R63), (float)TS_R62);
+    b[7] = th2 * rn_fmaf(th, rn_fmaf(th, (float)TS_R74, (float)TS_R73), (float)TS_R72);
+}
 
 // ---- small PTX wrappers ----------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

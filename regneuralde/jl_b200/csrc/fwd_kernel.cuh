@@ -258,6 +258,19 @@ __global__ void __launch_bounds__(NT, 1) fwd_kernel(const KParams P) {
     __syncthreads();
     if constexpr (G > 1) cluster_sync_all();   // peers' shared memory is live before any DSMEM store
 
+    // saveat: times <= t0 save the initial state (save_start when tspan[1] is in saveat)
+    int save_idx = 0;
+    auto save_out = [&](const int sidx, auto val) {
+        for (int e = tid; e < RP * NP; e += NT) {
+            const int n = e / RP, m = e - n * RP;
+            if (m < Rloc && n < Nloc) P.usave[(size_t)D * (sidx + (size_t)P.n_saveat * (c0 + n)) + r0 + m] = val(m * NP + n);
+        }
+    };
+    while (save_idx < P.n_saveat && __ldg(P.saveat + save_idx) <= P.t0) {
+        save_out(save_idx, [&](int e) { return sU[e]; });
+        ++save_idx;
+    }
+
     unsigned norm_seq = 0, bar_gen = 0;
     unsigned* xseq_ptr = reinterpret_cast<unsigned*>(P.peers[P.rank]) + P.flag_off + 32;
     const unsigned xseq_base = (P.nranks > 1) ? *xseq_ptr : 0u;
@@ -585,6 +598,25 @@ __global__ void __launch_bounds__(NT, 1) fwd_kernel(const KParams P) {
         __syncthreads();
         const int accepted = ctl->accept, finished = ctl->done;
         __syncthreads();   // everyone has read ctl before thread 0 starts the next loopheader!
+        if (accepted && save_idx < P.n_saveat) {   // savevalues!: every pending saveat time <= t_new
+            const float tnew = t + dt;
+            while (save_idx < P.n_saveat) {
+                const float tau = __ldg(P.saveat + save_idx);
+                if (!(tau <= tnew)) break;
+                if (tau == tnew) save_out(save_idx, [&](int e) { return sZ[e]; });
+                else {
+                    float bw[8];
+                    interp_weights(rn_divf(tau - t, dt), bw);
+                    save_out(save_idx, [&](int e) {
+                        float sacc = bw[1] * K(1)[e];
+#pragma unroll
+                        for (int j = 2; j <= 7; ++j) sacc = rn_fmaf(bw[j], K(j)[e], sacc);
+                        return rn_fmaf(dt, sacc, sU[e]);
+                    });
+                }
+                ++save_idx;
+            }
+        }
         if (accepted) {    // apply_step!: u <- u_new, fsalfirst <- fsallast
             float* tmp = sU; sU = sZ; sZ = tmp;
             flipK ^= 1;
@@ -595,7 +627,7 @@ __global__ void __launch_bounds__(NT, 1) fwd_kernel(const KParams P) {
     // ---- write back ----------------------------------------------------------
     for (int e = tid; e < RP * NP; e += NT) {
         const int n = e / RP, m = e - n * RP;
-        if (m < Rloc && n < Nloc) P.u_out[(size_t)D * (c0 + n) + r0 + m] = sU[m * NP + n];
+        if (P.u_out && m < Rloc && n < Nloc) P.u_out[(size_t)D * (c0 + n) + r0 + m] = sU[m * NP + n];
     }
     if (blockIdx.x == 0 && tid == 0) {
         DevStats s;

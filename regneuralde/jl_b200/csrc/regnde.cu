@@ -41,6 +41,7 @@ struct rnde_handle {
     float* saveval_int = nullptr;       // used when the caller passes no saveval buffer
     float* dtile = nullptr;             // dx staging in tile layout
     float* head_ws = nullptr;
+    float* saveat_dev = nullptr; int n_saveat = 0;
     long long* dbg = nullptr;
     // host-path staging
     float *hx = nullptr, *hp = nullptr, *hu = nullptr, *hsv = nullptr, *hdu = nullptr, *hdsv = nullptr, *hdp = nullptr, *hdx = nullptr;
@@ -176,7 +177,7 @@ static void free_all(rnde_handle* h) {
     for (int i = 0; i < 8; ++i) if (h->peers_open[i]) cudaIpcCloseMemHandle((void*)h->peers[i]);
     cudaFree(h->colsum); cudaFree(h->bar); cudaFree(h->steps); cudaFree(h->stats);
     cudaFree(h->tapeZ); cudaFree(h->tapeK); cudaFree(h->tapeH); cudaFree(h->tapeD1); cudaFree(h->wg_ws); cudaFree(h->scal); cudaFree(h->saveval_int);
-    cudaFree(h->dtile); cudaFree(h->head_ws); cudaFree(h->dbg);
+    cudaFree(h->dtile); cudaFree(h->head_ws); cudaFree(h->dbg); cudaFree(h->saveat_dev);
     cudaFree(h->hx); cudaFree(h->hp); cudaFree(h->hu); cudaFree(h->hsv); cudaFree(h->hdu); cudaFree(h->hdsv); cudaFree(h->hdp); cudaFree(h->hdx);
     if (h->stats_pinned) cudaFreeHost(h->stats_pinned);
 }
@@ -196,6 +197,7 @@ static int try_variant(rnde_handle* h, int variant, size_t smem_limit, std::stri
     const int HS = (H + G - 1) / G;
     const int Q = (B + NP - 1) / NP;
     if (variant == RNDE_KERNEL_CLUSTER4) {
+        if (c.max_saveat > 0) { *why = "cluster-4 variant has no saveat path"; return 0; }
         if (!v2_shape_ok(D, H) || h->kblock != D / 8) { *why = "cluster-4 variant needs D % 8 == 0, kblock == D/8, H <= 128, D <= 1024"; return 0; }
         if (c.need_backward && !bwd_kernel_for(variant)) { *why = "cluster-4 backward not available"; return 0; }
     } else if (G > 1 && h->kblock != R) { *why = "cluster variant needs kblock == ceil(D/8)"; return 0; }
@@ -312,6 +314,7 @@ extern "C" int rnde_create(const rnde_config* cfg, rnde_handle** out) {
         if (cudaMalloc(&h->wg_ws, sizeof(float) * h->wg_ws_floats) != cudaSuccess) return fail("cudaMalloc wgrad workspace");
         if (cudaMalloc(&h->scal, sizeof(float) * 2 * c.tape_capacity) != cudaSuccess) return fail("cudaMalloc scal");
     }
+    if (c.max_saveat > 0 && cudaMalloc(&h->saveat_dev, sizeof(float) * c.max_saveat) != cudaSuccess) return fail("cudaMalloc saveat");
     if (getenv("RNDE_DEBUG_TIMELINE")) { cudaMalloc(&h->dbg, sizeof(long long) * 8000); cudaMemset(h->dbg, 0, sizeof(long long) * 8000); }
     *out = h;
     return RNDE_OK;
@@ -355,6 +358,18 @@ extern "C" int rnde_set_tspan(rnde_handle* h, float t0, float t1) {
     return RNDE_OK;
 }
 
+extern "C" int rnde_set_saveat(rnde_handle* h, const float* saveat_host, int32_t n) {
+    if (!h || n < 0 || (n > 0 && !saveat_host)) return RNDE_ERR_ARG;
+    if (n > h->cfg.max_saveat) return set_err(h, RNDE_ERR_ARG, "more saveat times than rnde_config.max_saveat");
+    for (int i = 0; i < n; ++i) {
+        if (!(saveat_host[i] >= h->cfg.t0 && saveat_host[i] <= h->cfg.t1)) return set_err(h, RNDE_ERR_ARG, "saveat time outside tspan");
+        if (i > 0 && !(saveat_host[i] > saveat_host[i - 1])) return set_err(h, RNDE_ERR_ARG, "saveat times must be strictly increasing");
+    }
+    if (n > 0) CUDA_TRY(h, cudaMemcpy(h->saveat_dev, saveat_host, sizeof(float) * n, cudaMemcpyHostToDevice));
+    h->n_saveat = n;
+    return RNDE_OK;
+}
+
 static void fill_params(const rnde_handle* h, KParams& P) {
     const rnde_config& c = h->cfg;
     memset(&P, 0, sizeof(P));
@@ -388,15 +403,19 @@ static int launch(rnde_handle* h, kern_t k, const KParams& P, size_t smem, cudaS
     return RNDE_OK;
 }
 
-extern "C" int rnde_forward(rnde_handle* h, const float* x_dev, const float* p_dev, float* u_out_dev, float* saveval_dev,
-                            rnde_stats* stats_host, void* stream) {
-    if (!h || !x_dev || !p_dev || !u_out_dev) return RNDE_ERR_ARG;
+static int forward_impl(rnde_handle* h, const float* x_dev, const float* p_dev, float* u_out_dev, float* usave_dev, float* saveval_dev,
+                        rnde_stats* stats_host, void* stream) {
+    if (!h || !x_dev || !p_dev || (!u_out_dev && !usave_dev)) return RNDE_ERR_ARG;
     if (!h->dist_ready) return set_err(h, RNDE_ERR_STATE, "RNDE_DIST_EXACT: call rnde_dist_export / rnde_dist_import on every rank first");
     cudaStream_t st = (cudaStream_t)stream;
     KParams P;
     fill_params(h, P);
     P.x = x_dev; P.p = p_dev; P.u_out = u_out_dev;
     P.saveval = saveval_dev ? saveval_dev : h->saveval_int;
+    if (usave_dev) {
+        if (h->n_saveat <= 0) return set_err(h, RNDE_ERR_STATE, "rnde_forward_saveat needs rnde_set_saveat first");
+        P.saveat = h->saveat_dev; P.n_saveat = h->n_saveat; P.usave = usave_dev;
+    }
     CUDA_TRY(h, cudaMemsetAsync(h->bar, 0, sizeof(unsigned) * 4, st));
     int rc = launch(h, fwd_kernel_for(h->variant, h->cfg.state_dim, h->cfg.hidden_dim), P, h->smem_fwd, st);
     if (rc != RNDE_OK) return rc;
@@ -412,6 +431,18 @@ extern "C" int rnde_forward(rnde_handle* h, const float* x_dev, const float* p_d
         if (s.retcode != RNDE_OK) return set_err(h, s.retcode, rnde_status_string(s.retcode));
     }
     return RNDE_OK;
+}
+
+extern "C" int rnde_forward(rnde_handle* h, const float* x_dev, const float* p_dev, float* u_out_dev, float* saveval_dev,
+                            rnde_stats* stats_host, void* stream) {
+    if (!u_out_dev) return RNDE_ERR_ARG;
+    return forward_impl(h, x_dev, p_dev, u_out_dev, nullptr, saveval_dev, stats_host, stream);
+}
+
+extern "C" int rnde_forward_saveat(rnde_handle* h, const float* x_dev, const float* p_dev, float* u_out_dev, float* usave_dev, float* saveval_dev,
+                                   rnde_stats* stats_host, void* stream) {
+    if (!usave_dev) return RNDE_ERR_ARG;
+    return forward_impl(h, x_dev, p_dev, u_out_dev, usave_dev, saveval_dev, stats_host, stream);
 }
 
 extern "C" int rnde_get_steps(rnde_handle* h, float* t, float* dt, float* eest, float* eig, int32_t cap) {
@@ -432,8 +463,9 @@ extern "C" int rnde_get_steps(rnde_handle* h, float* t, float* dt, float* eest, 
 }
 
 // ---- backward -----------------------------------------------------------------
-extern "C" int rnde_backward(rnde_handle* h, const float* du_dev, const float* dsaveval_dev, float* dp_dev, float* dx_dev, void* stream) {
-    if (!h || !du_dev || !dp_dev) return RNDE_ERR_ARG;
+static int backward_impl(rnde_handle* h, const float* du_dev, const float* dusave_dev, const float* dsaveval_dev, float* dp_dev, float* dx_dev,
+                         void* stream) {
+    if (!h || (!du_dev && !dusave_dev) || !dp_dev) return RNDE_ERR_ARG;
     if (!h->have_tape || !h->cfg.need_backward) return set_err(h, RNDE_ERR_STATE, "rnde_backward needs a preceding rnde_forward on a handle created with need_backward=1");
     cudaStream_t st = (cudaStream_t)stream;
     // number of accepted steps of the forward on this handle (already copied to pinned memory)
@@ -444,6 +476,10 @@ extern "C" int rnde_backward(rnde_handle* h, const float* du_dev, const float* d
     fill_params(h, P);
     P.p = h->last_p; P.du = du_dev; P.dsaveval = (h->cfg.reg_kind != RNDE_REG_NONE) ? dsaveval_dev : nullptr; P.dx = dx_dev;
     P.nsteps = s.naccept;
+    if (dusave_dev) {
+        if (h->n_saveat <= 0) return set_err(h, RNDE_ERR_STATE, "rnde_backward_saveat needs rnde_set_saveat first");
+        P.saveat = h->saveat_dev; P.n_saveat = h->n_saveat; P.dusave = dusave_dev;
+    }
     CUDA_TRY(h, cudaMemsetAsync(h->bar, 0, sizeof(unsigned) * 4, st));
     int rc = launch(h, bwd_kernel_for(h->variant, h->cfg.state_dim, h->cfg.hidden_dim), P, h->smem_bwd, st);
     if (rc != RNDE_OK) return rc;
@@ -461,6 +497,17 @@ extern "C" int rnde_backward(rnde_handle* h, const float* du_dev, const float* d
                       h->tapeZ, h->tapeK, h->tapeH, h->tapeD1, h->steps, h->cfg.t0, h->wg_ws, dp_dev, st, &h->launches);
     if (rc != 0) return set_err(h, RNDE_ERR_CUDA, std::string("wgrad launch: ") + cudaGetErrorString((cudaError_t)rc));
     return RNDE_OK;
+}
+
+extern "C" int rnde_backward(rnde_handle* h, const float* du_dev, const float* dsaveval_dev, float* dp_dev, float* dx_dev, void* stream) {
+    if (!du_dev) return RNDE_ERR_ARG;
+    return backward_impl(h, du_dev, nullptr, dsaveval_dev, dp_dev, dx_dev, stream);
+}
+
+extern "C" int rnde_backward_saveat(rnde_handle* h, const float* du_dev, const float* dusave_dev, const float* dsaveval_dev, float* dp_dev,
+                                    float* dx_dev, void* stream) {
+    if (!dusave_dev) return RNDE_ERR_ARG;
+    return backward_impl(h, du_dev, dusave_dev, dsaveval_dev, dp_dev, dx_dev, stream);
 }
 
 // ---- host-buffer (end-to-end) variants ------------------------------------------

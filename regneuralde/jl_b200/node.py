@@ -195,6 +195,41 @@ class _Solve(torch.autograd.Function):
         return dx, dp, None, None
 
 
+class _SolveSaveat(torch.autograd.Function):
+    """Multi-save functors (neural_ode.jl:79-108, :146-180): the result is the state at every saveat time."""
+
+    @staticmethod
+    def forward(ctx, xbuf: torch.Tensor, p: torch.Tensor, node: "TrackedNeuralODE", hd: _Handle, nsave: int):
+        cfg = hd.cfg
+        D, B = cfg.state_dim, cfg.batch
+        us = torch.zeros(D * nsave * B, device=xbuf.device, dtype=torch.float32)
+        sv = torch.zeros(cfg.tape_capacity + 1, device=xbuf.device, dtype=torch.float32)
+        st = L.Stats()
+        rc = hd.lib.rnde_forward_saveat(hd.h, xbuf.data_ptr(), p.data_ptr(), None, us.data_ptr(), sv.data_ptr(), C.byref(st), _stream_ptr())
+        node.last_stats = st
+        hd.check(rc, "rnde_forward_saveat")
+        ctx.hd, ctx.n_saved, ctx.p_ref = hd, st.n_saved, p
+        return us, sv[: st.n_saved]
+
+    @staticmethod
+    def backward(ctx, dus: torch.Tensor, dsv: torch.Tensor):
+        hd = ctx.hd
+        cfg = hd.cfg
+        D, B = cfg.state_dim, cfg.batch
+        dev = ctx.p_ref.device
+        dus = dus.contiguous() if dus is not None else None
+        dsv_full = torch.zeros(cfg.tape_capacity + 1, device=dev, dtype=torch.float32)
+        if dsv is not None and ctx.n_saved > 0:
+            dsv_full[: ctx.n_saved] = dsv
+        if dus is None:
+            dus = torch.zeros(1, device=dev)    # unreachable in practice: the saved states are the primary output
+        dp = torch.empty(ctx.p_ref.numel(), device=dev, dtype=torch.float32)
+        dx = torch.empty(D * B, device=dev, dtype=torch.float32)
+        rc = hd.lib.rnde_backward_saveat(hd.h, None, dus.data_ptr(), dsv_full.data_ptr(), dp.data_ptr(), dx.data_ptr(), _stream_ptr())
+        hd.check(rc, "rnde_backward_saveat")
+        return dx, dp, None, None, None
+
+
 class TrackedNeuralODE:
     """src/models/neural_ode.jl:1-33.  ``TrackedNeuralODE(model, tspan, time_dep, regularize,
     solver; reltol, abstol, save_everystep=false, save_start=false)``."""
@@ -203,8 +238,11 @@ class TrackedNeuralODE:
                  reltol: float = 1.4e-8, abstol: float = 1.4e-8, save_everystep: bool = False, save_start: bool = False,
                  saveat=None, maxiters: int = 0, tape_capacity: int = 256, kernel_variant: int = L.KERNEL_AUTO,
                  kblock: int = 0, device: str = "cuda", dist_mode: int = L.DIST_SINGLE, rank: int = 0, world: int = 1):
-        if save_everystep or saveat is not None:
-            raise NotImplementedError("return_multiple (save_everystep/saveat) is a NEXT row (SURVEY.md 8f N1)")
+        if save_everystep:
+            raise NotImplementedError("save_everystep=true has no call site in the reference; use saveat")
+        # return_multiple = haskey(kwargs, :saveat)  (neural_ode.jl:11): fixes which functor the object dispatches to
+        self.return_multiple = saveat is not None
+        self.saveat = None if saveat is None else [float(v) for v in saveat]
         if not time_dep:
             raise NotImplementedError("the reference's fields on this path are all time dependent")
         L.require_device()
@@ -227,8 +265,8 @@ class TrackedNeuralODE:
     def parameters(self) -> torch.Tensor:
         return self.p
 
-    def _handle(self, B: int, reg_kind: int, need_backward: bool) -> _Handle:
-        key = (B, reg_kind, need_backward)
+    def _handle(self, B: int, reg_kind: int, need_backward: bool, max_saveat: int = 0) -> _Handle:
+        key = (B, reg_kind, need_backward, max_saveat)
         if key not in self._handles:
             cfg = L.Config()
             cfg.struct_bytes = C.sizeof(L.Config)
@@ -245,6 +283,7 @@ class TrackedNeuralODE:
             cfg.dist_mode, cfg.rank, cfg.nranks = self.dist_mode, self.rank, self.world
             cfg.t0, cfg.t1 = self.tspan
             cfg.abstol, cfg.reltol, cfg.dtmin = self.abstol, self.reltol, 0.0
+            cfg.max_saveat = max_saveat
             cfg.global_batch = B * (self.world if self.dist_mode == L.DIST_EXACT else 1)
             hd = _Handle(cfg)
             if self.dist_mode == L.DIST_EXACT and self.world > 1:
@@ -259,9 +298,11 @@ class TrackedNeuralODE:
 
     def __call__(self, x: torch.Tensor, p: Optional[torch.Tensor] = None, *, func: Optional[SaveFunc] = None, tspan=None,
                  saveat=None):
-        """-> (res, nfe, sv): final state (D, B), sol.destats.nf, SavedValues or None."""
-        if saveat is not None:
-            raise NotImplementedError("saveat is a NEXT row (SURVEY.md 8f N1)")
+        """-> (res, nfe, sv): final state (D, B) -- or, for a node built with ``saveat``, the states at the save
+        times as (D, nsave, B) (diffeqsol_to_3dtrackedarray, utils.jl) -- then sol.destats.nf, SavedValues or None.
+        The per-call ``saveat`` keyword replaces the stored times for this call (update_saveat!, neural_ode.jl:35-45)."""
+        if saveat is not None and not self.return_multiple:
+            raise ValueError("this node was built without saveat: its functor returns the final state only (neural_ode.jl:11)")
         p = self.p if p is None else p
         D = self.model.D
         if x.dim() != 2 or x.shape[0] != D:
@@ -275,12 +316,21 @@ class TrackedNeuralODE:
         else:
             reg_kind = L.REG_NONE                               # {false,*}: func is ignored (neural_ode.jl:51)
         need_bwd = torch.is_grad_enabled() and (x.requires_grad or p.requires_grad)
-        hd = self._handle(B, reg_kind, need_bwd)
+        times = None
+        if self.return_multiple:
+            times = self.saveat if saveat is None else [float(v) for v in (saveat.tolist() if torch.is_tensor(saveat) else saveat)]
+        hd = self._handle(B, reg_kind, need_bwd, 0 if times is None else 64 * ((len(times) + 63) // 64))
         t0, t1 = self.tspan if tspan is None else (float(tspan[0]), float(tspan[1]))
         hd.check(hd.lib.rnde_set_tspan(hd.h, t0, t1), "rnde_set_tspan")
         xbuf = colmajor(x.to(torch.float32))
-        ubuf, saveval = _Solve.apply(xbuf, p.contiguous(), self, hd)
-        res = from_colmajor(ubuf, D, B)
+        if times is None:
+            ubuf, saveval = _Solve.apply(xbuf, p.contiguous(), self, hd)
+            res = from_colmajor(ubuf, D, B)
+        else:
+            arr = (C.c_float * len(times))(*times)
+            hd.check(hd.lib.rnde_set_saveat(hd.h, arr, len(times)), "rnde_set_saveat")
+            usbuf, saveval = _SolveSaveat.apply(xbuf, p.contiguous(), self, hd, len(times))
+            res = usbuf.view(B, len(times), D).permute(2, 1, 0)        # feat x nsave x batch
         nfe = int(self.last_stats.nf)
         if not self.regularize:
             return res, nfe, None
@@ -294,7 +344,7 @@ class TrackedNeuralODE:
 
     def steps(self, B: int, reg_kind: int = L.REG_NONE, need_backward: bool = False):
         """(t, dt, EEst, eigen_est) of every accepted step of the last solve on that handle."""
-        hd = self._handles[(B, reg_kind, need_backward)]
+        hd = next(h for k, h in self._handles.items() if k[:3] == (B, reg_kind, need_backward))
         n = int(self.last_stats.naccept)
         arrs = [(C.c_float * max(n, 1))() for _ in range(4)]
         hd.check(hd.lib.rnde_get_steps(hd.h, *arrs, n), "rnde_get_steps")

@@ -194,6 +194,75 @@ def test_mnist_training_step_against_oracle(oracle_built):
     assert rel(pp2.grad.cpu().numpy(), dp2_hi) <= max(1e-4, 10 * rel(dp2_32, dp2_hi))
 
 
+SAVEAT_CASES = [
+    # name, D, H, B, act_out, auto, func, variant, saveat
+    ("toy unreg, t0 and t1 saved", 2, 10, 5, 0, False, None, 0, [0.0, 0.1, 0.25, 0.5, 0.75, 1.0]),
+    ("toy errreg, interior only", 2, 10, 7, 0, False, "ERROR_ESTIMATE", 0, [0.05, 0.3, 0.31, 0.32, 0.9]),
+    ("latent-sized stiffreg, 40 irregular times", 20, 50, 100, 1, True, "ERROR_PLUS_STIFFNESS", 0, None),
+    ("mnist-sized B=32 cluster8", 784, 100, 32, 1, False, "ERROR_ESTIMATE", 3, [0.0, 0.2, 0.6, 1.0]),
+    ("toy streamed weights", 2, 10, 33, 0, False, "ERROR_ESTIMATE", 2, [0.5, 1.0]),
+]
+
+
+@pytest.mark.parametrize("name,D,H,B,act_out,auto,func,variant,saveat", SAVEAT_CASES, ids=[c[0] for c in SAVEAT_CASES])
+def test_saveat_multi_save_functors(oracle_built, name, D, H, B, act_out, auto, func, variant, saveat):
+    """The {false,true} / {true,true} functors (neural_ode.jl:79-108,146-180; call site time_series.jl:51): res is
+    feat x nsave x batch, saved states bit-identical to the oracle's dense output, gradient of a weighted sum of all
+    saved states (+ saved regulariser values) against the oracle adjoint."""
+    r = R()
+    rng = np.random.default_rng(42)
+    if saveat is None:      # irregular observation times like the PhysioNet grid (latent_ode.jl:137)
+        saveat = np.unique(np.round(np.sort(rng.random(40)), 3)).astype(np.float32).tolist()
+    sa32 = np.asarray(saveat, np.float32)
+    p_np = orc.glorot_params(rng, D, H)
+    x_np = rng.random((D, B), dtype=np.float32)
+    regularize = func is not None
+    solver = r.AutoTsit5() if auto else r.Tsit5()
+    model = r.TDChain(r.Dense(D + 1, H, "tanh"), r.Dense(H + 1, D, "tanh" if act_out else None))
+    node = r.TrackedNeuralODE(model, [0.0, 1.0], True, regularize, solver, saveat=sa32.tolist(), reltol=1.4e-8, abstol=1.4e-8,
+                              kernel_variant=variant)
+    fobj = getattr(r, func) if func else None
+    reg_kind = fobj.kind if fobj else orc.REG_NONE
+    x = torch.from_numpy(x_np).cuda().requires_grad_(True)
+    p = torch.from_numpy(p_np).cuda().requires_grad_(True)
+    res, nfe, sv = node(x, p, func=fobj)
+    cfg = oracle_cfg(D, H, B, act_out, 1 if auto else 0, reg_kind)
+    cfg.saveat = sa32.astype(np.float64)
+    o = orc.Oracle(cfg)
+    ref = o.forward(x_np, p_np)
+    assert tuple(res.shape) == (D, len(sa32), B)                       # feat x nsave x batch
+    assert (nfe, node.last_stats.naccept) == (ref.nf, ref.naccept)     # saveat adds no tstops: same steps as without it
+    got = res.detach().permute(1, 0, 2).cpu().numpy()                  # -> (nsave, D, B) like the oracle
+    assert ref.usave.shape == got.shape
+    assert np.array_equal(bits(got), bits(ref.usave)), "saved states not bit-identical"
+    if sa32[0] == 0.0:
+        assert np.array_equal(bits(got[0]), bits(x_np))                # save_start: tspan[1] in saveat
+    if regularize:
+        assert np.array_equal(bits(sv.saveval.detach().cpu().numpy()), bits(ref.saveval))
+    w = rng.standard_normal(ref.usave.shape).astype(np.float32)
+    ws = rng.standard_normal(len(ref.saveval) if regularize else 1).astype(np.float32)
+    loss = (res * torch.from_numpy(np.ascontiguousarray(w.transpose(1, 0, 2))).cuda()).sum()
+    if regularize:
+        loss = loss + (sv.saveval * torch.from_numpy(ws).cuda()).sum()
+    loss.backward()
+    torch.cuda.synchronize()
+    zeros = np.zeros((D, B), np.float32)
+    dp_hi, dx_hi, _, _ = o.backward(zeros, ws if regularize else None, hi=True, dusave=w)
+    dp_32, dx_32, _, _ = o.backward(zeros, ws if regularize else None, dusave=w)
+    rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()
+    e_p, e_x = rel(p.grad.cpu().numpy(), dp_hi), rel(x.grad.cpu().numpy(), dx_hi)
+    c_p, c_x = rel(dp_32, dp_hi), rel(dx_32, dx_hi)
+    assert e_p <= max(1e-4, 10 * c_p) and e_x <= max(1e-4, 10 * c_x), (e_p, c_p, e_x, c_x)
+    if not regularize:
+        assert e_p <= 1e-4 and e_x <= 1e-4, (e_p, e_x)
+    # per-call saveat keyword (update_saveat!): a different grid on the same node, then the stored grid is back
+    with torch.no_grad():
+        res2, _, _ = node(x.detach(), p.detach(), func=fobj, saveat=[0.5])
+        res3, _, _ = node(x.detach(), p.detach(), func=fobj)
+    assert tuple(res2.shape) == (D, 1, B) and tuple(res3.shape) == tuple(res.shape)
+    assert torch.equal(res3, res.detach())
+
+
 def test_update_parameters_matches_flux_momentum():
     """Optimiser(InvDecay(1e-5), Momentum(0.1, 0.9)) on raw arrays, empty parameter vectors skipped (src/utils.jl:149-156)."""
     r = R()

@@ -77,3 +77,43 @@ def test_first_saved_value_conventions(oracle_built):
     stab = np.float32(1) / np.float32(3.5068)
     assert first[orc.REG_STIFF_SCALED] == stab
     assert first[orc.REG_ERR_PLUS_STIFF] == np.float32(0.1) * stab
+
+
+@pytest.mark.parametrize("reg,alg", [(orc.REG_NONE, 0), (orc.REG_ERR_DT, 0), (orc.REG_ERR_PLUS_STIFF, 1)])
+def test_saveat_dense_output_matches_autograd_fp64(oracle_built, reg, alg):
+    """Multi-save functors (neural_ode.jl:79-108,146-180): the C oracle's saved states (Tsit5 free interpolant,
+    SURVEY.md Appendix A.9) and their adjoint against torch autograd in FP64; saveat must not change the steps."""
+    torch.set_default_dtype(torch.float64)
+    rng = np.random.default_rng(11)
+    D, H, B = 5, 8, 3
+    sa = np.array([0.0, 0.07, 0.4, 0.41, 0.93, 1.0])
+    p = orc.glorot_params(rng, D, H, dtype=np.float64) * 1.5
+    x = rng.random((D, B))
+    cfg = orc.OracleConfig(D=D, H=H, B=B, reg_kind=reg, alg=alg, saveat=sa)
+    o = orc.Oracle(cfg, f64=True)
+    r = o.forward(x, p)
+    plain = orc.Oracle(orc.OracleConfig(D=D, H=H, B=B, reg_kind=reg, alg=alg), f64=True).forward(x, p)
+    assert (r.nf, r.naccept, r.nreject) == (plain.nf, plain.naccept, plain.nreject)      # no tstops added
+    assert np.array_equal(r.usave[0], x) and np.array_equal(r.usave[-1], plain.u)          # t0 -> input, t1 -> copy of u
+    pt = torch.tensor(p, requires_grad=True); xt = torch.tensor(x, requires_grad=True)
+    tr = to.solve(xt, pt, D=D, H=H, reg_kind=reg, auto_tsit5=bool(alg), saveat=sa)
+    us = torch.stack(tr.usave)
+    assert np.abs(r.usave - us.detach().numpy()).max() < 1e-12
+    w = rng.standard_normal(r.usave.shape)
+    loss = (us * torch.tensor(w)).sum()
+    ws = None
+    if reg != orc.REG_NONE:
+        ws = rng.standard_normal(len(r.saveval))
+        loss = loss + (torch.stack(tr.saveval) * torch.tensor(ws)).sum()
+    gp, gx = torch.autograd.grad(loss, [pt, xt])
+    dp, dx, _, _ = o.backward(np.zeros((D, B)), ws, dusave=w)
+    assert np.abs(dp - gp.numpy()).max() <= 1e-7 * np.abs(gp.numpy()).max()
+    assert np.abs(dx - gx.numpy()).max() <= 1e-7 * np.abs(gx.numpy()).max()
+    torch.set_default_dtype(torch.float32)
+
+
+def test_free_interpolant_endpoint_identities():
+    """b_i(1) = a_7i (the interpolant ends on the step's new state) and b_i(0) = 0."""
+    b1 = to.interp_weights(1.0)
+    assert np.allclose(b1[:6], to.A[7], atol=1e-14) and abs(b1[6]) < 1e-14
+    assert all(v == 0.0 for v in to.interp_weights(0.0))
