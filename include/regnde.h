@@ -67,7 +67,8 @@ enum { RNDE_REG_NONE = 0, RNDE_REG_ERR_DT = 1, RNDE_REG_STIFF_DT_ABS = 2, RNDE_R
 /* CTA: weights + state of a column tile in one CTA's shared memory (small fields);
  * STREAM: weights streamed from L2 (any size, slow fallback); CLUSTER: 8-CTA clusters, state in
  * distributed shared memory; CLUSTER4: 4-CTA clusters, state in registers (MNIST-shaped fields). */
-enum { RNDE_KERNEL_AUTO = 0, RNDE_KERNEL_CTA = 1, RNDE_KERNEL_STREAM = 2, RNDE_KERNEL_CLUSTER = 3, RNDE_KERNEL_CLUSTER4 = 4 };
+enum { RNDE_KERNEL_AUTO = 0, RNDE_KERNEL_CTA = 1, RNDE_KERNEL_STREAM = 2, RNDE_KERNEL_CLUSTER = 3, RNDE_KERNEL_CLUSTER4 = 4,
+       RNDE_KERNEL_CHAIN = 5 /* CTA variant with 4-column tiles: chain fields, one CTA per SM at batch 512 */ };
 enum { RNDE_DIST_SINGLE = 0, RNDE_DIST_EXACT = 1, RNDE_DIST_INDEPENDENT = 2 };
 
 typedef struct rnde_config {
@@ -91,8 +92,16 @@ typedef struct rnde_config {
     float abstol, reltol;     /* solver kwargs */
     float dtmin;              /* 0 = 1e-10 */
     int32_t max_saveat;       /* > 0: the handle serves the multi-save functors (saveat keyword); sizes the saveat buffer */
-    int32_t reserved0;
+    int32_t n_layers;         /* 0: the 2-layer time-concatenated field above; 1..8: chain field, see layer_width */
     int64_t global_batch;     /* columns over all ranks (EXACT mode); 0 = batch */
+    /* chain field (n_layers > 0): Flux Chain of Dense layers evaluated as re(p)(u), time_dep = 0 -- the Latent-ODE
+     * generator dynamics (experiments/latent_ode.jl:109-121).  Layer l maps layer_width[l-1] -> layer_width[l]
+     * (layer_width[-1] = layer_width[n_layers-1] = state_dim), activation layer_act[l] (RNDE_ACT_*); pre_act = RNDE_ACT_TANH
+     * applies the leading `x -> tanh.(x)`.  p in Flux.destructure order: W_l (out x in, column-major), b_l.  hidden_dim is ignored. */
+    int32_t pre_act;
+    int32_t layer_width[8];
+    int32_t layer_act[8];
+    int32_t reserved1;
 } rnde_config;
 
 typedef struct rnde_stats {

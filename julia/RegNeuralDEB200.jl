@@ -25,8 +25,9 @@ struct RndeConfig
     need_backward::Int32; kernel_variant::Int32; dist_mode::Int32
     rank::Int32; nranks::Int32
     t0::Float32; t1::Float32; abstol::Float32; reltol::Float32; dtmin::Float32
-    max_saveat::Int32; reserved0::Int32
+    max_saveat::Int32; n_layers::Int32
     global_batch::Int64
+    pre_act::Int32; layer_width::NTuple{8,Int32}; layer_act::NTuple{8,Int32}; reserved1::Int32
 end
 
 mutable struct RndeStats
@@ -77,7 +78,7 @@ end
 function handle!(n::TrackedNeuralODE, D, H, B, reg_kind, need_backward, layers)
     get!(n.handles, (B, reg_kind, need_backward)) do
         cfg = Ref(RndeConfig(sizeof(RndeConfig), D, H, B, _act(layers[1]), _act(layers[2]), 1, 0, n.alg, reg_kind, 0, 256,
-                             need_backward, 0, 0, 0, 1, n.tspan[1], n.tspan[2], n.abstol, n.reltol, 0f0, 0, 0, B))
+                             need_backward, 0, 0, 0, 1, n.tspan[1], n.tspan[2], n.abstol, n.reltol, 0f0, 0, 0, B, 0, ntuple(_ -> Int32(0), 8), ntuple(_ -> Int32(0), 8), 0))
         h = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:rnde_create, LIB), Cint, (Ref{RndeConfig}, Ref{Ptr{Cvoid}}), cfg, h))
         h[]

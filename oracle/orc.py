@@ -32,6 +32,7 @@ class _Cfg(C.Structure):
         ("dtmin", C.c_double),
         ("n_forced", C.c_int), ("forced_dt", C.POINTER(C.c_double)), ("forced_accept", C.POINTER(C.c_int)),
         ("n_saveat", C.c_int), ("saveat", C.POINTER(C.c_double)),
+        ("n_layers", C.c_int), ("width", C.c_int * 8), ("act", C.c_int * 8), ("pre_act", C.c_int),
     ]
 
 
@@ -85,9 +86,19 @@ class OracleConfig:
     forced_dt: np.ndarray | None = None
     forced_accept: np.ndarray | None = None
     saveat: np.ndarray | None = None
+    # chain field: widths of the Dense layers (last == D), their activations, tanh pre-activation flag
+    widths: tuple | None = None
+    acts: tuple | None = None
+    pre_act: int = 0
 
     @property
     def n_params(self) -> int:
+        if self.widths is not None:
+            n, K = 0, self.D
+            for M in self.widths:
+                n += M * K + M
+                K = M
+            return n
         td = 1 if self.time_dep else 0
         return self.H * (self.D + td) + self.H + self.D * (self.H + td) + self.D
 
@@ -131,6 +142,15 @@ class Oracle:
             c.n_forced = len(fd)
             c.forced_dt = fd.ctypes.data_as(C.POINTER(C.c_double))
             c.forced_accept = fa.ctypes.data_as(C.POINTER(C.c_int))
+        if cfg.widths is not None:
+            assert cfg.widths[-1] == cfg.D and len(cfg.widths) <= 8
+            c.n_layers = len(cfg.widths)
+            for i, wdt in enumerate(cfg.widths):
+                c.width[i] = int(wdt)
+                c.act[i] = int(cfg.acts[i]) if cfg.acts is not None else ACT_TANH
+            c.pre_act = int(cfg.pre_act)
+            c.time_dep = 0
+            c.H = max(cfg.widths)
         if cfg.saveat is not None:
             sa = np.ascontiguousarray(cfg.saveat, dtype=np.float64)
             self._keep.append(sa)
@@ -251,3 +271,15 @@ def glorot_params(rng: np.random.Generator, D: int, H: int, time_dep: bool = Tru
     W1 = glorot(H, D + td)
     W2 = glorot(D, H + td)
     return np.concatenate([W1.flatten(order="F"), np.zeros(H, dtype), W2.flatten(order="F"), np.zeros(D, dtype)]).astype(dtype)
+
+
+def glorot_chain_params(rng: np.random.Generator, D: int, widths, dtype=np.float32, bias_scale: float = 0.0) -> np.ndarray:
+    """Parameters of Chain(Dense(D,w0), Dense(w0,w1), ...) in Flux.destructure order (W_l column-major out x in, b_l);
+    glorot_uniform weights; biases zero like Flux's default unless bias_scale is given (tests exercise db too)."""
+    parts, K = [], D
+    for M in widths:
+        s = np.sqrt(6.0 / (K + M))
+        parts.append(rng.uniform(-s, s, size=(M, K)).astype(dtype).flatten(order="F"))
+        parts.append((bias_scale * rng.standard_normal(M)).astype(dtype))
+        K = M
+    return np.concatenate(parts).astype(dtype)

@@ -78,6 +78,14 @@ typedef struct {
      * [t0,t1]; a time equal to a step end copies u, others use the Tsit5 free interpolant; t0 in saveat saves u0 */
     int n_saveat;
     const double* saveat;
+    /* chain field (n_layers > 0): Flux Chain of Dense layers without time input, width[l-1] -> width[l] with
+     * width[-1] = width[n_layers-1] = D, optional elementwise tanh on the input first -- the Latent-ODE generator
+     * dynamics Chain(x -> tanh.(x), Dense(20,50,tanh), ..., Dense(50,20,tanh)) (experiments/latent_ode.jl:109-121),
+     * called as re(p)(u) because time_dep = false (neural_ode.jl:57).  H must hold max(width). */
+    int n_layers;
+    int width[8];
+    int act[8];
+    int pre_act;
 } orc_config;
 
 typedef struct {
@@ -105,6 +113,11 @@ typedef struct {
 
 static size_t n_params(const orc_config* c) {
     int td = c->time_dep ? 1 : 0;
+    if (c->n_layers > 0) {
+        size_t n = 0;
+        for (int l = 0; l < c->n_layers; ++l) { const int K = l ? c->width[l - 1] : c->D; n += (size_t)c->width[l] * K + c->width[l]; }
+        return n;
+    }
     return (size_t)c->H * (c->D + td) + c->H + (size_t)c->D * (c->H + td) + c->D;
 }
 
@@ -160,8 +173,41 @@ static REAL rms_from_total(REAL tot, long long count) { return R_SQRT(tot / (REA
 static REAL act_apply(int act, REAL s) { return act == ACT_TANH ? R_TANH(s) : s; }
 
 /* z: D x B (col-major), out k: D x B, optional hout: H x B */
+/* chain field, one column: a_0 = pre(z); a_l = act_l(W_l a_{l-1} + b_l).  Canonical order: one fma chain over the
+ * inputs in ascending order starting from 0, then + bias, then the activation.  acts (may be NULL) receives
+ * a_0 .. a_{L-1} back to back (the last entry is the output). */
+static void chain_column(const orc_config* c, const REAL* p, const REAL* zj, REAL* out, REAL* acts) {
+    REAL a[2][1024];
+    int cur = 0;
+    const int D = c->D;
+    for (int i = 0; i < D; ++i) a[0][i] = c->pre_act == ACT_TANH ? act_apply(ACT_TANH, zj[i]) : zj[i];
+    size_t ao = 0;
+    if (acts) { memcpy(acts, a[0], sizeof(REAL) * D); ao = D; }
+    const REAL* W = p;
+    int K = D;
+    for (int l = 0; l < c->n_layers; ++l) {
+        const int M = c->width[l];
+        const REAL* b = W + (size_t)M * K;
+        for (int o = 0; o < M; ++o) {
+            REAL acc = 0;
+            for (int i = 0; i < K; ++i) acc = R_FMA(W[(size_t)M * i + o], a[cur][i], acc);
+            a[cur ^ 1][o] = act_apply(c->act[l], acc + b[o]);
+        }
+        cur ^= 1;
+        if (acts) { memcpy(acts + ao, a[cur], sizeof(REAL) * M); ao += M; }
+        W = b + M; K = M;
+    }
+    memcpy(out, a[cur], sizeof(REAL) * D);
+}
+
 static void rhs_eval(const orc_config* c, const REAL* p, const REAL* z, REAL t, REAL* k, REAL* hout) {
     const int D = c->D, H = c->H, B = c->B, td = c->time_dep ? 1 : 0;
+    if (c->n_layers > 0) {
+        (void)t; (void)hout;
+#pragma omp parallel for schedule(static)
+        for (int j = 0; j < B; ++j) chain_column(c, p, z + (size_t)D * j, k + (size_t)D * j, NULL);
+        return;
+    }
     const REAL* W1 = p;
     const REAL* b1 = W1 + (size_t)H * (D + td);
     const REAL* W2 = b1 + H;

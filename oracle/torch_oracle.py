@@ -78,6 +78,20 @@ def field(p, z, t, D, H, act2_tanh=True, time_dep=True):
     return torch.tanh(y) if act2_tanh else y
 
 
+def chain_field(p, z, D, widths, acts, pre_act):
+    """Chain([x -> tanh.(x),] Dense(D,w0,act0), ...)(z) with p in Flux.destructure order (latent_ode.jl:109-121)."""
+    a = torch.tanh(z) if pre_act else z
+    o, K = 0, D
+    for M, act in zip(widths, acts):
+        W = p[o:o + M * K].reshape(K, M).T; o += M * K
+        b = p[o:o + M]; o += M
+        a = W @ a + b[:, None]
+        if act:
+            a = torch.tanh(a)
+        K = M
+    return a
+
+
 R = [[1.0, -2.763706197274826, 2.9132554618219126, -1.0530884977290216],
      [0.13169999999999998, -0.2234, 0.1017], [3.9302962368947516, -5.941033872131505, 2.490627285651253],
      [-12.411077166933676, 30.33818863028232, -16.548102889244902], [37.50931341651104, -88.1789048947664, 47.37952196281928],
@@ -115,7 +129,7 @@ def saved_value(kind, EEst, eig, dt, dtype):
 
 def solve(x, p, *, D, H, act2_tanh=True, time_dep=True, t0=0.0, t1=1.0, abstol=1.4e-8, reltol=1.4e-8,
           auto_tsit5=False, reg_kind=REG_NONE, detach="all", forced_dt=None, forced_accept=None,
-          dt_leaf=None, max_steps=100000, saveat=None) -> TorchResult:
+          dt_leaf=None, max_steps=100000, saveat=None, chain=None) -> TorchResult:
     """x: (D,B) tensor, p: flat parameter tensor (Flux.destructure order).
 
     forced_dt/forced_accept replay a recorded attempt sequence (controller
@@ -125,6 +139,8 @@ def solve(x, p, *, D, H, act2_tanh=True, time_dep=True, t0=0.0, t1=1.0, abstol=1
     """
     dtype = x.dtype
     f = lambda z, t: field(p, z, t, D, H, act2_tanh, time_dep)
+    if chain is not None:       # (widths, acts, pre_act): field without time input
+        f = lambda z, t: chain_field(p, z, D, chain[0], chain[1], chain[2])
     c = lambda v: torch.tensor(v, dtype=dtype)
     t = c(t0)
     tf = c(t1)

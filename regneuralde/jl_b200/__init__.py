@@ -8,11 +8,11 @@ the host-side mirror of the reference's Julia surface for that path.  No CPU fal
 from . import _lib
 from ._lib import RndeError, build, lib
 from .node import (AutoTsit5, Dense, ERROR_ESTIMATE, ERROR_PLUS_STIFFNESS, MLPDynamics, STIFFNESS_ESTIMATE, STIFFNESS_SCALED,
-                   SavedValues, SaveFunc, TDChain, TrackedNeuralODE, Tsit5, colmajor, from_colmajor, track, untrack)
+                   SavedValues, SaveFunc, TDChain, Chain, TrackedNeuralODE, Tsit5, colmajor, from_colmajor, track, untrack)
 from .classifier import ClassifierNODE, Optimiser, update_parameters_
 
 __all__ = [
-    "RndeError", "build", "lib", "AutoTsit5", "Tsit5", "Dense", "TDChain", "MLPDynamics", "TrackedNeuralODE", "SavedValues", "SaveFunc",
+    "RndeError", "build", "lib", "AutoTsit5", "Tsit5", "Dense", "TDChain", "Chain", "MLPDynamics", "TrackedNeuralODE", "SavedValues", "SaveFunc",
     "ERROR_ESTIMATE", "STIFFNESS_ESTIMATE", "STIFFNESS_SCALED", "ERROR_PLUS_STIFFNESS", "ClassifierNODE", "Optimiser",
     "update_parameters_", "track", "untrack", "colmajor", "from_colmajor",
 ]

@@ -29,7 +29,7 @@ OK, ERR_MAXITERS, ERR_DTMIN, ERR_NAN, ERR_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_TA
 ACT_IDENTITY, ACT_TANH = 0, 1
 ALG_TSIT5, ALG_AUTO_TSIT5 = 0, 1
 REG_NONE, REG_ERR_DT, REG_STIFF_DT_ABS, REG_STIFF_SCALED, REG_ERR_PLUS_STIFF = range(5)
-KERNEL_AUTO, KERNEL_CTA, KERNEL_STREAM, KERNEL_CLUSTER, KERNEL_CLUSTER4 = range(5)
+KERNEL_AUTO, KERNEL_CTA, KERNEL_STREAM, KERNEL_CLUSTER, KERNEL_CLUSTER4, KERNEL_CHAIN = range(6)
 DIST_SINGLE, DIST_EXACT, DIST_INDEPENDENT = range(3)
 
 EXPORTS = [
@@ -49,8 +49,9 @@ class Config(C.Structure):
         ("need_backward", C.c_int32), ("kernel_variant", C.c_int32), ("dist_mode", C.c_int32),
         ("rank", C.c_int32), ("nranks", C.c_int32),
         ("t0", C.c_float), ("t1", C.c_float), ("abstol", C.c_float), ("reltol", C.c_float), ("dtmin", C.c_float),
-        ("max_saveat", C.c_int32), ("reserved0", C.c_int32),
+        ("max_saveat", C.c_int32), ("n_layers", C.c_int32),
         ("global_batch", C.c_int64),
+        ("pre_act", C.c_int32), ("layer_width", C.c_int32 * 8), ("layer_act", C.c_int32 * 8), ("reserved1", C.c_int32),
     ]
 
 

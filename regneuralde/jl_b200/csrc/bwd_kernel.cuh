@@ -12,6 +12,7 @@
 // (wgrad_kernel.cuh) instead of rank-NP updates inside this latency-bound sweep.
 #pragma once
 #include "common.cuh"
+#include "chain.cuh"
 
 namespace rnde {
 
@@ -72,7 +73,12 @@ __global__ void __launch_bounds__(NT, 1) bwd_kernel(const KParams P) {
     auto tile_off_D = [&](int rec) -> size_t { return ((size_t)rec * P.Q + q) * tileD + (size_t)r0 * NP; };
     auto tile_off_H = [&](int rec) -> size_t { return ((size_t)rec * P.Q + q) * tileH; };
 
-    if constexpr (WS) {
+    const bool chain = (G == 1) && P.n_layers > 0;
+    ChainView cv;
+    cv.L = P.n_layers; cv.D = D; cv.NP = NP; cv.hrows = P.hrows; cv.w = P.lw; cv.a = P.la; cv.pre = P.pre_act;
+    cv.sW = smem + P.oCW; cv.sA = smem + P.oCA; cv.sB = smem + P.oCB;
+    if (chain) for (int e = tid; e < P.chain_np; e += NT) smem[P.oCW + e] = __ldg(P.p + e);
+    if constexpr (WS) if (!chain) {
         for (int e = tid; e < R * HP; e += NT) {       // W2T[k][m] = W2[r0+k, m]
             const int k = e / HP, m = e - k * HP;
             sW2T[e] = (k < Rloc && m < H) ? __ldg(gW2 + (size_t)D * m + r0 + k) : 0.f;
@@ -96,6 +102,17 @@ __global__ void __launch_bounds__(NT, 1) bwd_kernel(const KParams P) {
     // VJP of one field evaluation (record `rec`).  On entry Kb(i) holds kbar_i; it is
     // turned into delta2 in place.  `epi(m, n0, zbar[4])` consumes zbar = W1^T delta1.
     auto vjp = [&](float* sKbar, const int rec, auto epi) {
+        if constexpr (G == 1 && WS) {
+            if (chain) {
+                const float* zb = chain_vjp<NP, NT>(P, cv, sKbar, rec, q);
+                for (int e = tid; e < Rloc * (NP / 4); e += NT) {
+                    const int m = e / (NP / 4), nn = (e - m * (NP / 4)) * 4;
+                    epi(m, nn, zb + m * NP + nn);
+                }
+                __syncthreads();
+                return;
+            }
+        }
         const size_t offD = tile_off_D(rec), offH = tile_off_H(rec);
         for (int e = tid; e < Rloc * NP; e += NT) {
             const float kb = sKbar[e];

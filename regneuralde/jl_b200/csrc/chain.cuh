@@ -1,0 +1,178 @@
+// chain.cuh -- field evaluation and VJP for "chain" fields: a Flux Chain of up to 8 Dense layers without time
+// input, optionally preceded by an elementwise tanh -- the Latent-ODE generator dynamics
+//   Chain(x -> tanh.(x), Dense(20,50,tanh), Dense(50,20,tanh), ... x8)      /root/reference/experiments/latent_ode.jl:109-121
+// evaluated as re(p)(u) because the node is built with time_dep = false (src/models/neural_ode.jl:57,88,119,155).
+// All weights (8 280 floats for the reference's shape) live in shared memory for the whole solve; one CTA owns a tile
+// of NP columns and one thread one (output row, column) element of a layer.
+// Canonical arithmetic (oracle/rnde_oracle.c chain_column): one fma chain over the inputs in ascending order starting
+// from 0, then + bias, then the activation.
+#pragma once
+#include "common.cuh"
+
+namespace rnde {
+
+struct ChainView {
+    int L, D, NP, hrows;
+    const int* w;      // widths
+    const int* a;      // activations
+    int pre;
+    const float* sW;   // all parameters, Flux.destructure order
+    float* sA; float* sB;   // ping-pong activations, maxw x NP each
+};
+
+// sOut = f(sIn).  rec >= 0: record z, a_0..a_{L-2} and k on the tape ([rec][tile][row][NP]).
+template <int NP, int NT>
+__device__ __forceinline__ void chain_rhs(const KParams& P, const ChainView& c, const float* sIn, float* sOut, const int rec, const int q) {
+    const int tid = threadIdx.x;
+    const int D = c.D;
+    float* cur = c.sA; float* nxt = c.sB;
+    const size_t hbase = ((size_t)max(rec, 0) * P.Q + q) * c.hrows * NP;
+    const size_t dbase = ((size_t)max(rec, 0) * P.Q + q) * D * NP;
+    for (int e = tid; e < D * NP; e += NT) {
+        const float z = sIn[e];
+        const float a0 = c.pre == RNDE_ACT_TANH ? canon_tanhf(z) : z;
+        cur[e] = a0;
+        if (rec >= 0) { P.tapeZ[dbase + e] = z; P.tapeH[hbase + e] = a0; }
+    }
+    __syncthreads();
+    const float* W = c.sW;
+    int K = D, hoff = D;
+    for (int l = 0; l < c.L; ++l) {
+        const int M = c.w[l];
+        const float* b = W + M * K;
+        const bool last = (l == c.L - 1);
+        float* dst = last ? sOut : nxt;
+        for (int e = tid; e < M * NP; e += NT) {
+            const int o = e / NP, n = e - o * NP;
+            float acc = 0.f;
+#pragma unroll 4
+            for (int i = 0; i < K; ++i) acc = rn_fmaf(W[M * i + o], cur[i * NP + n], acc);
+            float v = acc + b[o];
+            if (c.a[l] == RNDE_ACT_TANH) v = canon_tanhf(v);
+            dst[e] = v;
+            if (rec >= 0) {
+                if (last) P.tapeK[dbase + e] = v;
+                else P.tapeH[hbase + (size_t)hoff * NP + e] = v;
+            }
+        }
+        __syncthreads();
+        if (!last) { float* t = cur; cur = nxt; nxt = t; hoff += M; }
+        W = b + M; K = M;
+    }
+}
+
+// VJP of record `rec`: on entry sKbar holds kbar (D x NP); delta_{L-1} replaces k on the tape, delta_l (l < L-1) goes
+// to tapeD1 at the row offset of a_{l+1}; the input cotangent ends up in c.sA (D x NP) -- the caller applies it.
+template <int NP, int NT>
+__device__ __forceinline__ const float* chain_vjp(const KParams& P, const ChainView& c, float* sKbar, const int rec, const int q) {
+    const int tid = threadIdx.x;
+    const int D = c.D;
+    const size_t hbase = ((size_t)rec * P.Q + q) * c.hrows * NP;
+    const size_t dbase = ((size_t)rec * P.Q + q) * D * NP;
+    // parameter / activation-row offsets of every layer
+    int poff[9], hoff[9];
+    poff[0] = 0; hoff[0] = 0;
+    {
+        int K = D;
+        for (int l = 0; l < c.L; ++l) { poff[l + 1] = poff[l] + c.w[l] * K + c.w[l]; hoff[l + 1] = hoff[l] + K; K = c.w[l]; }
+    }
+    float* g = c.sB; float* gn = c.sA;
+    for (int e = tid; e < D * NP; e += NT) {
+        float d = sKbar[e];
+        if (c.a[c.L - 1] == RNDE_ACT_TANH) { const float kv = __ldcg(P.tapeK + dbase + e); d = d * (1.f - kv * kv); }
+        g[e] = d;
+        P.tapeK[dbase + e] = d;
+    }
+    __syncthreads();
+    for (int l = c.L - 1; l >= 0; --l) {
+        const int K = l ? c.w[l - 1] : D, M = c.w[l];
+        const float* W = c.sW + poff[l];
+        for (int e = tid; e < K * NP; e += NT) {
+            const int i = e / NP, n = e - i * NP;
+            float acc = 0.f;
+#pragma unroll 4
+            for (int o = 0; o < M; ++o) acc = rn_fmaf(W[M * i + o], g[o * NP + n], acc);
+            // derivative of the activation that produced this layer's input (layer l-1's, or the pre-activation)
+            const int actin = l ? c.a[l - 1] : c.pre;
+            if (actin == RNDE_ACT_TANH) { const float av = __ldcg(P.tapeH + hbase + (size_t)hoff[l] * NP + e); acc = acc * (1.f - av * av); }
+            gn[e] = acc;
+            if (l) P.tapeD1[hbase + (size_t)hoff[l] * NP + e] = acc;
+        }
+        __syncthreads();
+        float* t = g; g = gn; gn = t;
+    }
+    return g;
+}
+
+// Parameter gradients of a chain field from the tape: for every layer dW_l = sum over (record, column) of
+// delta_l a_l^T and db_l = sum delta_l.  grid = (splits, L); a CTA walks a contiguous range of (record, tile) pairs,
+// stages 64 columns at a time and every thread owns up to CW_OUT (output, input) pairs; partial sums are FP32 over one
+// stage and FP64 across stages (the regulariser cotangents cancel between records: DESIGN.md section 5).
+constexpr int CW_NT = 256, CW_COLS = 64, CW_LD = 68, CW_OUT = 6;   // CW_LD: padded row stride (conflict-free LDS.128)
+__global__ void __launch_bounds__(CW_NT) chain_wgrad_kernel(const KParams P, const int NPt, const int nrec, double* __restrict__ acc_out) {
+    extern __shared__ __align__(16) float csm[];
+    const int tid = threadIdx.x, l = blockIdx.y, L = P.n_layers, D = P.D;
+    int poff = 0, hoff = 0, K = D;
+    for (int j = 0; j < l; ++j) { poff += P.lw[j] * K + P.lw[j]; hoff += K; K = P.lw[j]; }
+    const int M = P.lw[l];
+    const bool last = (l == L - 1);
+    float* sDel = csm;                      // M x CW_COLS
+    float* sAct = csm + M * CW_LD;        // (K+1) x CW_COLS, last row = 1 (bias)
+    const int tiles_per_stage = CW_COLS / NPt;
+    const long long ntile = (long long)nrec * P.Q;
+    const long long nstage = (ntile + tiles_per_stage - 1) / tiles_per_stage;
+    const long long s0 = nstage * blockIdx.x / gridDim.x, s1 = nstage * (blockIdx.x + 1) / gridDim.x;
+    const int nout = M * (K + 1);
+    double acc[CW_OUT];
+#pragma unroll
+    for (int r = 0; r < CW_OUT; ++r) acc[r] = 0.0;
+    const size_t hstride = (size_t)P.hrows * NPt, dstride = (size_t)D * NPt;
+    for (long long s = s0; s < s1; ++s) {
+        const long long t0 = s * tiles_per_stage;
+        __syncthreads();
+        for (int e = tid; e < M * CW_COLS; e += CW_NT) {
+            const int tl = e / (M * NPt), rem = e - tl * (M * NPt), o = rem / NPt, n = rem - o * NPt;
+            const long long tile = t0 + tl;
+            float v = 0.f;
+            if (tile < ntile) v = last ? __ldcg(P.tapeK + (size_t)tile * dstride + (size_t)o * NPt + n)
+                                       : __ldcg(P.tapeD1 + (size_t)tile * hstride + (size_t)(hoff + K + o) * NPt + n);
+            sDel[o * CW_LD + tl * NPt + n] = v;
+        }
+        for (int e = tid; e < (K + 1) * CW_COLS; e += CW_NT) {
+            const int tl = e / ((K + 1) * NPt), rem = e - tl * ((K + 1) * NPt), i = rem / NPt, n = rem - i * NPt;
+            const long long tile = t0 + tl;
+            float v = 0.f;
+            if (tile < ntile) v = (i == K) ? 1.f : __ldcg(P.tapeH + (size_t)tile * hstride + (size_t)(hoff + i) * NPt + n);
+            sAct[i * CW_LD + tl * NPt + n] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < CW_OUT; ++r) {
+            const int e = tid + r * CW_NT;
+            if (e < nout) {
+                const int i = e / M, o = e - i * M;       // Flux order: column-major out x in, bias after the weights
+                const float4* d4 = reinterpret_cast<const float4*>(sDel + o * CW_LD);
+                const float4* a4 = reinterpret_cast<const float4*>(sAct + i * CW_LD);
+                float s32 = 0.f;
+#pragma unroll
+                for (int c4 = 0; c4 < CW_COLS / 4; ++c4) {
+                    const float4 dv = d4[c4], av = a4[c4];
+                    s32 = fmaf(dv.x, av.x, s32); s32 = fmaf(dv.y, av.y, s32); s32 = fmaf(dv.z, av.z, s32); s32 = fmaf(dv.w, av.w, s32);
+                }
+                acc[r] += (double)s32;
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < CW_OUT; ++r) {
+        const int e = tid + r * CW_NT;
+        if (e < nout) atomicAdd(acc_out + poff + e, acc[r]);
+    }
+}
+
+__global__ void chain_wgrad_finish_kernel(const double* __restrict__ acc, float* __restrict__ dp, const int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dp[i] = (float)acc[i];
+}
+
+}  // namespace rnde

@@ -25,6 +25,7 @@
 // them in the same fixed order, so all CTAs take identical controller decisions.
 #pragma once
 #include "common.cuh"
+#include "chain.cuh"
 
 namespace rnde {
 
@@ -220,7 +221,8 @@ __global__ void __launch_bounds__(NT, 1) fwd_kernel(const KParams P) {
     const float* gb2 = gW2 + (size_t)D * (H + td);
 
     // ---- stage weights / biases / initial state into shared memory -------
-    if constexpr (WS) {
+    const bool chain = (G == 1) && P.n_layers > 0;
+    if constexpr (WS) if (!chain) {
         for (int e = tid; e < R * HP; e += NT) {
             const int k = e / HP, m = e - k * HP;
             sW1[e] = (k < Rloc && m < H) ? __ldg(gW1 + (size_t)(r0 + k) * H + m) : 0.f;
@@ -230,14 +232,21 @@ __global__ void __launch_bounds__(NT, 1) fwd_kernel(const KParams P) {
             sW2[e] = (m < Rloc) ? __ldg(gW2 + (size_t)D * k + r0 + m) : 0.f;
         }
     }
-    for (int m = tid; m < HP; m += NT) {
-        sW1t[m] = (td && m < H) ? __ldg(gW1 + (size_t)H * D + m) : 0.f;
-        sb1[m] = (m < H) ? __ldg(gb1 + m) : 0.f;
+    if (!chain) {
+        for (int m = tid; m < HP; m += NT) {
+            sW1t[m] = (td && m < H) ? __ldg(gW1 + (size_t)H * D + m) : 0.f;
+            sb1[m] = (m < H) ? __ldg(gb1 + m) : 0.f;
+        }
+        for (int m = tid; m < RP; m += NT) {
+            sW2t[m] = (td && m < Rloc) ? __ldg(gW2 + (size_t)D * H + r0 + m) : 0.f;
+            sb2[m] = (m < Rloc) ? __ldg(gb2 + r0 + m) : 0.f;
+        }
+    } else {
+        for (int e = tid; e < P.chain_np; e += NT) smem[P.oCW + e] = __ldg(P.p + e);
     }
-    for (int m = tid; m < RP; m += NT) {
-        sW2t[m] = (td && m < Rloc) ? __ldg(gW2 + (size_t)D * H + r0 + m) : 0.f;
-        sb2[m] = (m < Rloc) ? __ldg(gb2 + r0 + m) : 0.f;
-    }
+    ChainView cv;
+    cv.L = P.n_layers; cv.D = D; cv.NP = NP; cv.hrows = P.hrows; cv.w = P.lw; cv.a = P.la; cv.pre = P.pre_act;
+    cv.sW = smem + P.oCW; cv.sA = smem + P.oCA; cv.sB = smem + P.oCB;
     for (int e = tid; e < RP * NP; e += NT) {
         const int n = e / RP, m = e - n * RP;   // m fastest: coalesced read of column-major x
         sU[m * NP + n] = (m < Rloc && n < Nloc) ? __ldg(P.x + (size_t)D * (c0 + n) + r0 + m) : 0.f;
@@ -277,6 +286,9 @@ __global__ void __launch_bounds__(NT, 1) fwd_kernel(const KParams P) {
 
     // ---- one evaluation of the vector field: sOut = f(sIn, tstage) --------
     auto rhs = [&](const float* sIn, float* sOut, const float tstage, const int rec) {
+        if constexpr (G == 1 && WS) {
+            if (chain) { chain_rhs<NP, NT>(P, cv, sIn, sOut, rec, q); return; }
+        }
         // phase A: partial hidden pre-activations over this CTA's input rows
         const int ln = lane % LN, lm = lane / LN, n0 = ln * 4;
         for (int mt = warp; mt * TMW < H; mt += NW) {

@@ -98,6 +98,7 @@ static kern_t fwd_kernel_for(int variant, int D = 0, int H = 0) {
     switch (variant) {
         case RNDE_KERNEL_CTA: return fwd_kernel<1, 32, 4, true, NT_FWD>;
         case RNDE_KERNEL_STREAM: return fwd_kernel<1, 4, 1, false, NT_FWD>;
+        case RNDE_KERNEL_CHAIN: return fwd_kernel<1, 4, 1, true, NT_FWD>;
         case RNDE_KERNEL_CLUSTER: return fwd_kernel<8, 32, 4, true, NT_FWD>;
         case RNDE_KERNEL_CLUSTER4: return (H == 100 && D == 784) ? fwd4_kernel<100, 98> : fwd4_kernel<0, 0>;
         default: return nullptr;
@@ -107,6 +108,7 @@ static kern_t bwd_kernel_for(int variant, int D = 0, int H = 0) {
     switch (variant) {
         case RNDE_KERNEL_CTA: return bwd_kernel<1, 32, 4, true, NT_FWD>;
         case RNDE_KERNEL_STREAM: return bwd_kernel<1, 4, 1, false, NT_FWD>;
+        case RNDE_KERNEL_CHAIN: return bwd_kernel<1, 4, 1, true, NT_FWD>;
         case RNDE_KERNEL_CLUSTER: return bwd_kernel<8, 32, 4, true, NT_FWD>;
         case RNDE_KERNEL_CLUSTER4: return (H == 100 && D == 784) ? bwd4_kernel<100, 98> : bwd4_kernel<0, 0>;
         default: return nullptr;
@@ -116,6 +118,7 @@ static void variant_shape(int variant, int* G, int* NP, bool* WS) {
     switch (variant) {
         case RNDE_KERNEL_CTA: *G = 1; *NP = 32; *WS = true; break;
         case RNDE_KERNEL_STREAM: *G = 1; *NP = 4; *WS = false; break;
+        case RNDE_KERNEL_CHAIN: *G = 1; *NP = 4; *WS = true; break;
         case RNDE_KERNEL_CLUSTER4: *G = V2_G; *NP = V2_NP; *WS = true; break;
         default: *G = 8; *NP = 32; *WS = true; break;
     }
@@ -144,8 +147,26 @@ extern "C" int rnde_device_count(void) {
     return n;
 }
 
+// chain fields: widest activation (incl. the state) and tape rows per column (a_0 .. a_{L-2})
+static int chain_maxw(const rnde_config& c) {
+    int m = c.state_dim;
+    for (int l = 0; l < c.n_layers; ++l) m = std::max(m, (int)c.layer_width[l]);
+    return m;
+}
+static int chain_hrows(const rnde_config& c) {
+    int r = c.state_dim;
+    for (int l = 0; l + 1 < c.n_layers; ++l) r += c.layer_width[l];
+    return r;
+}
+
 extern "C" int64_t rnde_num_params(const rnde_config* c) {
     const int td = c->time_dep ? 1 : 0;
+    if (c->n_layers > 0) {
+        int64_t n = 0;
+        int K = c->state_dim;
+        for (int l = 0; l < c->n_layers; ++l) { n += (int64_t)c->layer_width[l] * K + c->layer_width[l]; K = c->layer_width[l]; }
+        return n;
+    }
     return (int64_t)c->hidden_dim * (c->state_dim + td) + c->hidden_dim + (int64_t)c->state_dim * (c->hidden_dim + td) + c->state_dim;
 }
 
@@ -171,6 +192,12 @@ static size_t smem_bytes_bwd(int variant, int D, int H, int R, int HS, int kbloc
     int G, NP; bool WS;
     variant_shape(variant, &G, &NP, &WS);
     return (size_t)make_bwd_layout(G, NP, WS, D, H, R, HS).total * sizeof(float);
+}
+
+// extra shared memory of a chain field: all parameters + two ping-pong activation tiles
+static size_t chain_smem_floats(const rnde_config& c, int NP) {
+    if (c.n_layers <= 0) return 0;
+    return (size_t)round_up((int)rnde_num_params(&c), 4) + 2 * (size_t)round_up(chain_maxw(c), 4) * NP;
 }
 
 static void free_all(rnde_handle* h) {
@@ -204,8 +231,9 @@ static int try_variant(rnde_handle* h, int variant, size_t smem_limit, std::stri
     if (G > 1 && (D < 64 || (G - 1) * R >= D)) { *why = "state too small for the cluster variant"; return 0; }
     const int nbl = (D + h->kblock - 1) / h->kblock;
     if (nbl > 64) { *why = "more than 64 canonical K-blocks"; return 0; }
-    const size_t sf = smem_bytes_fwd(variant, D, H, R, HS, h->kblock);
-    const size_t sb = c.need_backward ? smem_bytes_bwd(variant, D, H, R, HS, h->kblock) : 0;
+    if (c.n_layers > 0 && variant != RNDE_KERNEL_CHAIN && variant != RNDE_KERNEL_CTA) { *why = "chain fields run on the CHAIN / CTA variants"; return 0; }
+    const size_t sf = smem_bytes_fwd(variant, D, H, R, HS, h->kblock) + sizeof(float) * chain_smem_floats(c, NP);
+    const size_t sb = c.need_backward ? smem_bytes_bwd(variant, D, H, R, HS, h->kblock) + sizeof(float) * chain_smem_floats(c, NP) : 0;
     if (sf > smem_limit || sb > smem_limit) { *why = "shared memory: need " + std::to_string(std::max(sf, sb)) + " B"; return 0; }
     // all CTAs must be co-resident (persistent grid with a grid barrier)
     kern_t kf = fwd_kernel_for(variant, D, H);
@@ -249,7 +277,18 @@ extern "C" int rnde_create(const rnde_config* cfg, rnde_handle** out) {
     if (!cfg || !out) return RNDE_ERR_ARG;
     *out = nullptr;
     if (cfg->struct_bytes != (int32_t)sizeof(rnde_config)) return RNDE_ERR_ARG;
-    if (cfg->state_dim <= 0 || cfg->hidden_dim <= 0 || cfg->batch <= 0) return RNDE_ERR_ARG;
+    if (cfg->state_dim <= 0 || cfg->batch <= 0 || cfg->n_layers < 0 || cfg->n_layers > 8) return RNDE_ERR_ARG;
+    if (cfg->n_layers == 0 && cfg->hidden_dim <= 0) return RNDE_ERR_ARG;
+    if (cfg->n_layers > 0) {
+        if (cfg->time_dep || cfg->layer_width[cfg->n_layers - 1] != cfg->state_dim || cfg->pre_act < 0 || cfg->pre_act > 1) return RNDE_ERR_ARG;
+        int K = cfg->state_dim;
+        for (int l = 0; l < cfg->n_layers; ++l) {
+            const int M = cfg->layer_width[l];
+            if (M <= 0 || M > 1024 || cfg->layer_act[l] < 0 || cfg->layer_act[l] > 1) return RNDE_ERR_ARG;
+            if ((int64_t)M * (K + 1) > (int64_t)CW_OUT * CW_NT) return RNDE_ERR_UNSUPPORTED;      // chain_wgrad_kernel's per-thread outputs
+            K = M;
+        }
+    }
     if (cfg->act_hidden < 0 || cfg->act_hidden > 1 || cfg->act_out < 0 || cfg->act_out > 1) return RNDE_ERR_ARG;
     if (cfg->reg_kind < 0 || cfg->reg_kind > RNDE_REG_ERR_PLUS_STIFF || cfg->alg < 0 || cfg->alg > 1) return RNDE_ERR_ARG;
     if (!(cfg->t1 > cfg->t0) || !(cfg->abstol > 0.f) || !(cfg->reltol > 0.f)) return RNDE_ERR_ARG;
@@ -265,6 +304,7 @@ extern "C" int rnde_create(const rnde_config* cfg, rnde_handle** out) {
     else h->cfg.global_batch = (int64_t)h->cfg.batch * h->cfg.nranks;     // equal shards
     h->kblock = cfg->kblock > 0 ? std::min(cfg->kblock, cfg->state_dim) : rnde_default_kblock(cfg);
     h->np = rnde_num_params(cfg);
+    if (cfg->n_layers > 0) h->cfg.hidden_dim = chain_maxw(*cfg);      // sizes the shared scratch of the generic kernels
     cudaDeviceProp prop;
     if (cudaGetDevice(&h->device) != cudaSuccess || cudaGetDeviceProperties(&prop, h->device) != cudaSuccess) { delete h; return RNDE_ERR_CUDA; }
     h->num_sms = prop.multiProcessorCount;
@@ -277,7 +317,9 @@ extern "C" int rnde_create(const rnde_config* cfg, rnde_handle** out) {
         ok = try_variant(h, cfg->kernel_variant, smem_limit, &why);
         all = why;
     } else {
-        const int order[4] = {RNDE_KERNEL_CTA, RNDE_KERNEL_CLUSTER4, RNDE_KERNEL_CLUSTER, RNDE_KERNEL_STREAM};
+        // chain fields: 4-column tiles while they give every SM at most one CTA, else 32-column tiles
+        const bool chain4 = cfg->n_layers > 0 && (cfg->batch + 3) / 4 <= h->num_sms;
+        const int order[4] = {chain4 ? RNDE_KERNEL_CHAIN : RNDE_KERNEL_CTA, chain4 ? RNDE_KERNEL_CTA : RNDE_KERNEL_CLUSTER4, RNDE_KERNEL_CLUSTER, RNDE_KERNEL_STREAM};
         for (int i = 0; i < 4 && !ok; ++i) {
             ok = try_variant(h, order[i], smem_limit, &why);
             if (!ok) all += "[variant " + std::to_string(order[i]) + ": " + why + "] ";
@@ -308,9 +350,10 @@ extern "C" int rnde_create(const rnde_config* cfg, rnde_handle** out) {
         const size_t tile = (size_t)h->Q * h->NP;
         if (cudaMalloc(&h->tapeZ, sizeof(float) * nrec * tile * D) != cudaSuccess) return fail("cudaMalloc tapeZ (lower tape_capacity?)");
         if (cudaMalloc(&h->tapeK, sizeof(float) * nrec * tile * D) != cudaSuccess) return fail("cudaMalloc tapeK (lower tape_capacity?)");
-        if (cudaMalloc(&h->tapeH, sizeof(float) * nrec * tile * H) != cudaSuccess) return fail("cudaMalloc tapeH");
-        if (cudaMalloc(&h->tapeD1, sizeof(float) * nrec * tile * H) != cudaSuccess) return fail("cudaMalloc tapeD1");
-        h->wg_ws_floats = wgrad_workspace_floats(D, H);
+        const size_t hrows = c.n_layers > 0 ? (size_t)chain_hrows(c) : (size_t)H;
+        if (cudaMalloc(&h->tapeH, sizeof(float) * nrec * tile * hrows) != cudaSuccess) return fail("cudaMalloc tapeH");
+        if (cudaMalloc(&h->tapeD1, sizeof(float) * nrec * tile * hrows) != cudaSuccess) return fail("cudaMalloc tapeD1");
+        h->wg_ws_floats = std::max(wgrad_workspace_floats(D, H), (size_t)2 * h->np + 8);
         if (cudaMalloc(&h->wg_ws, sizeof(float) * h->wg_ws_floats) != cudaSuccess) return fail("cudaMalloc wgrad workspace");
         if (cudaMalloc(&h->scal, sizeof(float) * 2 * c.tape_capacity) != cudaSuccess) return fail("cudaMalloc scal");
     }
@@ -384,7 +427,18 @@ static void fill_params(const rnde_handle* h, KParams& P) {
     for (int i = 0; i < 8; ++i) P.peers[i] = h->peers[i];
     P.colsum = h->colsum; P.colsum_stride = h->colsum_stride; P.bar = h->bar; P.steps = h->steps; P.stats = h->stats;
     P.dbg = h->dbg;
+    P.n_layers = c.n_layers; P.pre_act = c.pre_act; P.hrows = c.n_layers > 0 ? chain_hrows(c) : 0; P.chain_np = c.n_layers > 0 ? (int)h->np : 0;
+    for (int l = 0; l < 8; ++l) { P.lw[l] = c.layer_width[l]; P.la[l] = c.layer_act[l]; }
     P.tapeZ = h->tapeZ; P.tapeK = h->tapeK; P.tapeH = h->tapeH; P.tapeD1 = h->tapeD1; P.scal = h->scal;
+}
+
+// shared-memory offsets of the chain region: right after the generic kernel's own layout
+static void set_chain_offsets(const rnde_handle* h, KParams& P, int base_floats) {
+    if (h->cfg.n_layers <= 0) return;
+    const int mw = round_up(chain_maxw(h->cfg), 4);
+    P.oCW = round_up(base_floats, 4);
+    P.oCA = P.oCW + round_up((int)h->np, 4);
+    P.oCB = P.oCA + mw * h->NP;
 }
 
 static int launch(rnde_handle* h, kern_t k, const KParams& P, size_t smem, cudaStream_t st) {
@@ -415,6 +469,10 @@ static int forward_impl(rnde_handle* h, const float* x_dev, const float* p_dev, 
     if (usave_dev) {
         if (h->n_saveat <= 0) return set_err(h, RNDE_ERR_STATE, "rnde_forward_saveat needs rnde_set_saveat first");
         P.saveat = h->saveat_dev; P.n_saveat = h->n_saveat; P.usave = usave_dev;
+    }
+    if (h->cfg.n_layers > 0) {
+        bool WS; int G, NP; variant_shape(h->variant, &G, &NP, &WS);
+        set_chain_offsets(h, P, make_layout(G, NP, WS, h->cfg.state_dim, h->cfg.hidden_dim, h->R, h->HS, h->kblock).total);
     }
     CUDA_TRY(h, cudaMemsetAsync(h->bar, 0, sizeof(unsigned) * 4, st));
     int rc = launch(h, fwd_kernel_for(h->variant, h->cfg.state_dim, h->cfg.hidden_dim), P, h->smem_fwd, st);
@@ -480,9 +538,26 @@ static int backward_impl(rnde_handle* h, const float* du_dev, const float* dusav
         if (h->n_saveat <= 0) return set_err(h, RNDE_ERR_STATE, "rnde_backward_saveat needs rnde_set_saveat first");
         P.saveat = h->saveat_dev; P.n_saveat = h->n_saveat; P.dusave = dusave_dev;
     }
+    if (h->cfg.n_layers > 0) {
+        bool WS; int G, NP; variant_shape(h->variant, &G, &NP, &WS);
+        set_chain_offsets(h, P, make_bwd_layout(G, NP, WS, h->cfg.state_dim, h->cfg.hidden_dim, h->R, h->HS).total);
+    }
     CUDA_TRY(h, cudaMemsetAsync(h->bar, 0, sizeof(unsigned) * 4, st));
     int rc = launch(h, bwd_kernel_for(h->variant, h->cfg.state_dim, h->cfg.hidden_dim), P, h->smem_bwd, st);
     if (rc != RNDE_OK) return rc;
+    if (h->cfg.n_layers > 0) {      // chain field: per-layer contractions over the tape, FP64 across stages
+        const int nrec_c = 1 + 6 * s.naccept;
+        double* acc = reinterpret_cast<double*>(h->wg_ws);
+        CUDA_TRY(h, cudaMemsetAsync(acc, 0, sizeof(double) * h->np, st));
+        int maxrows = 0, K = h->cfg.state_dim;
+        for (int l = 0; l < h->cfg.n_layers; ++l) { maxrows = std::max(maxrows, h->cfg.layer_width[l] + K + 1); K = h->cfg.layer_width[l]; }
+        const int splits = std::max(1, std::min(4 * h->num_sms / h->cfg.n_layers, (nrec_c * h->Q * h->NP + CW_COLS - 1) / CW_COLS));
+        chain_wgrad_kernel<<<dim3(splits, h->cfg.n_layers), CW_NT, sizeof(float) * maxrows * CW_LD, st>>>(P, h->NP, nrec_c, acc);
+        chain_wgrad_finish_kernel<<<((int)h->np + 255) / 256, 256, 0, st>>>(acc, dp_dev, (int)h->np);
+        CUDA_TRY(h, cudaGetLastError());
+        h->launches += 2;
+        return RNDE_OK;
+    }
     // parameter gradients: two batched contractions over (record, column) -- see wgrad_kernel.cuh
     const int nrec = 1 + 6 * s.naccept;
     // tensor-core (tcgen05 3xTF32) contraction for the 16-column tape layout; RNDE_WGRAD_FFMA=1 selects the FFMA kernel

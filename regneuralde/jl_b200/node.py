@@ -105,6 +105,34 @@ class TDChain:
         return torch.cat([l.destructure() for l in self.layers])
 
 
+class Chain:
+    """Flux.Chain of Dense layers, optionally led by the elementwise ``x -> tanh.(x)`` -- the Latent-ODE generator
+    dynamics (experiments/latent_ode.jl:109-121).  Used with ``time_dep=False``: the field is ``re(p)(u)``
+    (src/models/neural_ode.jl:57).  Up to 8 layers; the last one maps back to the state dimension."""
+
+    def __init__(self, *layers, pre_act=None):
+        layers = list(layers)
+        if layers and not isinstance(layers[0], Dense):        # Chain(x -> tanh.(x), Dense..., ) spelling of the reference
+            if layers[0] not in (torch.tanh, math.tanh, "tanh"):
+                raise ValueError("only an elementwise tanh may lead the chain")
+            pre_act = "tanh"
+            layers = layers[1:]
+        if not 1 <= len(layers) <= 8:
+            raise NotImplementedError("chain fields hold 1..8 Dense layers")
+        for a, b in zip(layers[:-1], layers[1:]):
+            if b.inp != a.out:
+                raise ValueError("Dense layer sizes do not chain")
+        if layers[-1].out != layers[0].inp:
+            raise ValueError("a vector field maps the state dimension onto itself")
+        self.layers = tuple(layers)
+        self.pre_act = L.ACT_TANH if pre_act in (torch.tanh, math.tanh, "tanh") else L.ACT_IDENTITY
+        self.D = layers[0].inp
+        self.H = max(l.out for l in layers)
+
+    def destructure(self) -> torch.Tensor:
+        return torch.cat([l.destructure() for l in self.layers])
+
+
 def MLPDynamics(inp: int, hidden: int, *, generator: Optional[torch.Generator] = None) -> TDChain:
     """experiments/mnist_node.jl:41-54: Dense(in+1, hidden, tanh), Dense(hidden+1, in, tanh)."""
     return TDChain(Dense(inp + 1, hidden, "tanh", generator=generator), Dense(hidden + 1, inp, "tanh", generator=generator))
@@ -243,8 +271,8 @@ class TrackedNeuralODE:
         # return_multiple = haskey(kwargs, :saveat)  (neural_ode.jl:11): fixes which functor the object dispatches to
         self.return_multiple = saveat is not None
         self.saveat = None if saveat is None else [float(v) for v in saveat]
-        if not time_dep:
-            raise NotImplementedError("the reference's fields on this path are all time dependent")
+        if isinstance(model, Chain) == bool(time_dep):
+            raise NotImplementedError("TDChain fields are time dependent (basic.jl:16-28), Chain fields are not (latent_ode.jl:109-121)")
         L.require_device()
         self.model = model
         self.device = torch.device(device)
@@ -271,8 +299,13 @@ class TrackedNeuralODE:
             cfg = L.Config()
             cfg.struct_bytes = C.sizeof(L.Config)
             cfg.state_dim, cfg.hidden_dim, cfg.batch = self.model.D, self.model.H, B
-            cfg.act_hidden, cfg.act_out = self.model.layers[0].act, self.model.layers[1].act
-            cfg.time_dep = 1
+            if isinstance(self.model, Chain):
+                cfg.n_layers, cfg.pre_act, cfg.time_dep = len(self.model.layers), self.model.pre_act, 0
+                for i, lay in enumerate(self.model.layers):
+                    cfg.layer_width[i], cfg.layer_act[i] = lay.out, lay.act
+            else:
+                cfg.act_hidden, cfg.act_out = self.model.layers[0].act, self.model.layers[1].act
+                cfg.time_dep = 1
             cfg.kblock = self.kblock
             cfg.alg = self.solver.alg
             cfg.reg_kind = reg_kind

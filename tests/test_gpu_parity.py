@@ -263,6 +263,78 @@ def test_saveat_multi_save_functors(oracle_built, name, D, H, B, act_out, auto, 
     assert torch.equal(res3, res.detach())
 
 
+LATENT_WIDTHS = (50, 20, 50, 20, 50, 20, 50, 20)       # gen_dynamics of experiments/latent_ode.jl:109-121
+
+CHAIN_CASES = [
+    # name, D, widths, acts, pre_act, B, auto, func, variant, n_saveat
+    ("latent ODE field B=512, 49 save times, unregularised", 20, LATENT_WIDTHS, (1,) * 8, 1, 512, False, None, 0, 49),
+    ("latent ODE field B=512, error_est", 20, LATENT_WIDTHS, (1,) * 8, 1, 512, False, "ERROR_ESTIMATE", 0, 49),
+    ("latent ODE field B=130 ragged, error_stiff_est", 20, LATENT_WIDTHS, (1,) * 8, 1, 130, True, "ERROR_PLUS_STIFFNESS", 0, 49),
+    ("3-layer chain, identity output, no pre-activation, 32-column tiles", 6, (9, 11, 6), (1, 1, 0), 0, 70, False, "ERROR_ESTIMATE", 1, 5),
+    ("1-layer chain, final state only", 4, (4,), (1,), 1, 9, True, "STIFFNESS_ESTIMATE", 0, 0),
+]
+
+
+@pytest.mark.parametrize("name,D,widths,acts,pre_act,B,auto,func,variant,nsave", CHAIN_CASES, ids=[c[0] for c in CHAIN_CASES])
+def test_chain_field_latent_ode(oracle_built, name, D, widths, acts, pre_act, B, auto, func, variant, nsave):
+    """TrackedNeuralODE(gen_dynamics, [0,1], false, REGULARIZE, solver, saveat = saveat, reltol = abstol = 1.4f-8)
+    (experiments/latent_ode.jl:137-147) called as in time_series.jl:51: forward bit-identical to the oracle
+    (steps, NFE, every saved state, saved regulariser values), gradient against the oracle adjoint."""
+    r = R()
+    rng = np.random.default_rng(1234)
+    p_np = orc.glorot_chain_params(rng, D, widths, bias_scale=0.05)
+    x_np = rng.standard_normal((D, B)).astype(np.float32)           # z0 = sample * exp(logvar/2) + mu
+    saveat = None
+    if nsave:
+        saveat = np.unique(np.concatenate([[0.0], np.sort(rng.random(nsave - 2)), [1.0]]).astype(np.float32))
+    regularize = func is not None
+    solver = r.AutoTsit5() if auto else r.Tsit5()
+    layers = []
+    K = D
+    for M, a in zip(widths, acts):
+        layers.append(r.Dense(K, M, "tanh" if a else None)); K = M
+    model = r.Chain(*(["tanh"] if pre_act else []), *layers)
+    kw = dict(saveat=saveat.tolist()) if saveat is not None else {}
+    node = r.TrackedNeuralODE(model, [0.0, 1.0], False, regularize, solver, reltol=1.4e-8, abstol=1.4e-8, kernel_variant=variant, **kw)
+    fobj = getattr(r, func) if func else None
+    reg_kind = fobj.kind if fobj else orc.REG_NONE
+    x = torch.from_numpy(x_np).cuda().requires_grad_(True)
+    p = torch.from_numpy(p_np).cuda().requires_grad_(True)
+    res, nfe, sv = node(x, p, func=fobj)
+    cfg = orc.OracleConfig(D=D, H=max(widths), B=B, alg=1 if auto else 0, reg_kind=reg_kind, kblock1=D, widths=widths, acts=acts,
+                           pre_act=pre_act, saveat=None if saveat is None else saveat.astype(np.float64))
+    o = orc.Oracle(cfg)
+    ref = o.forward(x_np, p_np)
+    assert (nfe, node.last_stats.naccept, node.last_stats.nreject) == (ref.nf, ref.naccept, ref.nreject)
+    if saveat is not None:
+        got = res.detach().permute(1, 0, 2).cpu().numpy()
+        assert got.shape == ref.usave.shape == (len(saveat), D, B)
+        assert np.array_equal(bits(got), bits(ref.usave)), "saved states not bit-identical"
+        w = rng.standard_normal(ref.usave.shape).astype(np.float32)
+        loss = (res * torch.from_numpy(np.ascontiguousarray(w.transpose(1, 0, 2))).cuda()).sum()
+        bw = dict(du=np.zeros((D, B), np.float32), dusave=w)
+    else:
+        assert np.array_equal(bits(res.detach().cpu().numpy()), bits(ref.u)), "final state not bit-identical"
+        w = rng.standard_normal((D, B)).astype(np.float32)
+        loss = (res * torch.from_numpy(w).cuda()).sum()
+        bw = dict(du=w, dusave=None)
+    ws = None
+    if regularize:
+        assert np.array_equal(bits(sv.saveval.detach().cpu().numpy()), bits(ref.saveval))
+        ws = rng.standard_normal(len(ref.saveval)).astype(np.float32)
+        loss = loss + (sv.saveval * torch.from_numpy(ws).cuda()).sum()
+    loss.backward()
+    torch.cuda.synchronize()
+    dp_hi, dx_hi, _, _ = o.backward(bw["du"], ws, hi=True, dusave=bw["dusave"])
+    dp_32, dx_32, _, _ = o.backward(bw["du"], ws, dusave=bw["dusave"])
+    rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()
+    e_p, e_x = rel(p.grad.cpu().numpy(), dp_hi), rel(x.grad.cpu().numpy(), dx_hi)
+    c_p, c_x = rel(dp_32, dp_hi), rel(dx_32, dx_hi)
+    assert e_p <= max(1e-4, 10 * c_p) and e_x <= max(1e-4, 10 * c_x), (e_p, c_p, e_x, c_x)
+    if not regularize:
+        assert e_p <= 1e-4 and e_x <= 1e-4, (e_p, e_x)
+
+
 def test_update_parameters_matches_flux_momentum():
     """Optimiser(InvDecay(1e-5), Momentum(0.1, 0.9)) on raw arrays, empty parameter vectors skipped (src/utils.jl:149-156)."""
     r = R()

@@ -117,3 +117,36 @@ def test_free_interpolant_endpoint_identities():
     b1 = to.interp_weights(1.0)
     assert np.allclose(b1[:6], to.A[7], atol=1e-14) and abs(b1[6]) < 1e-14
     assert all(v == 0.0 for v in to.interp_weights(0.0))
+
+
+@pytest.mark.parametrize("reg,alg", [(orc.REG_NONE, 0), (orc.REG_ERR_DT, 0), (orc.REG_ERR_PLUS_STIFF, 1)])
+def test_chain_field_matches_autograd_fp64(oracle_built, reg, alg):
+    """Chain fields (Latent-ODE generator dynamics, experiments/latent_ode.jl:109-121: tanh pre-activation, Dense
+    layers, no time input) with saveat: C oracle against torch autograd in FP64 -- steps, saved states, gradients."""
+    torch.set_default_dtype(torch.float64)
+    rng = np.random.default_rng(5)
+    D, B = 6, 4
+    widths, acts = (9, 6, 11, 6), (1, 1, 1, 0)
+    sa = np.array([0.0, 0.13, 0.5, 0.77, 1.0])
+    cfg = orc.OracleConfig(D=D, H=11, B=B, reg_kind=reg, alg=alg, saveat=sa, widths=widths, acts=acts, pre_act=1)
+    p = orc.glorot_chain_params(rng, D, widths, dtype=np.float64, bias_scale=0.1) * 1.5
+    assert p.size == cfg.n_params == sum(m * k + m for m, k in zip(widths, (D,) + widths[:-1]))
+    x = rng.random((D, B))
+    o = orc.Oracle(cfg, f64=True)
+    r = o.forward(x, p)
+    pt = torch.tensor(p, requires_grad=True); xt = torch.tensor(x, requires_grad=True)
+    tr = to.solve(xt, pt, D=D, H=11, reg_kind=reg, auto_tsit5=bool(alg), saveat=sa, chain=(widths, acts, 1))
+    assert (r.nf, r.naccept) == (tr.nf, tr.naccept)
+    us = torch.stack(tr.usave)
+    assert np.abs(r.usave - us.detach().numpy()).max() < 1e-12
+    w = rng.standard_normal(r.usave.shape)
+    loss = (us * torch.tensor(w)).sum()
+    ws = None
+    if reg != orc.REG_NONE:
+        ws = rng.standard_normal(len(r.saveval))
+        loss = loss + (torch.stack(tr.saveval) * torch.tensor(ws)).sum()
+    gp, gx = torch.autograd.grad(loss, [pt, xt])
+    dp, dx, _, _ = o.backward(np.zeros((D, B)), ws, dusave=w)
+    assert np.abs(dp - gp.numpy()).max() <= 1e-7 * np.abs(gp.numpy()).max()
+    assert np.abs(dx - gx.numpy()).max() <= 1e-7 * np.abs(gx.numpy()).max()
+    torch.set_default_dtype(torch.float32)
