@@ -163,6 +163,32 @@ int rnde_forward_saveat(rnde_handle* h, const float* x_dev, const float* p_dev, 
 int rnde_backward_saveat(rnde_handle* h, const float* du_dev, const float* dusave_dev, const float* dsaveval_dev, float* dp_dev,
                          float* dx_dev, void* stream);
 
+/* ---- Latent-ODE recognition RNN (BASELINE.json north_star (4)) ------------------------------
+ * (p::LatentGRU)(x)  experiments/latent_ode.jl:39-99: update / reset / new-state gate networks
+ * Chain(Dense(2L+2I+1, H, tanh), Dense(H, L | L | 2L, sigmoid | sigmoid | identity)), sequence consumed backwards
+ * in time, observation-mask gating of the state update.  One persistent kernel per direction, weights in shared
+ * memory.  x_dev: (2I+1) x T x B column-major (data; mask; delta-t row), p_dev: Flux.destructure order
+ * (update_gate, reset_gate, new_state; each W1,b1,W2,b2), out_dev: 2L x B = vcat(y_mean, y_std).
+ * rnde_gru_backward: dout_dev 2L x B -> dp_dev (overwritten).  x carries data, so no dx is produced. */
+typedef struct rnde_gru_config {
+    int32_t struct_bytes;
+    int32_t in_dim;        /* I (37 in latent_ode.jl:105; BASELINE.json says 41: a parameter) */
+    int32_t hidden_dim;    /* H (40) */
+    int32_t latent_dim;    /* L (50) */
+    int32_t batch;         /* B */
+    int32_t seq_len;       /* T (49 observation times) */
+    int32_t need_backward;
+    int32_t reserved;
+} rnde_gru_config;
+typedef struct rnde_gru rnde_gru;
+int64_t rnde_gru_num_params(const rnde_gru_config* cfg);
+int rnde_gru_create(const rnde_gru_config* cfg, rnde_gru** out);
+void rnde_gru_destroy(rnde_gru* g);
+const char* rnde_gru_last_error(const rnde_gru* g);
+int rnde_gru_forward(rnde_gru* g, const float* x_dev, const float* p_dev, float* out_dev, void* stream);
+int rnde_gru_backward(rnde_gru* g, const float* dout_dev, float* dp_dev, void* stream);
+int64_t rnde_gru_launch_count(const rnde_gru* g);
+
 /* Host-buffer variants (end-to-end path: copies inside the call). */
 int rnde_forward_host(rnde_handle* h, const float* x_host, const float* p_host, float* u_out_host, float* saveval_host,
                       rnde_stats* stats_host);

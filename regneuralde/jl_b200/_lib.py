@@ -38,6 +38,8 @@ EXPORTS = [
     "rnde_forward", "rnde_backward", "rnde_forward_host", "rnde_backward_host", "rnde_head_loss_grad", "rnde_get_steps",
     "rnde_opt_update", "rnde_test_tanh", "rnde_test_tanh_bits", "rnde_test_pow", "rnde_debug_timeline", "rnde_dist_export", "rnde_dist_import",
     "rnde_set_saveat", "rnde_forward_saveat", "rnde_backward_saveat",
+    "rnde_gru_num_params", "rnde_gru_create", "rnde_gru_destroy", "rnde_gru_last_error", "rnde_gru_forward", "rnde_gru_backward",
+    "rnde_gru_launch_count",
 ]
 
 
@@ -52,6 +54,13 @@ class Config(C.Structure):
         ("max_saveat", C.c_int32), ("n_layers", C.c_int32),
         ("global_batch", C.c_int64),
         ("pre_act", C.c_int32), ("layer_width", C.c_int32 * 8), ("layer_act", C.c_int32 * 8), ("reserved1", C.c_int32),
+    ]
+
+
+class GruConfig(C.Structure):
+    _fields_ = [
+        ("struct_bytes", C.c_int32), ("in_dim", C.c_int32), ("hidden_dim", C.c_int32), ("latent_dim", C.c_int32),
+        ("batch", C.c_int32), ("seq_len", C.c_int32), ("need_backward", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -136,6 +145,17 @@ def lib() -> C.CDLL:
     L.rnde_dist_export.argtypes = [vp, vp]
     L.rnde_dist_import.argtypes = [vp, vp, C.c_int32]
     L.rnde_set_saveat.argtypes = [vp, vp, C.c_int32]
+    L.rnde_gru_num_params.restype = C.c_int64
+    L.rnde_gru_num_params.argtypes = [C.POINTER(GruConfig)]
+    L.rnde_gru_create.argtypes = [C.POINTER(GruConfig), C.POINTER(vp)]
+    L.rnde_gru_destroy.argtypes = [vp]
+    L.rnde_gru_destroy.restype = None
+    L.rnde_gru_last_error.restype = C.c_char_p
+    L.rnde_gru_last_error.argtypes = [vp]
+    L.rnde_gru_forward.argtypes = [vp, vp, vp, vp, vp]
+    L.rnde_gru_backward.argtypes = [vp, vp, vp, vp]
+    L.rnde_gru_launch_count.restype = C.c_int64
+    L.rnde_gru_launch_count.argtypes = [vp]
     L.rnde_forward_saveat.argtypes = [vp, vp, vp, vp, vp, vp, C.POINTER(Stats), vp]
     L.rnde_backward_saveat.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     _lib = L

@@ -104,51 +104,55 @@ __device__ __forceinline__ const float* chain_vjp(const KParams& P, const ChainV
     return g;
 }
 
-// Parameter gradients of a chain field from the tape: for every layer dW_l = sum over (record, column) of
-// delta_l a_l^T and db_l = sum delta_l.  grid = (splits, L); a CTA walks a contiguous range of (record, tile) pairs,
-// stages 64 columns at a time and every thread owns up to CW_OUT (output, input) pairs; partial sums are FP32 over one
-// stage and FP64 across stages (the regulariser cotangents cancel between records: DESIGN.md section 5).
+// Parameter gradients of Dense layers from a tape: for every layer dW = sum over (record, column) of delta a^T and
+// db = sum delta.  Tapes are [record][tile][row][NP]; a layer is described by where its delta and its input rows live.
+// grid = (splits, layers, output chunks); a CTA walks a contiguous range of (record, tile) pairs, stages 64 columns at
+// a time and every thread owns up to CW_OUT (output, input) pairs of its chunk; partial sums are FP32 over one stage
+// and FP64 across stages (the regulariser cotangents cancel between records: DESIGN.md section 5).
 constexpr int CW_NT = 256, CW_COLS = 64, CW_LD = 68, CW_OUT = 6;   // CW_LD: padded row stride (conflict-free LDS.128)
-__global__ void __launch_bounds__(CW_NT) chain_wgrad_kernel(const KParams P, const int NPt, const int nrec, double* __restrict__ acc_out) {
+struct WgLayer {
+    const float* dptr; const float* aptr;     // delta tape, input-activation tape
+    int dstride, astride;                     // floats per (record, tile) block of each tape
+    int doff, aoff;                           // first row of this layer's delta / input inside a block
+    int M, K, poff;                           // out, in, offset of W in the parameter vector (bias follows W)
+};
+struct WgDesc { WgLayer l[8]; int nl; };
+
+__global__ void __launch_bounds__(CW_NT) dense_wgrad_kernel(const WgDesc desc, const int NPt, const long long ntile, double* __restrict__ acc_out) {
     extern __shared__ __align__(16) float csm[];
-    const int tid = threadIdx.x, l = blockIdx.y, L = P.n_layers, D = P.D;
-    int poff = 0, hoff = 0, K = D;
-    for (int j = 0; j < l; ++j) { poff += P.lw[j] * K + P.lw[j]; hoff += K; K = P.lw[j]; }
-    const int M = P.lw[l];
-    const bool last = (l == L - 1);
-    float* sDel = csm;                      // M x CW_COLS
-    float* sAct = csm + M * CW_LD;        // (K+1) x CW_COLS, last row = 1 (bias)
+    const int tid = threadIdx.x;
+    const WgLayer& Ld = desc.l[blockIdx.y];
+    const int M = Ld.M, K = Ld.K;
+    const int nout = M * (K + 1);
+    const int e0 = blockIdx.z * (CW_OUT * CW_NT);
+    if (e0 >= nout) return;
+    float* sDel = csm;                      // M x CW_LD
+    float* sAct = csm + M * CW_LD;          // (K+1) x CW_LD, last row = 1 (bias)
     const int tiles_per_stage = CW_COLS / NPt;
-    const long long ntile = (long long)nrec * P.Q;
     const long long nstage = (ntile + tiles_per_stage - 1) / tiles_per_stage;
     const long long s0 = nstage * blockIdx.x / gridDim.x, s1 = nstage * (blockIdx.x + 1) / gridDim.x;
-    const int nout = M * (K + 1);
     double acc[CW_OUT];
 #pragma unroll
     for (int r = 0; r < CW_OUT; ++r) acc[r] = 0.0;
-    const size_t hstride = (size_t)P.hrows * NPt, dstride = (size_t)D * NPt;
     for (long long s = s0; s < s1; ++s) {
         const long long t0 = s * tiles_per_stage;
         __syncthreads();
         for (int e = tid; e < M * CW_COLS; e += CW_NT) {
             const int tl = e / (M * NPt), rem = e - tl * (M * NPt), o = rem / NPt, n = rem - o * NPt;
             const long long tile = t0 + tl;
-            float v = 0.f;
-            if (tile < ntile) v = last ? __ldcg(P.tapeK + (size_t)tile * dstride + (size_t)o * NPt + n)
-                                       : __ldcg(P.tapeD1 + (size_t)tile * hstride + (size_t)(hoff + K + o) * NPt + n);
-            sDel[o * CW_LD + tl * NPt + n] = v;
+            sDel[o * CW_LD + tl * NPt + n] = (tile < ntile) ? __ldcg(Ld.dptr + (size_t)tile * Ld.dstride + (size_t)(Ld.doff + o) * NPt + n) : 0.f;
         }
         for (int e = tid; e < (K + 1) * CW_COLS; e += CW_NT) {
             const int tl = e / ((K + 1) * NPt), rem = e - tl * ((K + 1) * NPt), i = rem / NPt, n = rem - i * NPt;
             const long long tile = t0 + tl;
             float v = 0.f;
-            if (tile < ntile) v = (i == K) ? 1.f : __ldcg(P.tapeH + (size_t)tile * hstride + (size_t)(hoff + i) * NPt + n);
+            if (tile < ntile) v = (i == K) ? 1.f : __ldcg(Ld.aptr + (size_t)tile * Ld.astride + (size_t)(Ld.aoff + i) * NPt + n);
             sAct[i * CW_LD + tl * NPt + n] = v;
         }
         __syncthreads();
 #pragma unroll
         for (int r = 0; r < CW_OUT; ++r) {
-            const int e = tid + r * CW_NT;
+            const int e = e0 + tid + r * CW_NT;
             if (e < nout) {
                 const int i = e / M, o = e - i * M;       // Flux order: column-major out x in, bias after the weights
                 const float4* d4 = reinterpret_cast<const float4*>(sDel + o * CW_LD);
@@ -165,14 +169,40 @@ __global__ void __launch_bounds__(CW_NT) chain_wgrad_kernel(const KParams P, con
     }
 #pragma unroll
     for (int r = 0; r < CW_OUT; ++r) {
-        const int e = tid + r * CW_NT;
-        if (e < nout) atomicAdd(acc_out + poff + e, acc[r]);
+        const int e = e0 + tid + r * CW_NT;
+        if (e < nout) atomicAdd(acc_out + Ld.poff + e, acc[r]);
     }
 }
 
-__global__ void chain_wgrad_finish_kernel(const double* __restrict__ acc, float* __restrict__ dp, const int n) {
+__global__ void wgrad_finish_kernel(const double* __restrict__ acc, float* __restrict__ dp, const int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dp[i] = (float)acc[i];
+}
+
+// host helper: launch the contraction for all layers of `desc` and convert the FP64 sums to dp (overwritten)
+inline cudaError_t launch_dense_wgrad(const WgDesc& desc, int NPt, long long ntile, int np, int num_sms, double* acc, float* dp,
+                                      cudaStream_t st, int64_t* launches) {
+    cudaError_t e = cudaMemsetAsync(acc, 0, sizeof(double) * np, st);
+    if (e != cudaSuccess) return e;
+    int maxrows = 0, maxout = 0;
+    for (int l = 0; l < desc.nl; ++l) {
+        maxrows = maxrows > desc.l[l].M + desc.l[l].K + 1 ? maxrows : desc.l[l].M + desc.l[l].K + 1;
+        maxout = maxout > desc.l[l].M * (desc.l[l].K + 1) ? maxout : desc.l[l].M * (desc.l[l].K + 1);
+    }
+    const int chunks = (maxout + CW_OUT * CW_NT - 1) / (CW_OUT * CW_NT);
+    const long long nstage = (ntile * NPt + CW_COLS - 1) / CW_COLS;
+    long long splits = 4LL * num_sms / (desc.nl * chunks);
+    if (splits > nstage) splits = nstage;
+    if (splits < 1) splits = 1;
+    const size_t smem = sizeof(float) * (size_t)maxrows * CW_LD;
+    if (smem > 48 * 1024) {
+        e = cudaFuncSetAttribute(dense_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    dense_wgrad_kernel<<<dim3((unsigned)splits, desc.nl, chunks), CW_NT, smem, st>>>(desc, NPt, ntile, acc);
+    wgrad_finish_kernel<<<(np + 255) / 256, 256, 0, st>>>(acc, dp, np);
+    if (launches) *launches += 2;
+    return cudaGetLastError();
 }
 
 }  // namespace rnde

@@ -17,6 +17,7 @@
 #include "wgrad_kernel.cuh"
 #include "wgrad_tc_kernel.cuh"
 #include "head_kernel.cuh"
+#include "gru_kernel.cuh"
 
 using namespace rnde;
 
@@ -285,7 +286,6 @@ extern "C" int rnde_create(const rnde_config* cfg, rnde_handle** out) {
         for (int l = 0; l < cfg->n_layers; ++l) {
             const int M = cfg->layer_width[l];
             if (M <= 0 || M > 1024 || cfg->layer_act[l] < 0 || cfg->layer_act[l] > 1) return RNDE_ERR_ARG;
-            if ((int64_t)M * (K + 1) > (int64_t)CW_OUT * CW_NT) return RNDE_ERR_UNSUPPORTED;      // chain_wgrad_kernel's per-thread outputs
             K = M;
         }
     }
@@ -547,15 +547,20 @@ static int backward_impl(rnde_handle* h, const float* du_dev, const float* dusav
     if (rc != RNDE_OK) return rc;
     if (h->cfg.n_layers > 0) {      // chain field: per-layer contractions over the tape, FP64 across stages
         const int nrec_c = 1 + 6 * s.naccept;
-        double* acc = reinterpret_cast<double*>(h->wg_ws);
-        CUDA_TRY(h, cudaMemsetAsync(acc, 0, sizeof(double) * h->np, st));
-        int maxrows = 0, K = h->cfg.state_dim;
-        for (int l = 0; l < h->cfg.n_layers; ++l) { maxrows = std::max(maxrows, h->cfg.layer_width[l] + K + 1); K = h->cfg.layer_width[l]; }
-        const int splits = std::max(1, std::min(4 * h->num_sms / h->cfg.n_layers, (nrec_c * h->Q * h->NP + CW_COLS - 1) / CW_COLS));
-        chain_wgrad_kernel<<<dim3(splits, h->cfg.n_layers), CW_NT, sizeof(float) * maxrows * CW_LD, st>>>(P, h->NP, nrec_c, acc);
-        chain_wgrad_finish_kernel<<<((int)h->np + 255) / 256, 256, 0, st>>>(acc, dp_dev, (int)h->np);
-        CUDA_TRY(h, cudaGetLastError());
-        h->launches += 2;
+        WgDesc desc; memset(&desc, 0, sizeof(desc));
+        desc.nl = h->cfg.n_layers;
+        const int hrows = chain_hrows(h->cfg), Dd = h->cfg.state_dim;
+        int K = Dd, poff = 0, hoff = 0;
+        for (int l = 0; l < desc.nl; ++l) {
+            WgLayer& w = desc.l[l];
+            const bool last = (l == desc.nl - 1);
+            w.M = h->cfg.layer_width[l]; w.K = K; w.poff = poff;
+            w.aptr = h->tapeH; w.astride = hrows * h->NP; w.aoff = hoff;
+            w.dptr = last ? h->tapeK : h->tapeD1; w.dstride = (last ? Dd : hrows) * h->NP; w.doff = last ? 0 : hoff + K;
+            poff += w.M * K + w.M; hoff += K; K = w.M;
+        }
+        cudaError_t ce = launch_dense_wgrad(desc, h->NP, (long long)nrec_c * h->Q, (int)h->np, h->num_sms, reinterpret_cast<double*>(h->wg_ws), dp_dev, st, &h->launches);
+        if (ce != cudaSuccess) return set_err(h, RNDE_ERR_CUDA, std::string("chain wgrad launch: ") + cudaGetErrorString(ce));
         return RNDE_OK;
     }
     // parameter gradients: two batched contractions over (record, column) -- see wgrad_kernel.cuh
@@ -673,4 +678,109 @@ extern "C" int rnde_test_tanh_bits(uint32_t first_bits, int64_t n, float* y_dev,
 extern "C" int rnde_test_pow(const float* x_dev, float e, float* y_dev, float* l10_dev, int64_t n, void* stream) {
     canon_pow_test_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x_dev, e, y_dev, l10_dev, (long long)n);
     return cudaGetLastError() == cudaSuccess ? RNDE_OK : RNDE_ERR_CUDA;
+}
+
+
+// ---- Latent-ODE recognition RNN ------------------------------------------------------------------------
+struct rnde_gru {
+    rnde_gru_config cfg;
+    GruOffsets off;
+    int Q = 0, num_sms = 0;
+    size_t smem_fwd = 0, smem_bwd = 0;
+    float* tapeA = nullptr; float* tapeD = nullptr; double* acc = nullptr;
+    const float* last_p = nullptr;
+    bool have_tape = false;
+    int64_t launches = 0;
+    std::string err;
+};
+
+extern "C" int64_t rnde_gru_num_params(const rnde_gru_config* c) {
+    if (!c) return 0;
+    return gru_offsets(c->in_dim, c->hidden_dim, c->latent_dim).np;
+}
+extern "C" const char* rnde_gru_last_error(const rnde_gru* g) { return g ? g->err.c_str() : "null handle"; }
+extern "C" int64_t rnde_gru_launch_count(const rnde_gru* g) { return g ? g->launches : 0; }
+
+extern "C" void rnde_gru_destroy(rnde_gru* g) {
+    if (!g) return;
+    cudaFree(g->tapeA); cudaFree(g->tapeD); cudaFree(g->acc);
+    delete g;
+}
+
+extern "C" int rnde_gru_create(const rnde_gru_config* cfg, rnde_gru** out) {
+    if (!cfg || !out || cfg->struct_bytes != (int32_t)sizeof(rnde_gru_config)) return RNDE_ERR_ARG;
+    *out = nullptr;
+    if (cfg->in_dim <= 0 || cfg->hidden_dim <= 0 || cfg->latent_dim <= 0 || cfg->batch <= 0 || cfg->seq_len <= 0) return RNDE_ERR_ARG;
+    if (rnde_device_count() <= 0) return RNDE_ERR_CUDA;
+    rnde_gru* g = new rnde_gru();
+    g->cfg = *cfg;
+    const int I = cfg->in_dim, H = cfg->hidden_dim, L = cfg->latent_dim, C = 2 * L + 2 * I + 1;
+    g->off = gru_offsets(I, H, L);
+    g->Q = (cfg->batch + GRU_NP - 1) / GRU_NP;
+    int dev = 0; cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { delete g; return RNDE_ERR_CUDA; }
+    g->num_sms = prop.multiProcessorCount;
+    g->smem_fwd = sizeof(float) * ((size_t)round_up(g->off.np, 4) + (size_t)GRU_NP * (2 * C + 3 * H + 2 * L + 2 * L) + GRU_NP);
+    g->smem_bwd = sizeof(float) * ((size_t)round_up(g->off.np, 4) + (size_t)GRU_NP * (2 * L * 4 + 2 * L + 3 * H));
+    if (g->smem_fwd > prop.sharedMemPerBlockOptin || g->smem_bwd > prop.sharedMemPerBlockOptin) {
+        fprintf(stderr, "regnde: GRU weights (%d floats) do not fit shared memory\n", g->off.np);
+        delete g; return RNDE_ERR_UNSUPPORTED;
+    }
+    if (cudaFuncSetAttribute(gru_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_fwd) != cudaSuccess ||
+        cudaFuncSetAttribute(gru_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_bwd) != cudaSuccess) { cudaGetLastError(); delete g; return RNDE_ERR_CUDA; }
+    if (cfg->need_backward) {
+        const size_t blocks = (size_t)cfg->seq_len * g->Q * GRU_NP;
+        if (cudaMalloc(&g->tapeA, sizeof(float) * blocks * g->off.arows) != cudaSuccess ||
+            cudaMalloc(&g->tapeD, sizeof(float) * blocks * g->off.drows) != cudaSuccess ||
+            cudaMalloc(&g->acc, sizeof(double) * g->off.np) != cudaSuccess) { cudaGetLastError(); rnde_gru_destroy(g); return RNDE_ERR_CUDA; }
+    }
+    *out = g;
+    return RNDE_OK;
+}
+
+static void gru_fill(const rnde_gru* g, GruParams& P) {
+    memset(&P, 0, sizeof(P));
+    const rnde_gru_config& c = g->cfg;
+    P.I = c.in_dim; P.H = c.hidden_dim; P.L = c.latent_dim; P.X = 2 * c.in_dim + 1; P.C = 2 * c.latent_dim + P.X;
+    P.T = c.seq_len; P.B = c.batch; P.Q = g->Q;
+    P.tapeA = g->tapeA; P.tapeD = g->tapeD; P.arows = g->off.arows; P.drows = g->off.drows; P.need_tape = c.need_backward ? 1 : 0;
+}
+
+extern "C" int rnde_gru_forward(rnde_gru* g, const float* x_dev, const float* p_dev, float* out_dev, void* stream) {
+    if (!g || !x_dev || !p_dev || !out_dev) return RNDE_ERR_ARG;
+    GruParams P; gru_fill(g, P);
+    P.x = x_dev; P.p = p_dev; P.out = out_dev;
+    gru_fwd_kernel<<<g->Q, GRU_NT, g->smem_fwd, (cudaStream_t)stream>>>(P);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { g->err = std::string("gru_fwd_kernel: ") + cudaGetErrorString(e); return RNDE_ERR_CUDA; }
+    g->launches += 1; g->last_p = p_dev; g->have_tape = g->cfg.need_backward != 0;
+    return RNDE_OK;
+}
+
+extern "C" int rnde_gru_backward(rnde_gru* g, const float* dout_dev, float* dp_dev, void* stream) {
+    if (!g || !dout_dev || !dp_dev) return RNDE_ERR_ARG;
+    if (!g->have_tape) { g->err = "rnde_gru_backward needs a preceding rnde_gru_forward on a handle created with need_backward=1"; return RNDE_ERR_STATE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    GruParams P; gru_fill(g, P);
+    P.p = g->last_p; P.dout = dout_dev;
+    gru_bwd_kernel<<<g->Q, GRU_NT, g->smem_bwd, st>>>(P);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { g->err = std::string("gru_bwd_kernel: ") + cudaGetErrorString(e); return RNDE_ERR_CUDA; }
+    g->launches += 1;
+    const GruOffsets& O = g->off;
+    const int H = P.H, L = P.L, C = P.C;
+    WgDesc desc; memset(&desc, 0, sizeof(desc));
+    desc.nl = 6;
+    const int spec[6][5] = {   // delta row, input row, M, K, parameter offset
+        {O.d_hu, O.a_yc, H, C, O.Wu1}, {O.d_u, O.a_hu, L, H, O.Wu2}, {O.d_hr, O.a_yc, H, C, O.Wr1},
+        {O.d_r, O.a_hr, L, H, O.Wr2}, {O.d_hn, O.a_cc, H, C, O.Wn1}, {O.d_ns, O.a_hn, 2 * L, H, O.Wn2}};
+    for (int l = 0; l < 6; ++l) {
+        WgLayer& w = desc.l[l];
+        w.dptr = g->tapeD; w.dstride = O.drows * GRU_NP; w.doff = spec[l][0];
+        w.aptr = g->tapeA; w.astride = O.arows * GRU_NP; w.aoff = spec[l][1];
+        w.M = spec[l][2]; w.K = spec[l][3]; w.poff = spec[l][4];
+    }
+    e = launch_dense_wgrad(desc, GRU_NP, (long long)P.T * g->Q, O.np, g->num_sms, g->acc, dp_dev, st, &g->launches);
+    if (e != cudaSuccess) { g->err = std::string("gru wgrad: ") + cudaGetErrorString(e); return RNDE_ERR_CUDA; }
+    return RNDE_OK;
 }
