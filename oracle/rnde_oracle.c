@@ -173,8 +173,10 @@ static REAL rms_from_total(REAL tot, long long count) { return R_SQRT(tot / (REA
 static REAL act_apply(int act, REAL s) { return act == ACT_TANH ? R_TANH(s) : s; }
 
 /* z: D x B (col-major), out k: D x B, optional hout: H x B */
-/* chain field, one column: a_0 = pre(z); a_l = act_l(W_l a_{l-1} + b_l).  Canonical order: one fma chain over the
- * inputs in ascending order starting from 0, then + bias, then the activation.  acts (may be NULL) receives
+/* chain field, one column: a_0 = pre(z); a_l = act_l(W_l a_{l-1} + b_l).  Canonical order: the inputs are cut into 4
+ * contiguous quarters of ceil(K/4); each quarter is an fma chain in ascending order starting from 0 (an empty quarter
+ * is +0); the quarters are added as (q0 + q1) + (q2 + q3); then + bias, then the activation.  (The kernel gives the
+ * four quarters of an output to four adjacent lanes: csrc/chain.cuh quad_dense.)  acts (may be NULL) receives
  * a_0 .. a_{L-1} back to back (the last entry is the output). */
 static void chain_column(const orc_config* c, const REAL* p, const REAL* zj, REAL* out, REAL* acts) {
     REAL a[2][1024];
@@ -188,10 +190,17 @@ static void chain_column(const orc_config* c, const REAL* p, const REAL* zj, REA
     for (int l = 0; l < c->n_layers; ++l) {
         const int M = c->width[l];
         const REAL* b = W + (size_t)M * K;
+        const int kb = (K + 3) / 4;
         for (int o = 0; o < M; ++o) {
-            REAL acc = 0;
-            for (int i = 0; i < K; ++i) acc = R_FMA(W[(size_t)M * i + o], a[cur][i], acc);
-            a[cur ^ 1][o] = act_apply(c->act[l], acc + b[o]);
+            REAL qv[4];
+            for (int blk = 0; blk < 4; ++blk) {
+                const int i0 = blk * kb, i1 = i0 + kb < K ? i0 + kb : K;
+                REAL acc = 0;
+                for (int i = i0; i < i1; ++i) acc = R_FMA(W[(size_t)M * i + o], a[cur][i], acc);
+                qv[blk] = acc;
+            }
+            const REAL tot = (qv[0] + qv[1]) + (qv[2] + qv[3]);
+            a[cur ^ 1][o] = act_apply(c->act[l], tot + b[o]);
         }
         cur ^= 1;
         if (acts) { memcpy(acts + ao, a[cur], sizeof(REAL) * M); ao += M; }

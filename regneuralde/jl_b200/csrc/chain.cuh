@@ -20,6 +20,43 @@ struct ChainView {
     float* sA; float* sB;   // ping-pong activations, maxw x NP each
 };
 
+// Quad-parallel small dense product.  Work item = (block of the contraction index, output row, group of 4 columns);
+// the 4 items of a row sit in adjacent lanes, each runs one fma chain over its contiguous quarter of the contraction
+// index for 4 columns, and two xor-shuffles add the quarters as (q0 + q1) + (q2 + q3) -- the canonical order of
+// oracle chain_column.  Lane `blk` of the quad then finalises column 4*cg + blk through fin(row, column, value).
+//   TRANS = false: value[a][n] = sum_c W[M*c + a] * in[c][n]   (a < M rows, c < K)      forward layer
+//   TRANS = true : value[a][n] = sum_c W[M*a + c] * in[c][n]   (a < K rows, c < M)      W^T g in the VJP
+template <int NP, int NT, bool TRANS, class Fin>
+__device__ __forceinline__ void quad_dense(const float* __restrict__ W, const int M, const int K, const float* __restrict__ in, Fin fin) {
+    const int A = TRANS ? K : M, Cn = TRANS ? M : K;
+    const int kb = (Cn + 3) >> 2;
+    const int total = A * 4 * (NP / 4);
+    for (int base = 0; base < total; base += NT) {
+        const int item = base + (int)threadIdx.x;
+        const bool valid = item < total;
+        const int blk = item & 3, rest = item >> 2;
+        const int a = valid ? rest % A : 0, cg = valid ? rest / A : 0;
+        const int c0 = blk * kb, c1 = valid ? min(c0 + kb, Cn) : c0;
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+        const float* wp = TRANS ? W + M * a + c0 : W + M * c0 + a;
+        const int wstep = TRANS ? 1 : M;
+        const float* ip = in + c0 * NP + cg * 4;
+#pragma unroll 4
+        for (int c = c0; c < c1; ++c) {
+            const float w = *wp; wp += wstep;
+            const float4 x = *reinterpret_cast<const float4*>(ip); ip += NP;
+            acc0 = rn_fmaf(w, x.x, acc0); acc1 = rn_fmaf(w, x.y, acc1); acc2 = rn_fmaf(w, x.z, acc2); acc3 = rn_fmaf(w, x.w, acc3);
+        }
+        // (q0 + q1), (q2 + q3), then their sum: identical in all 4 lanes (IEEE addition commutes)
+        acc0 = acc0 + __shfl_xor_sync(0xffffffffu, acc0, 1); acc1 = acc1 + __shfl_xor_sync(0xffffffffu, acc1, 1);
+        acc2 = acc2 + __shfl_xor_sync(0xffffffffu, acc2, 1); acc3 = acc3 + __shfl_xor_sync(0xffffffffu, acc3, 1);
+        acc0 = acc0 + __shfl_xor_sync(0xffffffffu, acc0, 2); acc1 = acc1 + __shfl_xor_sync(0xffffffffu, acc1, 2);
+        acc2 = acc2 + __shfl_xor_sync(0xffffffffu, acc2, 2); acc3 = acc3 + __shfl_xor_sync(0xffffffffu, acc3, 2);
+        const float v = blk == 0 ? acc0 : (blk == 1 ? acc1 : (blk == 2 ? acc2 : acc3));
+        if (valid) fin(a, cg * 4 + blk, v);
+    }
+}
+
 // sOut = f(sIn).  rec >= 0: record z, a_0..a_{L-2} and k on the tape ([rec][tile][row][NP]).
 template <int NP, int NT>
 __device__ __forceinline__ void chain_rhs(const KParams& P, const ChainView& c, const float* sIn, float* sOut, const int rec, const int q) {
@@ -42,19 +79,14 @@ __device__ __forceinline__ void chain_rhs(const KParams& P, const ChainView& c, 
         const float* b = W + M * K;
         const bool last = (l == c.L - 1);
         float* dst = last ? sOut : nxt;
-        for (int e = tid; e < M * NP; e += NT) {
-            const int o = e / NP, n = e - o * NP;
-            float acc = 0.f;
-#pragma unroll 4
-            for (int i = 0; i < K; ++i) acc = rn_fmaf(W[M * i + o], cur[i * NP + n], acc);
-            float v = acc + b[o];
-            if (c.a[l] == RNDE_ACT_TANH) v = canon_tanhf(v);
-            dst[e] = v;
-            if (rec >= 0) {
-                if (last) P.tapeK[dbase + e] = v;
-                else P.tapeH[hbase + (size_t)hoff * NP + e] = v;
-            }
-        }
+        const int act = c.a[l];
+        float* tp = rec < 0 ? nullptr : (last ? P.tapeK + dbase : P.tapeH + hbase + (size_t)hoff * NP);
+        quad_dense<NP, NT, false>(W, M, K, cur, [&](const int o, const int n, const float s) {
+            float v = s + b[o];
+            if (act == RNDE_ACT_TANH) v = canon_tanhf(v);
+            dst[o * NP + n] = v;
+            if (tp) tp[o * NP + n] = v;
+        });
         __syncthreads();
         if (!last) { float* t = cur; cur = nxt; nxt = t; hoff += M; }
         W = b + M; K = M;
@@ -62,7 +94,7 @@ __device__ __forceinline__ void chain_rhs(const KParams& P, const ChainView& c, 
 }
 
 // VJP of record `rec`: on entry sKbar holds kbar (D x NP); delta_{L-1} replaces k on the tape, delta_l (l < L-1) goes
-// to tapeD1 at the row offset of a_{l+1}; the input cotangent ends up in c.sA (D x NP) -- the caller applies it.
+// to tapeD1 at the row offset of a_{l+1}; the input cotangent ends up in shared memory (D x NP), returned.
 template <int NP, int NT>
 __device__ __forceinline__ const float* chain_vjp(const KParams& P, const ChainView& c, float* sKbar, const int rec, const int q) {
     const int tid = threadIdx.x;
@@ -86,18 +118,15 @@ __device__ __forceinline__ const float* chain_vjp(const KParams& P, const ChainV
     __syncthreads();
     for (int l = c.L - 1; l >= 0; --l) {
         const int K = l ? c.w[l - 1] : D, M = c.w[l];
-        const float* W = c.sW + poff[l];
-        for (int e = tid; e < K * NP; e += NT) {
-            const int i = e / NP, n = e - i * NP;
-            float acc = 0.f;
-#pragma unroll 4
-            for (int o = 0; o < M; ++o) acc = rn_fmaf(W[M * i + o], g[o * NP + n], acc);
-            // derivative of the activation that produced this layer's input (layer l-1's, or the pre-activation)
-            const int actin = l ? c.a[l - 1] : c.pre;
-            if (actin == RNDE_ACT_TANH) { const float av = __ldcg(P.tapeH + hbase + (size_t)hoff[l] * NP + e); acc = acc * (1.f - av * av); }
-            gn[e] = acc;
-            if (l) P.tapeD1[hbase + (size_t)hoff[l] * NP + e] = acc;
-        }
+        // derivative of the activation that produced this layer's input (layer l-1's, or the pre-activation)
+        const int actin = l ? c.a[l - 1] : c.pre;
+        const float* ain = P.tapeH + hbase + (size_t)hoff[l] * NP;
+        float* dout = l ? P.tapeD1 + hbase + (size_t)hoff[l] * NP : nullptr;
+        quad_dense<NP, NT, true>(c.sW + poff[l], M, K, g, [&](const int i, const int n, float v) {
+            if (actin == RNDE_ACT_TANH) { const float av = __ldcg(ain + i * NP + n); v = v * (1.f - av * av); }
+            gn[i * NP + n] = v;
+            if (dout) dout[i * NP + n] = v;
+        });
         __syncthreads();
         float* t = g; g = gn; gn = t;
     }

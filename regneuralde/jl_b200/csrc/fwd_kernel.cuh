@@ -495,8 +495,15 @@ __global__ void __launch_bounds__(NT, 1) fwd_kernel(const KParams P) {
     const float beta1 = (float)(7.0 / 50.0), beta2 = (float)(2.0 / 25.0), qoldinit = (float)1e-4;
     const bool limited = P.need_tape || P.reg_kind != RNDE_REG_NONE;
 
+#ifdef RNDE_TIMELINE      // phase accumulators for tools/latent_timeline.py; compiled out of the product build
+    long long tl_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tl_t = clock64();
+#define TL(k) do { const long long _n = clock64(); tl_acc[k] += _n - tl_t; tl_t = _n; } while (0)
+#else
+#define TL(k) do { } while (0)
+#endif
     // ---- solve!: the hot loop ---------------------------------------------
     while (true) {
+        TL(7);
         if (tid == 0) {   // loopheader!
             Ctl& c = *ctl;
             if (!(c.t < P.t1)) c.done = 1;
@@ -528,6 +535,7 @@ __global__ void __launch_bounds__(NT, 1) fwd_kernel(const KParams P) {
         }
         __syncthreads();
         if (ctl->done) break;
+        TL(0);
         const float t = ctl->t, dt = ctl->dt;
         const int srec = P.need_tape ? 1 + 6 * ctl->naccept : -1;
         // (ctl is next written by thread 0 in loopfooter!, after the barriers inside grid_rms)
@@ -536,7 +544,9 @@ __global__ void __launch_bounds__(NT, 1) fwd_kernel(const KParams P) {
         for (int i = 2; i <= 7; ++i) {
             for (int e = tid; e < Rloc * NP; e += NT) sZ[e] = combo_val(i, dt, a2, e);
             __syncthreads();
+            TL(1);
             rhs(sZ, K(i), stage_time(t, dt, i), srec >= 0 ? srec + (i - 2) : -1);
+            TL(2);
         }
         // embedded error estimate (+ eigen_est for the composite algorithm)
         float EEst, eig = 1.f, en1 = 0.f, en2 = 0.f;
@@ -567,6 +577,7 @@ __global__ void __launch_bounds__(NT, 1) fwd_kernel(const KParams P) {
                 [&](int r, int n, float* o) { o[0] = atmp_val(r, n); }, o1, xseq_base);
             EEst = o1[0];
         }
+        TL(3);
         if (tid == 0) {   // loopfooter!
             Ctl& c = *ctl;
             c.nf += 6;
@@ -610,6 +621,7 @@ __global__ void __launch_bounds__(NT, 1) fwd_kernel(const KParams P) {
         __syncthreads();
         const int accepted = ctl->accept, finished = ctl->done;
         __syncthreads();   // everyone has read ctl before thread 0 starts the next loopheader!
+        TL(4);
         if (accepted && save_idx < P.n_saveat) {   // savevalues!: every pending saveat time <= t_new
             const float tnew = t + dt;
             while (save_idx < P.n_saveat) {
@@ -633,8 +645,12 @@ __global__ void __launch_bounds__(NT, 1) fwd_kernel(const KParams P) {
             float* tmp = sU; sU = sZ; sZ = tmp;
             flipK ^= 1;
         }
+        TL(5);
         if (finished) break;
     }
+#ifdef RNDE_TIMELINE
+    if (P.dbg && blockIdx.x == 0 && tid == 0) for (int k = 0; k < 8; ++k) P.dbg[k] = tl_acc[k];
+#endif
 
     // ---- write back ----------------------------------------------------------
     for (int e = tid; e < RP * NP; e += NT) {
