@@ -201,6 +201,17 @@ int rnde_backward_host(rnde_handle* h, const float* du_host, const float* dsavev
 int rnde_head_loss_grad(rnde_handle* h, const float* u_dev, const float* p3_dev, const float* y_onehot_dev, int32_t n_classes,
                         float loss_scale, float* loss_dev, float* logits_dev, float* du_dev, float* dp3_dev, void* stream);
 
+/* Statistics of the last rnde_forward on `h` (waits for that forward only, not for work queued behind it). */
+int rnde_last_stats(rnde_handle* h, rnde_stats* out);
+
+/* Regulariser term of the experiment's loss, lambda * agg(sv.saveval) (mnist_node.jl:69,80,98,146), and its
+ * cotangents for rnde_backward, computed on the device from the saved values of the last forward on `h` -- the
+ * number of saved values is read on the device, so the training step needs no host round trip between the forward
+ * solve and the backward sweep.  agg: 0 mean, 1 maximum, 2 sum.  dsaveval_dev (tape_capacity+1 floats) is
+ * overwritten with cot_scale * d(reg)/d(saveval[i]); reg_dev receives the value (1 float). */
+int rnde_reg_agg(rnde_handle* h, int32_t agg, float lam, float cot_scale, const float* saveval_dev, float* dsaveval_dev, float* reg_dev,
+                 void* stream);
+
 /* update_parameters!(ps, gs, opt) with opt = Optimiser(InvDecay(gamma), Momentum(eta, rho))
  * (src/utils.jl:149-156, experiments/mnist_node.jl:130), in place on raw arrays:
  *   delta = g * inv_decay_scale   [InvDecay: 1/(1 + gamma*n), n = 1-based update count]

@@ -21,6 +21,9 @@ from . import _lib as L
 from .node import (ERROR_ESTIMATE, Dense, SaveFunc, SavedValues, TrackedNeuralODE, _stream_ptr, colmajor, from_colmajor)
 
 
+_AGG = {"mean": 0, "maximum": 1, "sum": 2}
+
+
 class ClassifierNODE:
     """pre-net (reshape to 784 x B) -> NODE -> post-net Dense(784, 10), three flat parameter vectors."""
 
@@ -70,44 +73,36 @@ class ClassifierNODE:
         ws = self._workspace(B, dev, hd.cfg.tape_capacity)
         xbuf = colmajor(x.to(torch.float32))
         ybuf = colmajor(y_onehot.to(torch.float32))
-        st = L.Stats()
         stream = _stream_ptr()
-        hd.check(lib.rnde_forward(hd.h, xbuf.data_ptr(), self.p2.data_ptr(), ws["u"].data_ptr(), ws["sv"].data_ptr(), C.byref(st), stream),
+        # forward solve, head and regulariser aggregation are queued back to back without a host round trip; the one
+        # stream synchronisation of the step happens inside rnde_backward (it needs the accepted-step count)
+        hd.check(lib.rnde_forward(hd.h, xbuf.data_ptr(), self.p2.data_ptr(), ws["u"].data_ptr(), ws["sv"].data_ptr(), None, stream),
                  "rnde_forward")
-        node.last_stats = st
         hd.check(lib.rnde_head_loss_grad(hd.h, ws["u"].data_ptr(), self.p3.data_ptr(), ybuf.data_ptr(), Cn, float(ce_scale), ws["loss"].data_ptr(),
                                          ws["logits"].data_ptr(), ws["du"].data_ptr(), ws["g3"].data_ptr(), stream), "rnde_head_loss_grad")
-        n_saved = int(st.n_saved)
-        dsv = ws["dsv"]
-        reg = None
-        if n_saved > 0:
-            sv = ws["sv"][:n_saved]
-            if agg == "mean":           # mnist_node.jl:69,98
-                dsv.zero_(); dsv[:n_saved] = reg_scale * lam / n_saved
-                reg = lam * sv.mean()
-            elif agg == "maximum":      # mnist_node.jl:80
-                k = int(torch.argmax(sv))
-                dsv.zero_(); dsv[k] = reg_scale * lam
-                reg = lam * sv[k]
-            elif agg == "sum":          # test/test_node.jl:55
-                dsv.zero_(); dsv[:n_saved] = reg_scale * lam
-                reg = lam * sv.sum()
-            else:
-                raise ValueError(agg)
-        else:
-            dsv.zero_()
-        hd.check(lib.rnde_backward(hd.h, ws["du"].data_ptr(), dsv.data_ptr(), ws["g2"].data_ptr(), None, stream), "rnde_backward")
+        if agg not in _AGG:
+            raise ValueError(agg)
+        regularized = reg_kind != L.REG_NONE
+        if regularized:
+            hd.check(lib.rnde_reg_agg(hd.h, _AGG[agg], float(lam), float(reg_scale), ws["sv"].data_ptr(), ws["dsv"].data_ptr(),
+                                      ws["reg"].data_ptr(), stream), "rnde_reg_agg")
+        hd.check(lib.rnde_backward(hd.h, ws["du"].data_ptr(), ws["dsv"].data_ptr() if regularized else None, ws["g2"].data_ptr(), None, stream),
+                 "rnde_backward")
+        st = L.Stats()
+        hd.check(lib.rnde_last_stats(hd.h, C.byref(st)), "rnde_last_stats")
+        node.last_stats = st
         ce = ws["loss"][0]
+        reg = ws["reg"][0] if regularized else None
         loss = ce + reg if reg is not None else ce
         return {"loss": loss, "ce": ce, "reg": reg, "nfe": int(st.nf), "naccept": int(st.naccept), "nreject": int(st.nreject),
-                "g2": ws["g2"], "g3": ws["g3"], "logits": from_colmajor(ws["logits"], Cn, B), "n_saved": n_saved}
+                "g2": ws["g2"], "g3": ws["g3"], "logits": from_colmajor(ws["logits"], Cn, B), "n_saved": int(st.n_saved)}
 
     def _workspace(self, B, dev, cap):
         key = (B, str(dev))
         if getattr(self, "_ws_key", None) != key:
             D, Cn = self.node.model.D, self.n_classes
             f = lambda n: torch.empty(n, device=dev, dtype=torch.float32)
-            self._ws = {"u": f(D * B), "sv": torch.zeros(cap + 1, device=dev), "dsv": torch.zeros(cap + 1, device=dev), "loss": f(1),
+            self._ws = {"u": f(D * B), "sv": torch.zeros(cap + 1, device=dev), "dsv": torch.zeros(cap + 1, device=dev), "loss": f(1), "reg": f(1),
                         "logits": f(Cn * B), "du": f(D * B), "g3": f(Cn * D + Cn), "g2": f(self.p2.numel())}
             self._ws_key = key
         return self._ws

@@ -89,6 +89,44 @@ static int launch_head(int D, int B, int C, const float* u, const float* p3, con
     return (int)cudaGetLastError();
 }
 
+// lambda * agg(sv.saveval) and its cotangents, with the number of saved values read on the device (no host round trip
+// between the forward solve and the backward sweep).  agg: 0 mean (mnist_node.jl:69,98), 1 maximum (:80), 2 sum
+// (test/test_node.jl:55).  One block.
+__global__ void reg_agg_kernel(const DevStats* __restrict__ stats, const int agg, const float lam, const float cot_scale,
+                               const float* __restrict__ sv, float* __restrict__ dsv, const int cap, float* __restrict__ reg_out) {
+    __shared__ float sval[32];
+    __shared__ int sidx[32];
+    const int n = min(stats->n_saved, cap), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float acc = (agg == 1) ? -INFINITY : 0.f;
+    int best = 0;
+    for (int i = tid; i < n; i += blockDim.x) {
+        const float v = sv[i];
+        if (agg == 1) { if (v > acc) { acc = v; best = i; } }
+        else acc += v;
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const float o = __shfl_xor_sync(0xffffffffu, acc, off);
+        const int ob = __shfl_xor_sync(0xffffffffu, best, off);
+        if (agg == 1) { if (o > acc || (o == acc && ob < best)) { acc = o; best = ob; } }
+        else acc += o;
+    }
+    if (lane == 0) { sval[warp] = acc; sidx[warp] = best; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+            if (agg == 1) { if (sval[w] > acc || (sval[w] == acc && sidx[w] < best)) { acc = sval[w]; best = sidx[w]; } }
+            else acc += sval[w];
+        }
+        sval[0] = acc; sidx[0] = best;
+    }
+    __syncthreads();
+    acc = sval[0]; best = sidx[0];
+    const float cot = (agg == 0) ? (n > 0 ? cot_scale * lam / (float)n : 0.f) : cot_scale * lam;
+    for (int i = tid; i <= cap; i += blockDim.x) dsv[i] = (i < n && (agg != 1 || i == best)) ? cot : 0.f;
+    if (tid == 0) reg_out[0] = (n == 0) ? 0.f : (agg == 0 ? lam * (acc / (float)n) : lam * acc);
+}
+
 __global__ void opt_update_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ v, long long n, float scale,
                                   float eta, float rho) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

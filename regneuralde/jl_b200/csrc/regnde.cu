@@ -47,6 +47,7 @@ struct rnde_handle {
     // host-path staging
     float *hx = nullptr, *hp = nullptr, *hu = nullptr, *hsv = nullptr, *hdu = nullptr, *hdsv = nullptr, *hdp = nullptr, *hdx = nullptr;
     DevStats* stats_pinned = nullptr;
+    cudaEvent_t ev_stats = nullptr;      // recorded after the forward's stats copy: the backward waits on it, not on the stream
     const float* last_p = nullptr;
     rnde_stats last_stats{};
     bool have_tape = false;
@@ -206,6 +207,7 @@ static void free_all(rnde_handle* h) {
     cudaFree(h->colsum); cudaFree(h->bar); cudaFree(h->steps); cudaFree(h->stats);
     cudaFree(h->tapeZ); cudaFree(h->tapeK); cudaFree(h->tapeH); cudaFree(h->tapeD1); cudaFree(h->wg_ws); cudaFree(h->scal); cudaFree(h->saveval_int);
     cudaFree(h->dtile); cudaFree(h->head_ws); cudaFree(h->dbg); cudaFree(h->saveat_dev);
+    if (h->ev_stats) cudaEventDestroy(h->ev_stats);
     cudaFree(h->hx); cudaFree(h->hp); cudaFree(h->hu); cudaFree(h->hsv); cudaFree(h->hdu); cudaFree(h->hdsv); cudaFree(h->hdp); cudaFree(h->hdx);
     if (h->stats_pinned) cudaFreeHost(h->stats_pinned);
 }
@@ -345,6 +347,7 @@ extern "C" int rnde_create(const rnde_config* cfg, rnde_handle** out) {
     if (cudaMalloc(&h->stats, sizeof(DevStats)) != cudaSuccess) return fail("cudaMalloc stats");
     if (cudaMalloc(&h->saveval_int, sizeof(float) * (c.tape_capacity + 1)) != cudaSuccess) return fail("cudaMalloc saveval");
     if (cudaMallocHost(&h->stats_pinned, sizeof(DevStats)) != cudaSuccess) return fail("cudaMallocHost stats");
+    if (cudaEventCreateWithFlags(&h->ev_stats, cudaEventDisableTiming) != cudaSuccess) return fail("cudaEventCreate");
     if (c.need_backward) {
         const size_t nrec = 1 + (size_t)6 * c.tape_capacity;
         const size_t tile = (size_t)h->Q * h->NP;
@@ -480,6 +483,7 @@ static int forward_impl(rnde_handle* h, const float* x_dev, const float* p_dev, 
     h->last_p = p_dev;
     h->have_tape = h->cfg.need_backward != 0;
     CUDA_TRY(h, cudaMemcpyAsync(h->stats_pinned, h->stats, sizeof(DevStats), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaEventRecord(h->ev_stats, st));
     if (stats_host) {
         CUDA_TRY(h, cudaStreamSynchronize(st));
         const DevStats& s = *h->stats_pinned;
@@ -526,9 +530,12 @@ static int backward_impl(rnde_handle* h, const float* du_dev, const float* dusav
     if (!h || (!du_dev && !dusave_dev) || !dp_dev) return RNDE_ERR_ARG;
     if (!h->have_tape || !h->cfg.need_backward) return set_err(h, RNDE_ERR_STATE, "rnde_backward needs a preceding rnde_forward on a handle created with need_backward=1");
     cudaStream_t st = (cudaStream_t)stream;
-    // number of accepted steps of the forward on this handle (already copied to pinned memory)
-    CUDA_TRY(h, cudaStreamSynchronize(st));
+    // number of accepted steps of the forward on this handle: wait for its stats copy only, so that work queued
+    // behind the forward (classifier head, regulariser aggregation) keeps the GPU busy while the host gets here
+    CUDA_TRY(h, cudaEventSynchronize(h->ev_stats));
     const DevStats s = *h->stats_pinned;
+    h->last_stats.nf = s.nf; h->last_stats.naccept = s.naccept; h->last_stats.nreject = s.nreject; h->last_stats.n_saved = s.n_saved;
+    h->last_stats.retcode = s.retcode; h->last_stats.t_final = s.t_final; h->last_stats.dt_last = s.dt_last; h->last_stats.dt_init = s.dt_init;
     if (s.retcode != RNDE_OK) return set_err(h, RNDE_ERR_STATE, "forward solve failed; nothing to differentiate");
     KParams P;
     fill_params(h, P);
@@ -629,6 +636,25 @@ extern "C" int rnde_backward_host(rnde_handle* h, const float* du_host, const fl
     if (rc != RNDE_OK) return rc;
     CUDA_TRY(h, cudaMemcpy(dp_host, h->hdp, sizeof(float) * h->np, cudaMemcpyDeviceToHost));
     if (dx_host) CUDA_TRY(h, cudaMemcpy(dx_host, h->hdx, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    return RNDE_OK;
+}
+
+extern "C" int rnde_last_stats(rnde_handle* h, rnde_stats* out) {
+    if (!h || !out) return RNDE_ERR_ARG;
+    if (h->ev_stats) CUDA_TRY(h, cudaEventSynchronize(h->ev_stats));
+    const DevStats& s = *h->stats_pinned;
+    out->nf = s.nf; out->naccept = s.naccept; out->nreject = s.nreject; out->n_saved = s.n_saved;
+    out->retcode = s.retcode; out->t_final = s.t_final; out->dt_last = s.dt_last; out->dt_init = s.dt_init;
+    h->last_stats = *out;
+    return RNDE_OK;
+}
+
+extern "C" int rnde_reg_agg(rnde_handle* h, int32_t agg, float lam, float cot_scale, const float* saveval_dev, float* dsaveval_dev, float* reg_dev,
+                            void* stream) {
+    if (!h || agg < 0 || agg > 2 || !saveval_dev || !dsaveval_dev || !reg_dev) return RNDE_ERR_ARG;
+    reg_agg_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(h->stats, agg, lam, cot_scale, saveval_dev, dsaveval_dev, h->cfg.tape_capacity, reg_dev);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 1;
     return RNDE_OK;
 }
 
