@@ -385,6 +385,7 @@ __global__ void __launch_bounds__(V2_NT, 1) fwd4_kernel(const KParams P) {
             }
         }
         __syncthreads();
+        mark(11);
         const unsigned slot = norm_seq & 1u;
         float* gcol = P.colsum + (size_t)slot * 3 * P.colsum_stride;
         if (tid < NP * NV) {
@@ -400,6 +401,7 @@ __global__ void __launch_bounds__(V2_NT, 1) fwd4_kernel(const KParams P) {
             st_cluster_f32(mapa_u32(smem_u32(sCP + (v * G + rank) * NP + n), 0), bs[0] + bs[1]);
         }
         cluster_sync_all();
+        mark(12);
         if (rank == 0 && tid < NP * NV) {
             const int n = tid % NP, v = tid / NP;
             float tot = sCP[(v * G) * NP + n];
@@ -408,7 +410,9 @@ __global__ void __launch_bounds__(V2_NT, 1) fwd4_kernel(const KParams P) {
             if (n < Nloc) publish_colsum(P, (size_t)slot * 3 * P.colsum_stride + (size_t)v * P.colsum_stride + P.col_offset + q * NP + n, tot);
             if (P.nranks > 1) __threadfence_system();
         }
+        mark(13);
         grid_barrier(P.bar, gridDim.x, bar_gen);
+        mark(14);
         xrank_barrier(P, xseq_base + norm_seq + 1u);
         const int warp = tid >> 5, lane = tid & 31;
         if (warp < NV) {
@@ -424,6 +428,7 @@ __global__ void __launch_bounds__(V2_NT, 1) fwd4_kernel(const KParams P) {
         for (int v = 0; v < NV; ++v) result[v] = sTot[v];
         norm_seq += 1;
         __syncthreads();
+        mark(15);
     };
 
     const float dtmax = P.t1 - P.t0;
@@ -629,6 +634,7 @@ __global__ void __launch_bounds__(V2_NT, 1) fwd4_kernel(const KParams P) {
             }
         }
         __syncthreads();
+        mark(16);
         const int accepted = ctl->accept, finished = ctl->done;
         __syncthreads();
         if (accepted) {   // apply_step!: u <- u_new, fsalfirst <- fsallast

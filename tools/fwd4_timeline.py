@@ -1,0 +1,41 @@
+"""Developer diagnostic: clock64 phase timeline of fwd4_kernel<100,98> (MNIST shape, batch 512), CTA 0.
+Builds a -DRNDE_TIMELINE copy of the library into /tmp; the product build has the markers compiled out."""
+import ctypes as C, os, subprocess, sys
+import numpy as np, torch
+sys.path.insert(0, ".")
+os.environ["RNDE_DEBUG_TIMELINE"] = "1"
+from regneuralde.jl_b200 import _lib as L
+tl = "/tmp/libregnde_tl.so"
+subprocess.run(["nvcc", *L.NVCC_FLAGS, "-DRNDE_TIMELINE", f"-I{L._INCLUDE}", "-o", tl, str(L.sources()[0])], check=True, capture_output=True)
+L.LIB_PATH = type(L.LIB_PATH)(tl)
+import regneuralde.jl_b200 as r
+from oracle import orc
+rng = np.random.default_rng(1999)
+D, H, B = 784, 100, 512
+p = torch.from_numpy(orc.glorot_params(rng, D, H)).cuda()
+x = torch.from_numpy(rng.random((D, B), dtype=np.float32)).cuda()
+node = r.TrackedNeuralODE(r.MLPDynamics(D, H), [0.0, 1.0], True, True, r.Tsit5(), tape_capacity=128)
+need = len(sys.argv) > 1 and sys.argv[1] == "tape"
+x.requires_grad_(need)
+for _ in range(2):
+    res, nfe, sv = node(x, p, func=r.ERROR_ESTIMATE)
+torch.cuda.synchronize()
+hd = next(iter(node._handles.values()))
+buf = (C.c_longlong * 8000)()
+hd.lib.rnde_debug_timeline(hd.h, buf, 8000)
+a = np.array(list(buf)).reshape(-1, 2)
+a = a[: np.nonzero(a[:, 1])[0].max() + 1]
+ids, ts = a[:, 0], a[:, 1]
+names = {1: "stageZ+sync", 2: "layer-1 partial", 3: "sync", 4: "pair+scatter", 5: "sync", 6: "wait partials", 7: "reduce+tanh+gather", 8: "sync",
+         9: "wait hidden", 10: "layer-2+tanh", 0: "between evals / combos", 11: "norm: col sumsq + sync", 12: "norm: cluster reduce + sync",
+         13: "norm: publish", 14: "norm: grid barrier", 15: "norm: total", 16: "controller"}
+dur = {}
+for i in range(40, len(ids) - 1):
+    dur.setdefault(int(ids[i + 1]), []).append(ts[i + 1] - ts[i])        # time spent reaching marker ids[i+1]
+print(f"nfe {nfe} naccept {node.last_stats.naccept} tape={need}")
+tot = 0
+for k in [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 0, 11, 12, 13, 14, 15, 16]:
+    if k in dur:
+        v = np.array(dur[k]); print(f"  -> {names[k]:28s} n={len(v):4d} mean {v.mean():8.0f} median {np.median(v):8.0f}")
+steps = np.nonzero(ids == 16)[0]
+print("cycles per step (controller to controller):", np.diff(ts[steps]).mean())
