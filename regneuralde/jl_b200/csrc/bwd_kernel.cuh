@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(NT, 1) bwd_kernel(const KParams P) {
     const bool chain = (G == 1) && P.n_layers > 0;
     ChainView cv;
     cv.L = P.n_layers; cv.D = D; cv.NP = NP; cv.hrows = P.hrows; cv.w = P.lw; cv.a = P.la; cv.pre = P.pre_act;
-    cv.sW = smem + P.oCW; cv.sA = smem + P.oCA; cv.sB = smem + P.oCB;
+    cv.sW = smem + P.oCW; cv.sA = smem + P.oCA; cv.sB = smem + P.oCB; cv.sH = smem + P.oCH;
     if (chain) for (int e = tid; e < P.chain_np; e += NT) smem[P.oCW + e] = __ldg(P.p + e);
     if constexpr (WS) if (!chain) {
         for (int e = tid; e < R * HP; e += NT) {       // W2T[k][m] = W2[r0+k, m]

@@ -18,6 +18,7 @@ struct ChainView {
     int pre;
     const float* sW;   // all parameters, Flux.destructure order
     float* sA; float* sB;   // ping-pong activations, maxw x NP each
+    float* sH;              // backward only: this record's activations a_0..a_{L-2} (hrows x NP), staged once per VJP
 };
 
 // Quad-parallel small dense product.  Work item = (block of the contraction index, output row, group of 4 columns);
@@ -35,7 +36,9 @@ __device__ __forceinline__ void quad_dense(const float* __restrict__ W, const in
         const int item = base + (int)threadIdx.x;
         const bool valid = item < total;
         const int blk = item & 3, rest = item >> 2;
-        const int a = valid ? rest % A : 0, cg = valid ? rest / A : 0;
+        int a, cg;
+        if constexpr (NP == 4) { a = valid ? rest : 0; cg = 0; }        // one column group: no index division
+        else { a = valid ? rest % A : 0; cg = valid ? rest / A : 0; }
         const int c0 = blk * kb, c1 = valid ? min(c0 + kb, Cn) : c0;
         float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
         const float* wp = TRANS ? W + M * a + c0 : W + M * c0 + a;
@@ -109,6 +112,8 @@ __device__ __forceinline__ const float* chain_vjp(const KParams& P, const ChainV
         for (int l = 0; l < c.L; ++l) { poff[l + 1] = poff[l] + c.w[l] * K + c.w[l]; hoff[l + 1] = hoff[l] + K; K = c.w[l]; }
     }
     float* g = c.sB; float* gn = c.sA;
+    // one batch of tape loads per VJP (a single L2/HBM latency) instead of one dependent load per layer
+    for (int e = tid; e < c.hrows * NP; e += NT) c.sH[e] = __ldcg(P.tapeH + hbase + e);
     for (int e = tid; e < D * NP; e += NT) {
         float d = sKbar[e];
         if (c.a[c.L - 1] == RNDE_ACT_TANH) { const float kv = __ldcg(P.tapeK + dbase + e); d = d * (1.f - kv * kv); }
@@ -120,10 +125,10 @@ __device__ __forceinline__ const float* chain_vjp(const KParams& P, const ChainV
         const int K = l ? c.w[l - 1] : D, M = c.w[l];
         // derivative of the activation that produced this layer's input (layer l-1's, or the pre-activation)
         const int actin = l ? c.a[l - 1] : c.pre;
-        const float* ain = P.tapeH + hbase + (size_t)hoff[l] * NP;
+        const float* ain = c.sH + hoff[l] * NP;
         float* dout = l ? P.tapeD1 + hbase + (size_t)hoff[l] * NP : nullptr;
         quad_dense<NP, NT, true>(c.sW + poff[l], M, K, g, [&](const int i, const int n, float v) {
-            if (actin == RNDE_ACT_TANH) { const float av = __ldcg(ain + i * NP + n); v = v * (1.f - av * av); }
+            if (actin == RNDE_ACT_TANH) { const float av = ain[i * NP + n]; v = v * (1.f - av * av); }
             gn[i * NP + n] = v;
             if (dout) dout[i * NP + n] = v;
         });

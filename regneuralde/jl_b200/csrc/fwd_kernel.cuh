@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(NT, 1) fwd_kernel(const KParams P) {
     }
     ChainView cv;
     cv.L = P.n_layers; cv.D = D; cv.NP = NP; cv.hrows = P.hrows; cv.w = P.lw; cv.a = P.la; cv.pre = P.pre_act;
-    cv.sW = smem + P.oCW; cv.sA = smem + P.oCA; cv.sB = smem + P.oCB;
+    cv.sW = smem + P.oCW; cv.sA = smem + P.oCA; cv.sB = smem + P.oCB; cv.sH = nullptr;
     for (int e = tid; e < RP * NP; e += NT) {
         const int n = e / RP, m = e - n * RP;   // m fastest: coalesced read of column-major x
         sU[m * NP + n] = (m < Rloc && n < Nloc) ? __ldg(P.x + (size_t)D * (c0 + n) + r0 + m) : 0.f;

@@ -59,16 +59,40 @@ constexpr int GRU_NT = 256, GRU_NP = 4;
 
 __device__ __forceinline__ float gru_sigmoid(const float v) { return rn_fmaf(0.5f, canon_tanhf(0.5f * v), 0.5f); }
 
-// out[o][n] = act(sum_i W[o,i] in[i][n] + b[o]) for o < M; W column-major M x K in shared memory
-template <class Act>
-__device__ __forceinline__ void gru_dense(const float* W, const float* b, const float* in, int K, int M, float* out, int e_first, int e_count, Act act) {
-    for (int ee = (int)threadIdx.x - e_first; ee < M * GRU_NP; ee += e_count) {
-        if (ee < 0) continue;
-        const int o = ee / GRU_NP, n = ee - o * GRU_NP;
-        float acc = 0.f;
-#pragma unroll 5
-        for (int i = 0; i < K; ++i) acc = fmaf(W[M * i + o], in[i * GRU_NP + n], acc);
-        out[ee] = act(acc + b[o]);
+// Up to two small dense products side by side (e.g. the hidden layers of the update and reset gates), each split
+// over lane quads like chain.cuh quad_dense: item = (quarter of the contraction index, row), the four quarters of a row
+// sit in adjacent lanes and are added by two xor-shuffles; lane q of the quad finalises column q (GRU_NP == 4).
+//   TRANS = false: value[a][n] = sum_c W[M*c + a] * in[c][n]  (a < M, c < K);   TRANS = true: sum_c W[M*a + c] * in[c][n]  (a < K, c < M)
+struct GruJob { const float* W; const float* in; int M, K; };
+template <bool TRANS, class Fin>
+__device__ __forceinline__ void gru_quad(const GruJob j0, const GruJob j1, const int njobs, Fin fin) {
+    const int A0 = TRANS ? j0.K : j0.M, A1 = njobs > 1 ? (TRANS ? j1.K : j1.M) : 0;
+    const int total = 4 * (A0 + A1);
+    for (int base = 0; base < total; base += GRU_NT) {
+        const int item = base + (int)threadIdx.x;
+        const bool valid = item < total;
+        const int blk = item & 3, rest = item >> 2;
+        const int job = (valid && rest >= A0) ? 1 : 0;
+        const GruJob& J = job ? j1 : j0;
+        const int a = valid ? rest - (job ? A0 : 0) : 0;
+        const int Cn = TRANS ? J.M : J.K, kb = (Cn + 3) >> 2;
+        const int c0 = blk * kb, c1 = valid ? min(c0 + kb, Cn) : c0;
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+        const float* wp = TRANS ? J.W + J.M * a + c0 : J.W + J.M * c0 + a;
+        const int wstep = TRANS ? 1 : J.M;
+        const float* ip = J.in + c0 * GRU_NP;
+#pragma unroll 4
+        for (int c = c0; c < c1; ++c) {
+            const float w = *wp; wp += wstep;
+            const float4 x = *reinterpret_cast<const float4*>(ip); ip += GRU_NP;
+            acc0 = fmaf(w, x.x, acc0); acc1 = fmaf(w, x.y, acc1); acc2 = fmaf(w, x.z, acc2); acc3 = fmaf(w, x.w, acc3);
+        }
+        acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1); acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1);
+        acc2 += __shfl_xor_sync(0xffffffffu, acc2, 1); acc3 += __shfl_xor_sync(0xffffffffu, acc3, 1);
+        acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2); acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
+        acc2 += __shfl_xor_sync(0xffffffffu, acc2, 2); acc3 += __shfl_xor_sync(0xffffffffu, acc3, 2);
+        const float v = blk == 0 ? acc0 : (blk == 1 ? acc1 : (blk == 2 ? acc2 : acc3));
+        if (valid) fin(job, a, blk, v);
     }
 }
 
@@ -91,9 +115,6 @@ __global__ void __launch_bounds__(GRU_NT, 1) gru_fwd_kernel(const GruParams P) {
     for (int e = tid; e < O.np; e += GRU_NT) sW[e] = __ldg(P.p + e);
     for (int e = tid; e < 2 * L * GRU_NP; e += GRU_NT) sYc[e] = 0.f;
     __syncthreads();
-    auto tanh_act = [](float v) { return canon_tanhf(v); };
-    auto sig_act = [](float v) { return gru_sigmoid(v); };
-    auto id_act = [](float v) { return v; };
     for (int step = 0; step < P.T; ++step) {
         const int t = P.T - 1 - step;            // for t = size(x, 2):-1:1
         for (int e = tid; e < X * GRU_NP; e += GRU_NT) {
@@ -108,21 +129,27 @@ __global__ void __launch_bounds__(GRU_NT, 1) gru_fwd_kernel(const GruParams P) {
             for (int f = X / 2; f < X; ++f) s += sYc[(2 * L + f) * GRU_NP + tid];
             sMask[tid] = s > 0.f ? 1.f : 0.f;
         }
-        // hidden layers of the two gates (thread ranges side by side)
-        gru_dense(sW + O.Wu1, sW + O.bu1, sYc, C, H, sHu, 0, GRU_NT, tanh_act);
-        gru_dense(sW + O.Wr1, sW + O.br1, sYc, C, H, sHr, (H * GRU_NP) % GRU_NT, GRU_NT, tanh_act);
+        // hidden layers of the two gates side by side, then their sigmoid outputs
+        gru_quad<false>(GruJob{sW + O.Wu1, sYc, H, C}, GruJob{sW + O.Wr1, sYc, H, C}, 2, [&](int job, int o, int n, float v) {
+            (job ? sHr : sHu)[o * GRU_NP + n] = canon_tanhf(v + sW[(job ? O.br1 : O.bu1) + o]);
+        });
         __syncthreads();
-        gru_dense(sW + O.Wu2, sW + O.bu2, sHu, H, L, sU, 0, GRU_NT, sig_act);
-        gru_dense(sW + O.Wr2, sW + O.br2, sHr, H, L, sR, (L * GRU_NP) % GRU_NT, GRU_NT, sig_act);
+        gru_quad<false>(GruJob{sW + O.Wu2, sHu, L, H}, GruJob{sW + O.Wr2, sHr, L, H}, 2, [&](int job, int o, int n, float v) {
+            (job ? sR : sU)[o * GRU_NP + n] = gru_sigmoid(v + sW[(job ? O.br2 : O.bu2) + o]);
+        });
         __syncthreads();
         for (int e = tid; e < 2 * L * GRU_NP; e += GRU_NT) {
             const int j = e / GRU_NP, n = e - j * GRU_NP;
             sCc[e] = sYc[e] * sR[(j % L) * GRU_NP + n];
         }
         __syncthreads();
-        gru_dense(sW + O.Wn1, sW + O.bn1, sCc, C, H, sHn, 0, GRU_NT, tanh_act);
+        gru_quad<false>(GruJob{sW + O.Wn1, sCc, H, C}, GruJob{nullptr, nullptr, 0, 0}, 1, [&](int, int o, int n, float v) {
+            sHn[o * GRU_NP + n] = canon_tanhf(v + sW[O.bn1 + o]);
+        });
         __syncthreads();
-        gru_dense(sW + O.Wn2, sW + O.bn2, sHn, H, 2 * L, sNs, 0, GRU_NT, id_act);
+        gru_quad<false>(GruJob{sW + O.Wn2, sHn, 2 * L, H}, GruJob{nullptr, nullptr, 0, 0}, 1, [&](int, int o, int n, float v) {
+            sNs[o * GRU_NP + n] = v + sW[O.bn2 + o];
+        });
         __syncthreads();
         if (P.need_tape) {
             float* A = P.tapeA + ((size_t)step * P.Q + q) * P.arows * GRU_NP;
@@ -144,17 +171,6 @@ __global__ void __launch_bounds__(GRU_NT, 1) gru_fwd_kernel(const GruParams P) {
     for (int e = tid; e < 2 * L * GRU_NP; e += GRU_NT) {
         const int n = e / (2 * L), j = e - n * (2 * L);
         if (c0 + n < P.B) P.out[(size_t)2 * L * (c0 + n) + j] = sYc[j * GRU_NP + n];
-    }
-}
-
-// in-place accumulate: dst[i][n] += sum_o W[o,i] g[o][n] for i < Kuse (W column-major M x K)
-__device__ __forceinline__ void gru_dense_T(const float* W, const float* g, int M, int Kuse, float* dst, bool accumulate) {
-    for (int e = threadIdx.x; e < Kuse * GRU_NP; e += GRU_NT) {
-        const int i = e / GRU_NP, n = e - i * GRU_NP;
-        float acc = 0.f;
-#pragma unroll 5
-        for (int o = 0; o < M; ++o) acc = fmaf(W[M * i + o], g[o * GRU_NP + n], acc);
-        dst[e] = accumulate ? dst[e] + acc : acc;
     }
 }
 
@@ -202,11 +218,14 @@ __global__ void __launch_bounds__(GRU_NT, 1) gru_bwd_kernel(const GruParams P) {
         for (int e = tid; e < 2 * L * GRU_NP; e += GRU_NT) Dl[O.d_ns * GRU_NP + e] = sDns[e];
         for (int e = tid; e < L * GRU_NP; e += GRU_NT) Dl[O.d_u * GRU_NP + e] = sDu[e];
         // new_state network
-        gru_dense_T(sW + O.Wn2, sDns, 2 * L, H, sDhn, false);
+        gru_quad<true>(GruJob{sW + O.Wn2, sDns, 2 * L, H}, GruJob{nullptr, nullptr, 0, 0}, 1, [&](int, int i, int n, float v) {
+            const float hv = A[(O.a_hn + i) * GRU_NP + n];
+            const float d = v * (1.f - hv * hv);
+            sDhn[i * GRU_NP + n] = d; Dl[(O.d_hn + i) * GRU_NP + n] = d;
+        });
         __syncthreads();
-        for (int e = tid; e < H * GRU_NP; e += GRU_NT) { const float hv = A[O.a_hn * GRU_NP + e]; const float d = sDhn[e] * (1.f - hv * hv); sDhn[e] = d; Dl[O.d_hn * GRU_NP + e] = d; }
-        __syncthreads();
-        gru_dense_T(sW + O.Wn1, sDhn, H, 2 * L, sCb, false);
+        // only the first 2L inputs of the new-state network carry a cotangent (the rest is data): K is cut to 2L rows
+        gru_quad<true>(GruJob{sW + O.Wn1, sDhn, H, 2 * L}, GruJob{nullptr, nullptr, 0, 0}, 1, [&](int, int j, int n, float v) { sCb[j * GRU_NP + n] = v; });
         __syncthreads();
         for (int e = tid; e < L * GRU_NP; e += GRU_NT) {
             const float r = A[O.a_r * GRU_NP + e];
@@ -219,19 +238,16 @@ __global__ void __launch_bounds__(GRU_NT, 1) gru_bwd_kernel(const GruParams P) {
         }
         __syncthreads();
         // gate networks
-        gru_dense_T(sW + O.Wr2, sDr, L, H, sDhr, false);
-        gru_dense_T(sW + O.Wu2, sDu, L, H, sDhu, false);
+        gru_quad<true>(GruJob{sW + O.Wu2, sDu, L, H}, GruJob{sW + O.Wr2, sDr, L, H}, 2, [&](int job, int i, int n, float v) {
+            const float hv = A[((job ? O.a_hr : O.a_hu) + i) * GRU_NP + n];
+            const float d = v * (1.f - hv * hv);
+            (job ? sDhr : sDhu)[i * GRU_NP + n] = d;
+            Dl[((job ? O.d_hr : O.d_hu) + i) * GRU_NP + n] = d;
+        });
         __syncthreads();
-        for (int e = tid; e < H * GRU_NP; e += GRU_NT) {
-            const float hr = A[O.a_hr * GRU_NP + e], hu = A[O.a_hu * GRU_NP + e];
-            const float dr = sDhr[e] * (1.f - hr * hr), du = sDhu[e] * (1.f - hu * hu);
-            sDhr[e] = dr; sDhu[e] = du;
-            Dl[O.d_hr * GRU_NP + e] = dr; Dl[O.d_hu * GRU_NP + e] = du;
-        }
+        gru_quad<true>(GruJob{sW + O.Wr1, sDhr, H, 2 * L}, GruJob{nullptr, nullptr, 0, 0}, 1, [&](int, int j, int n, float v) { sYp[j * GRU_NP + n] += v; });
         __syncthreads();
-        gru_dense_T(sW + O.Wr1, sDhr, H, 2 * L, sYp, true);
-        __syncthreads();
-        gru_dense_T(sW + O.Wu1, sDhu, H, 2 * L, sYp, true);
+        gru_quad<true>(GruJob{sW + O.Wu1, sDhu, H, 2 * L}, GruJob{nullptr, nullptr, 0, 0}, 1, [&](int, int j, int n, float v) { sYp[j * GRU_NP + n] += v; });
         __syncthreads();
         { float* tmp = sYb; sYb = sYp; sYp = tmp; }
     }

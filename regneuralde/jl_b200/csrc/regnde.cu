@@ -197,9 +197,9 @@ static size_t smem_bytes_bwd(int variant, int D, int H, int R, int HS, int kbloc
 }
 
 // extra shared memory of a chain field: all parameters + two ping-pong activation tiles
-static size_t chain_smem_floats(const rnde_config& c, int NP) {
+static size_t chain_smem_floats(const rnde_config& c, int NP, bool backward) {
     if (c.n_layers <= 0) return 0;
-    return (size_t)round_up((int)rnde_num_params(&c), 4) + 2 * (size_t)round_up(chain_maxw(c), 4) * NP;
+    return (size_t)round_up((int)rnde_num_params(&c), 4) + 2 * (size_t)round_up(chain_maxw(c), 4) * NP + (backward ? (size_t)chain_hrows(c) * NP : 0);
 }
 
 static void free_all(rnde_handle* h) {
@@ -235,8 +235,8 @@ static int try_variant(rnde_handle* h, int variant, size_t smem_limit, std::stri
     const int nbl = (D + h->kblock - 1) / h->kblock;
     if (nbl > 64) { *why = "more than 64 canonical K-blocks"; return 0; }
     if (c.n_layers > 0 && variant != RNDE_KERNEL_CHAIN && variant != RNDE_KERNEL_CTA) { *why = "chain fields run on the CHAIN / CTA variants"; return 0; }
-    const size_t sf = smem_bytes_fwd(variant, D, H, R, HS, h->kblock) + sizeof(float) * chain_smem_floats(c, NP);
-    const size_t sb = c.need_backward ? smem_bytes_bwd(variant, D, H, R, HS, h->kblock) + sizeof(float) * chain_smem_floats(c, NP) : 0;
+    const size_t sf = smem_bytes_fwd(variant, D, H, R, HS, h->kblock) + sizeof(float) * chain_smem_floats(c, NP, false);
+    const size_t sb = c.need_backward ? smem_bytes_bwd(variant, D, H, R, HS, h->kblock) + sizeof(float) * chain_smem_floats(c, NP, true) : 0;
     if (sf > smem_limit || sb > smem_limit) { *why = "shared memory: need " + std::to_string(std::max(sf, sb)) + " B"; return 0; }
     // all CTAs must be co-resident (persistent grid with a grid barrier)
     kern_t kf = fwd_kernel_for(variant, D, H);
@@ -442,6 +442,7 @@ static void set_chain_offsets(const rnde_handle* h, KParams& P, int base_floats)
     P.oCW = round_up(base_floats, 4);
     P.oCA = P.oCW + round_up((int)h->np, 4);
     P.oCB = P.oCA + mw * h->NP;
+    P.oCH = P.oCB + mw * h->NP;
 }
 
 static int launch(rnde_handle* h, kern_t k, const KParams& P, size_t smem, cudaStream_t st) {
