@@ -314,9 +314,9 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4_kernel(const KParams P) {
                         const float g6v[4] = {g64.x, g64.y, g64.z, g64.w};
 #pragma unroll
                         for (int jj = 0; jj < 4; ++jj) {
-                            if (cn0 + jj >= Nloc) continue;
                             const int e = ii * 4 + jj;
                             const float up = upv[jj], un = unv[jj];
+                            const float live = (cn0 + jj < Nloc) ? 1.f : 0.f;      // columns past the batch contribute nothing
                             if (use_eest) {
                                 float ssum = c_BT[1] * kv[0][jj];
 #pragma unroll
@@ -324,23 +324,24 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4_kernel(const KParams P) {
                                 const float ut = dt * ssum;
                                 const float a0 = fabsf(up), a1 = fabsf(un);
                                 const float mx = a0 > a1 ? a0 : a1;
-                                const float den = rn_fmaf(mx, rtol, atol);
-                                const float at = ut / den;
-                                const float ab = gE * at;
-                                const float utb = ab / den;
-                                const float mb = (-ab * at / den) * rtol;
-                                if (a0 > a1) upb[e] += mb * (up >= 0.f ? 1.f : -1.f);
-                                else if (a1 > a0) ubar[e] += mb * (un >= 0.f ? 1.f : -1.f);
-                                else {
-                                    upb[e] += 0.5f * mb * (up > 0.f ? 1.f : (up < 0.f ? -1.f : 0.f));
-                                    ubar[e] += 0.5f * mb * (un > 0.f ? 1.f : (un < 0.f ? -1.f : 0.f));
-                                }
+                                const float rden = __frcp_rn(rn_fmaf(mx, rtol, atol));     // one reciprocal instead of three IEEE divisions
+                                const float at = ut * rden;
+                                const float ab = live * gE * at;
+                                const float utb = ab * rden;
+                                const float mb = (-ab * at * rden) * rtol;
+                                // max(|up|, |un|): the larger branch gets the cotangent, a tie splits it (branch-free selects;
+                                // the strictly larger magnitude is non-zero, so the three-way sign equals the two-way one there)
+                                const float wu = a0 > a1 ? 1.f : (a1 > a0 ? 0.f : 0.5f);
+                                const float su = up > 0.f ? 1.f : (up < 0.f ? -1.f : 0.f), sn = un > 0.f ? 1.f : (un < 0.f ? -1.f : 0.f);
+                                upb[e] += wu * mb * su;
+                                ubar[e] += (1.f - wu) * mb * sn;
+                                const float dtu = dt * utb;
 #pragma unroll
-                                for (int j = 1; j <= 7; ++j) kb[j - 1][e] += dt * c_BT[j] * utb;
+                                for (int j = 1; j <= 7; ++j) kb[j - 1][e] += c_BT[j] * dtu;
                             }
                             if (use_eig) {
-                                const float ga = gA * (kv[6][jj] - kv[5][jj]);
-                                const float gb = gB * (un - g6v[jj]);
+                                const float ga = live * gA * (kv[6][jj] - kv[5][jj]);
+                                const float gb = live * gB * (un - g6v[jj]);
                                 kb[6][e] += ga; kb[5][e] -= ga;
                                 ubar[e] += gb;       // the matching -gb on g6 is applied after stage 6's VJP
                             }

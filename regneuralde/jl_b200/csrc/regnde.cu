@@ -14,6 +14,7 @@
 #include "fwd4_kernel.cuh"
 #include "bwd_kernel.cuh"
 #include "bwd4_kernel.cuh"
+#include "bwd4tc_kernel.cuh"
 #include "wgrad_kernel.cuh"
 #include "wgrad_tc_kernel.cuh"
 #include "head_kernel.cuh"
@@ -106,13 +107,21 @@ static kern_t fwd_kernel_for(int variant, int D = 0, int H = 0) {
         default: return nullptr;
     }
 }
+// the reverse sweep of the cluster-4 decomposition runs its products on the tensor cores (bwd4tc_kernel.cuh) whenever the
+// shape fits; RNDE_BWD_FFMA=1 selects the FFMA sweep (bwd4_kernel.cuh)
+static bool bwd4_use_tc(int D, int H) {
+    static const bool force_ffma = getenv("RNDE_BWD_FFMA") != nullptr;
+    return !force_ffma && D > 0 && H > 0 && b4t_shape_ok(D, H);
+}
 static kern_t bwd_kernel_for(int variant, int D = 0, int H = 0) {
     switch (variant) {
         case RNDE_KERNEL_CTA: return bwd_kernel<1, 32, 4, true, NT_FWD>;
         case RNDE_KERNEL_STREAM: return bwd_kernel<1, 4, 1, false, NT_FWD>;
         case RNDE_KERNEL_CHAIN: return bwd_kernel<1, 4, 1, true, NT_FWD>;
         case RNDE_KERNEL_CLUSTER: return bwd_kernel<8, 32, 4, true, NT_FWD>;
-        case RNDE_KERNEL_CLUSTER4: return (H == 100 && D == 784) ? bwd4_kernel<100, 98> : bwd4_kernel<0, 0>;
+        case RNDE_KERNEL_CLUSTER4:
+            if (bwd4_use_tc(D, H)) return bwd4tc_kernel;
+            return (H == 100 && D == 784) ? bwd4_kernel<100, 98> : bwd4_kernel<0, 0>;
         default: return nullptr;
     }
 }
@@ -190,7 +199,7 @@ static size_t smem_bytes_fwd(int variant, int D, int H, int R, int HS, int kbloc
     return (size_t)make_layout(G, NP, WS, D, H, R, HS, kblock).total * sizeof(float);
 }
 static size_t smem_bytes_bwd(int variant, int D, int H, int R, int HS, int kblock) {
-    if (variant == RNDE_KERNEL_CLUSTER4) return (size_t)make_b4_layout(D, H).total * sizeof(float);
+    if (variant == RNDE_KERNEL_CLUSTER4) return bwd4_use_tc(D, H) ? (size_t)make_b4t_layout(D, H).total : (size_t)make_b4_layout(D, H).total * sizeof(float);
     int G, NP; bool WS;
     variant_shape(variant, &G, &NP, &WS);
     return (size_t)make_bwd_layout(G, NP, WS, D, H, R, HS).total * sizeof(float);
