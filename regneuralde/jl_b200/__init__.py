@@ -8,13 +8,14 @@ the host-side mirror of the reference's Julia surface for that path.  No CPU fal
 from . import _lib
 from ._lib import RndeError, build, lib
 from .node import (AutoTsit5, Dense, ERROR_ESTIMATE, ERROR_PLUS_STIFFNESS, MLPDynamics, STIFFNESS_ESTIMATE, STIFFNESS_SCALED,
-                   SavedValues, SaveFunc, TDChain, Chain, TrackedNeuralODE, Tsit5, colmajor, from_colmajor, track, untrack)
+                   SavedValues, SaveFunc, TDChain, Chain, TrackedNeuralODE, Tsit5, colmajor, from_colmajor, track, untrack,
+                   solution, ODESolution, DEStats)
 from .classifier import ClassifierNODE, Optimiser, update_parameters_
 from .latent import LatentGRU, LatentTimeSeriesModel, kl_divergence, latent_ode_model, log_likelihood, loss_function
 
 __all__ = [
     "RndeError", "build", "lib", "AutoTsit5", "Tsit5", "Dense", "TDChain", "Chain", "MLPDynamics", "TrackedNeuralODE", "SavedValues", "SaveFunc",
     "ERROR_ESTIMATE", "STIFFNESS_ESTIMATE", "STIFFNESS_SCALED", "ERROR_PLUS_STIFFNESS", "ClassifierNODE", "Optimiser",
-    "update_parameters_", "track", "untrack", "colmajor", "from_colmajor",
+    "update_parameters_", "track", "untrack", "colmajor", "from_colmajor", "solution", "ODESolution", "DEStats",
     "LatentGRU", "LatentTimeSeriesModel", "latent_ode_model", "log_likelihood", "kl_divergence", "loss_function",
 ]

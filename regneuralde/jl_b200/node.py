@@ -385,3 +385,56 @@ class TrackedNeuralODE:
 
     def launch_count(self) -> int:
         return sum(int(h.lib.rnde_launch_count(h.h)) for h in self._handles.values())
+
+
+@dataclass
+class DEStats:
+    """sol.destats of OrdinaryDiffEq (the fields the reference reads: nf; plus the accept/reject counts)."""
+    nf: int
+    naccept: int
+    nreject: int
+
+
+@dataclass
+class ODESolution:
+    """What ``solution(n, x, p; ...)`` hands back (src/models/neural_ode.jl:182-210): the time points and states the
+    solver saved, the statistics and the return code.  Without ``saveat`` the node's kwargs (``save_everystep=false``,
+    ``save_start=false``) leave exactly the final state; with ``saveat`` the states at those times."""
+    t: torch.Tensor
+    u: list
+    destats: DEStats
+    retcode: str
+    step_t: torch.Tensor        # end time of every accepted step (not part of the reference object; handy for plots)
+
+    def __getitem__(self, i):
+        return self.u[i]
+
+    def __len__(self):
+        return len(self.u)
+
+
+def solution(n: TrackedNeuralODE, x: torch.Tensor, p: Optional[torch.Tensor] = None, *, solver=None, tspan=None, saveat=None) -> ODESolution:
+    """src/models/neural_ode.jl:182-210: solve without the regulariser callback, optionally with another solver
+    (``Tsit5()`` / ``AutoTsit5(Tsit5())``) or time span, and return the solution object instead of the functor's tuple."""
+    times = saveat if saveat is not None else n.saveat
+    node = TrackedNeuralODE(n.model, n.tspan if tspan is None else tspan, n.time_dep, False, n.solver if solver is None else solver,
+                            reltol=n.reltol, abstol=n.abstol, maxiters=n.maxiters, tape_capacity=n.tape_capacity,
+                            kernel_variant=n.kernel_variant, kblock=n.kblock, device=str(n.device),
+                            **({"saveat": list(times)} if times is not None else {}))
+    with torch.no_grad():
+        res, nfe, _ = node(x, n.p if p is None else p)
+    st = node.last_stats
+    t0, t1 = node.tspan
+    hd = next(iter(node._handles.values()))
+    k = int(st.naccept)
+    tb, db = (C.c_float * max(k, 1))(), (C.c_float * max(k, 1))()
+    hd.check(hd.lib.rnde_get_steps(hd.h, tb, db, None, None, k), "rnde_get_steps")
+    step_t = torch.tensor([t0] + [tb[i] + db[i] for i in range(k)], dtype=torch.float32)
+    if times is not None:
+        ts = torch.tensor(list(times), dtype=torch.float32)
+        us = [res[:, i, :] for i in range(res.shape[1])]
+    else:
+        ts = torch.tensor([t1], dtype=torch.float32)
+        us = [res]
+    return ODESolution(t=ts, u=us, destats=DEStats(int(st.nf), int(st.naccept), int(st.nreject)),
+                       retcode="Success" if st.retcode == L.OK else L.lib().rnde_status_string(st.retcode).decode(), step_t=step_t)

@@ -335,6 +335,27 @@ def test_chain_field_latent_ode(oracle_built, name, D, widths, acts, pre_act, B,
         assert e_p <= 1e-4 and e_x <= 1e-4, (e_p, e_x)
 
 
+def test_solution_object(oracle_built):
+    """solution(n, x, p; solver, tspan, saveat) (neural_ode.jl:182-210): same solve without the callback, solver override."""
+    r = R()
+    rng = np.random.default_rng(3)
+    D, H, B = 2, 10, 6
+    p_np = orc.glorot_params(rng, D, H); x_np = rng.random((D, B), dtype=np.float32)
+    node = make_node(D, H, 0, True, r.Tsit5())
+    x = torch.from_numpy(x_np).cuda(); p = torch.from_numpy(p_np).cuda()
+    sol = r.solution(node, x, p)
+    ref = orc.Oracle(oracle_cfg(D, H, B, 0, 0, orc.REG_NONE)).forward(x_np, p_np)
+    assert sol.retcode == "Success" and len(sol) == 1 and float(sol.t[-1]) == 1.0
+    assert (sol.destats.nf, sol.destats.naccept, sol.destats.nreject) == (ref.nf, ref.naccept, ref.nreject)
+    assert np.array_equal(bits(sol[0].cpu().numpy()), bits(ref.u))
+    assert len(sol.step_t) == ref.naccept + 1 and abs(float(sol.step_t[-1]) - 1.0) < 1e-6
+    sol2 = r.solution(node, x, p, solver=r.AutoTsit5(), tspan=[0.0, 0.5], saveat=[0.0, 0.25, 0.5])
+    cfg = oracle_cfg(D, H, B, 0, 1, orc.REG_NONE); cfg.t1 = 0.5; cfg.saveat = np.array([0.0, 0.25, 0.5])
+    ref2 = orc.Oracle(cfg).forward(x_np, p_np)
+    assert len(sol2) == 3 and sol2.destats.nf == ref2.nf
+    assert np.array_equal(bits(torch.stack(sol2.u).cpu().numpy()), bits(ref2.usave))
+
+
 def test_update_parameters_matches_flux_momentum():
     """Optimiser(InvDecay(1e-5), Momentum(0.1, 0.9)) on raw arrays, empty parameter vectors skipped (src/utils.jl:149-156)."""
     r = R()
