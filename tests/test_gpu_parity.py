@@ -335,6 +335,50 @@ def test_chain_field_latent_ode(oracle_built, name, D, widths, acts, pre_act, B,
         assert e_p <= 1e-4 and e_x <= 1e-4, (e_p, e_x)
 
 
+_SWEEP_SCRIPT = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, ".")
+import regneuralde.jl_b200 as r
+from oracle import orc
+rng = np.random.default_rng(21)
+D, H, B = 784, 100, 80
+p_np = orc.glorot_params(rng, D, H); x_np = rng.random((D, B), dtype=np.float32)
+w = rng.standard_normal((D, B)).astype(np.float32)
+node = r.TrackedNeuralODE(r.MLPDynamics(D, H), [0.0, 1.0], True, True, r.AutoTsit5(), tape_capacity=64)
+x = torch.from_numpy(x_np).cuda().requires_grad_(True); p = torch.from_numpy(p_np).cuda().requires_grad_(True)
+res, nfe, sv = node(x, p, func=r.ERROR_PLUS_STIFFNESS)
+ws = rng.standard_normal(len(sv)).astype(np.float32)
+((res * torch.from_numpy(w).cuda()).sum() + (sv.saveval * torch.from_numpy(ws).cuda()).sum()).backward()
+np.savez(sys.argv[1], dp=p.grad.cpu().numpy(), dx=x.grad.cpu().numpy(), w=w, ws=ws, x=x_np, p=p_np, nfe=nfe)
+"""
+
+
+def test_tensor_core_sweep_agrees_with_ffma_sweep(oracle_built, tmp_path):
+    """bwd4tc_kernel (tcgen05, BF16 hi+lo split) against bwd4_kernel (FFMA, RNDE_BWD_FFMA=1) and the oracle on the same
+    tape: MNIST-shaped field, ragged batch (80 = 5 clusters), AutoTsit5 with the combined regulariser (all cotangent paths)."""
+    import os, subprocess, sys
+    outs = {}
+    for name, env in (("tc", {}), ("ffma", {"RNDE_BWD_FFMA": "1"})):
+        f = tmp_path / f"{name}.npz"
+        e = dict(os.environ); e.update(env)
+        r_ = subprocess.run([sys.executable, "-c", _SWEEP_SCRIPT, str(f)], env=e, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(__file__)))
+        assert r_.returncode == 0, r_.stderr[-2000:]
+        outs[name] = np.load(f)
+    a, b = outs["tc"], outs["ffma"]
+    assert int(a["nfe"]) == int(b["nfe"])
+    rel = lambda u, v: np.abs(u - v).max() / np.abs(v).max()
+    D, H, B = 784, 100, 80
+    o = orc.Oracle(oracle_cfg(D, H, B, 1, 1, orc.REG_ERR_PLUS_STIFF))
+    o.forward(a["x"], a["p"])
+    dp_hi, dx_hi, _, _ = o.backward(a["w"], a["ws"], hi=True)
+    dp_32, dx_32, _, _ = o.backward(a["w"], a["ws"])
+    for name, g in outs.items():
+        e_p, e_x = rel(g["dp"], dp_hi), rel(g["dx"], dx_hi)
+        assert e_p <= max(1e-4, 10 * rel(dp_32, dp_hi)) and e_x <= max(1e-4, 10 * rel(dx_32, dx_hi)), (name, e_p, e_x)
+    # the two sweeps see the same tape: they differ only by the rounding of their products
+    assert rel(a["dx"], b["dx"]) <= max(1e-4, 10 * rel(dx_32, dx_hi)) and rel(a["dp"], b["dp"]) <= max(1e-4, 10 * rel(dp_32, dp_hi))
+
+
 def test_solution_object(oracle_built):
     """solution(n, x, p; solver, tspan, saveat) (neural_ode.jl:182-210): same solve without the callback, solver override."""
     r = R()
