@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(V2_NT, 1) fwd4_kernel(const KParams P) {
     if (tid == 0) {
         Ctl c;
         c.t = P.t0; c.dt = 0.f; c.dtpropose = 0.f; c.qold = (float)1e-4; c.q11 = 1.f; c.eig_prev = 1.f; c.EEst = 1.f; c.eig = 1.f;
+        c.qold_pow = canon_powf((float)1e-4, (float)(2.0 / 25.0)); c.qold_pow_next = c.qold_pow;
         c.dt_init = 0.f; c.dt_last = 0.f;
         c.accept = 0; c.accept_prev = 1; c.done = 0; c.iter = 0; c.nf = 0; c.naccept = 0; c.nreject = 0; c.n_saved = 0;
         c.retcode = RNDE_OK; c.as_count = 0; c.as_stiff = 0;
@@ -418,7 +419,13 @@ __global__ void __launch_bounds__(V2_NT, 1) fwd4_kernel(const KParams P) {
         if (warp < NV) {
             const float* g = gcol + (size_t)warp * P.colsum_stride;
             float s = 0.f;
-            for (int jx = lane; jx < P.Bglobal; jx += 32) s = s + __ldcg(g + jx);
+            for (int j0 = lane; j0 < P.Bglobal; j0 += 32 * 8) {      // 8 loads in flight, added in the canonical order
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = (j0 + 32 * u < P.Bglobal) ? __ldcg(g + j0 + 32 * u) : 0.f;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) if (j0 + 32 * u < P.Bglobal) s = s + v[u];
+            }
 #pragma unroll
             for (int off = 16; off >= 1; off >>= 1) s = s + __shfl_xor_sync(0xffffffffu, s, off);
             if (lane == 0) sTot[warp] = rn_sqrtf(rn_divf(s, (float)P.norm_count));
@@ -593,6 +600,10 @@ __global__ void __launch_bounds__(V2_NT, 1) fwd4_kernel(const KParams P) {
             norms([&](int e, float* o) { o[0] = atmp_val(e); }, std::integral_constant<int, 1>{}, o1);
             EEst = o1[0];
         }
+        if (tid == 32) {  // next step's qold^beta2, side by side with thread 0's EEst^beta1 (both are ~1 k-cycle double-precision pows)
+            const float qn = EEst > qoldinit ? EEst : qoldinit;
+            ctl->qold_pow_next = canon_powf(qn, beta2);
+        }
         if (tid == 0) {   // loopfooter!
             Ctl& c = *ctl;
             c.nf += 6;
@@ -603,7 +614,7 @@ __global__ void __launch_bounds__(V2_NT, 1) fwd4_kernel(const KParams P) {
                 if (EEst == 0.f) qv = rn_divf(1.f, qmax);
                 else {
                     c.q11 = canon_powf(EEst, beta1);
-                    qv = rn_divf(c.q11, canon_powf(c.qold, beta2));
+                    qv = rn_divf(c.q11, c.qold_pow);
                     float qq = rn_divf(qv, gamma);
                     const float hi = rn_divf(1.f, qmin), lo = rn_divf(1.f, qmax);
                     qq = hi < qq ? hi : qq;
@@ -636,6 +647,7 @@ __global__ void __launch_bounds__(V2_NT, 1) fwd4_kernel(const KParams P) {
         __syncthreads();
         mark(16);
         const int accepted = ctl->accept, finished = ctl->done;
+        if (tid == 0 && accepted) ctl->qold_pow = ctl->qold_pow_next;     // qold was updated: its power follows
         __syncthreads();
         if (accepted) {   // apply_step!: u <- u_new, fsalfirst <- fsallast
 #pragma unroll

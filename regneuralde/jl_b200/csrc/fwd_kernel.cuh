@@ -36,6 +36,7 @@ struct SmemLayout {
 
 struct Ctl {
     float t, dt, dtpropose, qold, q11, eig_prev, EEst, eig, dt_init, dt_last;
+    float qold_pow, qold_pow_next;     // qold^beta2 of the current / of the candidate next qold (computed by a second thread)
     int accept, accept_prev, done, iter, nf, naccept, nreject, n_saved, retcode, as_count, as_stiff;
 };
 
@@ -153,7 +154,13 @@ __device__ __forceinline__ void grid_rms(const KParams& P, const SmemLayout& L, 
     if (warp < NV) {
         const float* g = gcol + (size_t)warp * P.colsum_stride;
         float s = 0.f;
-        for (int j = lane; j < P.Bglobal; j += 32) s = s + __ldcg(g + j);
+        for (int j0 = lane; j0 < P.Bglobal; j0 += 32 * 16) {      // 16 loads in flight, added in the canonical order
+            float v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v[u] = (j0 + 32 * u < P.Bglobal) ? __ldcg(g + j0 + 32 * u) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) if (j0 + 32 * u < P.Bglobal) s = s + v[u];
+        }
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) s = s + __shfl_xor_sync(0xffffffffu, s, off);
         if (lane == 0) sTot[warp] = rn_sqrtf(rn_divf(s, (float)P.norm_count));
