@@ -488,7 +488,20 @@ def _exact_worker(rank, world, port, q):
                               dist_mode=L.DIST_EXACT, rank=rank, world=world)
     with torch.no_grad():
         res, nfe, sv = node(torch.from_numpy(np.ascontiguousarray(x_np[:, rank * Bl:(rank + 1) * Bl])).cuda(), torch.from_numpy(p_np).cuda())
-    q.put((rank, res.cpu().numpy(), sv.saveval.cpu().numpy(), nfe))
+    # the Latent-ODE solver half (chain field + saveat) in the same mode
+    Dc, Bc = 20, 64
+    rngc = np.random.default_rng(77)
+    pc = orc.glorot_chain_params(rngc, Dc, LATENT_WIDTHS, bias_scale=0.05); xc = rngc.standard_normal((Dc, Bc)).astype(np.float32)
+    layers, K = [], Dc
+    for M in LATENT_WIDTHS:
+        layers.append(r.Dense(K, M, "tanh")); K = M
+    nodec = r.TrackedNeuralODE(r.Chain("tanh", *layers), [0.0, 1.0], False, True, r.AutoTsit5(), saveat=[0.0, 0.3, 0.55, 1.0], reltol=1.4e-8,
+                               abstol=1.4e-8, dist_mode=L.DIST_EXACT, rank=rank, world=world)
+    Blc = Bc // world
+    with torch.no_grad():
+        resc, nfec, svc = nodec(torch.from_numpy(np.ascontiguousarray(xc[:, rank * Blc:(rank + 1) * Blc])).cuda(), torch.from_numpy(pc).cuda(),
+                                func=r.ERROR_PLUS_STIFFNESS)
+    q.put((rank, res.cpu().numpy(), sv.saveval.cpu().numpy(), nfe, resc.cpu().numpy(), svc.saveval.cpu().numpy(), nfec))
     dist.destroy_process_group()
 
 
@@ -515,3 +528,13 @@ def test_exact_data_parallel_matches_single_solve(oracle_built):
     assert outs[0][3] == ref.nf and outs[1][3] == ref.nf
     assert np.array_equal(bits(u), bits(ref.u))
     assert np.array_equal(bits(outs[0][2]), bits(ref.saveval)) and np.array_equal(bits(outs[1][2]), bits(ref.saveval))
+    Dc, Bc = 20, 64
+    rngc = np.random.default_rng(77)
+    pc = orc.glorot_chain_params(rngc, Dc, LATENT_WIDTHS, bias_scale=0.05); xc = rngc.standard_normal((Dc, Bc)).astype(np.float32)
+    cfg = orc.OracleConfig(D=Dc, H=50, B=Bc, alg=1, reg_kind=orc.REG_ERR_PLUS_STIFF, kblock1=Dc, widths=LATENT_WIDTHS, acts=(1,) * 8, pre_act=1,
+                           saveat=np.array([0.0, 0.3, 0.55, 1.0], dtype=np.float32).astype(np.float64))
+    refc = orc.Oracle(cfg).forward(xc, pc)
+    usave = np.concatenate([o[4] for o in outs], axis=2).transpose(1, 0, 2)          # (D, S, B) shards -> (S, D, B)
+    assert outs[0][6] == refc.nf and outs[1][6] == refc.nf
+    assert np.array_equal(bits(usave), bits(refc.usave)), "chain field + saveat in exact mode not bit-identical"
+    assert np.array_equal(bits(outs[0][5]), bits(refc.saveval))
