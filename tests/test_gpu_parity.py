@@ -99,6 +99,8 @@ BWD_CASES = [
     ("mnist B=48 cluster4 grad", 784, 100, 48, 1, False, "ERROR_ESTIMATE", 4, 1e-4),
     ("mnist B=512 grad", 784, 100, 512, 1, False, "ERROR_ESTIMATE", 0, 1e-4),
     ("mnist B=512 stiff_est grad", 784, 100, 512, 1, True, "STIFFNESS_SCALED", 0, None),
+    ("D=640 H=72 cluster4 (tensor-core sweep, generic dims)", 640, 72, 40, 1, True, "ERROR_PLUS_STIFFNESS", 4, None),
+    ("D=800 H=96 cluster4 (tensor-core sweep, identity output)", 800, 96, 20, 0, False, None, 4, 1e-4),
 ]
 
 
