@@ -1,0 +1,49 @@
+"""Small end-to-end cases for compute-sanitizer (memcheck / racecheck / synccheck):
+    compute-sanitizer --tool memcheck python tools/sanitize_cases.py [case ...]
+cases: toy (CTA variant), stream, mnist (cluster-4 forward, tensor-core sweep, tcgen05 weight gradients), cluster8, chain (chain field + saveat), gru."""
+import sys
+import numpy as np
+import torch
+sys.path.insert(0, ".")
+import regneuralde.jl_b200 as r
+from oracle import orc
+
+cases = sys.argv[1:] or ["toy", "stream", "mnist", "cluster8", "chain", "gru"]
+rng = np.random.default_rng(0)
+
+
+def tdchain(D, H, B, variant, solver, func, act_out=True, cap=16):
+    model = r.TDChain(r.Dense(D + 1, H, "tanh"), r.Dense(H + 1, D, "tanh" if act_out else None))
+    node = r.TrackedNeuralODE(model, [0.0, 0.05], True, True, solver, kernel_variant=variant, tape_capacity=cap)
+    x = torch.from_numpy(rng.random((D, B), dtype=np.float32)).cuda().requires_grad_(True)
+    p = torch.from_numpy(orc.glorot_params(rng, D, H)).cuda().requires_grad_(True)
+    res, nfe, sv = node(x, p, func=func)
+    (res.sum() + sv.saveval.sum()).backward()
+    torch.cuda.synchronize()
+    return nfe
+
+
+for c in cases:
+    if c == "toy":
+        print(c, tdchain(2, 10, 7, 1, r.Tsit5(), r.ERROR_ESTIMATE, act_out=False))
+    elif c == "stream":
+        print(c, tdchain(2, 10, 9, 2, r.AutoTsit5(), r.ERROR_PLUS_STIFFNESS, act_out=False))
+    elif c == "mnist":
+        print(c, tdchain(784, 100, 20, 4, r.AutoTsit5(), r.ERROR_PLUS_STIFFNESS))
+    elif c == "cluster8":
+        print(c, tdchain(784, 100, 33, 3, r.Tsit5(), r.ERROR_ESTIMATE))
+    elif c == "chain":
+        W = (50, 20, 50, 20)
+        layers, K = [], 20
+        for M in W:
+            layers.append(r.Dense(K, M, "tanh")); K = M
+        node = r.TrackedNeuralODE(r.Chain("tanh", *layers), [0.0, 0.1], False, True, r.Tsit5(), saveat=[0.0, 0.03, 0.1], tape_capacity=16)
+        x = torch.randn(20, 6, device="cuda", requires_grad=True); p = node.p.clone().requires_grad_(True)
+        res, nfe, sv = node(x, p, func=r.ERROR_ESTIMATE)
+        (res.sum() + sv.saveval.sum()).backward(); torch.cuda.synchronize()
+        print(c, nfe)
+    elif c == "gru":
+        gru = r.LatentGRU(5, 6, 4)
+        x = torch.randn(11, 5, 6, device="cuda"); p = gru.p.clone().requires_grad_(True)
+        gru(x, p).sum().backward(); torch.cuda.synchronize()
+        print(c, "ok")
