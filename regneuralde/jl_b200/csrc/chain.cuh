@@ -143,7 +143,8 @@ __device__ __forceinline__ const float* chain_vjp(const KParams& P, const ChainV
 // grid = (splits, layers, output chunks); a CTA walks a contiguous range of (record, tile) pairs, stages 64 columns at
 // a time and every thread owns up to CW_OUT (output, input) pairs of its chunk; partial sums are FP32 over one stage
 // and FP64 across stages (the regulariser cotangents cancel between records: DESIGN.md section 5).
-constexpr int CW_NT = 256, CW_COLS = 64, CW_LD = 68, CW_OUT = 6;   // CW_LD: padded row stride (conflict-free LDS.128)
+constexpr int CW_NT = 256, CW_COLS = 64, CW_LD = 68;   // CW_LD: padded row stride (conflict-free LDS.128)
+constexpr int CW_TPT = 2;                              // 4 x 4 output tiles per thread: 512 tiles >= 10 x 44 (the 40 x 176 GRU layers)
 struct WgLayer {
     const float* dptr; const float* aptr;     // delta tape, input-activation tape
     int dstride, astride;                     // floats per (record, tile) block of each tape
@@ -152,59 +153,91 @@ struct WgLayer {
 };
 struct WgDesc { WgLayer l[8]; int nl; };
 
+// rows x 64 columns of a tape into shared memory as float4 (tile-major items: consecutive threads read consecutive rows of one
+// (record, tile) block = contiguous memory); `ones` appends a row of 1 (the bias input)
+__device__ __forceinline__ void wg_stage(float* dst, const float* __restrict__ src, const int stride, const int row0, const int rows, const bool ones,
+                                         const int NPt, const long long t0, const long long ntile) {
+    const int v4 = NPt / 4, tiles = CW_COLS / NPt;
+    const int per_tile = rows * v4;
+    for (int item = threadIdx.x; item < tiles * per_tile; item += CW_NT) {
+        const int tl = item / per_tile, rem = item - tl * per_tile;
+        const int row = rem / v4, v = rem - row * v4;
+        const long long tile = t0 + tl;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tile < ntile) x = __ldcg(reinterpret_cast<const float4*>(src + (size_t)tile * stride + (size_t)(row0 + row) * NPt + v * 4));
+        *reinterpret_cast<float4*>(dst + row * CW_LD + tl * NPt + v * 4) = x;
+    }
+    if (ones) {
+        for (int c = threadIdx.x; c < CW_COLS; c += CW_NT) dst[rows * CW_LD + c] = (t0 + c / NPt < ntile) ? 1.f : 0.f;
+    }
+}
+
 __global__ void __launch_bounds__(CW_NT) dense_wgrad_kernel(const WgDesc desc, const int NPt, const long long ntile, double* __restrict__ acc_out) {
     extern __shared__ __align__(16) float csm[];
     const int tid = threadIdx.x;
     const WgLayer& Ld = desc.l[blockIdx.y];
     const int M = Ld.M, K = Ld.K;
-    const int nout = M * (K + 1);
-    const int e0 = blockIdx.z * (CW_OUT * CW_NT);
-    if (e0 >= nout) return;
-    float* sDel = csm;                      // M x CW_LD
-    float* sAct = csm + M * CW_LD;          // (K+1) x CW_LD, last row = 1 (bias)
+    const int MT = (M + 3) / 4, IT = (K + 1 + 3) / 4;        // 4 x 4 output tiles: 4 outputs x 4 inputs (input K = bias)
+    const int ntiles_out = MT * IT;
+    float* sDel = csm;                                       // round_up(M,4) x CW_LD
+    float* sAct = csm + MT * 4 * CW_LD;                      // round_up(K+1,4) x CW_LD, row K = 1 (bias)
+    for (int e = tid; e < (MT * 4 + IT * 4) * CW_LD; e += CW_NT) csm[e] = 0.f;      // padding rows stay zero
     const int tiles_per_stage = CW_COLS / NPt;
     const long long nstage = (ntile + tiles_per_stage - 1) / tiles_per_stage;
     const long long s0 = nstage * blockIdx.x / gridDim.x, s1 = nstage * (blockIdx.x + 1) / gridDim.x;
-    double acc[CW_OUT];
+    double acc[CW_TPT][16];
 #pragma unroll
-    for (int r = 0; r < CW_OUT; ++r) acc[r] = 0.0;
+    for (int t = 0; t < CW_TPT; ++t)
+#pragma unroll
+        for (int r = 0; r < 16; ++r) acc[t][r] = 0.0;
     for (long long s = s0; s < s1; ++s) {
         const long long t0 = s * tiles_per_stage;
         __syncthreads();
-        for (int e = tid; e < M * CW_COLS; e += CW_NT) {
-            const int tl = e / (M * NPt), rem = e - tl * (M * NPt), o = rem / NPt, n = rem - o * NPt;
-            const long long tile = t0 + tl;
-            sDel[o * CW_LD + tl * NPt + n] = (tile < ntile) ? __ldcg(Ld.dptr + (size_t)tile * Ld.dstride + (size_t)(Ld.doff + o) * NPt + n) : 0.f;
-        }
-        for (int e = tid; e < (K + 1) * CW_COLS; e += CW_NT) {
-            const int tl = e / ((K + 1) * NPt), rem = e - tl * ((K + 1) * NPt), i = rem / NPt, n = rem - i * NPt;
-            const long long tile = t0 + tl;
-            float v = 0.f;
-            if (tile < ntile) v = (i == K) ? 1.f : __ldcg(Ld.aptr + (size_t)tile * Ld.astride + (size_t)(Ld.aoff + i) * NPt + n);
-            sAct[i * CW_LD + tl * NPt + n] = v;
-        }
+        wg_stage(sDel, Ld.dptr, Ld.dstride, Ld.doff, M, false, NPt, t0, ntile);
+        wg_stage(sAct, Ld.aptr, Ld.astride, Ld.aoff, K, true, NPt, t0, ntile);
         __syncthreads();
 #pragma unroll
-        for (int r = 0; r < CW_OUT; ++r) {
-            const int e = e0 + tid + r * CW_NT;
-            if (e < nout) {
-                const int i = e / M, o = e - i * M;       // Flux order: column-major out x in, bias after the weights
-                const float4* d4 = reinterpret_cast<const float4*>(sDel + o * CW_LD);
-                const float4* a4 = reinterpret_cast<const float4*>(sAct + i * CW_LD);
-                float s32 = 0.f;
+        for (int t = 0; t < CW_TPT; ++t) {
+            const int ot = tid + t * CW_NT;
+            if (ot < ntiles_out) {
+                const int it = ot / MT, mt = ot - it * MT;
+                const float* dp = sDel + mt * 4 * CW_LD;
+                const float* ap = sAct + it * 4 * CW_LD;
+                float s32[16];
 #pragma unroll
+                for (int r = 0; r < 16; ++r) s32[r] = 0.f;
+#pragma unroll 4
                 for (int c4 = 0; c4 < CW_COLS / 4; ++c4) {
-                    const float4 dv = d4[c4], av = a4[c4];
-                    s32 = fmaf(dv.x, av.x, s32); s32 = fmaf(dv.y, av.y, s32); s32 = fmaf(dv.z, av.z, s32); s32 = fmaf(dv.w, av.w, s32);
+                    float4 d[4], a[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) { d[r] = *reinterpret_cast<const float4*>(dp + r * CW_LD + c4 * 4); a[r] = *reinterpret_cast<const float4*>(ap + r * CW_LD + c4 * 4); }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int o = 0; o < 4; ++o) {
+                            float v = s32[i * 4 + o];
+                            v = fmaf(d[o].x, a[i].x, v); v = fmaf(d[o].y, a[i].y, v); v = fmaf(d[o].z, a[i].z, v); v = fmaf(d[o].w, a[i].w, v);
+                            s32[i * 4 + o] = v;
+                        }
                 }
-                acc[r] += (double)s32;
+#pragma unroll
+                for (int r = 0; r < 16; ++r) acc[t][r] += (double)s32[r];
             }
         }
     }
 #pragma unroll
-    for (int r = 0; r < CW_OUT; ++r) {
-        const int e = e0 + tid + r * CW_NT;
-        if (e < nout) atomicAdd(acc_out + Ld.poff + e, acc[r]);
+    for (int t = 0; t < CW_TPT; ++t) {
+        const int ot = tid + t * CW_NT;
+        if (ot < ntiles_out) {
+            const int it = ot / MT, mt = ot - it * MT;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    const int in = it * 4 + i, on = mt * 4 + o;
+                    if (in <= K && on < M) atomicAdd(acc_out + Ld.poff + in * M + on, acc[t][i * 4 + o]);   // Flux order: W column-major, bias (in == K) behind it
+                }
+        }
     }
 }
 
@@ -218,14 +251,14 @@ inline cudaError_t launch_dense_wgrad(const WgDesc& desc, int NPt, long long nti
                                       cudaStream_t st, int64_t* launches) {
     cudaError_t e = cudaMemsetAsync(acc, 0, sizeof(double) * np, st);
     if (e != cudaSuccess) return e;
-    int maxrows = 0, maxout = 0;
+    int maxrows = 0;
     for (int l = 0; l < desc.nl; ++l) {
-        maxrows = maxrows > desc.l[l].M + desc.l[l].K + 1 ? maxrows : desc.l[l].M + desc.l[l].K + 1;
-        maxout = maxout > desc.l[l].M * (desc.l[l].K + 1) ? maxout : desc.l[l].M * (desc.l[l].K + 1);
+        const int rows = (desc.l[l].M + 3) / 4 * 4 + (desc.l[l].K + 1 + 3) / 4 * 4;
+        maxrows = maxrows > rows ? maxrows : rows;
+        if (((desc.l[l].M + 3) / 4) * ((desc.l[l].K + 1 + 3) / 4) > CW_TPT * CW_NT) return cudaErrorInvalidValue;
     }
-    const int chunks = (maxout + CW_OUT * CW_NT - 1) / (CW_OUT * CW_NT);
     const long long nstage = (ntile * NPt + CW_COLS - 1) / CW_COLS;
-    long long splits = 4LL * num_sms / (desc.nl * chunks);
+    long long splits = 2LL * num_sms / desc.nl;
     if (splits > nstage) splits = nstage;
     if (splits < 1) splits = 1;
     const size_t smem = sizeof(float) * (size_t)maxrows * CW_LD;
@@ -233,7 +266,7 @@ inline cudaError_t launch_dense_wgrad(const WgDesc& desc, int NPt, long long nti
         e = cudaFuncSetAttribute(dense_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    dense_wgrad_kernel<<<dim3((unsigned)splits, desc.nl, chunks), CW_NT, smem, st>>>(desc, NPt, ntile, acc);
+    dense_wgrad_kernel<<<dim3((unsigned)splits, desc.nl), CW_NT, smem, st>>>(desc, NPt, ntile, acc);
     wgrad_finish_kernel<<<(np + 255) / 256, 256, 0, st>>>(acc, dp, np);
     if (launches) *launches += 2;
     return cudaGetLastError();
