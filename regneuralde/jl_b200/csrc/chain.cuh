@@ -60,6 +60,48 @@ __device__ __forceinline__ void quad_dense(const float* __restrict__ W, const in
     }
 }
 
+// The same product with compile-time layer shape (MC x KC) for 4-column tiles: the quarter loops unroll completely and every
+// offset is a constant -- these layers are tiny (5 or 13 fma per lane) and otherwise dominated by loop and index overhead.
+template <int NT, bool TRANS, int MC, int KC, class Fin>
+__device__ __forceinline__ void quad_dense_fixed(const float* __restrict__ W, const float* __restrict__ in, Fin fin) {
+    constexpr int NP = 4;
+    constexpr int A = TRANS ? KC : MC, Cn = TRANS ? MC : KC;
+    constexpr int kb = (Cn + 3) / 4;
+    constexpr int total = A * 4;
+    static_assert(total <= NT, "one pass");
+    const int item = (int)threadIdx.x;
+    const bool valid = item < total;
+    const int blk = item & 3, a = valid ? (item >> 2) : 0;
+    const int c0 = blk * kb;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    const float* wp = TRANS ? W + MC * a + c0 : W + MC * c0 + a;
+    const float* ip = in + c0 * NP;
+#pragma unroll
+    for (int j = 0; j < kb; ++j) {
+        if (valid && c0 + j < Cn) {
+            const float w = TRANS ? wp[j] : wp[j * MC];
+            const float4 x = *reinterpret_cast<const float4*>(ip + j * NP);
+            acc0 = rn_fmaf(w, x.x, acc0); acc1 = rn_fmaf(w, x.y, acc1); acc2 = rn_fmaf(w, x.z, acc2); acc3 = rn_fmaf(w, x.w, acc3);
+        }
+    }
+    acc0 = acc0 + __shfl_xor_sync(0xffffffffu, acc0, 1); acc1 = acc1 + __shfl_xor_sync(0xffffffffu, acc1, 1);
+    acc2 = acc2 + __shfl_xor_sync(0xffffffffu, acc2, 1); acc3 = acc3 + __shfl_xor_sync(0xffffffffu, acc3, 1);
+    acc0 = acc0 + __shfl_xor_sync(0xffffffffu, acc0, 2); acc1 = acc1 + __shfl_xor_sync(0xffffffffu, acc1, 2);
+    acc2 = acc2 + __shfl_xor_sync(0xffffffffu, acc2, 2); acc3 = acc3 + __shfl_xor_sync(0xffffffffu, acc3, 2);
+    const float v = blk == 0 ? acc0 : (blk == 1 ? acc1 : (blk == 2 ? acc2 : acc3));
+    if (valid) fin(a, blk, v);
+}
+
+// dispatch: the Latent-ODE layer shapes (20 <-> 50, latent_ode.jl:109-121) get the unrolled form
+template <int NP, int NT, bool TRANS, class Fin>
+__device__ __forceinline__ void quad_dense_any(const float* __restrict__ W, const int M, const int K, const float* __restrict__ in, Fin fin) {
+    if constexpr (NP == 4) {
+        if (M == 50 && K == 20) { quad_dense_fixed<NT, TRANS, 50, 20>(W, in, fin); return; }
+        if (M == 20 && K == 50) { quad_dense_fixed<NT, TRANS, 20, 50>(W, in, fin); return; }
+    }
+    quad_dense<NP, NT, TRANS>(W, M, K, in, fin);
+}
+
 // sOut = f(sIn).  rec >= 0: record z, a_0..a_{L-2} and k on the tape ([rec][tile][row][NP]).
 template <int NP, int NT>
 __device__ __forceinline__ void chain_rhs(const KParams& P, const ChainView& c, const float* sIn, float* sOut, const int rec, const int q) {
@@ -84,7 +126,7 @@ __device__ __forceinline__ void chain_rhs(const KParams& P, const ChainView& c, 
         float* dst = last ? sOut : nxt;
         const int act = c.a[l];
         float* tp = rec < 0 ? nullptr : (last ? P.tapeK + dbase : P.tapeH + hbase + (size_t)hoff * NP);
-        quad_dense<NP, NT, false>(W, M, K, cur, [&](const int o, const int n, const float s) {
+        quad_dense_any<NP, NT, false>(W, M, K, cur, [&](const int o, const int n, const float s) {
             float v = s + b[o];
             if (act == RNDE_ACT_TANH) v = canon_tanhf(v);
             dst[o * NP + n] = v;
@@ -127,7 +169,7 @@ __device__ __forceinline__ const float* chain_vjp(const KParams& P, const ChainV
         const int actin = l ? c.a[l - 1] : c.pre;
         const float* ain = c.sH + hoff[l] * NP;
         float* dout = l ? P.tapeD1 + hbase + (size_t)hoff[l] * NP : nullptr;
-        quad_dense<NP, NT, true>(c.sW + poff[l], M, K, g, [&](const int i, const int n, float v) {
+        quad_dense_any<NP, NT, true>(c.sW + poff[l], M, K, g, [&](const int i, const int n, float v) {
             if (actin == RNDE_ACT_TANH) { const float av = ain[i * NP + n]; v = v * (1.f - av * av); }
             gn[i * NP + n] = v;
             if (dout) dout[i * NP + n] = v;
