@@ -70,6 +70,11 @@ enum { RNDE_REG_NONE = 0, RNDE_REG_ERR_DT = 1, RNDE_REG_STIFF_DT_ABS = 2, RNDE_R
 enum { RNDE_KERNEL_AUTO = 0, RNDE_KERNEL_CTA = 1, RNDE_KERNEL_STREAM = 2, RNDE_KERNEL_CLUSTER = 3, RNDE_KERNEL_CLUSTER4 = 4,
        RNDE_KERNEL_CHAIN = 5 /* CTA variant with 4-column tiles: chain fields, one CTA per SM at batch 512 */ };
 enum { RNDE_DIST_SINGLE = 0, RNDE_DIST_EXACT = 1, RNDE_DIST_INDEPENDENT = 2 };
+/* FMA_CHAIN: blocked fma chains in a fixed order (every kernel variant).
+ * FIXED24: exact truncated fixed-point products, order-independent, run as integer tensor-core MMAs by the cluster-4
+ * variant (csrc/fwd4x_kernel.cuh); bit-identical to the oracle's arith = 1.  The two modes are two
+ * different roundings of the same field (relative difference ~1e-7 per evaluation). */
+enum { RNDE_ARITH_FMA_CHAIN = 0, RNDE_ARITH_FIXED24 = 1 };
 
 typedef struct rnde_config {
     int32_t struct_bytes;     /* sizeof(rnde_config), for versioning */
@@ -101,7 +106,7 @@ typedef struct rnde_config {
     int32_t pre_act;
     int32_t layer_width[8];
     int32_t layer_act[8];
-    int32_t reserved1;
+    int32_t arith;            /* RNDE_ARITH_*: canonical arithmetic of the layer products (2-layer fields) */
 } rnde_config;
 
 typedef struct rnde_stats {

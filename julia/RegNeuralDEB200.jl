@@ -27,7 +27,7 @@ struct RndeConfig
     t0::Float32; t1::Float32; abstol::Float32; reltol::Float32; dtmin::Float32
     max_saveat::Int32; n_layers::Int32
     global_batch::Int64
-    pre_act::Int32; layer_width::NTuple{8,Int32}; layer_act::NTuple{8,Int32}; reserved1::Int32
+    pre_act::Int32; layer_width::NTuple{8,Int32}; layer_act::NTuple{8,Int32}; arith::Int32
 end
 
 mutable struct RndeStats

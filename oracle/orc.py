@@ -32,7 +32,7 @@ class _Cfg(C.Structure):
         ("dtmin", C.c_double),
         ("n_forced", C.c_int), ("forced_dt", C.POINTER(C.c_double)), ("forced_accept", C.POINTER(C.c_int)),
         ("n_saveat", C.c_int), ("saveat", C.POINTER(C.c_double)),
-        ("n_layers", C.c_int), ("width", C.c_int * 8), ("act", C.c_int * 8), ("pre_act", C.c_int),
+        ("n_layers", C.c_int), ("width", C.c_int * 8), ("act", C.c_int * 8), ("pre_act", C.c_int), ("arith", C.c_int),
     ]
 
 
@@ -90,6 +90,7 @@ class OracleConfig:
     widths: tuple | None = None
     acts: tuple | None = None
     pre_act: int = 0
+    arith: int = 0          # 1 = FIXED24 exact fixed-point layer products (rnde_oracle.c), the tensor-core forward stepper's arithmetic
 
     @property
     def n_params(self) -> int:
@@ -151,6 +152,7 @@ class Oracle:
             c.pre_act = int(cfg.pre_act)
             c.time_dep = 0
             c.H = max(cfg.widths)
+        c.arith = int(cfg.arith)
         if cfg.saveat is not None:
             sa = np.ascontiguousarray(cfg.saveat, dtype=np.float64)
             self._keep.append(sa)

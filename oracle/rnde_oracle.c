@@ -86,6 +86,9 @@ typedef struct {
     int width[8];
     int act[8];
     int pre_act;
+    /* arith = 1 (FIXED24): the layer products of the 2-layer field are exact truncated fixed-point products -- the
+     * arithmetic of the tensor-core forward stepper (csrc/fwd4x_kernel.cuh); see fixed24_* below. */
+    int arith;
 } orc_config;
 
 typedef struct {
@@ -209,8 +212,134 @@ static void chain_column(const orc_config* c, const REAL* p, const REAL* zj, REA
     memcpy(out, a[cur], sizeof(REAL) * D);
 }
 
+/* ------------------------------------------------------------------ */
+/* FIXED24 layer arithmetic (arith = 1)                                 */
+/* A dot product over one block of K inputs is evaluated as an exact integer expression, so that its value does not  */
+/* depend on the order of summation (tensor cores, any tiling):                                                      */
+/*   weights, per output row and block:  e_w = exponent(max_k |w|) (2^(e_w-1) <= max < 2^e_w), q_w = rint(w * 2^(22-e_w))  */
+/*   inputs, per column and block:       e_x likewise over the block's rows,                q_x = rint(x * 2^(22-e_x))  */
+/*   balanced base-256 digits q = d0*65536 + d1*256 + d2 (d1, d2 in [-128,127], |d0| <= 64)                           */
+/*   I_ac = sum_k dw_a[k] * dx_c[k] (exact integers),  T = I_00*2^24 + (I_01+I_10)*2^16 + (I_02+I_11+I_20)*2^8 + (I_12+I_21)  */
+/*   value = float(T) * 2^(e_w + e_x - 36)      -- only the digit product d2*d2 (2^-30 of full scale) is dropped          */
+/* max < 2^-102 (incl. 0 and subnormals) quantises to 0.  Layer 1 has 4 blocks of D/4 rows (= the CTAs of a cluster),  */
+/* combined as ((p0+p1)+p2)+p3; layer 2 one block of H.  Float32 build only.                                          */
+/* ------------------------------------------------------------------ */
+typedef struct { int valid; int D, H, R; int8_t* w1[3]; int* ew1; int8_t* w2[3]; int* ew2; } fixed24_weights;
+static fixed24_weights g_f24 = {0};
+
+static int f24_exponent(float amax) {      /* e with 2^(e-1) <= amax < 2^e; returns INT32_MIN when the block quantises to zero */
+    uint32_t u; memcpy(&u, &amax, 4);
+    const int eb = (int)((u >> 23) & 0xFF);
+    if (eb < 24) return -2147483647 - 1;
+    return eb - 126;
+}
+static float f24_pow2(int e) {             /* 2^e, clamped to the normal range (e < -126 gives 0) */
+    if (e < -126) return 0.0f;
+    if (e > 127) e = 127;
+    uint32_t u = (uint32_t)(e + 127) << 23; float f; memcpy(&f, &u, 4); return f;
+}
+static void f24_digits(float x, int e, int8_t* d0, int8_t* d1, int8_t* d2) {
+    if (e == -2147483647 - 1) { *d0 = *d1 = *d2 = 0; return; }
+    const float sc = fminf(fmaxf(x * f24_pow2(22 - e), -8388607.0f), 8388607.0f);   /* never binds for finite data (|x| < 2^e) */
+    int q = (int)lrintf(sc);
+    const int b2 = ((q + 128) & 255) - 128; q = (q - b2) >> 8;
+    const int b1 = ((q + 128) & 255) - 128; q = (q - b1) >> 8;
+    *d0 = (int8_t)q; *d1 = (int8_t)b1; *d2 = (int8_t)b2;
+}
+static void fixed24_prepare(const orc_config* c, const REAL* p) {
+    const int D = c->D, H = c->H, td = c->time_dep ? 1 : 0, R = D / 4;
+    fixed24_weights* q = &g_f24;
+    for (int a = 0; a < 3; ++a) { free(q->w1[a]); free(q->w2[a]); q->w1[a] = (int8_t*)malloc((size_t)H * D); q->w2[a] = (int8_t*)malloc((size_t)D * H); }
+    free(q->ew1); free(q->ew2);
+    q->ew1 = (int*)malloc(sizeof(int) * H * 4); q->ew2 = (int*)malloc(sizeof(int) * D);
+    const REAL* W1 = p;
+    const REAL* W2 = p + (size_t)H * (D + td) + H;
+    for (int o = 0; o < H; ++o)
+        for (int b = 0; b < 4; ++b) {
+            float amax = 0;
+            for (int k = b * R; k < (b + 1) * R; ++k) { const float a = fabsf((float)W1[(size_t)H * k + o]); if (a > amax) amax = a; }
+            const int e = f24_exponent(amax);
+            q->ew1[o * 4 + b] = e;
+            for (int k = b * R; k < (b + 1) * R; ++k)
+                f24_digits((float)W1[(size_t)H * k + o], e, &q->w1[0][(size_t)o * D + k], &q->w1[1][(size_t)o * D + k], &q->w1[2][(size_t)o * D + k]);
+        }
+    for (int r = 0; r < D; ++r) {
+        float amax = 0;
+        for (int k = 0; k < H; ++k) { const float a = fabsf((float)W2[(size_t)D * k + r]); if (a > amax) amax = a; }
+        const int e = f24_exponent(amax);
+        q->ew2[r] = e;
+        for (int k = 0; k < H; ++k) f24_digits((float)W2[(size_t)D * k + r], e, &q->w2[0][(size_t)r * H + k], &q->w2[1][(size_t)r * H + k], &q->w2[2][(size_t)r * H + k]);
+    }
+    q->D = D; q->H = H; q->R = R; q->valid = 1;
+}
+/* exact block product: dw[3] point at K digits of one weight row, dx[3] at K digits of one input column */
+static float f24_block(const int8_t* const dw[3], int ew, const int8_t* const dx[3], int ex, int K) {
+    if (ew == -2147483647 - 1 || ex == -2147483647 - 1) return 0.0f;
+    int I00 = 0, I01 = 0, I02 = 0, I10 = 0, I11 = 0, I12 = 0, I20 = 0, I21 = 0;
+    for (int k = 0; k < K; ++k) {
+        const int w0 = dw[0][k], w1 = dw[1][k], w2 = dw[2][k], x0 = dx[0][k], x1 = dx[1][k], x2 = dx[2][k];
+        I00 += w0 * x0; I01 += w0 * x1; I02 += w0 * x2; I10 += w1 * x0; I11 += w1 * x1; I12 += w1 * x2; I20 += w2 * x0; I21 += w2 * x1;
+    }
+    const long long T = ((long long)I00 << 24) + ((long long)(I01 + I10) << 16) + ((long long)(I02 + I11 + I20) << 8) + (long long)(I12 + I21);
+    return (float)T * f24_pow2(ew + ex - 36);
+}
+static void rhs_eval_fixed24(const orc_config* c, const REAL* p, const REAL* z, REAL t, REAL* k, REAL* hout) {
+    const int D = c->D, H = c->H, B = c->B, td = c->time_dep ? 1 : 0, R = D / 4;
+    const fixed24_weights* q = &g_f24;
+    const REAL* W1 = p;
+    const REAL* b1 = W1 + (size_t)H * (D + td);
+    const REAL* W2 = b1 + H;
+    const REAL* b2 = W2 + (size_t)D * (H + td);
+#pragma omp parallel
+    {
+        int8_t* dz[3]; int8_t* dh[3];
+        for (int a = 0; a < 3; ++a) { dz[a] = (int8_t*)malloc((size_t)D); dh[a] = (int8_t*)malloc((size_t)H); }
+        float* hh = (float*)malloc(sizeof(float) * H);
+#pragma omp for schedule(static)
+        for (int j = 0; j < B; ++j) {
+            const REAL* zj = z + (size_t)D * j;
+            int ex[4];
+            for (int b = 0; b < 4; ++b) {
+                float amax = 0;
+                for (int i = b * R; i < (b + 1) * R; ++i) { const float a = fabsf((float)zj[i]); if (a > amax) amax = a; }
+                ex[b] = f24_exponent(amax);
+                for (int i = b * R; i < (b + 1) * R; ++i) f24_digits((float)zj[i], ex[b], &dz[0][i], &dz[1][i], &dz[2][i]);
+            }
+            for (int o = 0; o < H; ++o) {
+                float pb[4];
+                for (int b = 0; b < 4; ++b) {
+                    const int8_t* dw[3] = {q->w1[0] + (size_t)o * D + b * R, q->w1[1] + (size_t)o * D + b * R, q->w1[2] + (size_t)o * D + b * R};
+                    const int8_t* dx[3] = {dz[0] + b * R, dz[1] + b * R, dz[2] + b * R};
+                    pb[b] = f24_block(dw, q->ew1[o * 4 + b], dx, ex[b], R);
+                }
+                float v = ((pb[0] + pb[1]) + pb[2]) + pb[3];      /* the reducer CTA adds the four CTAs' partials in rank order */
+                if (td) v = __builtin_fmaf((float)W1[(size_t)H * D + o], (float)t, v);
+                v = v + (float)b1[o];
+                hh[o] = (float)act_apply(c->act1, (REAL)v);
+            }
+            if (hout) for (int o = 0; o < H; ++o) hout[(size_t)H * j + o] = (REAL)hh[o];
+            float amax = 0;
+            for (int o = 0; o < H; ++o) { const float a = fabsf(hh[o]); if (a > amax) amax = a; }
+            const int eh = f24_exponent(amax);
+            for (int o = 0; o < H; ++o) f24_digits(hh[o], eh, &dh[0][o], &dh[1][o], &dh[2][o]);
+            REAL* kj = k + (size_t)D * j;
+            for (int r = 0; r < D; ++r) {
+                const int8_t* dw[3] = {q->w2[0] + (size_t)r * H, q->w2[1] + (size_t)r * H, q->w2[2] + (size_t)r * H};
+                const int8_t* dx[3] = {dh[0], dh[1], dh[2]};
+                float v = f24_block(dw, q->ew2[r], dx, eh, H);
+                if (td) v = __builtin_fmaf((float)W2[(size_t)D * H + r], (float)t, v);
+                v = v + (float)b2[r];
+                kj[r] = act_apply(c->act2, (REAL)v);
+            }
+        }
+        for (int a = 0; a < 3; ++a) { free(dz[a]); free(dh[a]); }
+        free(hh);
+    }
+}
+
 static void rhs_eval(const orc_config* c, const REAL* p, const REAL* z, REAL t, REAL* k, REAL* hout) {
     const int D = c->D, H = c->H, B = c->B, td = c->time_dep ? 1 : 0;
+    if (c->arith == 1 && c->n_layers == 0 && sizeof(REAL) == 4) { rhs_eval_fixed24(c, p, z, t, k, hout); return; }
     if (c->n_layers > 0) {
         (void)t; (void)hout;
 #pragma omp parallel for schedule(static)
@@ -569,6 +698,7 @@ int FN(forward)(void* hv, const REAL* x, const REAL* p, REAL* u_out, orc_stats* 
     h->u0 = (REAL*)malloc(sizeof(REAL) * n); memcpy(h->u0, x, sizeof(REAL) * n);
     h->p = (REAL*)malloc(sizeof(REAL) * h->np); memcpy(h->p, p, sizeof(REAL) * h->np);
     if (!h->saveval) { h->saveval = (REAL*)malloc(sizeof(REAL) * 65); }
+    if (c->arith == 1 && c->n_layers == 0 && sizeof(REAL) == 4) fixed24_prepare(c, h->p);
     step_ws* w = ws_alloc(c);
     REAL* u = (REAL*)malloc(sizeof(REAL) * n);
     REAL* scratch = (REAL*)malloc(sizeof(REAL) * 3 * n);
@@ -737,6 +867,7 @@ int FN(get_step)(void* hv, int j, double* t, double* dt, double* eest, double* e
 
 /* field evaluation exported for unit tests */
 int FN(rhs)(const orc_config* cfg, const REAL* p, const REAL* z, double t, REAL* k, REAL* hout) {
+    if (cfg->arith == 1 && cfg->n_layers == 0 && sizeof(REAL) == 4) fixed24_prepare(cfg, p);
     rhs_eval(cfg, p, z, (REAL)t, k, hout);
     return ORC_OK;
 }

@@ -31,6 +31,7 @@ ALG_TSIT5, ALG_AUTO_TSIT5 = 0, 1
 REG_NONE, REG_ERR_DT, REG_STIFF_DT_ABS, REG_STIFF_SCALED, REG_ERR_PLUS_STIFF = range(5)
 KERNEL_AUTO, KERNEL_CTA, KERNEL_STREAM, KERNEL_CLUSTER, KERNEL_CLUSTER4, KERNEL_CHAIN = range(6)
 DIST_SINGLE, DIST_EXACT, DIST_INDEPENDENT = range(3)
+ARITH_FMA_CHAIN, ARITH_FIXED24 = 0, 1
 
 EXPORTS = [
     "rnde_version", "rnde_status_string", "rnde_device_count", "rnde_create", "rnde_destroy", "rnde_last_error",
@@ -53,7 +54,7 @@ class Config(C.Structure):
         ("t0", C.c_float), ("t1", C.c_float), ("abstol", C.c_float), ("reltol", C.c_float), ("dtmin", C.c_float),
         ("max_saveat", C.c_int32), ("n_layers", C.c_int32),
         ("global_batch", C.c_int64),
-        ("pre_act", C.c_int32), ("layer_width", C.c_int32 * 8), ("layer_act", C.c_int32 * 8), ("reserved1", C.c_int32),
+        ("pre_act", C.c_int32), ("layer_width", C.c_int32 * 8), ("layer_act", C.c_int32 * 8), ("arith", C.c_int32),
     ]
 
 

@@ -15,6 +15,7 @@
 #include "bwd_kernel.cuh"
 #include "bwd4_kernel.cuh"
 #include "bwd4tc_kernel.cuh"
+#include "fwd4x_kernel.cuh"
 #include "wgrad_kernel.cuh"
 #include "wgrad_tc_kernel.cuh"
 #include "head_kernel.cuh"
@@ -97,13 +98,15 @@ static int init_constants(rnde_handle* h) {
 constexpr int NT_FWD = 256;
 typedef void (*kern_t)(const KParams);
 
-static kern_t fwd_kernel_for(int variant, int D = 0, int H = 0) {
+static kern_t fwd_kernel_for(int variant, int D = 0, int H = 0, int arith = 0) {
     switch (variant) {
         case RNDE_KERNEL_CTA: return fwd_kernel<1, 32, 4, true, NT_FWD>;
         case RNDE_KERNEL_STREAM: return fwd_kernel<1, 4, 1, false, NT_FWD>;
         case RNDE_KERNEL_CHAIN: return fwd_kernel<1, 4, 1, true, NT_FWD>;
         case RNDE_KERNEL_CLUSTER: return fwd_kernel<8, 32, 4, true, NT_FWD>;
-        case RNDE_KERNEL_CLUSTER4: return (H == 100 && D == 784) ? fwd4_kernel<100, 98> : fwd4_kernel<0, 0>;
+        case RNDE_KERNEL_CLUSTER4:
+            if (arith == RNDE_ARITH_FIXED24) return fwd4x_kernel;
+            return (H == 100 && D == 784) ? fwd4_kernel<100, 98> : fwd4_kernel<0, 0>;
         default: return nullptr;
     }
 }
@@ -192,7 +195,8 @@ extern "C" const char* rnde_last_error(const rnde_handle* h) { return h ? h->err
 extern "C" int rnde_kernel_variant(const rnde_handle* h) { return h ? h->variant : 0; }
 extern "C" int64_t rnde_launch_count(const rnde_handle* h) { return h ? h->launches : 0; }
 
-static size_t smem_bytes_fwd(int variant, int D, int H, int R, int HS, int kblock) {
+static size_t smem_bytes_fwd(int variant, int D, int H, int R, int HS, int kblock, int arith = 0) {
+    if (variant == RNDE_KERNEL_CLUSTER4 && arith == RNDE_ARITH_FIXED24) return (size_t)make_v4x_layout(D, H).total;
     if (variant == RNDE_KERNEL_CLUSTER4) return (size_t)make_v2_layout(D, H).total * sizeof(float);
     int G, NP; bool WS;
     variant_shape(variant, &G, &NP, &WS);
@@ -244,11 +248,14 @@ static int try_variant(rnde_handle* h, int variant, size_t smem_limit, std::stri
     const int nbl = (D + h->kblock - 1) / h->kblock;
     if (nbl > 64) { *why = "more than 64 canonical K-blocks"; return 0; }
     if (c.n_layers > 0 && variant != RNDE_KERNEL_CHAIN && variant != RNDE_KERNEL_CTA) { *why = "chain fields run on the CHAIN / CTA variants"; return 0; }
-    const size_t sf = smem_bytes_fwd(variant, D, H, R, HS, h->kblock) + sizeof(float) * chain_smem_floats(c, NP, false);
+    const size_t sf = smem_bytes_fwd(variant, D, H, R, HS, h->kblock, c.arith) + sizeof(float) * chain_smem_floats(c, NP, false);
     const size_t sb = c.need_backward ? smem_bytes_bwd(variant, D, H, R, HS, h->kblock) + sizeof(float) * chain_smem_floats(c, NP, true) : 0;
     if (sf > smem_limit || sb > smem_limit) { *why = "shared memory: need " + std::to_string(std::max(sf, sb)) + " B"; return 0; }
     // all CTAs must be co-resident (persistent grid with a grid barrier)
-    kern_t kf = fwd_kernel_for(variant, D, H);
+    if (c.arith == RNDE_ARITH_FIXED24 && (variant != RNDE_KERNEL_CLUSTER4 || c.n_layers > 0 || !v4x_shape_ok(D, H))) {
+        *why = "RNDE_ARITH_FIXED24 is implemented by the cluster-4 variant for 128 < D/4 <= 256, H <= 128"; return 0;
+    }
+    kern_t kf = fwd_kernel_for(variant, D, H, c.arith);
     if (cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sf) != cudaSuccess) { cudaGetLastError(); *why = "cudaFuncSetAttribute(fwd) failed"; return 0; }
     if (c.need_backward) {
         kern_t kb = bwd_kernel_for(variant, D, H);
@@ -304,6 +311,7 @@ extern "C" int rnde_create(const rnde_config* cfg, rnde_handle** out) {
     if (cfg->reg_kind < 0 || cfg->reg_kind > RNDE_REG_ERR_PLUS_STIFF || cfg->alg < 0 || cfg->alg > 1) return RNDE_ERR_ARG;
     if (!(cfg->t1 > cfg->t0) || !(cfg->abstol > 0.f) || !(cfg->reltol > 0.f)) return RNDE_ERR_ARG;
     if (cfg->dist_mode < RNDE_DIST_SINGLE || cfg->dist_mode > RNDE_DIST_INDEPENDENT) return RNDE_ERR_ARG;
+    if (cfg->arith < RNDE_ARITH_FMA_CHAIN || cfg->arith > RNDE_ARITH_FIXED24) return RNDE_ERR_ARG;
     if (cfg->dist_mode == RNDE_DIST_EXACT && (cfg->nranks < 1 || cfg->nranks > 8 || cfg->rank < 0 || cfg->rank >= cfg->nranks)) return RNDE_ERR_ARG;
     if (rnde_device_count() <= 0) return RNDE_ERR_CUDA;
     rnde_handle* h = new rnde_handle();
@@ -488,7 +496,7 @@ static int forward_impl(rnde_handle* h, const float* x_dev, const float* p_dev, 
         set_chain_offsets(h, P, make_layout(G, NP, WS, h->cfg.state_dim, h->cfg.hidden_dim, h->R, h->HS, h->kblock).total);
     }
     CUDA_TRY(h, cudaMemsetAsync(h->bar, 0, sizeof(unsigned) * 4, st));
-    int rc = launch(h, fwd_kernel_for(h->variant, h->cfg.state_dim, h->cfg.hidden_dim), P, h->smem_fwd, st);
+    int rc = launch(h, fwd_kernel_for(h->variant, h->cfg.state_dim, h->cfg.hidden_dim, h->cfg.arith), P, h->smem_fwd, st);
     if (rc != RNDE_OK) return rc;
     h->last_p = p_dev;
     h->have_tape = h->cfg.need_backward != 0;

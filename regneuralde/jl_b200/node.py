@@ -265,7 +265,8 @@ class TrackedNeuralODE:
     def __init__(self, model: TDChain, tspan: Sequence[float], time_dep: bool, regularize: bool, solver=Tsit5(), *,
                  reltol: float = 1.4e-8, abstol: float = 1.4e-8, save_everystep: bool = False, save_start: bool = False,
                  saveat=None, maxiters: int = 0, tape_capacity: int = 256, kernel_variant: int = L.KERNEL_AUTO,
-                 kblock: int = 0, device: str = "cuda", dist_mode: int = L.DIST_SINGLE, rank: int = 0, world: int = 1):
+                 kblock: int = 0, device: str = "cuda", dist_mode: int = L.DIST_SINGLE, rank: int = 0, world: int = 1,
+                 arith: int = L.ARITH_FMA_CHAIN):
         if save_everystep:
             raise NotImplementedError("save_everystep=true has no call site in the reference; use saveat")
         # return_multiple = haskey(kwargs, :saveat)  (neural_ode.jl:11): fixes which functor the object dispatches to
@@ -286,6 +287,8 @@ class TrackedNeuralODE:
         # data parallel: DIST_EXACT shares the step sequence of the global batched solve across ranks (x holds this
         # rank's columns, all shards equal); DIST_INDEPENDENT / DIST_SINGLE integrate the local columns on their own
         self.dist_mode, self.rank, self.world = dist_mode, rank, world
+        # canonical arithmetic of the layer products: ARITH_FMA_CHAIN (all variants) or ARITH_FIXED24 (exact integer tensor-core MMAs)
+        self.arith = arith
         self._handles: dict = {}
         self.last_stats: Optional[L.Stats] = None
 
@@ -317,6 +320,7 @@ class TrackedNeuralODE:
             cfg.t0, cfg.t1 = self.tspan
             cfg.abstol, cfg.reltol, cfg.dtmin = self.abstol, self.reltol, 0.0
             cfg.max_saveat = max_saveat
+            cfg.arith = self.arith
             cfg.global_batch = B * (self.world if self.dist_mode == L.DIST_EXACT else 1)
             hd = _Handle(cfg)
             if self.dist_mode == L.DIST_EXACT and self.world > 1:

@@ -381,6 +381,58 @@ def test_tensor_core_sweep_agrees_with_ffma_sweep(oracle_built, tmp_path):
     assert rel(a["dx"], b["dx"]) <= max(1e-4, 10 * rel(dx_32, dx_hi)) and rel(a["dp"], b["dp"]) <= max(1e-4, 10 * rel(dp_32, dp_hi))
 
 
+FIXED24_CASES = [
+    # name, D, H, B, act_out, auto, func
+    ("mnist B=17 ragged", 784, 100, 17, 1, False, "ERROR_ESTIMATE"),
+    ("mnist B=48 AutoTsit5 error_stiff_est", 784, 100, 48, 1, True, "ERROR_PLUS_STIFFNESS"),
+    ("mnist B=512 vanilla", 784, 100, 512, 1, False, None),
+    ("D=640 H=72 identity output", 640, 72, 40, 0, True, "STIFFNESS_ESTIMATE"),
+]
+
+
+@pytest.mark.parametrize("name,D,H,B,act_out,auto,func", FIXED24_CASES, ids=[c[0] for c in FIXED24_CASES])
+def test_fixed24_tensor_core_forward_bit_identical(oracle_built, name, D, H, B, act_out, auto, func):
+    """RNDE_ARITH_FIXED24: the layer products as exact integer tensor-core MMAs (csrc/fwd4x_kernel.cuh) against the oracle's
+    arith = 1 -- states, saved values, step sizes and NFE bit for bit; gradient (tensor-core sweep over the same tape) against
+    the oracle adjoint of the same arithmetic."""
+    r = R()
+    from regneuralde.jl_b200 import _lib as L
+    rng = np.random.default_rng(1999)
+    p_np = orc.glorot_params(rng, D, H)
+    x_np = rng.random((D, B), dtype=np.float32)
+    regularize = func is not None
+    model = r.TDChain(r.Dense(D + 1, H, "tanh"), r.Dense(H + 1, D, "tanh" if act_out else None))
+    node = r.TrackedNeuralODE(model, [0.0, 1.0], True, regularize, r.AutoTsit5() if auto else r.Tsit5(), reltol=1.4e-8, abstol=1.4e-8,
+                              arith=L.ARITH_FIXED24, tape_capacity=96)
+    fobj = getattr(r, func) if func else None
+    x = torch.from_numpy(x_np).cuda().requires_grad_(True); p = torch.from_numpy(p_np).cuda().requires_grad_(True)
+    res, nfe, sv = node(x, p, func=fobj)
+    cfg = oracle_cfg(D, H, B, act_out, 1 if auto else 0, fobj.kind if fobj else orc.REG_NONE)
+    cfg.arith = 1
+    o = orc.Oracle(cfg)
+    ref = o.forward(x_np, p_np)
+    st = node.last_stats
+    assert (nfe, st.naccept, st.nreject) == (ref.nf, ref.naccept, ref.nreject)
+    assert np.array_equal(bits(res.detach().cpu().numpy()), bits(ref.u)), "trajectory not bit-identical"
+    if regularize:
+        assert np.array_equal(bits(sv.saveval.detach().cpu().numpy()), bits(ref.saveval)), "saved values not bit-identical"
+    w = rng.standard_normal((D, B)).astype(np.float32)
+    ws = rng.standard_normal(max(len(ref.saveval), 1)).astype(np.float32)
+    loss = (res * torch.from_numpy(w).cuda()).sum()
+    if regularize:
+        loss = loss + (sv.saveval * torch.from_numpy(ws[: len(ref.saveval)]).cuda()).sum()
+    loss.backward()
+    dp_hi, dx_hi, _, _ = o.backward(w, ws, hi=True)
+    dp_32, dx_32, _, _ = o.backward(w, ws)
+    rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()
+    e_p, e_x = rel(p.grad.cpu().numpy(), dp_hi), rel(x.grad.cpu().numpy(), dx_hi)
+    # unit-size random cotangents on every saved value are far harsher than the training loss (lambda/n each); the sweep's products
+    # carry 16 mantissa bits (BF16 hi+lo), so on this ill-conditioned part it may sit at ~10x the CPU FP32 adjoint's own error
+    assert e_p <= max(1e-4, 20 * rel(dp_32, dp_hi)) and e_x <= max(1e-4, 20 * rel(dx_32, dx_hi)), (e_p, e_x)
+    if not regularize:
+        assert e_p <= 1e-4 and e_x <= 1e-4
+
+
 def test_solution_object(oracle_built):
     """solution(n, x, p; solver, tspan, saveat) (neural_ode.jl:182-210): same solve without the callback, solver override."""
     r = R()

@@ -150,3 +150,20 @@ def test_chain_field_matches_autograd_fp64(oracle_built, reg, alg):
     assert np.abs(dp - gp.numpy()).max() <= 1e-7 * np.abs(gp.numpy()).max()
     assert np.abs(dx - gx.numpy()).max() <= 1e-7 * np.abs(gx.numpy()).max()
     torch.set_default_dtype(torch.float32)
+
+
+def test_fixed24_arithmetic_is_a_rounding_of_the_same_field(oracle_built):
+    """arith = 1 (exact truncated fixed-point layer products, the tensor-core forward stepper's arithmetic): one field
+    evaluation agrees with the FMA-chain arithmetic and with Float64 to Float32 round-off, and the solve takes a comparable
+    number of steps (the embedded error estimate is rounding noise at tol 1.4e-8: a noisier arithmetic would take more)."""
+    rng = np.random.default_rng(5)
+    D, H, B = 784, 100, 6
+    p = orc.glorot_params(rng, D, H); x = rng.random((D, B), dtype=np.float32)
+    k0, _ = orc.Oracle(orc.OracleConfig(D=D, H=H, B=B, kblock1=98)).rhs(p, x, 0.3)
+    k1, _ = orc.Oracle(orc.OracleConfig(D=D, H=H, B=B, kblock1=98, arith=1)).rhs(p, x, 0.3)
+    k64, _ = orc.Oracle(orc.OracleConfig(D=D, H=H, B=B, kblock1=98), f64=True).rhs(p.astype(np.float64), x.astype(np.float64), 0.3)
+    assert np.abs(k1 - k64).max() <= 4e-7 and np.abs(k0 - k64).max() <= 4e-7
+    r0 = orc.Oracle(orc.OracleConfig(D=D, H=H, B=B, reg_kind=orc.REG_ERR_DT, kblock1=98)).forward(x, p)
+    r1 = orc.Oracle(orc.OracleConfig(D=D, H=H, B=B, reg_kind=orc.REG_ERR_DT, kblock1=98, arith=1)).forward(x, p)
+    assert np.abs(r1.u - r0.u).max() <= 2e-6 * np.abs(r0.u).max()
+    assert abs(r1.nf - r0.nf) <= 0.1 * r0.nf
