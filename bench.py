@@ -248,7 +248,7 @@ def run_ours(args):
         if exact:      # global loss: CE mean over world*B samples, one shared regulariser; gradients are summed
             out = clf.loss_and_gradient(x, y, lam=LAMBDA, func=R.ERROR_ESTIMATE, agg="mean", ce_scale=1.0 / world)
             g2, g3 = out["g2"], out["g3"]
-            dist.all_reduce(g2); dist.all_reduce(g3)
+            node.allreduce_(g2, g3)        # one-shot push all-reduce over NVLink peer memory (rnde_allreduce_grads), no NCCL call
         else:
             out = clf.loss_and_gradient(x, y, lam=LAMBDA, func=R.ERROR_ESTIMATE, agg="mean")
             g2, g3 = out["g2"], out["g3"]

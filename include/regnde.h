@@ -206,6 +206,12 @@ int rnde_backward_host(rnde_handle* h, const float* du_host, const float* dsavev
 int rnde_head_loss_grad(rnde_handle* h, const float* u_dev, const float* p3_dev, const float* y_onehot_dev, int32_t n_classes,
                         float loss_scale, float* loss_dev, float* logits_dev, float* du_dev, float* dp3_dev, void* stream);
 
+/* Sum of `buf_dev` (n floats, n <= num_params + 16384) over all ranks of a RNDE_DIST_EXACT group, in place, by a one-shot
+ * push all-reduce over the CUDA-IPC mapped peer buffers (NVLink; no NCCL call): ranks are added in rank order on every
+ * rank, so the result is bitwise identical everywhere.  Collective: every rank must call it the same number of times.
+ * (SURVEY.md 8b rnde_allreduce_grads; with RNDE_DIST_SINGLE / INDEPENDENT handles use the host layer's NCCL all-reduce.) */
+int rnde_allreduce_grads(rnde_handle* h, float* buf_dev, int64_t n, void* stream);
+
 /* Statistics of the last rnde_forward on `h` (waits for that forward only, not for work queued behind it). */
 int rnde_last_stats(rnde_handle* h, rnde_stats* out);
 

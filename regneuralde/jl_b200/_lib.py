@@ -40,7 +40,7 @@ EXPORTS = [
     "rnde_opt_update", "rnde_test_tanh", "rnde_test_tanh_bits", "rnde_test_pow", "rnde_debug_timeline", "rnde_dist_export", "rnde_dist_import",
     "rnde_set_saveat", "rnde_forward_saveat", "rnde_backward_saveat",
     "rnde_gru_num_params", "rnde_gru_create", "rnde_gru_destroy", "rnde_gru_last_error", "rnde_gru_forward", "rnde_gru_backward",
-    "rnde_gru_launch_count", "rnde_reg_agg", "rnde_last_stats",
+    "rnde_gru_launch_count", "rnde_reg_agg", "rnde_last_stats", "rnde_allreduce_grads",
 ]
 
 
@@ -147,6 +147,7 @@ def lib() -> C.CDLL:
     L.rnde_dist_import.argtypes = [vp, vp, C.c_int32]
     L.rnde_set_saveat.argtypes = [vp, vp, C.c_int32]
     L.rnde_last_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.rnde_allreduce_grads.argtypes = [vp, vp, C.c_int64, vp]
     L.rnde_reg_agg.argtypes = [vp, C.c_int32, C.c_float, C.c_float, vp, vp, vp, vp]
     L.rnde_gru_num_params.restype = C.c_int64
     L.rnde_gru_num_params.argtypes = [C.POINTER(GruConfig)]

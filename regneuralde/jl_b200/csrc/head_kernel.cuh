@@ -127,6 +127,54 @@ __global__ void reg_agg_kernel(const DevStats* __restrict__ stats, const int agg
     if (tid == 0) reg_out[0] = (n == 0) ? 0.f : (agg == 0 ? lam * (acc / (float)n) : lam * acc);
 }
 
+// ---- gradient all-reduce over NVLink peer memory (reference-exact data-parallel mode) -----------------------------------
+// One-shot push all-reduce on the CUDA-IPC mapped exchange buffers (no NCCL call): every rank writes its vector into slot
+// [parity][rank] of EVERY rank's buffer, publishes "call seq done" flags with st.release.sys, then each rank adds the slots
+// it received in rank order -- the same order on all ranks, so the result is bitwise identical everywhere.  Slots are
+// double buffered by call parity: a rank can only reach call k+2 after every rank finished pushing call k+1, i.e. after
+// every rank finished reading call k.  Waiting is bounded (~seconds); a missing peer traps instead of hanging the GPU.
+struct ArParams {
+    unsigned long long peers[8];      // base of every rank's exchange buffer
+    unsigned long long goff;          // byte offset of the gradient area inside a buffer: [flags 32 u32][done 32 u32][2][nranks][gcap] floats
+    int nranks, rank; unsigned seq; long long n, gcap;
+};
+__global__ void ar_push_kernel(const ArParams A, const float* __restrict__ src) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+    const size_t slot = ((size_t)(A.seq & 1u) * A.nranks + A.rank) * (size_t)A.gcap;
+    for (int r = 0; r < A.nranks; ++r) {
+        float* dst = reinterpret_cast<float*>(A.peers[r] + A.goff) + 64 + slot;
+        for (long long i = tid; i < A.n; i += nth) dst[i] = src[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned* done = reinterpret_cast<unsigned*>(A.peers[A.rank] + A.goff) + 32;
+        const unsigned prev = atomicAdd(done, 1u);
+        if (prev == gridDim.x - 1) {           // last block: everything this rank pushed is visible before the flags
+            *done = 0u;
+            __threadfence_system();
+            for (int r = 0; r < A.nranks; ++r) st_release_sys(reinterpret_cast<unsigned*>(A.peers[r] + A.goff) + A.rank, A.seq);
+        }
+    }
+}
+__global__ void ar_sum_kernel(const ArParams A, float* __restrict__ dst) {
+    if (threadIdx.x == 0) {
+        const unsigned* mine = reinterpret_cast<const unsigned*>(A.peers[A.rank] + A.goff);
+        for (int r = 0; r < A.nranks; ++r) {
+            long long spins = 0;
+            while ((int)(ld_acquire_sys(mine + r) - A.seq) < 0) { if (++spins > (1ll << 31)) __trap(); }
+        }
+    }
+    __syncthreads();
+    const float* base = reinterpret_cast<const float*>(A.peers[A.rank] + A.goff) + 64 + (size_t)(A.seq & 1u) * A.nranks * (size_t)A.gcap;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+    for (long long i = tid; i < A.n; i += nth) {
+        float s = __ldcg(base + i);
+        for (int r = 1; r < A.nranks; ++r) s += __ldcg(base + (size_t)r * A.gcap + i);
+        dst[i] = s;
+    }
+}
+
 __global__ void opt_update_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ v, long long n, float scale,
                                   float eta, float rho) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -49,6 +49,7 @@ struct rnde_handle {
     // host-path staging
     float *hx = nullptr, *hp = nullptr, *hu = nullptr, *hsv = nullptr, *hdu = nullptr, *hdsv = nullptr, *hdp = nullptr, *hdx = nullptr;
     DevStats* stats_pinned = nullptr;
+    size_t goff_bytes = 0; long long gcap = 0; unsigned ar_seq = 0;     // gradient all-reduce area of the exchange buffer (EXACT mode)
     cudaEvent_t ev_stats = nullptr;      // recorded after the forward's stats copy: the backward waits on it, not on the stream
     const float* last_p = nullptr;
     rnde_stats last_stats{};
@@ -354,7 +355,13 @@ extern "C" int rnde_create(const rnde_config* cfg, rnde_handle** out) {
     const int D = c.state_dim, H = c.hidden_dim;
     h->colsum_stride = round_up((int)c.global_batch, 32);
     auto fail = [&](const char* what) { h->err = what; free_all(h); delete h; return RNDE_ERR_CUDA; };
-    const size_t xwords = (size_t)2 * 3 * h->colsum_stride + 128;
+    size_t xwords = (size_t)2 * 3 * h->colsum_stride + 128;
+    if (h->cfg.dist_mode == RNDE_DIST_EXACT && h->cfg.nranks > 1) {      // + gradient all-reduce area: flags, done counter, 2 x nranks slots
+        xwords = (xwords + 3) / 4 * 4;
+        h->goff_bytes = xwords * sizeof(float);
+        h->gcap = ((long long)h->np + 16384 + 3) / 4 * 4;
+        xwords += 64 + (size_t)2 * h->cfg.nranks * (size_t)h->gcap;
+    }
     if (cudaMalloc(&h->colsum, sizeof(float) * xwords) != cudaSuccess) return fail("cudaMalloc colsum");
     if (cudaMemset(h->colsum, 0, sizeof(float) * xwords) != cudaSuccess) return fail("cudaMemset colsum");
     h->peers[h->cfg.rank] = (unsigned long long)h->colsum;
@@ -654,6 +661,23 @@ extern "C" int rnde_backward_host(rnde_handle* h, const float* du_host, const fl
     if (rc != RNDE_OK) return rc;
     CUDA_TRY(h, cudaMemcpy(dp_host, h->hdp, sizeof(float) * h->np, cudaMemcpyDeviceToHost));
     if (dx_host) CUDA_TRY(h, cudaMemcpy(dx_host, h->hdx, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    return RNDE_OK;
+}
+
+extern "C" int rnde_allreduce_grads(rnde_handle* h, float* buf_dev, int64_t n, void* stream) {
+    if (!h || !buf_dev || n <= 0) return RNDE_ERR_ARG;
+    if (h->cfg.nranks <= 1) return RNDE_OK;
+    if (h->cfg.dist_mode != RNDE_DIST_EXACT || !h->dist_ready || h->gcap == 0)
+        return set_err(h, RNDE_ERR_STATE, "rnde_allreduce_grads needs a RNDE_DIST_EXACT handle after rnde_dist_import");
+    if (n > h->gcap) return set_err(h, RNDE_ERR_ARG, "rnde_allreduce_grads: n exceeds num_params + 16384");
+    ArParams A; memset(&A, 0, sizeof(A));
+    for (int i = 0; i < 8; ++i) A.peers[i] = h->peers[i];
+    A.goff = h->goff_bytes; A.nranks = h->cfg.nranks; A.rank = h->cfg.rank; A.seq = ++h->ar_seq; A.n = n; A.gcap = h->gcap;
+    const int blocks = (int)std::min<long long>(64, (n + 1023) / 1024);
+    ar_push_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(A, buf_dev);
+    ar_sum_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(A, buf_dev);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 2;
     return RNDE_OK;
 }
 

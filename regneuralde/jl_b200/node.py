@@ -387,6 +387,17 @@ class TrackedNeuralODE:
         hd.check(hd.lib.rnde_get_steps(hd.h, *arrs, n), "rnde_get_steps")
         return [list(a)[:n] for a in arrs]
 
+    def allreduce_(self, *tensors: torch.Tensor) -> None:
+        """Sum flat Float32 tensors over the ranks of a reference-exact group, in place, through the library's one-shot
+        all-reduce over NVLink peer memory (rnde_allreduce_grads; no NCCL call; bitwise identical result on every rank)."""
+        if self.dist_mode != L.DIST_EXACT or self.world <= 1:
+            raise RuntimeError("allreduce_ needs dist_mode=DIST_EXACT with world > 1")
+        hd = next(iter(self._handles.values()))
+        for t in tensors:
+            if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
+                raise ValueError("contiguous CUDA Float32 tensors only")
+            hd.check(hd.lib.rnde_allreduce_grads(hd.h, t.data_ptr(), t.numel(), _stream_ptr()), "rnde_allreduce_grads")
+
     def launch_count(self) -> int:
         return sum(int(h.lib.rnde_launch_count(h.h)) for h in self._handles.values())
 

@@ -555,7 +555,15 @@ def _exact_worker(rank, world, port, q):
     with torch.no_grad():
         resc, nfec, svc = nodec(torch.from_numpy(np.ascontiguousarray(xc[:, rank * Blc:(rank + 1) * Blc])).cuda(), torch.from_numpy(pc).cuda(),
                                 func=r.ERROR_PLUS_STIFFNESS)
-    q.put((rank, res.cpu().numpy(), sv.saveval.cpu().numpy(), nfe, resc.cpu().numpy(), svc.saveval.cpu().numpy(), nfec))
+    # the library's peer-memory all-reduce against NCCL's, twice (slots are double buffered by call parity), odd length
+    ar_ok = True
+    for rep in range(3):
+        g = torch.from_numpy(np.random.default_rng(100 * rep + rank).standard_normal(158568 + 7 * rep).astype(np.float32)).cuda()
+        ref_g = g.clone(); dist.all_reduce(ref_g)
+        node.allreduce_(g)
+        torch.cuda.synchronize()
+        ar_ok = ar_ok and bool(torch.equal(g, ref_g))
+    q.put((rank, res.cpu().numpy(), sv.saveval.cpu().numpy(), nfe, resc.cpu().numpy(), svc.saveval.cpu().numpy(), nfec, ar_ok))
     dist.destroy_process_group()
 
 
@@ -592,3 +600,4 @@ def test_exact_data_parallel_matches_single_solve(oracle_built):
     assert outs[0][6] == refc.nf and outs[1][6] == refc.nf
     assert np.array_equal(bits(usave), bits(refc.usave)), "chain field + saveat in exact mode not bit-identical"
     assert np.array_equal(bits(outs[0][5]), bits(refc.saveval))
+    assert outs[0][7] and outs[1][7], "rnde_allreduce_grads differs from the NCCL all-reduce"
