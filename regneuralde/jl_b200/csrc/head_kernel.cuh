@@ -162,7 +162,8 @@ __global__ void ar_sum_kernel(const ArParams A, float* __restrict__ dst) {
         const unsigned* mine = reinterpret_cast<const unsigned*>(A.peers[A.rank] + A.goff);
         for (int r = 0; r < A.nranks; ++r) {
             long long spins = 0;
-            while ((int)(ld_acquire_sys(mine + r) - A.seq) < 0) { if (++spins > (1ll << 24)) __trap();      // ~10 s: a peer that never arrives is an error, not a hang }
+            // bounded (~10 s): a peer that never arrives is an error, not a hang
+            while ((int)(ld_acquire_sys(mine + r) - A.seq) < 0) { if (++spins > (1ll << 24)) __trap(); }
         }
     }
     __syncthreads();
