@@ -30,7 +30,7 @@ constexpr int V2_NT = 256;
 
 struct V2Layout {
     int KB, KBP, R, RPAD, HP, HS, NGC, NGH;
-    int oW1, oW1t, ob1, oW2, oW2t, ob2, oZ, oP1, oPart, oH, oRed, oCP, oTot, oCtl, oBar, total;
+    int oW1, oW1t, ob1, oW2, oW2t, ob2, oZ, oP1, oPart, oH, oRed, oCP, oTot, oCtl, oBar, oKt, total;
 };
 
 __host__ __device__ inline V2Layout make_v2_layout(int D, int H) {
@@ -59,6 +59,7 @@ __host__ __device__ inline V2Layout make_v2_layout(int D, int H) {
     L.oTot = o; o += 4;
     L.oCtl = o; o += 32;
     L.oBar = o; o += 8;                    // two 8-byte mbarriers (+pad), 16B aligned
+    L.oKt = o; o += L.R * V2_NP;           // layer-2 output staged for the bulk store to the tape
     L.total = o;
     return L;
 }
@@ -92,6 +93,14 @@ __device__ __forceinline__ void st_async_f4(uint32_t remote_addr, float4 v, uint
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(remote_addr), "f"(v.x),
                  "f"(v.y), "f"(v.z), "f"(v.w), "r"(remote_bar) : "memory");
 }
+
+// ---- bulk (TMA engine) stores shared -> global: the tape tiles leave the SM without occupying the threads' store path ----
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // z_I = uprev + dt * sum_j a_Ij k_j with the canonical association, specialised per stage so the
 // 16 elements of the thread's tile are straight-line independent FMA chains.
@@ -136,6 +145,7 @@ __global__ void __launch_bounds__(V2_NT, 1) fwd4_kernel(const KParams P) {
     float* sW2 = smem + L.oW2; float* sW2t = smem + L.oW2t; float* sb2 = smem + L.ob2;
     float* sZ = smem + L.oZ; float* sP1 = smem + L.oP1; float* sPart = smem + L.oPart; float* sH = smem + L.oH;
     float* sRed = smem + L.oRed; float* sCP = smem + L.oCP; float* sTot = smem + L.oTot;
+    float* sKt = smem + L.oKt;
     Ctl* ctl = reinterpret_cast<Ctl*>(smem + L.oCtl);
     const uint32_t barP = smem_u32(smem + L.oBar), barH = barP + 8;
 
@@ -224,6 +234,7 @@ __global__ void __launch_bounds__(V2_NT, 1) fwd4_kernel(const KParams P) {
     const uint32_t bytesP = (uint32_t)((G - 1) * HSloc * NP * 4);
     const uint32_t bytesH = (uint32_t)((H - HSloc) * NP * 4);
 
+    int pend_rec = -1;      // record whose layer-2 output sits in sKt, not yet handed to the bulk-store engine
     // ---- one field evaluation: out = f(zin, tstage); zin (registers) is also staged to sZ ---------
     auto rhs = [&](const float (&zin)[16], float (&out)[16], const float tstage, const int rec) {
         mark(0);
@@ -233,7 +244,14 @@ __global__ void __launch_bounds__(V2_NT, 1) fwd4_kernel(const KParams P) {
             for (int i = 0; i < 4; ++i)
                 if (i < cvalid) *reinterpret_cast<float4*>(sZ + (crow0 + i) * NP + cn0) = make_float4(zin[i * 4], zin[i * 4 + 1], zin[i * 4 + 2], zin[i * 4 + 3]);
         }
+        if (rec >= 0 || pend_rec >= 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
+        if (tid == 0) {     // tape: this evaluation's input tile (sZ) and the previous evaluation's output tile (sKt) as bulk stores
+            if (rec >= 0) bulk_store(P.tapeZ + (((size_t)rec * P.Q + q) * D + r0) * NP, sZ, (uint32_t)(R * NP * 4));
+            if (pend_rec >= 0) bulk_store(P.tapeK + (((size_t)pend_rec * P.Q + q) * D + r0) * NP, sKt, (uint32_t)(R * NP * 4));
+            if (rec >= 0 || pend_rec >= 0) bulk_commit();
+        }
+        pend_rec = -1;
         mark(1);
         // phase A: one canonical K-block (KB rows) per thread tile, software pipelined operand loads
         float acc[16];
@@ -282,6 +300,7 @@ __global__ void __launch_bounds__(V2_NT, 1) fwd4_kernel(const KParams P) {
             }
         }
         mark(4);
+        if (tid == 0) bulk_wait_read();      // sZ, sKt and the hidden slice of the previous evaluation may be overwritten from here on
         __syncthreads();
         mark(5);
         mbar_wait(barP, ev_parity);
@@ -313,10 +332,14 @@ __global__ void __launch_bounds__(V2_NT, 1) fwd4_kernel(const KParams P) {
                 const int peer = (rank + d) & (G - 1);
                 st_async_f4(mapa_u32(da, peer), h4, mapa_u32(barH, peer));
             }
-            if (rec >= 0) *reinterpret_cast<float4*>(P.tapeH + ((size_t)rec * P.Q + q) * H * NP + (size_t)m * NP + n4) = h4;
         }
+        if (rec >= 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mark(7);
         __syncthreads();
+        if (rec >= 0 && tid == 0 && HSloc > 0) {      // this CTA's hidden slice of the tape
+            bulk_store(P.tapeH + (((size_t)rec * P.Q + q) * H + rank * HS) * NP, sH + rank * HS * NP, (uint32_t)(HSloc * NP * 4));
+            bulk_commit();
+        }
         mark(8);
         mbar_wait(barH, ev_parity);
         mark(9);
@@ -350,17 +373,24 @@ __global__ void __launch_bounds__(V2_NT, 1) fwd4_kernel(const KParams P) {
                     v = v + bb;
                     out[i * 4 + j] = act_apply(P.act2, v);
                 }
-                if (rec >= 0 && i < cvalid) {
-                    const size_t off = ((size_t)rec * P.Q + q) * D * NP + (size_t)(r0 + crow0 + i) * NP + cn0;
-                    *reinterpret_cast<float4*>(P.tapeK + off) = make_float4(out[i * 4], out[i * 4 + 1], out[i * 4 + 2], out[i * 4 + 3]);
-                    *reinterpret_cast<float4*>(P.tapeZ + off) = make_float4(zin[i * 4], zin[i * 4 + 1], zin[i * 4 + 2], zin[i * 4 + 3]);
-                }
+                if (rec >= 0 && i < cvalid)
+                    *reinterpret_cast<float4*>(sKt + (crow0 + i) * NP + cn0) = make_float4(out[i * 4], out[i * 4 + 1], out[i * 4 + 2], out[i * 4 + 3]);
             }
         } else {
 #pragma unroll
             for (int e = 0; e < 16; ++e) out[e] = 0.f;
         }
+        pend_rec = rec;      // its output tile is stored to the tape at the next block-wide barrier (next evaluation or flush_tape)
         mark(10);
+    };
+    // the last staged output tile must reach the tape before anything reuses sKt / before the kernel ends
+    auto flush_tape = [&]() {
+        if (pend_rec >= 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (tid == 0) { bulk_store(P.tapeK + (((size_t)pend_rec * P.Q + q) * D + r0) * NP, sKt, (uint32_t)(R * NP * 4)); bulk_commit(); }
+            pend_rec = -1;
+        }
     };
 
     // ---- canonical norms from register tiles: val(e, out[NV]) for the thread's 16 elements ---------
@@ -648,6 +678,10 @@ __global__ void __launch_bounds__(V2_NT, 1) fwd4_kernel(const KParams P) {
         mark(16);
         const int accepted = ctl->accept, finished = ctl->done;
         if (tid == 0 && accepted) ctl->qold_pow = ctl->qold_pow_next;     // qold was updated: its power follows
+        if (!accepted) {      // the retried attempt rewrites the same tape records: the pending tile first, then let every bulk store land
+            flush_tape();
+            if (tid == 0) bulk_wait_all();
+        }
         __syncthreads();
         if (accepted) {   // apply_step!: u <- u_new, fsalfirst <- fsallast
 #pragma unroll
@@ -662,6 +696,8 @@ __global__ void __launch_bounds__(V2_NT, 1) fwd4_kernel(const KParams P) {
     }
 
     // ---- write back ------------------------------------------------------------------------------
+    flush_tape();
+    if (tid == 0) bulk_wait_all();
     if (own) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
