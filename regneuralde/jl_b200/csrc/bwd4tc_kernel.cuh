@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
                         d2.x = d2.x * (1.f - kv.x * kv.x); d2.y = d2.y * (1.f - kv.y * kv.y);
                         d2.z = d2.z * (1.f - kv.z * kv.z); d2.w = d2.w * (1.f - kv.w * kv.w);
                     }
-                    *reinterpret_cast<float4*>(tp) = d2;
+                    *reinterpret_cast<float4*>(sZb + (crow0 + i) * NP + cn0) = d2;      // delta2 replaces k on the tape: bulk store below
                 } else d2 = make_float4(0.f, 0.f, 0.f, 0.f);
                 d2v[i][0] = d2.x; d2v[i][1] = d2.y; d2v[i][2] = d2.z; d2v[i][3] = d2.w;
             }
@@ -264,6 +264,10 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #endif
         __syncthreads();
+        if (tid == 0) {     // the delta2 tile of this CTA's rows -> tape (wgrad operand), by the bulk-store engine
+            bulk_store(P.tapeK + (((size_t)rec * P.Q + q) * D + r0) * NP, sZb, (uint32_t)(R * NP * 4));
+            bulk_commit();
+        }
         TLB(1);
         if (issuer >= 0) {     // GEMM 1 (a K quarter per issuer; descriptors advance by 2 core matrices = 256 bytes per k-step)
             tc_fence_after();
@@ -329,9 +333,13 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
                 const int peer = (rank + d) & (G - 1);
                 st_async_f4(mapa_u32(da, peer), s, mapa_u32(barH, peer));
             }
-            *reinterpret_cast<float4*>(P.tapeD1 + oh) = s;
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
+        if (tid == 0 && HSloc > 0) {      // this CTA's slice of delta1 -> tape
+            bulk_store(P.tapeD1 + (((size_t)rec * P.Q + q) * H + rank * HS) * NP, sD1 + rank * HS * NP, (uint32_t)(HSloc * NP * 4));
+            bulk_commit();
+        }
         mbar_wait(barH, ev_parity);
         TLB(5);
         // delta1 (H x 16, FP32) -> split B operand of GEMM 2: one 16-byte chunk = 8 consecutive hidden units of one column
@@ -348,6 +356,7 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
             *reinterpret_cast<uint4*>(sb + L.oB2lo + off) = *reinterpret_cast<const uint4*>(l8);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (tid == 0) bulk_wait_read();      // sZb (delta2 tile) is reused by the transposition below, sD1 by the next evaluation
         __syncthreads();
         TLB(6);
         if (issuer >= 0) {     // GEMM 2: M tile issuer >> 1, half of the k-steps each
@@ -595,6 +604,7 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
 #ifdef RNDE_TIMELINE
     if (P.dbg && blockIdx.x == 0 && tid == 0) for (int k = 0; k < 14; ++k) P.dbg[k] = tl_acc[k];
 #endif
+    if (tid == 0) bulk_wait_all();
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
