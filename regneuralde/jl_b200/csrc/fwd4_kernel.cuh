@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(V2_NT, 1) fwd4_kernel(const KParams P) {
             float4 w = *reinterpret_cast<const float4*>(wp), x = *reinterpret_cast<const float4*>(xp);
             // operands of iteration k+1 are fetched before the 16 FMAs of iteration k (the last
             // iteration re-fetches row KB-1, harmlessly); 98 = 14 x 7 for the MNIST instantiation
-#pragma unroll (KBC > 0 ? 7 : 4)
+#pragma unroll (KBC > 0 ? 14 : 4)
             for (int k = 0; k < KB; ++k) {
                 const int kn = (k + 1 < KB) ? k + 1 : k;
                 const float4 wn = *reinterpret_cast<const float4*>(wp + kn * HP);
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(V2_NT, 1) fwd4_kernel(const KParams P) {
             const float* wp = sW2 + cprow0;
             const float* xp = sH + cn0;
             float4 w = *reinterpret_cast<const float4*>(wp), x = *reinterpret_cast<const float4*>(xp);
-#pragma unroll (HC > 0 ? 5 : 4)
+#pragma unroll (HC > 0 ? 10 : 4)
             for (int k = 0; k < H; ++k) {
                 const int kn = (k + 1 < H) ? k + 1 : k;
                 const float4 wn = *reinterpret_cast<const float4*>(wp + kn * RPAD);

@@ -52,28 +52,55 @@ __global__ void __launch_bounds__(256) head_col_kernel(int D, int B, int C, cons
 }
 
 // dW3[c][d] = sum_j g[c][j] u[d][j]; db3[c] = sum_j g[c][j]; loss = scale * mean_j loss_j
-__global__ void __launch_bounds__(256) head_wgrad_kernel(int D, int B, int C, const float* __restrict__ u, const float* __restrict__ g_ws,
-                                                        const float* __restrict__ loss_ws, float scale, float* __restrict__ dp3,
-                                                        float* __restrict__ loss_out) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int total = C * D + C;
-    if (idx < C * D) {
-        const int d = idx / C, c = idx - d * C;
-        float s = 0.f;
-        for (int j = 0; j < B; ++j) s = fmaf(__ldg(g_ws + (size_t)C * j + c), __ldg(u + (size_t)D * j + d), s);
-        dp3[idx] = s;
-    } else if (idx < total) {
-        const int c = idx - C * D;
-        float s = 0.f;
-        for (int j = 0; j < B; ++j) s += __ldg(g_ws + (size_t)C * j + c);
-        dp3[idx] = s;
-    }
-    if (blockIdx.x == 0 && threadIdx.x < 32) {
-        float s = 0.f;
-        for (int j = threadIdx.x; j < B; j += 32) s += loss_ws[j];
+// A block owns 32 consecutive state rows d (one coalesced 128-byte segment of u per batch column) and splits the batch
+// over its 8 warps; lane = row, every lane keeps C accumulators; g is read as warp-uniform broadcasts.  The 8 partial sums
+// are combined in a fixed order (deterministic).  The last block also reduces db3 and the loss.
+constexpr int HW_ROWS = 32, HW_SLICES = 8, HW_MAXC = 32;
+__global__ void __launch_bounds__(HW_ROWS * HW_SLICES) head_wgrad_kernel(int D, int B, int C, const float* __restrict__ u, const float* __restrict__ g_ws,
+                                                                    const float* __restrict__ loss_ws, float scale, float* __restrict__ dp3,
+                                                                    float* __restrict__ loss_out) {
+    __shared__ float part[HW_SLICES][HW_MAXC][HW_ROWS + 1];
+    const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int nrb = (D + HW_ROWS - 1) / HW_ROWS;
+    if ((int)blockIdx.x < nrb) {
+        const int d = blockIdx.x * HW_ROWS + lane;
+        float acc[HW_MAXC];
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-        if (threadIdx.x == 0) loss_out[0] = scale * s / (float)B;
+        for (int c = 0; c < HW_MAXC; ++c) acc[c] = 0.f;
+        const int per = (B + HW_SLICES - 1) / HW_SLICES;
+        const int j0 = sl * per, j1 = min(B, j0 + per);
+        for (int j = j0; j < j1; ++j) {
+            const float uv = d < D ? __ldg(u + (size_t)D * j + d) : 0.f;
+            const float* gj = g_ws + (size_t)C * j;
+#pragma unroll
+            for (int c = 0; c < HW_MAXC; ++c) if (c < C) acc[c] = fmaf(__ldg(gj + c), uv, acc[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < HW_MAXC; ++c) if (c < C) part[sl][c][lane] = acc[c];
+        __syncthreads();
+        for (int e = threadIdx.x; e < C * HW_ROWS; e += blockDim.x) {
+            const int c = e / HW_ROWS, l = e - c * HW_ROWS;
+            float s = part[0][c][l];
+#pragma unroll
+            for (int k = 1; k < HW_SLICES; ++k) s += part[k][c][l];
+            const int dd = blockIdx.x * HW_ROWS + l;
+            if (dd < D) dp3[(size_t)C * dd + c] = s;
+        }
+    } else {        // the extra block: bias gradient and the loss
+        for (int c = sl; c < C; c += HW_SLICES) {
+            float s = 0.f;
+            for (int j = lane; j < B; j += 32) s += __ldg(g_ws + (size_t)C * j + c);
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            if (lane == 0) dp3[(size_t)C * D + c] = s;
+        }
+        if (sl == 0) {
+            float s = 0.f;
+            for (int j = lane; j < B; j += 32) s += loss_ws[j];
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            if (lane == 0) loss_out[0] = scale * s / (float)B;
+        }
     }
 }
 
@@ -83,8 +110,7 @@ static int launch_head(int D, int B, int C, const float* u, const float* p3, con
     float* loss_ws = ws + (size_t)C * B;
     const int warps_per_block = 8;
     head_col_kernel<<<(B + warps_per_block - 1) / warps_per_block, 256, 0, st>>>(D, B, C, u, p3, y, scale, logits, du, g_ws, loss_ws);
-    const int total = C * D + C;
-    head_wgrad_kernel<<<(total + 255) / 256, 256, 0, st>>>(D, B, C, u, g_ws, loss_ws, scale, dp3, loss);
+    head_wgrad_kernel<<<(D + HW_ROWS - 1) / HW_ROWS + 1, HW_ROWS * HW_SLICES, 0, st>>>(D, B, C, u, g_ws, loss_ws, scale, dp3, loss);
     if (launches) *launches += 2;
     return (int)cudaGetLastError();
 }
