@@ -198,10 +198,7 @@ __global__ void __launch_bounds__(WGT_THREADS, 1) wgrad_tc_kernel(const float* _
         const int m = m_base + row;
         for (int chunk = 0; chunk < WGT_MAXCHUNK; ++chunk) {
             float* prow = partial + ((size_t)blockIdx.z * WGT_MAXCHUNK + chunk) * Naug * M;     // [n][m], m fastest
-            if (chunk >= nchunk) {      // unused slots are zeroed so the reduce needs no bookkeeping
-                if (m < M) for (int n = n_base; n < min(n_base + WGT_N, Naug); ++n) prow[(size_t)n * M + m] = 0.f;
-                continue;
-            }
+            if (chunk >= nchunk) break;      // unused slots are neither written nor read (the reduce recomputes every split's chunk count)
             const int acc = chunk & 1;
             mbar_wait(bar_accfull(acc), (uint32_t)((chunk / 2) & 1));
             tc_fence_after();
@@ -236,14 +233,20 @@ __global__ void __launch_bounds__(WGT_THREADS, 1) wgrad_tc_kernel(const float* _
 }
 
 // fixed-order FP64 sum over splits of the [split][n][m] partials; scatter into Flux.destructure layout
-__global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, int nslots, int M, int Nrows, int td, float* __restrict__ outW,
-                                       float* __restrict__ outb) {
+__global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, int nsplit, int ntiles, int flush, int M, int Nrows, int td,
+                                       float* __restrict__ outW, float* __restrict__ outb) {
     const int Naug = Nrows + 2;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= M * Naug) return;
     const int n = idx / M, m = idx - n * M;
+    const int per = (ntiles + nsplit - 1) / nsplit;
     double s = 0.0;
-    for (int sp = 0; sp < nslots; ++sp) s += (double)partial[((size_t)sp * Naug + n) * M + m];
+    for (int sp = 0; sp < nsplit; ++sp) {       // the chunks each split really produced (same arithmetic as wgrad_tc_kernel), in order
+        const int tile0 = sp * per, tile1 = min(ntiles, tile0 + per);
+        const int nstage = (max(tile1 - tile0, 0) + 1) / 2;
+        const int nchunk = (nstage + flush - 1) / flush;
+        for (int ch = 0; ch < nchunk; ++ch) s += (double)partial[(((size_t)sp * WGT_MAXCHUNK + ch) * Naug + n) * M + m];
+    }
     if (n < Nrows) outW[(size_t)M * n + m] = (float)s;
     else if (n == Nrows) { if (td) outW[(size_t)M * Nrows + m] = (float)s; }
     else outb[m] = (float)s;
@@ -260,7 +263,6 @@ static int launch_wgrad_tc(int D, int H, int td, int nrec, int Q, const float* t
     int flush = (nstage + WGT_MAXCHUNK - 1) / WGT_MAXCHUNK;
     if (flush < WGT_FLUSH_MIN) flush = WGT_FLUSH_MIN;
     float* wsd = ws;
-    const int nslots = nsplit * WGT_MAXCHUNK;
     float* dW1 = dp;
     float* db1 = dW1 + (size_t)H * (D + td);
     float* dW2 = db1 + H;
@@ -269,13 +271,13 @@ static int launch_wgrad_tc(int D, int H, int td, int nrec, int Q, const float* t
         dim3 grid((H + WGT_M - 1) / WGT_M, (D + 2 + WGT_N - 1) / WGT_N, nsplit);
         wgrad_tc_kernel<<<grid, WGT_THREADS, WGT_SMEM, st>>>(tapeD1, H, tapeZ, D, ntiles, Q, steps, t0, td, flush, wsd);
         const int tot = H * (D + 2);
-        wgrad_tc_reduce_kernel<<<(tot + 255) / 256, 256, 0, st>>>(wsd, nslots, H, D, td, dW1, db1);
+        wgrad_tc_reduce_kernel<<<(tot + 255) / 256, 256, 0, st>>>(wsd, nsplit, ntiles, flush, H, D, td, dW1, db1);
     }
     {   // dW2aug = delta2 . [Hact; t; 1]^T   (M = D, N = H + 2)
         dim3 grid((D + WGT_M - 1) / WGT_M, (H + 2 + WGT_N - 1) / WGT_N, nsplit);
         wgrad_tc_kernel<<<grid, WGT_THREADS, WGT_SMEM, st>>>(tapeD2, D, tapeH, H, ntiles, Q, steps, t0, td, flush, wsd);
         const int tot = D * (H + 2);
-        wgrad_tc_reduce_kernel<<<(tot + 255) / 256, 256, 0, st>>>(wsd, nslots, D, H, td, dW2, db2);
+        wgrad_tc_reduce_kernel<<<(tot + 255) / 256, 256, 0, st>>>(wsd, nsplit, ntiles, flush, D, H, td, dW2, db2);
     }
     if (launches) *launches += 4;
     return (int)cudaGetLastError();
