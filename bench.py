@@ -40,8 +40,10 @@ LAMBDA = 1.0e2
 
 def stepper_dram_traffic() -> float | None:
     """dram__bytes_read.sum + dram__bytes_write.sum of the forward stepper per launch, from the committed
-    `ncu --set full` capture (profiles/r1h_steppers_ncu_raw_metrics.json)."""
-    f = ROOT / "profiles" / "r1h_steppers_ncu_raw_metrics.json"
+    `ncu --set full` capture of the final round-1 build (profiles/r1x_fwd4_final_ncu_raw_metrics.json; r1h = earlier build)."""
+    f = ROOT / "profiles" / "r1x_fwd4_final_ncu_raw_metrics.json"
+    if not f.exists():
+        f = ROOT / "profiles" / "r1h_steppers_ncu_raw_metrics.json"
     try:
         d = json.loads(f.read_text())
         k = next(v for n, v in d.items() if "fwd4" in n)
