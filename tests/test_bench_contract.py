@@ -1,0 +1,32 @@
+"""CPU: the reference arm of bench.py (`--impl reference`, the oracle port on the host cores) prints one JSON line with the
+contract's keys; the GPU arm refuses to run without a device (no CPU fallback)."""
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_reference_arm_prints_the_contract_line(oracle_built):
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
+                       cwd=ROOT, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["metric"] == "mnist_reg_node_train_samples_per_sec" and d["unit"] == "samples/s"
+    for k in ("value", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config", "e2e", "cpu_baseline"):
+        assert k in d, k
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"] > 0
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["vs_baseline"] is None and d["higher_is_better"] is True and "workload" in d["config"]
+
+
+def test_gpu_arm_fails_loudly_without_a_device():
+    torch = pytest.importorskip("torch")
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--steps", "1", "--warmup", "3", "--no-cpu-baseline"], capture_output=True, text=True,
+                       cwd=ROOT, timeout=600)
+    assert r.returncode != 0            # no silent CPU path
