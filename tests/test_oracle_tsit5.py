@@ -102,3 +102,24 @@ def test_rejections_and_failure_codes(oracle_built):
     pn = p.copy(); pn[0] = np.nan
     r = orc.Oracle(orc.OracleConfig(D=D, H=H, B=B)).forward(x, pn)
     assert r.retcode == 3      # NaN
+
+
+def test_free_interpolant_is_fourth_order_accurate(oracle_built):
+    """Dense output behind `saveat`: on the analytic linear ODE the states interpolated INSIDE fixed
+    steps converge with order >= 4 towards expm -- wrong interpolant coefficients would leave an O(1) error independent of dt."""
+    rng = np.random.default_rng(9)
+    D, H = 3, 4
+    p, A, c0, c1 = linear_field_params(rng, D, H)
+    u0 = rng.standard_normal((D, 1))
+    errs = []
+    for n in (4, 8, 16, 32):
+        dt = np.full(n, 1.0 / n)
+        # three interior points of every step, never a step end
+        sa = np.sort(np.concatenate([(np.arange(n) + th) / n for th in (0.17, 0.5, 0.83)]))
+        cfg = orc.OracleConfig(D=D, H=H, B=1, act1=orc.ACT_ID, act2=orc.ACT_ID, forced_dt=dt, forced_accept=np.ones(n, np.int32), saveat=sa)
+        r = orc.Oracle(cfg, f64=True).forward(u0, p)
+        ref = np.stack([exact_linear(A, c0, c1, u0[:, 0], t) for t in sa])
+        errs.append(np.abs(r.usave[:, :, 0] - ref).max())
+    rate = np.log2(np.array(errs[:-1]) / np.array(errs[1:]))
+    assert np.all(rate > 3.7), (rate, errs)
+    assert errs[-1] < 1e-6
