@@ -305,6 +305,8 @@ extern "C" int rnde_create(const rnde_config* cfg, rnde_handle** out) {
         for (int l = 0; l < cfg->n_layers; ++l) {
             const int M = cfg->layer_width[l];
             if (M <= 0 || M > 1024 || cfg->layer_act[l] < 0 || cfg->layer_act[l] > 1) return RNDE_ERR_ARG;
+            // dense_wgrad_kernel: every thread owns at most CW_TPT 4x4 tiles of a layer's (out x (in + bias)) gradient
+            if (cfg->need_backward && ((M + 3) / 4) * ((K + 1 + 3) / 4) > CW_TPT * CW_NT) return RNDE_ERR_UNSUPPORTED;
             K = M;
         }
     }
