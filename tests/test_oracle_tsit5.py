@@ -123,3 +123,25 @@ def test_free_interpolant_is_fourth_order_accurate(oracle_built):
     rate = np.log2(np.array(errs[:-1]) / np.array(errs[1:]))
     assert np.all(rate > 3.7), (rate, errs)
     assert errs[-1] < 1e-6
+
+
+def test_initial_step_matches_the_hairer_wanner_heuristic_of_scipy(oracle_built):
+    """SURVEY.md Appendix A.5 (initial dt, UNVERIFIED upstream detail): the same algorithm is implemented independently by
+    scipy.integrate (select_initial_step, Hairer-Wanner II.4) -- same RMS norms, same 0.01*d0/d1, same (0.01/max(d1,d2))^(1/5)."""
+    from scipy.integrate._ivp.common import select_initial_step
+    rng = np.random.default_rng(21)
+    D, H, B = 4, 7, 3
+    p = orc.glorot_params(rng, D, H, dtype=np.float64) * 1.3
+    x = rng.standard_normal((D, B))
+    tol = 1e-6
+    cfg = orc.OracleConfig(D=D, H=H, B=B, abstol=tol, reltol=tol)
+    o = orc.Oracle(cfg, f64=True)
+    r = o.forward(x, p)
+
+    def fun(t, y):      # the batched field on the flattened (column-major) state
+        k, _ = o.rhs(p, y.reshape(B, D).T, t)
+        return np.ascontiguousarray(k.T).reshape(-1)
+
+    y0 = np.ascontiguousarray(x.T).reshape(-1)
+    h = select_initial_step(fun, 0.0, y0, 1.0, np.inf, fun(0.0, y0), 1, 4, tol, tol)
+    assert abs(r.dt_init - h) <= 1e-9 * h, (r.dt_init, h)
