@@ -145,3 +145,22 @@ def test_initial_step_matches_the_hairer_wanner_heuristic_of_scipy(oracle_built)
     y0 = np.ascontiguousarray(x.T).reshape(-1)
     h = select_initial_step(fun, 0.0, y0, 1.0, np.inf, fun(0.0, y0), 1, 4, tol, tol)
     assert abs(r.dt_init - h) <= 1e-9 * h, (r.dt_init, h)
+
+
+def test_stiffness_estimate_is_a_rayleigh_type_quotient_of_the_jacobian(oracle_built):
+    """eigen_est = ||k7 - k6|| / ||u_new - g6||.  For u' = A u + c(t) with c constant in t, k7 - k6 =
+    A (u_new - g6) exactly, so every recorded estimate lies between the smallest and the largest singular value of A."""
+    rng = np.random.default_rng(13)
+    D, H, B = 5, 6, 2
+    p, A, c0, c1 = linear_field_params(rng, D, H)
+    # remove the explicit time dependence (time columns of both layers) so that c1 = 0
+    W1 = p[: H * (D + 1)].reshape(D + 1, H).T.copy(); W1[:, D] = 0
+    o2 = H * (D + 1) + H
+    W2 = p[o2: o2 + D * (H + 1)].reshape(H + 1, D).T.copy(); W2[:, H] = 0
+    p = np.concatenate([W1.flatten(order="F"), p[H * (D + 1): o2], W2.flatten(order="F"), p[o2 + D * (H + 1):]])
+    sv = np.linalg.svd(W2[:, :H] @ W1[:, :D], compute_uv=False)
+    cfg = orc.OracleConfig(D=D, H=H, B=B, act1=orc.ACT_ID, act2=orc.ACT_ID, alg=orc.ALG_AUTO_TSIT5, reg_kind=orc.REG_STIFF_DT_ABS,
+                           abstol=1e-9, reltol=1e-9)
+    r = orc.Oracle(cfg, f64=True).forward(rng.standard_normal((D, B)), p)
+    eig = np.array([s[3] for s in r.steps])
+    assert len(eig) > 5 and np.all(eig <= sv[0] * (1 + 1e-6)) and np.all(eig >= sv[-1] * (1 - 1e-6)), (eig.min(), eig.max(), sv)
