@@ -65,6 +65,12 @@ class ClassifierNODE:
         x = self.preode(x) if self.preode is not None else x
         B = x.shape[1]
         dev = x.device
+        if agg not in _AGG:
+            raise ValueError(f"agg must be one of {sorted(_AGG)}")
+        if x.dim() != 2 or x.shape[0] != D or tuple(y_onehot.shape) != (Cn, B):
+            raise ValueError(f"x must be ({D}, B) and y_onehot ({Cn}, B)")
+        if not x.is_cuda or not y_onehot.is_cuda:
+            raise RuntimeError("regneuralde.jl_b200 runs on CUDA tensors only (no CPU fallback)")
         reg_kind = (ERROR_ESTIMATE if func is None else func).kind if node.regularize else L.REG_NONE
         hd = node._handle(B, reg_kind, True)
         lib = hd.lib
@@ -78,10 +84,9 @@ class ClassifierNODE:
         # stream synchronisation of the step happens inside rnde_backward (it needs the accepted-step count)
         hd.check(lib.rnde_forward(hd.h, xbuf.data_ptr(), self.p2.data_ptr(), ws["u"].data_ptr(), ws["sv"].data_ptr(), None, stream),
                  "rnde_forward")
+        hd.serial += 1      # the handle's tape now belongs to this step (node.py _Handle.check_tape)
         hd.check(lib.rnde_head_loss_grad(hd.h, ws["u"].data_ptr(), self.p3.data_ptr(), ybuf.data_ptr(), Cn, float(ce_scale), ws["loss"].data_ptr(),
                                          ws["logits"].data_ptr(), ws["du"].data_ptr(), ws["g3"].data_ptr(), stream), "rnde_head_loss_grad")
-        if agg not in _AGG:
-            raise ValueError(agg)
         regularized = reg_kind != L.REG_NONE
         if regularized:
             hd.check(lib.rnde_reg_agg(hd.h, _AGG[agg], float(lam), float(reg_scale), ws["sv"].data_ptr(), ws["dsv"].data_ptr(),

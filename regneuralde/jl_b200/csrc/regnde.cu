@@ -6,6 +6,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <mutex>
 #include <algorithm>
 #include <cuda_runtime.h>
 #include "regnde.h"
@@ -59,6 +60,7 @@ struct rnde_handle {
 };
 
 static bool g_const_init[64] = {false};
+static std::mutex g_const_mutex;      // handles may be created from several host threads
 
 static int set_err(rnde_handle* h, int code, const std::string& msg) {
     if (h) h->err = msg;
@@ -75,6 +77,7 @@ static int set_err(rnde_handle* h, int code, const std::string& msg) {
 static int init_constants(rnde_handle* h) {
     int dev = 0;
     CUDA_TRY(h, cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_const_mutex);
     if (dev < 64 && g_const_init[dev]) return RNDE_OK;
     float A[8][8]; float BT[8]; float C[8];
     memset(A, 0, sizeof(A)); memset(BT, 0, sizeof(BT)); memset(C, 0, sizeof(C));
@@ -175,6 +178,7 @@ static int chain_hrows(const rnde_config& c) {
 }
 
 extern "C" int64_t rnde_num_params(const rnde_config* c) {
+    if (!c) return 0;
     const int td = c->time_dep ? 1 : 0;
     if (c->n_layers > 0) {
         int64_t n = 0;
@@ -188,6 +192,7 @@ extern "C" int64_t rnde_num_params(const rnde_config* c) {
 extern "C" int rnde_default_kblock(const rnde_config* c) {
     // canonical K-blocking of layer 1 (DESIGN.md "canonical arithmetic"): large states are
     // summed in 8 blocks (one per CTA of the cluster kernel), small ones in a single chain.
+    if (!c) return 0;
     const int D = c->state_dim;
     return D >= 128 ? (D + 7) / 8 : D;
 }
@@ -394,8 +399,9 @@ extern "C" int rnde_create(const rnde_config* cfg, rnde_handle** out) {
 
 extern "C" int rnde_debug_timeline(rnde_handle* h, long long* out, int n) {
     if (!h || !h->dbg) return RNDE_ERR_STATE;
-    cudaDeviceSynchronize();
-    cudaMemcpy(out, h->dbg, sizeof(long long) * n, cudaMemcpyDeviceToHost);
+    if (!out || n < 0 || n > 8000) return RNDE_ERR_ARG;
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    CUDA_TRY(h, cudaMemcpy(out, h->dbg, sizeof(long long) * n, cudaMemcpyDeviceToHost));
     return RNDE_OK;
 }
 
@@ -412,7 +418,7 @@ extern "C" int rnde_dist_import(rnde_handle* h, const void* ipc_handles, int32_t
     if (!h || !ipc_handles || nranks != h->cfg.nranks) return RNDE_ERR_ARG;
     const unsigned char* p = (const unsigned char*)ipc_handles;
     for (int r = 0; r < nranks; ++r) {
-        if (r == h->cfg.rank) continue;
+        if (r == h->cfg.rank || h->peers_open[r]) continue;      // a repeated import keeps the mappings it already has
         cudaIpcMemHandle_t mh;
         memcpy(&mh, p + (size_t)r * RNDE_IPC_HANDLE_BYTES, sizeof(mh));
         void* ptr = nullptr;
@@ -471,6 +477,15 @@ static void set_chain_offsets(const rnde_handle* h, KParams& P, int base_floats)
     P.oCH = P.oCB + mw * h->NP;
 }
 
+// a handle's workspace, constants and kernel attributes belong to the device that was current in rnde_create
+static int check_device(rnde_handle* h) {
+    int dev = -1;
+    CUDA_TRY(h, cudaGetDevice(&dev));
+    if (dev != h->device)
+        return set_err(h, RNDE_ERR_STATE, "handle was created on device " + std::to_string(h->device) + " but the current device is " + std::to_string(dev));
+    return RNDE_OK;
+}
+
 static int launch(rnde_handle* h, kern_t k, const KParams& P, size_t smem, cudaStream_t st) {
     cudaLaunchConfig_t lc{};
     lc.gridDim = dim3(h->Q * h->G); lc.blockDim = dim3(NT_FWD); lc.dynamicSmemBytes = smem; lc.stream = st;
@@ -491,6 +506,7 @@ static int forward_impl(rnde_handle* h, const float* x_dev, const float* p_dev, 
                         rnde_stats* stats_host, void* stream) {
     if (!h || !x_dev || !p_dev || (!u_out_dev && !usave_dev)) return RNDE_ERR_ARG;
     if (!h->dist_ready) return set_err(h, RNDE_ERR_STATE, "RNDE_DIST_EXACT: call rnde_dist_export / rnde_dist_import on every rank first");
+    if (int drc = check_device(h)) return drc;
     cudaStream_t st = (cudaStream_t)stream;
     KParams P;
     fill_params(h, P);
@@ -556,6 +572,7 @@ static int backward_impl(rnde_handle* h, const float* du_dev, const float* dusav
                          void* stream) {
     if (!h || (!du_dev && !dusave_dev) || !dp_dev) return RNDE_ERR_ARG;
     if (!h->have_tape || !h->cfg.need_backward) return set_err(h, RNDE_ERR_STATE, "rnde_backward needs a preceding rnde_forward on a handle created with need_backward=1");
+    if (int drc = check_device(h)) return drc;
     cudaStream_t st = (cudaStream_t)stream;
     // number of accepted steps of the forward on this handle: wait for its stats copy only, so that work queued
     // behind the forward (classifier head, regulariser aggregation) keeps the GPU busy while the host gets here
@@ -706,7 +723,7 @@ extern "C" int rnde_head_loss_grad(rnde_handle* h, const float* u_dev, const flo
                                    float loss_scale, float* loss_dev, float* logits_dev, float* du_dev, float* dp3_dev, void* stream) {
     if (!h || !u_dev || !p3_dev || !y_onehot_dev || !loss_dev || !du_dev || !dp3_dev || n_classes <= 0 || n_classes > 32) return RNDE_ERR_ARG;
     const int D = h->cfg.state_dim, B = h->cfg.batch;
-    if (!h->head_ws) CUDA_TRY(h, cudaMalloc(&h->head_ws, sizeof(float) * ((size_t)n_classes * B + B + 4)));
+    if (!h->head_ws) CUDA_TRY(h, cudaMalloc(&h->head_ws, sizeof(float) * ((size_t)32 * B + B + 4)));
     int rc = launch_head(D, B, n_classes, u_dev, p3_dev, y_onehot_dev, loss_scale, loss_dev, logits_dev, du_dev, dp3_dev, h->head_ws,
                          (cudaStream_t)stream, &h->launches);
     if (rc != 0) return set_err(h, RNDE_ERR_CUDA, std::string("head launch: ") + cudaGetErrorString((cudaError_t)rc));

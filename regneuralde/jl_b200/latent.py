@@ -27,6 +27,7 @@ class _GruHandle:
         self.lib = L.lib()
         self.cfg = cfg
         self.h = C.c_void_p()
+        self.serial = 0          # taped forwards so far: the tape in the handle serves the latest one only
         rc = self.lib.rnde_gru_create(C.byref(cfg), C.byref(self.h))
         if rc != L.OK:
             raise L.RndeError(rc, f"rnde_gru_create(I={cfg.in_dim}, H={cfg.hidden_dim}, L={cfg.latent_dim}, B={cfg.batch}, T={cfg.seq_len})")
@@ -50,12 +51,16 @@ class _GruRun(torch.autograd.Function):
         cfg = hd.cfg
         out = torch.empty(2 * cfg.latent_dim * cfg.batch, device=xbuf.device, dtype=torch.float32)
         hd.check(hd.lib.rnde_gru_forward(hd.h, xbuf.data_ptr(), p.data_ptr(), out.data_ptr(), _stream_ptr()), "rnde_gru_forward")
-        ctx.hd, ctx.p_ref = hd, p
+        hd.serial += 1
+        ctx.hd, ctx.p_ref, ctx.serial = hd, p, hd.serial
         return out
 
     @staticmethod
     def backward(ctx, dout: torch.Tensor):
         hd = ctx.hd
+        if ctx.serial != hd.serial:
+            raise RuntimeError("backward through a LatentGRU run whose tape was overwritten by a later forward of the same "
+                               "batch size and sequence length; call backward before the next forward")
         dp = torch.empty(ctx.p_ref.numel(), device=dout.device, dtype=torch.float32)
         hd.check(hd.lib.rnde_gru_backward(hd.h, dout.contiguous().data_ptr(), dp.data_ptr(), _stream_ptr()), "rnde_gru_backward")
         return None, dp, None
@@ -91,6 +96,8 @@ class LatentGRU:
             raise ValueError(f"x must have {2 * self.in_dim + 1} rows (data, mask, time)")
         if not x.is_cuda or not p.is_cuda:
             raise RuntimeError("regneuralde.jl_b200 runs on CUDA tensors only (no CPU fallback)")
+        if p.dtype != torch.float32 or p.dim() != 1 or p.numel() != self.p.numel():
+            raise ValueError(f"p must be the flat Float32 parameter vector of length {self.p.numel()} (Flux.destructure order)")
         need_bwd = torch.is_grad_enabled() and p.requires_grad
         hd = self._handle(B, T, need_bwd)
         xbuf = x.detach().to(torch.float32).permute(2, 1, 0).contiguous().view(-1)       # Julia layout X x T x B
@@ -169,7 +176,9 @@ def loss_function(data, mask, t_row, model: LatentTimeSeriesModel, p1, p2, p3, p
     kl = lam_k * kl_divergence(mu0, logvar)
     reg = torch.zeros((), device=data.device)
     if regularize:
-        reg = lam_r * (sv.saveval.mean() if agg == "mean" else sv.saveval.max())
+        if agg not in ("mean", "maximum", "sum"):
+            raise ValueError("agg must be mean, maximum or sum")
+        reg = lam_r * {"mean": torch.mean, "maximum": torch.max, "sum": torch.sum}[agg](sv.saveval)
     total = -(ll - kl).mean() + reg
     return total, nfe, {"nll": -ll.mean().detach(), "kl": kl.mean().detach(), "reg": reg.detach()}
 

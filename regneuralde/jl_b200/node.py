@@ -167,6 +167,7 @@ class _Handle:
         self.lib = L.lib()
         self.cfg = cfg
         self.h = C.c_void_p()
+        self.serial = 0          # number of taped forwards: a backward may only consume the latest tape
         rc = self.lib.rnde_create(C.byref(cfg), C.byref(self.h))
         if rc != L.OK:
             raise L.RndeError(rc, f"rnde_create(D={cfg.state_dim}, H={cfg.hidden_dim}, B={cfg.batch})")
@@ -174,6 +175,12 @@ class _Handle:
     def check(self, rc: int, what: str):
         if rc != L.OK:
             raise L.RndeError(rc, what + ": " + self.lib.rnde_last_error(self.h).decode())
+
+    def check_tape(self, serial: int):
+        """The tape lives in the handle (one per batch size / regulariser): a second forward overwrites it."""
+        if serial != self.serial:
+            raise RuntimeError("backward through a solve whose tape was overwritten by a later forward of the same node and "
+                               "batch size; call backward before the next forward (or use a second TrackedNeuralODE)")
 
     def __del__(self):
         try:
@@ -202,6 +209,8 @@ class _Solve(torch.autograd.Function):
         rc = hd.lib.rnde_forward(hd.h, xbuf.data_ptr(), p.data_ptr(), u.data_ptr(), sv.data_ptr(), C.byref(st), _stream_ptr())
         node.last_stats = st
         hd.check(rc, "rnde_forward")
+        hd.serial += 1
+        ctx.serial = hd.serial
         ctx.hd = hd
         ctx.n_saved = st.n_saved
         ctx.p_ref = p            # keeps the parameter buffer alive until backward
@@ -210,6 +219,7 @@ class _Solve(torch.autograd.Function):
     @staticmethod
     def backward(ctx, du: torch.Tensor, dsv: torch.Tensor):
         hd = ctx.hd
+        hd.check_tape(ctx.serial)
         cfg = hd.cfg
         D, B = cfg.state_dim, cfg.batch
         du = du.contiguous() if du is not None else torch.zeros(D * B, device=ctx.p_ref.device)
@@ -236,12 +246,14 @@ class _SolveSaveat(torch.autograd.Function):
         rc = hd.lib.rnde_forward_saveat(hd.h, xbuf.data_ptr(), p.data_ptr(), None, us.data_ptr(), sv.data_ptr(), C.byref(st), _stream_ptr())
         node.last_stats = st
         hd.check(rc, "rnde_forward_saveat")
-        ctx.hd, ctx.n_saved, ctx.p_ref = hd, st.n_saved, p
+        hd.serial += 1
+        ctx.hd, ctx.n_saved, ctx.p_ref, ctx.serial = hd, st.n_saved, p, hd.serial
         return us, sv[: st.n_saved]
 
     @staticmethod
     def backward(ctx, dus: torch.Tensor, dsv: torch.Tensor):
         hd = ctx.hd
+        hd.check_tape(ctx.serial)
         cfg = hd.cfg
         D, B = cfg.state_dim, cfg.batch
         dev = ctx.p_ref.device
@@ -346,6 +358,8 @@ class TrackedNeuralODE:
             raise ValueError(f"x must be ({D}, B)")
         if not x.is_cuda or not p.is_cuda:
             raise RuntimeError("regneuralde.jl_b200 runs on CUDA tensors only (no CPU fallback)")
+        if p.dtype != torch.float32 or p.dim() != 1 or p.numel() != self.p.numel():
+            raise ValueError(f"p must be the flat Float32 parameter vector of length {self.p.numel()} (Flux.destructure order)")
         B = x.shape[1]
         if self.regularize:
             func = ERROR_ESTIMATE if func is None else func     # default of neural_ode.jl:116

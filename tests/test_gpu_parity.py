@@ -433,6 +433,23 @@ def test_fixed24_tensor_core_forward_bit_identical(oracle_built, name, D, H, B, 
         assert e_p <= 1e-4 and e_x <= 1e-4
 
 
+def test_backward_through_an_overwritten_tape_is_refused():
+    """The tape lives in the handle (one per batch size): a second forward overwrites it, so differentiating the first
+    result afterwards must fail loudly instead of returning gradients of the wrong solve."""
+    r = R()
+    node = make_node(2, 10, 0, False, r.Tsit5())
+    p = r.track(node.p)
+    x = torch.rand(2, 3, device="cuda")
+    u1, _, _ = node(x, p)
+    u2, _, _ = node(2 * x, p)
+    with pytest.raises(RuntimeError, match="overwritten"):
+        u1.sum().backward()
+    u2.sum().backward()
+    assert p.grad is not None and torch.isfinite(p.grad).all()
+    with pytest.raises(ValueError, match="Float32"):
+        node(x, p.detach().double())
+
+
 def test_solution_object(oracle_built):
     """solution(n, x, p; solver, tspan, saveat) (neural_ode.jl:182-210): same solve without the callback, solver override."""
     r = R()
