@@ -158,24 +158,37 @@ def cpu_train_step(orc, o, x, y, p2, p3, B):
     return ce + reg, dp2, np.concatenate([dW3.flatten(order="F"), g.sum(axis=1)]).astype(np.float32), r
 
 
-def cpu_baseline(B: int, steps: int, warmup: int = 0):
+def cpu_baseline(B: int, steps: int, warmup: int = 0, budget_s: float = 0.0):
+    """Times `steps` CPU training steps after `warmup` untimed ones.  With budget_s > 0 the per-step sample (columns of the
+    batch) is cut so that warmup + steps fit the budget, judged from one probe step on the full batch."""
     from oracle import orc
     orc.build()
     rng = np.random.default_rng(SEED)
     p2, p3 = init_params(rng)
     xs, ys = synth_batches(rng, 1, B)
     cores = os.cpu_count() or 1
-    o = orc.Oracle(orc.OracleConfig(D=D, H=H, B=B, kblock1=(D + 7) // 8, reg_kind=orc.REG_ERR_DT, nthreads=cores))
-    for _ in range(warmup):
+    Bs = B
+    if budget_s > 0:
+        o = orc.Oracle(orc.OracleConfig(D=D, H=H, B=B, kblock1=(D + 7) // 8, reg_kind=orc.REG_ERR_DT, nthreads=cores))
+        tp = time.perf_counter()
         cpu_train_step(orc, o, xs[0], ys[0], p2, p3, B)
+        probe = time.perf_counter() - tp
+        need = probe * (steps + warmup)
+        if need > budget_s:
+            Bs = max(16, int(B * budget_s / need) // 16 * 16)
+    x, y = np.ascontiguousarray(xs[0][:, :Bs]), np.ascontiguousarray(ys[0][:, :Bs])
+    o = orc.Oracle(orc.OracleConfig(D=D, H=H, B=Bs, kblock1=(D + 7) // 8, reg_kind=orc.REG_ERR_DT, nthreads=cores))
+    for _ in range(warmup):
+        cpu_train_step(orc, o, x, y, p2, p3, Bs)
     t0 = time.perf_counter()
     nf = 0
     for _ in range(steps):
-        _, _, _, r = cpu_train_step(orc, o, xs[0], ys[0], p2, p3, B)
+        _, _, _, r = cpu_train_step(orc, o, x, y, p2, p3, Bs)
         nf = r.nf
     el = time.perf_counter() - t0
-    return {"value": B * steps / el, "unit": "samples/s", "cores": cores, "kind": "port",
-            "sample": f"{steps} training step(s) of the full {B}-sample batch (C oracle, OpenMP, forward+adjoint+head), nfe={nf}",
+    what = f"the full {B}-sample batch" if Bs == B else f"the first {Bs} of the batch's {B} samples (cut to fit {budget_s:.0f} s)"
+    return {"value": Bs * steps / el, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} training step(s) of {what} (C oracle, OpenMP, forward+adjoint+head), nfe={nf}",
             "ms_per_step": 1e3 * el / steps}
 
 
@@ -184,11 +197,11 @@ def run_reference(args):
     if rank != 0:
         return
     B = args.batch
-    steps = max(1, min(args.steps, 4))
-    cb = cpu_baseline(B, steps, warmup=1 if args.warmup > 0 else 0)
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    cb = cpu_baseline(B, steps, warmup=warm, budget_s=150.0)      # exactly K timed steps after W warm-up steps, each a bounded sample
     line = {
         "impl": "reference", "metric": "mnist_reg_node_train_samples_per_sec", "value": cb["value"], "unit": "samples/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": 1 if args.warmup > 0 else 0, "ms_per_step": cb["ms_per_step"],
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": cb["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"mnist_node reg(error_est) train step, MLPDynamics(784,100), batch {B}, Tsit5 tol 1.4e-8",
                    "note": "CPU restatement of the reference path (Julia toolchain unavailable); oracle/rnde_oracle.c on all host cores"},

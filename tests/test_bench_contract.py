@@ -23,6 +23,18 @@ def test_reference_arm_prints_the_contract_line(oracle_built):
     assert d["vs_baseline"] is None and d["higher_is_better"] is True and "workload" in d["config"]
 
 
+def test_reference_arm_under_torchrun_prints_one_line_from_rank_0(oracle_built):
+    """N > 1: the driver launches the reference arm like ours; rank 0 alone works and prints, the others exit 0."""
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29731", str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, cwd=ROOT, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["steps"] == 1 and d["warmup"] == 0 and d["value"] > 0
+
+
 def test_gpu_arm_fails_loudly_without_a_device():
     torch = pytest.importorskip("torch")
     if torch.cuda.is_available():
