@@ -129,7 +129,7 @@ def saved_value(kind, EEst, eig, dt, dtype):
 
 def solve(x, p, *, D, H, act2_tanh=True, time_dep=True, t0=0.0, t1=1.0, abstol=1.4e-8, reltol=1.4e-8,
           auto_tsit5=False, reg_kind=REG_NONE, detach="all", forced_dt=None, forced_accept=None,
-          dt_leaf=None, max_steps=100000, saveat=None, chain=None) -> TorchResult:
+          dt_leaf=None, max_steps=100000, saveat=None, chain=None, rhs=None) -> TorchResult:
     """x: (D,B) tensor, p: flat parameter tensor (Flux.destructure order).
 
     forced_dt/forced_accept replay a recorded attempt sequence (controller
@@ -141,6 +141,8 @@ def solve(x, p, *, D, H, act2_tanh=True, time_dep=True, t0=0.0, t1=1.0, abstol=1
     f = lambda z, t: field(p, z, t, D, H, act2_tanh, time_dep)
     if chain is not None:       # (widths, acts, pre_act): field without time input
         f = lambda z, t: chain_field(p, z, D, chain[0], chain[1], chain[2])
+    if rhs is not None:         # any (z, t) -> dz/dt on the stepper's state (oracle/ffjord_oracle.py: the augmented CNF state)
+        f = rhs
     c = lambda v: torch.tensor(v, dtype=dtype)
     t = c(t0)
     tf = c(t1)
@@ -175,7 +177,7 @@ def solve(x, p, *, D, H, act2_tanh=True, time_dep=True, t0=0.0, t1=1.0, abstol=1
         f1 = f(u1, t + dt0)
         d2 = rms((f1 - k1) / sk) / dt0
         md = torch.maximum(d1, d2)
-        if float(md) <= 1e-15:
+        if float(md.detach()) <= 1e-15:
             dt1 = torch.maximum(c(1e-6), dt0 * 1e-3)
         else:
             dt1 = 10.0 ** (-(2 + torch.log10(md)) / 5)
