@@ -1,0 +1,83 @@
+"""CPU: the three statements of the C ABI's structs -- include/regnde.h (authoritative), the ctypes mirror the Python host
+uses, and the Julia structs a maintainer of the reference would add (julia/RegNeuralDEB200.jl) -- must name
+the same fields with the same types in the same order, and the Julia file may only ccall symbols the header declares."""
+import ctypes as C
+import re
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+HEADER = (ROOT / "include" / "regnde.h").read_text()
+JULIA = (ROOT / "julia" / "RegNeuralDEB200.jl").read_text()
+
+CTYPE = {"int32_t": (C.c_int32, "Int32"), "int64_t": (C.c_int64, "Int64"), "float": (C.c_float, "Float32")}
+
+
+def header_struct(name):
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), HEADER, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        ty, rest = decl.split(None, 1)
+        for item in rest.split(","):
+            m = re.fullmatch(r"\s*(\w+)(?:\[(\d+)\])?\s*", item)
+            fields.append((m.group(1), ty, int(m.group(2)) if m.group(2) else 0))
+    return fields
+
+
+def julia_struct(name):
+    body = re.search(r"struct %s\n(.*?)\nend" % name, JULIA, re.S).group(1)
+    fields = []
+    for line in body.splitlines():
+        line = line.split("#")[0]
+        if "= new(" in line:
+            continue
+        for item in line.split(";"):
+            item = item.strip()
+            if not item:
+                continue
+            fname, ty = item.split("::")
+            m = re.fullmatch(r"NTuple\{(\d+),(\w+)\}", ty)
+            fields.append((fname, m.group(2), int(m.group(1))) if m else (fname, ty, 0))
+    return fields
+
+
+def check(cname, pycls, jname):
+    hf = header_struct(cname)
+    assert [(n, (CTYPE[t][0] * k) if k else CTYPE[t][0]) for n, t, k in hf] == \
+        [(n, t) for n, t in pycls._fields_], f"ctypes mirror of {cname} differs from the header"
+    assert [(n, CTYPE[t][1], k) for n, t, k in hf] == julia_struct(jname), f"Julia mirror of {cname} differs from the header"
+
+
+def test_struct_mirrors_agree_with_the_header():
+    from regneuralde.jl_b200 import _lib as L
+    check("rnde_config", L.Config, "RndeConfig")
+    check("rnde_stats", L.Stats, "RndeStats")
+    check("rnde_gru_config", L.GruConfig, "RndeGruConfig")
+    assert C.sizeof(L.Config) == 176 and C.sizeof(L.Stats) == 32 and C.sizeof(L.GruConfig) == 32
+
+
+def test_julia_binding_only_calls_declared_symbols_and_integration_lists_all():
+    declared = set(re.findall(r"\b(rnde_\w+)\s*\(", re.sub(r"/\*.*?\*/", "", HEADER, flags=re.S)))
+    called = set(re.findall(r"ccall\(\(:(\w+), LIB\)", JULIA))
+    assert called and called <= declared, called - declared
+    integ = (ROOT / "INTEGRATION.md").read_text()
+    missing = [s for s in sorted(declared) if s not in integ]
+    assert not missing, missing
+
+
+def test_enum_values_agree():
+    from regneuralde.jl_b200 import _lib as L
+    enums = dict(re.findall(r"\b(RNDE_\w+)\s*=\s*(-?\d+)", HEADER))
+    for py, c in [("ACT_IDENTITY", "RNDE_ACT_IDENTITY"), ("ACT_TANH", "RNDE_ACT_TANH"), ("ALG_TSIT5", "RNDE_ALG_TSIT5"),
+                  ("ALG_AUTO_TSIT5", "RNDE_ALG_AUTO_TSIT5"), ("REG_NONE", "RNDE_REG_NONE"), ("REG_ERR_DT", "RNDE_REG_ERR_DT"),
+                  ("REG_STIFF_DT_ABS", "RNDE_REG_STIFF_DT_ABS"), ("REG_STIFF_SCALED", "RNDE_REG_STIFF_SCALED"),
+                  ("REG_ERR_PLUS_STIFF", "RNDE_REG_ERR_PLUS_STIFF"), ("KERNEL_AUTO", "RNDE_KERNEL_AUTO"), ("KERNEL_CHAIN", "RNDE_KERNEL_CHAIN"),
+                  ("DIST_SINGLE", "RNDE_DIST_SINGLE"), ("DIST_EXACT", "RNDE_DIST_EXACT"), ("DIST_INDEPENDENT", "RNDE_DIST_INDEPENDENT"),
+                  ("ARITH_FMA_CHAIN", "RNDE_ARITH_FMA_CHAIN"), ("ARITH_FIXED24", "RNDE_ARITH_FIXED24"), ("OK", "RNDE_OK")]:
+        assert c in enums, c
+        assert getattr(L, py) == int(enums[c]), (py, c)
+    for name, val in re.findall(r"const (\w+)\s*=\s*Int32\((\d+)\)", JULIA):
+        assert int(enums["RNDE_" + name]) == int(val), name
