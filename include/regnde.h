@@ -27,7 +27,10 @@
  *   - Every function returns an rnde_status; nothing throws across the ABI.
  *     Solver failures (maxiters, dt<=dtmin, NaN) are reported in the return
  *     code AND in rnde_stats.retcode, mirroring upstream retcodes.
- *   - A handle is not thread-safe; distinct handles are independent.
+ *   - A handle is not thread-safe; distinct handles are independent.  A handle
+ *     belongs to the device that was current in rnde_create / rnde_gru_create;
+ *     its entry points run there whatever the caller's current device is and
+ *     restore the caller's device before returning.
  *   - There is NO CPU fallback: with no CUDA device every call returns
  *     RNDE_ERR_CUDA.
  */

@@ -74,6 +74,23 @@ static int set_err(rnde_handle* h, int code, const std::string& msg) {
         }                                                                                         \
     } while (0)
 
+// A handle's workspace, constants and kernel attributes belong to the device that was current in rnde_create.  Entry
+// points that touch the device run on it whatever the caller's current device is and put the caller's back on return
+// (the library never changes the current device behind the caller's back).
+struct DeviceScope {
+    int prev = -1; bool switched = false; cudaError_t err = cudaSuccess;
+    explicit DeviceScope(int dev) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) { err = cudaSetDevice(dev); switched = (err == cudaSuccess); }
+    }
+    ~DeviceScope() { if (switched) cudaSetDevice(prev); }
+    DeviceScope(const DeviceScope&) = delete;
+    DeviceScope& operator=(const DeviceScope&) = delete;
+};
+#define ON_HANDLE_DEVICE(h)                                                                                          \
+    DeviceScope _dev_scope((h)->device);                                                                             \
+    if (_dev_scope.err != cudaSuccess) return set_err((h), RNDE_ERR_CUDA, std::string("selecting the handle's device: ") + cudaGetErrorString(_dev_scope.err))
+
 static int init_constants(rnde_handle* h) {
     int dev = 0;
     CUDA_TRY(h, cudaGetDevice(&dev));
@@ -233,6 +250,7 @@ static void free_all(rnde_handle* h) {
 
 extern "C" void rnde_destroy(rnde_handle* h) {
     if (!h) return;
+    DeviceScope scope(h->device);
     free_all(h);
     delete h;
 }
@@ -400,6 +418,7 @@ extern "C" int rnde_create(const rnde_config* cfg, rnde_handle** out) {
 extern "C" int rnde_debug_timeline(rnde_handle* h, long long* out, int n) {
     if (!h || !h->dbg) return RNDE_ERR_STATE;
     if (!out || n < 0 || n > 8000) return RNDE_ERR_ARG;
+    ON_HANDLE_DEVICE(h);
     CUDA_TRY(h, cudaDeviceSynchronize());
     CUDA_TRY(h, cudaMemcpy(out, h->dbg, sizeof(long long) * n, cudaMemcpyDeviceToHost));
     return RNDE_OK;
@@ -408,6 +427,7 @@ extern "C" int rnde_debug_timeline(rnde_handle* h, long long* out, int n) {
 extern "C" int rnde_dist_export(rnde_handle* h, void* ipc_handle_out) {
     if (!h || !ipc_handle_out) return RNDE_ERR_ARG;
     static_assert(sizeof(cudaIpcMemHandle_t) == RNDE_IPC_HANDLE_BYTES, "IPC handle size");
+    ON_HANDLE_DEVICE(h);
     cudaIpcMemHandle_t mh;
     CUDA_TRY(h, cudaIpcGetMemHandle(&mh, h->colsum));
     memcpy(ipc_handle_out, &mh, sizeof(mh));
@@ -416,6 +436,7 @@ extern "C" int rnde_dist_export(rnde_handle* h, void* ipc_handle_out) {
 
 extern "C" int rnde_dist_import(rnde_handle* h, const void* ipc_handles, int32_t nranks) {
     if (!h || !ipc_handles || nranks != h->cfg.nranks) return RNDE_ERR_ARG;
+    ON_HANDLE_DEVICE(h);
     const unsigned char* p = (const unsigned char*)ipc_handles;
     for (int r = 0; r < nranks; ++r) {
         if (r == h->cfg.rank || h->peers_open[r]) continue;      // a repeated import keeps the mappings it already has
@@ -443,6 +464,7 @@ extern "C" int rnde_set_saveat(rnde_handle* h, const float* saveat_host, int32_t
         if (!(saveat_host[i] >= h->cfg.t0 && saveat_host[i] <= h->cfg.t1)) return set_err(h, RNDE_ERR_ARG, "saveat time outside tspan");
         if (i > 0 && !(saveat_host[i] > saveat_host[i - 1])) return set_err(h, RNDE_ERR_ARG, "saveat times must be strictly increasing");
     }
+    ON_HANDLE_DEVICE(h);
     if (n > 0) CUDA_TRY(h, cudaMemcpy(h->saveat_dev, saveat_host, sizeof(float) * n, cudaMemcpyHostToDevice));
     h->n_saveat = n;
     return RNDE_OK;
@@ -477,15 +499,6 @@ static void set_chain_offsets(const rnde_handle* h, KParams& P, int base_floats)
     P.oCH = P.oCB + mw * h->NP;
 }
 
-// a handle's workspace, constants and kernel attributes belong to the device that was current in rnde_create
-static int check_device(rnde_handle* h) {
-    int dev = -1;
-    CUDA_TRY(h, cudaGetDevice(&dev));
-    if (dev != h->device)
-        return set_err(h, RNDE_ERR_STATE, "handle was created on device " + std::to_string(h->device) + " but the current device is " + std::to_string(dev));
-    return RNDE_OK;
-}
-
 static int launch(rnde_handle* h, kern_t k, const KParams& P, size_t smem, cudaStream_t st) {
     cudaLaunchConfig_t lc{};
     lc.gridDim = dim3(h->Q * h->G); lc.blockDim = dim3(NT_FWD); lc.dynamicSmemBytes = smem; lc.stream = st;
@@ -506,7 +519,7 @@ static int forward_impl(rnde_handle* h, const float* x_dev, const float* p_dev, 
                         rnde_stats* stats_host, void* stream) {
     if (!h || !x_dev || !p_dev || (!u_out_dev && !usave_dev)) return RNDE_ERR_ARG;
     if (!h->dist_ready) return set_err(h, RNDE_ERR_STATE, "RNDE_DIST_EXACT: call rnde_dist_export / rnde_dist_import on every rank first");
-    if (int drc = check_device(h)) return drc;
+    ON_HANDLE_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     KParams P;
     fill_params(h, P);
@@ -552,6 +565,7 @@ extern "C" int rnde_forward_saveat(rnde_handle* h, const float* x_dev, const flo
 
 extern "C" int rnde_get_steps(rnde_handle* h, float* t, float* dt, float* eest, float* eig, int32_t cap) {
     if (!h) return RNDE_ERR_ARG;
+    ON_HANDLE_DEVICE(h);
     CUDA_TRY(h, cudaDeviceSynchronize());
     DevStats s;
     CUDA_TRY(h, cudaMemcpy(&s, h->stats, sizeof(s), cudaMemcpyDeviceToHost));
@@ -572,7 +586,7 @@ static int backward_impl(rnde_handle* h, const float* du_dev, const float* dusav
                          void* stream) {
     if (!h || (!du_dev && !dusave_dev) || !dp_dev) return RNDE_ERR_ARG;
     if (!h->have_tape || !h->cfg.need_backward) return set_err(h, RNDE_ERR_STATE, "rnde_backward needs a preceding rnde_forward on a handle created with need_backward=1");
-    if (int drc = check_device(h)) return drc;
+    ON_HANDLE_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     // number of accepted steps of the forward on this handle: wait for its stats copy only, so that work queued
     // behind the forward (classifier head, regulariser aggregation) keeps the GPU busy while the host gets here
@@ -651,6 +665,7 @@ static int ensure(rnde_handle* h, float** p, size_t n) {
 extern "C" int rnde_forward_host(rnde_handle* h, const float* x_host, const float* p_host, float* u_out_host, float* saveval_host,
                                  rnde_stats* stats_host) {
     if (!h || !x_host || !p_host || !u_out_host) return RNDE_ERR_ARG;
+    ON_HANDLE_DEVICE(h);
     const size_t n = (size_t)h->cfg.state_dim * h->cfg.batch;
     int rc;
     if ((rc = ensure(h, &h->hx, n)) || (rc = ensure(h, &h->hp, (size_t)h->np)) || (rc = ensure(h, &h->hu, n)) ||
@@ -668,6 +683,7 @@ extern "C" int rnde_forward_host(rnde_handle* h, const float* x_host, const floa
 
 extern "C" int rnde_backward_host(rnde_handle* h, const float* du_host, const float* dsaveval_host, float* dp_host, float* dx_host) {
     if (!h || !du_host || !dp_host) return RNDE_ERR_ARG;
+    ON_HANDLE_DEVICE(h);
     const size_t n = (size_t)h->cfg.state_dim * h->cfg.batch;
     int rc;
     if ((rc = ensure(h, &h->hdu, n)) || (rc = ensure(h, &h->hdsv, (size_t)h->cfg.tape_capacity + 1)) || (rc = ensure(h, &h->hdp, (size_t)h->np)) ||
@@ -689,6 +705,7 @@ extern "C" int rnde_allreduce_grads(rnde_handle* h, float* buf_dev, int64_t n, v
     if (h->cfg.dist_mode != RNDE_DIST_EXACT || !h->dist_ready || h->gcap == 0)
         return set_err(h, RNDE_ERR_STATE, "rnde_allreduce_grads needs a RNDE_DIST_EXACT handle after rnde_dist_import");
     if (n > h->gcap) return set_err(h, RNDE_ERR_ARG, "rnde_allreduce_grads: n exceeds num_params + 16384");
+    ON_HANDLE_DEVICE(h);
     ArParams A; memset(&A, 0, sizeof(A));
     for (int i = 0; i < 8; ++i) A.peers[i] = h->peers[i];
     A.goff = h->goff_bytes; A.nranks = h->cfg.nranks; A.rank = h->cfg.rank; A.seq = ++h->ar_seq; A.n = n; A.gcap = h->gcap;
@@ -702,6 +719,7 @@ extern "C" int rnde_allreduce_grads(rnde_handle* h, float* buf_dev, int64_t n, v
 
 extern "C" int rnde_last_stats(rnde_handle* h, rnde_stats* out) {
     if (!h || !out) return RNDE_ERR_ARG;
+    ON_HANDLE_DEVICE(h);
     if (h->ev_stats) CUDA_TRY(h, cudaEventSynchronize(h->ev_stats));
     const DevStats& s = *h->stats_pinned;
     out->nf = s.nf; out->naccept = s.naccept; out->nreject = s.nreject; out->n_saved = s.n_saved;
@@ -713,6 +731,7 @@ extern "C" int rnde_last_stats(rnde_handle* h, rnde_stats* out) {
 extern "C" int rnde_reg_agg(rnde_handle* h, int32_t agg, float lam, float cot_scale, const float* saveval_dev, float* dsaveval_dev, float* reg_dev,
                             void* stream) {
     if (!h || agg < 0 || agg > 2 || !saveval_dev || !dsaveval_dev || !reg_dev) return RNDE_ERR_ARG;
+    ON_HANDLE_DEVICE(h);
     reg_agg_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(h->stats, agg, lam, cot_scale, saveval_dev, dsaveval_dev, h->cfg.tape_capacity, reg_dev);
     CUDA_TRY(h, cudaGetLastError());
     h->launches += 1;
@@ -722,6 +741,7 @@ extern "C" int rnde_reg_agg(rnde_handle* h, int32_t agg, float lam, float cot_sc
 extern "C" int rnde_head_loss_grad(rnde_handle* h, const float* u_dev, const float* p3_dev, const float* y_onehot_dev, int32_t n_classes,
                                    float loss_scale, float* loss_dev, float* logits_dev, float* du_dev, float* dp3_dev, void* stream) {
     if (!h || !u_dev || !p3_dev || !y_onehot_dev || !loss_dev || !du_dev || !dp3_dev || n_classes <= 0 || n_classes > 32) return RNDE_ERR_ARG;
+    ON_HANDLE_DEVICE(h);
     const int D = h->cfg.state_dim, B = h->cfg.batch;
     if (!h->head_ws) CUDA_TRY(h, cudaMalloc(&h->head_ws, sizeof(float) * ((size_t)32 * B + B + 4)));
     int rc = launch_head(D, B, n_classes, u_dev, p3_dev, y_onehot_dev, loss_scale, loss_dev, logits_dev, du_dev, dp3_dev, h->head_ws,
@@ -772,7 +792,7 @@ extern "C" int rnde_test_pow(const float* x_dev, float e, float* y_dev, float* l
 struct rnde_gru {
     rnde_gru_config cfg;
     GruOffsets off;
-    int Q = 0, num_sms = 0;
+    int Q = 0, num_sms = 0, device = 0;
     size_t smem_fwd = 0, smem_bwd = 0;
     float* tapeA = nullptr; float* tapeD = nullptr; double* acc = nullptr;
     const float* last_p = nullptr;
@@ -790,6 +810,7 @@ extern "C" int64_t rnde_gru_launch_count(const rnde_gru* g) { return g ? g->laun
 
 extern "C" void rnde_gru_destroy(rnde_gru* g) {
     if (!g) return;
+    DeviceScope scope(g->device);
     cudaFree(g->tapeA); cudaFree(g->tapeD); cudaFree(g->acc);
     delete g;
 }
@@ -806,7 +827,7 @@ extern "C" int rnde_gru_create(const rnde_gru_config* cfg, rnde_gru** out) {
     g->Q = (cfg->batch + GRU_NP - 1) / GRU_NP;
     int dev = 0; cudaDeviceProp prop;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { delete g; return RNDE_ERR_CUDA; }
-    g->num_sms = prop.multiProcessorCount;
+    g->num_sms = prop.multiProcessorCount; g->device = dev;
     g->smem_fwd = sizeof(float) * ((size_t)round_up(g->off.np, 4) + (size_t)GRU_NP * (2 * C + 3 * H + 2 * L + 2 * L) + GRU_NP);
     g->smem_bwd = sizeof(float) * ((size_t)round_up(g->off.np, 4) + (size_t)GRU_NP * (2 * L * 4 + 2 * L + 3 * H));
     if (g->smem_fwd > prop.sharedMemPerBlockOptin || g->smem_bwd > prop.sharedMemPerBlockOptin) {
@@ -835,6 +856,8 @@ static void gru_fill(const rnde_gru* g, GruParams& P) {
 
 extern "C" int rnde_gru_forward(rnde_gru* g, const float* x_dev, const float* p_dev, float* out_dev, void* stream) {
     if (!g || !x_dev || !p_dev || !out_dev) return RNDE_ERR_ARG;
+    DeviceScope scope(g->device);
+    if (scope.err != cudaSuccess) { g->err = std::string("selecting the handle's device: ") + cudaGetErrorString(scope.err); return RNDE_ERR_CUDA; }
     GruParams P; gru_fill(g, P);
     P.x = x_dev; P.p = p_dev; P.out = out_dev;
     gru_fwd_kernel<<<g->Q, GRU_NT, g->smem_fwd, (cudaStream_t)stream>>>(P);
@@ -847,6 +870,8 @@ extern "C" int rnde_gru_forward(rnde_gru* g, const float* x_dev, const float* p_
 extern "C" int rnde_gru_backward(rnde_gru* g, const float* dout_dev, float* dp_dev, void* stream) {
     if (!g || !dout_dev || !dp_dev) return RNDE_ERR_ARG;
     if (!g->have_tape) { g->err = "rnde_gru_backward needs a preceding rnde_gru_forward on a handle created with need_backward=1"; return RNDE_ERR_STATE; }
+    DeviceScope scope(g->device);
+    if (scope.err != cudaSuccess) { g->err = std::string("selecting the handle's device: ") + cudaGetErrorString(scope.err); return RNDE_ERR_CUDA; }
     cudaStream_t st = (cudaStream_t)stream;
     GruParams P; gru_fill(g, P);
     P.p = g->last_p; P.dout = dout_dev;
