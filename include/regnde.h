@@ -252,6 +252,8 @@ int rnde_get_steps(rnde_handle* h, float* t, float* dt, float* eest, float* eig,
 int rnde_test_tanh(const float* x_dev, float* y_dev, int64_t n, void* stream);
 int rnde_test_tanh_bits(uint32_t first_bits, int64_t n, float* y_dev, void* stream);
 int rnde_test_pow(const float* x_dev, float e, float* y_dev, float* l10_dev, int64_t n, void* stream);
+/* y[i] = fn(float with bit pattern first_bits + i); fn: 0 canon_tanhf, 1 canon_sigmoidf, 2 canon_softplusf, 3 canon_expnegf */
+int rnde_test_unary_bits(int32_t fn, uint32_t first_bits, int64_t n, float* y_dev, void* stream);
 int rnde_debug_timeline(rnde_handle* h, long long* out, int n);
 
 #ifdef __cplusplus

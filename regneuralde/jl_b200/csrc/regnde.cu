@@ -782,6 +782,18 @@ extern "C" int rnde_test_tanh_bits(uint32_t first_bits, int64_t n, float* y_dev,
     canon_tanh_range_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(first_bits, (long long)n, y_dev);
     return cudaGetLastError() == cudaSuccess ? RNDE_OK : RNDE_ERR_CUDA;
 }
+__global__ void canon_unary_range_kernel(int fn, unsigned int first_bits, long long n, float* __restrict__ y) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = __uint_as_float(first_bits + (unsigned int)i);
+    y[i] = fn == 0 ? canon_tanhf(x) : fn == 1 ? canon_sigmoidf(x) : fn == 2 ? canon_softplusf(x) : canon_expnegf(x);
+}
+extern "C" int rnde_test_unary_bits(int32_t fn, uint32_t first_bits, int64_t n, float* y_dev, void* stream) {
+    if (fn < 0 || fn > 3 || n < 0 || !y_dev) return RNDE_ERR_ARG;
+    if (n == 0) return RNDE_OK;
+    canon_unary_range_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(fn, first_bits, (long long)n, y_dev);
+    return cudaGetLastError() == cudaSuccess ? RNDE_OK : RNDE_ERR_CUDA;
+}
 extern "C" int rnde_test_pow(const float* x_dev, float e, float* y_dev, float* l10_dev, int64_t n, void* stream) {
     canon_pow_test_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x_dev, e, y_dev, l10_dev, (long long)n);
     return cudaGetLastError() == cudaSuccess ? RNDE_OK : RNDE_ERR_CUDA;
