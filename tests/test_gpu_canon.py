@@ -78,7 +78,7 @@ def test_pow_log10_bit_identical(cpu):
         assert np.array_equal(ld.cpu().numpy().view(np.uint32), l.view(np.uint32))
 
 
-def pending_test_sigmoid_softplus_bit_identical(cpu):
+def test_sigmoid_softplus_bit_identical(cpu):
     """The FFJORD activations (canon_sigmoidf / canon_softplusf): every Float32 with 2^-26 <= |x| < 104,
     both signs -- below 2^-26 the result no longer depends on x beyond the last bit and above 104 it is saturated, so those
     ranges and the specials are sampled."""
