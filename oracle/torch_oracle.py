@@ -239,7 +239,7 @@ def solve(x, p, *, D, H, act2_tanh=True, time_dep=True, t0=0.0, t1=1.0, abstol=1
         atmp = utilde / (abstol + torch.maximum(torch.abs(u), torch.abs(unew)) * reltol)
         EEst = rms(atmp)
         nf += 6
-        ee = float(EEst)
+        ee = float(EEst.detach())
         if math.isnan(ee):
             raise FloatingPointError("NaN EEst")
         if ee == 0:

@@ -115,3 +115,22 @@ def test_kinetic_rows_of_the_unregularised_functor():
     assert r.saveval is None and (r.lam1 > 0).all() and (r.lam2 > 0).all()
     r0 = F.ffjord(x, p, e, D=D, H=H, regularized_functor=False, regularize=False, abstol=1e-8, reltol=1e-8)
     assert torch.allclose(r.logpx, r0.logpx, rtol=0, atol=1e-6)                           # same flow, extra rows only
+
+
+def test_golden_fixture_of_the_tabular_shape():
+    """tests/golden/ffjord_tabular.npz (make_golden_ffjord.py): MLPDynamics(43, 100), both functors, loss gradient."""
+    from pathlib import Path
+    g = np.load(Path(__file__).resolve().parent / "golden" / "ffjord_tabular.npz")
+    D, H = 43, 100
+    p = torch.from_numpy(g["p"]).requires_grad_(True)
+    x, e = torch.from_numpy(g["x"]), torch.from_numpy(g["e"])
+    total, r = F.loss_function(x, p, e, D=D, H=H, regularized_functor=True, lam_r=100.0)
+    assert [r.nfe, r.sol.naccept, r.sol.nreject] == g["counts"].tolist()
+    assert np.allclose(r.logpx.detach().numpy(), g["logpx"], rtol=1e-11, atol=0)
+    assert np.allclose(r.saveval.detach().numpy(), g["saveval"], rtol=1e-8, atol=1e-14)
+    assert abs(float(total) - float(g["loss"])) <= 1e-10 * abs(float(g["loss"]))
+    dp, = torch.autograd.grad(total, p)
+    assert np.abs(dp.numpy() - g["dp"]).max() <= 1e-8 * np.abs(g["dp"]).max()
+    r0 = F.ffjord(x, p.detach(), e, D=D, H=H, regularized_functor=False, regularize=True)
+    assert [r0.nfe, r0.sol.naccept, r0.sol.nreject] == g["counts_kinetic"].tolist()
+    assert np.allclose(r0.lam1.numpy(), g["lam1"], rtol=1e-10) and np.allclose(r0.lam2.numpy(), g["lam2"], rtol=1e-10)
