@@ -83,7 +83,7 @@ def test_change_of_variables_identity():
     assert abs(-total - math.log(abs(float(torch.det(J))))) < 1e-7
     # and the functor's log-density is the standard normal at z(1) minus delta_logp
     z = r.sol.u[:D, 0].detach()
-    assert abs(float(r.logpx[0]) - (float(-(math.log(2 * math.pi) + z * z).sum() / 2) - float(r.sol.u[D, 0]))) < 1e-14
+    assert abs(float(r.logpx[0].detach()) - (float(-(math.log(2 * math.pi) + z * z).sum() / 2) - float(r.sol.u[D, 0].detach()))) < 1e-14
 
 
 def test_regularised_functor_and_loss_gradient_against_finite_differences():
