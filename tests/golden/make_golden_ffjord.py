@@ -26,10 +26,10 @@ def main():
     g, = torch.autograd.grad(total, tp)
     r0 = F.ffjord(tx, tp.detach(), te, D=D, H=H, regularized_functor=False, regularize=True)
     np.savez_compressed(out / "ffjord_tabular.npz", p=p, x=x, e=e, logpx=r.logpx.detach().numpy(), saveval=r.saveval.detach().numpy(),
-                        counts=np.array([r.nfe, r.sol.naccept, r.sol.nreject]), loss=np.array(float(total)), dp=g.numpy(),
+                        counts=np.array([r.nfe, r.sol.naccept, r.sol.nreject]), loss=np.array(float(total.detach())), dp=g.numpy(),
                         logpx_kinetic=r0.logpx.numpy(), lam1=r0.lam1.numpy(), lam2=r0.lam2.numpy(),
                         counts_kinetic=np.array([r0.nfe, r0.sol.naccept, r0.sol.nreject]))
-    print("ffjord_tabular: nfe", r.nfe, "naccept", r.sol.naccept, "loss", float(total), "| kinetic functor nfe", r0.nfe)
+    print("ffjord_tabular: nfe", r.nfe, "naccept", r.sol.naccept, "loss", float(total.detach()), "| kinetic functor nfe", r0.nfe)
 
 
 if __name__ == "__main__":

@@ -91,7 +91,7 @@ def test_regularised_functor_and_loss_gradient_against_finite_differences():
     p, x, e = setup(D, H, B, seed=5)
     pg = p.clone().requires_grad_(True)
     total, r = F.loss_function(x, pg, e, D=D, H=H, regularized_functor=True, lam_r=1.0, abstol=1e-5, reltol=1e-5)
-    assert r.saveval.shape[0] == r.sol.naccept + 1 and float(r.saveval[0]) == 0.0       # save_start entry: EEst*dt with dt = 0
+    assert r.saveval.shape[0] == r.sol.naccept + 1 and float(r.saveval[0].detach()) == 0.0       # save_start entry: EEst*dt with dt = 0
     assert r.nfe == 3 + 6 * (r.sol.naccept + r.sol.nreject)
     assert float(r.lam1.abs().sum()) == 0 and float(r.lam2.abs().sum()) == 0               # ffjord.jl:135 returns _z
     g, = torch.autograd.grad(total, pg)
@@ -128,7 +128,7 @@ def test_golden_fixture_of_the_tabular_shape():
     assert [r.nfe, r.sol.naccept, r.sol.nreject] == g["counts"].tolist()
     assert np.allclose(r.logpx.detach().numpy(), g["logpx"], rtol=1e-11, atol=0)
     assert np.allclose(r.saveval.detach().numpy(), g["saveval"], rtol=1e-8, atol=1e-14)
-    assert abs(float(total) - float(g["loss"])) <= 1e-10 * abs(float(g["loss"]))
+    assert abs(float(total.detach()) - float(g["loss"])) <= 1e-10 * abs(float(g["loss"]))
     dp, = torch.autograd.grad(total, p)
     assert np.abs(dp.numpy() - g["dp"]).max() <= 1e-8 * np.abs(g["dp"]).max()
     r0 = F.ffjord(x, p.detach(), e, D=D, H=H, regularized_functor=False, regularize=True)
