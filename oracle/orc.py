@@ -33,6 +33,7 @@ class _Cfg(C.Structure):
         ("n_forced", C.c_int), ("forced_dt", C.POINTER(C.c_double)), ("forced_accept", C.POINTER(C.c_int)),
         ("n_saveat", C.c_int), ("saveat", C.POINTER(C.c_double)),
         ("n_layers", C.c_int), ("width", C.c_int * 8), ("act", C.c_int * 8), ("pre_act", C.c_int), ("arith", C.c_int),
+        ("csq_extra", C.c_int), ("csq_noise", C.c_void_p),
     ]
 
 
@@ -90,10 +91,16 @@ class OracleConfig:
     widths: tuple | None = None
     acts: tuple | None = None
     pre_act: int = 0
+    # FFJORD field (forward only): csq_extra = 1 or 3 augmented rows (D counts them), csq_noise = the Hutchinson noise (D - extra, B)
+    csq_extra: int = 0
+    csq_noise: np.ndarray | None = None
     arith: int = 0          # 1 = FIXED24 exact fixed-point layer products (rnde_oracle.c), the tensor-core forward stepper's arithmetic
 
     @property
     def n_params(self) -> int:
+        if self.csq_extra:
+            Dz, H = self.D - self.csq_extra, self.H
+            return (H * Dz + 4 * H) + (H * H + 4 * H) + (Dz * H + 4 * Dz)
         if self.widths is not None:
             n, K = 0, self.D
             for M in self.widths:
@@ -153,6 +160,12 @@ class Oracle:
             c.time_dep = 0
             c.H = max(cfg.widths)
         c.arith = int(cfg.arith)
+        if cfg.csq_extra:
+            en = np.asfortranarray(cfg.csq_noise, dtype=self.dtype)
+            assert en.shape == (cfg.D - cfg.csq_extra, cfg.B)
+            self._keep.append(en)
+            c.csq_extra = int(cfg.csq_extra)
+            c.csq_noise = en.ctypes.data_as(C.c_void_p)
         if cfg.saveat is not None:
             sa = np.ascontiguousarray(cfg.saveat, dtype=np.float64)
             self._keep.append(sa)

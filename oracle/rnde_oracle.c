@@ -89,6 +89,12 @@ typedef struct {
     /* arith = 1 (FIXED24): the layer products of the 2-layer field are exact truncated fixed-point products -- the
      * arithmetic of the tensor-core forward stepper (csrc/fwd4x_kernel.cuh); see fixed24_* below. */
     int arith;
+    /* FFJORD field (csq_extra = 1 or 3; SURVEY.md 8f row N4, FORWARD ONLY -- no kernel exists for this row yet): the state
+     * holds D - csq_extra data rows z plus [delta_logp (; ||f||^2; ||e^T J||^2)] (src/models/ffjord.jl:53-66); the field is
+     * MLPDynamics(D - csq_extra, H) of three ConcatSquash layers with softplus between (experiments/ffjord_tabular.jl:47-105),
+     * evaluated together with e^T J for the fixed Hutchinson noise csq_noise ((D - csq_extra) x B, REAL, column-major). */
+    int csq_extra;
+    const void* csq_noise;
 } orc_config;
 
 typedef struct {
@@ -116,6 +122,10 @@ typedef struct {
 
 static size_t n_params(const orc_config* c) {
     int td = c->time_dep ? 1 : 0;
+    if (c->csq_extra > 0) {
+        const size_t Dz = (size_t)(c->D - c->csq_extra), H = (size_t)c->H;
+        return (H * Dz + 4 * H) + (H * H + 4 * H) + (Dz * H + 4 * Dz);
+    }
     if (c->n_layers > 0) {
         size_t n = 0;
         for (int l = 0; l < c->n_layers; ++l) { const int K = l ? c->width[l - 1] : c->D; n += (size_t)c->width[l] * K + c->width[l]; }
@@ -337,8 +347,82 @@ static void rhs_eval_fixed24(const orc_config* c, const REAL* p, const REAL* z, 
     }
 }
 
+/* ------------------------------------------------------------------ */
+/* FFJORD field: ConcatSquash MLP and its transposed-Jacobian product    */
+/* Canonical order (one column): every product W x and W^T u cuts its contraction index into 4 contiguous quarters of */
+/* ceil(K/4), each an fma chain in ascending order from 0, combined as (q0+q1)+(q2+q3) -- the order of quad_dense in    */
+/* csrc/chain.cuh.  A layer is r = fma(W x + B, g, fma(bW, t, bB)) with the gate g = sigmoid(G*t); the transposed chain  */
+/* multiplies by the gate first (u = g .* v, then W^T u: the same value as (W .* g)^T v of ffjord_tabular.jl:71 with M    */
+/* instead of M*K roundings); the row sums (trace, kinetic terms) are ascending fma chains from 0.                       */
+/* ------------------------------------------------------------------ */
+#ifdef ORC_F64
+static REAL csq_sigmoid(REAL x) { const REAL e = exp(-fabs(x)); return x >= 0 ? 1.0 / (1.0 + e) : e / (1.0 + e); }
+static REAL csq_softplus(REAL x) { const REAL l = log1p(exp(-fabs(x))); return x > 0 ? x + l : l; }
+#else
+static REAL csq_sigmoid(REAL x) { return canon_sigmoidf(x); }
+static REAL csq_softplus(REAL x) { return canon_softplusf(x); }
+#endif
+static REAL quad_sum(const REAL* w, size_t wstride, const REAL* x, int K) {
+    const int kb = (K + 3) / 4;
+    REAL qv[4];
+    for (int blk = 0; blk < 4; ++blk) {
+        const int i0 = blk * kb, i1 = i0 + kb < K ? i0 + kb : K;
+        REAL acc = 0;
+        for (int i = i0; i < i1; ++i) acc = R_FMA(w[wstride * (size_t)i], x[i], acc);
+        qv[blk] = acc;
+    }
+    return (qv[0] + qv[1]) + (qv[2] + qv[3]);
+}
+typedef struct { const REAL *W, *B, *bW, *bB, *G; int M, K; } csq_layer;
+static const REAL* csq_take(const REAL* p, int M, int K, csq_layer* L) {
+    L->M = M; L->K = K; L->W = p; L->B = p + (size_t)M * K; L->bW = L->B + M; L->bB = L->bW + M; L->G = L->bB + M;
+    return L->G + M;
+}
+/* r = layer(x), g = its gates (kept for the transposed chain) */
+static void csq_forward(const csq_layer* L, const REAL* x, REAL t, REAL* r, REAL* g) {
+    for (int o = 0; o < L->M; ++o) {
+        g[o] = csq_sigmoid(L->G[o] * t);
+        const REAL lin = quad_sum(L->W + o, (size_t)L->M, x, L->K) + L->B[o];        /* W column-major M x K: row o has stride M */
+        r[o] = R_FMA(lin, g[o], R_FMA(L->bW[o], t, L->bB[o]));
+    }
+}
+/* out = W^T (g .* v) */
+static void csq_back(const csq_layer* L, const REAL* g, const REAL* v, REAL* out, REAL* u) {
+    for (int o = 0; o < L->M; ++o) u[o] = g[o] * v[o];
+    for (int k = 0; k < L->K; ++k) out[k] = quad_sum(L->W + (size_t)L->M * k, 1, u, L->M);
+}
+static void csq_column(const orc_config* c, const REAL* p, const REAL* zj, const REAL* ej, REAL t, REAL* out) {
+    const int X = c->csq_extra, Dz = c->D - X, H = c->H;
+    csq_layer L1, L2, L3;
+    p = csq_take(p, H, Dz, &L1); p = csq_take(p, H, H, &L2); csq_take(p, Dz, H, &L3);
+    REAL r1[1024], r2[1024], g1[1024], g2[1024], g3[1024], v[1024], u[1024], eJ[1024];
+    REAL a[1024] = {0}, w[1024] = {0};
+    csq_forward(&L1, zj, t, r1, g1);
+    for (int i = 0; i < H; ++i) a[i] = csq_softplus(r1[i]);
+    csq_forward(&L2, a, t, r2, g2);
+    for (int i = 0; i < H; ++i) a[i] = csq_softplus(r2[i]);
+    csq_forward(&L3, a, t, out, g3);                           /* rows 0 .. Dz-1: f(z, t) */
+    csq_back(&L3, g3, ej, v, u);                               /* H */
+    for (int i = 0; i < H; ++i) w[i] = csq_sigmoid(r2[i]) * v[i];
+    csq_back(&L2, g2, w, v, u);                                /* H */
+    for (int i = 0; i < H; ++i) w[i] = csq_sigmoid(r1[i]) * v[i];
+    csq_back(&L1, g1, w, eJ, u);                               /* Dz: e^T J */
+    REAL tr = 0, f2 = 0, j2 = 0;
+    for (int i = 0; i < Dz; ++i) { tr = R_FMA(eJ[i], ej[i], tr); f2 = R_FMA(out[i], out[i], f2); j2 = R_FMA(eJ[i], eJ[i], j2); }
+    out[Dz] = -tr;
+    if (X == 3) { out[Dz + 1] = f2; out[Dz + 2] = j2; }
+}
+
 static void rhs_eval(const orc_config* c, const REAL* p, const REAL* z, REAL t, REAL* k, REAL* hout) {
     const int D = c->D, H = c->H, B = c->B, td = c->time_dep ? 1 : 0;
+    if (c->csq_extra > 0) {
+        (void)hout;
+        const REAL* e = (const REAL*)c->csq_noise;
+        const int Dz = D - c->csq_extra;
+#pragma omp parallel for schedule(static)
+        for (int j = 0; j < B; ++j) csq_column(c, p, z + (size_t)D * j, e + (size_t)Dz * j, t, k + (size_t)D * j);
+        return;
+    }
     if (c->arith == 1 && c->n_layers == 0 && sizeof(REAL) == 4) { rhs_eval_fixed24(c, p, z, t, k, hout); return; }
     if (c->n_layers > 0) {
         (void)t; (void)hout;
@@ -617,6 +701,8 @@ static REAL saved_value(int kind, REAL EEst, REAL eig, REAL dt) {
 int FN(create)(const orc_config* cfg, void** out) {
     if (!cfg || cfg->D <= 0 || cfg->H <= 0 || cfg->B <= 0) return ORC_ERR_ARG;
     if (cfg->kblock1 > 0 && (cfg->D + cfg->kblock1 - 1) / cfg->kblock1 > 64) return ORC_ERR_ARG;   /* col_sumsq part[64] */
+    if (cfg->csq_extra != 0 && ((cfg->csq_extra != 1 && cfg->csq_extra != 3) || cfg->D <= cfg->csq_extra || !cfg->csq_noise ||
+                                cfg->n_layers > 0 || cfg->arith != 0 || cfg->D > 1024 || cfg->H > 1024)) return ORC_ERR_ARG;
     orc_handle* h = (orc_handle*)calloc(1, sizeof(orc_handle));
     h->cfg = *cfg;
     if (h->cfg.max_steps <= 0) h->cfg.max_steps = 1000000;

@@ -134,3 +134,62 @@ def test_golden_fixture_of_the_tabular_shape():
     r0 = F.ffjord(x, p.detach(), e, D=D, H=H, regularized_functor=False, regularize=True)
     assert [r0.nfe, r0.sol.naccept, r0.sol.nreject] == g["counts_kinetic"].tolist()
     assert np.allclose(r0.lam1.numpy(), g["lam1"], rtol=1e-10) and np.allclose(r0.lam2.numpy(), g["lam2"], rtol=1e-10)
+
+
+# ---- the C restatement of the same field (oracle/rnde_oracle.c, csq_extra): the future bit-level specification ----
+def _c_oracle(D, H, B, extra, e, f64, **kw):
+    from oracle import orc
+    orc.build()
+    return orc.Oracle(orc.OracleConfig(D=D + extra, H=H, B=B, csq_extra=extra, csq_noise=e, kblock1=D + extra, **kw), f64=f64)
+
+
+@pytest.mark.parametrize("extra", [1, 3])
+def test_c_field_matches_the_torch_restatement(extra):
+    D, H, B = 5, 9, 4
+    p, x, e = setup(D, H, B, seed=11)
+    u = torch.cat([x, torch.from_numpy(np.random.default_rng(2).standard_normal((extra, B)))], 0)
+    ref = F.ffjord_rhs(u, p, torch.tensor(0.45, dtype=torch.float64), e, D, H, extra == 3).numpy()
+    o = _c_oracle(D, H, B, extra, e.numpy(), True)
+    assert o.cfg.n_params == F.n_params(D, H)
+    k, _ = o.rhs(p.numpy(), u.numpy(), 0.45)
+    assert np.abs(k - ref).max() <= 1e-13 * np.abs(ref).max()
+    o32 = _c_oracle(D, H, B, extra, e.numpy().astype(np.float32), False)
+    k32, _ = o32.rhs(p.numpy().astype(np.float32), u.numpy().astype(np.float32), 0.45)
+    assert np.abs(k32 - ref).max() <= 2e-6 * np.abs(ref).max()          # canonical Float32 arithmetic (regnde_canon.h activations)
+
+
+def test_c_solve_matches_the_torch_functors():
+    """Same Tsit5 controller on the augmented state: identical step counts, log-densities to 1e-11 (Float64 builds)."""
+    D, H, B = 4, 8, 3
+    p, x, e = setup(D, H, B, seed=12)
+    from oracle import orc
+    for extra, regf in ((1, True), (3, False)):
+        r = F.ffjord(x, p, e, D=D, H=H, regularized_functor=regf, regularize=not regf)
+        o = _c_oracle(D, H, B, extra, e.numpy(), True, reg_kind=orc.REG_ERR_DT if regf else orc.REG_NONE, abstol=1.4e-8, reltol=1.4e-8)
+        u0 = np.concatenate([x.numpy(), np.zeros((extra, B))], 0)
+        c = o.forward(u0, p.numpy())
+        assert (c.nf, c.naccept, c.nreject) == (r.nfe, r.sol.naccept, r.sol.nreject)
+        assert np.abs(c.u - r.sol.u.numpy()).max() <= 1e-11 * np.abs(c.u).max()
+        z = c.u[:D]
+        logpx = (-(np.log(2 * np.pi) + z * z) / 2).sum(0) - c.u[D]
+        assert np.abs(logpx - r.logpx.numpy()).max() <= 1e-10 * np.abs(logpx).max()
+        if regf:
+            # EEst cancels O(1) stage values down to O(tol): the two summation orders differ by ~1e-16 / 1.4e-8 relative per term
+            assert np.allclose(c.saveval, r.saveval.numpy(), rtol=1e-3, atol=1e-14)
+        with pytest.raises(Exception):
+            o.backward(np.zeros((D + extra, B)), np.zeros(len(c.saveval) or 1))      # forward only
+
+
+def test_c_float32_solve_is_deterministic_and_close():
+    D, H, B = 43, 100, 5
+    rng = np.random.default_rng(21)
+    p = F.glorot_params(rng, D, H, dtype=np.float32, bias_scale=0.05)
+    x = rng.standard_normal((D, B)).astype(np.float32); e = rng.standard_normal((D, B)).astype(np.float32)
+    u0 = np.concatenate([x, np.zeros((1, B), np.float32)], 0)
+    runs = []
+    for threads in (1, 4):
+        o = _c_oracle(D, H, B, 1, e, False, nthreads=threads)
+        runs.append(o.forward(u0, p))
+    assert runs[0].nf == runs[1].nf and np.array_equal(runs[0].u.view(np.uint32), runs[1].u.view(np.uint32))
+    r = F.ffjord(torch.from_numpy(x).double(), torch.from_numpy(p).double(), torch.from_numpy(e).double(), D=D, H=H, regularized_functor=False)
+    assert np.abs(runs[0].u - r.sol.u.numpy()).max() <= 5e-5 * np.abs(r.sol.u.numpy()).max()
