@@ -106,6 +106,11 @@ def interp_weights(th):
     return b
 
 
+def _f(v):
+    """value of a tensor (or number) for control flow -- never part of the autograd graph"""
+    return float(v.detach()) if torch.is_tensor(v) else float(v)
+
+
 def rms(x):
     return torch.sqrt(torch.sum(x * x) / x.numel())
 
@@ -118,11 +123,11 @@ def saved_value(kind, EEst, eig, dt, dtype):
         return torch.abs(eig * dt)
     if kind == REG_STIFF_SCALED:
         s = torch.abs(eig)
-        return stab * (s * 0 if (float(s) == 0 or math.isnan(float(s))) else s)
+        return stab * (s * 0 if (_f(s) == 0 or math.isnan(_f(s))) else s)
     if kind == REG_ERR_PLUS_STIFF:
         e = EEst * dt
-        a = e * 0 if (float(e) == 0 or math.isnan(float(e))) else e
-        b = eig * 0 if (float(eig) == 0 or math.isnan(float(eig))) else eig
+        a = e * 0 if (_f(e) == 0 or math.isnan(_f(e))) else e
+        b = eig * 0 if (_f(eig) == 0 or math.isnan(_f(eig))) else eig
         return (a + (float(np.float32(0.1)) * stab) * b) * 1.0
     raise ValueError(kind)
 
@@ -177,7 +182,7 @@ def solve(x, p, *, D, H, act2_tanh=True, time_dep=True, t0=0.0, t1=1.0, abstol=1
         f1 = f(u1, t + dt0)
         d2 = rms((f1 - k1) / sk) / dt0
         md = torch.maximum(d1, d2)
-        if float(md.detach()) <= 1e-15:
+        if _f(md.detach()) <= 1e-15:
             dt1 = torch.maximum(c(1e-6), dt0 * 1e-3)
         else:
             dt1 = 10.0 ** (-(2 + torch.log10(md)) / 5)
@@ -185,7 +190,7 @@ def solve(x, p, *, D, H, act2_tanh=True, time_dep=True, t0=0.0, t1=1.0, abstol=1
         if detach == "all":
             dt = dt.detach()
     nf += 2
-    dt_init = float(dt)
+    dt_init = _f(dt)
     dt_log, accept_log, eest_log, dt_list, t_list = [], [], [], [], []
     naccept = nreject = 0
     as_count, as_stiff = 0, False
@@ -193,7 +198,7 @@ def solve(x, p, *, D, H, act2_tanh=True, time_dep=True, t0=0.0, t1=1.0, abstol=1
     it = 0
     accept_prev = True
     dtpropose = dt
-    while float(t) < t1:
+    while _f(t) < t1:
         if it >= max_steps:
             raise RuntimeError("maxiters")
         if it > 0:
@@ -203,7 +208,7 @@ def solve(x, p, *, D, H, act2_tanh=True, time_dep=True, t0=0.0, t1=1.0, abstol=1
                 dt = dt / min(1 / qmin, q11 / gamma)
         it += 1
         if auto_tsit5 and not forced:
-            stiffness = abs(eig_prev * float(dt) / STAB)
+            stiffness = abs(eig_prev * _f(dt) / STAB)
             stiff = stiffness > 0.9
             as_count = (1 if as_count < 0 else as_count + 1) if stiff else (-1 if as_count > 0 else as_count - 1)
             if (not as_stiff) and as_count > 10:
@@ -215,7 +220,7 @@ def solve(x, p, *, D, H, act2_tanh=True, time_dep=True, t0=0.0, t1=1.0, abstol=1
         else:
             dt = torch.minimum(dt, c(dtmax))
             rem = tf - t
-            if float(rem) < float(dt):
+            if _f(rem) < _f(dt):
                 dt = rem if detach != "all" else rem.detach()
         ks = [None, k1]
         zs = {}
@@ -249,22 +254,22 @@ def solve(x, p, *, D, H, act2_tanh=True, time_dep=True, t0=0.0, t1=1.0, abstol=1
             q = q11 / (qold ** beta2)
             q = max(1 / qmax, min(1 / qmin, q / gamma))
         accept = bool(forced_accept[it - 1]) if forced else ee <= 1.0
-        dt_log.append(float(dt)); accept_log.append(int(accept)); eest_log.append(ee)
+        dt_log.append(_f(dt)); accept_log.append(int(accept)); eest_log.append(ee)
         if auto_tsit5:
-            eig_prev = float(eig)
+            eig_prev = _f(eig)
         if accept:
             naccept += 1
             qold = max(ee, qoldinit)
-            dtnew = float(dt) / q
+            dtnew = _f(dt) / q
             dt_list.append(dt); t_list.append(t)
             tprev = t
             t = t + dt
-            while saveat is not None and save_idx < len(saveat) and float(saveat[save_idx]) <= float(t):
+            while saveat is not None and save_idx < len(saveat) and _f(saveat[save_idx]) <= _f(t):
                 tau = float(saveat[save_idx])
-                if tau == float(t):
+                if tau == _f(t):
                     usave.append(unew)
                 else:
-                    th = (tau - float(tprev)) / float(dt)       # theta is not differentiated (frozen step sequence)
+                    th = (tau - _f(tprev)) / _f(dt)       # theta is not differentiated (frozen step sequence)
                     bw = interp_weights(th)
                     acc = bw[0] * ks[1]
                     for j in range(2, 8):
