@@ -81,3 +81,26 @@ def test_enum_values_agree():
         assert getattr(L, py) == int(enums[c]), (py, c)
     for name, val in re.findall(r"const (\w+)\s*=\s*Int32\((\d+)\)", JULIA):
         assert int(enums["RNDE_" + name]) == int(val), name
+
+
+def test_julia_ccall_arities_match_the_header_prototypes():
+    """Every ccall of the Julia stub passes as many arguments as the C prototype takes (a changed signature in
+    include/regnde.h must be followed in julia/RegNeuralDEB200.jl)."""
+    H = re.sub(r"/\*.*?\*/", "", HEADER, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(rnde_\w+)\s*\(([^;{]*?)\)\s*;", H, re.S):
+        args = m.group(2).strip()
+        protos[m.group(1)] = 0 if args in ("void", "") else len(args.split(","))
+    seen = 0
+    for m in re.finditer(r"ccall\(\(:(\w+), LIB\),\s*([\w{}]+),\s*\((.*?)\),\s", JULIA, re.S):
+        name, _, types = m.groups()
+        depth, n = 0, 1 if types.strip() else 0
+        for ch in types:
+            depth += ch == "{"
+            depth -= ch == "}"
+            n += ch == "," and depth == 0
+        if types.strip().endswith(","):
+            n -= 1
+        assert name in protos and n == protos[name], (name, n, protos.get(name))
+        seen += 1
+    assert seen >= 10
