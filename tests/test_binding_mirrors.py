@@ -104,3 +104,33 @@ def test_julia_ccall_arities_match_the_header_prototypes():
         assert name in protos and n == protos[name], (name, n, protos.get(name))
         seen += 1
     assert seen >= 10
+
+
+def _top_level_args(text, start):
+    """arguments of the call whose opening parenthesis is at text[start]"""
+    depth, args, cur = 0, [], ""
+    for ch in text[start:]:
+        if ch in "([{":
+            depth += 1
+            if depth == 1:
+                continue
+        elif ch in ")]}":
+            depth -= 1
+            if depth == 0:
+                args.append(cur.strip())
+                return args
+        if ch == "," and depth == 1:
+            args.append(cur.strip()); cur = ""
+        else:
+            cur += ch
+    raise AssertionError("unbalanced call")
+
+
+def test_julia_positional_struct_constructors_fill_every_field():
+    nfields = len(header_struct("rnde_config"))
+    calls = [m.end() - 1 for m in re.finditer(r"(?<!struct )RndeConfig\(", JULIA)]
+    assert len(calls) >= 2
+    for pos in calls:
+        args = _top_level_args(JULIA, pos)
+        assert len(args) == nfields, (len(args), nfields, args[:4])
+        assert args[0] == "sizeof(RndeConfig)"
