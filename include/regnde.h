@@ -254,6 +254,12 @@ int rnde_test_tanh_bits(uint32_t first_bits, int64_t n, float* y_dev, void* stre
 int rnde_test_pow(const float* x_dev, float e, float* y_dev, float* l10_dev, int64_t n, void* stream);
 /* y[i] = fn(float with bit pattern first_bits + i); fn: 0 canon_tanhf, 1 canon_sigmoidf, 2 canon_softplusf, 3 canon_expnegf */
 int rnde_test_unary_bits(int32_t fn, uint32_t first_bits, int64_t n, float* y_dev, void* stream);
+/* One evaluation of the FFJORD field (csrc/csq.cuh; src/models/ffjord.jl:53-66 over experiments/ffjord_tabular.jl:47-105):
+ * k ((data_dim + extra) x batch) = [f(z, t); -sum(eJ .* e) (; ||f||^2; ||eJ||^2)] for z's first data_dim rows, the noise e
+ * (data_dim x batch) and the MLPDynamics(data_dim, hidden) parameters p; extra = 1 or 3.  The field is not wired into a
+ * stepper yet: this hook exists so the device evaluation can be compared bit for bit with oracle/rnde_oracle.c. */
+int rnde_test_csq_rhs(int32_t data_dim, int32_t hidden, int32_t extra, int32_t batch, const float* p_dev, const float* z_dev,
+                      const float* e_dev, float t, float* k_dev, void* stream);
 int rnde_debug_timeline(rnde_handle* h, long long* out, int n);
 
 #ifdef __cplusplus

@@ -21,6 +21,7 @@
 #include "wgrad_tc_kernel.cuh"
 #include "head_kernel.cuh"
 #include "gru_kernel.cuh"
+#include "csq.cuh"
 
 using namespace rnde;
 
@@ -792,6 +793,16 @@ extern "C" int rnde_test_unary_bits(int32_t fn, uint32_t first_bits, int64_t n, 
     if (fn < 0 || fn > 3 || n < 0 || !y_dev) return RNDE_ERR_ARG;
     if (n == 0) return RNDE_OK;
     canon_unary_range_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(fn, first_bits, (long long)n, y_dev);
+    return cudaGetLastError() == cudaSuccess ? RNDE_OK : RNDE_ERR_CUDA;
+}
+extern "C" int rnde_test_csq_rhs(int32_t data_dim, int32_t hidden, int32_t extra, int32_t batch, const float* p_dev, const float* z_dev,
+                                 const float* e_dev, float t, float* k_dev, void* stream) {
+    if (data_dim <= 0 || hidden <= 0 || (extra != 1 && extra != 3) || batch <= 0 || !p_dev || !z_dev || !e_dev || !k_dev) return RNDE_ERR_ARG;
+    const int D = data_dim + extra;
+    const size_t smem = sizeof(float) * ((size_t)(2 * D + data_dim) * CSQ_TEST_NP + (size_t)csq_tile_floats(data_dim, hidden, CSQ_TEST_NP));
+    if (smem > 200 * 1024) return RNDE_ERR_UNSUPPORTED;
+    if (cudaFuncSetAttribute(csq_rhs_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return RNDE_ERR_CUDA; }
+    csq_rhs_test_kernel<<<(batch + CSQ_TEST_NP - 1) / CSQ_TEST_NP, CSQ_TEST_NT, smem, (cudaStream_t)stream>>>(p_dev, data_dim, hidden, extra, batch, t, z_dev, e_dev, k_dev);
     return cudaGetLastError() == cudaSuccess ? RNDE_OK : RNDE_ERR_CUDA;
 }
 extern "C" int rnde_test_pow(const float* x_dev, float e, float* y_dev, float* l10_dev, int64_t n, void* stream) {

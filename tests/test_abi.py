@@ -70,6 +70,14 @@ def test_no_cpu_fallback():
         L.require_device()
 
 
+def test_test_hooks_validate_arguments_before_touching_the_device():
+    from regneuralde.jl_b200 import _lib as L
+    lib = L.lib()
+    assert lib.rnde_test_csq_rhs(43, 100, 2, 8, None, None, None, C.c_float(0.0), None, None) == L.ERR_ARG      # extra must be 1 or 3
+    assert lib.rnde_test_csq_rhs(43, 100, 1, 8, None, None, None, C.c_float(0.0), None, None) == L.ERR_ARG      # null buffers
+    assert lib.rnde_test_unary_bits(7, 0, 1, None, None) == L.ERR_ARG
+
+
 def test_product_never_imports_oracle():
     pkg = ROOT / "regneuralde"
     for f in pkg.rglob("*.py"):
