@@ -89,7 +89,7 @@ typedef struct {
     /* arith = 1 (FIXED24): the layer products of the 2-layer field are exact truncated fixed-point products -- the
      * arithmetic of the tensor-core forward stepper (csrc/fwd4x_kernel.cuh); see fixed24_* below. */
     int arith;
-    /* FFJORD field (csq_extra = 1 or 3; SURVEY.md 8f row N4, FORWARD ONLY -- no kernel exists for this row yet): the state
+    /* FFJORD field (csq_extra = 1 or 3; forward here, reverse sweep in rnde_oracle_bwd.inc): the state
      * holds D - csq_extra data rows z plus [delta_logp (; ||f||^2; ||e^T J||^2)] (src/models/ffjord.jl:53-66); the field is
      * MLPDynamics(D - csq_extra, H) of three ConcatSquash layers with softplus between (experiments/ffjord_tabular.jl:47-105),
      * evaluated together with e^T J for the fixed Hutchinson noise csq_noise ((D - csq_extra) x B, REAL, column-major). */

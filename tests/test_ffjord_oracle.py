@@ -176,8 +176,6 @@ def test_c_solve_matches_the_torch_functors():
         if regf:
             # EEst cancels O(1) stage values down to O(tol): the two summation orders differ by ~1e-16 / 1.4e-8 relative per term
             assert np.allclose(c.saveval, r.saveval.numpy(), rtol=1e-3, atol=1e-14)
-        with pytest.raises(Exception):
-            o.backward(np.zeros((D + extra, B)), np.zeros(len(c.saveval) or 1))      # forward only
 
 
 def test_c_float32_solve_is_deterministic_and_close():
@@ -193,3 +191,37 @@ def test_c_float32_solve_is_deterministic_and_close():
     assert runs[0].nf == runs[1].nf and np.array_equal(runs[0].u.view(np.uint32), runs[1].u.view(np.uint32))
     r = F.ffjord(torch.from_numpy(x).double(), torch.from_numpy(p).double(), torch.from_numpy(e).double(), D=D, H=H, regularized_functor=False)
     assert np.abs(runs[0].u - r.sol.u.numpy()).max() <= 5e-5 * np.abs(r.sol.u.numpy()).max()
+
+
+@pytest.mark.parametrize("extra,regf", [(1, True), (3, False), (1, False)])
+def test_c_adjoint_matches_autograd(extra, regf):
+    """The hand-written reverse sweep through csq_column + the Tsit5 adjoint (rnde_oracle_bwd.inc) against torch autograd
+    through the whole solve, Float64: gradients with respect to the parameters and the data."""
+    from oracle import orc
+    D, H, B = 4, 7, 3
+    p, x, e = setup(D, H, B, seed=31 + extra)
+    rng = np.random.default_rng(5)
+    pg, xg = p.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    r = F.ffjord(xg, pg, e, D=D, H=H, regularized_functor=regf, regularize=(extra == 3))
+    w = rng.standard_normal((D + extra, B))
+    ws = rng.standard_normal(r.sol.naccept + 1)
+    loss = (r.sol.u * torch.from_numpy(w)).sum()
+    if regf:
+        loss = loss + (r.saveval * torch.from_numpy(ws)).sum()
+    gp, gx = torch.autograd.grad(loss, (pg, xg))
+    o = _c_oracle(D, H, B, extra, e.numpy(), True, reg_kind=orc.REG_ERR_DT if regf else orc.REG_NONE, abstol=1.4e-8, reltol=1.4e-8)
+    c = o.forward(np.concatenate([x.numpy(), np.zeros((extra, B))], 0), p.numpy())
+    assert (c.nf, c.naccept) == (r.nfe, r.sol.naccept)
+    dp, dx, _, _ = o.backward(w, ws)
+    rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()
+    # the regulariser's cotangents are O(1/tol): its gradient carries the 1e-16/1.4e-8 noise of EEst (see the solve test)
+    tol = 1e-6 if regf else 1e-12         # observed 2.6e-8 / 5e-14
+    assert rel(dp, gp.numpy()) <= tol, rel(dp, gp.numpy())
+    assert rel(dx[:D], gx.numpy()) <= tol, rel(dx[:D], gx.numpy())
+    if not regf and extra == 1:
+        # Float32 build: canonical forward, cotangents in Float64 over it (the yardstick GPU adjoints are judged by) and in Float32
+        o32 = _c_oracle(D, H, B, extra, e.numpy().astype(np.float32), False, abstol=1.4e-8, reltol=1.4e-8)
+        o32.forward(np.concatenate([x.numpy(), np.zeros((extra, B))], 0).astype(np.float32), p.numpy().astype(np.float32))
+        dp_hi, dx_hi, _, _ = o32.backward(w.astype(np.float32), ws.astype(np.float32), hi=True)
+        dp_32, _, _, _ = o32.backward(w.astype(np.float32), ws.astype(np.float32))
+        assert rel(dp_hi, gp.numpy()) <= 1e-4 and rel(dx_hi[:D], gx.numpy()) <= 1e-4 and rel(dp_32, dp_hi) <= 1e-4
