@@ -91,7 +91,7 @@ class OracleConfig:
     widths: tuple | None = None
     acts: tuple | None = None
     pre_act: int = 0
-    # FFJORD field (forward only): csq_extra = 1 or 3 augmented rows (D counts them), csq_noise = the Hutchinson noise (D - extra, B)
+    # FFJORD field: csq_extra = 1 or 3 augmented rows (D counts them), csq_noise = the Hutchinson noise (D - extra, B)
     csq_extra: int = 0
     csq_noise: np.ndarray | None = None
     arith: int = 0          # 1 = FIXED24 exact fixed-point layer products (rnde_oracle.c), the tensor-core forward stepper's arithmetic
