@@ -32,6 +32,11 @@ def _worker(rank, world, port, q):
     g = torch.full((5,), float(rank + 1))
     average_gradients_([g], world)
     t = max_over_ranks(float(rank + 3))
+    # rendezvous of the reference-exact mode: every rank contributes the 64-byte IPC handle of its exchange buffer and
+    # receives all of them in rank order (rnde_dist_export -> exchange_ipc_handles -> rnde_dist_import)
+    from regneuralde.jl_b200.parallel import exchange_ipc_handles
+    hs = exchange_ipc_handles(bytes([rank + 1]) * 64, world)
+    assert [h[0] for h in hs] == list(range(1, world + 1)) and all(len(h) == 64 for h in hs)
     q.put((rank, lo, hi, owned.tolist(), g.tolist(), t))
     dist.destroy_process_group()
 
