@@ -112,8 +112,7 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
-        build()
+    build()          # no-op when fresh; rebuilds after any edit of csrc/ or include/ (falls back to the prebuilt library without nvcc)
     L = C.CDLL(str(LIB_PATH))
     vp, fp, ip = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)
     L.rnde_version.restype = C.c_int

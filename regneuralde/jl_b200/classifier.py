@@ -74,8 +74,9 @@ class ClassifierNODE:
         reg_kind = (ERROR_ESTIMATE if func is None else func).kind if node.regularize else L.REG_NONE
         hd = node._handle(B, reg_kind, True)
         lib = hd.lib
-        if tspan is not None:
-            hd.check(lib.rnde_set_tspan(hd.h, float(tspan[0]), float(tspan[1])), "rnde_set_tspan")
+        # a per-call tspan must not outlive the call: without the keyword the node's own tspan applies (neural_ode.jl:53,58)
+        t0, t1 = node.tspan if tspan is None else (float(tspan[0]), float(tspan[1]))
+        hd.check(lib.rnde_set_tspan(hd.h, t0, t1), "rnde_set_tspan")
         ws = self._workspace(B, dev, hd.cfg.tape_capacity)
         xbuf = colmajor(x.to(torch.float32))
         ybuf = colmajor(y_onehot.to(torch.float32))

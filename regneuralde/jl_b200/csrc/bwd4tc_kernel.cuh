@@ -6,11 +6,17 @@
 // columns, hidden dimension 100):
 //   GEMM 1  hbar_partial[100 x 16] = W2[rows, :]^T delta2[rows x 16]      M=128 N=16 K=196(208)   13 k-steps
 //   GEMM 2  zbar[196 x 16]         = W1[:, rows]^T delta1[100 x 16]       2 x (M=128 N=16) K=100(112)  7 k-steps
-// as tcgen05.mma.kind::f16 on BF16 operands with FP32 accumulation.  Float32 accuracy is approached by the two-term
-// split x = hi + lo (hi = bf16(x), lo = bf16(x - hi), 16 mantissa bits together) and the three products
-// hi*hi + hi*lo + lo*hi: relative error ~1e-5 per dot product, an order of magnitude inside the gradient bar.
-// (The 3xTF32 split of the weight-gradient kernel would need 8 bytes per weight; the CTA's 39 200 weights only fit
-// shared memory at 4.)  Weights are split once per launch into the UMMA K-major core-matrix layout (A operands); the
+// as tcgen05.mma.kind::f16 on BF16 operands with FP32 accumulation.  The two operands are split differently, because
+// their truncation errors act differently on the regulariser gradient (the error-estimate
+// cotangents are O(10) on the seven stages of a step and cancel to O(1e-2); measured with oracle/ emulation):
+//   * the COTANGENT (B operand) is split into three BF16 terms hi + mid + lo = the Float32 value exactly: its truncation
+//     error differs from stage to stage, so any of it survives the cancellation (two terms = 16 bits made the sweep 5x
+//     noisier than a CPU Float32 adjoint);
+//   * the WEIGHTS (A operand) keep two terms (16 bits): the same perturbed weights act on every stage, which perturbs the
+//     small result relatively, not the large terms absolutely (truncating weights to 12 bits changes nothing measurable).
+// Products per k-step: A_hi x [B_hi | B_mid | B_lo] (N = 48) and A_lo x [B_hi | B_mid] (N = 32); the dropped A_lo x B_lo is
+// 2^-26 relative.  hi/mid/lo products accumulate in separate TMEM columns and are added small-to-large in the epilogue.
+// (A third weight term or the 3xTF32 split of the weight-gradient kernel would not fit: 39 200 weights per CTA at 4 bytes.)  Weights are split once per launch into the UMMA K-major core-matrix layout (A operands); the
 // cotangents are split and written as B operands by the threads that own them; one elected thread issues the MMAs;
 // results come back with tcgen05.ld (TMEM lane = output row).  The exchange of the hidden cotangent between the four
 // CTAs of the cluster (st.async + mbarrier), the tape traffic and all per-step cotangent arithmetic are those of
@@ -32,7 +38,7 @@ struct B4TLayout {          // byte offsets
     int sbb1, sbb2;         // the same for the B operands, whose K-adjacent core matrices are B4T_LBO_B = 144 bytes apart
                             // (16 bytes of padding: the owners' 4-byte stores would otherwise be 8-way bank conflicted)
     int a2_groups, a1_groups;
-    int oA2hi, oA2lo, oA1hi, oA1lo, oB1hi, oB1lo, oB2hi, oB2lo, oPart, oD1, oZb, oBar, total;
+    int oA2hi, oA2lo, oA1hi, oA1lo, oB1, oB2, oPart, oD1, oZb, oBar, total;   // oB*: [hi | mid | lo], 2 * sbb* bytes each
 };
 
 __host__ __device__ inline B4TLayout make_b4t_layout(int D, int H) {
@@ -47,13 +53,12 @@ __host__ __device__ inline B4TLayout make_b4t_layout(int D, int H) {
     L.oA2lo = o; o += L.a2_groups * L.sbo2;
     L.oA1hi = o; o += L.a1_groups * L.sbo1;
     L.oA1lo = o; o += L.a1_groups * L.sbo1;
-    L.oB1hi = o; o += 2 * L.sbb1;
-    L.oB1lo = o; o += 2 * L.sbb1;
-    L.oB2hi = o; o += 2 * L.sbb2;
-    L.oB2lo = o; o += 2 * L.sbb2;
+    L.oB1 = o; o += 6 * L.sbb1;
     L.oPart = o; o += V2_G * L.HS * V2_NP * 4;
     L.oD1 = o; o += round_up(H, 4) * V2_NP * 4;
-    L.oZb = o; o += L.R * V2_NP * 4;
+    // the B operand of GEMM 2 lives in the delta2 / transposition tile: written after the tile's bulk store has been read,
+    // consumed by GEMM 2 before the transposition overwrites it
+    L.oZb = o; L.oB2 = o; o += (L.R * V2_NP * 4 > 6 * L.sbb2) ? L.R * V2_NP * 4 : 6 * L.sbb2;
     L.oBar = o; o += 64;
     L.total = o;
     return L;
@@ -78,6 +83,13 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t da, uint64
 __device__ __forceinline__ void bf16_split(const float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
     hi = __float2bfloat16_rn(x);
     lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+// x = hi + mid + lo exactly (8 + 8 + 8 significant bits; both remainders are exact Float32 subtractions)
+__device__ __forceinline__ void bf16_split3(const float x, __nv_bfloat16& hi, __nv_bfloat16& mid, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(hi);
+    mid = __float2bfloat16_rn(r1);
+    lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     uint32_t r[16];
@@ -142,8 +154,8 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
         mbar_init(barP, 1); mbar_init(barH, 1); mbar_init(barM1, 4); mbar_init(barM2, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {        // TMEM: 256 columns = 2 GEMMs x 4 issuers x (16 hi*hi+lo*hi | 16 hi*lo) FP32 accumulator columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256) : "memory");
+    if (warp == 0) {        // TMEM: 2 GEMMs x 4 issuers x (16 A*B_hi | 16 A*B_mid | 16 A_hi*B_lo) FP32 accumulator columns = 384 of 512
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -152,16 +164,16 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     // instruction descriptor: D = F32, A = B = BF16, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
-    const uint32_t idesc16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t idesc32 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc48 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(48 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     // Four threads (lane 0 of warps 0-3) issue the MMAs of a GEMM side by side, each into its own accumulator: the tiles
-    // are tiny (M128 N16/32 K16) and a single thread issues one only every ~70 cycles.  Per k-step: A_hi x [B_hi | B_lo]
-    // (N = 32: the lo half of a B operand is stored right behind the hi half) and A_lo x B_hi (N = 16, same first 16 columns).
+    // are tiny (M128 N32/48 K16) and a single thread issues one only every ~70 cycles.  Per k-step: A_hi x [B_hi | B_mid | B_lo]
+    // (N = 48: the three terms of a B operand are stored back to back) and A_lo x [B_hi | B_mid] (N = 32, the same first 32 columns).
     const int issuer = ((tid & 31) == 0 && warp < 4) ? warp : -1;
     const uint64_t dA1hi = umma_desc(sbase + L.oA1hi, 128, L.sbo1), dA1lo = umma_desc(sbase + L.oA1lo, 128, L.sbo1);
-    const uint64_t dB1 = umma_desc(sbase + L.oB1hi, B4T_LBO_B, L.sbb1);
+    const uint64_t dB1 = umma_desc(sbase + L.oB1, B4T_LBO_B, L.sbb1);
     const uint64_t dA2hi = umma_desc(sbase + L.oA2hi, 128, L.sbo2), dA2lo = umma_desc(sbase + L.oA2lo, 128, L.sbo2);
-    const uint64_t dB2 = umma_desc(sbase + L.oB2hi, B4T_LBO_B, L.sbb2);
+    const uint64_t dB2 = umma_desc(sbase + L.oB2, B4T_LBO_B, L.sbb2);
     const int nk1 = L.K1 / 16, nk2 = L.K2 / 16;
     // GEMM 1: issuer w takes k-steps [k1lo, k1hi); GEMM 2: issuer w takes M tile w >> 1 and half (w & 1) of the k-steps
     const int k1lo = issuer >= 0 ? nk1 * issuer / 4 : 0, k1hi = issuer >= 0 ? nk1 * (issuer + 1) / 4 : 0;
@@ -244,20 +256,22 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
                 for (int i = 0; i < 4; i += 2) {
                     const int k = crow0 + i;
                     const int off = (n >> 3) * L.sbb1 + (k >> 3) * B4T_LBO_B + (n & 7) * 16 + (k & 7) * 2;
-                    __nv_bfloat16 h2[2], l2[2];
-                    bf16_split(d2v[i][j], h2[0], l2[0]);
-                    bf16_split(d2v[i + 1][j], h2[1], l2[1]);
+                    __nv_bfloat16 h2[2], m2[2], l2[2];
+                    bf16_split3(d2v[i][j], h2[0], m2[0], l2[0]);
+                    bf16_split3(d2v[i + 1][j], h2[1], m2[1], l2[1]);
                     if (i + 1 < cvalid) {       // rows past cvalid belong to the next K-block's tiles: never touch them
-                        *reinterpret_cast<uint32_t*>(sb + L.oB1hi + off) = *reinterpret_cast<const uint32_t*>(h2);
-                        *reinterpret_cast<uint32_t*>(sb + L.oB1lo + off) = *reinterpret_cast<const uint32_t*>(l2);
+                        *reinterpret_cast<uint32_t*>(sb + L.oB1 + off) = *reinterpret_cast<const uint32_t*>(h2);
+                        *reinterpret_cast<uint32_t*>(sb + L.oB1 + 2 * L.sbb1 + off) = *reinterpret_cast<const uint32_t*>(m2);
+                        *reinterpret_cast<uint32_t*>(sb + L.oB1 + 4 * L.sbb1 + off) = *reinterpret_cast<const uint32_t*>(l2);
                     } else if (i < cvalid) {
-                        *reinterpret_cast<__nv_bfloat16*>(sb + L.oB1hi + off) = h2[0];
-                        *reinterpret_cast<__nv_bfloat16*>(sb + L.oB1lo + off) = l2[0];
+                        *reinterpret_cast<__nv_bfloat16*>(sb + L.oB1 + off) = h2[0];
+                        *reinterpret_cast<__nv_bfloat16*>(sb + L.oB1 + 2 * L.sbb1 + off) = m2[0];
+                        *reinterpret_cast<__nv_bfloat16*>(sb + L.oB1 + 4 * L.sbb1 + off) = l2[0];
                     }
                 }
             }
 #else
-            if (d2v[0][0] == 1234.5f) sb[L.oB1hi] = 1;
+            if (d2v[0][0] == 1234.5f) sb[L.oB1] = 1;
 #endif
         }
 #ifndef RNDE_EXP_NOFENCE
@@ -271,11 +285,11 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
         TLB(1);
         if (issuer >= 0) {     // GEMM 1 (a K quarter per issuer; descriptors advance by 2 core matrices = 256 bytes per k-step)
             tc_fence_after();
-            const uint32_t dcol = tmem_base + 32 * issuer;
+            const uint32_t dcol = tmem_base + 48 * issuer;
             for (int ks = k1lo; ks < k1hi; ++ks) {
                 const uint64_t adv = (uint64_t)(ks * 16), advb = (uint64_t)(ks * (2 * B4T_LBO_B / 16));
-                tc_mma_bf16(dcol, dA1hi + adv, dB1 + advb, idesc32, ks == k1lo ? 0u : 1u);
-                tc_mma_bf16(dcol, dA1lo + adv, dB1 + advb, idesc16, 1u);
+                tc_mma_bf16(dcol, dA1hi + adv, dB1 + advb, idesc48, ks == k1lo ? 0u : 1u);
+                tc_mma_bf16(dcol, dA1lo + adv, dB1 + advb, idesc32, 1u);
             }
             tc_commit(barM1);
         }
@@ -287,14 +301,15 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
             float v[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = 0.f;
-            for (int part = 0; part < 8; ++part) {      // 4 issuers x (hi*hi + lo*hi | hi*lo)
-                float t[16];
-                tmem_ld16(tmem_base + tlane + 16 * part, t);
-                if (nk1 * (part >> 1) / 4 < nk1 * ((part >> 1) + 1) / 4) {
+            for (int term = 2; term >= 0; --term)       // lo, mid, hi: the small terms are added first
+                for (int is = 0; is < 4; ++is) {        // 4 issuers (k-step quarters)
+                    float t[16];
+                    tmem_ld16(tmem_base + tlane + 48 * is + 16 * term, t);
+                    if (nk1 * is / 4 < nk1 * (is + 1) / 4) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] += t[j];
+                        for (int j = 0; j < 16; ++j) v[j] += t[j];
+                    }
                 }
-            }
             const int m = quad * 32 + lane;
             if (m < H) {
                 const int d = m / HS, ml = m - d * HS;
@@ -335,6 +350,7 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (tid == 0) bulk_wait_read();      // the delta2 tile in sZb has left: sZb becomes GEMM 2's B operand, then the transposition tile
         __syncthreads();
         if (tid == 0 && HSloc > 0) {      // this CTA's slice of delta1 -> tape
             bulk_store(P.tapeD1 + (((size_t)rec * P.Q + q) * H + rank * HS) * NP, sD1 + rank * HS * NP, (uint32_t)(HSloc * NP * 4));
@@ -342,31 +358,33 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
         }
         mbar_wait(barH, ev_parity);
         TLB(5);
-        // delta1 (H x 16, FP32) -> split B operand of GEMM 2: one 16-byte chunk = 8 consecutive hidden units of one column
+        // delta1 (H x 16, FP32) -> split B operand of GEMM 2: one 16-byte chunk = 8 consecutive hidden units of one column.
+        // The operand overlays sZb, whose delta2 tile was handed to the bulk-store engine before GEMM 1: thread 0 has waited
+        // for that read (below, before the barrier that precedes this loop).
         for (int ch = tid; ch < NP * (L.K2 / 8); ch += NT) {
             const int n = ch % NP, k0 = (ch / NP) * 8;
-            __nv_bfloat16 h8[8], l8[8];
+            __nv_bfloat16 h8[8], m8[8], l8[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float x = (k0 + i < H) ? sD1[(k0 + i) * NP + n] : 0.f;
-                bf16_split(x, h8[i], l8[i]);
+                bf16_split3(x, h8[i], m8[i], l8[i]);
             }
             const int off = (n >> 3) * L.sbb2 + (k0 >> 3) * B4T_LBO_B + (n & 7) * 16;
-            *reinterpret_cast<uint4*>(sb + L.oB2hi + off) = *reinterpret_cast<const uint4*>(h8);
-            *reinterpret_cast<uint4*>(sb + L.oB2lo + off) = *reinterpret_cast<const uint4*>(l8);
+            *reinterpret_cast<uint4*>(sb + L.oB2 + off) = *reinterpret_cast<const uint4*>(h8);
+            *reinterpret_cast<uint4*>(sb + L.oB2 + 2 * L.sbb2 + off) = *reinterpret_cast<const uint4*>(m8);
+            *reinterpret_cast<uint4*>(sb + L.oB2 + 4 * L.sbb2 + off) = *reinterpret_cast<const uint4*>(l8);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if (tid == 0) bulk_wait_read();      // sZb (delta2 tile) is reused by the transposition below, sD1 by the next evaluation
         __syncthreads();
         TLB(6);
         if (issuer >= 0) {     // GEMM 2: M tile issuer >> 1, half of the k-steps each
             tc_fence_after();
-            const uint32_t dcol = tmem_base + 128 + 32 * issuer;
+            const uint32_t dcol = tmem_base + 192 + 48 * issuer;
             const uint64_t aoff = (uint64_t)(((issuer >> 1) * 16 * L.sbo2) >> 4);
             for (int ks = k2lo; ks < k2hi; ++ks) {
                 const uint64_t adv = (uint64_t)(ks * 16), advb = (uint64_t)(ks * (2 * B4T_LBO_B / 16));
-                tc_mma_bf16(dcol, dA2hi + aoff + adv, dB2 + advb, idesc32, ks == k2lo ? 0u : 1u);
-                tc_mma_bf16(dcol, dA2lo + aoff + adv, dB2 + advb, idesc16, 1u);
+                tc_mma_bf16(dcol, dA2hi + aoff + adv, dB2 + advb, idesc48, ks == k2lo ? 0u : 1u);
+                tc_mma_bf16(dcol, dA2lo + aoff + adv, dB2 + advb, idesc32, 1u);
             }
             tc_commit(barM2);
         }
@@ -384,15 +402,16 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
             float v[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = 0.f;
-            for (int part = 0; part < 4; ++part) {      // 2 issuers of this M tile x (hi*hi + lo*hi | hi*lo)
-                const bool used = (part >> 1) ? (nk2 > (nk2 + 1) / 2) : true;
-                float t[16];
-                tmem_ld16(tmem_base + tlane + 128 + (warp < 4 ? 0u : 64u) + 16 * part, t);
-                if (used) {
+            for (int term = 2; term >= 0; --term)       // lo, mid, hi
+                for (int is = 0; is < 2; ++is) {        // the 2 issuers of this M tile (k-step halves)
+                    const bool used = is ? (nk2 > (nk2 + 1) / 2) : true;
+                    float t[16];
+                    tmem_ld16(tmem_base + tlane + 192 + (warp < 4 ? 0u : 96u) + 48 * is + 16 * term, t);
+                    if (used) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] += t[j];
+                        for (int j = 0; j < 16; ++j) v[j] += t[j];
+                    }
                 }
-            }
             if (row < R) {
 #pragma unroll
                 for (int c4 = 0; c4 < 4; ++c4)
@@ -609,7 +628,7 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
     }
     cluster_sync_all();
 }

@@ -120,8 +120,12 @@ __device__ __forceinline__ void xrank_barrier(const KParams& P, unsigned seq) {
                 st_release_sys(reinterpret_cast<unsigned*>(P.peers[r]) + P.flag_off + P.rank, seq);
         }
         const unsigned* mine = reinterpret_cast<const unsigned*>(P.peers[P.rank]) + P.flag_off;
-        for (int r = 0; r < P.nranks; ++r)
-            while ((int)(ld_acquire_sys(mine + r) - seq) < 0) { }
+        // bounded like ar_sum_kernel's wait: a rank that never launched (host exception, handle mismatch) must not hang
+        // the persistent kernels of all the others for ever -- tens of seconds of polling, then the launch fails with a trap
+        for (int r = 0; r < P.nranks; ++r) {
+            long long spins = 0;
+            while ((int)(ld_acquire_sys(mine + r) - seq) < 0) { if (++spins > (1ll << 25)) __trap(); }
+        }
     }
     __syncthreads();
 }

@@ -44,10 +44,15 @@ __global__ void __launch_bounds__(256) head_col_kernel(int D, int B, int C, cons
     }
     if (lane == 0) loss_ws[j] = lj;
     // du[:, j] = W3^T g
-    for (int d = lane; d < D; d += 32) {
+    // warp-uniform trip count: every lane takes part in the shuffles of the tail iteration too
+    for (int d0 = 0; d0 < D; d0 += 32) {
+        const int d = d0 + lane;
         float s = 0.f;
-        for (int c = 0; c < C; ++c) s = fmaf(__ldg(W3 + (size_t)C * d + c), __shfl_sync(0xffffffffu, g, c), s);
-        du[(size_t)D * j + d] = s;
+        for (int c = 0; c < C; ++c) {
+            const float gc = __shfl_sync(0xffffffffu, g, c);
+            if (d < D) s = fmaf(__ldg(W3 + (size_t)C * d + c), gc, s);
+        }
+        if (d < D) du[(size_t)D * j + d] = s;
     }
 }
 

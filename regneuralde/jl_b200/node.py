@@ -23,6 +23,7 @@ import math
 from dataclasses import dataclass
 from typing import Optional, Sequence
 
+import numpy as np
 import torch
 
 from . import _lib as L
@@ -204,7 +205,7 @@ class _Solve(torch.autograd.Function):
         cfg = hd.cfg
         D, B = cfg.state_dim, cfg.batch
         u = torch.empty(D * B, device=xbuf.device, dtype=torch.float32)
-        sv = torch.zeros(cfg.tape_capacity + 1 if cfg.tape_capacity > 0 else 257, device=xbuf.device, dtype=torch.float32)
+        sv = torch.zeros(cfg.tape_capacity + 1, device=xbuf.device, dtype=torch.float32)
         st = L.Stats()
         rc = hd.lib.rnde_forward(hd.h, xbuf.data_ptr(), p.data_ptr(), u.data_ptr(), sv.data_ptr(), C.byref(st), _stream_ptr())
         node.last_stats = st
@@ -294,7 +295,8 @@ class TrackedNeuralODE:
         self.time_dep, self.regularize = bool(time_dep), bool(regularize)
         self.solver = solver
         self.reltol, self.abstol = float(reltol), float(abstol)
-        self.maxiters, self.tape_capacity = maxiters, tape_capacity
+        # normalised once: every buffer below is sized tape_capacity + 1 (the library's default for <= 0 is 256)
+        self.maxiters, self.tape_capacity = maxiters, (int(tape_capacity) if int(tape_capacity) > 0 else 256)
         self.kernel_variant, self.kblock = kernel_variant, kblock
         # data parallel: DIST_EXACT shares the step sequence of the global batched solve across ranks (x holds this
         # rank's columns, all shards equal); DIST_INDEPENDENT / DIST_SINGLE integrate the local columns on their own
@@ -390,8 +392,9 @@ class TrackedNeuralODE:
         tcpu = (C.c_float * max(n, 1))()
         dcpu = (C.c_float * max(n, 1))()
         hd.check(hd.lib.rnde_get_steps(hd.h, tcpu, dcpu, None, None, n), "rnde_get_steps")
-        ts = [t0] + [tcpu[i] + dcpu[i] for i in range(n)]
-        return res, nfe, SavedValues(torch.tensor(ts, dtype=torch.float32), saveval)
+        # Float32 arithmetic like the stepper's own t + dt (a Float64 sum could differ from it in the last bit)
+        ts = np.concatenate([np.asarray([t0], np.float32), np.asarray(tcpu[:n], np.float32) + np.asarray(dcpu[:n], np.float32)])
+        return res, nfe, SavedValues(torch.from_numpy(ts), saveval)
 
     def steps(self, B: int, reg_kind: int = L.REG_NONE, need_backward: bool = False):
         """(t, dt, EEst, eigen_est) of every accepted step of the last solve on that handle."""
