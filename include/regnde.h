@@ -110,6 +110,12 @@ typedef struct rnde_config {
     int32_t layer_width[8];
     int32_t layer_act[8];
     int32_t arith;            /* RNDE_ARITH_*: canonical arithmetic of the layer products (2-layer fields) */
+    /* FFJORD field (src/models/ffjord.jl:53-66 over experiments/ffjord_tabular.jl:47-105): csq_extra = 1 or 3 makes the state
+     * [z; delta_logp (; ||f||^2; ||e^T J||^2)] with state_dim COUNTING the extra rows, the field MLPDynamics(state_dim -
+     * csq_extra, hidden_dim) of three ConcatSquash layers, evaluated with e^T J for the noise given by rnde_set_noise.
+     * Forward solves only so far (need_backward must be 0). */
+    int32_t csq_extra;
+    int32_t reserved0;
 } rnde_config;
 
 typedef struct rnde_stats {
@@ -166,6 +172,10 @@ int rnde_backward(rnde_handle* h, const float* du_dev, const float* dsaveval_dev
  * D x B) may be NULL.  Backward: dusave_dev has the shape of usave_dev, du_dev (cotangent of the final state) may
  * be NULL. */
 int rnde_set_saveat(rnde_handle* h, const float* saveat_host, int32_t n);
+/* FFJORD handles (rnde_config.csq_extra > 0): the Hutchinson noise e of the next solves, (state_dim - csq_extra) x batch,
+ * column-major, caller-owned device memory that must stay valid until the solve has run (the `e` argument of the
+ * TrackedFFJORD functors, src/models/ffjord.jl:68-72). */
+int rnde_set_noise(rnde_handle* h, const float* e_dev);
 int rnde_forward_saveat(rnde_handle* h, const float* x_dev, const float* p_dev, float* u_out_dev, float* usave_dev, float* saveval_dev,
                         rnde_stats* stats_host, void* stream);
 int rnde_backward_saveat(rnde_handle* h, const float* du_dev, const float* dusave_dev, const float* dsaveval_dev, float* dp_dev,

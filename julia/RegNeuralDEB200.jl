@@ -28,6 +28,7 @@ struct RndeConfig
     max_saveat::Int32; n_layers::Int32
     global_batch::Int64
     pre_act::Int32; layer_width::NTuple{8,Int32}; layer_act::NTuple{8,Int32}; arith::Int32
+    csq_extra::Int32; reserved0::Int32
 end
 
 mutable struct RndeStats
@@ -79,7 +80,7 @@ end
 function handle!(n::TrackedNeuralODE, D, H, B, reg_kind, need_backward, layers)
     get!(n.handles, (B, reg_kind, need_backward)) do
         cfg = Ref(RndeConfig(sizeof(RndeConfig), D, H, B, _act(layers[1]), _act(layers[2]), 1, 0, n.alg, reg_kind, 0, 256,
-                             need_backward, 0, 0, 0, 1, n.tspan[1], n.tspan[2], n.abstol, n.reltol, 0f0, 0, 0, B, 0, ntuple(_ -> Int32(0), 8), ntuple(_ -> Int32(0), 8), 0))
+                             need_backward, 0, 0, 0, 1, n.tspan[1], n.tspan[2], n.abstol, n.reltol, 0f0, 0, 0, B, 0, ntuple(_ -> Int32(0), 8), ntuple(_ -> Int32(0), 8), 0, 0, 0))
         h = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:rnde_create, LIB), Cint, (Ref{RndeConfig}, Ref{Ptr{Cvoid}}), cfg, h))
         h[]
@@ -157,7 +158,7 @@ function chain_config(n, D, B, reg_kind, need_backward)
     w = ntuple(i -> i <= length(ds) ? Int32(size(ds[i].W, 1)) : Int32(0), 8)
     a = ntuple(i -> i <= length(ds) ? _act(ds[i]) : Int32(0), 8)
     RndeConfig(sizeof(RndeConfig), D, 0, B, 0, 0, 0, 0, n.alg, reg_kind, 0, 256, need_backward, 0, 0, 0, 1,
-               n.tspan[1], n.tspan[2], n.abstol, n.reltol, 0f0, 64 * cld(length(n.saveat), 64), length(ds), B, pre, w, a, 0)
+               n.tspan[1], n.tspan[2], n.abstol, n.reltol, 0f0, 64 * cld(length(n.saveat), 64), length(ds), B, pre, w, a, 0, 0, 0)
 end
 
 function (n::TrackedNeuralODEMulti{R})(x, p = n.p; func = REG_ERR_DT, tspan = nothing, saveat = nothing) where {R}

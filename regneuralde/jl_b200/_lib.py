@@ -38,7 +38,7 @@ EXPORTS = [
     "rnde_num_params", "rnde_default_kblock", "rnde_kernel_variant", "rnde_launch_count", "rnde_set_tspan",
     "rnde_forward", "rnde_backward", "rnde_forward_host", "rnde_backward_host", "rnde_head_loss_grad", "rnde_get_steps",
     "rnde_opt_update", "rnde_test_tanh", "rnde_test_tanh_bits", "rnde_test_pow", "rnde_test_unary_bits", "rnde_test_csq_rhs", "rnde_debug_timeline", "rnde_dist_export", "rnde_dist_import",
-    "rnde_set_saveat", "rnde_forward_saveat", "rnde_backward_saveat",
+    "rnde_set_saveat", "rnde_forward_saveat", "rnde_backward_saveat", "rnde_set_noise",
     "rnde_gru_num_params", "rnde_gru_create", "rnde_gru_destroy", "rnde_gru_last_error", "rnde_gru_forward", "rnde_gru_backward",
     "rnde_gru_launch_count", "rnde_reg_agg", "rnde_last_stats", "rnde_allreduce_grads",
 ]
@@ -55,6 +55,7 @@ class Config(C.Structure):
         ("max_saveat", C.c_int32), ("n_layers", C.c_int32),
         ("global_batch", C.c_int64),
         ("pre_act", C.c_int32), ("layer_width", C.c_int32 * 8), ("layer_act", C.c_int32 * 8), ("arith", C.c_int32),
+        ("csq_extra", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -147,6 +148,7 @@ def lib() -> C.CDLL:
     L.rnde_dist_export.argtypes = [vp, vp]
     L.rnde_dist_import.argtypes = [vp, vp, C.c_int32]
     L.rnde_set_saveat.argtypes = [vp, vp, C.c_int32]
+    L.rnde_set_noise.argtypes = [vp, vp]
     L.rnde_last_stats.argtypes = [vp, C.POINTER(Stats)]
     L.rnde_allreduce_grads.argtypes = [vp, vp, C.c_int64, vp]
     L.rnde_reg_agg.argtypes = [vp, C.c_int32, C.c_float, C.c_float, vp, vp, vp, vp]

@@ -26,6 +26,7 @@
 #pragma once
 #include "common.cuh"
 #include "chain.cuh"
+#include "csq.cuh"
 
 namespace rnde {
 
@@ -188,7 +189,8 @@ __device__ __forceinline__ float saved_value(int kind, float EEst, float eig, fl
     }
 }
 
-template <int G, int NP, int TM, bool WS, int NT>
+// FIELD: 0 = the 2-layer time-concatenated field or a chain field (runtime P.n_layers); 1 = the FFJORD field of csq.cuh
+template <int G, int NP, int TM, bool WS, int NT, int FIELD = 0>
 __global__ void __launch_bounds__(NT, 1) fwd_kernel(const KParams P) {
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -229,7 +231,7 @@ __global__ void __launch_bounds__(NT, 1) fwd_kernel(const KParams P) {
 
     // ---- stage weights / biases / initial state into shared memory -------
     const bool chain = (G == 1) && P.n_layers > 0;
-    if constexpr (WS) if (!chain) {
+    if constexpr (WS && FIELD == 0) if (!chain) {
         for (int e = tid; e < R * HP; e += NT) {
             const int k = e / HP, m = e - k * HP;
             sW1[e] = (k < Rloc && m < H) ? __ldg(gW1 + (size_t)(r0 + k) * H + m) : 0.f;
@@ -239,7 +241,15 @@ __global__ void __launch_bounds__(NT, 1) fwd_kernel(const KParams P) {
             sW2[e] = (m < Rloc) ? __ldg(gW2 + (size_t)D * k + r0 + m) : 0.f;
         }
     }
-    if (!chain) {
+    if constexpr (FIELD == 1) {      // noise tile of this CTA's columns, [row][NP] like the state
+        static_assert(G == 1 && WS, "the FFJORD field runs on single-CTA tiles");
+        const int Dz = D - P.csq_extra;
+        float* sE = smem + P.oCS;
+        for (int e = tid; e < Dz * NP; e += NT) {
+            const int n = e / Dz, i = e - n * Dz;
+            sE[i * NP + n] = (n < Nloc) ? __ldg(P.noise + (size_t)Dz * (c0 + n) + i) : 0.f;
+        }
+    } else if (!chain) {
         for (int m = tid; m < HP; m += NT) {
             sW1t[m] = (td && m < H) ? __ldg(gW1 + (size_t)H * D + m) : 0.f;
             sb1[m] = (m < H) ? __ldg(gb1 + m) : 0.f;
@@ -293,6 +303,12 @@ __global__ void __launch_bounds__(NT, 1) fwd_kernel(const KParams P) {
 
     // ---- one evaluation of the vector field: sOut = f(sIn, tstage) --------
     auto rhs = [&](const float* sIn, float* sOut, const float tstage, const int rec) {
+        if constexpr (FIELD == 1) {
+            const int Dz = D - P.csq_extra;
+            float* sE = smem + P.oCS;
+            csq_rhs<NP, NT>(P.p, Dz, H, P.csq_extra, tstage, sIn, sE, sOut, csq_carve(sE + Dz * NP, Dz, H, NP));
+            return;
+        }
         if constexpr (G == 1 && WS) {
             if (chain) { chain_rhs<NP, NT>(P, cv, sIn, sOut, rec, q); return; }
         }

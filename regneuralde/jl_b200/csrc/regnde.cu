@@ -47,6 +47,7 @@ struct rnde_handle {
     float* dtile = nullptr;             // dx staging in tile layout
     float* head_ws = nullptr;
     float* saveat_dev = nullptr; int n_saveat = 0;
+    const float* noise = nullptr;       // FFJORD: caller-owned Hutchinson noise (rnde_set_noise)
     long long* dbg = nullptr;
     // host-path staging
     float *hx = nullptr, *hp = nullptr, *hu = nullptr, *hsv = nullptr, *hdu = nullptr, *hdsv = nullptr, *hdp = nullptr, *hdx = nullptr;
@@ -120,7 +121,8 @@ static int init_constants(rnde_handle* h) {
 constexpr int NT_FWD = 256;
 typedef void (*kern_t)(const KParams);
 
-static kern_t fwd_kernel_for(int variant, int D = 0, int H = 0, int arith = 0) {
+static kern_t fwd_kernel_for(int variant, int D = 0, int H = 0, int arith = 0, int csq = 0) {
+    if (csq > 0) return variant == RNDE_KERNEL_CHAIN ? fwd_kernel<1, 4, 1, true, NT_FWD, 1> : nullptr;
     switch (variant) {
         case RNDE_KERNEL_CTA: return fwd_kernel<1, 32, 4, true, NT_FWD>;
         case RNDE_KERNEL_STREAM: return fwd_kernel<1, 4, 1, false, NT_FWD>;
@@ -197,6 +199,7 @@ static int chain_hrows(const rnde_config& c) {
 
 extern "C" int64_t rnde_num_params(const rnde_config* c) {
     if (!c) return 0;
+    if (c->csq_extra > 0) return csq_num_params(c->state_dim - c->csq_extra, c->hidden_dim);
     const int td = c->time_dep ? 1 : 0;
     if (c->n_layers > 0) {
         int64_t n = 0;
@@ -239,6 +242,13 @@ static size_t chain_smem_floats(const rnde_config& c, int NP, bool backward) {
     return (size_t)round_up((int)rnde_num_params(&c), 4) + 2 * (size_t)round_up(chain_maxw(c), 4) * NP + (backward ? (size_t)chain_hrows(c) * NP : 0);
 }
 
+// extra shared memory of the FFJORD field: the noise tile and the tiles of one evaluation (csq.cuh)
+static size_t csq_smem_floats(const rnde_config& c, int NP) {
+    if (c.csq_extra <= 0) return 0;
+    const int Dz = c.state_dim - c.csq_extra;
+    return (size_t)Dz * NP + (size_t)csq_tile_floats(Dz, c.hidden_dim, NP) + 4;      // + alignment of the region's start
+}
+
 static void free_all(rnde_handle* h) {
     for (int i = 0; i < 8; ++i) if (h->peers_open[i]) cudaIpcCloseMemHandle((void*)h->peers[i]);
     cudaFree(h->colsum); cudaFree(h->bar); cudaFree(h->steps); cudaFree(h->stats);
@@ -273,14 +283,15 @@ static int try_variant(rnde_handle* h, int variant, size_t smem_limit, std::stri
     const int nbl = (D + h->kblock - 1) / h->kblock;
     if (nbl > 64) { *why = "more than 64 canonical K-blocks"; return 0; }
     if (c.n_layers > 0 && variant != RNDE_KERNEL_CHAIN && variant != RNDE_KERNEL_CTA) { *why = "chain fields run on the CHAIN / CTA variants"; return 0; }
-    const size_t sf = smem_bytes_fwd(variant, D, H, R, HS, h->kblock, c.arith) + sizeof(float) * chain_smem_floats(c, NP, false);
+    if (c.csq_extra > 0 && variant != RNDE_KERNEL_CHAIN) { *why = "the FFJORD field runs on the CHAIN variant (4-column tiles)"; return 0; }
+    const size_t sf = smem_bytes_fwd(variant, D, H, R, HS, h->kblock, c.arith) + sizeof(float) * (chain_smem_floats(c, NP, false) + csq_smem_floats(c, NP));
     const size_t sb = c.need_backward ? smem_bytes_bwd(variant, D, H, R, HS, h->kblock) + sizeof(float) * chain_smem_floats(c, NP, true) : 0;
     if (sf > smem_limit || sb > smem_limit) { *why = "shared memory: need " + std::to_string(std::max(sf, sb)) + " B"; return 0; }
     // all CTAs must be co-resident (persistent grid with a grid barrier)
     if (c.arith == RNDE_ARITH_FIXED24 && (variant != RNDE_KERNEL_CLUSTER4 || c.n_layers > 0 || !v4x_shape_ok(D, H))) {
         *why = "RNDE_ARITH_FIXED24 is implemented by the cluster-4 variant for 128 < D/4 <= 256, H <= 128"; return 0;
     }
-    kern_t kf = fwd_kernel_for(variant, D, H, c.arith);
+    kern_t kf = fwd_kernel_for(variant, D, H, c.arith, c.csq_extra);
     if (cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sf) != cudaSuccess) { cudaGetLastError(); *why = "cudaFuncSetAttribute(fwd) failed"; return 0; }
     if (c.need_backward) {
         kern_t kb = bwd_kernel_for(variant, D, H);
@@ -335,6 +346,11 @@ extern "C" int rnde_create(const rnde_config* cfg, rnde_handle** out) {
         }
     }
     if (cfg->act_hidden < 0 || cfg->act_hidden > 1 || cfg->act_out < 0 || cfg->act_out > 1) return RNDE_ERR_ARG;
+    if (cfg->csq_extra != 0) {
+        if ((cfg->csq_extra != 1 && cfg->csq_extra != 3) || cfg->state_dim <= cfg->csq_extra || cfg->n_layers != 0 || cfg->hidden_dim <= 0 ||
+            cfg->arith != RNDE_ARITH_FMA_CHAIN || cfg->max_saveat > 0) return RNDE_ERR_ARG;
+        if (cfg->need_backward || cfg->dist_mode == RNDE_DIST_EXACT) return RNDE_ERR_UNSUPPORTED;      // forward solves only so far
+    }
     if (cfg->reg_kind < 0 || cfg->reg_kind > RNDE_REG_ERR_PLUS_STIFF || cfg->alg < 0 || cfg->alg > 1) return RNDE_ERR_ARG;
     if (!(cfg->t1 > cfg->t0) || !(cfg->abstol > 0.f) || !(cfg->reltol > 0.f)) return RNDE_ERR_ARG;
     if (cfg->dist_mode < RNDE_DIST_SINGLE || cfg->dist_mode > RNDE_DIST_INDEPENDENT) return RNDE_ERR_ARG;
@@ -364,7 +380,7 @@ extern "C" int rnde_create(const rnde_config* cfg, rnde_handle** out) {
         all = why;
     } else {
         // chain fields: 4-column tiles while they give every SM at most one CTA, else 32-column tiles
-        const bool chain4 = cfg->n_layers > 0 && (cfg->batch + 3) / 4 <= h->num_sms;
+        const bool chain4 = (cfg->n_layers > 0 && (cfg->batch + 3) / 4 <= h->num_sms) || cfg->csq_extra > 0;
         const int order[4] = {chain4 ? RNDE_KERNEL_CHAIN : RNDE_KERNEL_CTA, chain4 ? RNDE_KERNEL_CTA : RNDE_KERNEL_CLUSTER4, RNDE_KERNEL_CLUSTER, RNDE_KERNEL_STREAM};
         for (int i = 0; i < 4 && !ok; ++i) {
             ok = try_variant(h, order[i], smem_limit, &why);
@@ -471,6 +487,13 @@ extern "C" int rnde_set_saveat(rnde_handle* h, const float* saveat_host, int32_t
     return RNDE_OK;
 }
 
+extern "C" int rnde_set_noise(rnde_handle* h, const float* e_dev) {
+    if (!h || !e_dev) return RNDE_ERR_ARG;
+    if (h->cfg.csq_extra <= 0) return set_err(h, RNDE_ERR_STATE, "rnde_set_noise: the handle was not created with csq_extra");
+    h->noise = e_dev;
+    return RNDE_OK;
+}
+
 static void fill_params(const rnde_handle* h, KParams& P) {
     const rnde_config& c = h->cfg;
     memset(&P, 0, sizeof(P));
@@ -534,8 +557,14 @@ static int forward_impl(rnde_handle* h, const float* x_dev, const float* p_dev, 
         bool WS; int G, NP; variant_shape(h->variant, &G, &NP, &WS);
         set_chain_offsets(h, P, make_layout(G, NP, WS, h->cfg.state_dim, h->cfg.hidden_dim, h->R, h->HS, h->kblock).total);
     }
+    if (h->cfg.csq_extra > 0) {
+        if (!h->noise) return set_err(h, RNDE_ERR_STATE, "FFJORD handle: call rnde_set_noise first");
+        bool WS; int G, NP; variant_shape(h->variant, &G, &NP, &WS);
+        P.noise = h->noise; P.csq_extra = h->cfg.csq_extra;
+        P.oCS = round_up(make_layout(G, NP, WS, h->cfg.state_dim, h->cfg.hidden_dim, h->R, h->HS, h->kblock).total, 4);
+    }
     CUDA_TRY(h, cudaMemsetAsync(h->bar, 0, sizeof(unsigned) * 4, st));
-    int rc = launch(h, fwd_kernel_for(h->variant, h->cfg.state_dim, h->cfg.hidden_dim, h->cfg.arith), P, h->smem_fwd, st);
+    int rc = launch(h, fwd_kernel_for(h->variant, h->cfg.state_dim, h->cfg.hidden_dim, h->cfg.arith, h->cfg.csq_extra), P, h->smem_fwd, st);
     if (rc != RNDE_OK) return rc;
     h->last_p = p_dev;
     h->have_tape = h->cfg.need_backward != 0;

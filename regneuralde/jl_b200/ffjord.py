@@ -1,0 +1,112 @@
+"""FFJORD model surface over libregnde.so -- FORWARD (log-density) ONLY so far.
+
+    TrackedFFJORD(model, tspan, time_dep, regularize, solver; dynamics, reltol, abstol, ...)   src/models/ffjord.jl:1-51
+    ffjord(x, p, e; regularize=false) -> (logpx, lambda1, lambda2, nfe, sv)                    src/models/ffjord.jl:68-137
+    ConcatSquashLinear / MLPDynamics(in, hidden)                                               experiments/ffjord_tabular.jl:47-90
+
+The augmented-state solve (z; delta_logp (; ||f||^2; ||e^T J||^2)) runs in the CUDA library (csrc/csq.cuh inside the generic
+Tsit5 stepper); the standard-normal log-density of z(1) is the host glue the reference keeps in Julia.  There is no backward
+yet: calling with gradients enabled on p raises."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib as L
+from .node import ERROR_ESTIMATE, SavedValues, Tsit5, _Handle, _stream_ptr, colmajor, from_colmajor
+
+
+class ConcatSquashLinear:
+    """experiments/ffjord_tabular.jl:49-63: glorot_uniform layer / bias / gate weights, zero biases."""
+
+    def __init__(self, inp: int, out: int, *, generator: Optional[torch.Generator] = None):
+        self.inp, self.out = inp, out
+        u = lambda r, c: (torch.rand(r, c, generator=generator, dtype=torch.float32) * 2 - 1) * math.sqrt(6.0 / (r + c))
+        self.layer_W, self.layer_B = u(out, inp), torch.zeros(out, 1)
+        self.bias_W, self.bias_B = u(out, 1), torch.zeros(out, 1)
+        self.gate_W = u(out, 1)
+
+    def destructure(self) -> torch.Tensor:
+        return torch.cat([self.layer_W.t().contiguous().view(-1), self.layer_B.view(-1), self.bias_W.view(-1), self.bias_B.view(-1),
+                          self.gate_W.view(-1)])
+
+
+class CSQDynamics:
+    """MLPDynamics(in_dims, hsize) of the tabular experiment (ffjord_tabular.jl:76-90): three ConcatSquash layers, softplus between."""
+
+    def __init__(self, in_dims: int, hsize: int, *, generator: Optional[torch.Generator] = None):
+        self.D, self.H = in_dims, hsize
+        self.layers = (ConcatSquashLinear(in_dims, hsize, generator=generator), ConcatSquashLinear(hsize, hsize, generator=generator),
+                       ConcatSquashLinear(hsize, in_dims, generator=generator))
+
+    def destructure(self) -> torch.Tensor:
+        return torch.cat([l.destructure() for l in self.layers])
+
+
+class TrackedFFJORD:
+    """src/models/ffjord.jl:1-51.  ``regularize`` is the type parameter R: True attaches the SavingCallback of EEst*dt."""
+
+    def __init__(self, model: CSQDynamics, tspan: Sequence[float], time_dep: bool, regularize: bool, solver=Tsit5(), *, reltol: float = 1.4e-8,
+                 abstol: float = 1.4e-8, save_everystep: bool = False, save_start: bool = False, dynamics=None, maxiters: int = 0,
+                 tape_capacity: int = 256, device: str = "cuda"):
+        if not isinstance(model, CSQDynamics) or not time_dep:
+            raise NotImplementedError("the CUDA field is the time-dependent ConcatSquash MLPDynamics with its own forw_n_back "
+                                      "(experiments/ffjord_tabular.jl:92-101)")
+        if save_everystep:
+            raise NotImplementedError("save_everystep=true has no call site in the reference")
+        L.require_device()
+        self.model, self.tspan, self.regularize, self.solver = model, (float(tspan[0]), float(tspan[1])), bool(regularize), solver
+        self.reltol, self.abstol, self.maxiters, self.tape_capacity = float(reltol), float(abstol), maxiters, tape_capacity
+        self.device = torch.device(device)
+        self.p = model.destructure().to(self.device)
+        self._handles: dict = {}
+        self.last_stats = None
+
+    def _handle(self, B: int, extra: int, reg_kind: int) -> _Handle:
+        key = (B, extra, reg_kind)
+        if key not in self._handles:
+            cfg = L.Config()
+            cfg.struct_bytes = C.sizeof(L.Config)
+            cfg.state_dim, cfg.hidden_dim, cfg.batch = self.model.D + extra, self.model.H, B
+            cfg.time_dep, cfg.alg, cfg.reg_kind = 1, self.solver.alg, reg_kind
+            cfg.max_steps, cfg.tape_capacity, cfg.need_backward = self.maxiters, self.tape_capacity, 0
+            cfg.t0, cfg.t1 = self.tspan
+            cfg.abstol, cfg.reltol = self.abstol, self.reltol
+            cfg.global_batch, cfg.csq_extra = B, extra
+            self._handles[key] = _Handle(cfg)
+        return self._handles[key]
+
+    def __call__(self, x: torch.Tensor, p: Optional[torch.Tensor] = None, e: Optional[torch.Tensor] = None, *, regularize: bool = False):
+        """-> (logpx (B,), lambda1, lambda2, nfe, sv).  x, e: (D, B).  ``regularize`` (keyword of the {false} functor) appends the
+        kinetic rows; the {true} functor ignores it (ffjord.jl:121)."""
+        p = self.p if p is None else p
+        D = self.model.D
+        if x.dim() != 2 or x.shape[0] != D:
+            raise ValueError(f"x must be ({D}, B)")
+        if not x.is_cuda or not p.is_cuda:
+            raise RuntimeError("regneuralde.jl_b200 runs on CUDA tensors only (no CPU fallback)")
+        if torch.is_grad_enabled() and (p.requires_grad or x.requires_grad):
+            raise NotImplementedError("the FFJORD backward is not built yet (DESIGN.md section 9); call under torch.no_grad()")
+        B = x.shape[1]
+        e = torch.randn(D, B, device=x.device) if e is None else e          # CUDA.randn(Float32, size(x)...)  (ffjord.jl:71)
+        extra = 3 if (regularize and not self.regularize) else 1
+        hd = self._handle(B, extra, ERROR_ESTIMATE.kind if self.regularize else L.REG_NONE)
+        ebuf = colmajor(e.to(torch.float32))
+        ubuf0 = colmajor(torch.cat([x.to(torch.float32), torch.zeros(extra, B, device=x.device)], 0))
+        u = torch.empty((D + extra) * B, device=x.device, dtype=torch.float32)
+        sv = torch.zeros(hd.cfg.tape_capacity + 1, device=x.device, dtype=torch.float32)
+        st = L.Stats()
+        hd.check(hd.lib.rnde_set_noise(hd.h, ebuf.data_ptr()), "rnde_set_noise")
+        rc = hd.lib.rnde_forward(hd.h, ubuf0.data_ptr(), p.contiguous().data_ptr(), u.data_ptr(), sv.data_ptr(), C.byref(st), _stream_ptr())
+        self.last_stats = st
+        hd.check(rc, "rnde_forward")
+        pred = from_colmajor(u, D + extra, B)
+        z, delta_logp = pred[:D], pred[D]
+        zero = torch.zeros(B, device=x.device)
+        lam1, lam2 = (pred[D + 1], pred[D + 2]) if extra == 3 else (zero, zero)
+        logpz = (-(math.log(2 * math.pi) + z * z) / 2).sum(0)
+        svals = SavedValues(torch.zeros(0), sv[: st.n_saved]) if self.regularize else None
+        return logpz - delta_logp, lam1, lam2, int(st.nf), svals

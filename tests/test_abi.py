@@ -34,7 +34,7 @@ def test_library_builds_and_exports_every_declared_symbol():
 def test_config_struct_matches_header():
     from regneuralde.jl_b200 import _lib as L
     # 17 int32 + 5 float + int64 (8-aligned)
-    assert C.sizeof(L.Config) == 176
+    assert C.sizeof(L.Config) == 184
     assert C.sizeof(L.Stats) == 32
     cfg = L.Config()
     cfg.struct_bytes = C.sizeof(L.Config)

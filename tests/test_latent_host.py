@@ -3,6 +3,7 @@
 import math
 
 import numpy as np
+import pytest
 import torch
 
 from regneuralde.jl_b200.latent import _dense_chain, kl_divergence, log_likelihood
@@ -50,3 +51,32 @@ def test_chain_model_shapes_and_validation():
         except (ValueError, NotImplementedError):
             continue
         raise AssertionError("invalid chain accepted")
+
+
+def test_ffjord_mirror_parameter_order_and_validation():
+    """CSQDynamics / ConcatSquashLinear destructure in the order the oracle unpacks (Flux.destructure of MLPDynamics,
+    ffjord_tabular.jl:49-55,76-80); the library's count agrees; unsupported constructions are refused."""
+    import ctypes as C
+    import regneuralde.jl_b200 as R
+    from regneuralde.jl_b200 import _lib as L
+    from oracle import ffjord_oracle as F
+    m = R.CSQDynamics(43, 100)
+    p = m.destructure()
+    assert p.numel() == F.n_params(43, 100) == 19572
+    W, B, bW, bB, G = F.unpack(p.double(), 43, 100)[0]
+    l0 = m.layers[0]
+    assert torch.equal(W.float(), l0.layer_W) and torch.equal(bW.float(), l0.bias_W) and torch.equal(G.float(), l0.gate_W)
+    W3 = F.unpack(p.double(), 43, 100)[2][0]
+    assert torch.equal(W3.float(), m.layers[2].layer_W)
+    cfg = L.Config(); cfg.struct_bytes = C.sizeof(L.Config); cfg.state_dim, cfg.hidden_dim, cfg.batch, cfg.csq_extra = 44, 100, 8, 1
+    assert L.lib().rnde_num_params(C.byref(cfg)) == 19572
+    # argument validation happens before any device work
+    cfg.t0, cfg.t1, cfg.abstol, cfg.reltol = 0.0, 1.0, 1e-6, 1e-6
+    h = C.c_void_p()
+    cfg.csq_extra = 2
+    assert L.lib().rnde_create(C.byref(cfg), C.byref(h)) == L.ERR_ARG
+    cfg.csq_extra, cfg.need_backward = 1, 1
+    assert L.lib().rnde_create(C.byref(cfg), C.byref(h)) == L.ERR_UNSUPPORTED
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            R.TrackedFFJORD(m, [0.0, 1.0], True, False)
