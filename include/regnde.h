@@ -77,7 +77,11 @@ enum { RNDE_DIST_SINGLE = 0, RNDE_DIST_EXACT = 1, RNDE_DIST_INDEPENDENT = 2 };
  * FIXED24: exact truncated fixed-point products, order-independent, run as integer tensor-core MMAs by the cluster-4
  * variant (csrc/fwd4x_kernel.cuh); bit-identical to the oracle's arith = 1.  The two modes are two
  * different roundings of the same field (relative difference ~1e-7 per evaluation). */
-enum { RNDE_ARITH_FMA_CHAIN = 0, RNDE_ARITH_FIXED24 = 1 };
+enum { RNDE_ARITH_FMA_CHAIN = 0, RNDE_ARITH_FIXED24 = 1,
+       /* SPLITK: fma chains like FMA_CHAIN, but the contraction index of each layer is dealt out to 8 (layer 1, per CTA) / 4
+        * (layer 2) interleaved chains combined by a balanced tree -- the order of the 8x8-tile FFMA2 stepper of the cluster-4
+        * variant (csrc/fwd4s_kernel.cuh); bit-identical to the oracle's arith = 2.  The fastest forward for MNIST-shaped fields. */
+       RNDE_ARITH_SPLITK = 2 };
 
 typedef struct rnde_config {
     int32_t struct_bytes;     /* sizeof(rnde_config), for versioning */
@@ -149,6 +153,12 @@ int64_t rnde_launch_count(const rnde_handle* h);
 
 /* tspan override per call (the functor's `tspan` keyword, neural_ode.jl:53,58) */
 int rnde_set_tspan(rnde_handle* h, float t0, float t1);
+
+/* Fixed-work replay (SURVEY.md 8d "controller forced to a recorded dt list"): every attempt i of the following forward
+ * solves takes dt_host[i] (the last entry repeats; the final step is still clamped to tspan) and is accepted whatever its
+ * error estimate, so the number of field evaluations no longer depends on the weights or the data -- a measurement aid
+ * (bench.py --fixed-work), not a reference code path.  n = 0 restores the adaptive controller.  RNDE_ARITH_SPLITK handles only. */
+int rnde_set_forced_steps(rnde_handle* h, const float* dt_host, int32_t n);
 
 /* Forward solve.  x_dev (D x B), p_dev (num_params), u_out_dev (D x B),
  * saveval_dev (>= tape_capacity+1 floats, may be NULL when reg_kind==NONE).

@@ -94,7 +94,7 @@ class OracleConfig:
     # FFJORD field: csq_extra = 1 or 3 augmented rows (D counts them), csq_noise = the Hutchinson noise (D - extra, B)
     csq_extra: int = 0
     csq_noise: np.ndarray | None = None
-    arith: int = 0          # 1 = FIXED24 exact fixed-point layer products (rnde_oracle.c), the tensor-core forward stepper's arithmetic
+    arith: int = 0          # 1 = FIXED24 exact fixed-point layer products (tensor-core forward stepper); 2 = SPLITK fma-chain order of csrc/fwd4s_kernel.cuh
 
     @property
     def n_params(self) -> int:

@@ -87,7 +87,8 @@ typedef struct {
     int act[8];
     int pre_act;
     /* arith = 1 (FIXED24): the layer products of the 2-layer field are exact truncated fixed-point products -- the
-     * arithmetic of the tensor-core forward stepper (csrc/fwd4x_kernel.cuh); see fixed24_* below. */
+     * arithmetic of the tensor-core forward stepper (csrc/fwd4x_kernel.cuh); see fixed24_* below.
+     * arith = 2 (SPLITK): the fma-chain order of csrc/fwd4s_kernel.cuh; see rhs_eval_splitk. */
     int arith;
     /* FFJORD field (csq_extra = 1 or 3; forward here, reverse sweep in rnde_oracle_bwd.inc): the state
      * holds D - csq_extra data rows z plus [delta_logp (; ||f||^2; ||e^T J||^2)] (src/models/ffjord.jl:53-66); the field is
@@ -152,6 +153,21 @@ static REAL combine_blocks(const REAL* p, int n) {
  * consecutive rows form one fma chain (acc = fma(v,v,acc) from 0), group sums are added in
  * order, block sums are combined by combine_blocks. */
 static REAL col_sumsq(const REAL* v, int D, int kb) {
+    if (kb < 0) {       /* arith = 2 (SPLITK): blocks of -kb rows (one CTA each); groups of 4 rows added in order inside a block, blocks in order */
+        REAL tot = 0;
+        for (int r0 = 0, b = 0; r0 < D; r0 += -kb, ++b) {
+            const int r1 = r0 - kb < D ? r0 - kb : D;
+            REAL s = 0;
+            for (int g0 = r0; g0 < r1; g0 += 4) {
+                const int g1 = g0 + 4 < r1 ? g0 + 4 : r1;
+                REAL q = 0;
+                for (int r = g0; r < g1; ++r) q = R_FMA(v[r], v[r], q);
+                s = (g0 == r0) ? q : s + q;
+            }
+            tot = (b == 0) ? s : tot + s;
+        }
+        return tot;
+    }
     REAL part[64]; int nb = 0;
     for (int r0 = 0; r0 < D; r0 += kb) {
         int r1 = r0 + kb < D ? r0 + kb : D;
@@ -413,6 +429,79 @@ static void csq_column(const orc_config* c, const REAL* p, const REAL* zj, const
     if (X == 3) { out[Dz + 1] = f2; out[Dz + 2] = j2; }
 }
 
+/* ------------------------------------------------------------------ */
+/* SPLITK layer arithmetic (arith = 2): the order of csrc/fwd4s_kernel.cuh (8x8 register tiles, packed fmas, the        */
+/* contraction index dealt out to 8 / 4 lanes).  Layer 1: the state rows form 4 blocks of R = D/4 (one CTA each); inside  */
+/* a block, chain s (s = 0..7) runs over the rows 8i + s, i = 0 .. ceil(R/8)-1, in ascending order from 0 (an index past   */
+/* the block is the padded fma(0, 0, acc)); the 8 chains are added as the xor-butterfly tree                              */
+/* ((c0+c1)+(c2+c3)) + ((c4+c5)+(c6+c7)); the blocks as ((p0+p1)+p2)+p3 (the reducer CTA, rank order).  Layer 2: chain s   */
+/* (s = 0..3) runs over the hidden units 4i + s; (c0+c1)+(c2+c3).  Then time column, bias, activation as everywhere.      */
+/* ------------------------------------------------------------------ */
+static void rhs_eval_splitk(const orc_config* c, const REAL* p, const REAL* z, REAL t, REAL* k, REAL* hout) {
+    const int D = c->D, H = c->H, B = c->B, td = c->time_dep ? 1 : 0, R = D / 4;
+    const int KS1 = (R + 7) / 8, KS2 = (H + 3) / 4;
+    const REAL* W1 = p;
+    const REAL* b1 = W1 + (size_t)H * (D + td);
+    const REAL* W2 = b1 + H;
+    const REAL* b2 = W2 + (size_t)D * (H + td);
+    const REAL zero = 0;
+#pragma omp parallel
+    {
+        REAL* ch = (REAL*)malloc(sizeof(REAL) * 8 * (size_t)(H > D ? H : D));
+        REAL* pb = (REAL*)malloc(sizeof(REAL) * 4 * (size_t)H);
+        REAL* hh = (REAL*)malloc(sizeof(REAL) * (size_t)H);
+#pragma omp for schedule(static)
+        for (int j = 0; j < B; ++j) {
+            const REAL* zj = z + (size_t)D * j;
+            for (int b = 0; b < 4; ++b) {
+                for (int e = 0; e < 8 * H; ++e) ch[e] = 0;
+                for (int i = 0; i < KS1; ++i)
+                    for (int s = 0; s < 8; ++s) {
+                        const int kk = 8 * i + s;
+                        REAL* acc = ch + (size_t)s * H;
+                        if (kk < R) {
+                            const REAL xv = zj[b * R + kk];
+                            const REAL* w = W1 + (size_t)H * (b * R + kk);
+                            for (int o = 0; o < H; ++o) acc[o] = R_FMA(w[o], xv, acc[o]);
+                        } else {
+                            for (int o = 0; o < H; ++o) acc[o] = R_FMA(zero, zero, acc[o]);
+                        }
+                    }
+                for (int o = 0; o < H; ++o)
+                    pb[(size_t)b * H + o] = ((ch[o] + ch[H + o]) + (ch[2 * H + o] + ch[3 * H + o])) + ((ch[4 * H + o] + ch[5 * H + o]) + (ch[6 * H + o] + ch[7 * H + o]));
+            }
+            for (int o = 0; o < H; ++o) {
+                REAL v = ((pb[o] + pb[H + o]) + pb[2 * H + o]) + pb[3 * H + o];
+                if (td) v = R_FMA(W1[(size_t)H * D + o], t, v);
+                v = v + b1[o];
+                hh[o] = act_apply(c->act1, v);
+            }
+            if (hout) memcpy(hout + (size_t)H * j, hh, sizeof(REAL) * H);
+            for (int e = 0; e < 4 * D; ++e) ch[e] = 0;
+            for (int i = 0; i < KS2; ++i)
+                for (int s = 0; s < 4; ++s) {
+                    const int kk = 4 * i + s;
+                    REAL* acc = ch + (size_t)s * D;
+                    if (kk < H) {
+                        const REAL xv = hh[kk];
+                        const REAL* w = W2 + (size_t)D * kk;
+                        for (int o = 0; o < D; ++o) acc[o] = R_FMA(w[o], xv, acc[o]);
+                    } else {
+                        for (int o = 0; o < D; ++o) acc[o] = R_FMA(zero, zero, acc[o]);
+                    }
+                }
+            REAL* kj = k + (size_t)D * j;
+            for (int o = 0; o < D; ++o) {
+                REAL v = (ch[o] + ch[D + o]) + (ch[2 * D + o] + ch[3 * D + o]);
+                if (td) v = R_FMA(W2[(size_t)D * H + o], t, v);
+                v = v + b2[o];
+                kj[o] = act_apply(c->act2, v);
+            }
+        }
+        free(ch); free(pb); free(hh);
+    }
+}
+
 static void rhs_eval(const orc_config* c, const REAL* p, const REAL* z, REAL t, REAL* k, REAL* hout) {
     const int D = c->D, H = c->H, B = c->B, td = c->time_dep ? 1 : 0;
     if (c->csq_extra > 0) {
@@ -424,6 +513,7 @@ static void rhs_eval(const orc_config* c, const REAL* p, const REAL* z, REAL t, 
         return;
     }
     if (c->arith == 1 && c->n_layers == 0 && sizeof(REAL) == 4) { rhs_eval_fixed24(c, p, z, t, k, hout); return; }
+    if (c->arith == 2 && c->n_layers == 0) { rhs_eval_splitk(c, p, z, t, k, hout); return; }
     if (c->n_layers > 0) {
         (void)t; (void)hout;
 #pragma omp parallel for schedule(static)
@@ -549,7 +639,7 @@ static void tsit5_attempt(const orc_config* c, const REAL* p, const REAL* uprev,
     const int D = c->D, B = c->B;
     const size_t n = (size_t)D * B;
     const long long cnt = (long long)D * B;
-    const int kb = c->kblock1 > 0 ? c->kblock1 : D;
+    const int kb = (c->arith == 2 && c->n_layers == 0) ? -(D / 4) : (c->kblock1 > 0 ? c->kblock1 : D);
     for (int i = 2; i <= 7; ++i) {
         stage_combo(c, i, dt, uprev, w->k, w->z[i]);
         rhs_eval(c, p, w->z[i], stage_time(t, dt, i), w->k[i], want_h ? w->h[i] : NULL);
@@ -616,7 +706,7 @@ static REAL initial_dt(const orc_config* c, const REAL* p, const REAL* u0, const
                        REAL* colq) {
     const int D = c->D, B = c->B;
     const long long cnt = (long long)D * B;
-    const int kb = c->kblock1 > 0 ? c->kblock1 : D;
+    const int kb = (c->arith == 2 && c->n_layers == 0) ? -(D / 4) : (c->kblock1 > 0 ? c->kblock1 : D);
     const REAL atol = (REAL)c->abstol, rtol = (REAL)c->reltol;
     REAL* tmp = scratch; REAL* u1 = scratch + (size_t)D * B; REAL* f1 = scratch + 2 * (size_t)D * B;
 #pragma omp parallel for schedule(static)
@@ -701,6 +791,7 @@ static REAL saved_value(int kind, REAL EEst, REAL eig, REAL dt) {
 int FN(create)(const orc_config* cfg, void** out) {
     if (!cfg || cfg->D <= 0 || cfg->H <= 0 || cfg->B <= 0) return ORC_ERR_ARG;
     if (cfg->kblock1 > 0 && (cfg->D + cfg->kblock1 - 1) / cfg->kblock1 > 64) return ORC_ERR_ARG;   /* col_sumsq part[64] */
+    if (cfg->arith == 2 && (cfg->D % 4 != 0 || cfg->n_layers > 0 || cfg->csq_extra != 0)) return ORC_ERR_ARG;
     if (cfg->csq_extra != 0 && ((cfg->csq_extra != 1 && cfg->csq_extra != 3) || cfg->D <= cfg->csq_extra || !cfg->csq_noise ||
                                 cfg->n_layers > 0 || cfg->arith != 0 || cfg->D > 1024 || cfg->H > 1024)) return ORC_ERR_ARG;
     orc_handle* h = (orc_handle*)calloc(1, sizeof(orc_handle));

@@ -48,6 +48,8 @@ struct KParams {
     // saveat (multi-save functors, neural_ode.jl:79-108,146-180): sorted times, states written as feat x nsave x batch
     const float* saveat; int n_saveat;
     float* usave; const float* dusave;
+    // fixed-work replay (rnde_set_forced_steps): dt of attempt i, every attempt accepted
+    const float* forced_dt; int n_forced;
     // chain field (chain.cuh): layer widths / activations, pre-activation, tape rows per column, shared-memory offsets (floats)
     int n_layers; int lw[8]; int la[8]; int pre_act; int hrows; int chain_np; int oCW, oCA, oCB, oCH;
     // FFJORD field (csq.cuh): Hutchinson noise ((D - csq_extra) x B, column-major), augmented rows, shared-memory offset of its region

@@ -17,6 +17,7 @@
 #include "bwd4_kernel.cuh"
 #include "bwd4tc_kernel.cuh"
 #include "fwd4x_kernel.cuh"
+#include "fwd4s_kernel.cuh"
 #include "wgrad_kernel.cuh"
 #include "wgrad_tc_kernel.cuh"
 #include "head_kernel.cuh"
@@ -47,6 +48,7 @@ struct rnde_handle {
     float* dtile = nullptr;             // dx staging in tile layout
     float* head_ws = nullptr;
     float* saveat_dev = nullptr; int n_saveat = 0;
+    float* forced_dev = nullptr; int n_forced = 0;      // fixed-work replay (rnde_set_forced_steps)
     const float* noise = nullptr;       // FFJORD: caller-owned Hutchinson noise (rnde_set_noise)
     long long* dbg = nullptr;
     // host-path staging
@@ -130,6 +132,7 @@ static kern_t fwd_kernel_for(int variant, int D = 0, int H = 0, int arith = 0, i
         case RNDE_KERNEL_CLUSTER: return fwd_kernel<8, 32, 4, true, NT_FWD>;
         case RNDE_KERNEL_CLUSTER4:
             if (arith == RNDE_ARITH_FIXED24) return fwd4x_kernel;
+            if (arith == RNDE_ARITH_SPLITK) return (H == 100 && D == 784) ? fwd4s_kernel<100, 784> : fwd4s_kernel<0, 0>;
             return (H == 100 && D == 784) ? fwd4_kernel<100, 98> : fwd4_kernel<0, 0>;
         default: return nullptr;
     }
@@ -224,6 +227,7 @@ extern "C" int64_t rnde_launch_count(const rnde_handle* h) { return h ? h->launc
 
 static size_t smem_bytes_fwd(int variant, int D, int H, int R, int HS, int kblock, int arith = 0) {
     if (variant == RNDE_KERNEL_CLUSTER4 && arith == RNDE_ARITH_FIXED24) return (size_t)make_v4x_layout(D, H).total;
+    if (variant == RNDE_KERNEL_CLUSTER4 && arith == RNDE_ARITH_SPLITK) return (size_t)make_v5_layout(D, H).total * sizeof(float);
     if (variant == RNDE_KERNEL_CLUSTER4) return (size_t)make_v2_layout(D, H).total * sizeof(float);
     int G, NP; bool WS;
     variant_shape(variant, &G, &NP, &WS);
@@ -253,7 +257,7 @@ static void free_all(rnde_handle* h) {
     for (int i = 0; i < 8; ++i) if (h->peers_open[i]) cudaIpcCloseMemHandle((void*)h->peers[i]);
     cudaFree(h->colsum); cudaFree(h->bar); cudaFree(h->steps); cudaFree(h->stats);
     cudaFree(h->tapeZ); cudaFree(h->tapeK); cudaFree(h->tapeH); cudaFree(h->tapeD1); cudaFree(h->wg_ws); cudaFree(h->scal); cudaFree(h->saveval_int);
-    cudaFree(h->dtile); cudaFree(h->head_ws); cudaFree(h->dbg); cudaFree(h->saveat_dev);
+    cudaFree(h->dtile); cudaFree(h->head_ws); cudaFree(h->dbg); cudaFree(h->saveat_dev); cudaFree(h->forced_dev);
     if (h->ev_stats) cudaEventDestroy(h->ev_stats);
     cudaFree(h->hx); cudaFree(h->hp); cudaFree(h->hu); cudaFree(h->hsv); cudaFree(h->hdu); cudaFree(h->hdsv); cudaFree(h->hdp); cudaFree(h->hdx);
     if (h->stats_pinned) cudaFreeHost(h->stats_pinned);
@@ -276,7 +280,10 @@ static int try_variant(rnde_handle* h, int variant, size_t smem_limit, std::stri
     const int Q = (B + NP - 1) / NP;
     if (variant == RNDE_KERNEL_CLUSTER4) {
         if (c.max_saveat > 0) { *why = "cluster-4 variant has no saveat path"; return 0; }
-        if (!v2_shape_ok(D, H) || h->kblock != D / 8) { *why = "cluster-4 variant needs D % 8 == 0, kblock == D/8, H <= 128, D <= 1024"; return 0; }
+        if (c.arith == RNDE_ARITH_SPLITK) {
+            if (!v5_shape_ok(D, H) || c.n_layers > 0) { *why = "RNDE_ARITH_SPLITK needs D % 4 == 0, 64 <= D <= 896, 4 <= H <= 112"; return 0; }
+            if (c.need_backward && !v2_shape_ok(D, H)) { *why = "cluster-4 reverse sweep needs D % 8 == 0"; return 0; }
+        } else if (!v2_shape_ok(D, H) || h->kblock != D / 8) { *why = "cluster-4 variant needs D % 8 == 0, kblock == D/8, H <= 128, D <= 1024"; return 0; }
         if (c.need_backward && !bwd_kernel_for(variant)) { *why = "cluster-4 backward not available"; return 0; }
     } else if (G > 1 && h->kblock != R) { *why = "cluster variant needs kblock == ceil(D/8)"; return 0; }
     if (G > 1 && (D < 64 || (G - 1) * R >= D)) { *why = "state too small for the cluster variant"; return 0; }
@@ -288,6 +295,7 @@ static int try_variant(rnde_handle* h, int variant, size_t smem_limit, std::stri
     const size_t sb = c.need_backward ? smem_bytes_bwd(variant, D, H, R, HS, h->kblock) + sizeof(float) * chain_smem_floats(c, NP, true) : 0;
     if (sf > smem_limit || sb > smem_limit) { *why = "shared memory: need " + std::to_string(std::max(sf, sb)) + " B"; return 0; }
     // all CTAs must be co-resident (persistent grid with a grid barrier)
+    if (c.arith == RNDE_ARITH_SPLITK && variant != RNDE_KERNEL_CLUSTER4) { *why = "RNDE_ARITH_SPLITK is implemented by the cluster-4 variant"; return 0; }
     if (c.arith == RNDE_ARITH_FIXED24 && (variant != RNDE_KERNEL_CLUSTER4 || c.n_layers > 0 || !v4x_shape_ok(D, H))) {
         *why = "RNDE_ARITH_FIXED24 is implemented by the cluster-4 variant for 128 < D/4 <= 256, H <= 128"; return 0;
     }
@@ -354,7 +362,7 @@ extern "C" int rnde_create(const rnde_config* cfg, rnde_handle** out) {
     if (cfg->reg_kind < 0 || cfg->reg_kind > RNDE_REG_ERR_PLUS_STIFF || cfg->alg < 0 || cfg->alg > 1) return RNDE_ERR_ARG;
     if (!(cfg->t1 > cfg->t0) || !(cfg->abstol > 0.f) || !(cfg->reltol > 0.f)) return RNDE_ERR_ARG;
     if (cfg->dist_mode < RNDE_DIST_SINGLE || cfg->dist_mode > RNDE_DIST_INDEPENDENT) return RNDE_ERR_ARG;
-    if (cfg->arith < RNDE_ARITH_FMA_CHAIN || cfg->arith > RNDE_ARITH_FIXED24) return RNDE_ERR_ARG;
+    if (cfg->arith < RNDE_ARITH_FMA_CHAIN || cfg->arith > RNDE_ARITH_SPLITK) return RNDE_ERR_ARG;
     if (cfg->dist_mode == RNDE_DIST_EXACT && (cfg->nranks < 1 || cfg->nranks > 8 || cfg->rank < 0 || cfg->rank >= cfg->nranks)) return RNDE_ERR_ARG;
     if (rnde_device_count() <= 0) return RNDE_ERR_CUDA;
     rnde_handle* h = new rnde_handle();
@@ -487,6 +495,21 @@ extern "C" int rnde_set_saveat(rnde_handle* h, const float* saveat_host, int32_t
     return RNDE_OK;
 }
 
+extern "C" int rnde_set_forced_steps(rnde_handle* h, const float* dt_host, int32_t n) {
+    if (!h || n < 0 || (n > 0 && !dt_host)) return RNDE_ERR_ARG;
+    if (n > 0 && (h->cfg.arith != RNDE_ARITH_SPLITK || h->variant != RNDE_KERNEL_CLUSTER4))
+        return set_err(h, RNDE_ERR_UNSUPPORTED, "rnde_set_forced_steps: only the RNDE_ARITH_SPLITK stepper replays a step list");
+    for (int i = 0; i < n; ++i) if (!(dt_host[i] > 0.f)) return set_err(h, RNDE_ERR_ARG, "forced dt must be positive");
+    ON_HANDLE_DEVICE(h);
+    if (n > h->n_forced || !h->forced_dev) {
+        cudaFree(h->forced_dev); h->forced_dev = nullptr;
+        if (n > 0) CUDA_TRY(h, cudaMalloc(&h->forced_dev, sizeof(float) * n));
+    }
+    if (n > 0) CUDA_TRY(h, cudaMemcpy(h->forced_dev, dt_host, sizeof(float) * n, cudaMemcpyHostToDevice));
+    h->n_forced = n;
+    return RNDE_OK;
+}
+
 extern "C" int rnde_set_noise(rnde_handle* h, const float* e_dev) {
     if (!h || !e_dev) return RNDE_ERR_ARG;
     if (h->cfg.csq_extra <= 0) return set_err(h, RNDE_ERR_STATE, "rnde_set_noise: the handle was not created with csq_extra");
@@ -511,6 +534,7 @@ static void fill_params(const rnde_handle* h, KParams& P) {
     P.n_layers = c.n_layers; P.pre_act = c.pre_act; P.hrows = c.n_layers > 0 ? chain_hrows(c) : 0; P.chain_np = c.n_layers > 0 ? (int)h->np : 0;
     for (int l = 0; l < 8; ++l) { P.lw[l] = c.layer_width[l]; P.la[l] = c.layer_act[l]; }
     P.tapeZ = h->tapeZ; P.tapeK = h->tapeK; P.tapeH = h->tapeH; P.tapeD1 = h->tapeD1; P.scal = h->scal;
+    P.forced_dt = h->forced_dev; P.n_forced = h->n_forced;
 }
 
 // shared-memory offsets of the chain region: right after the generic kernel's own layout

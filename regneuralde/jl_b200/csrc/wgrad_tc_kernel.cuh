@@ -6,9 +6,9 @@
 // One CTA = one 128 x 128 output tile x one contiguous range of the contraction (split-K).
 // Warp roles (416 threads):
 //   warps 0-7  load + split: cp.async the raw FP32 operand chunks of a stage (32 contraction entries)
-//              straight into the UMMA K-major no-swizzle core-matrix layout, then write the low parts
-//              lo = x - tf32_trunc(x) next to them (the tensor core itself truncates the raw tile to
-//              its high part), fence.proxy.async, arrive on ready[stage].
+//              straight into the UMMA K-major no-swizzle core-matrix layout, then replace them by
+//              hi = tf32_rn(x) and write lo = tf32_rn(x - hi) next to them (round-to-nearest split),
+//              fence.proxy.async, arrive on ready[stage].
 //   warp 8     one elected lane issues 4 K-blocks x 3 tcgen05.mma.kind::tf32 (M128 N128 K8) per stage
 //              into a TMEM accumulator, tcgen05.commit -> empty[stage]; every WGT_FLUSH stages the
 //              accumulator buffer is committed to the epilogue and the other TMEM buffer is used.
@@ -134,16 +134,20 @@ __global__ void __launch_bounds__(WGT_THREADS, 1) wgrad_tc_kernel(const float* _
             }
             cp_async_commit();
         };
+        // Round-to-nearest split (round 2): hi = tf32_rn(x) is written back over the raw value, lo = tf32_rn(x - hi) (the
+        // subtraction is exact).  The round-1 split left the truncation to the tensor core (hi = top 11 bits, lo >= 0 with 13
+        // bits of which the MMA keeps 11) -- a one-sided error of up to 2^-21 per operand plus a dropped lo*lo of up to
+        // 2^-20 per product, ~4x the rounding noise of an FP32 fma, which showed up 3x in the regulariser gradient
+        // (profiles/r2a_grad_err.txt).  Now |x - hi - lo| <= 2^-24 |x| and |lo*lo| <= 2^-22 |x y|, both signed.
+        auto tf32_rn = [](float v) -> float { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v)); return __uint_as_float(r); };
         auto split = [&](int g) {
             unsigned char* hi = tsm + (size_t)(g % WGT_STAGES) * WGT_STAGE_BYTES + lane_dst;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float4 x = *reinterpret_cast<const float4*>(hi + i * 1024);
-                float4 lo;
-                lo.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
-                lo.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-                lo.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
-                lo.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+                const float4 h = make_float4(tf32_rn(x.x), tf32_rn(x.y), tf32_rn(x.z), tf32_rn(x.w));
+                const float4 lo = make_float4(tf32_rn(x.x - h.x), tf32_rn(x.y - h.y), tf32_rn(x.z - h.z), tf32_rn(x.w - h.w));
+                *reinterpret_cast<float4*>(hi + i * 1024) = h;
                 *reinterpret_cast<float4*>(hi + i * 1024 + WGT_PART_BYTES) = lo;
             }
         };

@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from dataclasses import dataclass
 from typing import Optional, Sequence
 
@@ -271,6 +272,19 @@ class _SolveSaveat(torch.autograd.Function):
         return dx, dp, None, None, None
 
 
+def resolve_arith(model, kernel_variant: int = L.KERNEL_AUTO, saveat: bool = False) -> int:
+    """Default canonical arithmetic of a node (mirrors v5_shape_ok / try_variant in csrc/regnde.cu): the split-K stepper for
+    2-layer fields with 128 < D/4 <= 224 rows per CTA, D % 8 == 0 and 4 <= H <= 112, on the AUTO or cluster-4 variant."""
+    if isinstance(model, Chain) or saveat or kernel_variant not in (L.KERNEL_AUTO, L.KERNEL_CLUSTER4):
+        return L.ARITH_FMA_CHAIN
+    if os.environ.get("RNDE_ARITH"):          # A/B of the steppers (tools/fwd_time.py): 0 = FMA_CHAIN (fwd4_kernel), 2 = SPLITK (fwd4s_kernel)
+        return int(os.environ["RNDE_ARITH"])
+    D, H = model.D, model.H
+    if D % 8 == 0 and 128 < D // 4 <= 224 and 4 <= H <= 112:
+        return L.ARITH_SPLITK
+    return L.ARITH_FMA_CHAIN
+
+
 class TrackedNeuralODE:
     """src/models/neural_ode.jl:1-33.  ``TrackedNeuralODE(model, tspan, time_dep, regularize,
     solver; reltol, abstol, save_everystep=false, save_start=false)``."""
@@ -279,7 +293,7 @@ class TrackedNeuralODE:
                  reltol: float = 1.4e-8, abstol: float = 1.4e-8, save_everystep: bool = False, save_start: bool = False,
                  saveat=None, maxiters: int = 0, tape_capacity: int = 256, kernel_variant: int = L.KERNEL_AUTO,
                  kblock: int = 0, device: str = "cuda", dist_mode: int = L.DIST_SINGLE, rank: int = 0, world: int = 1,
-                 arith: int = L.ARITH_FMA_CHAIN):
+                 arith: Optional[int] = None):
         if save_everystep:
             raise NotImplementedError("save_everystep=true has no call site in the reference; use saveat")
         # return_multiple = haskey(kwargs, :saveat)  (neural_ode.jl:11): fixes which functor the object dispatches to
@@ -301,8 +315,10 @@ class TrackedNeuralODE:
         # data parallel: DIST_EXACT shares the step sequence of the global batched solve across ranks (x holds this
         # rank's columns, all shards equal); DIST_INDEPENDENT / DIST_SINGLE integrate the local columns on their own
         self.dist_mode, self.rank, self.world = dist_mode, rank, world
-        # canonical arithmetic of the layer products: ARITH_FMA_CHAIN (all variants) or ARITH_FIXED24 (exact integer tensor-core MMAs)
-        self.arith = arith
+        # canonical arithmetic of the layer products: ARITH_FMA_CHAIN (all variants), ARITH_FIXED24 (exact integer tensor-core
+        # MMAs) or ARITH_SPLITK (the 8x8-tile FFMA2 stepper of the cluster-4 variant).  None = SPLITK where that stepper
+        # applies (MNIST-shaped 2-layer fields on the AUTO / cluster-4 variants without saveat), FMA_CHAIN elsewhere.
+        self.arith = resolve_arith(model, kernel_variant, self.return_multiple) if arith is None else int(arith)
         self._handles: dict = {}
         self.last_stats: Optional[L.Stats] = None
 

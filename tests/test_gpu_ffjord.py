@@ -34,15 +34,9 @@ def test_field_evaluation_bit_identical(oracle_built, Dz, H, B, extra):
 
 
 # ---- the augmented-state solve through the C ABI / the TrackedFFJORD mirror (forward only) -----------------------------------
-# Written after round 1's GPU minutes were spent: compiled (148 registers, no spills) and wired, never run on hardware.
-# RNDE_RUN_UNVERIFIED=1 runs it; remove the gate once it has passed on a B200.
-import os  # noqa: E402
-
-unverified = pytest.mark.skipif(os.environ.get("RNDE_RUN_UNVERIFIED") != "1",
-                                reason="FFJORD stepper wiring not yet run on hardware; RNDE_RUN_UNVERIFIED=1 runs it")
+# First run on a B200 in round 2 (gpurun_out/r2a_ffjord.txt: 8 passed): bit-identical to the C oracle.
 
 
-@unverified
 @pytest.mark.parametrize("Dz,H,B,regf,kinetic", [(43, 100, 8, False, False), (43, 100, 7, True, False), (43, 100, 6, False, True), (5, 9, 130, True, False)])
 def test_ffjord_solve_bit_identical(oracle_built, Dz, H, B, regf, kinetic):
     """ffjord(x, p, e) -> (logpx, l1, l2, nfe, sv) (src/models/ffjord.jl:68-137): states, NFE and saved values of the augmented

@@ -33,9 +33,10 @@ def make_node(D, H, act_out, regularize, solver, variant=0, kblock=0, cap=256):
                               save_start=False, kernel_variant=variant, kblock=kblock, tape_capacity=cap)
 
 
-def oracle_cfg(D, H, B, act_out, alg, reg, kblock=0):
+def oracle_cfg(D, H, B, act_out, alg, reg, kblock=0, arith=0):
+    """arith: the canonical arithmetic the node resolved to (node.arith: FMA_CHAIN, or SPLITK on the cluster-4 stepper)."""
     kb = kblock if kblock else (D if D < 128 else (D + 7) // 8)
-    return orc.OracleConfig(D=D, H=H, B=B, act2=orc.ACT_TANH if act_out else orc.ACT_ID, alg=alg, reg_kind=reg, kblock1=kb)
+    return orc.OracleConfig(D=D, H=H, B=B, act2=orc.ACT_TANH if act_out else orc.ACT_ID, alg=alg, reg_kind=reg, kblock1=kb, arith=arith)
 
 
 FWD_CASES = [
@@ -71,7 +72,7 @@ def test_forward_bit_identical(oracle_built, name, D, H, B, act_out, auto, func,
         res, nfe, sv = node(torch.from_numpy(x_np).cuda(), torch.from_numpy(p_np).cuda(), func=fobj)
     torch.cuda.synchronize()
     reg_kind = fobj.kind if fobj else orc.REG_NONE
-    o = orc.Oracle(oracle_cfg(D, H, B, act_out, 1 if auto else 0, reg_kind, kblock))
+    o = orc.Oracle(oracle_cfg(D, H, B, act_out, 1 if auto else 0, reg_kind, kblock, arith=node.arith))
     ref = o.forward(x_np, p_np)
     st = node.last_stats
     assert ref.retcode == 0 and st.retcode == 0
@@ -118,7 +119,7 @@ def test_gradient_matches_oracle(oracle_built, name, D, H, B, act_out, auto, fun
     x = torch.from_numpy(x_np).cuda().requires_grad_(True)
     res, nfe, sv = node(x, p, func=fobj)
     reg_kind = fobj.kind if fobj else orc.REG_NONE
-    o = orc.Oracle(oracle_cfg(D, H, B, act_out, 1 if auto else 0, reg_kind))
+    o = orc.Oracle(oracle_cfg(D, H, B, act_out, 1 if auto else 0, reg_kind, arith=node.arith))
     ref = o.forward(x_np, p_np)
     assert np.array_equal(bits(res.detach().cpu().numpy()), bits(ref.u))
     w = rng.standard_normal((D, B)).astype(np.float32)
@@ -157,7 +158,7 @@ def test_mnist_training_step_against_oracle(oracle_built):
     clf.p2.copy_(torch.from_numpy(p2)); clf.p3.copy_(torch.from_numpy(p3)); node.p = clf.p2
     out = clf.loss_and_gradient(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), lam=lam, func=r.ERROR_ESTIMATE, agg="mean")
     torch.cuda.synchronize()
-    o = orc.Oracle(oracle_cfg(D, H, B, 1, 0, orc.REG_ERR_DT))
+    o = orc.Oracle(oracle_cfg(D, H, B, 1, 0, orc.REG_ERR_DT, arith=node.arith))
     ref = o.forward(x, p2)
     logits = W3 @ ref.u
     m = logits.max(0, keepdims=True)
@@ -228,7 +229,7 @@ def test_saveat_multi_save_functors(oracle_built, name, D, H, B, act_out, auto, 
     x = torch.from_numpy(x_np).cuda().requires_grad_(True)
     p = torch.from_numpy(p_np).cuda().requires_grad_(True)
     res, nfe, sv = node(x, p, func=fobj)
-    cfg = oracle_cfg(D, H, B, act_out, 1 if auto else 0, reg_kind)
+    cfg = oracle_cfg(D, H, B, act_out, 1 if auto else 0, reg_kind, arith=node.arith)
     cfg.saveat = sa32.astype(np.float64)
     o = orc.Oracle(cfg)
     ref = o.forward(x_np, p_np)
@@ -370,7 +371,7 @@ def test_tensor_core_sweep_agrees_with_ffma_sweep(oracle_built, tmp_path):
     assert int(a["nfe"]) == int(b["nfe"])
     rel = lambda u, v: np.abs(u - v).max() / np.abs(v).max()
     D, H, B = 784, 100, 80
-    o = orc.Oracle(oracle_cfg(D, H, B, 1, 1, orc.REG_ERR_PLUS_STIFF))
+    o = orc.Oracle(oracle_cfg(D, H, B, 1, 1, orc.REG_ERR_PLUS_STIFF, arith=node.arith))
     o.forward(a["x"], a["p"])
     dp_hi, dx_hi, _, _ = o.backward(a["w"], a["ws"], hi=True)
     dp_32, dx_32, _, _ = o.backward(a["w"], a["ws"])
@@ -407,7 +408,7 @@ def test_fixed24_tensor_core_forward_bit_identical(oracle_built, name, D, H, B, 
     fobj = getattr(r, func) if func else None
     x = torch.from_numpy(x_np).cuda().requires_grad_(True); p = torch.from_numpy(p_np).cuda().requires_grad_(True)
     res, nfe, sv = node(x, p, func=fobj)
-    cfg = oracle_cfg(D, H, B, act_out, 1 if auto else 0, fobj.kind if fobj else orc.REG_NONE)
+    cfg = oracle_cfg(D, H, B, act_out, 1 if auto else 0, fobj.kind if fobj else orc.REG_NONE, arith=node.arith)
     cfg.arith = 1
     o = orc.Oracle(cfg)
     ref = o.forward(x_np, p_np)
@@ -459,13 +460,13 @@ def test_solution_object(oracle_built):
     node = make_node(D, H, 0, True, r.Tsit5())
     x = torch.from_numpy(x_np).cuda(); p = torch.from_numpy(p_np).cuda()
     sol = r.solution(node, x, p)
-    ref = orc.Oracle(oracle_cfg(D, H, B, 0, 0, orc.REG_NONE)).forward(x_np, p_np)
+    ref = orc.Oracle(oracle_cfg(D, H, B, 0, 0, orc.REG_NONE, arith=node.arith)).forward(x_np, p_np)
     assert sol.retcode == "Success" and len(sol) == 1 and float(sol.t[-1]) == 1.0
     assert (sol.destats.nf, sol.destats.naccept, sol.destats.nreject) == (ref.nf, ref.naccept, ref.nreject)
     assert np.array_equal(bits(sol[0].cpu().numpy()), bits(ref.u))
     assert len(sol.step_t) == ref.naccept + 1 and abs(float(sol.step_t[-1]) - 1.0) < 1e-6
     sol2 = r.solution(node, x, p, solver=r.AutoTsit5(), tspan=[0.0, 0.5], saveat=[0.0, 0.25, 0.5])
-    cfg = oracle_cfg(D, H, B, 0, 1, orc.REG_NONE); cfg.t1 = 0.5; cfg.saveat = np.array([0.0, 0.25, 0.5])
+    cfg = oracle_cfg(D, H, B, 0, 1, orc.REG_NONE, arith=node.arith); cfg.t1 = 0.5; cfg.saveat = np.array([0.0, 0.25, 0.5])
     ref2 = orc.Oracle(cfg).forward(x_np, p_np)
     assert len(sol2) == 3 and sol2.destats.nf == ref2.nf
     assert np.array_equal(bits(torch.stack(sol2.u).cpu().numpy()), bits(ref2.usave))
@@ -512,7 +513,7 @@ def test_failure_codes_and_host_api(oracle_built):
     assert lib.rnde_create(C.byref(cfg), C.byref(h)) == 0
     xh = np.ascontiguousarray(x_np.T); u = np.zeros_like(xh); sv = np.zeros(300, np.float32); st = L.Stats()
     assert lib.rnde_forward_host(h, xh.ctypes.data, p_np.ctypes.data, u.ctypes.data, sv.ctypes.data, C.byref(st)) == 0
-    ref = orc.Oracle(oracle_cfg(D, H, B, 0, 0, orc.REG_ERR_DT)).forward(x_np, p_np)
+    ref = orc.Oracle(oracle_cfg(D, H, B, 0, 0, orc.REG_ERR_DT, arith=0)).forward(x_np, p_np)
     assert np.array_equal(bits(u.T), bits(ref.u)) and st.nf == ref.nf
     du = np.ones_like(xh); dsv = np.ones(300, np.float32); dp = np.zeros_like(p_np); dx = np.zeros_like(xh)
     assert lib.rnde_backward_host(h, du.ctypes.data, dsv.ctypes.data, dp.ctypes.data, dx.ctypes.data) == 0
@@ -602,7 +603,7 @@ def test_exact_data_parallel_matches_single_solve(oracle_built):
     D, H, Bg = 784, 100, 96
     rng = np.random.default_rng(1999)
     p_np = orc.glorot_params(rng, D, H); x_np = rng.random((D, Bg), dtype=np.float32)
-    ref = orc.Oracle(oracle_cfg(D, H, Bg, 1, 0, orc.REG_ERR_DT)).forward(x_np, p_np)
+    ref = orc.Oracle(oracle_cfg(D, H, Bg, 1, 0, orc.REG_ERR_DT, arith=2)).forward(x_np, p_np)
     u = np.concatenate([o[1] for o in outs], axis=1)
     assert outs[0][3] == ref.nf and outs[1][3] == ref.nf
     assert np.array_equal(bits(u), bits(ref.u))

@@ -12,7 +12,7 @@ node = r.TrackedNeuralODE(r.MLPDynamics(D, H), [0.0, 1.0], True, True, r.Tsit5()
 x = torch.from_numpy(x_np).cuda().requires_grad_(True); p = torch.from_numpy(p_np).cuda().requires_grad_(True)
 res, nfe, sv = node(x, p, func=r.ERROR_ESTIMATE)
 ws = rng.standard_normal(len(sv)).astype(np.float32)
-o = orc.Oracle(orc.OracleConfig(D=D, H=H, B=B, act2=orc.ACT_TANH, reg_kind=orc.REG_ERR_DT, kblock1=98)); ref = o.forward(x_np, p_np)
+o = orc.Oracle(orc.OracleConfig(D=D, H=H, B=B, act2=orc.ACT_TANH, reg_kind=orc.REG_ERR_DT, kblock1=98, arith=node.arith)); ref = o.forward(x_np, p_np)
 rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()
 for name, wsv in (("random cotangents on u only", 0 * ws), ("u + saved values", ws)):
     x.grad = None; p.grad = None

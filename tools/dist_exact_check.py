@@ -37,7 +37,7 @@ us = [torch.empty_like(res.contiguous()) for _ in range(world)]
 dist.all_gather(us, res.detach().contiguous())
 if rank == 0:
     u = torch.cat(us, dim=1).cpu().numpy()
-    o = orc.Oracle(orc.OracleConfig(D=D, H=H, B=Bg, kblock1=98, reg_kind=orc.REG_ERR_DT)); ref = o.forward(x_np, p_np)
+    o = orc.Oracle(orc.OracleConfig(D=D, H=H, B=Bg, kblock1=98, reg_kind=orc.REG_ERR_DT, arith=node.arith)); ref = o.forward(x_np, p_np)
     bits = lambda a: np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
     print("exact mode vs single batched solve: nfe", nfe, ref.nf, "naccept", node.last_stats.naccept, ref.naccept,
           "| u bit-equal", np.array_equal(bits(u), bits(ref.u)), "| saveval bit-equal", np.array_equal(bits(sv.saveval.detach().cpu().numpy()), bits(ref.saveval)))

@@ -29,7 +29,7 @@ def flagship_grad_errors(B=512, lam=100.0, seed=1999, func_name="ERROR_ESTIMATE"
     clf.p2.copy_(torch.from_numpy(p2)); clf.p3.copy_(torch.from_numpy(p3)); node.p = clf.p2
     xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
     agg = "maximum" if func_name == "STIFFNESS_SCALED" else "mean"
-    o = orc.Oracle(orc.OracleConfig(D=D, H=H, B=B, act2=orc.ACT_TANH, reg_kind=func.kind, kblock1=D // 8, alg=1 if auto else 0))
+    o = orc.Oracle(orc.OracleConfig(D=D, H=H, B=B, act2=orc.ACT_TANH, reg_kind=func.kind, kblock1=D // 8, alg=1 if auto else 0, arith=node.arith))
     ref = o.forward(x, p2)
     logits = W3 @ ref.u
     m = logits.max(0, keepdims=True)

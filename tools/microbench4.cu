@@ -54,7 +54,8 @@ __global__ void tile88(float* out, long long* cyc, int KS, int WP, int MG, int r
     int s, mg;
     if (S == 4) { s = b0 | (((lane >> 3) & 1) << 1); mg = ((lane >> 2) & 1) | (((lane >> 4) & 1) << 1) | (warp << 2); }
     else        { s = b0 | (((lane >> 3) & 3) << 1); mg = ((lane >> 2) & 1) | (warp << 1); }
-    const bool act = mg < MG;
+    const bool act = (S == 4 ? (warp << 2) : (warp << 1)) < MG;      // warp-uniform: the shuffles below need every lane of an active warp
+    if (mg >= MG) mg = MG - 1;
     const float* wp = sW + s * WP + mg * 8;
     const float* xp = sX + s * 16 + cg * 8;
     float res = 0.f;
@@ -247,6 +248,7 @@ int main() {
         cudaDeviceSynchronize();
         cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
         printf("pure FFMA2 ILP16  warps/SM %2d : %.1f lane-FMA/clk/SM\n", warps, (double)warps * 32 * 32 * iters / (double)h[0]);
+        fflush(stdout);
     }
     const int reps = 200;
     // layer 2: K = 100 (S = 4, KS = 25), weights pitch 196, 25 row groups -> 7 warps (224 threads, 200 active)
@@ -259,6 +261,7 @@ int main() {
         cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
         const double fma = (double)MG * 2 * 64 * S * KS * reps;      // useful lane-FMAs per CTA
         printf("%-58s thr %3d : %7.0f cyc/phase, %.1f lane-FMA/clk/SM (%s)\n", name, threads, (double)h[0] / reps, fma / (double)h[0], cudaGetErrorString(e));
+        fflush(stdout);
     };
     run("L2 8x8 S=4 FFMA2 + reduce-scatter, 25 row groups", tile88<4, true, true>, 4, 25, 196, 25, 224);
     run("L2 8x8 S=4 FFMA2, no scatter,      25 row groups", tile88<4, true, false>, 4, 25, 196, 25, 224);
