@@ -12,8 +12,15 @@ synthetic U[0,1) inputs and random one-hot labels, Glorot-uniform weights, seed 
     python bench.py --gpus N --steps K --warmup W            (N>1: launched under torch.distributed.run)
     python bench.py --impl reference ...                     (CPU arm: the oracle port on the host cores)
 
-Prints ONE JSON line (rank 0).  `value` = whole-job samples/s with inputs resident in HBM; `e2e` = the same
-through the public API with pinned-host inputs copied H2D and the loss read back D2H inside the timed region.
+Both arms run the SAME work: the same initial weights (default_rng(1999)), the same 8 rotating batches of rank 0
+(default_rng(2000)), the same canonical arithmetic (so the same step sequences), the optimiser update included, W warm-up
+steps then K timed ones.  They print the same `config`.
+
+Prints ONE JSON line (rank 0).  `value` = whole-job samples/s with inputs resident in HBM; `e2e` = the same through the
+public API with pinned-host inputs copied H2D and the loss read back D2H inside the timed region.  At N > 1 `value` is the
+REFERENCE-EXACT data-parallel mode (all ranks share the step sequence of the one batched solve); the independent-controller
+mode and the strong-scaling split of one 512 batch are reported beside it (`independent`, `strong_scaling`).  `fixed_work`
+repeats the timed steps with the controller replaying a recorded dt list (equal work per step whatever the weights).
 """
 from __future__ import annotations
 
@@ -36,24 +43,40 @@ D, H, NCLASS = 784, 100, 10
 F_RHS = 2 * (H * (D + 1) + D * (H + 1))      # 315 368 FLOP per sample per field evaluation
 SEED = 1999
 LAMBDA = 1.0e2
+NB = 8                                        # rotating batches
+GAMMA, ETA, RHO = 1.0e-5, 0.1, 0.9            # Optimiser(InvDecay(1e-5), Momentum(0.1, 0.9)), mnist_node.jl:130
+ARITH_SPLITK = 2                              # canonical arithmetic of the stepper both arms use (include/regnde.h)
+
+
+def workload_config(B: int, world: int) -> dict:
+    """The workload description both arms print (identical for identical flags)."""
+    return {
+        "workload": f"mnist_node reg(error_est) train step: MLPDynamics(784,100), batch {B}/GPU, Tsit5 reltol=abstol=1.4e-8, "
+                    "error-estimate regulariser (agg mean, lambda 100), Dense(784,10) head + logitcrossentropy, InvDecay(1e-5)+Momentum(0.1,0.9) update",
+        "global_batch": B * world, "per_gpu_batch": B, "n_ranks": world,
+        "inputs": f"{NB} rotating synthetic batches per rank (numpy default_rng({SEED + 1}+rank)), U[0,1) pixels, random one-hot labels",
+        "weights": f"Glorot-uniform from default_rng({SEED}), zero biases; trained through the warm-up and the timed steps",
+        "arithmetic": "Float32, canonical order RNDE_ARITH_SPLITK (csrc/fwd4s_kernel.cuh == oracle arith 2)",
+        "l2": "per-step tape working set (~3.4 MB x ~200 records) exceeds the 126 MB L2; inputs rotate over 8 batches",
+    }
 
 
 def stepper_dram_traffic() -> float | None:
-    """dram__bytes_read.sum + dram__bytes_write.sum of the forward stepper per launch, from the committed
-    `ncu --set full` capture of the final round-1 build (profiles/r1x_fwd4_final_ncu_raw_metrics.json; r1h = earlier build)."""
-    f = ROOT / "profiles" / "r1x_fwd4_final_ncu_raw_metrics.json"
-    if not f.exists():
-        f = ROOT / "profiles" / "r1h_steppers_ncu_raw_metrics.json"
-    try:
-        d = json.loads(f.read_text())
-        k = next(v for n, v in d.items() if "fwd4" in n)
-        tot = 0.0
-        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-            val, unit = k[key]
-            tot += float(val) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
-        return tot
-    except Exception:
-        return None
+    """dram__bytes_read.sum + dram__bytes_write.sum of the forward stepper per launch, from the newest committed
+    `ncu --set full` capture under profiles/ (r2* = this round's fwd4s_kernel, r1x = round 1's fwd4_kernel)."""
+    for name, pat in (("r2_fwd4s_ncu_raw_metrics.json", "fwd4s"), ("r1x_fwd4_final_ncu_raw_metrics.json", "fwd4")):
+        f = ROOT / "profiles" / name
+        try:
+            d = json.loads(f.read_text())
+            k = next(v for n, v in d.items() if pat in n)
+            tot = 0.0
+            for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                val, unit = k[key]
+                tot += float(val) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+            return tot
+        except Exception:
+            continue
+    return None
 
 
 def ffma_peak_tflops() -> tuple[float, str]:
@@ -78,7 +101,7 @@ class ClockSampler:
     def start(self):
         try:
             self.fh = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.gpu)], stdout=self.fh, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -138,10 +161,15 @@ def init_params(rng):
     return p2.astype(np.float32), p3.astype(np.float32)
 
 
+def flop_per_sample(nfe: int, naccept: int) -> int:
+    """forward nf evaluations, backward two GEMMs per taped evaluation (1 + 6 per accepted step)."""
+    return (nfe + 2 + 12 * naccept) * F_RHS
+
+
 # ----------------------------------------------------------------------------------------------
 # CPU arm: the oracle port (the reference itself needs Julia, absent from this image -- BASELINE.md 2)
 # ----------------------------------------------------------------------------------------------
-def cpu_train_step(orc, o, x, y, p2, p3, B):
+def cpu_loss_grad(o, x, y, p2, p3, B, hi=False):
     r = o.forward(x, p2)
     W3 = p3[: NCLASS * D].reshape(D, NCLASS).T
     b3 = p3[NCLASS * D:]
@@ -152,59 +180,83 @@ def cpu_train_step(orc, o, x, y, p2, p3, B):
     g = (np.exp(logits - lse) - y) / B
     du = (W3.T @ g).astype(np.float32)
     dsv = np.full(len(r.saveval), LAMBDA / max(len(r.saveval), 1), np.float32)
-    dp2, _, _, _ = o.backward(du, dsv)
+    dp2, _, _, _ = o.backward(du, dsv, hi=hi)
     dW3 = g @ r.u.T
     reg = LAMBDA * float(r.saveval.mean()) if len(r.saveval) else 0.0
     return ce + reg, dp2, np.concatenate([dW3.flatten(order="F"), g.sum(axis=1)]).astype(np.float32), r
 
 
-def cpu_baseline(B: int, steps: int, warmup: int = 0, budget_s: float = 0.0):
-    """Times `steps` CPU training steps after `warmup` untimed ones.  With budget_s > 0 the per-step sample (columns of the
-    batch) is cut so that warmup + steps fit the budget, judged from one probe step on the full batch."""
+class CpuOptimiser:
+    """Optimiser(InvDecay(gamma), Momentum(eta, rho)) on raw arrays (src/utils.jl:149-156; the arithmetic of rnde_opt_update)."""
+
+    def __init__(self):
+        self.n, self.v = {}, {}
+
+    def update(self, key, p, g):
+        n = self.n.get(key, 1)
+        v = self.v.get(key, np.zeros_like(p))
+        delta = g * np.float32(1.0 / (1.0 + GAMMA * n))
+        v = np.float32(RHO) * v - np.float32(ETA) * delta
+        p += v
+        self.n[key], self.v[key] = n + 1, v
+
+
+def cpu_run(B: int, steps: int, warmup: int, budget_s: float):
+    """W warm-up + K timed CPU training steps on rank 0's batches, weights training like the GPU arm's.  When the full batch
+    does not fit the time budget (judged from one probe step), every step takes the first Bs columns of its batch."""
     from oracle import orc
     orc.build()
-    rng = np.random.default_rng(SEED)
-    p2, p3 = init_params(rng)
-    xs, ys = synth_batches(rng, 1, B)
+    p2, p3 = init_params(np.random.default_rng(SEED))
+    xs, ys = synth_batches(np.random.default_rng(SEED + 1), NB, B)
     cores = os.cpu_count() or 1
+    mk = lambda b: orc.Oracle(orc.OracleConfig(D=D, H=H, B=b, kblock1=(D + 7) // 8, reg_kind=orc.REG_ERR_DT, nthreads=cores, arith=ARITH_SPLITK))
     Bs = B
     if budget_s > 0:
-        o = orc.Oracle(orc.OracleConfig(D=D, H=H, B=B, kblock1=(D + 7) // 8, reg_kind=orc.REG_ERR_DT, nthreads=cores))
+        o = mk(B)
         tp = time.perf_counter()
-        cpu_train_step(orc, o, xs[0], ys[0], p2, p3, B)
+        cpu_loss_grad(o, xs[0], ys[0], p2, p3, B)
         probe = time.perf_counter() - tp
         need = probe * (steps + warmup)
         if need > budget_s:
             Bs = max(16, int(B * budget_s / need) // 16 * 16)
-    x, y = np.ascontiguousarray(xs[0][:, :Bs]), np.ascontiguousarray(ys[0][:, :Bs])
-    o = orc.Oracle(orc.OracleConfig(D=D, H=H, B=Bs, kblock1=(D + 7) // 8, reg_kind=orc.REG_ERR_DT, nthreads=cores))
-    for _ in range(warmup):
-        cpu_train_step(orc, o, x, y, p2, p3, Bs)
+    o = mk(Bs)
+    opt = CpuOptimiser()
+    nfes = []
+
+    def step(i):
+        x, y = np.ascontiguousarray(xs[i % NB][:, :Bs]), np.ascontiguousarray(ys[i % NB][:, :Bs])
+        _, g2, g3, r = cpu_loss_grad(o, x, y, p2, p3, Bs)
+        opt.update("p2", p2, g2); opt.update("p3", p3, g3)
+        return r
+
+    for i in range(warmup):
+        step(i)
     t0 = time.perf_counter()
-    nf = 0
-    for _ in range(steps):
-        _, _, _, r = cpu_train_step(orc, o, x, y, p2, p3, Bs)
-        nf = r.nf
+    for i in range(steps):
+        nfes.append(step(warmup + i).nf)
     el = time.perf_counter() - t0
-    what = f"the full {B}-sample batch" if Bs == B else f"the first {Bs} of the batch's {B} samples (cut to fit {budget_s:.0f} s)"
+    what = f"the full {B}-sample batches" if Bs == B else f"the first {Bs} of each batch's {B} samples (cut to fit {budget_s:.0f} s)"
     return {"value": Bs * steps / el, "unit": "samples/s", "cores": cores, "kind": "port",
-            "sample": f"{steps} training step(s) of {what} (C oracle, OpenMP, forward+adjoint+head), nfe={nf}",
-            "ms_per_step": 1e3 * el / steps}
+            "sample": f"{steps} training step(s) after {warmup} warm-up on {what} (C oracle, OpenMP, forward + adjoint + head + optimiser update), "
+                      f"nfe mean {statistics.mean(nfes):.1f}",
+            "ms_per_step": 1e3 * el / steps, "nfe_mean": statistics.mean(nfes), "us_per_nfe": 1e6 * el / steps / statistics.mean(nfes)}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     B = args.batch
     steps, warm = max(1, args.steps), max(0, args.warmup)
-    cb = cpu_baseline(B, steps, warmup=warm, budget_s=150.0)      # exactly K timed steps after W warm-up steps, each a bounded sample
+    cb = cpu_run(B, steps, warm, budget_s=150.0)      # exactly K timed steps after W warm-up steps, each a bounded sample
     line = {
         "impl": "reference", "metric": "mnist_reg_node_train_samples_per_sec", "value": cb["value"], "unit": "samples/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": cb["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"mnist_node reg(error_est) train step, MLPDynamics(784,100), batch {B}, Tsit5 tol 1.4e-8",
-                   "note": "CPU restatement of the reference path (Julia toolchain unavailable); oracle/rnde_oracle.c on all host cores"},
+        "config": workload_config(B, world),
+        "note": "CPU restatement of the reference path (Julia toolchain unavailable): oracle/rnde_oracle.c on all host cores, rank 0's batches",
+        "run": {"nfe_mean": cb["nfe_mean"], "us_per_nfe": cb["us_per_nfe"]},
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -233,149 +285,215 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
-    rng = np.random.default_rng(SEED)                     # same weights on every rank
-    p2_np, p3_np = init_params(rng)
-    rng_data = np.random.default_rng(SEED + 1 + rank)     # each rank its own shard (weak scaling)
-    NB = 8
-    xs_np, ys_np = synth_batches(rng_data, NB, B)
-
-    gen = torch.Generator().manual_seed(SEED)
-    model = R.MLPDynamics(D, H, generator=gen)
-    exact = world > 1 and args.dist == "exact"
-    node = R.TrackedNeuralODE(model, [0.0, 1.0], True, True, R.Tsit5(), save_everystep=False, reltol=1.4e-8, abstol=1.4e-8,
-                              save_start=False, tape_capacity=args.tape_capacity,
-                              dist_mode=L.DIST_EXACT if exact else L.DIST_SINGLE, rank=rank if exact else 0, world=world if exact else 1)
-    clf = R.ClassifierNODE(None, node, R.Dense(D, NCLASS, generator=gen))
-    clf.p2.copy_(torch.from_numpy(p2_np)); clf.p3.copy_(torch.from_numpy(p3_np))
-    node.p = clf.p2
-    opt = R.Optimiser(1.0e-5, 0.1, 0.9)
-
-    xs_dev = [torch.from_numpy(x).to(dev) for x in xs_np]            # (D,B) tensors resident in HBM
-    ys_dev = [torch.from_numpy(y).to(dev) for y in ys_np]
-    xs_pin = [torch.from_numpy(np.ascontiguousarray(x.T)).pin_memory() for x in xs_np]   # column-major D x B == row-major (B,D)
-    ys_pin = [torch.from_numpy(np.ascontiguousarray(y.T)).pin_memory() for y in ys_np]
-    x_stage = torch.empty(B, D, device=dev); y_stage = torch.empty(B, NCLASS, device=dev)
-    loss_pin = torch.empty(1).pin_memory()
-
-    gflat = None
-
-    def train_step(x, y):
-        if exact:      # global loss: CE mean over world*B samples, one shared regulariser; gradients are summed
-            out = clf.loss_and_gradient(x, y, lam=LAMBDA, func=R.ERROR_ESTIMATE, agg="mean", ce_scale=1.0 / world)
-            g2, g3 = out["g2"], out["g3"]
-            node.allreduce_(g2, g3)        # one-shot push all-reduce over NVLink peer memory (rnde_allreduce_grads), no NCCL call
-        else:
-            out = clf.loss_and_gradient(x, y, lam=LAMBDA, func=R.ERROR_ESTIMATE, agg="mean")
-            g2, g3 = out["g2"], out["g3"]
-            average_gradients_([g2, g3], world)
-        R.update_parameters_((clf.p1, clf.p2, clf.p3), (clf.p1, g2, g3), opt)
-        return out
-
-    def step_resident(i):
-        return train_step(xs_dev[i % NB], ys_dev[i % NB])
-
-    def step_e2e(i):
-        x_stage.copy_(xs_pin[i % NB], non_blocking=True)
-        y_stage.copy_(ys_pin[i % NB], non_blocking=True)
-        out = train_step(x_stage.t(), y_stage.t())
-        loss_pin.copy_(out["loss"].reshape(1), non_blocking=False)
-        return out
+    p2_np, p3_np = init_params(np.random.default_rng(SEED))                     # same weights on every rank
+    xs_np, ys_np = synth_batches(np.random.default_rng(SEED + 1 + rank), NB, B)  # each rank its own shard (weak scaling)
+    W, K = max(args.warmup, 3), max(1, args.steps)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def launches():
-        return node.launch_count()
+    class Trainer:
+        """One data-parallel mode: its node (handles, tape), parameters and optimiser state."""
 
-    nfe_sum = [0]
+        def __init__(self, mode: str, Bl: int, xs, ys):
+            self.mode, self.B = mode, Bl
+            exact = world > 1 and mode in ("exact", "strong")
+            self.exact = exact
+            gen = torch.Generator().manual_seed(SEED)
+            self.node = R.TrackedNeuralODE(R.MLPDynamics(D, H, generator=gen), [0.0, 1.0], True, True, R.Tsit5(), save_everystep=False,
+                                           reltol=1.4e-8, abstol=1.4e-8, save_start=False, tape_capacity=args.tape_capacity,
+                                           dist_mode=L.DIST_EXACT if exact else L.DIST_SINGLE, rank=rank if exact else 0, world=world if exact else 1)
+            self.clf = R.ClassifierNODE(None, self.node, R.Dense(D, NCLASS, generator=gen))
+            self.clf.p2.copy_(torch.from_numpy(p2_np)); self.clf.p3.copy_(torch.from_numpy(p3_np))
+            self.node.p = self.clf.p2
+            self.opt = R.Optimiser(GAMMA, ETA, RHO)
+            self.xs = [torch.from_numpy(np.ascontiguousarray(x[:, :Bl])).to(dev) for x in xs]            # (D,B) tensors resident in HBM
+            self.ys = [torch.from_numpy(np.ascontiguousarray(y[:, :Bl])).to(dev) for y in ys]
+            self.xs_pin = [torch.from_numpy(np.ascontiguousarray(x[:, :Bl].T)).pin_memory() for x in xs]   # column-major D x B == row-major (B,D)
+            self.ys_pin = [torch.from_numpy(np.ascontiguousarray(y[:, :Bl].T)).pin_memory() for y in ys]
+            self.x_stage = torch.empty(Bl, D, device=dev); self.y_stage = torch.empty(Bl, NCLASS, device=dev)
+            self.loss_pin = torch.empty(1).pin_memory()
 
-    def timed(fn, K):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = launches()
-        e0.record()
-        last = None
-        nfe_sum[0] = 0
-        for i in range(K):
-            last = fn(i)
-            nfe_sum[0] += last["nfe"]
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        ms = max_over_ranks(ms, dev)
-        return ms, last, launches() - l0
+        def train_step(self, x, y):
+            clf, node = self.clf, self.node
+            if self.exact:      # global loss: CE mean over world*B samples, one shared regulariser; gradients are summed
+                out = clf.loss_and_gradient(x, y, lam=LAMBDA, func=R.ERROR_ESTIMATE, agg="mean", ce_scale=1.0 / world)
+                g2, g3 = out["g2"], out["g3"]
+                node.allreduce_(g2, g3)        # one-shot push all-reduce over NVLink peer memory (rnde_allreduce_grads), no NCCL call
+            else:
+                out = clf.loss_and_gradient(x, y, lam=LAMBDA, func=R.ERROR_ESTIMATE, agg="mean")
+                g2, g3 = out["g2"], out["g3"]
+                average_gradients_([g2, g3], world)      # NCCL all-reduce (no-op at world 1)
+            R.update_parameters_((clf.p1, clf.p2, clf.p3), (clf.p1, g2, g3), self.opt)
+            return out
 
-    W, K = max(args.warmup, 3), args.steps
+        def step_resident(self, i):
+            return self.train_step(self.xs[i % NB], self.ys[i % NB])
+
+        def step_e2e(self, i):
+            self.x_stage.copy_(self.xs_pin[i % NB], non_blocking=True)
+            self.y_stage.copy_(self.ys_pin[i % NB], non_blocking=True)
+            out = self.train_step(self.x_stage.t(), self.y_stage.t())
+            self.loss_pin.copy_(out["loss"].reshape(1), non_blocking=False)
+            return out
+
+        def snapshot(self):
+            return (self.clf.p2.clone(), self.clf.p3.clone(), {k: (v["n"], v["v"].clone()) for k, v in self.opt.state.items()})
+
+        def restore(self, snap):
+            self.clf.p2.copy_(snap[0]); self.clf.p3.copy_(snap[1])
+            for k, (n_upd, vel) in snap[2].items():
+                self.opt.state[k]["n"] = n_upd; self.opt.state[k]["v"].copy_(vel)
+
+        def timed(self, fn, first, n):
+            """n steps fn(first), fn(first+1), ... bracketed by barrier + synchronize; device time, max over ranks."""
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0 = self.node.launch_count()
+            e0.record()
+            nfes, naccs, last = [], [], None
+            for i in range(n):
+                last = fn(first + i)
+                nfes.append(last["nfe"]); naccs.append(last["naccept"])
+            e1.record()
+            barrier()
+            ms = max_over_ranks(e0.elapsed_time(e1), dev)
+            flops = sum(flop_per_sample(a, b) for a, b in zip(nfes, naccs)) * self.B * world
+            return {"ms": ms, "nfes": nfes, "naccs": naccs, "last": last, "launches": self.node.launch_count() - l0, "flops": flops}
+
+        def handle(self):
+            return self.node._handle(self.B, L.REG_ERR_DT, True)
+
+    def summarise(tr, r, n):
+        nfe_mean = statistics.mean(r["nfes"])
+        return {"value": tr.B * world * n / (r["ms"] * 1e-3), "unit": "samples/s", "ms_per_step": r["ms"] / n, "nfe_mean": nfe_mean,
+                "us_per_nfe": r["ms"] / n / nfe_mean * 1e3}
+
+    peak, peak_src = ffma_peak_tflops()
+    main_mode = "exact" if world > 1 else "single"
+    tr = Trainer(main_mode, B, xs_np, ys_np)
     for i in range(W):
-        step_resident(i)
+        tr.step_resident(i)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    # both timed phases run the SAME K training steps: the state after warm-up is restored before the end-to-end phase,
-    # so the step-size sequences (NFE drifts as the weights train) and hence the work are identical
-    snap = (clf.p2.clone(), clf.p3.clone(), {k: (v["n"], v["v"].clone()) for k, v in opt.state.items()})
-    ms, last, nlaunch = timed(step_resident, K)
-    nfe_mean = nfe_sum[0] / K
-    clf.p2.copy_(snap[0]); clf.p3.copy_(snap[1])
-    for k, (n_upd, vel) in snap[2].items():
-        opt.state[k]["n"] = n_upd; opt.state[k]["v"].copy_(vel)
-    ms_e2e, last_e2e, _ = timed(step_e2e, K)
+    # every timed phase runs the SAME K training steps: the state after warm-up is restored before each of them, so the
+    # step-size sequences (NFE drifts as the weights train) and hence the work are identical
+    snap = tr.snapshot()
+    res = tr.timed(tr.step_resident, W, K)
+    tr.restore(snap)
+    res_e2e = tr.timed(tr.step_e2e, W, K)
     clocks = sampler.stop() if rank == 0 else {}
 
-    # ---- roofline of the dominant kernel: the fused forward stepper, timed alone with CUDA events ----
-    hd = node._handle(B, L.REG_ERR_DT, True)
+    # ---- fixed work: the controller replays the dt list recorded at the snapshot weights (SURVEY.md 8d) ----
+    tr.restore(snap)
+    hd = tr.handle()
+    tr.step_resident(W)
+    torch.cuda.synchronize()
+    dts = tr.node.steps(B, L.REG_ERR_DT, True)[1]
+    tr.restore(snap)
+    arr = (C.c_float * len(dts))(*dts)
+    hd.check(hd.lib.rnde_set_forced_steps(hd.h, arr, len(dts)), "rnde_set_forced_steps")
+    res_fixed = tr.timed(tr.step_resident, W, K)
+    hd.check(hd.lib.rnde_set_forced_steps(hd.h, None, 0), "rnde_set_forced_steps")
+    tr.restore(snap)
+
+    # ---- roofline of the dominant kernel: the fused forward stepper, timed alone with CUDA events (snapshot weights) ----
     lib = hd.lib
     st = L.Stats()
-    xb = R.colmajor(xs_dev[0]); ub = torch.empty(D * B, device=dev); svb = torch.zeros(args.tape_capacity + 1, device=dev)
+    xb = R.colmajor(tr.xs[0]); ub = torch.empty(D * B, device=dev); svb = torch.zeros(args.tape_capacity + 1, device=dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fw_ms, nfs = [], []
-    for _ in range(5):
-        torch.cuda.synchronize()
+    sptr = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for _ in range(7):
+        barrier()
         e0.record()
-        lib.rnde_forward(hd.h, xb.data_ptr(), clf.p2.data_ptr(), ub.data_ptr(), svb.data_ptr(), None, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        lib.rnde_forward(hd.h, xb.data_ptr(), tr.clf.p2.data_ptr(), ub.data_ptr(), svb.data_ptr(), None, sptr())
         e1.record()
         torch.cuda.synchronize()
-        lib.rnde_forward(hd.h, xb.data_ptr(), clf.p2.data_ptr(), ub.data_ptr(), svb.data_ptr(), C.byref(st), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        lib.rnde_last_stats(hd.h, C.byref(st))
         fw_ms.append(e0.elapsed_time(e1)); nfs.append(st.nf)
     fwd_ms = statistics.median(fw_ms)
     nf = int(statistics.median(nfs))
-    peak, peak_src = ffma_peak_tflops()
     achieved = nf * F_RHS * B / (fwd_ms * 1e-3) / 1e12
     variant = {1: "cta", 2: "stream", 3: "cluster8", 4: "cluster4"}.get(int(lib.rnde_kernel_variant(hd.h)), "?")
-    kname = {"cluster4": "fwd4_kernel<100,98>", "cluster8": "fwd_kernel<8,32,4,true>", "cta": "fwd_kernel<1,32,4,true>", "stream": "fwd_kernel<1,4,1,false>"}.get(variant, "fwd_kernel")
+    arith = {0: "fma_chain", 1: "fixed24", 2: "splitk"}.get(tr.node.arith, "?")
+    kname = {("cluster4", "splitk"): "fwd4s_kernel<100,784>", ("cluster4", "fma_chain"): "fwd4_kernel<100,98>", ("cluster8", "fma_chain"): "fwd_kernel<8,32,4,true>"}.get((variant, arith), "fwd_kernel")
+
+    # ---- the other data-parallel modes (N > 1) ----
+    extra = {}
+    if world > 1:
+        ti = Trainer("independent", B, xs_np, ys_np)
+        for i in range(W):
+            ti.step_resident(i)
+        ri = ti.timed(ti.step_resident, W, K)
+        extra["independent"] = dict(summarise(ti, ri, K), note="every rank its own step-size controller (a different numerical method from the one batched solve); NCCL gradient all-reduce")
+        del ti
+        if B % world == 0 and B // world >= 16:
+            # strong scaling (SURVEY.md 8e): the ONE 512 batch of rank 0's stream, rank r owns columns [r*B/R, (r+1)*B/R)
+            xs0, ys0 = synth_batches(np.random.default_rng(SEED + 1), NB, B)
+            Bl = B // world
+            sl = slice(rank * Bl, (rank + 1) * Bl)
+            ts = Trainer("strong", Bl, [x[:, sl] for x in xs0], [y[:, sl] for y in ys0])
+            for i in range(W):
+                ts.step_resident(i)
+            rs = ts.timed(ts.step_resident, W, K)
+            extra["strong_scaling"] = dict(summarise(ts, rs, K), global_batch=B, per_gpu_batch=Bl,
+                                           note="reference-exact mode on the columns of one global batch of 512")
+            del ts
 
     if rank == 0:
-        total_samples = B * world * K
-        value = total_samples / (ms * 1e-3)
-        e2e_value = total_samples / (ms_e2e * 1e-3)
+        main = summarise(tr, res, K)
+        e2e = summarise(tr, res_e2e, K)
+        fixed = summarise(tr, res_fixed, K)
         h2d = (D * B + NCLASS * B) * 4
-        cb = cpu_baseline(B, 2, warmup=1) if (world == 1 and not args.no_cpu_baseline) else None
-        nacc = last["naccept"]
-        flop_per_sample = (last["nfe"] + 2 + 12 * nacc) * F_RHS
+        cfg = workload_config(B, world)
+        par = "single" if world == 1 else f"dp{world} reference-exact: shared step sequence (in-kernel peer-memory norm exchange), peer-memory gradient all-reduce (rnde_allreduce_grads, no NCCL call)"
         line = {
-            "metric": "mnist_reg_node_train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"mnist_node reg(error_est) train step, MLPDynamics(784,100), batch {B}/GPU, Tsit5 tol 1.4e-8, "
-                                   "Dense(784,10) head, InvDecay+Momentum update",
-                       "global_batch": B * world, "parallelism": (f"dp{world} " + ("reference-exact shared step sequence (in-kernel peer-memory norm exchange)" if exact else "independent-controller") + ", NCCL grad all-reduce") if world > 1 else "single",
-                       "kernel_variant": variant, "nfe_per_step": last["nfe"], "nfe_mean": nfe_mean, "us_per_nfe": ms / K / nfe_mean * 1e3, "naccept": nacc, "nreject": last["nreject"],
-                       "l2": "per-step tape working set (~3.4 MB x records) exceeds the 126 MB L2; inputs rotate over 8 resident batches",
-                       "loss": float(last["loss"]), "flop_per_sample": flop_per_sample},
-            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K},
-            "gpu_launches": int(nlaunch),
+            "metric": "mnist_reg_node_train_samples_per_sec", "value": main["value"], "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": cfg,
+            "run": {"parallelism": par, "kernel_variant": variant, "arith": arith, "nfe_mean": main["nfe_mean"], "us_per_nfe": main["us_per_nfe"],
+                    "nfe_first": res["nfes"][0], "nfe_last": res["nfes"][-1], "naccept_last": res["naccs"][-1], "nreject_last": res["last"]["nreject"],
+                    "loss_last": float(res["last"]["loss"]), "flop_per_sample_mean": res["flops"] / (B * world * K),
+                    "backward": "tensor-core sweep (3-term BF16 cotangents)" if "RNDE_BWD_FFMA" not in os.environ else "FFMA sweep (RNDE_BWD_FFMA=1)"},
+            "e2e": {"value": e2e["value"], "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": e2e["ms_per_step"]},
+            "fixed_work": dict(fixed, n_forced_steps=len(dts), note="controller replays the dt list recorded at the post-warm-up weights: equal NFE every step"),
+            "gpu_launches": int(res["launches"]),
             "clocks": clocks,
             "roofline": {"bound": "fp32_ffma", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": stepper_dram_traffic(), "traffic_unit": "bytes/launch (ncu, tape writes; algorithmic = 3.416 MB x records)", "peak_source": peak_src, "kernel_ms": fwd_ms, "nfe": nf,
-                         "flop_per_launch": nf * F_RHS * B,
-                         "train_step_frac": flop_per_sample * B * world * K / (ms * 1e-3) / 1e12 / (peak * world)},
+                         "frac": achieved / peak, "traffic": stepper_dram_traffic(),
+                         "traffic_unit": "bytes/launch (ncu, tape writes; algorithmic = 3.416 MB x records)", "peak_source": peak_src,
+                         "kernel_ms": fwd_ms, "nfe": nf, "flop_per_launch": nf * F_RHS * B,
+                         "train_step_frac": res["flops"] / (res["ms"] * 1e-3) / 1e12 / (peak * world),
+                         "train_step_frac_note": "sum over the timed steps of (nfe + 2 + 12 naccept) F_rhs B / their device time / FFMA peak"},
         }
-        if cb is not None:
+        line.update(extra)
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_run(B, 2, 1, budget_s=0.0)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["grad_check"] = grad_check(tr, torch, R)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def grad_check(tr, torch, R) -> dict:
+    """Error of the device gradient of the flagship loss (batch 512, lambda 100) at the current weights against the
+    Float64-cotangent adjoint over the same Float32 forward, beside the CPU Float32 adjoint's own error."""
+    from oracle import orc
+    B = tr.B
+    p2 = tr.clf.p2.detach().cpu().numpy().copy(); p3 = tr.clf.p3.detach().cpu().numpy().copy()
+    x, y = tr.xs[0], tr.ys[0]
+    g2 = tr.clf.loss_and_gradient(x, y, lam=LAMBDA, func=R.ERROR_ESTIMATE, agg="mean")["g2"].cpu().numpy().copy()
+    o = orc.Oracle(orc.OracleConfig(D=D, H=H, B=B, kblock1=(D + 7) // 8, reg_kind=orc.REG_ERR_DT, arith=tr.node.arith))
+    xn, yn = x.cpu().numpy(), y.cpu().numpy()
+    _, hi, _, _ = cpu_loss_grad(o, xn, yn, p2, p3, B, hi=True)
+    _, c32, _, _ = cpu_loss_grad(o, xn, yn, p2, p3, B, hi=False)
+    rel = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())
+    return {"e_device": rel(g2, hi), "c_cpu32": rel(c32, hi), "what": "max-norm relative error of dL/dp2 vs the Float64-cotangent adjoint of the same Float32 forward"}
 
 
 def main():
@@ -387,8 +505,6 @@ def main():
     ap.add_argument("--batch", type=int, default=512, help="samples per GPU")
     ap.add_argument("--tape-capacity", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--dist", default="independent", choices=["independent", "exact"],
-                    help="N>1: independent step-size controllers per rank (default) or the reference-exact shared step sequence")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

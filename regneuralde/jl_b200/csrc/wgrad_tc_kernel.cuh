@@ -1,23 +1,31 @@
 // wgrad_tc_kernel.cuh -- the weight-gradient contractions on the 5th-gen tensor cores (tcgen05),
 // Float32 accuracy preserved by the 3xTF32 split  a*b ~= ah*bh + ah*bl + al*bh  (north_star item 2:
 // "tensor cores only where batch x hidden makes a real dense contraction": here the contraction
-// length is nrec*B ~ 1e5).  Same operands, ordering and FP64 partial sums as wgrad_kernel.cuh.
+// length is nrec*B ~ 1e5).  Same operands and FP64 partial sums as wgrad_kernel.cuh.
 //
-// One CTA = one 128 x 128 output tile x one contiguous range of the contraction (split-K).
+// Contraction order (round 2).  The regulariser puts +-O(10) cotangents on the stages of one step that cancel to
+// O(1e-2), and the tensor core ACCUMULATES WITH TRUNCATION: a running sum that swings to O(10) and
+// back picks up a one-sided error at every add, coherent over all columns and steps -- measured 2.3x (error estimate) and
+// 5.4x (error + stiffness estimate) the error of a CPU Float32 adjoint, reproduced on the CPU by truncating adds
+// (profiles/r2b_grad_err.txt; with the FFMA contraction the same sweep is 4x BETTER than the CPU adjoint).  So the cancelling
+// terms must meet INSIDE one MMA, whose 8-term dot product is summed before it touches the accumulator: the K index of
+// an MMA K-block is now the 6 records of one step (+ record 0 in the first step's spare slot + a zero) for ONE batch
+// column, instead of 8 columns of one record.  A stage = (step, column tile, column quad) = 4 K-blocks; the accumulator
+// only ever sees the small per-step sums.
+//
+// One CTA = one 128 x 128 output tile x one contiguous range of stages (split-K).
 // Warp roles (416 threads):
-//   warps 0-7  load + split: cp.async the raw FP32 operand chunks of a stage (32 contraction entries)
-//              straight into the UMMA K-major no-swizzle core-matrix layout, then replace them by
-//              hi = tf32_rn(x) and write lo = tf32_rn(x - hi) next to them (round-to-nearest split),
-//              fence.proxy.async, arrive on ready[stage].
+//   warps 0-7  load + split: thread = (operand, row); per stage 6-7 LDG.128 (4 columns of each record of the group; the
+//              loads of stage g+1 are in flight while stage g is converted), a register transposition to record-major,
+//              hi = tf32_rn(x), lo = tf32_rn(x - hi), 16 STS.128 into the UMMA K-major no-swizzle core-matrix layout
+//              (8-row groups 1152 bytes apart: the 32 rows of a warp store conflict free), fence.proxy.async,
+//              arrive on ready[stage].
 //   warp 8     one elected lane issues 4 K-blocks x 3 tcgen05.mma.kind::tf32 (M128 N128 K8) per stage
-//              into a TMEM accumulator, tcgen05.commit -> empty[stage]; every WGT_FLUSH stages the
+//              into a TMEM accumulator, tcgen05.commit -> empty[stage]; every `flush` stages the
 //              accumulator buffer is committed to the epilogue and the other TMEM buffer is used.
-//   warps 9-12 epilogue: tcgen05.ld the 128 x 128 FP32 accumulator (lane = output row) and add it
-//              into the CTA's private FP64 partial tile in global memory (exclusive owner: plain
-//              read-modify-write, deterministic), release the TMEM buffer.
-//              [now: every chunk is stored to its own FP32 slot; the FP64 summation over
-//               (split, chunk) happens in the fixed-order reduce kernel -- no read-modify-write]
-// Shared memory: 3 stages x (A_hi, A_lo, B_hi, B_lo) x 16 KB = 192 KB.  TMEM: 2 x 128 columns.
+//   warps 9-12 epilogue: tcgen05.ld the 128 x 128 FP32 accumulator (lane = output row); every chunk is stored to its
+//              own FP32 slot; the FP64 summation over (split, chunk) happens in the fixed-order reduce kernel.
+// Shared memory: 3 stages x (A_hi, A_lo, B_hi, B_lo) x 18 KB = 216 KB.  TMEM: 2 x 128 columns.
 #pragma once
 #include "common.cuh"
 #include "fwd4_kernel.cuh"      // mbarrier wrappers
@@ -32,7 +40,8 @@ constexpr int WGT_FLUSH_MIN = 16;          // stages per FP32 accumulation chunk
 constexpr int WGT_MAXCHUNK = 16;           // chunks per split (bounds the partial workspace)
 constexpr int WGT_LOADERS = 256;
 constexpr int WGT_THREADS = 32 * (8 + 1 + 4);
-constexpr int WGT_PART_BYTES = 128 * WGT_KC * 4;                  // one operand part of a stage: 16 KB
+constexpr int WGT_SBO = 1152;                                     // stride of 8-row groups: 1024 + 128 (conflict-free row-parallel stores)
+constexpr int WGT_PART_BYTES = 16 * WGT_SBO;                      // one operand part of a stage: 128 rows x 32 entries, 18 KB
 constexpr int WGT_STAGE_BYTES = 4 * WGT_PART_BYTES;               // A_hi, A_lo, B_hi, B_lo
 constexpr size_t WGT_SMEM = (size_t)WGT_STAGES * WGT_STAGE_BYTES + 256;
 constexpr int WGT_SPLITS = 21;             // 7 tiles x 21 splits = 147 CTAs: one wave on 148 SMs
@@ -62,12 +71,13 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
 }
 __device__ __forceinline__ void mbar_arrive_local(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 
-// A: [tiles][M][16], Bm: [tiles][Nrows][16] (physical tile = rec*Q + q); partial: [split][chunk][Naug][M] floats
+// A: [tiles][M][16], Bm: [tiles][Nrows][16] (physical tile = rec*Q + q); partial: [split][chunk][Naug][M] floats.
+// Stage sg = ((s*Q + q) << 2) | cq : step s, column tile q, columns [4cq, 4cq+4) of the tile; K slot j of a column = record
+// 1+6s+j (j < 6), record 0 (j = 6, s = 0 only), zero otherwise.
 __global__ void __launch_bounds__(WGT_THREADS, 1) wgrad_tc_kernel(const float* __restrict__ A, int M, const float* __restrict__ Bm, int Nrows,
-                                                                 int ntiles, int Q, const StepRec* __restrict__ steps, float t0, int td,
+                                                                 int nsteps, int Q, const StepRec* __restrict__ steps, float t0, int td,
                                                                  int flush, float* __restrict__ partial) {
     constexpr int NP = 16;
-    constexpr int TPS = WGT_KC / NP;              // tiles per stage = 2
     extern __shared__ __align__(1024) unsigned char tsm[];
     const uint32_t sbase = smem_u32(tsm);
     uint64_t* bars = reinterpret_cast<uint64_t*>(tsm + (size_t)WGT_STAGES * WGT_STAGE_BYTES);
@@ -81,9 +91,10 @@ __global__ void __launch_bounds__(WGT_THREADS, 1) wgrad_tc_kernel(const float* _
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m_base = blockIdx.x * WGT_M, n_base = blockIdx.y * WGT_N;
     const int Naug = Nrows + 2;
-    const int per = (ntiles + gridDim.z - 1) / gridDim.z;
-    const int tile0 = blockIdx.z * per, tile1 = min(ntiles, tile0 + per);
-    const int nstage = (tile1 - tile0 + TPS - 1) / TPS;
+    const int NS = max(nsteps, 1) * Q * 4;                 // stages in all
+    const int per = (NS + gridDim.z - 1) / gridDim.z;
+    const int stage0 = blockIdx.z * per, stage1 = min(NS, stage0 + per);
+    const int nstage = max(stage1 - stage0, 0);
     const int nchunk = (nstage + flush - 1) / flush;
 
     if (tid == 0) {
@@ -101,70 +112,66 @@ __global__ void __launch_bounds__(WGT_THREADS, 1) wgrad_tc_kernel(const float* _
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < 8) {
-        // ================= loaders / splitters =================
-        // warp w owns (operand = w>>2, tile-in-stage = (w>>1)&1, row groups [8*(w&1), 8*(w&1)+8)); inside a row group
-        // lane -> (row r8 = lane & 7, 16-byte chunk k4 = lane >> 3): the warp reads 8 rows x 64 B = 512 contiguous bytes
-        // of the tape and writes four conflict-free 128-byte core-matrix rows.  No index arithmetic in the loop.
-        const int r8 = lane & 7, k4 = lane >> 3;
-        const int opnd = warp >> 2, sub = (warp >> 1) & 1, rg0 = (warp & 1) * 8;
+        // ================= loaders / splitters: thread = (operand, row) =================
+        const int opnd = tid >> 7, row = tid & 127;
         const float* gsrc = opnd ? Bm : A;
         const int nrows_src = opnd ? Nrows : M;                  // rows that exist in the tape operand
-        const int row_base = (opnd ? n_base : m_base) + rg0 * 8 + r8;
-        const uint32_t lane_dst = (uint32_t)((opnd ? 2 * WGT_PART_BYTES : 0) + rg0 * 1024 + (sub * 4 + k4) * 128 + r8 * 16);
-        auto issue = [&](int g) {
-            unsigned char* stage = tsm + (size_t)(g % WGT_STAGES) * WGT_STAGE_BYTES;
-            const int tt = tile0 + g * TPS + sub;
-            const bool live = tt < tile1;
-            int rec = 0, q = 0;
-            if (live) tile_of(tt, Q, rec, q);
-            const float* src = gsrc + (((size_t)rec * Q + q) * nrows_src + row_base) * NP + k4 * 4;
-            float augv = 0.f, onev = 0.f;
-            if (opnd && live) { augv = td ? rec_time(steps, t0, rec) : 0.f; onev = 1.f; }
-            unsigned char* dst = stage + lane_dst;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int row = row_base + i * 8;
-                if (live && row < nrows_src) cp_async16(dst + i * 1024, src + (size_t)i * 8 * NP);
-                else {
-                    float v = 0.f;
-                    if (opnd && row == Nrows) v = augv;
-                    else if (opnd && row == Nrows + 1) v = onev;
-                    *reinterpret_cast<float4*>(dst + i * 1024) = make_float4(v, v, v, v);
-                }
-            }
-            cp_async_commit();
-        };
-        // Round-to-nearest split (round 2): hi = tf32_rn(x) is written back over the raw value, lo = tf32_rn(x - hi) (the
-        // subtraction is exact).  The round-1 split left the truncation to the tensor core (hi = top 11 bits, lo >= 0 with 13
-        // bits of which the MMA keeps 11) -- a one-sided error of up to 2^-21 per operand plus a dropped lo*lo of up to
-        // 2^-20 per product, ~4x the rounding noise of an FP32 fma, which showed up 3x in the regulariser gradient
-        // (profiles/r2a_grad_err.txt).  Now |x - hi - lo| <= 2^-24 |x| and |lo*lo| <= 2^-22 |x y|, both signed.
+        const int grow = (opnd ? n_base : m_base) + row;
+        const bool real_row = grow < nrows_src;
+        const bool aug_t = opnd && grow == Nrows, aug_1 = opnd && grow == Nrows + 1;
+        const uint32_t dst_off = (uint32_t)((opnd ? 2 * WGT_PART_BYTES : 0) + (row >> 3) * WGT_SBO + (row & 7) * 16);
         auto tf32_rn = [](float v) -> float { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v)); return __uint_as_float(r); };
-        auto split = [&](int g) {
-            unsigned char* hi = tsm + (size_t)(g % WGT_STAGES) * WGT_STAGE_BYTES + lane_dst;
+        auto issue = [&](int g, float4 (&buf)[7]) {
+            const int sg = stage0 + g;
+            const int grp = sg >> 2, cq = sg & 3;
+            const int s = grp / Q, q = grp - s * Q;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float4 x = *reinterpret_cast<const float4*>(hi + i * 1024);
-                const float4 h = make_float4(tf32_rn(x.x), tf32_rn(x.y), tf32_rn(x.z), tf32_rn(x.w));
-                const float4 lo = make_float4(tf32_rn(x.x - h.x), tf32_rn(x.y - h.y), tf32_rn(x.z - h.z), tf32_rn(x.w - h.w));
-                *reinterpret_cast<float4*>(hi + i * 1024) = h;
-                *reinterpret_cast<float4*>(hi + i * 1024 + WGT_PART_BYTES) = lo;
+            for (int j = 0; j < 7; ++j) {
+                const int rec = (j < 6) ? 1 + 6 * s + j : 0;
+                const bool have = (j < 6) ? (s < nsteps) : (s == 0);
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (have) {
+                    if (real_row) v = __ldg(reinterpret_cast<const float4*>(gsrc + (((size_t)rec * Q + q) * nrows_src + grow) * NP + cq * 4));
+                    else if (aug_t) { const float tv = td ? rec_time(steps, t0, rec) : 0.f; v = make_float4(tv, tv, tv, tv); }
+                    else if (aug_1) v = make_float4(1.f, 1.f, 1.f, 1.f);
+                }
+                buf[j] = v;
             }
         };
-        // software pipeline: loads of stage g+1 are in flight while stage g is split and published
-        if (nstage > 0) issue(0);
-        for (int g = 0; g < nstage; ++g) {
-            if (g + 1 < nstage) {
-                const int bn = (g + 1) % WGT_STAGES;
-                if (g + 1 >= WGT_STAGES) mbar_wait(bar_empty(bn), (uint32_t)(((g + 1) / WGT_STAGES - 1) & 1));
-                issue(g + 1);
-                cp_async_wait<1>();
-            } else {
-                cp_async_wait<0>();
+        // x = hi + lo (+ <= 2^-24 |x|), both rounded to nearest TF32; column c of the quad -> K-block c, slots 0-3 | 4-7
+        auto convert_store = [&](int g, const float4 (&buf)[7]) {
+            unsigned char* st = tsm + (size_t)(g % WGT_STAGES) * WGT_STAGE_BYTES + dst_off;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float v[8], hi[8], lo[8];
+#pragma unroll
+                for (int j = 0; j < 7; ++j) v[j] = (c == 0) ? buf[j].x : (c == 1) ? buf[j].y : (c == 2) ? buf[j].z : buf[j].w;
+                v[7] = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { hi[j] = tf32_rn(v[j]); lo[j] = tf32_rn(v[j] - hi[j]); }
+                *reinterpret_cast<float4*>(st + c * 256) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4*>(st + c * 256 + 128) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+                *reinterpret_cast<float4*>(st + WGT_PART_BYTES + c * 256) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                *reinterpret_cast<float4*>(st + WGT_PART_BYTES + c * 256 + 128) = make_float4(lo[4], lo[5], lo[6], lo[7]);
             }
-            split(g);        // each lane splits exactly the chunks it loaded itself
+        };
+        auto publish = [&](int g, const float4 (&buf)[7]) {
+            const int b = g % WGT_STAGES;
+            if (g >= WGT_STAGES) mbar_wait(bar_empty(b), (uint32_t)((g / WGT_STAGES - 1) & 1));
+            convert_store(g, buf);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive_local(bar_ready(g % WGT_STAGES));
+            mbar_arrive_local(bar_ready(b));
+        };
+        // software pipeline over register buffers: the loads of stage g+1 are in flight while stage g is converted
+        float4 bufA[7], bufB[7];
+        if (nstage > 0) issue(0, bufA);
+        for (int g = 0; g < nstage; g += 2) {
+            if (g + 1 < nstage) issue(g + 1, bufB);
+            publish(g, bufA);
+            if (g + 1 < nstage) {
+                if (g + 2 < nstage) issue(g + 2, bufA);
+                publish(g + 1, bufB);
+            }
         }
     } else if (warp == 8) {
         // ================= MMA issuer =================
@@ -182,13 +189,14 @@ __global__ void __launch_bounds__(WGT_THREADS, 1) wgrad_tc_kernel(const float* _
                 const uint32_t d_tmem = tmem_base + acc * 128;
 #pragma unroll
                 for (int kb = 0; kb < WGT_KC / 8; ++kb) {
-                    const uint64_t a_hi = umma_desc(st + kb * 256, 128, 1024);
-                    const uint64_t a_lo = umma_desc(st + WGT_PART_BYTES + kb * 256, 128, 1024);
-                    const uint64_t b_hi = umma_desc(st + 2 * WGT_PART_BYTES + kb * 256, 128, 1024);
-                    const uint64_t b_lo = umma_desc(st + 3 * WGT_PART_BYTES + kb * 256, 128, 1024);
-                    tc_mma_tf32(d_tmem, a_hi, b_hi, idesc, (first_in_chunk && kb == 0) ? 0u : 1u);
-                    tc_mma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
+                    const uint64_t a_hi = umma_desc(st + kb * 256, 128, WGT_SBO);
+                    const uint64_t a_lo = umma_desc(st + WGT_PART_BYTES + kb * 256, 128, WGT_SBO);
+                    const uint64_t b_hi = umma_desc(st + 2 * WGT_PART_BYTES + kb * 256, 128, WGT_SBO);
+                    const uint64_t b_lo = umma_desc(st + 3 * WGT_PART_BYTES + kb * 256, 128, WGT_SBO);
+                    // the small products first: the accumulator receives hi*hi last
+                    tc_mma_tf32(d_tmem, a_hi, b_lo, idesc, (first_in_chunk && kb == 0) ? 0u : 1u);
                     tc_mma_tf32(d_tmem, a_lo, b_hi, idesc, 1u);
+                    tc_mma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
                 }
                 tc_commit(bar_empty(b));                                  // stage buffer free when these MMAs retire
                 if ((g % flush) == flush - 1 || g == nstage - 1) tc_commit(bar_accfull(acc));
@@ -196,7 +204,7 @@ __global__ void __launch_bounds__(WGT_THREADS, 1) wgrad_tc_kernel(const float* _
             __syncwarp();
         }
     } else {
-        // ================= epilogue: TMEM -> FP64 partial tile in global memory =================
+        // ================= epilogue: TMEM -> FP32 chunk slots in global memory =================
         const int quad = warp & 3;                    // TMEM lanes [32*quad, 32*quad+32) are this warp's
         const int row = quad * 32 + lane;
         const int m = m_base + row;
@@ -237,17 +245,17 @@ __global__ void __launch_bounds__(WGT_THREADS, 1) wgrad_tc_kernel(const float* _
 }
 
 // fixed-order FP64 sum over splits of the [split][n][m] partials; scatter into Flux.destructure layout
-__global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, int nsplit, int ntiles, int flush, int M, int Nrows, int td,
+__global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, int nsplit, int NS, int flush, int M, int Nrows, int td,
                                        float* __restrict__ outW, float* __restrict__ outb) {
     const int Naug = Nrows + 2;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= M * Naug) return;
     const int n = idx / M, m = idx - n * M;
-    const int per = (ntiles + nsplit - 1) / nsplit;
+    const int per = (NS + nsplit - 1) / nsplit;
     double s = 0.0;
     for (int sp = 0; sp < nsplit; ++sp) {       // the chunks each split really produced (same arithmetic as wgrad_tc_kernel), in order
-        const int tile0 = sp * per, tile1 = min(ntiles, tile0 + per);
-        const int nstage = (max(tile1 - tile0, 0) + 1) / 2;
+        const int stage0 = sp * per, stage1 = min(NS, stage0 + per);
+        const int nstage = max(stage1 - stage0, 0);
         const int nchunk = (nstage + flush - 1) / flush;
         for (int ch = 0; ch < nchunk; ++ch) s += (double)partial[(((size_t)sp * WGT_MAXCHUNK + ch) * Naug + n) * M + m];
     }
@@ -259,11 +267,12 @@ __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, int ns
 static int launch_wgrad_tc(int D, int H, int td, int nrec, int Q, const float* tapeZ, const float* tapeD2, const float* tapeH,
                            const float* tapeD1, const StepRec* steps, float t0, float* ws, float* dp, cudaStream_t st, int64_t* launches) {
     cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WGT_SMEM);
-    const int ntiles = nrec * Q;
+    const int nsteps = (nrec - 1) / 6;
+    const int NS = (nsteps > 0 ? nsteps : 1) * Q * 4;       // stages: (step, column tile, column quad)
     int nsplit = WGT_SPLITS;
-    if (ntiles < nsplit * 2) nsplit = (ntiles + 1) / 2;
+    if (NS < nsplit) nsplit = NS;
     if (nsplit < 1) nsplit = 1;
-    const int per = (ntiles + nsplit - 1) / nsplit, nstage = (per + 1) / 2;
+    const int nstage = (NS + nsplit - 1) / nsplit;
     int flush = (nstage + WGT_MAXCHUNK - 1) / WGT_MAXCHUNK;
     if (flush < WGT_FLUSH_MIN) flush = WGT_FLUSH_MIN;
     float* wsd = ws;
@@ -273,15 +282,15 @@ static int launch_wgrad_tc(int D, int H, int td, int nrec, int Q, const float* t
     float* db2 = dW2 + (size_t)D * (H + td);
     {   // dW1aug = delta1 . [Z; t; 1]^T      (M = H, N = D + 2)
         dim3 grid((H + WGT_M - 1) / WGT_M, (D + 2 + WGT_N - 1) / WGT_N, nsplit);
-        wgrad_tc_kernel<<<grid, WGT_THREADS, WGT_SMEM, st>>>(tapeD1, H, tapeZ, D, ntiles, Q, steps, t0, td, flush, wsd);
+        wgrad_tc_kernel<<<grid, WGT_THREADS, WGT_SMEM, st>>>(tapeD1, H, tapeZ, D, nsteps, Q, steps, t0, td, flush, wsd);
         const int tot = H * (D + 2);
-        wgrad_tc_reduce_kernel<<<(tot + 255) / 256, 256, 0, st>>>(wsd, nsplit, ntiles, flush, H, D, td, dW1, db1);
+        wgrad_tc_reduce_kernel<<<(tot + 255) / 256, 256, 0, st>>>(wsd, nsplit, NS, flush, H, D, td, dW1, db1);
     }
     {   // dW2aug = delta2 . [Hact; t; 1]^T   (M = D, N = H + 2)
         dim3 grid((D + WGT_M - 1) / WGT_M, (H + 2 + WGT_N - 1) / WGT_N, nsplit);
-        wgrad_tc_kernel<<<grid, WGT_THREADS, WGT_SMEM, st>>>(tapeD2, D, tapeH, H, ntiles, Q, steps, t0, td, flush, wsd);
+        wgrad_tc_kernel<<<grid, WGT_THREADS, WGT_SMEM, st>>>(tapeD2, D, tapeH, H, nsteps, Q, steps, t0, td, flush, wsd);
         const int tot = D * (H + 2);
-        wgrad_tc_reduce_kernel<<<(tot + 255) / 256, 256, 0, st>>>(wsd, nsplit, ntiles, flush, D, H, td, dW2, db2);
+        wgrad_tc_reduce_kernel<<<(tot + 255) / 256, 256, 0, st>>>(wsd, nsplit, NS, flush, D, H, td, dW2, db2);
     }
     if (launches) *launches += 4;
     return (int)cudaGetLastError();
