@@ -16,7 +16,7 @@
 // One CTA = one 128 x 128 output tile x one contiguous range of stages (split-K).
 // Warp roles (416 threads):
 //   warps 0-7  load + split: thread = (operand, row); per stage 6-7 LDG.128 (4 columns of each record of the group; the
-//              loads of stage g+1 are in flight while stage g is converted), a register transposition to record-major,
+//              loads of stages g+1 and g+2 are in flight while stage g is converted), a register transposition to record-major,
 //              hi = tf32_rn(x), lo = tf32_rn(x - hi), 16 STS.128 into the UMMA K-major no-swizzle core-matrix layout
 //              (8-row groups 1152 bytes apart: the 32 rows of a warp store conflict free), fence.proxy.async,
 //              arrive on ready[stage].
@@ -132,11 +132,24 @@ __global__ void __launch_bounds__(WGT_THREADS, 1) wgrad_tc_kernel(const float* _
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (have) {
                     if (real_row) v = __ldg(reinterpret_cast<const float4*>(gsrc + (((size_t)rec * Q + q) * nrows_src + grow) * NP + cq * 4));
-                    else if (aug_t) { const float tv = td ? rec_time(steps, t0, rec) : 0.f; v = make_float4(tv, tv, tv, tv); }
                     else if (aug_1) v = make_float4(1.f, 1.f, 1.f, 1.f);
                 }
                 buf[j] = v;
             }
+            // the time row: fetch the step record (t, dt, ...) like any other operand -- asynchronously; the stage times are
+            // formed from it in convert_store (a dependent load here would stall this thread, and with it the stage, once per stage)
+            if (aug_t && td) {
+                buf[0] = (s < nsteps) ? __ldg(reinterpret_cast<const float4*>(steps + s)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                buf[1] = make_float4((s < nsteps) ? 1.f : 0.f, (s == 0) ? 1.f : 0.f, 0.f, 0.f);      // which slots are live
+            }
+        };
+        auto time_row = [&](float4 (&buf)[7]) {      // expand (t, dt) of the step into the 7 slot times (same arithmetic as rec_time)
+            const float st = buf[0].x, sdt = buf[0].y;
+            const bool live6 = buf[1].x != 0.f, live0 = buf[1].y != 0.f;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) { const float tv = live6 ? stage_time(st, sdt, j + 2) : 0.f; buf[j] = make_float4(tv, tv, tv, tv); }
+            const float tz = live0 ? t0 : 0.f;
+            buf[6] = make_float4(tz, tz, tz, tz);
         };
         // x = hi + lo (+ <= 2^-24 |x|), both rounded to nearest TF32; column c of the quad -> K-block c, slots 0-3 | 4-7
         auto convert_store = [&](int g, const float4 (&buf)[7]) {
@@ -155,22 +168,28 @@ __global__ void __launch_bounds__(WGT_THREADS, 1) wgrad_tc_kernel(const float* _
                 *reinterpret_cast<float4*>(st + WGT_PART_BYTES + c * 256 + 128) = make_float4(lo[4], lo[5], lo[6], lo[7]);
             }
         };
-        auto publish = [&](int g, const float4 (&buf)[7]) {
+        auto publish = [&](int g, float4 (&buf)[7]) {
             const int b = g % WGT_STAGES;
+            if (aug_t && td) time_row(buf);
             if (g >= WGT_STAGES) mbar_wait(bar_empty(b), (uint32_t)((g / WGT_STAGES - 1) & 1));
             convert_store(g, buf);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive_local(bar_ready(b));
         };
-        // software pipeline over register buffers: the loads of stage g+1 are in flight while stage g is converted
-        float4 bufA[7], bufB[7];
+        // software pipeline over three register buffers: the loads of stages g+1 and g+2 are in flight while stage g is converted
+        float4 bufA[7], bufB[7], bufC[7];
         if (nstage > 0) issue(0, bufA);
-        for (int g = 0; g < nstage; g += 2) {
-            if (g + 1 < nstage) issue(g + 1, bufB);
+        if (nstage > 1) issue(1, bufB);
+        for (int g = 0; g < nstage; g += 3) {
+            if (g + 2 < nstage) issue(g + 2, bufC);
             publish(g, bufA);
             if (g + 1 < nstage) {
-                if (g + 2 < nstage) issue(g + 2, bufA);
+                if (g + 3 < nstage) issue(g + 3, bufA);
                 publish(g + 1, bufB);
+            }
+            if (g + 2 < nstage) {
+                if (g + 4 < nstage) issue(g + 4, bufB);
+                publish(g + 2, bufC);
             }
         }
     } else if (warp == 8) {

@@ -8,6 +8,8 @@ import pytest
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
+GRAD_BAR = 1.5      # at most 1.5x the CPU Float32 adjoint's own error where that exceeds 1e-4
+
 from oracle import gru_oracle as G  # noqa: E402  (the checker)
 from oracle import orc              # noqa: E402
 
@@ -107,6 +109,6 @@ def test_latent_ode_training_loss_and_gradients(oracle_built):
     e1, e2 = rel(ps[0].grad.cpu().numpy(), p1.grad.numpy()), rel(ps[1].grad.cpu().numpy(), p2.grad.numpy())
     e3, e4 = rel(ps[2].grad.cpu().numpy(), dp3_hi), rel(ps[3].grad.cpu().numpy(), p4.grad.numpy())
     assert e4 <= 1e-4, e4
-    assert e3 <= max(1e-4, 10 * c3), (e3, c3)
+    assert e3 <= max(1e-4, GRAD_BAR * c3), (e3, c3)
     cz = rel(dz0_32, dz0_hi)
-    assert e1 <= max(1e-4, 10 * cz) and e2 <= max(1e-4, 10 * cz), (e1, e2, cz)
+    assert e1 <= max(1e-4, GRAD_BAR * cz) and e2 <= max(1e-4, GRAD_BAR * cz), (e1, e2, cz)

@@ -4,8 +4,10 @@ TDChain(Dense(3,10,tanh), Dense(11,2)), x 2xB, tspan [0,1], reltol = abstol = 1.
 and experiments/mnist_node.jl (MLPDynamics(784,100), batch 512, the three regulariser closures).
 
 Bars (BASELINE.json north_star): accepted steps and NFE identical; trajectory / saved values / loss -- we get
-BIT-identical Float32 (tolerance 0 is asserted); gradient relative error <= 1e-4 wherever an FP32 adjoint is
-that well conditioned (see DESIGN.md "gradient conditioning"), otherwise within 10x of the CPU FP32 adjoint's own error."""
+BIT-identical Float32 (tolerance 0 is asserted); gradient relative error <= 1e-4 against the Float64-cotangent adjoint of the
+same Float32 forward wherever a Float32 adjoint is that well conditioned (c_cpu32 <= 1e-4); where it is not (the
+regulariser gradient cancels O(10) cotangents) the CUDA adjoint must be at most GRAD_BAR = 1.5 times
+as far from that yardstick as the plain CPU Float32 adjoint is."""
 import ctypes as C
 
 import numpy as np
@@ -13,6 +15,8 @@ import pytest
 
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
+
+GRAD_BAR = 1.5
 
 from oracle import orc  # noqa: E402  (the checker)
 
@@ -137,7 +141,7 @@ def test_gradient_matches_oracle(oracle_built, name, D, H, B, act_out, auto, fun
     c_p, c_x = rel(dp_32, dp_hi), rel(dx_32, dx_hi)
     if tol is not None:
         assert e_p <= tol and e_x <= tol, (e_p, e_x)
-    assert e_p <= max(1e-4, 10 * c_p) and e_x <= max(1e-4, 10 * c_x), (e_p, c_p, e_x, c_x)
+    assert e_p <= max(1e-4, GRAD_BAR * c_p) and e_x <= max(1e-4, GRAD_BAR * c_x), (e_p, c_p, e_x, c_x)
 
 
 def test_mnist_training_step_against_oracle(oracle_built):
@@ -181,7 +185,7 @@ def test_mnist_training_step_against_oracle(oracle_built):
     assert e3 <= 1e-4, e3
     # The regulariser part of dL/dp2 is ill-conditioned in ANY FP32 adjoint at reltol 1.4e-8 (the CPU FP32 adjoint
     # itself is ~0.5% off on this loss, ~8% on the regulariser part alone: DESIGN.md "gradient conditioning").
-    assert e2 <= max(1e-4, 10 * rel(dp2_32, dp2_hi)), (e2, rel(dp2_32, dp2_hi))
+    assert e2 <= max(1e-4, GRAD_BAR * rel(dp2_32, dp2_hi)), (e2, rel(dp2_32, dp2_hi))
     # the cross-entropy part alone is well conditioned: <= 1e-4 (measured ~1e-6)
     out0 = clf.loss_and_gradient(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), lam=0.0, func=r.ERROR_ESTIMATE, agg="mean")
     dp2_ce, _, _, _ = o.backward(du, 0 * dsv, hi=True)
@@ -194,7 +198,7 @@ def test_mnist_training_step_against_oracle(oracle_built):
     l2.backward()
     assert abs(float(l2) - float(out["loss"])) <= 1e-5 * abs(float(l2))
     # two FP32 evaluations with cotangents that differ in the last bit: equal up to the adjoint's rounding noise
-    assert rel(pp2.grad.cpu().numpy(), dp2_hi) <= max(1e-4, 10 * rel(dp2_32, dp2_hi))
+    assert rel(pp2.grad.cpu().numpy(), dp2_hi) <= max(1e-4, GRAD_BAR * rel(dp2_32, dp2_hi))
 
 
 SAVEAT_CASES = [
@@ -255,7 +259,7 @@ def test_saveat_multi_save_functors(oracle_built, name, D, H, B, act_out, auto, 
     rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()
     e_p, e_x = rel(p.grad.cpu().numpy(), dp_hi), rel(x.grad.cpu().numpy(), dx_hi)
     c_p, c_x = rel(dp_32, dp_hi), rel(dx_32, dx_hi)
-    assert e_p <= max(1e-4, 10 * c_p) and e_x <= max(1e-4, 10 * c_x), (e_p, c_p, e_x, c_x)
+    assert e_p <= max(1e-4, GRAD_BAR * c_p) and e_x <= max(1e-4, GRAD_BAR * c_x), (e_p, c_p, e_x, c_x)
     if not regularize:
         assert e_p <= 1e-4 and e_x <= 1e-4, (e_p, e_x)
     # per-call saveat keyword (update_saveat!): a different grid on the same node, then the stored grid is back
@@ -333,7 +337,7 @@ def test_chain_field_latent_ode(oracle_built, name, D, widths, acts, pre_act, B,
     rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()
     e_p, e_x = rel(p.grad.cpu().numpy(), dp_hi), rel(x.grad.cpu().numpy(), dx_hi)
     c_p, c_x = rel(dp_32, dp_hi), rel(dx_32, dx_hi)
-    assert e_p <= max(1e-4, 10 * c_p) and e_x <= max(1e-4, 10 * c_x), (e_p, c_p, e_x, c_x)
+    assert e_p <= max(1e-4, GRAD_BAR * c_p) and e_x <= max(1e-4, GRAD_BAR * c_x), (e_p, c_p, e_x, c_x)
     if not regularize:
         assert e_p <= 1e-4 and e_x <= 1e-4, (e_p, e_x)
 
@@ -352,7 +356,7 @@ x = torch.from_numpy(x_np).cuda().requires_grad_(True); p = torch.from_numpy(p_n
 res, nfe, sv = node(x, p, func=r.ERROR_PLUS_STIFFNESS)
 ws = rng.standard_normal(len(sv)).astype(np.float32)
 ((res * torch.from_numpy(w).cuda()).sum() + (sv.saveval * torch.from_numpy(ws).cuda()).sum()).backward()
-np.savez(sys.argv[1], dp=p.grad.cpu().numpy(), dx=x.grad.cpu().numpy(), w=w, ws=ws, x=x_np, p=p_np, nfe=nfe)
+np.savez(sys.argv[1], dp=p.grad.cpu().numpy(), dx=x.grad.cpu().numpy(), w=w, ws=ws, x=x_np, p=p_np, nfe=nfe, arith=node.arith)
 """
 
 
@@ -371,15 +375,36 @@ def test_tensor_core_sweep_agrees_with_ffma_sweep(oracle_built, tmp_path):
     assert int(a["nfe"]) == int(b["nfe"])
     rel = lambda u, v: np.abs(u - v).max() / np.abs(v).max()
     D, H, B = 784, 100, 80
-    o = orc.Oracle(oracle_cfg(D, H, B, 1, 1, orc.REG_ERR_PLUS_STIFF, arith=node.arith))
+    o = orc.Oracle(oracle_cfg(D, H, B, 1, 1, orc.REG_ERR_PLUS_STIFF, arith=int(a["arith"])))
     o.forward(a["x"], a["p"])
     dp_hi, dx_hi, _, _ = o.backward(a["w"], a["ws"], hi=True)
     dp_32, dx_32, _, _ = o.backward(a["w"], a["ws"])
     for name, g in outs.items():
         e_p, e_x = rel(g["dp"], dp_hi), rel(g["dx"], dx_hi)
-        assert e_p <= max(1e-4, 10 * rel(dp_32, dp_hi)) and e_x <= max(1e-4, 10 * rel(dx_32, dx_hi)), (name, e_p, e_x)
+        assert e_p <= max(1e-4, GRAD_BAR * rel(dp_32, dp_hi)) and e_x <= max(1e-4, GRAD_BAR * rel(dx_32, dx_hi)), (name, e_p, e_x)
     # the two sweeps see the same tape: they differ only by the rounding of their products
-    assert rel(a["dx"], b["dx"]) <= max(1e-4, 10 * rel(dx_32, dx_hi)) and rel(a["dp"], b["dp"]) <= max(1e-4, 10 * rel(dp_32, dp_hi))
+    assert rel(a["dx"], b["dx"]) <= max(1e-4, GRAD_BAR * rel(dx_32, dx_hi)) and rel(a["dp"], b["dp"]) <= max(1e-4, GRAD_BAR * rel(dp_32, dp_hi))
+
+
+def test_flagship_gradient_both_sweeps(oracle_built):
+    """The flagship training loss (experiments/mnist_node.jl:132-152: logitcrossentropy + 100 * mean(sv.saveval), batch 512)
+    with BOTH reverse sweeps -- tensor cores (default) and FFMA (RNDE_BWD_FFMA=1) -- and both regularisers of the experiment:
+    e = error of dL/dp2 against the Float64-cotangent adjoint of the same Float32 forward, c = the CPU Float32 adjoint's own.
+    Bars: cross-entropy part <= 1e-4 (well conditioned); full gradient <= max(1e-4, 1.5 c).  The numbers are printed (-s)."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for sweep, env in (("tensor", {}), ("ffma", {"RNDE_BWD_FFMA": "1"})):
+        e = dict(os.environ); e.update(env)
+        r_ = subprocess.run([sys.executable, os.path.join(root, "tools", "grad_err.py"), "512"], env=e, capture_output=True, text=True, cwd=root)
+        assert r_.returncode == 0, r_.stderr[-2000:]
+        for line in r_.stdout.strip().splitlines()[-2:]:
+            d = json.loads(line)
+            print(f"flagship gradient [{d['func']}, {sweep} sweep]: e = {d['full']['e']:.2e}, c_cpu32 = {d['full']['c_cpu32']:.2e}; "
+                  f"CE part e = {d['ce']['e']:.2e}; regulariser part e = {d['reg']['e']:.2e}, c_cpu32 = {d['reg']['c_cpu32']:.2e}")
+            assert d["sweep"] == sweep
+            assert d["ce"]["e"] <= 1e-4, d
+            assert d["full"]["e"] <= max(1e-4, GRAD_BAR * d["full"]["c_cpu32"]), d
+            assert d["reg"]["e"] <= max(1e-4, GRAD_BAR * d["reg"]["c_cpu32"]), d
 
 
 FIXED24_CASES = [
@@ -429,7 +454,7 @@ def test_fixed24_tensor_core_forward_bit_identical(oracle_built, name, D, H, B, 
     e_p, e_x = rel(p.grad.cpu().numpy(), dp_hi), rel(x.grad.cpu().numpy(), dx_hi)
     # unit-size random cotangents on every saved value are far harsher than the training loss (lambda/n each); the sweep's products
     # carry 16 mantissa bits (BF16 hi+lo), so on this ill-conditioned part it may sit at ~10x the CPU FP32 adjoint's own error
-    assert e_p <= max(1e-4, 20 * rel(dp_32, dp_hi)) and e_x <= max(1e-4, 20 * rel(dx_32, dx_hi)), (e_p, e_x)
+    assert e_p <= max(1e-4, GRAD_BAR * rel(dp_32, dp_hi)) and e_x <= max(1e-4, GRAD_BAR * rel(dx_32, dx_hi)), (e_p, e_x)
     if not regularize:
         assert e_p <= 1e-4 and e_x <= 1e-4
 
