@@ -237,20 +237,15 @@ __global__ void __launch_bounds__(V5_NT, 1) fwd4s_kernel(const KParams P) {
                 for (int j = 0; j < 8; ++j) acc[a][j] = 0ull;
             const float* wp = sW1 + s1 * P1 + 8 * mgc;
             const float* xp = sZ + s1 * NP + 8 * cg;
-            // software pipeline: the operands of k-step i+1 are fetched while the 32 FFMA2 of k-step i issue (without it the
-            // warps run in lockstep -- all loading, then all multiplying -- and the phase costs LDS time + FMA time instead of
-            // their maximum: tools/microbench4.cu, 5.7 k vs 3.4 k cycles); the last step re-fetches its own row
-            float4 w0 = *reinterpret_cast<const float4*>(wp), w1 = *reinterpret_cast<const float4*>(wp + 4);
-            float4 x0 = *reinterpret_cast<const float4*>(xp), x1 = *reinterpret_cast<const float4*>(xp + 4);
-#pragma unroll 1
+            // (an explicit register double buffer for the next k-step's operands was measured SLOWER -- 1.55 vs 1.37 ms per
+            // solve, profiles/r2d_*: the loop then no longer unrolls and ptxas' own hoisting of the unrolled loads does better)
+#pragma unroll 5
             for (int i = 0; i < KS1; ++i) {
-                const int in = (i + 1 < KS1) ? i + 1 : i;
-                const float4 nw0 = *reinterpret_cast<const float4*>(wp + in * 8 * P1);
-                const float4 nw1 = *reinterpret_cast<const float4*>(wp + in * 8 * P1 + 4);
-                const float4 nx0 = *reinterpret_cast<const float4*>(xp + in * 8 * NP);
-                const float4 nx1 = *reinterpret_cast<const float4*>(xp + in * 8 * NP + 4);
+                const float4 w0 = *reinterpret_cast<const float4*>(wp + i * 8 * P1);
+                const float4 w1 = *reinterpret_cast<const float4*>(wp + i * 8 * P1 + 4);
+                const float4 x0 = *reinterpret_cast<const float4*>(xp + i * 8 * NP);
+                const float4 x1 = *reinterpret_cast<const float4*>(xp + i * 8 * NP + 4);
                 tile_step(acc, w0, w1, x0, x1);
-                w0 = nw0; w1 = nw1; x0 = nx0; x1 = nx1;
             }
             // reduce-scatter over the 8 lanes of the tile: ((c0+c1)+(c2+c3)) + ((c4+c5)+(c6+c7))
             u64 h1[2][8];       // rows 4*b0 + {0,1 | 2,3}
@@ -341,17 +336,13 @@ __global__ void __launch_bounds__(V5_NT, 1) fwd4s_kernel(const KParams P) {
                 for (int j = 0; j < 8; ++j) acc[a][j] = 0ull;
             const float* wp = sW2 + s2 * P2 + 8 * rgc;
             const float* xp = sH + s2 * NP + 8 * cg;
-            float4 w0 = *reinterpret_cast<const float4*>(wp), w1 = *reinterpret_cast<const float4*>(wp + 4);
-            float4 x0 = *reinterpret_cast<const float4*>(xp), x1 = *reinterpret_cast<const float4*>(xp + 4);
-#pragma unroll 1
+#pragma unroll 5
             for (int i = 0; i < KS2; ++i) {
-                const int in = (i + 1 < KS2) ? i + 1 : i;
-                const float4 nw0 = *reinterpret_cast<const float4*>(wp + in * 4 * P2);
-                const float4 nw1 = *reinterpret_cast<const float4*>(wp + in * 4 * P2 + 4);
-                const float4 nx0 = *reinterpret_cast<const float4*>(xp + in * 4 * NP);
-                const float4 nx1 = *reinterpret_cast<const float4*>(xp + in * 4 * NP + 4);
+                const float4 w0 = *reinterpret_cast<const float4*>(wp + i * 4 * P2);
+                const float4 w1 = *reinterpret_cast<const float4*>(wp + i * 4 * P2 + 4);
+                const float4 x0 = *reinterpret_cast<const float4*>(xp + i * 4 * NP);
+                const float4 x1 = *reinterpret_cast<const float4*>(xp + i * 4 * NP + 4);
                 tile_step(acc, w0, w1, x0, x1);
-                w0 = nw0; w1 = nw1; x0 = nx0; x1 = nx1;
             }
             // reduce-scatter over the 4 lanes of the tile: (c0+c1) + (c2+c3); rows by b0, columns by b3
             u64 h1[2][8];
