@@ -217,6 +217,48 @@ int rnde_gru_forward(rnde_gru* g, const float* x_dev, const float* p_dev, float*
 int rnde_gru_backward(rnde_gru* g, const float* dout_dev, float* dp_dev, void* stream);
 int64_t rnde_gru_launch_count(const rnde_gru* g);
 
+/* ---- Neural SDE (BASELINE.json north_star (4)) -------------------------------------------------
+ * (n::TrackedNeuralDSDE{R,false})(x, p; func) -> (res, nfe1, nfe2, sv)   src/models/neural_sde.jl:84-146:
+ * SDEProblem{false}(drift, diffusion, x, tspan, p) with drift Chain(Dense(D,H,tanh), Dense(H,D)) and DIAGONAL diffusion
+ * Dense(D,D) (experiments/mnist_nsde.jl:73-74), solved by SOSRI() or AutoSOSRI2(SOSRI2()) at reltol = abstol = 1.4f-1
+ * (:79-80), SavingCallback(func, sv) with func = EEst*dt (:48) or the scaled stiffness estimate (:52-56).
+ * p = vcat(p_drift, p_diffusion) in Flux.destructure order (neural_sde.jl:16-18).  One persistent kernel: the adaptive
+ * Roessler-SRI stepper with the RSwM3 noise bookkeeping on the device.  The reference's random stream (randn! of Julia's
+ * MersenneTwister) cannot be reproduced: the caller SUPPLIES the standard normals, normals_dev[draw][row][column]
+ * (n_draws x D x B floats); every request of the solver (dW then dZ of a fresh step, the two bridges of a rejected one)
+ * consumes the next draws; rnde_sde_stats.draws reports how many were used, RNDE_ERR_ARG that they ran out.
+ * Forward solves only: Tracker.gradient through the SDE solve (mnist_nsde.jl:201-204) is not built. */
+enum { RNDE_SDE_SOSRI = 0, RNDE_SDE_AUTO_SOSRI2 = 1 };
+typedef struct rnde_sde_config {
+    int32_t struct_bytes;
+    int32_t state_dim;     /* D (32) */
+    int32_t hidden_dim;    /* H (64) */
+    int32_t batch;         /* B: columns incl. the trajectory replication of ClassifierNSDE */
+    int32_t alg;           /* RNDE_SDE_* */
+    int32_t reg_kind;      /* RNDE_REG_NONE | RNDE_REG_ERR_DT | RNDE_REG_STIFF_SCALED */
+    int32_t max_steps;     /* maxiters; 0 = 100000 */
+    int32_t max_saved;     /* capacity of saveval; 0 = 1024 */
+    float t0, t1, abstol, reltol;
+} rnde_sde_config;
+typedef struct rnde_sde_stats {
+    int32_t nfe1, nfe2;    /* drift / diffusion evaluations (neural_sde.jl:46,50) */
+    int32_t naccept, nreject, n_saved;
+    int32_t draws;         /* normals consumed (in units of one D x B array) */
+    int32_t retcode, reserved;
+    float t_final, dt_init, dt_last, reserved2;
+} rnde_sde_stats;
+typedef struct rnde_sde rnde_sde;
+int64_t rnde_sde_num_params(const rnde_sde_config* cfg);
+int rnde_sde_create(const rnde_sde_config* cfg, rnde_sde** out);
+void rnde_sde_destroy(rnde_sde* s);
+const char* rnde_sde_last_error(const rnde_sde* s);
+/* x_dev, u_out_dev: D x B column-major; saveval_dev: max_saved floats or NULL; stats_host filled after a stream sync */
+int rnde_sde_forward(rnde_sde* s, const float* x_dev, const float* p_dev, const float* normals_dev, int32_t n_draws, float* u_out_dev,
+                     float* saveval_dev, rnde_sde_stats* stats_host, void* stream);
+/* introspection for tests: (dt, EEst, accepted) of the first `cap` attempts of the last solve, host array of 3*cap floats */
+int rnde_sde_get_log(rnde_sde* s, float* log_host, int32_t cap);
+int64_t rnde_sde_launch_count(const rnde_sde* s);
+
 /* Host-buffer variants (end-to-end path: copies inside the call). */
 int rnde_forward_host(rnde_handle* h, const float* x_host, const float* p_host, float* u_out_host, float* saveval_host,
                       rnde_stats* stats_host);

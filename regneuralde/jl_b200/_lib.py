@@ -32,6 +32,7 @@ REG_NONE, REG_ERR_DT, REG_STIFF_DT_ABS, REG_STIFF_SCALED, REG_ERR_PLUS_STIFF = r
 KERNEL_AUTO, KERNEL_CTA, KERNEL_STREAM, KERNEL_CLUSTER, KERNEL_CLUSTER4, KERNEL_CHAIN = range(6)
 DIST_SINGLE, DIST_EXACT, DIST_INDEPENDENT = range(3)
 ARITH_FMA_CHAIN, ARITH_FIXED24, ARITH_SPLITK = 0, 1, 2
+SDE_SOSRI, SDE_AUTO_SOSRI2 = 0, 1
 
 EXPORTS = [
     "rnde_version", "rnde_status_string", "rnde_device_count", "rnde_create", "rnde_destroy", "rnde_last_error",
@@ -41,6 +42,7 @@ EXPORTS = [
     "rnde_set_saveat", "rnde_forward_saveat", "rnde_backward_saveat", "rnde_set_noise",
     "rnde_gru_num_params", "rnde_gru_create", "rnde_gru_destroy", "rnde_gru_last_error", "rnde_gru_forward", "rnde_gru_backward",
     "rnde_gru_launch_count", "rnde_reg_agg", "rnde_last_stats", "rnde_allreduce_grads",
+    "rnde_sde_num_params", "rnde_sde_create", "rnde_sde_destroy", "rnde_sde_last_error", "rnde_sde_forward", "rnde_sde_get_log", "rnde_sde_launch_count",
 ]
 
 
@@ -63,6 +65,22 @@ class GruConfig(C.Structure):
     _fields_ = [
         ("struct_bytes", C.c_int32), ("in_dim", C.c_int32), ("hidden_dim", C.c_int32), ("latent_dim", C.c_int32),
         ("batch", C.c_int32), ("seq_len", C.c_int32), ("need_backward", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class SdeConfig(C.Structure):
+    _fields_ = [
+        ("struct_bytes", C.c_int32), ("state_dim", C.c_int32), ("hidden_dim", C.c_int32), ("batch", C.c_int32), ("alg", C.c_int32),
+        ("reg_kind", C.c_int32), ("max_steps", C.c_int32), ("max_saved", C.c_int32),
+        ("t0", C.c_float), ("t1", C.c_float), ("abstol", C.c_float), ("reltol", C.c_float),
+    ]
+
+
+class SdeStats(C.Structure):
+    _fields_ = [
+        ("nfe1", C.c_int32), ("nfe2", C.c_int32), ("naccept", C.c_int32), ("nreject", C.c_int32), ("n_saved", C.c_int32), ("draws", C.c_int32),
+        ("retcode", C.c_int32), ("reserved", C.c_int32),
+        ("t_final", C.c_float), ("dt_init", C.c_float), ("dt_last", C.c_float), ("reserved2", C.c_float),
     ]
 
 
@@ -164,6 +182,17 @@ def lib() -> C.CDLL:
     L.rnde_gru_backward.argtypes = [vp, vp, vp, vp]
     L.rnde_gru_launch_count.restype = C.c_int64
     L.rnde_gru_launch_count.argtypes = [vp]
+    L.rnde_sde_num_params.argtypes = [C.POINTER(SdeConfig)]
+    L.rnde_sde_num_params.restype = C.c_int64
+    L.rnde_sde_create.argtypes = [C.POINTER(SdeConfig), C.POINTER(vp)]
+    L.rnde_sde_destroy.argtypes = [vp]
+    L.rnde_sde_destroy.restype = None
+    L.rnde_sde_last_error.argtypes = [vp]
+    L.rnde_sde_last_error.restype = C.c_char_p
+    L.rnde_sde_forward.argtypes = [vp, vp, vp, vp, C.c_int32, vp, vp, C.POINTER(SdeStats), vp]
+    L.rnde_sde_get_log.argtypes = [vp, fp, C.c_int32]
+    L.rnde_sde_launch_count.argtypes = [vp]
+    L.rnde_sde_launch_count.restype = C.c_int64
     L.rnde_forward_saveat.argtypes = [vp, vp, vp, vp, vp, vp, C.POINTER(Stats), vp]
     L.rnde_backward_saveat.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     _lib = L

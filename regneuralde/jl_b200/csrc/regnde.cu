@@ -23,6 +23,7 @@
 #include "head_kernel.cuh"
 #include "gru_kernel.cuh"
 #include "csq.cuh"
+#include "sde_kernel.cuh"
 
 using namespace rnde;
 
@@ -970,5 +971,155 @@ extern "C" int rnde_gru_backward(rnde_gru* g, const float* dout_dev, float* dp_d
     }
     e = launch_dense_wgrad(desc, GRU_NP, (long long)P.T * g->Q, O.np, g->num_sms, g->acc, dp_dev, st, &g->launches);
     if (e != cudaSuccess) { g->err = std::string("gru wgrad: ") + cudaGetErrorString(e); return RNDE_ERR_CUDA; }
+    return RNDE_OK;
+}
+
+// ---- Neural SDE (sde_kernel.cuh) -----------------------------------------------------------------------------------------
+struct rnde_sde {
+    rnde_sde_config cfg;
+    int device = 0, NP = 4, Q = 0;
+    size_t smem = 0;
+    double* partial = nullptr; float* stacks = nullptr; unsigned* bar = nullptr; SdeStats* stats = nullptr; float* log = nullptr; float* saveval_int = nullptr;
+    int log_cap = 4096;
+    int64_t launches = 0;
+    std::string err;
+};
+static int sde_err(rnde_sde* s, int code, const std::string& msg) { if (s) s->err = msg; return code; }
+static bool g_sri_init[64] = {false};
+
+static void fill_sri(SriTableau& t, const double* v) {
+    float* f = reinterpret_cast<float*>(&t);
+    for (int i = 0; i < 44; ++i) f[i] = (float)v[i];
+}
+static int init_sri_tables(rnde_sde* s) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return RNDE_ERR_CUDA;
+    std::lock_guard<std::mutex> lock(g_const_mutex);
+    if (dev < 64 && g_sri_init[dev]) return RNDE_OK;
+    // StochasticDiffEq constructSOSRI / constructSOSRI2 (the same Float64 literals as oracle/sde_oracle.py; order of SriTableau)
+    static const double sosri[44] = {
+        -0.04199224421316468, 2.842612915017106, -2.0527723684000727, 4.338237071435815, -2.8895936137439793, 2.3017575594644466,
+        0.26204282091330466, 0.20903646383505375, -0.1502377115150942, 0.05836595312746999, 0.6149440396332373, 0.08535117634046772,
+        -0.21641093549612528, 1.5336352863679572, 0.26066223492647056, -1.0536037558179159, 1.7015284721089472, -0.20725685784180017,
+        -0.5119011827621657, 2.67767339866713, -4.9395031322250995, 0.15580956238299215, 3.2361551006624674, -1.4223118283355949,
+        1.140099274172029, -0.6401334255743456, 0.4736296532772559, 0.026404498125060714,
+        -1.8453464565104432, 2.688764531100726, -0.2523866501071323, 0.40896857551684956,
+        0.4969658141589478, -0.5771202869753592, -0.12919702470322217, 0.2093514975196336,
+        2.8453464565104425, -2.688764531100725, 0.2523866501071322, -0.40896857551684945,
+        0.11522663875443433, -0.57877086147738, 0.2857851028163886, 0.17775911990655704};
+    static const double sosri2[44] = {
+        0.13804532298278663, 0.5818361298250374, 0.4181638701749618, 0.4670018408674211, 0.8046204792187386, -0.27162232008616016,
+        0.45605532163856893, 0.7555807846451692, 0.24441921535482677, 0.6981181143266059, 0.3453277086024727, -0.04344582292908241,
+        0.08852381537667678, 1.0317752458971061, 0.4563552922077882, 1.73078280444124, -0.46089678470929774, -0.9637509618944188,
+        0.6753186815412179, -0.07452812525785148, -0.49783736486149366, -0.5591906709928903, 0.022696571806569924, -0.8984927888368557,
+        -0.15036858140642623, 0.7545275856696072, 0.686995463807979, -0.2911544680711602,
+        -0.45315689727309133, 0.8330937231303951, 0.3792843195533544, 0.24077885458934192,
+        -0.4994383733810986, 0.9181786186154077, -0.25613778661003145, -0.16260245862427797,
+        1.4531568972730915, -0.8330937231303933, -0.3792843195533583, -0.24077885458934023,
+        -0.4976090683622265, 0.9148155835648892, -1.4102107084476505, 0.9930041932449877};
+    SriTableau t[2];
+    fill_sri(t[0], sosri); fill_sri(t[1], sosri2);
+    if (cudaMemcpyToSymbol(c_SRI, t, sizeof(t)) != cudaSuccess) return RNDE_ERR_CUDA;
+    if (dev < 64) g_sri_init[dev] = true;
+    (void)s;
+    return RNDE_OK;
+}
+
+extern "C" int64_t rnde_sde_num_params(const rnde_sde_config* c) {
+    if (!c) return 0;
+    const int64_t D = c->state_dim, H = c->hidden_dim;
+    return H * D + H + D * H + D + D * D + D;
+}
+extern "C" const char* rnde_sde_last_error(const rnde_sde* s) { return s ? s->err.c_str() : "null handle"; }
+extern "C" int64_t rnde_sde_launch_count(const rnde_sde* s) { return s ? s->launches : 0; }
+
+template <int NP>
+static int sde_capacity(size_t smem, int num_sms, int* out) {
+    if (cudaFuncSetAttribute(sde_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sde_kernel<NP>, SDE_NT, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    *out = per_sm * num_sms;
+    return 1;
+}
+
+extern "C" int rnde_sde_create(const rnde_sde_config* cfg, rnde_sde** out) {
+    if (!cfg || !out) return RNDE_ERR_ARG;
+    *out = nullptr;
+    if (cfg->struct_bytes != (int32_t)sizeof(rnde_sde_config)) return RNDE_ERR_ARG;
+    if (cfg->state_dim <= 0 || cfg->state_dim > 64 || cfg->hidden_dim <= 0 || cfg->hidden_dim > 256 || cfg->batch <= 0) return RNDE_ERR_ARG;
+    if (cfg->alg < 0 || cfg->alg > 1 || !(cfg->t1 > cfg->t0) || !(cfg->abstol > 0.f) || !(cfg->reltol > 0.f)) return RNDE_ERR_ARG;
+    if (cfg->reg_kind != RNDE_REG_NONE && cfg->reg_kind != RNDE_REG_ERR_DT && cfg->reg_kind != RNDE_REG_STIFF_SCALED) return RNDE_ERR_ARG;
+    if (cfg->reg_kind == RNDE_REG_STIFF_SCALED && cfg->alg != RNDE_SDE_AUTO_SOSRI2) return RNDE_ERR_ARG;      // eigen_est exists for the composite algorithm only
+    if (rnde_device_count() <= 0) return RNDE_ERR_CUDA;
+    rnde_sde* s = new rnde_sde();
+    s->cfg = *cfg;
+    if (s->cfg.max_steps <= 0) s->cfg.max_steps = 100000;
+    if (s->cfg.max_saved <= 0) s->cfg.max_saved = 1024;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&s->device) != cudaSuccess || cudaGetDeviceProperties(&prop, s->device) != cudaSuccess) { delete s; return RNDE_ERR_CUDA; }
+    if (init_sri_tables(s) != RNDE_OK) { delete s; return RNDE_ERR_CUDA; }
+    const int D = cfg->state_dim, H = cfg->hidden_dim, B = cfg->batch;
+    const int np = (int)rnde_sde_num_params(cfg);
+    // 4-column tiles while every CTA can be co-resident (the norm needs a grid barrier), else 8-column tiles
+    int cap4 = 0, cap8 = 0;
+    const size_t sm4 = sizeof(float) * sde_smem_floats(D, H, np, 4), sm8 = sizeof(float) * sde_smem_floats(D, H, np, 8);
+    const bool ok4 = sm4 <= prop.sharedMemPerBlockOptin && sde_capacity<4>(sm4, prop.multiProcessorCount, &cap4) && (B + 3) / 4 <= cap4;
+    const bool ok8 = !ok4 && sm8 <= prop.sharedMemPerBlockOptin && sde_capacity<8>(sm8, prop.multiProcessorCount, &cap8) && (B + 7) / 8 <= cap8;
+    if (!ok4 && !ok8) { fprintf(stderr, "regnde: SDE batch %d exceeds the co-resident capacity (%d / %d tiles)\n", B, cap4, cap8); delete s; return RNDE_ERR_UNSUPPORTED; }
+    s->NP = ok4 ? 4 : 8; s->smem = ok4 ? sm4 : sm8; s->Q = (B + s->NP - 1) / s->NP;
+    auto fail = [&](const char* what) { s->err = what; rnde_sde_destroy(s); return RNDE_ERR_CUDA; };
+    if (cudaMalloc(&s->partial, sizeof(double) * 2 * 3 * s->Q) != cudaSuccess) return fail("cudaMalloc partial");
+    if (cudaMalloc(&s->stacks, sizeof(float) * (size_t)s->Q * 4 * SDE_MAXS * D * s->NP) != cudaSuccess) return fail("cudaMalloc stacks");
+    if (cudaMalloc(&s->bar, sizeof(unsigned) * 4) != cudaSuccess) return fail("cudaMalloc bar");
+    if (cudaMalloc(&s->stats, sizeof(SdeStats)) != cudaSuccess) return fail("cudaMalloc stats");
+    if (cudaMalloc(&s->log, sizeof(float) * 3 * s->log_cap) != cudaSuccess) return fail("cudaMalloc log");
+    if (cudaMalloc(&s->saveval_int, sizeof(float) * s->cfg.max_saved) != cudaSuccess) return fail("cudaMalloc saveval");
+    *out = s;
+    return RNDE_OK;
+}
+
+extern "C" void rnde_sde_destroy(rnde_sde* s) {
+    if (!s) return;
+    DeviceScope scope(s->device);
+    cudaFree(s->partial); cudaFree(s->stacks); cudaFree(s->bar); cudaFree(s->stats); cudaFree(s->log); cudaFree(s->saveval_int);
+    delete s;
+}
+
+extern "C" int rnde_sde_forward(rnde_sde* s, const float* x_dev, const float* p_dev, const float* normals_dev, int32_t n_draws, float* u_out_dev,
+                                float* saveval_dev, rnde_sde_stats* stats_host, void* stream) {
+    if (!s || !x_dev || !p_dev || !normals_dev || n_draws <= 0 || !u_out_dev) return RNDE_ERR_ARG;
+    DeviceScope scope(s->device);
+    if (scope.err != cudaSuccess) return sde_err(s, RNDE_ERR_CUDA, "selecting the handle's device");
+    cudaStream_t st = (cudaStream_t)stream;
+    SdeParams P;
+    memset(&P, 0, sizeof(P));
+    const rnde_sde_config& c = s->cfg;
+    P.D = c.state_dim; P.H = c.hidden_dim; P.B = c.batch; P.Q = s->Q; P.alg = c.alg; P.reg_kind = c.reg_kind; P.max_steps = c.max_steps;
+    P.max_saved = c.max_saved; P.n_draws = n_draws; P.t0 = c.t0; P.t1 = c.t1; P.abstol = c.abstol; P.reltol = c.reltol;
+    P.x = x_dev; P.p = p_dev; P.normals = normals_dev; P.u_out = u_out_dev; P.saveval = saveval_dev ? saveval_dev : s->saveval_int;
+    P.partial = s->partial; P.stacks = s->stacks; P.bar = s->bar; P.stats = s->stats; P.log = s->log; P.log_cap = s->log_cap;
+    if (cudaMemsetAsync(s->bar, 0, sizeof(unsigned) * 4, st) != cudaSuccess) return sde_err(s, RNDE_ERR_CUDA, "cudaMemsetAsync");
+    if (s->NP == 4) sde_kernel<4><<<s->Q, SDE_NT, s->smem, st>>>(P);
+    else sde_kernel<8><<<s->Q, SDE_NT, s->smem, st>>>(P);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return sde_err(s, RNDE_ERR_CUDA, std::string("sde_kernel launch: ") + cudaGetErrorString(e));
+    s->launches += 1;
+    if (stats_host) {
+        SdeStats h;
+        if (cudaMemcpyAsync(&h, s->stats, sizeof(h), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+            return sde_err(s, RNDE_ERR_CUDA, std::string("sde stats: ") + cudaGetErrorString(cudaGetLastError()));
+        stats_host->nfe1 = h.nfe1; stats_host->nfe2 = h.nfe2; stats_host->naccept = h.naccept; stats_host->nreject = h.nreject; stats_host->n_saved = h.n_saved;
+        stats_host->draws = h.draws; stats_host->retcode = h.retcode; stats_host->reserved = 0;
+        stats_host->t_final = h.t_final; stats_host->dt_init = h.dt_init; stats_host->dt_last = h.dt_last; stats_host->reserved2 = 0.f;
+        if (h.retcode != RNDE_OK) return sde_err(s, h.retcode, h.retcode == RNDE_ERR_ARG ? "the supplied normals ran out" : rnde_status_string(h.retcode));
+    }
+    return RNDE_OK;
+}
+
+extern "C" int rnde_sde_get_log(rnde_sde* s, float* log_host, int32_t cap) {
+    if (!s || !log_host || cap <= 0 || cap > s->log_cap) return RNDE_ERR_ARG;
+    DeviceScope scope(s->device);
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpy(log_host, s->log, sizeof(float) * 3 * cap, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return sde_err(s, RNDE_ERR_CUDA, "reading the attempt log");
     return RNDE_OK;
 }

@@ -1,0 +1,94 @@
+"""GPU parity of the Neural-SDE stepper (csrc/sde_kernel.cuh through the C ABI / the TrackedNeuralDSDE mirror) against
+oracle/sde_oracle.py WITH SUPPLIED NOISE (the reference's random stream cannot be reproduced).
+Bars: accepted / rejected attempts, nfe1, nfe2 and the number of consumed draws identical; final state, saved values and the
+per-attempt (dt, EEst) within 1e-5 relative (the oracle's matrix products run through BLAS, so not bit for bit)."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import sde_oracle as S  # noqa: E402  (the checker)
+
+
+def make(seed, D, H, B, ndraw=400):
+    rng = np.random.default_rng(seed)
+    s = lambda o, i: np.sqrt(6.0 / (i + o))
+    p = np.concatenate([rng.uniform(-s(H, D), s(H, D), H * D), 0.1 * rng.standard_normal(H), rng.uniform(-s(D, H), s(D, H), D * H),
+                        0.1 * rng.standard_normal(D), rng.uniform(-s(D, D), s(D, D), D * D), 0.1 * rng.standard_normal(D)]).astype(np.float32)
+    x = rng.standard_normal((D, B)).astype(np.float32)
+    z = rng.standard_normal((ndraw, D, B)).astype(np.float32)
+    return p, x, z
+
+
+def node_for(D, H, regularize, solver, tol):
+    import regneuralde.jl_b200 as r
+    return r.TrackedNeuralDSDE(r.Chain(r.Dense(D, H, "tanh"), r.Dense(H, D)), r.Dense(D, D), [0.0, 1.0], regularize, solver,
+                               reltol=tol, abstol=tol, save_everystep=False, save_start=False)
+
+
+CASES = [
+    # name, D, H, B, tol, regularize, auto
+    ("mnist_nsde shape B=48 error_est", 32, 64, 48, 0.14, True, False),
+    ("mnist_nsde shape B=512 error_est", 32, 64, 512, 0.14, True, False),
+    ("B=7 ragged tile, tight tolerance (rejections)", 32, 64, 7, 0.02, True, False),
+    ("unregularised", 32, 64, 33, 0.14, False, False),
+    ("AutoSOSRI2 stiff_est", 32, 64, 40, 0.14, True, True),
+    ("generic dims D=12 H=20, many rejections", 12, 20, 9, 0.005, True, False),
+    ("8-column tiles (batch beyond the 4-column capacity)", 32, 64, 6000, 0.14, True, False),
+]
+
+
+@pytest.mark.parametrize("name,D,H,B,tol,regularize,auto", CASES, ids=[c[0] for c in CASES])
+def test_sde_forward_matches_oracle(name, D, H, B, tol, regularize, auto):
+    import regneuralde.jl_b200 as r
+    p, x, z = make(1999, D, H, B, ndraw=120 if B > 1000 else 400)
+    node = node_for(D, H, regularize, r.AutoSOSRI2() if auto else r.SOSRI(), tol)
+    func = (r.STIFFNESS_SCALED if auto else r.ERROR_ESTIMATE) if regularize else None
+    with torch.no_grad():
+        res, nfe1, nfe2, sv = node(torch.from_numpy(x).cuda(), torch.from_numpy(p).cuda(), func=func, noise=torch.from_numpy(z).cuda())
+    f, g = S.drift_diffusion(p, np.float32, D=D, H=H)
+    reg = (S.REG_STIFF_SCALED if auto else S.REG_ERR_DT) if regularize else S.REG_NONE
+    ref = S.solve(x, f, g, z, alg=S.ALG_AUTO_SOSRI2 if auto else S.ALG_SOSRI, reg_kind=reg, abstol=tol, reltol=tol)
+    assert min(abs(e - 1.0) for e in ref.eests) > 1e-3, "an attempt of the oracle sits on the accept threshold: pick another seed"
+    st = node.last_stats
+    assert (nfe1, nfe2) == (ref.nfe1, ref.nfe2) and nfe1 == 2 + 4 * (st.naccept + st.nreject)
+    assert (st.naccept, st.nreject, st.draws) == (ref.naccept, ref.nreject, ref.draws)
+    got = node.attempts()
+    assert [a for _, _, a in got] == ref.accepted
+    assert np.allclose([d for d, _, _ in got], ref.dts, rtol=1e-5) and np.allclose([e for _, e, _ in got], ref.eests, rtol=2e-4)
+    u = res.cpu().numpy()
+    assert np.abs(u - ref.u).max() <= 1e-5 * max(1.0, np.abs(ref.u).max()), np.abs(u - ref.u).max()
+    if regularize:
+        assert len(sv) == st.naccept + 1
+        assert np.allclose(sv.saveval.cpu().numpy(), ref.saveval, rtol=2e-4, atol=1e-7)
+    else:
+        assert sv is None
+    if "rejections" in name:
+        assert st.nreject > 0
+
+
+def test_classifier_nsde_and_errors():
+    import regneuralde.jl_b200 as r
+    from regneuralde.jl_b200 import _lib as L
+    rng = np.random.default_rng(7)
+    B, traj = 24, 3
+    p2, _, z = make(7, 32, 64, B * traj)
+    node = node_for(32, 64, True, r.SOSRI(), 0.14)
+    clf = r.ClassifierNSDE(r.Dense(784, 32), node, r.Dense(32, 10))
+    p1 = (0.05 * rng.standard_normal(784 * 32 + 32)).astype(np.float32); p3 = (0.3 * rng.standard_normal(32 * 10 + 10)).astype(np.float32)
+    x = rng.random((784, B), dtype=np.float32)
+    with torch.no_grad():
+        zl, nfe1, nfe2, sv = clf(torch.from_numpy(x).cuda(), torch.from_numpy(p1).cuda(), torch.from_numpy(p2).cuda(), torch.from_numpy(p3).cuda(),
+                                 trajectories=traj, func=r.ERROR_ESTIMATE, noise=torch.from_numpy(z).cuda())
+    zr, ref = S.classifier_nsde(x, p1, p2, p3, z, trajectories=traj, reg_kind=S.REG_ERR_DT)
+    assert (nfe1, nfe2) == (ref.nfe1, ref.nfe2)
+    assert np.abs(zl.cpu().numpy() - zr).max() <= 1e-4 * max(1.0, np.abs(zr).max())
+    # too few normals: reported, not silently reused
+    with pytest.raises(L.RndeError) as ei, torch.no_grad():
+        node(torch.zeros(32, B * traj, device="cuda"), torch.from_numpy(p2).cuda(), noise=torch.from_numpy(z[:3]).cuda())
+    assert ei.value.code == L.ERR_ARG
+    # no backward yet: loud
+    pp = torch.from_numpy(p2).cuda().requires_grad_(True)
+    with pytest.raises(NotImplementedError):
+        node(torch.zeros(32, B * traj, device="cuda"), pp, noise=torch.from_numpy(z).cuda())
