@@ -245,9 +245,9 @@ __global__ void __launch_bounds__(CW_NT) dense_wgrad_kernel(const WgDesc desc, c
                 const int it = ot / MT, mt = ot - it * MT;
                 const float* dp = sDel + mt * 4 * CW_LD;
                 const float* ap = sAct + it * 4 * CW_LD;
-                float s32[16];
-#pragma unroll
-                for (int r = 0; r < 16; ++r) s32[r] = 0.f;
+                // Float32 partial sums over FOUR columns only, then Float64 (round 2: a 64-column Float32 partial made the parameter
+                // gradient of the regularised toy / chain cases 2-2.5x noisier than the CPU Float32 adjoint; the products of the
+                // cancelling O(10) cotangents must not pile up in Float32)
 #pragma unroll 4
                 for (int c4 = 0; c4 < CW_COLS / 4; ++c4) {
                     float4 d[4], a[4];
@@ -257,13 +257,12 @@ __global__ void __launch_bounds__(CW_NT) dense_wgrad_kernel(const WgDesc desc, c
                     for (int i = 0; i < 4; ++i)
 #pragma unroll
                         for (int o = 0; o < 4; ++o) {
-                            float v = s32[i * 4 + o];
-                            v = fmaf(d[o].x, a[i].x, v); v = fmaf(d[o].y, a[i].y, v); v = fmaf(d[o].z, a[i].z, v); v = fmaf(d[o].w, a[i].w, v);
-                            s32[i * 4 + o] = v;
+                            double v = acc[t][i * 4 + o];
+                            v = fma((double)d[o].x, (double)a[i].x, v); v = fma((double)d[o].y, (double)a[i].y, v);
+                            v = fma((double)d[o].z, (double)a[i].z, v); v = fma((double)d[o].w, (double)a[i].w, v);
+                            acc[t][i * 4 + o] = v;
                         }
                 }
-#pragma unroll
-                for (int r = 0; r < 16; ++r) acc[t][r] += (double)s32[r];
             }
         }
     }

@@ -133,6 +133,27 @@ __device__ __forceinline__ void xrank_barrier(const KParams& P, unsigned seq) {
     }
     __syncthreads();
 }
+// Merged barrier of the exact data-parallel mode (round 2): the cluster's publishing CTA has written its column sums into every
+// rank's exchange buffer; one release-add per rank on that rank's arrival counter then says so, and every CTA of every rank
+// waits until its own counter has seen all Q x nranks clusters of this norm.  One NVLink round instead of a local grid
+// barrier + eight serialised st.release.sys flags + a poll of eight flags.  Call with the whole CTA; `publisher` = this CTA
+// published column sums (cluster rank 0); `seq` counts norms from 1 across launches (same on every rank).
+__device__ __forceinline__ void xrank_arrive_wait(const KParams& P, bool publisher, unsigned seq, unsigned nclusters) {
+    constexpr unsigned ARRIVE = 48;      // word inside the flag block
+    __syncthreads();                     // the publishing threads' peer stores are ordered before thread 0's release
+    if (threadIdx.x == 0) {
+        if (publisher) {
+            __threadfence_system();
+            for (int r = 0; r < P.nranks; ++r)
+                asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(reinterpret_cast<unsigned*>(P.peers[r]) + P.flag_off + ARRIVE) : "memory");
+        }
+        const unsigned target = seq * nclusters * (unsigned)P.nranks;
+        const unsigned* mine = reinterpret_cast<const unsigned*>(P.peers[P.rank]) + P.flag_off + ARRIVE;
+        long long spins = 0;
+        while ((int)(ld_acquire_sys(mine) - target) < 0) { if (++spins > (1ll << 25)) __trap(); }
+    }
+    __syncthreads();
+}
 // write one per-column sum into every rank's exchange buffer (own buffer included)
 __device__ __forceinline__ void publish_colsum(const KParams& P, size_t word_off, float v) {
     if (P.nranks <= 1) { P.colsum[word_off] = v; return; }

@@ -435,12 +435,11 @@ __global__ void __launch_bounds__(V5_NT, 1) fwd4s_kernel(const KParams P) {
 #pragma unroll
             for (int c = 1; c < G; ++c) tot = tot + sCP[(v * G + c) * NP + n];
             if (n < Nloc) publish_colsum(P, (size_t)slot * 3 * P.colsum_stride + (size_t)v * P.colsum_stride + P.col_offset + q * NP + n, tot);
-            if (P.nranks > 1) __threadfence_system();
         }
         mark(13);
-        grid_barrier(P.bar, gridDim.x, bar_gen);
+        if (P.nranks > 1) xrank_arrive_wait(P, rank == 0, xseq_base + norm_seq + 1u, gridDim.x / G);      // all ranks' clusters, one NVLink round
+        else grid_barrier(P.bar, gridDim.x, bar_gen);
         mark(14);
-        xrank_barrier(P, xseq_base + norm_seq + 1u);
         if (warp < NV) {
             const float* g = gcol + (size_t)warp * P.colsum_stride;
             float s = 0.f;

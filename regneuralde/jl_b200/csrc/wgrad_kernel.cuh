@@ -18,7 +18,7 @@
 //   * the contraction runs step by step and, inside a step, column tile by column tile with the six
 //     records of the step back to back (tile_of): cancelling terms meet inside one FP32 chunk,
 //   * split-K assigns CONTIGUOUS ranges of that order to a split,
-//   * FP32 accumulators are flushed into FP64 every 4 stages (256 entries), partials are FP64, the
+//   * FP32 accumulators are flushed into FP64 every stage (64 entries), partials are FP64, the
 //     final fixed-order reduction over splits is FP64 (deterministic, no atomics).
 #pragma once
 #include "common.cuh"
@@ -30,7 +30,7 @@ constexpr int WG_TN = 64;            // output columns per CTA (operand B)
 constexpr int WG_KC = 64;            // contraction entries per pipeline stage
 constexpr int WG_LD = WG_KC + 4;     // padded row stride (floats): k-contiguous float4 reads are conflict free
 constexpr int WG_SPLITS = 20;
-constexpr int WG_FLUSH = 4;          // stages between FP32 -> FP64 flushes
+constexpr int WG_FLUSH = 1;          // stages between FP32 -> FP64 flushes (round 2: every stage of 64 entries; 4 was measurably noisier on the toy shapes)
 
 __host__ inline size_t wgrad_workspace_floats(int D, int H) {
     const size_t a = (size_t)H * (D + 2), b = (size_t)D * (H + 2);

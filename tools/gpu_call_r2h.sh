@@ -1,0 +1,6 @@
+#!/usr/bin/env bash
+mkdir -p gpurun_out
+(timeout 300 python -m pytest tests/test_gpu_nsde.py -q 2>&1 | tail -40) > gpurun_out/r2h_nsde.txt
+(timeout 900 python -m pytest tests -q -m gpu -s --deselect tests/test_gpu_nsde.py 2>&1 | grep -v "^$" | tail -40) > gpurun_out/r2h_gputests.txt
+(timeout 600 python bench.py --steps 20 --warmup 5 2>&1 | tail -3) > gpurun_out/r2h_bench.txt
+tail -n 45 gpurun_out/r2h_*.txt
