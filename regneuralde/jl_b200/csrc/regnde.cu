@@ -1061,12 +1061,13 @@ extern "C" int rnde_sde_create(const rnde_sde_config* cfg, rnde_sde** out) {
     const int D = cfg->state_dim, H = cfg->hidden_dim, B = cfg->batch;
     const int np = (int)rnde_sde_num_params(cfg);
     // 4-column tiles while every CTA can be co-resident (the norm needs a grid barrier), else 8-column tiles
-    int cap4 = 0, cap8 = 0;
-    const size_t sm4 = sizeof(float) * sde_smem_floats(D, H, np, 4), sm8 = sizeof(float) * sde_smem_floats(D, H, np, 8);
+    int cap4 = 0, cap8 = 0, cap16 = 0;
+    const size_t sm4 = sizeof(float) * sde_smem_floats(D, H, np, 4), sm8 = sizeof(float) * sde_smem_floats(D, H, np, 8), sm16 = sizeof(float) * sde_smem_floats(D, H, np, 16);
     const bool ok4 = sm4 <= prop.sharedMemPerBlockOptin && sde_capacity<4>(sm4, prop.multiProcessorCount, &cap4) && (B + 3) / 4 <= cap4;
     const bool ok8 = !ok4 && sm8 <= prop.sharedMemPerBlockOptin && sde_capacity<8>(sm8, prop.multiProcessorCount, &cap8) && (B + 7) / 8 <= cap8;
-    if (!ok4 && !ok8) { fprintf(stderr, "regnde: SDE batch %d exceeds the co-resident capacity (%d / %d tiles)\n", B, cap4, cap8); delete s; return RNDE_ERR_UNSUPPORTED; }
-    s->NP = ok4 ? 4 : 8; s->smem = ok4 ? sm4 : sm8; s->Q = (B + s->NP - 1) / s->NP;
+    const bool ok16 = !ok4 && !ok8 && sm16 <= prop.sharedMemPerBlockOptin && sde_capacity<16>(sm16, prop.multiProcessorCount, &cap16) && (B + 15) / 16 <= cap16;
+    if (!ok4 && !ok8 && !ok16) { fprintf(stderr, "regnde: SDE batch %d exceeds the co-resident capacity (%d / %d / %d tiles of 4 / 8 / 16 columns)\n", B, cap4, cap8, cap16); delete s; return RNDE_ERR_UNSUPPORTED; }
+    s->NP = ok4 ? 4 : (ok8 ? 8 : 16); s->smem = ok4 ? sm4 : (ok8 ? sm8 : sm16); s->Q = (B + s->NP - 1) / s->NP;
     auto fail = [&](const char* what) { s->err = what; rnde_sde_destroy(s); return RNDE_ERR_CUDA; };
     if (cudaMalloc(&s->partial, sizeof(double) * 2 * 3 * s->Q) != cudaSuccess) return fail("cudaMalloc partial");
     if (cudaMalloc(&s->stacks, sizeof(float) * (size_t)s->Q * 4 * SDE_MAXS * D * s->NP) != cudaSuccess) return fail("cudaMalloc stacks");
@@ -1100,7 +1101,8 @@ extern "C" int rnde_sde_forward(rnde_sde* s, const float* x_dev, const float* p_
     P.partial = s->partial; P.stacks = s->stacks; P.bar = s->bar; P.stats = s->stats; P.log = s->log; P.log_cap = s->log_cap;
     if (cudaMemsetAsync(s->bar, 0, sizeof(unsigned) * 4, st) != cudaSuccess) return sde_err(s, RNDE_ERR_CUDA, "cudaMemsetAsync");
     if (s->NP == 4) sde_kernel<4><<<s->Q, SDE_NT, s->smem, st>>>(P);
-    else sde_kernel<8><<<s->Q, SDE_NT, s->smem, st>>>(P);
+    else if (s->NP == 8) sde_kernel<8><<<s->Q, SDE_NT, s->smem, st>>>(P);
+    else sde_kernel<16><<<s->Q, SDE_NT, s->smem, st>>>(P);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return sde_err(s, RNDE_ERR_CUDA, std::string("sde_kernel launch: ") + cudaGetErrorString(e));
     s->launches += 1;

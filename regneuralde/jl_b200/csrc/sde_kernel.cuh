@@ -6,8 +6,8 @@
 // bridging on rejection), the two NFE counters and the regulariser's saved values all run on the device.
 //
 // Decomposition: the same scaffolding as the chain stepper -- one CTA owns a tile of 4 batch columns, all 5 248 parameters
-// sit in shared memory, the state and every stage value of the tile too (D x 4 floats each; 8-column tiles for batches
-// beyond ~4000 columns), the RSwM3 stacks of the tile in HBM (L2-resident); the only grid-wide dependency
+// sit in shared memory, the state and every stage value of the tile too (D x 4 floats each; 8- or 16-column tiles when the batch
+// exceeds the co-resident capacity: 1776 / 3552 / 7104 columns), the RSwM3 stacks of the tile in HBM (L2-resident); the only grid-wide dependency
 // is the RMS norm of the error estimate (per-CTA partial sums of squares in Float64 -> global -> grid barrier -> every CTA
 // adds the Q partials in the same order, so all CTAs take identical controller decisions).
 // Noise is INJECTED: normals[draw][row][column] holds standard normals; every request of the solver (dW, dZ of a fresh step,
