@@ -475,9 +475,84 @@ def run_ours(args):
             cb = cpu_run(B, 2, 1, budget_s=0.0)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
             line["grad_check"] = grad_check(tr, torch, R)
+        if world == 1 and not args.no_secondary:
+            line["secondary"] = secondary_workloads(torch, R, peak)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def secondary_workloads(torch, R, peak) -> dict:
+    """The widened rows on the record: one Latent-ODE training step (N1: GRU encoder + chain-field solve with 49
+    save times + decoder, PhysioNet-shaped synthetic batch 37 x 49 x 512, error-estimate regulariser) and one Neural-SDE
+    forward solve (N2: SOSRI, 32-dim state, batch 512, tol 1.4e-1, supplied noise); device times, CUDA events."""
+    out = {}
+
+    def timed(fn, iters=10, warm=3):
+        tot = 0.0
+        for it in range(iters + warm):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            if it >= warm:
+                tot += e0.elapsed_time(e1)
+        return tot / iters
+
+    try:
+        B, I, T = 512, 37, 49
+        rng = np.random.default_rng(1234)
+        times = np.unique(np.concatenate([[0.0], np.sort(rng.random(T - 2)), [1.0]]).astype(np.float32))
+        S = len(times)
+        data = rng.standard_normal((I, S, B)).astype(np.float32)
+        mask = (rng.random((I, S, B)) < 0.15).astype(np.float32)
+        trow = np.broadcast_to(times[None, :, None], (1, S, B)).astype(np.float32).copy()
+        model = R.latent_ode_model(I, 40, 50, 20, 50, saveat=times.tolist(), regularize=True, solver=R.Tsit5(), generator=torch.Generator().manual_seed(5))
+        ps = [p.clone().requires_grad_(True) for p in model.trainable()]
+        d, m, t = (torch.from_numpy(a).cuda() for a in (data * mask, mask, trow))
+        sample = torch.randn(20, B, device="cuda")
+        info = {}
+
+        def step():
+            total, nfe, _ = R.loss_function(d, m, t, model, *ps, func=R.ERROR_ESTIMATE, regularize=True, lam_r=1.0e3, sample=sample)
+            total.backward()
+            info["nfe"] = nfe
+            for p in ps:
+                p.grad = None
+
+        ms = timed(step)
+        z0 = torch.randn(20, B, device="cuda")
+
+        def fwd_only():
+            with torch.no_grad():
+                model.node(z0, ps[2].detach(), func=R.ERROR_ESTIMATE)
+
+        ms_fwd = timed(fwd_only)
+        f_rhs = 2 * 8 * 20 * 50        # FLOP per sample per evaluation of Chain(tanh, Dense(20,50,tanh), Dense(50,20,tanh), ... x8)
+        out["latent_ode"] = {"workload": f"latent_ode train step, {I} features x {S} times x batch {B}, error_est", "ms_per_step": ms, "samples_per_s": B / (ms * 1e-3),
+                             "nfe": info["nfe"], "chain_solve_fwd_ms": ms_fwd, "chain_stepper_tflops": info["nfe"] * f_rhs * B / (ms_fwd * 1e-3) / 1e12,
+                             "chain_stepper_frac_of_ffma_peak": info["nfe"] * f_rhs * B / (ms_fwd * 1e-3) / 1e12 / peak,
+                             "note": "8 280 weights in shared memory, 128 CTAs x 4 columns: instruction-latency bound, not FFMA bound"}
+    except Exception as ex:      # a secondary row must never take the headline down
+        out["latent_ode"] = {"error": repr(ex)[:200]}
+    try:
+        D, H, B = 32, 64, 512
+        rng = np.random.default_rng(SEED)
+        node = R.TrackedNeuralDSDE(R.Chain(R.Dense(D, H, "tanh"), R.Dense(H, D)), R.Dense(D, D), [0.0, 1.0], True, R.SOSRI(), reltol=1.4e-1, abstol=1.4e-1)
+        x = torch.from_numpy(rng.standard_normal((D, B)).astype(np.float32)).cuda()
+        z = torch.randn(256, D, B, device="cuda")
+        info = {}
+
+        def solve():
+            with torch.no_grad():
+                _, n1, n2, _ = node(x, func=R.ERROR_ESTIMATE, noise=z)
+            info["nfe"] = (n1, n2)
+
+        ms = timed(solve)
+        out["neural_sde"] = {"workload": f"mnist_nsde forward solve (SOSRI, {D}-dim state, batch {B}, tol 1.4e-1, supplied noise)", "ms_per_solve": ms,
+                             "samples_per_s": B / (ms * 1e-3), "nfe1": info["nfe"][0], "nfe2": info["nfe"][1], "naccept": int(node.last_stats.naccept),
+                             "nreject": int(node.last_stats.nreject)}
+    except Exception as ex:
+        out["neural_sde"] = {"error": repr(ex)[:200]}
+    return out
 
 
 def grad_check(tr, torch, R) -> dict:
@@ -505,6 +580,7 @@ def main():
     ap.add_argument("--batch", type=int, default=512, help="samples per GPU")
     ap.add_argument("--tape-capacity", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the Latent-ODE / Neural-SDE rows")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

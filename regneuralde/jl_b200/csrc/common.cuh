@@ -143,14 +143,21 @@ __device__ __forceinline__ void xrank_arrive_wait(const KParams& P, bool publish
     __syncthreads();                     // the publishing threads' peer stores are ordered before thread 0's release
     if (threadIdx.x == 0) {
         if (publisher) {
+            // ONE system-scope fence orders the column sums before the arrivals; the arrivals themselves are relaxed
+            // fire-and-forget reductions (a release on each of them would wait for the NVLink round trip once per rank)
             __threadfence_system();
             for (int r = 0; r < P.nranks; ++r)
-                asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(reinterpret_cast<unsigned*>(P.peers[r]) + P.flag_off + ARRIVE) : "memory");
+                asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(reinterpret_cast<unsigned*>(P.peers[r]) + P.flag_off + ARRIVE) : "memory");
         }
         const unsigned target = seq * nclusters * (unsigned)P.nranks;
         const unsigned* mine = reinterpret_cast<const unsigned*>(P.peers[P.rank]) + P.flag_off + ARRIVE;
         long long spins = 0;
-        while ((int)(ld_acquire_sys(mine) - target) < 0) { if (++spins > (1ll << 25)) __trap(); }
+        unsigned cur;
+        do {
+            asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(cur) : "l"(mine) : "memory");
+            if (++spins > (1ll << 26)) __trap();
+        } while ((int)(cur - target) < 0);
+        __threadfence_system();      // acquire side: the peers' column sums are visible to the fold below
     }
     __syncthreads();
 }
