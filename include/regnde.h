@@ -160,6 +160,20 @@ int rnde_set_tspan(rnde_handle* h, float t0, float t1);
  * (bench.py --fixed-work), not a reference code path.  n = 0 restores the adaptive controller.  RNDE_ARITH_SPLITK handles only. */
 int rnde_set_forced_steps(rnde_handle* h, const float* dt_host, int32_t n);
 
+/* What the backward pass differentiates.  `_convert_tspan` (/root/reference/src/utils.jl:21-23)
+ * makes tspan tracked, so t and dt are tracked scalars in the reference; every step size the controller proposes is
+ * detached (DiffEqBase.value in loopfooter!), the first one -- the Hairer-Wanner initial-dt heuristic -- is not.
+ *   RNDE_DETACH_ALL_BUT_FIRST (default, the recalled upstream behaviour): the gradient includes
+ *       dL/d(dt_1) * d(dt_1)/d(theta, x), where dt_1 is the first accepted step size, the shift of every later step's start
+ *       time and the shortening of the last (clamped) step; costs two more field VJPs per backward pass.
+ *   RNDE_DETACH_ALL: the discrete adjoint of the frozen step sequence only.
+ * Takes effect from the next rnde_forward (the initial-dt evaluation has to be on the tape).  Handles that replay forced
+ * steps always behave as RNDE_DETACH_ALL (their dt_1 does not come from the heuristic).
+ *   RNDE_DETACH_FIRST_TERM_ONLY: diagnostic -- the backward returns that extra term alone (dp, dx), so that a test can
+ *       check it against the oracle without the Float32 noise of the frozen-step gradient it is 1e-3 ... 1e-7 of. */
+enum { RNDE_DETACH_ALL = 0, RNDE_DETACH_ALL_BUT_FIRST = 1, RNDE_DETACH_FIRST_TERM_ONLY = 2 };
+int rnde_set_detach(rnde_handle* h, int32_t mode);
+
 /* Forward solve.  x_dev (D x B), p_dev (num_params), u_out_dev (D x B),
  * saveval_dev (>= tape_capacity+1 floats, may be NULL when reg_kind==NONE).
  * stats_host may be NULL (fully asynchronous); otherwise the stream is

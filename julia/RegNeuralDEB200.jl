@@ -47,6 +47,7 @@ const REG_STIFF_SCALED = Int32(3)    # stability_size * |eigen_est|             
 const REG_ERR_PLUS_STIFF = Int32(4)  # EEst*dt + 0.1*stability_size*eigen_est       mnist_node.jl:88-97
 
 const ARITH_FMA_CHAIN, ARITH_FIXED24, ARITH_SPLITK = Int32(0), Int32(1), Int32(2)
+const DETACH_ALL, DETACH_ALL_BUT_FIRST = Int32(0), Int32(1)      # rnde_set_detach: what the tape differentiates (utils.jl:21-23)
 const KERNEL_AUTO, KERNEL_CLUSTER4 = Int32(0), Int32(4)
 
 # ---- what the reference passes, recognised (closures and solver objects cannot cross a C ABI) ----------------------
@@ -121,6 +122,9 @@ function handle!(n::TrackedNeuralODE, D, H, B, reg_kind, need_backward, layers)
                              need_backward, 0, 0, 0, 1, n.tspan[1], n.tspan[2], n.abstol, n.reltol, 0f0, 0, 0, B, 0, ntuple(_ -> Int32(0), 8), ntuple(_ -> Int32(0), 8), _arith(D, H), 0, 0))
         h = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:rnde_create, LIB), Cint, (Ref{RndeConfig}, Ref{Ptr{Cvoid}}), cfg, h))
+        # _convert_tspan (utils.jl:21-23) makes tspan tracked whenever p is: the first dt stays on the tape (the library's default,
+        # spelled out here because it is the reference's behaviour; DETACH_ALL gives the frozen-step adjoint alone)
+        check(ccall((:rnde_set_detach, LIB), Cint, (Ptr{Cvoid}, Int32), h[], DETACH_ALL_BUT_FIRST), h[])
         h[]
     end
 end

@@ -248,8 +248,11 @@ class Oracle:
         res.usave = usave
         return res
 
-    def backward(self, du, dsaveval=None, hi: bool = False, dusave=None):
+    def backward(self, du, dsaveval=None, hi: bool = False, dusave=None, first_dt_tracked: bool = True):
         """Discrete adjoint with frozen dt.  Returns dp, dx, dtbar[naccept], tbar[naccept].
+        first_dt_tracked=True: Appendix A.6 with detach_dt = all_but_first -- the initial-dt heuristic
+        (and through it the start time of every later step and the length of the last one) stays on the tape;
+        first_dt_tracked="term" returns that extra term alone (the difference of the two modes, without their rounding).
         hi=True (FP32 oracle only): cotangents and accumulations in Float64 over the same FP32
         forward values -- the reference for judging the accuracy of FP32 adjoints."""
         D, B = self.cfg.D, self.cfg.B
@@ -262,6 +265,8 @@ class Oracle:
         nacc = max(self._naccept, 1)
         dtbar = np.zeros(nacc, dtype=np.float64)
         tbar = np.zeros(nacc, dtype=np.float64)
+        sd = self._fn("set_detach"); sd.argtypes = [C.c_void_p, C.c_int]
+        sd(self.h, 2 if first_dt_tracked == "term" else (1 if first_dt_tracked else 0))
         f = self._fn("backward_hi" if (hi and not self.f64) else "backward")
         f.argtypes = [C.c_void_p] * 8
         dus = None

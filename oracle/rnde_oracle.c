@@ -119,6 +119,10 @@ typedef struct {
     REAL* save_theta;       /* theta of the save inside its step (1 = copied end state) */
     int n_usaved;
     orc_stats st;
+    /* Appendix A.6 with detach_dt = all_but_first: the initial-dt heuristic stays on the tape (set_detach) */
+    int first_dt_tracked;   /* 0: every dt frozen (default); 1: dt_1 = initial_dt(theta, x) differentiated */
+    int last_clamped;       /* the last attempt's dt was tf - t (tracked through t when first_dt_tracked) */
+    REAL id_d0, id_d1, id_d2, id_dt0, id_dt1;   /* scalars of the initial-dt heuristic, kept for its adjoint */
 } orc_handle;
 
 static size_t n_params(const orc_config* c) {
@@ -703,7 +707,7 @@ static void interp_weights(REAL th, REAL* b) {
 /* initial dt (Hairer-Wanner, Appendix A.5)                            */
 /* ------------------------------------------------------------------ */
 static REAL initial_dt(const orc_config* c, const REAL* p, const REAL* u0, const REAL* f0, REAL t0, REAL dtmax, REAL* scratch /*3*D*B*/,
-                       REAL* colq) {
+                       REAL* colq, REAL* keep /* d0, d1, d2, dt0, dt1 */) {
     const int D = c->D, B = c->B;
     const long long cnt = (long long)D * B;
     const int kb = (c->arith == 2 && c->n_layers == 0) ? -(D / 4) : (c->kblock1 > 0 ? c->kblock1 : D);
@@ -754,6 +758,7 @@ static REAL initial_dt(const orc_config* c, const REAL* p, const REAL* u0, const
     if (dt1 < dt) dt = dt1;
     if (dtmax < dt) dt = dtmax;
     if (dt < (REAL)c->dtmin) dt = (REAL)c->dtmin;
+    if (keep) { keep[0] = d0; keep[1] = d1; keep[2] = d2; keep[3] = dt0; keep[4] = dt1; }
     return dt;
 }
 
@@ -908,7 +913,9 @@ int FN(forward)(void* hv, const REAL* x, const REAL* p, REAL* u_out, orc_stats* 
     rhs_eval(c, p, u, t, w->k[1], NULL); st.nf += 1;
     REAL dt;
     if (c->n_forced > 0) dt = (REAL)c->forced_dt[0];
-    else dt = initial_dt(c, p, u, w->k[1], t, dtmax, scratch, w->colq);
+    else { REAL keep[5]; dt = initial_dt(c, p, u, w->k[1], t, dtmax, scratch, w->colq, keep);
+           h->id_d0 = keep[0]; h->id_d1 = keep[1]; h->id_d2 = keep[2]; h->id_dt0 = keep[3]; h->id_dt1 = keep[4]; }
+    h->last_clamped = 0;
     st.nf += 2;
     st.dt_init = dt;
     /* AutoSwitch state (Appendix A.8) */
@@ -943,6 +950,7 @@ int FN(forward)(void* hv, const REAL* x, const REAL* p, REAL* u_out, orc_stats* 
             if (dt > dtmax) dt = dtmax;
             if (dt < (REAL)c->dtmin) dt = (REAL)c->dtmin;
             REAL rem = tf - t;
+            h->last_clamped = rem < dt;
             if (rem < dt) dt = rem;
         }
         REAL EEst, eig;
@@ -1069,4 +1077,7 @@ int FN(rhs)(const orc_config* cfg, const REAL* p, const REAL* z, double t, REAL*
 #undef BWD_FN
 #endif
 
+/* Appendix A.6: 0 = every dt frozen, 1 = the first dt (initial-dt heuristic) stays on the tape (recalled upstream default),
+ * 2 = diagnostic: the backward returns the first-dt term alone */
+int FN(set_detach)(void* hv, int first_dt_tracked) { ((orc_handle*)hv)->first_dt_tracked = first_dt_tracked; return ORC_OK; }
 int FN(sizeof_real)(void) { return (int)sizeof(REAL); }

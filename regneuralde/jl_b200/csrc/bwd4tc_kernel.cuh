@@ -24,6 +24,7 @@
 #pragma once
 #include <cuda_bf16.h>
 #include "common.cuh"
+#include "a6.cuh"
 #include "fwd4_kernel.cuh"
 #include "bwd4_kernel.cuh"
 #include "wgrad_tc_kernel.cuh"      // tcgen05 wrappers, umma_desc
@@ -201,6 +202,11 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
     const uint32_t bytesH = (uint32_t)((H - HSloc) * NP * 4);
     const size_t tileD = (size_t)D * NP, tileH = (size_t)H * NP;
     auto offD = [&](int rec, int i) -> size_t { return ((size_t)rec * P.Q + q) * tileD + (size_t)(r0 + crow0 + i) * NP + cn0; };
+    // Appendix A.6 (a6.cuh): this thread's part of dL/d(dt_1), and the time columns of W2 / W1 for the rows / hidden unit it owns
+    double dacc = 0.0;
+    float wdir = 0.f, wshift = 0.f;
+    const float* const w2t = gW2 + (size_t)D * H + r0 + crow0;      // read where needed (L1 resident): no registers held across the sweep
+    const float* const w1tp = gW1 + (size_t)H * D + rank * HS + (tid >> 2);
     const int quad = warp & 3;
     const uint32_t tlane = (uint32_t)(quad * 32) << 16;
 
@@ -214,7 +220,8 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
     float4 kvn[4];
     int kvn_rec = -1;
     // VJP of record `rec`: cur = kbar of that evaluation (in), zb = W1^T delta1 for the tile (out)
-    auto vjp = [&](const float (&cur)[16], float (&zb)[16], const int rec, const int rec_next) {
+    auto vjp = [&](const float (&cur)[16], float (&zb)[16], const int rec, const int rec_next, const float wt) {
+        const bool want_t = (wt != 0.f) && td;
         TLB(0);
         if (tid == 0) { mbar_expect_tx(barP, bytesP); mbar_expect_tx(barH, bytesH); }
         if (rec_next >= 0) {        // pull the next record's tiles towards L2
@@ -246,6 +253,7 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
                     *reinterpret_cast<float4*>(sZb + (crow0 + i) * NP + cn0) = d2;      // delta2 replaces k on the tape: bulk store below
                 } else d2 = make_float4(0.f, 0.f, 0.f, 0.f);
                 d2v[i][0] = d2.x; d2v[i][1] = d2.y; d2v[i][2] = d2.z; d2v[i][3] = d2.w;
+                if (want_t && i < cvalid) dacc += (double)(wt * __ldg(w2t + i) * ((d2.x + d2.y) + (d2.z + d2.w)));
             }
             // element (n, k = local row): crow0 is even, so rows (i, i+1) are an aligned bf16 pair inside one 8-group
 #ifndef RNDE_EXP_NOSPLIT
@@ -340,6 +348,7 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
                 const float4 hv = __ldcg(reinterpret_cast<const float4*>(P.tapeH + oh));
                 s.x *= (1.f - hv.x * hv.x); s.y *= (1.f - hv.y * hv.y); s.z *= (1.f - hv.z * hv.z); s.w *= (1.f - hv.w * hv.w);
             }
+            if (want_t) dacc += (double)(wt * __ldg(w1tp) * ((s.x + s.y) + (s.z + s.w)));
             float* dst = sD1 + m * NP + n4;
             *reinterpret_cast<float4*>(dst) = s;
             const uint32_t da = smem_u32(dst);
@@ -480,6 +489,14 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
             const float gA = use_eig ? n1b / (cntf * n1) : 0.f;
             gB = use_eig ? n2b / (cntf * n2) : 0.f;
             recU1 = 6 * s + 6; recG6 = 6 * s + 5;
+            // weight of this step's explicit dt in dL/d(dt_1) (first step: +1, last step when it was cut: -1) and of its start time
+            wdir = P.a6 ? ((s == 0 ? 1.f : 0.f) - (s == P.nsteps - 1 ? P.initdt[5] : 0.f)) : 0.f;
+            wshift = (P.a6 && s >= 1) ? 1.f : 0.f;
+            if (wdir != 0.f && sbar != 0.f && blockIdx.x == 0 && tid == 0) {
+                if (P.reg_kind == RNDE_REG_ERR_DT) dacc += wdir * sbar * EEst;
+                else if (P.reg_kind == RNDE_REG_STIFF_DT_ABS && P.alg == RNDE_ALG_AUTO_TSIT5) dacc += wdir * sbar * ((eig * dt) >= 0.f ? 1.f : -1.f) * eig;
+                else if (P.reg_kind == RNDE_REG_ERR_PLUS_STIFF) { const float e = EEst * dt; if (!(e == 0.f || e != e)) dacc += wdir * sbar * EEst; }
+            }
 #pragma unroll
             for (int a = 0; a < 6; ++a)
 #pragma unroll
@@ -529,6 +546,7 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
                                 const float dtu = dt * utb;
 #pragma unroll
                                 for (int j = 1; j <= 7; ++j) kb[j - 1][e] += c_BT[j] * dtu;
+                                dacc += (double)(wdir * utb * ssum);
                             }
                             if (use_eig) {
                                 const float ga = live * gA * (kv[6][jj] - kv[5][jj]);
@@ -572,7 +590,7 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
                 }
             }
         }
-        vjp(cur, zb, rec, rec_next);
+        vjp(cur, zb, rec, rec_next, last ? 0.f : wshift + wdir * ts_c(i));
         if (last) {
             // initial fsalfirst = f(u0, t0): dx = ubar + zbar
             if (P.dx && own) {
@@ -604,6 +622,26 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
                 }
             }
         }
+        if (wdir != 0.f && own) {       // explicit dt of z_i = u + dt * sum_j a_ij k_j (the records of stages < i still hold k)
+#pragma unroll 1
+            for (int ii = 0; ii < cvalid; ++ii) {
+                float a4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+                for (int jj = 1; jj < i; ++jj) {
+                    const float4 k4 = __ldcg(reinterpret_cast<const float4*>(P.tapeK + offD(6 * s + jj - 1, ii)));
+                    const float a = ts_a(i, jj);
+                    a4[0] = rn_fmaf(a, k4.x, a4[0]); a4[1] = rn_fmaf(a, k4.y, a4[1]); a4[2] = rn_fmaf(a, k4.z, a4[2]); a4[3] = rn_fmaf(a, k4.w, a4[3]);
+                }
+                float z4[4];
+                switch (ii) {       // zb lives in registers: constant indices only
+                    case 0: z4[0] = zb[0]; z4[1] = zb[1]; z4[2] = zb[2]; z4[3] = zb[3]; break;
+                    case 1: z4[0] = zb[4]; z4[1] = zb[5]; z4[2] = zb[6]; z4[3] = zb[7]; break;
+                    case 2: z4[0] = zb[8]; z4[1] = zb[9]; z4[2] = zb[10]; z4[3] = zb[11]; break;
+                    default: z4[0] = zb[12]; z4[1] = zb[13]; z4[2] = zb[14]; z4[3] = zb[15]; break;
+                }
+                dacc += (double)wdir * (((double)z4[0] * a4[0] + (double)z4[1] * a4[1]) + ((double)z4[2] * a4[2] + (double)z4[3] * a4[3]));
+            }
+        }
         switch (i) {
             case 2: bwd_distribute<2>(kb, zb, dt); break;
             case 3: bwd_distribute<3>(kb, zb, dt); break;
@@ -623,6 +661,7 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
 #ifdef RNDE_TIMELINE
     if (P.dbg && blockIdx.x == 0 && tid == 0) for (int k = 0; k < 14; ++k) P.dbg[k] = tl_acc[k];
 #endif
+    if (P.a6) a6_block_sum<NT>(dacc, sPart, P.a6_part);
     if (tid == 0) bulk_wait_all();
     tc_fence_before();
     __syncthreads();

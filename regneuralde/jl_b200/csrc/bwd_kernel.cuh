@@ -13,6 +13,7 @@
 #pragma once
 #include "common.cuh"
 #include "chain.cuh"
+#include "a6.cuh"
 
 namespace rnde {
 
@@ -101,10 +102,13 @@ __global__ void __launch_bounds__(NT, 1) bwd_kernel(const KParams P) {
 
     // VJP of one field evaluation (record `rec`).  On entry Kb(i) holds kbar_i; it is
     // turned into delta2 in place.  `epi(m, n0, zbar[4])` consumes zbar = W1^T delta1.
-    auto vjp = [&](float* sKbar, const int rec, auto epi) {
+    // Appendix A.6 (a6.cuh): this thread's part of dL/d(dt_1); `wt` weighs the time cotangent of the evaluation,
+    // `accum` adds the deltas to the record instead of replacing k (second VJP of record 0, k taken from the copy a6_f0)
+    double dacc = 0.0;
+    auto vjp = [&](float* sKbar, const int rec, const float wt, const bool accum, auto epi) {
         if constexpr (G == 1 && WS) {
             if (chain) {
-                const float* zb = chain_vjp<NP, NT>(P, cv, sKbar, rec, q);
+                const float* zb = chain_vjp<NP, NT>(P, cv, sKbar, rec, q, accum ? P.a6_f0 + (size_t)q * tileD : nullptr);
                 for (int e = tid; e < Rloc * (NP / 4); e += NT) {
                     const int m = e / (NP / 4), nn = (e - m * (NP / 4)) * 4;
                     epi(m, nn, zb + m * NP + nn);
@@ -114,12 +118,18 @@ __global__ void __launch_bounds__(NT, 1) bwd_kernel(const KParams P) {
             }
         }
         const size_t offD = tile_off_D(rec), offH = tile_off_H(rec);
+        const bool want_t = (wt != 0.f) && td;
         for (int e = tid; e < Rloc * NP; e += NT) {
             const float kb = sKbar[e];
             float d2 = kb;
-            if (P.act2 == RNDE_ACT_TANH) { const float kv = __ldcg(P.tapeK + offD + e); d2 = kb * (1.f - kv * kv); }
+            if (P.act2 == RNDE_ACT_TANH) {
+                const float kv = accum ? __ldcg(P.a6_f0 + (size_t)q * tileD + (size_t)r0 * NP + e) : __ldcg(P.tapeK + offD + e);
+                d2 = kb * (1.f - kv * kv);
+            }
             sKbar[e] = d2;
-            P.tapeK[offD + e] = d2;       // delta2 replaces k in the tape (consumed by wgrad)
+            if (accum) P.tapeK[offD + e] += d2;
+            else P.tapeK[offD + e] = d2;       // delta2 replaces k in the tape (consumed by wgrad)
+            if (want_t) dacc += (double)(wt * d2 * __ldg(gW2 + (size_t)D * H + r0 + e / NP));
         }
         __syncthreads();
         // phase A': hbar partial = W2[rows, :H]^T delta2   (split-K over this CTA's rows)
@@ -188,7 +198,9 @@ __global__ void __launch_bounds__(NT, 1) bwd_kernel(const KParams P) {
             } else {
                 sD1[m * NP + n] = d1;
             }
-            P.tapeD1[offH + (size_t)m * NP + n] = d1;
+            if (accum) P.tapeD1[offH + (size_t)m * NP + n] += d1;
+            else P.tapeD1[offH + (size_t)m * NP + n] = d1;
+            if (want_t) dacc += (double)(wt * d1 * __ldg(gW1 + (size_t)H * D + m));
         }
         group_sync<G>();
         // phase C': zbar = W1[:, rows]^T delta1  for this CTA's rows
@@ -239,6 +251,79 @@ __global__ void __launch_bounds__(NT, 1) bwd_kernel(const KParams P) {
     const float cntf = (float)P.norm_count;
     const float stab = rn_divf(1.0f, (float)TS_STABILITY_SIZE);
 
+    // ---- Appendix A.6: the two evaluations of the initial-dt heuristic (launched after the sweep, a6.cuh) ----------------
+    if (P.a6_mode != 0) {
+        const A6Scal sc = a6_scalars(P);
+        const float d0 = P.initdt[0], d1 = P.initdt[1], d2 = P.initdt[2], dt0 = P.initdt[3];
+        const float* f0t = P.a6_f0 + (size_t)q * tileD + (size_t)r0 * NP;
+        const size_t boff = (size_t)q * tileD + (size_t)r0 * NP, bstr = (size_t)P.Q * tileD;     // three buffers: u1bar, f1bar, w * wbar
+        const size_t off0 = tile_off_D(0);
+        double part = 0.0;
+        if (P.a6_mode == 1) {
+            // cotangent of f1 through d2 = rms((f1 - f0) / sk) / dt0
+            const float r2 = d2 * dt0;
+            const float coef = (sc.d2bar != 0.f && r2 > 0.f) ? (sc.d2bar / dt0) / (cntf * r2) : 0.f;
+            const size_t offx = tile_off_D(P.rec_x);
+            for (int e = tid; e < Rloc * NP; e += NT) {
+                const float u0 = __ldcg(P.tapeZ + off0 + e), f0 = __ldcg(f0t + e), f1 = __ldcg(P.tapeK + offx + e);
+                const float sk = rn_fmaf(fabsf(u0), rtol, atol);
+                const float wv = (f1 - f0) / sk;
+                const float wb = ((e % NP) < Nloc) ? coef * wv : 0.f;
+                Kb(7)[e] = wb / sk;
+                P.a6_u1bar[bstr + boff + e] = wb / sk;
+                P.a6_u1bar[2 * bstr + boff + e] = wb * wv / sk;
+            }
+            __syncthreads();
+            vjp(Kb(7), P.rec_x, 1.f, false, [&](const int m, const int nn, const float* zb) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int e = m * NP + nn + j;
+                    P.a6_u1bar[boff + e] = zb[j];
+                    part += (double)(zb[j] * __ldcg(f0t + e));       // u1 = u0 + dt0 f0: <u1bar, f0> goes to dt0
+                }
+            });
+            part += dacc;      // the evaluation's time t0 + dt0
+            if (blockIdx.x == 0 && tid == 0) {      // the pseudo-step whose stage 7 (time t + dt) is this record, for the wgrad time row
+                StepRec sr; sr.t = P.t0; sr.dt = dt0; sr.eest = 0.f; sr.eig = 0.f; sr.n1 = 0.f; sr.n2 = 0.f; sr.pad0 = 0.f; sr.pad1 = 0.f;
+                P.steps[P.nsteps] = sr;
+            }
+        } else {
+            float dt0bar = sc.dt0bar + (float)P.a6_sum[1], d0bar = 0.f, d1bar = sc.d1bar;
+            if (sc.dt0_free) { d0bar = dt0bar * dt0 / d0; d1bar -= dt0bar * dt0 / d1; }
+            const float c1 = (d1bar != 0.f && d1 > 0.f) ? d1bar / (cntf * d1) : 0.f;
+            const float c0f = (d0bar != 0.f && d0 > 0.f) ? d0bar / (cntf * d0) : 0.f;
+            for (int e = tid; e < Rloc * NP; e += NT) {
+                float f0bar = 0.f, u0bar = 0.f;
+                if ((e % NP) < Nloc) {
+                    const float u0 = __ldcg(P.tapeZ + off0 + e), f0 = __ldcg(f0t + e);
+                    const float sk = rn_fmaf(fabsf(u0), rtol, atol);
+                    const float u1b = P.a6_u1bar[boff + e], f1b = P.a6_u1bar[bstr + boff + e], wwb = P.a6_u1bar[2 * bstr + boff + e];
+                    const float v = f0 / sk, y = u0 / sk;
+                    const float vb = c1 * v, yb = c0f * y;
+                    f0bar = rn_fmaf(dt0, u1b, vb / sk - f1b);
+                    const float skbar = -wwb - (vb * v + yb * y) / sk;
+                    u0bar = u1b + yb / sk + skbar * rtol * (u0 > 0.f ? 1.f : (u0 < 0.f ? -1.f : 0.f));
+                }
+                Kb(7)[e] = f0bar;
+                sUb[e] = u0bar;
+            }
+            __syncthreads();
+            vjp(Kb(7), 0, 0.f, true, [&](const int m, const int nn, const float* zb) {
+                if (P.dx) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int n = nn + j;
+                        if (n < Nloc) P.dx[(size_t)D * (c0 + n) + r0 + m] += sUb[m * NP + n] + zb[j];
+                    }
+                }
+            });
+        }
+        a6_block_sum<NT>(part, sUpb, P.a6_part);
+        if constexpr (G > 1) cluster_sync_all();
+        return;
+    }
+    const float clampN = P.a6 ? P.initdt[5] : 0.f;
+
     // saveat cotangents are consumed newest first; times beyond the last accepted step were never saved
     int sidx = P.dusave ? P.n_saveat - 1 : -1;
     if (sidx >= 0) {
@@ -279,6 +364,14 @@ __global__ void __launch_bounds__(NT, 1) bwd_kernel(const KParams P) {
         const float gA = use_eig ? n1b / (cntf * n1) : 0.f;    // multiplies (k7-k6)
         const float gB = use_eig ? n2b / (cntf * n2) : 0.f;    // multiplies (u-g6)
         const int recU0 = 6 * s, recU1 = 6 * s + 6, recG6 = 6 * s + 5;
+        // weight of this step's explicit dt in dL/d(dt_1): the first step takes dt_1, the last one shrinks by it when it was cut
+        const float wdir = P.a6 ? ((s == 0 ? 1.f : 0.f) - (s == P.nsteps - 1 ? clampN : 0.f)) : 0.f;
+        const float wshift = (P.a6 && s >= 1) ? 1.f : 0.f;      // ... and every later step starts dt_1 later
+        if (wdir != 0.f && sbar != 0.f && blockIdx.x == 0 && tid == 0) {
+            if (P.reg_kind == RNDE_REG_ERR_DT) dacc += (double)(wdir * sbar * EEst);
+            else if (P.reg_kind == RNDE_REG_STIFF_DT_ABS && P.alg == RNDE_ALG_AUTO_TSIT5) dacc += wdir * sbar * ((eig * dt) >= 0.f ? 1.f : -1.f) * eig;
+            else if (P.reg_kind == RNDE_REG_ERR_PLUS_STIFF) { const float e = EEst * dt; if (!(e == 0.f || e != e)) dacc += wdir * sbar * EEst; }
+        }
 
         // reset the per-step cotangents (Kb(7) carries k7bar from the following step)
         for (int e = tid; e < Rloc * NP; e += NT) {
@@ -300,6 +393,11 @@ __global__ void __launch_bounds__(NT, 1) bwd_kernel(const KParams P) {
                     sUpb[e] += g;
 #pragma unroll
                     for (int j = 1; j <= 7; ++j) Kb(j)[e] += (dt * bw[j]) * g;
+                    if (wdir != 0.f) {
+                        float ssum = 0.f;
+                        for (int j = 1; j <= 7; ++j) ssum = rn_fmaf(bw[j], __ldcg(P.tapeK + tile_off_D(6 * s + j - 1) + e), ssum);
+                        dacc += (double)(wdir * g * ssum);
+                    }
                 }
             }
             --sidx;
@@ -333,6 +431,7 @@ __global__ void __launch_bounds__(NT, 1) bwd_kernel(const KParams P) {
                     }
 #pragma unroll
                     for (int j = 1; j <= 7; ++j) Kb(j)[e] += dt * ts_bt(j) * utb;
+                    dacc += (double)(wdir * utb * ssum);
                 }
                 if (use_eig) {
                     const float g6 = __ldcg(P.tapeZ + tile_off_D(recG6) + e);
@@ -346,7 +445,7 @@ __global__ void __launch_bounds__(NT, 1) bwd_kernel(const KParams P) {
         }
         for (int i = 7; i >= 2; --i) {
             const int rec = 6 * s + i - 1;
-            vjp(Kb(i), rec, [&](const int m, const int nn, const float* zb) {
+            vjp(Kb(i), rec, wshift + wdir * ts_c(i), false, [&](const int m, const int nn, const float* zb) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int e = m * NP + nn + j;
@@ -359,6 +458,11 @@ __global__ void __launch_bounds__(NT, 1) bwd_kernel(const KParams P) {
                     }
                     for (int jj = 1; jj < i; ++jj) Kb(jj)[e] = rn_fmaf(dt * ts_a(i, jj), g, Kb(jj)[e]);
                     sUpb[e] += g;
+                    if (wdir != 0.f && (nn + j) < Nloc) {       // z_i = u + dt * sum_j a_ij k_j (records of the later stages already hold deltas)
+                        float ssum = 0.f;
+                        for (int jj = 1; jj < i; ++jj) ssum = rn_fmaf(ts_a(i, jj), __ldcg(P.tapeK + tile_off_D(6 * s + jj - 1) + e), ssum);
+                        dacc += (double)(wdir * g * ssum);
+                    }
                 }
             });
         }
@@ -368,7 +472,7 @@ __global__ void __launch_bounds__(NT, 1) bwd_kernel(const KParams P) {
         __syncthreads();
     }
     // initial fsalfirst = f(u0, t0): record 0, cotangent carried in Kb(7)
-    vjp(Kb(7), 0, [&](const int m, const int nn, const float* zb) {
+    vjp(Kb(7), 0, 0.f, false, [&](const int m, const int nn, const float* zb) {
         if (P.dx) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -381,6 +485,7 @@ __global__ void __launch_bounds__(NT, 1) bwd_kernel(const KParams P) {
             }
         }
     });
+    if (P.a6) a6_block_sum<NT>(dacc, sUpb, P.a6_part);
     if constexpr (G > 1) cluster_sync_all();
 }
 

@@ -140,8 +140,9 @@ __device__ __forceinline__ void chain_rhs(const KParams& P, const ChainView& c, 
 
 // VJP of record `rec`: on entry sKbar holds kbar (D x NP); delta_{L-1} replaces k on the tape, delta_l (l < L-1) goes
 // to tapeD1 at the row offset of a_{l+1}; the input cotangent ends up in shared memory (D x NP), returned.
+// kalt != nullptr (a6.cuh, second VJP of record 0): k is read from that copy and the deltas are ADDED to the record's.
 template <int NP, int NT>
-__device__ __forceinline__ const float* chain_vjp(const KParams& P, const ChainView& c, float* sKbar, const int rec, const int q) {
+__device__ __forceinline__ const float* chain_vjp(const KParams& P, const ChainView& c, float* sKbar, const int rec, const int q, const float* kalt = nullptr) {
     const int tid = threadIdx.x;
     const int D = c.D;
     const size_t hbase = ((size_t)rec * P.Q + q) * c.hrows * NP;
@@ -158,9 +159,10 @@ __device__ __forceinline__ const float* chain_vjp(const KParams& P, const ChainV
     for (int e = tid; e < c.hrows * NP; e += NT) c.sH[e] = __ldcg(P.tapeH + hbase + e);
     for (int e = tid; e < D * NP; e += NT) {
         float d = sKbar[e];
-        if (c.a[c.L - 1] == RNDE_ACT_TANH) { const float kv = __ldcg(P.tapeK + dbase + e); d = d * (1.f - kv * kv); }
+        if (c.a[c.L - 1] == RNDE_ACT_TANH) { const float kv = kalt ? __ldcg(kalt + e) : __ldcg(P.tapeK + dbase + e); d = d * (1.f - kv * kv); }
         g[e] = d;
-        P.tapeK[dbase + e] = d;
+        if (kalt) P.tapeK[dbase + e] += d;
+        else P.tapeK[dbase + e] = d;
     }
     __syncthreads();
     for (int l = c.L - 1; l >= 0; --l) {
@@ -172,7 +174,7 @@ __device__ __forceinline__ const float* chain_vjp(const KParams& P, const ChainV
         quad_dense_any<NP, NT, true>(c.sW + poff[l], M, K, g, [&](const int i, const int n, float v) {
             if (actin == RNDE_ACT_TANH) { const float av = ain[i * NP + n]; v = v * (1.f - av * av); }
             gn[i * NP + n] = v;
-            if (dout) dout[i * NP + n] = v;
+            if (dout) { if (kalt) dout[i * NP + n] += v; else dout[i * NP + n] = v; }
         });
         __syncthreads();
         float* t = g; g = gn; gn = t;

@@ -50,6 +50,16 @@ struct KParams {
     float* usave; const float* dusave;
     // fixed-work replay (rnde_set_forced_steps): dt of attempt i, every attempt accepted
     const float* forced_dt; int n_forced;
+    // Appendix A.6 with the first dt on the tape (rnde_set_detach, a6.cuh): dt_1 = initial_dt(theta, x) is differentiated
+    int a6;                 // forward: tape the evaluation of the initial-dt heuristic; sweep: accumulate dL/d(dt_1)
+    int a6_mode;            // bwd_kernel: 0 = sweep, 1 = VJP of f(u0 + dt0 f0, t0 + dt0), 2 = VJP of f0 added to record 0
+    int rec_init;           // tape record the forward writes the initial-dt evaluation to (copied behind the last step for wgrad)
+    int rec_x;              // record the adjoint of that evaluation is written to: 6 * nsteps + 6 (stage 7 of a pseudo-step)
+    float* initdt;          // [8] d0, d1, d2, dt0, dt1, last attempt cut to land on t1 (0/1)
+    double* a6_part;        // [gridDim.x] per-CTA partial sums of the running kernel
+    const float* a6_sum;    // [2] reduced over CTAs (and ranks): dL/d(dt_1) of the sweep; <u1bar, f0> + tbar of phase 1
+    float* a6_u1bar;        // [tile][row][NP] cotangent of u1 = u0 + dt0 f0 (phase 1 -> phase 2)
+    const float* a6_f0;     // [tile][row][NP] copy of record 0's k = f0, taken before the sweep replaces it by delta2
     // chain field (chain.cuh): layer widths / activations, pre-activation, tape rows per column, shared-memory offsets (floats)
     int n_layers; int lw[8]; int la[8]; int pre_act; int hrows; int chain_np; int oCW, oCA, oCB, oCH;
     // FFJORD field (csq.cuh): Hutchinson noise ((D - csq_extra) x B, column-major), augmented rows, shared-memory offset of its region

@@ -496,6 +496,7 @@ __global__ void __launch_bounds__(V5_NT, 1) fwd4s_kernel(const KParams P) {
                 if (dt > dtmax) dt = dtmax;
                 if (dt < P.dtmin) dt = P.dtmin;
                 const float rem = P.t1 - c.t;
+                if (blockIdx.x == 0 && P.initdt) P.initdt[5] = rem < dt ? 1.f : 0.f;
                 if (rem < dt) dt = rem;
                 c.dt = dt;
             }
@@ -505,7 +506,7 @@ __global__ void __launch_bounds__(V5_NT, 1) fwd4s_kernel(const KParams P) {
 
     // One field evaluation per trip; `stage`: 0 = fsalfirst = f(u0,t0); 1 = f(u0 + dt0*f0) of the initial-dt heuristic; 2..7 = Tsit5 stages
     int stage = 0;
-    float t = P.t0, dt = 0.f, a2 = 0.f, dt0 = 0.f, d1_keep = 0.f;
+    float t = P.t0, dt = 0.f, a2 = 0.f, dt0 = 0.f, d1_keep = 0.f, d0_keep = 0.f;
     int srec = -1;
     while (true) {
         float tstage;
@@ -522,6 +523,7 @@ __global__ void __launch_bounds__(V5_NT, 1) fwd4s_kernel(const KParams P) {
 #pragma unroll
                 for (int e = 0; e < 16; ++e) zc[e] = rn_fmaf(dt0, kk[0][e], up[e]);
                 tstage = P.t0 + dt0;
+                rec = (P.need_tape && P.a6) ? P.rec_init : -1;      // Appendix A.6: this evaluation stays on the tape
             } else {
                 switch (stage) {
                     case 2: combo_stage<2>(kk, up, dt, a2, zc); break;
@@ -553,7 +555,7 @@ __global__ void __launch_bounds__(V5_NT, 1) fwd4s_kernel(const KParams P) {
             if (d0 < (float)1e-5 || d1 < (float)1e-5) dt0 = (float)1e-6;
             else dt0 = rn_divf(rn_divf(d0, d1), 100.f);
             if (dt0 > dtmax) dt0 = dtmax;
-            d1_keep = d1;
+            d1_keep = d1; d0_keep = d0;
             stage = 1;
             continue;
         }
@@ -583,6 +585,7 @@ __global__ void __launch_bounds__(V5_NT, 1) fwd4s_kernel(const KParams P) {
                 if (dtmax < dti) dti = dtmax;
                 if (dti < P.dtmin) dti = P.dtmin;
                 ctl->dt = dti; ctl->dtpropose = dti; ctl->dt_init = dti; ctl->nf = 3;
+                if (blockIdx.x == 0 && P.initdt) { P.initdt[0] = d0_keep; P.initdt[1] = d1; P.initdt[2] = d2; P.initdt[3] = dt0; P.initdt[4] = dt1; }
             }
             __syncthreads();
             loopheader();

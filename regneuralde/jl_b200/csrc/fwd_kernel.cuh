@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(NT, 1) fwd_kernel(const KParams P) {
         if (dt0 > dtmax) dt0 = dtmax;
         for (int e = tid; e < Rloc * NP; e += NT) sZ[e] = rn_fmaf(dt0, K(1)[e], sU[e]);
         __syncthreads();
-        rhs(sZ, K(2), P.t0 + dt0, -1);
+        rhs(sZ, K(2), P.t0 + dt0, (P.need_tape && P.a6) ? P.rec_init : -1);      // Appendix A.6: this evaluation stays on the tape
         float d2v[1];
         grid_rms<G, NP, 1, NT>(P, L, smem, rank, q, Rloc, Nloc, norm_seq, bar_gen,
             [&](int r, int n, float* o) {
@@ -510,6 +510,7 @@ __global__ void __launch_bounds__(NT, 1) fwd_kernel(const KParams P) {
             if (dtmax < dt) dt = dtmax;
             if (dt < P.dtmin) dt = P.dtmin;
             ctl->dt = dt; ctl->dtpropose = dt; ctl->dt_init = dt; ctl->nf = 3;
+            if (blockIdx.x == 0 && P.initdt) { P.initdt[0] = d0; P.initdt[1] = d1; P.initdt[2] = d2; P.initdt[3] = dt0; P.initdt[4] = dt1; }
         }
         __syncthreads();
     }
@@ -552,6 +553,7 @@ __global__ void __launch_bounds__(NT, 1) fwd_kernel(const KParams P) {
                 if (dt > dtmax) dt = dtmax;
                 if (dt < P.dtmin) dt = P.dtmin;
                 const float rem = P.t1 - c.t;
+                if (blockIdx.x == 0 && P.initdt) P.initdt[5] = rem < dt ? 1.f : 0.f;
                 if (rem < dt) dt = rem;
                 c.dt = dt;
             }

@@ -50,6 +50,10 @@ struct rnde_handle {
     float* head_ws = nullptr;
     float* saveat_dev = nullptr; int n_saveat = 0;
     float* forced_dev = nullptr; int n_forced = 0;      // fixed-work replay (rnde_set_forced_steps)
+    // Appendix A.6 with the first dt on the tape (rnde_set_detach, a6.cuh)
+    int detach = RNDE_DETACH_ALL_BUT_FIRST;
+    float* initdt = nullptr; double* a6_part = nullptr; float* a6_sum = nullptr; float* a6_buf = nullptr; float* a6_f0 = nullptr;
+    size_t smem_a6 = 0;
     const float* noise = nullptr;       // FFJORD: caller-owned Hutchinson noise (rnde_set_noise)
     long long* dbg = nullptr;
     // host-path staging
@@ -156,6 +160,12 @@ static kern_t bwd_kernel_for(int variant, int D = 0, int H = 0) {
         default: return nullptr;
     }
 }
+// the two extra VJPs of Appendix A.6 (bwd_kernel a6_mode 1 / 2): the variant's own generic sweep, or for the cluster-4
+// variant the generic kernel on the same cluster shape and tape layout (4 CTAs x 16 columns, weights streamed from L2)
+static kern_t a6_kernel_for(int variant) {
+    if (variant == RNDE_KERNEL_CLUSTER4) return bwd_kernel<4, 16, 4, false, NT_FWD>;
+    return bwd_kernel_for(variant);
+}
 static void variant_shape(int variant, int* G, int* NP, bool* WS) {
     switch (variant) {
         case RNDE_KERNEL_CTA: *G = 1; *NP = 32; *WS = true; break;
@@ -258,6 +268,7 @@ static void free_all(rnde_handle* h) {
     for (int i = 0; i < 8; ++i) if (h->peers_open[i]) cudaIpcCloseMemHandle((void*)h->peers[i]);
     cudaFree(h->colsum); cudaFree(h->bar); cudaFree(h->steps); cudaFree(h->stats);
     cudaFree(h->tapeZ); cudaFree(h->tapeK); cudaFree(h->tapeH); cudaFree(h->tapeD1); cudaFree(h->wg_ws); cudaFree(h->scal); cudaFree(h->saveval_int);
+    cudaFree(h->initdt); cudaFree(h->a6_part); cudaFree(h->a6_sum); cudaFree(h->a6_buf); cudaFree(h->a6_f0);
     cudaFree(h->dtile); cudaFree(h->head_ws); cudaFree(h->dbg); cudaFree(h->saveat_dev); cudaFree(h->forced_dev);
     if (h->ev_stats) cudaEventDestroy(h->ev_stats);
     cudaFree(h->hx); cudaFree(h->hp); cudaFree(h->hu); cudaFree(h->hsv); cudaFree(h->hdu); cudaFree(h->hdsv); cudaFree(h->hdp); cudaFree(h->hdx);
@@ -302,9 +313,15 @@ static int try_variant(rnde_handle* h, int variant, size_t smem_limit, std::stri
     }
     kern_t kf = fwd_kernel_for(variant, D, H, c.arith, c.csq_extra);
     if (cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sf) != cudaSuccess) { cudaGetLastError(); *why = "cudaFuncSetAttribute(fwd) failed"; return 0; }
+    size_t sa = sb;
     if (c.need_backward) {
         kern_t kb = bwd_kernel_for(variant, D, H);
         if (cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb) != cudaSuccess) { cudaGetLastError(); *why = "cudaFuncSetAttribute(bwd) failed"; return 0; }
+        if (variant == RNDE_KERNEL_CLUSTER4) {
+            sa = (size_t)make_bwd_layout(4, 16, false, D, H, R, HS).total * sizeof(float);
+            if (sa > smem_limit) { *why = "shared memory (initial-dt adjoint): need " + std::to_string(sa) + " B"; return 0; }
+            if (cudaFuncSetAttribute(a6_kernel_for(variant), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa) != cudaSuccess) { cudaGetLastError(); *why = "cudaFuncSetAttribute(a6) failed"; return 0; }
+        }
     }
     int max_cta = 0;
     if (G == 1) {
@@ -333,7 +350,7 @@ static int try_variant(rnde_handle* h, int variant, size_t smem_limit, std::stri
         }
     }
     if (Q * G > max_cta) { *why = "grid of " + std::to_string(Q * G) + " CTAs exceeds co-resident capacity " + std::to_string(max_cta); return 0; }
-    h->variant = variant; h->G = G; h->NP = NP; h->R = R; h->HS = HS; h->Q = Q; h->smem_fwd = sf; h->smem_bwd = sb;
+    h->variant = variant; h->G = G; h->NP = NP; h->R = R; h->HS = HS; h->Q = Q; h->smem_fwd = sf; h->smem_bwd = sb; h->smem_a6 = sa;
     return 1;
 }
 
@@ -418,14 +435,20 @@ extern "C" int rnde_create(const rnde_config* cfg, rnde_handle** out) {
     h->peers[h->cfg.rank] = (unsigned long long)h->colsum;
     h->dist_ready = h->cfg.dist_mode != RNDE_DIST_EXACT || h->cfg.nranks == 1;
     if (cudaMalloc(&h->bar, sizeof(unsigned) * 4) != cudaSuccess) return fail("cudaMalloc bar");
-    if (cudaMalloc(&h->steps, sizeof(StepRec) * c.tape_capacity) != cudaSuccess) return fail("cudaMalloc steps");
+    if (cudaMalloc(&h->steps, sizeof(StepRec) * (c.tape_capacity + 1)) != cudaSuccess) return fail("cudaMalloc steps");      // + the pseudo-step of a6.cuh
+    if (cudaMalloc(&h->initdt, sizeof(float) * 8) != cudaSuccess || cudaMemset(h->initdt, 0, sizeof(float) * 8) != cudaSuccess) return fail("cudaMalloc initdt");
     if (cudaMalloc(&h->stats, sizeof(DevStats)) != cudaSuccess) return fail("cudaMalloc stats");
     if (cudaMalloc(&h->saveval_int, sizeof(float) * (c.tape_capacity + 1)) != cudaSuccess) return fail("cudaMalloc saveval");
     if (cudaMallocHost(&h->stats_pinned, sizeof(DevStats)) != cudaSuccess) return fail("cudaMallocHost stats");
     if (cudaEventCreateWithFlags(&h->ev_stats, cudaEventDisableTiming) != cudaSuccess) return fail("cudaEventCreate");
     if (c.need_backward) {
-        const size_t nrec = 1 + (size_t)6 * c.tape_capacity;
+        // records: fsalfirst + 6 per step, + one pseudo-step and the initial-dt evaluation of Appendix A.6 (a6.cuh)
+        const size_t nrec = 1 + (size_t)6 * (c.tape_capacity + 1) + 1;
         const size_t tile = (size_t)h->Q * h->NP;
+        if (cudaMalloc(&h->a6_part, sizeof(double) * (size_t)h->Q * h->G) != cudaSuccess) return fail("cudaMalloc a6_part");
+        if (cudaMalloc(&h->a6_sum, sizeof(float) * 4) != cudaSuccess) return fail("cudaMalloc a6_sum");
+        if (cudaMalloc(&h->a6_buf, sizeof(float) * 3 * tile * D) != cudaSuccess) return fail("cudaMalloc a6_buf");
+        if (cudaMalloc(&h->a6_f0, sizeof(float) * tile * D) != cudaSuccess) return fail("cudaMalloc a6_f0");
         if (cudaMalloc(&h->tapeZ, sizeof(float) * nrec * tile * D) != cudaSuccess) return fail("cudaMalloc tapeZ (lower tape_capacity?)");
         if (cudaMalloc(&h->tapeK, sizeof(float) * nrec * tile * D) != cudaSuccess) return fail("cudaMalloc tapeK (lower tape_capacity?)");
         const size_t hrows = c.n_layers > 0 ? (size_t)chain_hrows(c) : (size_t)H;
@@ -536,6 +559,9 @@ static void fill_params(const rnde_handle* h, KParams& P) {
     for (int l = 0; l < 8; ++l) { P.lw[l] = c.layer_width[l]; P.la[l] = c.layer_act[l]; }
     P.tapeZ = h->tapeZ; P.tapeK = h->tapeK; P.tapeH = h->tapeH; P.tapeD1 = h->tapeD1; P.scal = h->scal;
     P.forced_dt = h->forced_dev; P.n_forced = h->n_forced;
+    P.a6 = (c.need_backward && h->detach != RNDE_DETACH_ALL && h->n_forced == 0 && c.csq_extra == 0) ? 1 : 0;
+    P.rec_init = 1 + 6 * (c.tape_capacity + 1);
+    P.initdt = h->initdt; P.a6_part = h->a6_part; P.a6_sum = h->a6_sum; P.a6_u1bar = h->a6_buf; P.a6_f0 = h->a6_f0;
 }
 
 // shared-memory offsets of the chain region: right after the generic kernel's own layout
@@ -662,11 +688,58 @@ static int backward_impl(rnde_handle* h, const float* du_dev, const float* dusav
         bool WS; int G, NP; variant_shape(h->variant, &G, &NP, &WS);
         set_chain_offsets(h, P, make_bwd_layout(G, NP, WS, h->cfg.state_dim, h->cfg.hidden_dim, h->R, h->HS).total);
     }
+    // Appendix A.6 (a6.cuh): the sweep also accumulates dL/d(dt_1); two more VJPs then differentiate the initial-dt heuristic.
+    // Their records sit behind the last step: 6N+1..6N+5 empty, 6N+6 the evaluation f(u0 + dt0 f0, t0 + dt0).
+    const bool a6 = P.a6 && s.naccept > 0;
+    P.a6 = a6 ? 1 : 0;
+    // the tensor-core contraction takes the extra record in the spare K slot of the first step's group, where it lies;
+    // the other contractions see it as stage 7 of a pseudo-step behind the last one (records 6N+1..6N+5 empty)
+    static const bool force_ffma = getenv("RNDE_WGRAD_FFMA") != nullptr;
+    const bool wg_tc = h->NP == 16 && !force_ffma && h->cfg.n_layers == 0;
+    const size_t tileN = (size_t)h->Q * h->NP;
+    const size_t recD = tileN * h->cfg.state_dim;
+    const size_t recH = tileN * (h->cfg.n_layers > 0 ? (size_t)chain_hrows(h->cfg) : (size_t)h->cfg.hidden_dim);
+    if (a6) CUDA_TRY(h, cudaMemcpyAsync(h->a6_f0, h->tapeK, sizeof(float) * recD, cudaMemcpyDeviceToDevice, st));      // f0, before delta2 replaces it
+    if (a6 && !wg_tc) {
+        const size_t rx = (size_t)6 * s.naccept + 6, ri = (size_t)P.rec_init;
+        CUDA_TRY(h, cudaMemcpyAsync(h->tapeZ + rx * recD, h->tapeZ + ri * recD, sizeof(float) * recD, cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(h, cudaMemcpyAsync(h->tapeK + rx * recD, h->tapeK + ri * recD, sizeof(float) * recD, cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(h, cudaMemcpyAsync(h->tapeH + rx * recH, h->tapeH + ri * recH, sizeof(float) * recH, cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(h, cudaMemsetAsync(h->tapeK + (rx - 5) * recD, 0, sizeof(float) * 5 * recD, st));
+        CUDA_TRY(h, cudaMemsetAsync(h->tapeD1 + (rx - 5) * recH, 0, sizeof(float) * 5 * recH, st));
+    }
     CUDA_TRY(h, cudaMemsetAsync(h->bar, 0, sizeof(unsigned) * 4, st));
     int rc = launch(h, bwd_kernel_for(h->variant, h->cfg.state_dim, h->cfg.hidden_dim), P, h->smem_bwd, st);
     if (rc != RNDE_OK) return rc;
+    if (a6) {
+        const int nparts = h->Q * h->G;
+        auto reduce = [&](int slot) -> int {
+            a6_reduce_kernel<<<1, 256, 0, st>>>(h->a6_part, nparts, h->a6_sum, slot);
+            CUDA_TRY(h, cudaGetLastError());
+            h->launches += 1;
+            // reference-exact data parallel: the step sequence is shared, so dL/d(dt_1) is the sum over all ranks' columns
+            if (h->cfg.nranks > 1 && h->cfg.dist_mode == RNDE_DIST_EXACT) return rnde_allreduce_grads(h, h->a6_sum + slot, 1, stream);
+            return RNDE_OK;
+        };
+        KParams PA = P;
+        PA.du = nullptr; PA.dusave = nullptr; PA.n_saveat = 0; PA.rec_x = wg_tc ? P.rec_init : 6 * s.naccept + 6;
+        if (h->variant == RNDE_KERNEL_CLUSTER4) { PA.n_layers = 0; }
+        if ((rc = reduce(0)) != RNDE_OK) return rc;
+        if (h->detach == RNDE_DETACH_FIRST_TERM_ONLY) {      // diagnostic: drop what the sweep produced, keep only the first-dt term
+            const size_t nr = (size_t)6 * s.naccept + 1;
+            CUDA_TRY(h, cudaMemsetAsync(h->tapeK, 0, sizeof(float) * nr * recD, st));
+            CUDA_TRY(h, cudaMemsetAsync(h->tapeD1, 0, sizeof(float) * nr * recH, st));
+            if (dx_dev) CUDA_TRY(h, cudaMemsetAsync(dx_dev, 0, sizeof(float) * (size_t)h->cfg.state_dim * h->cfg.batch, st));
+        }
+        PA.a6_mode = 1;
+        if ((rc = launch(h, a6_kernel_for(h->variant), PA, h->smem_a6, st)) != RNDE_OK) return rc;
+        if ((rc = reduce(1)) != RNDE_OK) return rc;
+        PA.a6_mode = 2;
+        if ((rc = launch(h, a6_kernel_for(h->variant), PA, h->smem_a6, st)) != RNDE_OK) return rc;
+    }
+    const int nsteps_w = s.naccept + ((a6 && !wg_tc) ? 1 : 0);      // steps the weight-gradient contraction runs over
     if (h->cfg.n_layers > 0) {      // chain field: per-layer contractions over the tape, FP64 across stages
-        const int nrec_c = 1 + 6 * s.naccept;
+        const int nrec_c = 1 + 6 * nsteps_w;
         WgDesc desc; memset(&desc, 0, sizeof(desc));
         desc.nl = h->cfg.n_layers;
         const int hrows = chain_hrows(h->cfg), Dd = h->cfg.state_dim;
@@ -684,12 +757,11 @@ static int backward_impl(rnde_handle* h, const float* du_dev, const float* dusav
         return RNDE_OK;
     }
     // parameter gradients: two batched contractions over (record, column) -- see wgrad_kernel.cuh
-    const int nrec = 1 + 6 * s.naccept;
+    const int nrec = 1 + 6 * nsteps_w;
     // tensor-core (tcgen05 3xTF32) contraction for the 16-column tape layout; RNDE_WGRAD_FFMA=1 selects the FFMA kernel
-    static const bool force_ffma = getenv("RNDE_WGRAD_FFMA") != nullptr;
-    if (h->NP == 16 && !force_ffma) {
+    if (wg_tc) {
         rc = launch_wgrad_tc(h->cfg.state_dim, h->cfg.hidden_dim, h->cfg.time_dep ? 1 : 0, nrec, h->Q, h->tapeZ, h->tapeK, h->tapeH, h->tapeD1,
-                             h->steps, h->cfg.t0, h->wg_ws, dp_dev, st, &h->launches);
+                             h->steps, h->cfg.t0, h->wg_ws, dp_dev, st, &h->launches, a6 ? P.rec_init : -1);
         if (rc != 0) return set_err(h, RNDE_ERR_CUDA, std::string("wgrad (tcgen05) launch: ") + cudaGetErrorString((cudaError_t)rc));
         return RNDE_OK;
     }
@@ -769,6 +841,13 @@ extern "C" int rnde_allreduce_grads(rnde_handle* h, float* buf_dev, int64_t n, v
     ar_sum_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(A, buf_dev);
     CUDA_TRY(h, cudaGetLastError());
     h->launches += 2;
+    return RNDE_OK;
+}
+
+extern "C" int rnde_set_detach(rnde_handle* h, int32_t mode) {
+    if (!h || mode < RNDE_DETACH_ALL || mode > RNDE_DETACH_FIRST_TERM_ONLY) return RNDE_ERR_ARG;
+    h->detach = mode;
+    h->have_tape = false;      // the forward tapes the initial-dt evaluation only in the all_but_first mode
     return RNDE_OK;
 }
 

@@ -293,7 +293,7 @@ class TrackedNeuralODE:
                  reltol: float = 1.4e-8, abstol: float = 1.4e-8, save_everystep: bool = False, save_start: bool = False,
                  saveat=None, maxiters: int = 0, tape_capacity: int = 256, kernel_variant: int = L.KERNEL_AUTO,
                  kblock: int = 0, device: str = "cuda", dist_mode: int = L.DIST_SINGLE, rank: int = 0, world: int = 1,
-                 arith: Optional[int] = None):
+                 arith: Optional[int] = None, detach_dt: str = "all_but_first"):
         if save_everystep:
             raise NotImplementedError("save_everystep=true has no call site in the reference; use saveat")
         # return_multiple = haskey(kwargs, :saveat)  (neural_ode.jl:11): fixes which functor the object dispatches to
@@ -319,6 +319,12 @@ class TrackedNeuralODE:
         # MMAs) or ARITH_SPLITK (the 8x8-tile FFMA2 stepper of the cluster-4 variant).  None = SPLITK where that stepper
         # applies (MNIST-shaped 2-layer fields on the AUTO / cluster-4 variants without saveat), FMA_CHAIN elsewhere.
         self.arith = resolve_arith(model, kernel_variant, self.return_multiple) if arith is None else int(arith)
+        # what the backward differentiates (utils.jl:21-23 makes tspan tracked): "all_but_first" = the
+        # frozen-step discrete adjoint plus the gradient through the first step size (initial-dt heuristic), the recalled
+        # upstream behaviour; "all" = the frozen-step adjoint only
+        if detach_dt not in ("all", "all_but_first", "first_term_only"):      # the last one is a test diagnostic: only the extra term
+            raise ValueError('detach_dt must be "all" or "all_but_first"')
+        self.detach_dt = detach_dt
         self._handles: dict = {}
         self.last_stats: Optional[L.Stats] = None
 
@@ -353,6 +359,7 @@ class TrackedNeuralODE:
             cfg.arith = self.arith
             cfg.global_batch = B * (self.world if self.dist_mode == L.DIST_EXACT else 1)
             hd = _Handle(cfg)
+            hd.check(hd.lib.rnde_set_detach(hd.h, {"all": L.DETACH_ALL, "all_but_first": L.DETACH_ALL_BUT_FIRST, "first_term_only": L.DETACH_FIRST_TERM_ONLY}[self.detach_dt]), "rnde_set_detach")
             if self.dist_mode == L.DIST_EXACT and self.world > 1:
                 from .parallel import exchange_ipc_handles
                 mine = (C.c_ubyte * 64)()

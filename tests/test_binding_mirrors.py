@@ -76,7 +76,8 @@ def test_enum_values_agree():
                   ("REG_STIFF_DT_ABS", "RNDE_REG_STIFF_DT_ABS"), ("REG_STIFF_SCALED", "RNDE_REG_STIFF_SCALED"),
                   ("REG_ERR_PLUS_STIFF", "RNDE_REG_ERR_PLUS_STIFF"), ("KERNEL_AUTO", "RNDE_KERNEL_AUTO"), ("KERNEL_CHAIN", "RNDE_KERNEL_CHAIN"),
                   ("DIST_SINGLE", "RNDE_DIST_SINGLE"), ("DIST_EXACT", "RNDE_DIST_EXACT"), ("DIST_INDEPENDENT", "RNDE_DIST_INDEPENDENT"),
-                  ("ARITH_FMA_CHAIN", "RNDE_ARITH_FMA_CHAIN"), ("ARITH_FIXED24", "RNDE_ARITH_FIXED24"), ("ARITH_SPLITK", "RNDE_ARITH_SPLITK"), ("OK", "RNDE_OK")]:
+                  ("ARITH_FMA_CHAIN", "RNDE_ARITH_FMA_CHAIN"), ("ARITH_FIXED24", "RNDE_ARITH_FIXED24"), ("ARITH_SPLITK", "RNDE_ARITH_SPLITK"), ("OK", "RNDE_OK"),
+                  ("DETACH_ALL", "RNDE_DETACH_ALL"), ("DETACH_ALL_BUT_FIRST", "RNDE_DETACH_ALL_BUT_FIRST")]:
         assert c in enums, c
         assert getattr(L, py) == int(enums[c]), (py, c)
     for name, val in re.findall(r"const (\w+)\s*=\s*Int32\((\d+)\)", JULIA):

@@ -212,7 +212,7 @@ def test_c_adjoint_matches_autograd(extra, regf):
     o = _c_oracle(D, H, B, extra, e.numpy(), True, reg_kind=orc.REG_ERR_DT if regf else orc.REG_NONE, abstol=1.4e-8, reltol=1.4e-8)
     c = o.forward(np.concatenate([x.numpy(), np.zeros((extra, B))], 0), p.numpy())
     assert (c.nf, c.naccept) == (r.nfe, r.sol.naccept)
-    dp, dx, _, _ = o.backward(w, ws)
+    dp, dx, _, _ = o.backward(w, ws, first_dt_tracked=False)      # oracle/ffjord_oracle.py solves with detach = all
     rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()
     # the regulariser's cotangents are O(1/tol): its gradient carries the 1e-16/1.4e-8 noise of EEst (see the solve test)
     tol = 1e-6 if regf else 1e-12         # observed 2.6e-8 / 5e-14
@@ -222,6 +222,6 @@ def test_c_adjoint_matches_autograd(extra, regf):
         # Float32 build: canonical forward, cotangents in Float64 over it (the yardstick GPU adjoints are judged by) and in Float32
         o32 = _c_oracle(D, H, B, extra, e.numpy().astype(np.float32), False, abstol=1.4e-8, reltol=1.4e-8)
         o32.forward(np.concatenate([x.numpy(), np.zeros((extra, B))], 0).astype(np.float32), p.numpy().astype(np.float32))
-        dp_hi, dx_hi, _, _ = o32.backward(w.astype(np.float32), ws.astype(np.float32), hi=True)
-        dp_32, _, _, _ = o32.backward(w.astype(np.float32), ws.astype(np.float32))
+        dp_hi, dx_hi, _, _ = o32.backward(w.astype(np.float32), ws.astype(np.float32), hi=True, first_dt_tracked=False)
+        dp_32, _, _, _ = o32.backward(w.astype(np.float32), ws.astype(np.float32), first_dt_tracked=False)
         assert rel(dp_hi, gp.numpy()) <= 1e-4 and rel(dx_hi[:D], gx.numpy()) <= 1e-4 and rel(dp_32, dp_hi) <= 1e-4

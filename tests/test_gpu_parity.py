@@ -649,3 +649,53 @@ def test_exact_data_parallel_matches_single_solve(oracle_built):
     assert np.array_equal(bits(usave), bits(refc.usave)), "chain field + saveat in exact mode not bit-identical"
     assert np.array_equal(bits(outs[0][5]), bits(refc.saveval))
     assert outs[0][7] and outs[1][7], "rnde_allreduce_grads differs from the NCCL all-reduce"
+
+
+A6_CASES = [
+    # name, D, H, B, act_out, auto, func, variant
+    ("test_node errreg", 2, 10, 5, 0, False, "ERROR_ESTIMATE", 0),
+    ("test_node stiffreg", 2, 10, 5, 0, True, "STIFFNESS_ESTIMATE", 0),
+    ("toy B=33 streamed weights", 2, 10, 33, 0, False, "ERROR_ESTIMATE", 2),
+    ("mid combined", 20, 50, 100, 1, True, "ERROR_PLUS_STIFFNESS", 0),
+    ("mnist B=32 cluster8", 784, 100, 32, 1, False, "ERROR_ESTIMATE", 3),
+    ("mnist B=48 cluster4 (split-K stepper, tensor-core sweep)", 784, 100, 48, 1, True, "ERROR_PLUS_STIFFNESS", 4),
+    ("mnist B=512 (auto variant)", 784, 100, 512, 1, False, "ERROR_ESTIMATE", 0),
+    ("D=200 H=37 cluster4 (FFMA sweep)", 200, 37, 33, 0, True, "STIFFNESS_ESTIMATE", 4),
+]
+
+
+@pytest.mark.parametrize("name,D,H,B,act_out,auto,func,variant", A6_CASES, ids=[c[0] for c in A6_CASES])
+def test_first_dt_gradient_term(oracle_built, name, D, H, B, act_out, auto, func, variant):
+    """`_convert_tspan` (utils.jl:21-23) makes tspan tracked, so the first step size
+    (initial-dt heuristic) stays on the tape.  The extra term -- gradient with detach_dt = "all_but_first" minus the
+    frozen-step gradient -- is 1e-7 ... 1e-3 of the gradient, below the Float32 noise of the regulariser part, so it is
+    checked on its own: the library's diagnostic mode returns the term alone, and so does the oracle (Float64 cotangents
+    over the Float32 forward).  The term is dL/d(dt_1) * d(dt_1)/d(theta, x); dL/d(dt_1) is a sum of the same cancelling
+    cotangents as the regulariser gradient, so the bar is the one of the gradient tests: <= 1e-3, or 1.5x the CPU Float32
+    adjoint's own error on the term."""
+    r = R()
+    rng = np.random.default_rng(11)
+    p_np = orc.glorot_params(rng, D, H)
+    x_np = rng.random((D, B), dtype=np.float32)
+    fobj = getattr(r, func)
+    model = r.TDChain(r.Dense(D + 1, H, "tanh"), r.Dense(H + 1, D, "tanh" if act_out else None))
+    node = r.TrackedNeuralODE(model, [0.0, 1.0], True, True, r.AutoTsit5() if auto else r.Tsit5(), reltol=1.4e-8, abstol=1.4e-8,
+                              kernel_variant=variant, detach_dt="first_term_only")
+    p = torch.from_numpy(p_np).cuda().requires_grad_(True)
+    x = torch.from_numpy(x_np).cuda().requires_grad_(True)
+    res, nfe, sv = node(x, p, func=fobj)
+    o = orc.Oracle(oracle_cfg(D, H, B, act_out, 1 if auto else 0, fobj.kind, arith=node.arith))
+    ref = o.forward(x_np, p_np)
+    w = rng.standard_normal((D, B)).astype(np.float32)
+    ws = rng.standard_normal(len(ref.saveval)).astype(np.float32)
+    assert np.array_equal(bits(res.detach().cpu().numpy()), bits(ref.u))
+    ((res * torch.from_numpy(w).cuda()).sum() + (sv.saveval * torch.from_numpy(ws).cuda()).sum()).backward()
+    torch.cuda.synchronize()
+    tp, tx, _, _ = o.backward(w, ws, hi=True, first_dt_tracked="term")
+    cp, cx, _, _ = o.backward(w, ws, first_dt_tracked="term")
+    full, _, _, _ = o.backward(w, ws, hi=True)
+    assert np.abs(tp).max() > 0 and np.abs(tx).max() > 0
+    rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()
+    e_p, e_x, c_p, c_x = rel(p.grad.cpu().numpy(), tp), rel(x.grad.cpu().numpy(), tx), rel(cp, tp), rel(cx, tx)
+    note = (e_p, e_x, c_p, c_x, np.abs(tp).max() / np.abs(full).max())
+    assert e_p <= max(1e-3, GRAD_BAR * c_p) and e_x <= max(1e-3, GRAD_BAR * c_x), note

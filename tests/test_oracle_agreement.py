@@ -20,8 +20,11 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("detach", ["all", "all_but_first"])
 @pytest.mark.parametrize("D,H,B,act2,alg,reg,kb", CASES)
-def test_c_oracle_matches_autograd_fp64(oracle_built, D, H, B, act2, alg, reg, kb):
+def test_c_oracle_matches_autograd_fp64(oracle_built, D, H, B, act2, alg, reg, kb, detach):
+    """detach: SURVEY.md Appendix A.6 -- "all" = every dt frozen; "all_but_first" = the initial-dt heuristic stays on the
+    tape (utils.jl:21-23 makes tspan tracked; the recalled upstream behaviour and the default of both oracles' callers)."""
     torch.set_default_dtype(torch.float64)
     try:
         rng = np.random.default_rng(7 + D + 10 * reg)
@@ -32,7 +35,7 @@ def test_c_oracle_matches_autograd_fp64(oracle_built, D, H, B, act2, alg, reg, k
         r = o.forward(x, p)
         pt = torch.tensor(p, requires_grad=True)
         xt = torch.tensor(x, requires_grad=True)
-        tr = to.solve(xt, pt, D=D, H=H, act2_tanh=(act2 == 1), auto_tsit5=(alg == 1), reg_kind=reg, detach="all")
+        tr = to.solve(xt, pt, D=D, H=H, act2_tanh=(act2 == 1), auto_tsit5=(alg == 1), reg_kind=reg, detach=detach)
         # identical step sequence / NFE accounting (nf = 3 + 6*(naccept+nreject))
         assert (r.nf, r.naccept, r.nreject) == (tr.nf, tr.naccept, tr.nreject)
         assert r.nf == 3 + 6 * (r.naccept + r.nreject)
@@ -48,9 +51,11 @@ def test_c_oracle_matches_autograd_fp64(oracle_built, D, H, B, act2, alg, reg, k
         if reg:
             loss = loss + (sv_t * torch.tensor(ws[: len(r.saveval)])).sum()
         gp, gx = torch.autograd.grad(loss, [pt, xt])
-        dp, dx, dtb, tb = o.backward(w, ws)
+        dp, dx, dtb, tb = o.backward(w, ws, first_dt_tracked=(detach == "all_but_first"))
         assert np.abs(dp - gp.numpy()).max() <= 1e-6 * np.abs(gp.numpy()).max()
         assert np.abs(dx - gx.numpy()).max() <= 1e-6 * np.abs(gx.numpy()).max()
+        if detach != "all":
+            return
         # scalar adjoints w.r.t. every accepted dt (direct + time-shift paths) via replay with leaf dts
         dts = torch.tensor(r.dt_log, requires_grad=True)
         tr2 = to.solve(xt, pt, D=D, H=H, act2_tanh=(act2 == 1), auto_tsit5=(alg == 1), reg_kind=reg, detach="all",
@@ -79,8 +84,9 @@ def test_first_saved_value_conventions(oracle_built):
     assert first[orc.REG_ERR_PLUS_STIFF] == np.float32(0.1) * stab
 
 
+@pytest.mark.parametrize("detach", ["all", "all_but_first"])
 @pytest.mark.parametrize("reg,alg", [(orc.REG_NONE, 0), (orc.REG_ERR_DT, 0), (orc.REG_ERR_PLUS_STIFF, 1)])
-def test_saveat_dense_output_matches_autograd_fp64(oracle_built, reg, alg):
+def test_saveat_dense_output_matches_autograd_fp64(oracle_built, reg, alg, detach):
     """Multi-save functors (neural_ode.jl:79-108,146-180): the C oracle's saved states (Tsit5 free interpolant,
     SURVEY.md Appendix A.9) and their adjoint against torch autograd in FP64; saveat must not change the steps."""
     torch.set_default_dtype(torch.float64)
@@ -96,7 +102,7 @@ def test_saveat_dense_output_matches_autograd_fp64(oracle_built, reg, alg):
     assert (r.nf, r.naccept, r.nreject) == (plain.nf, plain.naccept, plain.nreject)      # no tstops added
     assert np.array_equal(r.usave[0], x) and np.array_equal(r.usave[-1], plain.u)          # t0 -> input, t1 -> copy of u
     pt = torch.tensor(p, requires_grad=True); xt = torch.tensor(x, requires_grad=True)
-    tr = to.solve(xt, pt, D=D, H=H, reg_kind=reg, auto_tsit5=bool(alg), saveat=sa)
+    tr = to.solve(xt, pt, D=D, H=H, reg_kind=reg, auto_tsit5=bool(alg), saveat=sa, detach=detach)
     us = torch.stack(tr.usave)
     assert np.abs(r.usave - us.detach().numpy()).max() < 1e-12
     w = rng.standard_normal(r.usave.shape)
@@ -106,7 +112,7 @@ def test_saveat_dense_output_matches_autograd_fp64(oracle_built, reg, alg):
         ws = rng.standard_normal(len(r.saveval))
         loss = loss + (torch.stack(tr.saveval) * torch.tensor(ws)).sum()
     gp, gx = torch.autograd.grad(loss, [pt, xt])
-    dp, dx, _, _ = o.backward(np.zeros((D, B)), ws, dusave=w)
+    dp, dx, _, _ = o.backward(np.zeros((D, B)), ws, dusave=w, first_dt_tracked=(detach == "all_but_first"))
     assert np.abs(dp - gp.numpy()).max() <= 1e-7 * np.abs(gp.numpy()).max()
     assert np.abs(dx - gx.numpy()).max() <= 1e-7 * np.abs(gx.numpy()).max()
     torch.set_default_dtype(torch.float32)
@@ -119,8 +125,9 @@ def test_free_interpolant_endpoint_identities():
     assert all(v == 0.0 for v in to.interp_weights(0.0))
 
 
+@pytest.mark.parametrize("detach", ["all", "all_but_first"])
 @pytest.mark.parametrize("reg,alg", [(orc.REG_NONE, 0), (orc.REG_ERR_DT, 0), (orc.REG_ERR_PLUS_STIFF, 1)])
-def test_chain_field_matches_autograd_fp64(oracle_built, reg, alg):
+def test_chain_field_matches_autograd_fp64(oracle_built, reg, alg, detach):
     """Chain fields (Latent-ODE generator dynamics, experiments/latent_ode.jl:109-121: tanh pre-activation, Dense
     layers, no time input) with saveat: C oracle against torch autograd in FP64 -- steps, saved states, gradients."""
     torch.set_default_dtype(torch.float64)
@@ -135,7 +142,7 @@ def test_chain_field_matches_autograd_fp64(oracle_built, reg, alg):
     o = orc.Oracle(cfg, f64=True)
     r = o.forward(x, p)
     pt = torch.tensor(p, requires_grad=True); xt = torch.tensor(x, requires_grad=True)
-    tr = to.solve(xt, pt, D=D, H=11, reg_kind=reg, auto_tsit5=bool(alg), saveat=sa, chain=(widths, acts, 1))
+    tr = to.solve(xt, pt, D=D, H=11, reg_kind=reg, auto_tsit5=bool(alg), saveat=sa, chain=(widths, acts, 1), detach=detach)
     assert (r.nf, r.naccept) == (tr.nf, tr.naccept)
     us = torch.stack(tr.usave)
     assert np.abs(r.usave - us.detach().numpy()).max() < 1e-12
@@ -146,7 +153,7 @@ def test_chain_field_matches_autograd_fp64(oracle_built, reg, alg):
         ws = rng.standard_normal(len(r.saveval))
         loss = loss + (torch.stack(tr.saveval) * torch.tensor(ws)).sum()
     gp, gx = torch.autograd.grad(loss, [pt, xt])
-    dp, dx, _, _ = o.backward(np.zeros((D, B)), ws, dusave=w)
+    dp, dx, _, _ = o.backward(np.zeros((D, B)), ws, dusave=w, first_dt_tracked=(detach == "all_but_first"))
     assert np.abs(dp - gp.numpy()).max() <= 1e-7 * np.abs(gp.numpy()).max()
     assert np.abs(dx - gx.numpy()).max() <= 1e-7 * np.abs(gx.numpy()).max()
     torch.set_default_dtype(torch.float32)
