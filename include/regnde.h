@@ -337,6 +337,8 @@ int rnde_test_unary_bits(int32_t fn, uint32_t first_bits, int64_t n, float* y_de
 int rnde_test_csq_rhs(int32_t data_dim, int32_t hidden, int32_t extra, int32_t batch, const float* p_dev, const float* z_dev,
                       const float* e_dev, float t, float* k_dev, void* stream);
 int rnde_debug_timeline(rnde_handle* h, long long* out, int n);
+/* developer diagnostic of the first-dt adjoint (rnde_set_detach): the two reduced sums of its separate-launch path */
+int rnde_debug_a6(rnde_handle* h, float* out2);
 
 #ifdef __cplusplus
 }

@@ -39,7 +39,7 @@ EXPORTS = [
     "rnde_version", "rnde_status_string", "rnde_device_count", "rnde_create", "rnde_destroy", "rnde_last_error",
     "rnde_num_params", "rnde_default_kblock", "rnde_kernel_variant", "rnde_launch_count", "rnde_set_tspan", "rnde_set_forced_steps", "rnde_set_detach",
     "rnde_forward", "rnde_backward", "rnde_forward_host", "rnde_backward_host", "rnde_head_loss_grad", "rnde_get_steps",
-    "rnde_opt_update", "rnde_test_tanh", "rnde_test_tanh_bits", "rnde_test_pow", "rnde_test_unary_bits", "rnde_test_csq_rhs", "rnde_debug_timeline", "rnde_dist_export", "rnde_dist_import",
+    "rnde_opt_update", "rnde_test_tanh", "rnde_test_tanh_bits", "rnde_test_pow", "rnde_test_unary_bits", "rnde_test_csq_rhs", "rnde_debug_timeline", "rnde_debug_a6", "rnde_dist_export", "rnde_dist_import",
     "rnde_set_saveat", "rnde_forward_saveat", "rnde_backward_saveat", "rnde_set_noise",
     "rnde_gru_num_params", "rnde_gru_create", "rnde_gru_destroy", "rnde_gru_last_error", "rnde_gru_forward", "rnde_gru_backward",
     "rnde_gru_launch_count", "rnde_reg_agg", "rnde_last_stats", "rnde_allreduce_grads",
@@ -166,6 +166,7 @@ def lib() -> C.CDLL:
     L.rnde_test_unary_bits.argtypes = [C.c_int32, C.c_uint32, C.c_int64, vp, vp]
     L.rnde_test_csq_rhs.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, C.c_float, vp, vp]
     L.rnde_debug_timeline.argtypes = [vp, vp, C.c_int]
+    L.rnde_debug_a6.argtypes = [vp, fp]
     L.rnde_dist_export.argtypes = [vp, vp]
     L.rnde_dist_import.argtypes = [vp, vp, C.c_int32]
     L.rnde_set_saveat.argtypes = [vp, vp, C.c_int32]

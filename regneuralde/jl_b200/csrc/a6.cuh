@@ -32,11 +32,11 @@ struct A6Scal {
     bool dt0_free;     // dt0 = 0.01 d0/d1 (neither the 1e-6 fallback nor the dtmax clamp)
 };
 
-__device__ inline A6Scal a6_scalars(const KParams& P) {
+__device__ inline A6Scal a6_scalars(const KParams& P, const float dsum) {      // dsum: dL/d(dt_1) summed over all columns
     A6Scal s;
     const float d0 = P.initdt[0], d1 = P.initdt[1], d2 = P.initdt[2], dt0 = P.initdt[3], dt1 = P.initdt[4];
     const float dti = P.stats->dt_init, dtmax = P.t1 - P.t0;
-    s.Dt = P.a6_sum[0] * (P.steps[0].dt / dti);
+    s.Dt = dsum * (P.steps[0].dt / dti);
     s.d2bar = 0.f; s.d1bar = 0.f; s.dt0bar = 0.f;
     float dt1b = 0.f;
     if (dti >= dtmax || dti <= P.dtmin) { }                    // clamped: a constant
@@ -72,6 +72,201 @@ __device__ __forceinline__ void a6_block_sum(double v, float* scratch_f, double*
     }
     __syncthreads();
 }
+
+// Sum of `v` over the whole (co-resident) grid, returned to every thread: per-CTA partials, a grid barrier, then every CTA
+// adds the partials in the same fixed order.  `slot` selects one of the two partial arrays (two sums per launch).
+template <int NT>
+__device__ __forceinline__ double a6_grid_sum(double v, float* scratch_f, const KParams& P, unsigned& bar_gen, int slot) {
+    double* part = P.a6_part + (size_t)slot * gridDim.x;
+    a6_block_sum<NT>(v, scratch_f, part);
+    grid_barrier(P.bar, gridDim.x, bar_gen);
+    double* scratch = reinterpret_cast<double*>(scratch_f);
+    if (threadIdx.x < 32) {
+        double s = 0.0;
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += 32) s += __ldcg(part + b);
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (threadIdx.x == 0) scratch[0] = s;
+    }
+    __syncthreads();
+    const double tot = scratch[0];
+    __syncthreads();
+    return tot;
+}
+
+// Explicit dt of the stage input z_i = u + dt * sum_{j<i} a_ij k_j of one 4x4 tile: sum_e zbar[e] * (sum_j a_ij k_j[e]).
+// Out of line: it runs in two steps of a sweep only, and the sweeps' hot loop has no instruction-cache room to spare.
+// kbase: this thread's tile row 0 in the record of k_1 (stage j lives rstride floats further per stage), 16 columns per row.
+__device__ __noinline__ double a6_direct_term(const float* kbase, size_t rstride, int NPc, int nrows, int i, const float* zc) {
+    double acc = 0.0;
+    for (int ii = 0; ii < nrows; ++ii) {
+        float a4[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int jj = 1; jj < i; ++jj) {
+            const float4 k4 = __ldcg(reinterpret_cast<const float4*>(kbase + (size_t)(jj - 1) * rstride + (size_t)ii * NPc));
+            const float a = ts_a(i, jj);
+            a4[0] = rn_fmaf(a, k4.x, a4[0]); a4[1] = rn_fmaf(a, k4.y, a4[1]); a4[2] = rn_fmaf(a, k4.z, a4[2]); a4[3] = rn_fmaf(a, k4.w, a4[3]);
+        }
+        acc += ((double)zc[ii * 4] * a4[0] + (double)zc[ii * 4 + 1] * a4[1]) + ((double)zc[ii * 4 + 2] * a4[2] + (double)zc[ii * 4 + 3] * a4[3]);
+    }
+    return acc;
+}
+
+// This thread's part of dL/d(dt_1) for the tensor-core sweep, which keeps its hot loop free of it: the sweep only leaves
+//   a6_zb  : the cotangent of every stage input z_i of the first and of the last step ([slot 0-5 | 6-11][tile][row][NP]), and
+//   a6_tau : per record and CTA the time cotangents sum W2[:, t] . delta2 (this CTA's rows) and sum W1[:, t] . delta1, which the
+//            tensor cores produce in one spare accumulator row each;
+// everything else follows from the tape:
+//   a6_kc  : copies of k_1..k_6 of those two steps, taken by the host before the sweep replaces k by delta2 on the tape
+//            ((z_i - u) / dt from the taped stage inputs would do for long steps, but the last step can be 1e-6 long);
+//   explicit dt of z_i = u + dt sum_j a_ij k_j :  <zbar_i, sum_j a_ij k_j>
+//   explicit dt of utilde and of EEst * dt     :  2 sbar EEst        (sum_e utbar utilde / dt = eestbar EEst / dt, closed form)
+//   start time of step s >= 1, stage times     :  weights 1 and c_i on the time cotangents.
+// base_off: offset of this thread's tile row 0 inside a record, rstride: floats per record.  All threads of the CTA call it.
+__device__ __forceinline__ double a6_sweep_partial(const KParams& P, const bool own, const int cvalid, const size_t base_off, const size_t rstride,
+                                                   const int NPc, const int q, const int rank, const int G) {
+    double part = 0.0;
+    const int N = P.nsteps;
+    const float clampN = P.initdt[5];
+#pragma unroll 1
+    for (int f = 0; f < 2; ++f) {
+        const int s = f ? N - 1 : 0;
+        const float w = f ? ((N > 1) ? -clampN : 0.f) : (1.f - (N == 1 ? clampN : 0.f));
+        if (w == 0.f) continue;
+        const StepRec sr = P.steps[s];
+        if (own) {
+#pragma unroll 1
+            for (int ii = 0; ii < cvalid; ++ii) {      // 12 independent loads in flight per row (one at a time would cost ~170 L2 round trips)
+                const size_t o = base_off + (size_t)ii * NPc + (size_t)(f ? 6 : 0) * rstride;
+                float4 k[6], zb[6];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    k[j] = __ldcg(reinterpret_cast<const float4*>(P.a6_kc + o + (size_t)j * rstride));        // k_{j+1}
+                    zb[j] = __ldcg(reinterpret_cast<const float4*>(P.a6_zb + o + (size_t)j * rstride));       // cotangent of z_{j+2}
+                }
+#pragma unroll
+                for (int i = 2; i <= 7; ++i) {
+                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int j = 1; j < i; ++j) {
+                        const float c = ts_a(i, j);
+                        a.x = rn_fmaf(c, k[j - 1].x, a.x); a.y = rn_fmaf(c, k[j - 1].y, a.y); a.z = rn_fmaf(c, k[j - 1].z, a.z); a.w = rn_fmaf(c, k[j - 1].w, a.w);
+                    }
+                    const float4 z = zb[i - 2];
+                    part += (double)w * (((double)z.x * a.x + (double)z.y * a.y) + ((double)z.z * a.z + (double)z.w * a.w));
+                }
+            }
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0 && P.dsaveval) {
+            const float sbar = __ldg(P.dsaveval + s + 1);
+            if (P.reg_kind == RNDE_REG_ERR_DT) part += (double)(2.f * w * sbar * sr.eest);
+            else if (P.reg_kind == RNDE_REG_STIFF_DT_ABS && P.alg == RNDE_ALG_AUTO_TSIT5) part += (double)(w * sbar * ((sr.eig * sr.dt) >= 0.f ? 1.f : -1.f) * sr.eig);
+            else if (P.reg_kind == RNDE_REG_ERR_PLUS_STIFF) { const float e = sr.eest * sr.dt; if (!(e == 0.f || e != e)) part += (double)(2.f * w * sbar * sr.eest); }
+        }
+    }
+    if (P.td) {
+#pragma unroll 1
+        for (int rec = 1 + (int)threadIdx.x; rec <= 6 * N; rec += (int)blockDim.x) {
+            const int s = (rec - 1) / 6, i = (rec - 1) % 6 + 2;
+            const float wdir = (s == 0 ? 1.f : 0.f) - (s == N - 1 ? clampN : 0.f);
+            const float wt = (s >= 1 ? 1.f : 0.f) + wdir * ts_c(i);
+            const float* tp = P.a6_tau + (((size_t)rec * P.Q + q) * G + rank) * 2;
+            part += (double)(wt * (__ldcg(tp) + (rank == 0 ? __ldcg(tp + 1) : 0.f)));
+        }
+    }
+    return part;
+}
+
+// The adjoint of the initial-dt heuristic inside the cluster-4 sweeps (bwd4_kernel.cuh, bwd4tc_kernel.cuh): one more task of
+// the sweep's loop, between the first step and record 0 -- the VJP of the evaluation f1 (record P.rec_x) between two
+// grid-wide sums; the cotangents of f0 and u0 then simply join kbar of record 0 and ubar.  PRE builds the cotangent of f1
+// (into CUR) before the loop's single vjp call, POST consumes its result ZB.  Nothing stays in registers across the vjp:
+// the few scalars wait in shared memory (SA6, 16 floats).  PARTIAL: this thread's part of dL/d(dt_1) (double); TAUX: the time
+// cotangent of the evaluation summed over this CTA's threads by whoever holds it (double, other threads 0).
+// Uses the kernels' locals: own, cvalid, cn0, Nloc, offD, tileD, kb, ubar, atol, rtol, cntf, tid, NT.
+#define RNDE_A6_TASK_PRE(SA6, CUR, SCR, PARTIAL)                                                                                       \
+    do {                                                                                                                               \
+        unsigned a6_gen = 0;                                                                                                           \
+        const double a6_tot = a6_grid_sum<NT>((PARTIAL), SCR, P, a6_gen, 0);                                                           \
+        const A6Scal a6_sc = a6_scalars(P, (float)a6_tot);                                                                             \
+        if (tid == 0) { SA6[0] = a6_sc.d2bar; SA6[1] = a6_sc.d1bar; SA6[2] = a6_sc.dt0bar; SA6[3] = a6_sc.dt0_free ? 1.f : 0.f; }      \
+        const float a6_d2 = P.initdt[2], a6_dt0 = P.initdt[3];                                                                         \
+        const float a6_r2 = a6_d2 * a6_dt0;                                                                                            \
+        const float a6_coef = (a6_sc.d2bar != 0.f && a6_r2 > 0.f) ? (a6_sc.d2bar / a6_dt0) / (cntf * a6_r2) : 0.f;                      \
+        const size_t a6_bstr = (size_t)P.Q * tileD;                                                                                    \
+        _Pragma("unroll") for (int e = 0; e < 16; ++e) CUR[e] = 0.f;                                                                   \
+        if (own) {                                                                                                                     \
+            _Pragma("unroll") for (int ii = 0; ii < 4; ++ii) {                                                                         \
+                if (ii < cvalid) {                                                                                                     \
+                    const float4 u4 = __ldcg(reinterpret_cast<const float4*>(P.tapeZ + offD(0, ii)));                                  \
+                    const float4 f4 = __ldcg(reinterpret_cast<const float4*>(P.tapeK + offD(0, ii)));                                  \
+                    const float4 g4 = __ldcg(reinterpret_cast<const float4*>(P.tapeK + offD(P.rec_x, ii)));                            \
+                    const float uv[4] = {u4.x, u4.y, u4.z, u4.w}, fv[4] = {f4.x, f4.y, f4.z, f4.w}, gv[4] = {g4.x, g4.y, g4.z, g4.w};  \
+                    float fb[4], wwb[4];                                                                                               \
+                    _Pragma("unroll") for (int jj = 0; jj < 4; ++jj) {                                                                 \
+                        const float rsk = __fdividef(1.f, rn_fmaf(fabsf(uv[jj]), rtol, atol));                                         \
+                        const float wv = (gv[jj] - fv[jj]) * rsk;                                                                      \
+                        const float wb = (cn0 + jj < Nloc) ? a6_coef * wv : 0.f;                                                       \
+                        fb[jj] = wb * rsk; wwb[jj] = wb * wv * rsk;                                                                    \
+                        CUR[ii * 4 + jj] = fb[jj];                                                                                     \
+                    }                                                                                                                  \
+                    *reinterpret_cast<float4*>(P.a6_u1bar + a6_bstr + offD(0, ii)) = make_float4(fb[0], fb[1], fb[2], fb[3]);          \
+                    *reinterpret_cast<float4*>(P.a6_u1bar + 2 * a6_bstr + offD(0, ii)) = make_float4(wwb[0], wwb[1], wwb[2], wwb[3]);  \
+                }                                                                                                                      \
+            }                                                                                                                          \
+        }                                                                                                                              \
+        __syncthreads();                                                                                                               \
+    } while (0)
+
+#define RNDE_A6_TASK_POST(SA6, ZB, SCR, TAUX)                                                                                          \
+    do {      /* ZB = cotangent of u1 = u0 + dt0 f0 */                                                                                 \
+        const float a6_d0 = P.initdt[0], a6_d1 = P.initdt[1], a6_dt0 = P.initdt[3];                                                    \
+        const size_t a6_bstr = (size_t)P.Q * tileD;                                                                                    \
+        double a6_part = (TAUX);                                                                                                       \
+        if (own) {                                                                                                                     \
+            _Pragma("unroll") for (int ii = 0; ii < 4; ++ii) {                                                                         \
+                if (ii < cvalid) {                                                                                                     \
+                    const float4 f4 = __ldcg(reinterpret_cast<const float4*>(P.tapeK + offD(0, ii)));                                  \
+                    a6_part += (double)((ZB[ii * 4] * f4.x + ZB[ii * 4 + 1] * f4.y) + (ZB[ii * 4 + 2] * f4.z + ZB[ii * 4 + 3] * f4.w)); \
+                }                                                                                                                      \
+            }                                                                                                                          \
+        }                                                                                                                              \
+        if (blockIdx.x == 0 && tid == 0) {      /* pseudo-step whose stage 7 (time t + dt) is that evaluation: the wgrad time row */   \
+            StepRec sr; sr.t = P.t0; sr.dt = a6_dt0; sr.eest = 0.f; sr.eig = 0.f; sr.n1 = 0.f; sr.n2 = 0.f; sr.pad0 = 0.f; sr.pad1 = 0.f; \
+            P.steps[P.nsteps] = sr;                                                                                                    \
+        }                                                                                                                              \
+        unsigned a6_gen = 1;                                                                                                           \
+        const double a6_tot2 = a6_grid_sum<NT>(a6_part, SCR, P, a6_gen, 1);                                                            \
+        float a6_dt0bar = SA6[2] + (float)a6_tot2, a6_d0bar = 0.f, a6_d1bar = SA6[1];                                                  \
+        if (SA6[3] != 0.f) { a6_d0bar = a6_dt0bar * a6_dt0 / a6_d0; a6_d1bar -= a6_dt0bar * a6_dt0 / a6_d1; }                           \
+        const float a6_c1 = (a6_d1bar != 0.f && a6_d1 > 0.f) ? a6_d1bar / (cntf * a6_d1) : 0.f;                                         \
+        const float a6_c0 = (a6_d0bar != 0.f && a6_d0 > 0.f) ? a6_d0bar / (cntf * a6_d0) : 0.f;                                         \
+        if (P.a6 == 3) {      /* diagnostic (RNDE_DETACH_FIRST_TERM_ONLY): drop what the sweep accumulated */                           \
+            _Pragma("unroll") for (int e = 0; e < 16; ++e) { kb[6][e] = 0.f; ubar[e] = 0.f; }                                          \
+        }                                                                                                                              \
+        if (own) {                                                                                                                     \
+            _Pragma("unroll") for (int ii = 0; ii < 4; ++ii) {                                                                         \
+                if (ii < cvalid) {                                                                                                     \
+                    const float4 u4 = __ldcg(reinterpret_cast<const float4*>(P.tapeZ + offD(0, ii)));                                  \
+                    const float4 f4 = __ldcg(reinterpret_cast<const float4*>(P.tapeK + offD(0, ii)));                                  \
+                    const float4 b4 = *reinterpret_cast<const float4*>(P.a6_u1bar + a6_bstr + offD(0, ii));                            \
+                    const float4 w4 = *reinterpret_cast<const float4*>(P.a6_u1bar + 2 * a6_bstr + offD(0, ii));                        \
+                    const float uv[4] = {u4.x, u4.y, u4.z, u4.w}, fv[4] = {f4.x, f4.y, f4.z, f4.w};                                    \
+                    const float bv[4] = {b4.x, b4.y, b4.z, b4.w}, wv4[4] = {w4.x, w4.y, w4.z, w4.w};                                   \
+                    _Pragma("unroll") for (int jj = 0; jj < 4; ++jj) {                                                                 \
+                        if (cn0 + jj < Nloc) {                                                                                         \
+                            const int e = ii * 4 + jj;                                                                                 \
+                            const float rsk = __fdividef(1.f, rn_fmaf(fabsf(uv[jj]), rtol, atol));                                     \
+                            const float v = fv[jj] * rsk, y = uv[jj] * rsk;                                                            \
+                            const float vb = a6_c1 * v, yb = a6_c0 * y;                                                                \
+                            const float skbar = -wv4[jj] - (vb * v + yb * y) * rsk;                                                    \
+                            kb[6][e] += rn_fmaf(a6_dt0, ZB[e], vb * rsk - bv[jj]);                                                     \
+                            ubar[e] += ZB[e] + yb * rsk + skbar * rtol * (uv[jj] > 0.f ? 1.f : (uv[jj] < 0.f ? -1.f : 0.f));           \
+                        }                                                                                                              \
+                    }                                                                                                                  \
+                }                                                                                                                      \
+            }                                                                                                                          \
+        }                                                                                                                              \
+    } while (0)
 
 // fixed-order sum of the per-CTA partials (in Float64) -> dst[slot]; one block
 __global__ void a6_reduce_kernel(const double* __restrict__ part, int n, float* __restrict__ dst, int slot) {

@@ -18,7 +18,7 @@ namespace rnde {
 
 struct B4Layout {
     int KB, KBP, R, RPAD, HP, HS, NGC, NGH;
-    int oW2T, oW1T, oD2, oP1, oPart, oD1, oBar, total;
+    int oW2T, oW1T, oD2, oP1, oPart, oD1, oBar, oWt, total;
 };
 
 __host__ __device__ inline B4Layout make_b4_layout(int D, int H) {
@@ -39,6 +39,7 @@ __host__ __device__ inline B4Layout make_b4_layout(int D, int H) {
     L.oPart = o; o += V2_G * L.HS * V2_NP;
     L.oD1 = o; o += L.HP * V2_NP;
     L.oBar = o; o += 8;
+    L.oWt = o; o += round_up(L.R + L.HS, 4) + 16;      // time columns of W2 / W1 and 16 floats of scratch (a6.cuh)
     L.total = o;
     return L;
 }
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4_kernel(const KParams P) {
     const int HSloc = max(0, min(HS, H - rank * HS));
     float* sW2T = smem + L.oW2T; float* sW1T = smem + L.oW1T;
     float* sD2 = smem + L.oD2; float* sP1 = smem + L.oP1; float* sPart = smem + L.oPart; float* sD1 = smem + L.oD1;
+    float* sWt = smem + L.oWt;
     const uint32_t barP = smem_u32(smem + L.oBar), barH = barP + 8;
     const float* gW1 = P.p;
     const float* gW2 = gW1 + (size_t)H * (D + td) + H;
@@ -129,12 +131,16 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4_kernel(const KParams P) {
     // Appendix A.6 (a6.cuh): this thread's part of dL/d(dt_1), and the time columns of W2 / W1 for the rows / hidden unit it owns
     double dacc = 0.0;
     float wdir = 0.f, wshift = 0.f;
-    const float* const w2t = gW2 + (size_t)D * H + r0 + crow0;      // read where needed (L1 resident): no registers held across the sweep
-    const float* const w1tp = gW1 + (size_t)H * D + rank * HS + (tid >> 2);
+    // time columns of W2 (this CTA's rows) and W1 (its hidden slice) in shared memory: read once per record without a trip to L2
+    if (P.a6 && td) {
+        for (int e = tid; e < R; e += NT) sWt[e] = __ldg(gW2 + (size_t)D * H + r0 + e);
+        for (int e = tid; e < HS; e += NT) sWt[R + e] = (rank * HS + e < H) ? __ldg(gW1 + (size_t)H * D + rank * HS + e) : 0.f;
+        __syncthreads();
+    }
 
     // VJP of record `rec`: cur = kbar of that evaluation (in), zb = W1^T delta1 for the tile (out)
     auto vjp = [&](const float (&cur)[16], float (&zb)[16], const int rec, const int rec_next, const float wt) {
-        const bool want_t = (wt != 0.f) && td;
+        const bool want_t = (wt != 0.f) && td && P.a6;
         if (tid == 0) { mbar_expect_tx(barP, bytesP); mbar_expect_tx(barH, bytesH); }
         // the tape is HBM resident (0.75 GB): pull the NEXT record's k / h tiles towards L2 while this record is processed
         if (rec_next >= 0) {
@@ -147,6 +153,7 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4_kernel(const KParams P) {
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(P.tapeH + ((size_t)rec_next * P.Q + q) * tileH + (size_t)(rank * HS + (tid >> 2)) * NP + (tid & 3) * 4));
         }
         if (own) {
+            float tsum = 0.f;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 if (i < cvalid) {
@@ -159,9 +166,10 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4_kernel(const KParams P) {
                     }
                     *reinterpret_cast<float4*>(sD2 + (crow0 + i) * NP + cn0) = d2;
                     *reinterpret_cast<float4*>(tp) = d2;      // delta2 replaces k in the tape (wgrad operand)
-                    if (want_t && i < cvalid) dacc += (double)(wt * __ldg(w2t + i) * ((d2.x + d2.y) + (d2.z + d2.w)));
+                    if (want_t) tsum = rn_fmaf(sWt[crow0 + i], (d2.x + d2.y) + (d2.z + d2.w), tsum);
                 }
             }
+            if (want_t) dacc += (double)(wt * tsum);
         }
         __syncthreads();
         float acc[16];
@@ -220,7 +228,7 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4_kernel(const KParams P) {
                 const float4 hv = __ldcg(reinterpret_cast<const float4*>(P.tapeH + oh));
                 s.x *= (1.f - hv.x * hv.x); s.y *= (1.f - hv.y * hv.y); s.z *= (1.f - hv.z * hv.z); s.w *= (1.f - hv.w * hv.w);
             }
-            if (want_t) dacc += (double)(wt * __ldg(w1tp) * ((s.x + s.y) + (s.z + s.w)));
+            if (want_t) dacc += (double)(wt * sWt[R + (tid >> 2)] * ((s.x + s.y) + (s.z + s.w)));
             float* dst = sD1 + m * NP + n4;
             *reinterpret_cast<float4*>(dst) = s;
             const uint32_t da = smem_u32(dst);
@@ -260,16 +268,21 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4_kernel(const KParams P) {
     const float stab = rn_divf(1.0f, (float)TS_STABILITY_SIZE);
 
     // task list, newest evaluation first: for s = nsteps-1..0: stages 7..2; then the initial record 0
-    const int ntask = 6 * P.nsteps + 1;
+    // (+ with P.a6 >= 2 one task before the last: the evaluation of the initial-dt heuristic, a6.cuh)
+    const int na6 = (P.a6 >= 2) ? 1 : 0;
+    const int ntask = 6 * P.nsteps + 1 + na6;
+    float* sA6 = sWt + round_up(R + HS, 4);      // scalars of the a6 task wait here (the layout reserves 16 floats behind the time columns)
     float dt = 0.f, gB = 0.f;
     bool use_eig = false;
     int recU1 = 0, recG6 = 0;
     for (int task = 0; task < ntask; ++task) {
         const bool last = (task == ntask - 1);
-        const int s = last ? 0 : P.nsteps - 1 - task / 6;
-        const int i = last ? 7 : 7 - task % 6;
-        const int rec = last ? 0 : 6 * s + i - 1;
-        if (!last && i == 7) {
+        const bool a6task = na6 && (task == ntask - 2);
+        const bool tail = last || a6task;
+        const int s = tail ? 0 : P.nsteps - 1 - task / 6;
+        const int i = tail ? 7 : 7 - task % 6;
+        const int rec = last ? 0 : (a6task ? P.rec_x : 6 * s + i - 1);
+        if (!tail && i == 7) {
             // ---- entering step s: reset per-step cotangents, add the saved-value cotangents --------
             const StepRec sr = P.steps[s];
             dt = sr.dt;
@@ -314,6 +327,7 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4_kernel(const KParams P) {
 #pragma unroll
             for (int e = 0; e < 16; ++e) upb[e] = 0.f;
             if ((use_eest || use_eig) && own) {
+                float esum = 0.f;      // explicit dt of utilde = dt * sum_j btilde_j k_j (a6.cuh)
 #pragma unroll
                 for (int ii = 0; ii < 4; ++ii) {
                     if (ii < cvalid) {
@@ -355,7 +369,7 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4_kernel(const KParams P) {
                                 const float dtu = dt * utb;
 #pragma unroll
                                 for (int j = 1; j <= 7; ++j) kb[j - 1][e] += c_BT[j] * dtu;
-                                dacc += (double)(wdir * utb * ssum);
+                                esum = rn_fmaf(utb, ssum, esum);
                             }
                             if (use_eig) {
                                 const float ga = live * gA * (kv[6][jj] - kv[5][jj]);
@@ -366,11 +380,13 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4_kernel(const KParams P) {
                         }
                     }
                 }
+                if (wdir != 0.f) dacc += (double)(wdir * esum);
             }
         }
         // kbar of this evaluation
         float cur[16], zb[16];
-        switch (i) {
+        if (a6task) { RNDE_A6_TASK_PRE(sA6, cur, sPart, dacc); dacc = 0.0; }
+        else switch (i) {
 #define RNDE_CUR(J) case J: _Pragma("unroll") for (int e = 0; e < 16; ++e) cur[e] = kb[J - 1][e]; break;
             RNDE_CUR(2) RNDE_CUR(3) RNDE_CUR(4) RNDE_CUR(5) RNDE_CUR(6)
             default: _Pragma("unroll") for (int e = 0; e < 16; ++e) cur[e] = kb[6][e]; break;
@@ -380,9 +396,11 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4_kernel(const KParams P) {
         if (!last) {
             const int t2 = task + 1;
             if (t2 == ntask - 1) rec_next = 0;
+            else if (na6 && t2 == ntask - 2) rec_next = P.rec_x;
             else { const int s2 = P.nsteps - 1 - t2 / 6, i2 = 7 - t2 % 6; rec_next = 6 * s2 + i2 - 1; }
         }
-        vjp(cur, zb, rec, rec_next, last ? 0.f : wshift + wdir * ts_c(i));
+        vjp(cur, zb, rec, rec_next, last ? 0.f : (a6task ? 1.f : wshift + wdir * ts_c(i)));
+        if (a6task) { RNDE_A6_TASK_POST(sA6, zb, sPart, dacc); continue; }      // dacc: reset before the vjp, now the evaluation's time cotangent
         if (last) {
             // initial fsalfirst = f(u0, t0): dx = ubar + zbar
             if (P.dx && own) {
@@ -414,25 +432,11 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4_kernel(const KParams P) {
                 }
             }
         }
-        if (wdir != 0.f && own) {       // explicit dt of z_i = u + dt * sum_j a_ij k_j (the records of stages < i still hold k)
-#pragma unroll 1
-            for (int ii = 0; ii < cvalid; ++ii) {
-                float a4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-                for (int jj = 1; jj < i; ++jj) {
-                    const float4 k4 = __ldcg(reinterpret_cast<const float4*>(P.tapeK + offD(6 * s + jj - 1, ii)));
-                    const float a = ts_a(i, jj);
-                    a4[0] = rn_fmaf(a, k4.x, a4[0]); a4[1] = rn_fmaf(a, k4.y, a4[1]); a4[2] = rn_fmaf(a, k4.z, a4[2]); a4[3] = rn_fmaf(a, k4.w, a4[3]);
-                }
-                float z4[4];
-                switch (ii) {       // zb lives in registers: constant indices only
-                    case 0: z4[0] = zb[0]; z4[1] = zb[1]; z4[2] = zb[2]; z4[3] = zb[3]; break;
-                    case 1: z4[0] = zb[4]; z4[1] = zb[5]; z4[2] = zb[6]; z4[3] = zb[7]; break;
-                    case 2: z4[0] = zb[8]; z4[1] = zb[9]; z4[2] = zb[10]; z4[3] = zb[11]; break;
-                    default: z4[0] = zb[12]; z4[1] = zb[13]; z4[2] = zb[14]; z4[3] = zb[15]; break;
-                }
-                dacc += (double)wdir * (((double)z4[0] * a4[0] + (double)z4[1] * a4[1]) + ((double)z4[2] * a4[2] + (double)z4[3] * a4[3]));
-            }
+        if (wdir != 0.f && own) {       // explicit dt of z_i = u + dt * sum_j a_ij k_j (the records of stages < i still hold k); cold path
+            float zc[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) zc[e] = zb[e];
+            dacc += (double)wdir * a6_direct_term(P.tapeK + offD(6 * s, 0), (size_t)P.Q * tileD, NP, cvalid, i, zc);
         }
         switch (i) {
             case 2: bwd_distribute<2>(kb, zb, dt); break;
@@ -450,7 +454,7 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4_kernel(const KParams P) {
             for (int e = 0; e < 16; ++e) { ubar[e] = upb[e]; kb[6][e] = kb[0][e]; }
         }
     }
-    if (P.a6) a6_block_sum<NT>(dacc, sPart, P.a6_part);
+    if (P.a6 == 1) a6_block_sum<NT>(dacc, sPart, P.a6_part);
     cluster_sync_all();
 }
 

@@ -39,7 +39,7 @@ struct B4TLayout {          // byte offsets
     int sbb1, sbb2;         // the same for the B operands, whose K-adjacent core matrices are B4T_LBO_B = 144 bytes apart
                             // (16 bytes of padding: the owners' 4-byte stores would otherwise be 8-way bank conflicted)
     int a2_groups, a1_groups;
-    int oA2hi, oA2lo, oA1hi, oA1lo, oB1, oB2, oPart, oD1, oZb, oBar, total;   // oB*: [hi | mid | lo], 2 * sbb* bytes each
+    int oA2hi, oA2lo, oA1hi, oA1lo, oB1, oB2, oPart, oD1, oZb, oBar, oA6, total;   // oB*: [hi | mid | lo], 2 * sbb* bytes each
 };
 
 __host__ __device__ inline B4TLayout make_b4t_layout(int D, int H) {
@@ -48,7 +48,7 @@ __host__ __device__ inline B4TLayout make_b4t_layout(int D, int H) {
     L.K1 = round_up(L.R, 16); L.K2 = round_up(H, 16);
     L.sbo1 = L.K1 * 16; L.sbo2 = L.K2 * 16;
     L.sbb1 = (L.K1 / 8) * B4T_LBO_B; L.sbb2 = (L.K2 / 8) * B4T_LBO_B;
-    L.a2_groups = (L.R + 7) / 8; L.a1_groups = (H + 7) / 8;
+    L.a2_groups = (L.R + 8) / 8; L.a1_groups = (H + 8) / 8;      // + one row: the time column of W1 / W2 (a6.cuh)
     int o = 0;
     L.oA2hi = o; o += L.a2_groups * L.sbo2;
     L.oA2lo = o; o += L.a2_groups * L.sbo2;
@@ -61,6 +61,7 @@ __host__ __device__ inline B4TLayout make_b4t_layout(int D, int H) {
     // consumed by GEMM 2 before the transposition overwrites it
     L.oZb = o; L.oB2 = o; o += (L.R * V2_NP * 4 > 6 * L.sbb2) ? L.R * V2_NP * 4 : 6 * L.sbb2;
     L.oBar = o; o += 64;
+    L.oA6 = o; o += 64;      // scalars of the initial-dt adjoint between its two halves (a6.cuh)
     L.total = o;
     return L;
 }
@@ -69,7 +70,7 @@ __host__ __device__ inline B4TLayout make_b4t_layout(int D, int H) {
 __host__ inline bool b4t_shape_ok(int D, int H) {
     if (!v2_shape_ok(D, H) || D % 4 != 0) return false;
     const B4TLayout L = make_b4t_layout(D, H);
-    if (L.R > 256 || L.R <= 128 || H > 128) return false;
+    if (L.R >= 256 || L.R <= 128 || H >= 128) return false;      // one accumulator row past R and past H carries the time cotangent
     if (L.oA2lo + 32 * L.sbo2 > L.total || L.oA1lo + 16 * L.sbo1 > L.total) return false;
     return true;
 }
@@ -104,6 +105,28 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
 }
 
+#ifdef RNDE_A6_COMPILED_OUT      // developer switch (tools/sweep_variants.py): what the first-dt additions cost the hot loop
+#define A6ON false
+#else
+#define A6ON (A6C && P.a6 != 0)
+#endif
+#ifdef RNDE_A6_NO_TAU
+#define A6TAU false
+#else
+#define A6TAU A6ON
+#endif
+#ifdef RNDE_A6_NO_ZB
+#define A6ZB false
+#else
+#define A6ZB A6ON
+#endif
+#ifdef RNDE_A6_NO_TASK
+#define A6TASK false
+#else
+#define A6TASK A6ON
+#endif
+// A6C: compile the first-dt additions in (a6.cuh); the <false> instantiation serves detach = all and forced-step replays
+template <bool A6C>
 __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
     constexpr int G = V2_G, NP = V2_NP, NT = V2_NT;
     extern __shared__ __align__(16) float smem[];
@@ -150,6 +173,11 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
     for (int e = tid; e < R * H; e += NT) {          // A2[i][k] = W1[k, r0 + i]   (k fastest: coalesced)
         const int i = e / H, k = e - i * H;
         put(L.oA2hi, L.oA2lo, L.sbo2, i, k, __ldg(gW1 + (size_t)H * (r0 + i) + k));
+    }
+    if (P.a6 && td) {      // a6.cuh: the time columns as one more operand row each -- the MMAs then deliver sum_r W2[r, t] delta2[r, :] in
+        // accumulator row H of GEMM 1 (this CTA's rows) and sum_h W1[h, t] delta1[h, :] in accumulator row R of GEMM 2
+        for (int k = tid; k < R; k += NT) put(L.oA1hi, L.oA1lo, L.sbo1, H, k, __ldg(gW2 + (size_t)D * H + r0 + k));
+        for (int k = tid; k < H; k += NT) put(L.oA2hi, L.oA2lo, L.sbo2, R, k, __ldg(gW1 + (size_t)H * D + k));
     }
     if (tid == 0) {
         mbar_init(barP, 1); mbar_init(barH, 1); mbar_init(barM1, 4); mbar_init(barM2, 4);
@@ -202,11 +230,6 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
     const uint32_t bytesH = (uint32_t)((H - HSloc) * NP * 4);
     const size_t tileD = (size_t)D * NP, tileH = (size_t)H * NP;
     auto offD = [&](int rec, int i) -> size_t { return ((size_t)rec * P.Q + q) * tileD + (size_t)(r0 + crow0 + i) * NP + cn0; };
-    // Appendix A.6 (a6.cuh): this thread's part of dL/d(dt_1), and the time columns of W2 / W1 for the rows / hidden unit it owns
-    double dacc = 0.0;
-    float wdir = 0.f, wshift = 0.f;
-    const float* const w2t = gW2 + (size_t)D * H + r0 + crow0;      // read where needed (L1 resident): no registers held across the sweep
-    const float* const w1tp = gW1 + (size_t)H * D + rank * HS + (tid >> 2);
     const int quad = warp & 3;
     const uint32_t tlane = (uint32_t)(quad * 32) << 16;
 
@@ -220,8 +243,7 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
     float4 kvn[4];
     int kvn_rec = -1;
     // VJP of record `rec`: cur = kbar of that evaluation (in), zb = W1^T delta1 for the tile (out)
-    auto vjp = [&](const float (&cur)[16], float (&zb)[16], const int rec, const int rec_next, const float wt) {
-        const bool want_t = (wt != 0.f) && td;
+    auto vjp = [&](const float (&cur)[16], float (&zb)[16], const int rec, const int rec_next) {
         TLB(0);
         if (tid == 0) { mbar_expect_tx(barP, bytesP); mbar_expect_tx(barH, bytesH); }
         if (rec_next >= 0) {        // pull the next record's tiles towards L2
@@ -253,7 +275,6 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
                     *reinterpret_cast<float4*>(sZb + (crow0 + i) * NP + cn0) = d2;      // delta2 replaces k on the tape: bulk store below
                 } else d2 = make_float4(0.f, 0.f, 0.f, 0.f);
                 d2v[i][0] = d2.x; d2v[i][1] = d2.y; d2v[i][2] = d2.z; d2v[i][3] = d2.w;
-                if (want_t && i < cvalid) dacc += (double)(wt * __ldg(w2t + i) * ((d2.x + d2.y) + (d2.z + d2.w)));
             }
             // element (n, k = local row): crow0 is even, so rows (i, i+1) are an aligned bf16 pair inside one 8-group
 #ifndef RNDE_EXP_NOSPLIT
@@ -319,6 +340,12 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
                     }
                 }
             const int m = quad * 32 + lane;
+            if (m == H && A6TAU) {      // time cotangent of layer 2, this CTA's rows (a6.cuh): kept per record, summed in the a6 task
+                float t = 0.f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) t += v[j];
+                P.a6_tau[(((size_t)rec * P.Q + q) * G + rank) * 2] = t;
+            }
             if (m < H) {
                 const int d = m / HS, ml = m - d * HS;
                 float* dst = sPart + (rank * HS + ml) * NP;
@@ -348,7 +375,6 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
                 const float4 hv = __ldcg(reinterpret_cast<const float4*>(P.tapeH + oh));
                 s.x *= (1.f - hv.x * hv.x); s.y *= (1.f - hv.y * hv.y); s.z *= (1.f - hv.z * hv.z); s.w *= (1.f - hv.w * hv.w);
             }
-            if (want_t) dacc += (double)(wt * __ldg(w1tp) * ((s.x + s.y) + (s.z + s.w)));
             float* dst = sD1 + m * NP + n4;
             *reinterpret_cast<float4*>(dst) = s;
             const uint32_t da = smem_u32(dst);
@@ -421,6 +447,12 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
                         for (int j = 0; j < 16; ++j) v[j] += t[j];
                     }
                 }
+            if (row == R && A6TAU) {      // time cotangent of layer 1 (the same in every CTA of the cluster)
+                float t = 0.f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) t += v[j];
+                P.a6_tau[(((size_t)rec * P.Q + q) * G + rank) * 2 + 1] = t;
+            }
             if (row < R) {
 #pragma unroll
                 for (int c4 = 0; c4 < 4; ++c4)
@@ -449,17 +481,22 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
     const float stab = rn_divf(1.0f, (float)TS_STABILITY_SIZE);
 
     // task list, newest evaluation first: for s = nsteps-1..0: stages 7..2; then the initial record 0
-    const int ntask = 6 * P.nsteps + 1;
+    // (+ with P.a6 >= 2 one task before the last: the evaluation of the initial-dt heuristic, a6.cuh)
+    const int na6 = (A6TASK && P.a6 >= 2) ? 1 : 0;
+    const int ntask = 6 * P.nsteps + 1 + na6;
+    float* sA6 = reinterpret_cast<float*>(sb + L.oA6);
     float dt = 0.f, gB = 0.f;
     bool use_eig = false;
     int recU1 = 0, recG6 = 0;
     for (int task = 0; task < ntask; ++task) {
         const bool last = (task == ntask - 1);
-        const int s = last ? 0 : P.nsteps - 1 - task / 6;
-        const int i = last ? 7 : 7 - task % 6;
-        const int rec = last ? 0 : 6 * s + i - 1;
+        const bool a6task = na6 && (task == ntask - 2);
+        const bool tail = last || a6task;
+        const int s = tail ? 0 : P.nsteps - 1 - task / 6;
+        const int i = tail ? 7 : 7 - task % 6;
+        const int rec = last ? 0 : (a6task ? P.rec_x : 6 * s + i - 1);
         TLB(10);
-        if (!last && i == 7) {
+        if (!tail && i == 7) {
             // ---- entering step s: reset per-step cotangents, add the saved-value cotangents --------
             const StepRec sr = P.steps[s];
             dt = sr.dt;
@@ -489,14 +526,6 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
             const float gA = use_eig ? n1b / (cntf * n1) : 0.f;
             gB = use_eig ? n2b / (cntf * n2) : 0.f;
             recU1 = 6 * s + 6; recG6 = 6 * s + 5;
-            // weight of this step's explicit dt in dL/d(dt_1) (first step: +1, last step when it was cut: -1) and of its start time
-            wdir = P.a6 ? ((s == 0 ? 1.f : 0.f) - (s == P.nsteps - 1 ? P.initdt[5] : 0.f)) : 0.f;
-            wshift = (P.a6 && s >= 1) ? 1.f : 0.f;
-            if (wdir != 0.f && sbar != 0.f && blockIdx.x == 0 && tid == 0) {
-                if (P.reg_kind == RNDE_REG_ERR_DT) dacc += wdir * sbar * EEst;
-                else if (P.reg_kind == RNDE_REG_STIFF_DT_ABS && P.alg == RNDE_ALG_AUTO_TSIT5) dacc += wdir * sbar * ((eig * dt) >= 0.f ? 1.f : -1.f) * eig;
-                else if (P.reg_kind == RNDE_REG_ERR_PLUS_STIFF) { const float e = EEst * dt; if (!(e == 0.f || e != e)) dacc += wdir * sbar * EEst; }
-            }
 #pragma unroll
             for (int a = 0; a < 6; ++a)
 #pragma unroll
@@ -546,7 +575,6 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
                                 const float dtu = dt * utb;
 #pragma unroll
                                 for (int j = 1; j <= 7; ++j) kb[j - 1][e] += c_BT[j] * dtu;
-                                dacc += (double)(wdir * utb * ssum);
                             }
                             if (use_eig) {
                                 const float ga = live * gA * (kv[6][jj] - kv[5][jj]);
@@ -566,7 +594,8 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
         TLB(9);
         // kbar of this evaluation
         float cur[16], zb[16];
-        switch (i) {
+        if (a6task) RNDE_A6_TASK_PRE(sA6, cur, sPart, a6_sweep_partial(P, own, cvalid, offD(0, 0), (size_t)P.Q * tileD, NP, q, rank, G));
+        else switch (i) {
 #define RNDE_CUR(J) case J: _Pragma("unroll") for (int e = 0; e < 16; ++e) cur[e] = kb[J - 1][e]; break;
             RNDE_CUR(2) RNDE_CUR(3) RNDE_CUR(4) RNDE_CUR(5) RNDE_CUR(6)
             default: _Pragma("unroll") for (int e = 0; e < 16; ++e) cur[e] = kb[6][e]; break;
@@ -576,6 +605,7 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
         if (!last) {
             const int t2 = task + 1;
             if (t2 == ntask - 1) rec_next = 0;
+            else if (na6 && t2 == ntask - 2) rec_next = P.rec_x;
             else { const int s2 = P.nsteps - 1 - t2 / 6, i2 = 7 - t2 % 6; rec_next = 6 * s2 + i2 - 1; }
         }
         if (!last && i == 2 && s > 0 && own) {   // one evaluation ahead of step s-1's entry: start its records towards L2
@@ -590,7 +620,12 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
                 }
             }
         }
-        vjp(cur, zb, rec, rec_next, last ? 0.f : wshift + wdir * ts_c(i));
+        vjp(cur, zb, rec, rec_next);
+        if (a6task) {      // its time cotangent: the two sums the tensor cores left for this CTA
+            const float* tp = P.a6_tau + (((size_t)rec * P.Q + q) * G + rank) * 2;
+            RNDE_A6_TASK_POST(sA6, zb, sPart, (tid == 0 && td) ? (double)(__ldcg(tp) + (rank == 0 ? __ldcg(tp + 1) : 0.f)) : 0.0);
+            continue;
+        }
         if (last) {
             // initial fsalfirst = f(u0, t0): dx = ubar + zbar
             if (P.dx && own) {
@@ -622,25 +657,11 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
                 }
             }
         }
-        if (wdir != 0.f && own) {       // explicit dt of z_i = u + dt * sum_j a_ij k_j (the records of stages < i still hold k)
-#pragma unroll 1
-            for (int ii = 0; ii < cvalid; ++ii) {
-                float a4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-                for (int jj = 1; jj < i; ++jj) {
-                    const float4 k4 = __ldcg(reinterpret_cast<const float4*>(P.tapeK + offD(6 * s + jj - 1, ii)));
-                    const float a = ts_a(i, jj);
-                    a4[0] = rn_fmaf(a, k4.x, a4[0]); a4[1] = rn_fmaf(a, k4.y, a4[1]); a4[2] = rn_fmaf(a, k4.z, a4[2]); a4[3] = rn_fmaf(a, k4.w, a4[3]);
-                }
-                float z4[4];
-                switch (ii) {       // zb lives in registers: constant indices only
-                    case 0: z4[0] = zb[0]; z4[1] = zb[1]; z4[2] = zb[2]; z4[3] = zb[3]; break;
-                    case 1: z4[0] = zb[4]; z4[1] = zb[5]; z4[2] = zb[6]; z4[3] = zb[7]; break;
-                    case 2: z4[0] = zb[8]; z4[1] = zb[9]; z4[2] = zb[10]; z4[3] = zb[11]; break;
-                    default: z4[0] = zb[12]; z4[1] = zb[13]; z4[2] = zb[14]; z4[3] = zb[15]; break;
-                }
-                dacc += (double)wdir * (((double)z4[0] * a4[0] + (double)z4[1] * a4[1]) + ((double)z4[2] * a4[2] + (double)z4[3] * a4[3]));
-            }
+        if (A6ZB && own && (s == 0 || s == P.nsteps - 1)) {      // a6.cuh: the explicit dt of z_i needs this cotangent later (first and last step)
+            const int slot = (s == 0 ? 0 : 6) + i - 2;
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii)
+                if (ii < cvalid) *reinterpret_cast<float4*>(P.a6_zb + offD(slot, ii)) = make_float4(zb[ii * 4], zb[ii * 4 + 1], zb[ii * 4 + 2], zb[ii * 4 + 3]);
         }
         switch (i) {
             case 2: bwd_distribute<2>(kb, zb, dt); break;
@@ -661,7 +682,10 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
 #ifdef RNDE_TIMELINE
     if (P.dbg && blockIdx.x == 0 && tid == 0) for (int k = 0; k < 14; ++k) P.dbg[k] = tl_acc[k];
 #endif
-    if (P.a6) a6_block_sum<NT>(dacc, sPart, P.a6_part);
+    if (A6ON && P.a6 == 1) {      // the two extra VJPs run as separate launches (reference-exact data parallel): leave this CTA's partial sum
+        const double part = a6_sweep_partial(P, own, cvalid, offD(0, 0), (size_t)P.Q * tileD, NP, q, rank, G);
+        a6_block_sum<NT>(part, sPart, P.a6_part);
+    }
     if (tid == 0) bulk_wait_all();
     tc_fence_before();
     __syncthreads();

@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(NT, 1) bwd_kernel(const KParams P) {
 
     // ---- Appendix A.6: the two evaluations of the initial-dt heuristic (launched after the sweep, a6.cuh) ----------------
     if (P.a6_mode != 0) {
-        const A6Scal sc = a6_scalars(P);
+        const A6Scal sc = a6_scalars(P, P.a6_sum[0]);
         const float d0 = P.initdt[0], d1 = P.initdt[1], d2 = P.initdt[2], dt0 = P.initdt[3];
         const float* f0t = P.a6_f0 + (size_t)q * tileD + (size_t)r0 * NP;
         const size_t boff = (size_t)q * tileD + (size_t)r0 * NP, bstr = (size_t)P.Q * tileD;     // three buffers: u1bar, f1bar, w * wbar

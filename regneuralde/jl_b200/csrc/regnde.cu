@@ -53,6 +53,7 @@ struct rnde_handle {
     // Appendix A.6 with the first dt on the tape (rnde_set_detach, a6.cuh)
     int detach = RNDE_DETACH_ALL_BUT_FIRST;
     float* initdt = nullptr; double* a6_part = nullptr; float* a6_sum = nullptr; float* a6_buf = nullptr; float* a6_f0 = nullptr;
+    float* a6_zb = nullptr; float* a6_tau = nullptr; float* a6_kc = nullptr;
     size_t smem_a6 = 0;
     const float* noise = nullptr;       // FFJORD: caller-owned Hutchinson noise (rnde_set_noise)
     long long* dbg = nullptr;
@@ -148,14 +149,15 @@ static bool bwd4_use_tc(int D, int H) {
     static const bool force_ffma = getenv("RNDE_BWD_FFMA") != nullptr;
     return !force_ffma && D > 0 && H > 0 && b4t_shape_ok(D, H);
 }
-static kern_t bwd_kernel_for(int variant, int D = 0, int H = 0) {
+// a6: the instantiation that also serves the first-dt term (a6.cuh); the plain one keeps the hot loop free of it
+static kern_t bwd_kernel_for(int variant, int D = 0, int H = 0, bool a6 = true) {
     switch (variant) {
         case RNDE_KERNEL_CTA: return bwd_kernel<1, 32, 4, true, NT_FWD>;
         case RNDE_KERNEL_STREAM: return bwd_kernel<1, 4, 1, false, NT_FWD>;
         case RNDE_KERNEL_CHAIN: return bwd_kernel<1, 4, 1, true, NT_FWD>;
         case RNDE_KERNEL_CLUSTER: return bwd_kernel<8, 32, 4, true, NT_FWD>;
         case RNDE_KERNEL_CLUSTER4:
-            if (bwd4_use_tc(D, H)) return bwd4tc_kernel;
+            if (bwd4_use_tc(D, H)) return a6 ? bwd4tc_kernel<true> : bwd4tc_kernel<false>;
             return (H == 100 && D == 784) ? bwd4_kernel<100, 98> : bwd4_kernel<0, 0>;
         default: return nullptr;
     }
@@ -268,7 +270,7 @@ static void free_all(rnde_handle* h) {
     for (int i = 0; i < 8; ++i) if (h->peers_open[i]) cudaIpcCloseMemHandle((void*)h->peers[i]);
     cudaFree(h->colsum); cudaFree(h->bar); cudaFree(h->steps); cudaFree(h->stats);
     cudaFree(h->tapeZ); cudaFree(h->tapeK); cudaFree(h->tapeH); cudaFree(h->tapeD1); cudaFree(h->wg_ws); cudaFree(h->scal); cudaFree(h->saveval_int);
-    cudaFree(h->initdt); cudaFree(h->a6_part); cudaFree(h->a6_sum); cudaFree(h->a6_buf); cudaFree(h->a6_f0);
+    cudaFree(h->a6_zb); cudaFree(h->a6_tau); cudaFree(h->a6_kc); cudaFree(h->initdt); cudaFree(h->a6_part); cudaFree(h->a6_sum); cudaFree(h->a6_buf); cudaFree(h->a6_f0);
     cudaFree(h->dtile); cudaFree(h->head_ws); cudaFree(h->dbg); cudaFree(h->saveat_dev); cudaFree(h->forced_dev);
     if (h->ev_stats) cudaEventDestroy(h->ev_stats);
     cudaFree(h->hx); cudaFree(h->hp); cudaFree(h->hu); cudaFree(h->hsv); cudaFree(h->hdu); cudaFree(h->hdsv); cudaFree(h->hdp); cudaFree(h->hdx);
@@ -315,8 +317,10 @@ static int try_variant(rnde_handle* h, int variant, size_t smem_limit, std::stri
     if (cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sf) != cudaSuccess) { cudaGetLastError(); *why = "cudaFuncSetAttribute(fwd) failed"; return 0; }
     size_t sa = sb;
     if (c.need_backward) {
-        kern_t kb = bwd_kernel_for(variant, D, H);
-        if (cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb) != cudaSuccess) { cudaGetLastError(); *why = "cudaFuncSetAttribute(bwd) failed"; return 0; }
+        for (int a = 0; a < 2; ++a) {      // both instantiations (with / without the first-dt additions)
+            kern_t kb = bwd_kernel_for(variant, D, H, a != 0);
+            if (cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb) != cudaSuccess) { cudaGetLastError(); *why = "cudaFuncSetAttribute(bwd) failed"; return 0; }
+        }
         if (variant == RNDE_KERNEL_CLUSTER4) {
             sa = (size_t)make_bwd_layout(4, 16, false, D, H, R, HS).total * sizeof(float);
             if (sa > smem_limit) { *why = "shared memory (initial-dt adjoint): need " + std::to_string(sa) + " B"; return 0; }
@@ -445,10 +449,15 @@ extern "C" int rnde_create(const rnde_config* cfg, rnde_handle** out) {
         // records: fsalfirst + 6 per step, + one pseudo-step and the initial-dt evaluation of Appendix A.6 (a6.cuh)
         const size_t nrec = 1 + (size_t)6 * (c.tape_capacity + 1) + 1;
         const size_t tile = (size_t)h->Q * h->NP;
-        if (cudaMalloc(&h->a6_part, sizeof(double) * (size_t)h->Q * h->G) != cudaSuccess) return fail("cudaMalloc a6_part");
+        if (cudaMalloc(&h->a6_part, sizeof(double) * 2 * (size_t)h->Q * h->G) != cudaSuccess) return fail("cudaMalloc a6_part");
         if (cudaMalloc(&h->a6_sum, sizeof(float) * 4) != cudaSuccess) return fail("cudaMalloc a6_sum");
         if (cudaMalloc(&h->a6_buf, sizeof(float) * 3 * tile * D) != cudaSuccess) return fail("cudaMalloc a6_buf");
         if (cudaMalloc(&h->a6_f0, sizeof(float) * tile * D) != cudaSuccess) return fail("cudaMalloc a6_f0");
+        if (h->variant == RNDE_KERNEL_CLUSTER4) {      // what the tensor-core sweep leaves for the first-dt term (a6.cuh)
+            if (cudaMalloc(&h->a6_zb, sizeof(float) * 12 * tile * D) != cudaSuccess) return fail("cudaMalloc a6_zb");
+            if (cudaMalloc(&h->a6_kc, sizeof(float) * 12 * tile * D) != cudaSuccess) return fail("cudaMalloc a6_kc");
+            if (cudaMalloc(&h->a6_tau, sizeof(float) * nrec * h->Q * h->G * 2) != cudaSuccess) return fail("cudaMalloc a6_tau");
+        }
         if (cudaMalloc(&h->tapeZ, sizeof(float) * nrec * tile * D) != cudaSuccess) return fail("cudaMalloc tapeZ (lower tape_capacity?)");
         if (cudaMalloc(&h->tapeK, sizeof(float) * nrec * tile * D) != cudaSuccess) return fail("cudaMalloc tapeK (lower tape_capacity?)");
         const size_t hrows = c.n_layers > 0 ? (size_t)chain_hrows(c) : (size_t)H;
@@ -461,6 +470,15 @@ extern "C" int rnde_create(const rnde_config* cfg, rnde_handle** out) {
     if (c.max_saveat > 0 && cudaMalloc(&h->saveat_dev, sizeof(float) * c.max_saveat) != cudaSuccess) return fail("cudaMalloc saveat");
     if (getenv("RNDE_DEBUG_TIMELINE")) { cudaMalloc(&h->dbg, sizeof(long long) * 8000); cudaMemset(h->dbg, 0, sizeof(long long) * 8000); }
     *out = h;
+    return RNDE_OK;
+}
+
+// developer diagnostic: the two reduced sums of the first-dt adjoint (dL/d(dt_1); <u1bar, f0> + tbar), separate-launch path only
+extern "C" int rnde_debug_a6(rnde_handle* h, float* out2) {
+    if (!h || !out2 || !h->a6_sum) return RNDE_ERR_ARG;
+    ON_HANDLE_DEVICE(h);
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    CUDA_TRY(h, cudaMemcpy(out2, h->a6_sum, sizeof(float) * 2, cudaMemcpyDeviceToHost));
     return RNDE_OK;
 }
 
@@ -561,7 +579,7 @@ static void fill_params(const rnde_handle* h, KParams& P) {
     P.forced_dt = h->forced_dev; P.n_forced = h->n_forced;
     P.a6 = (c.need_backward && h->detach != RNDE_DETACH_ALL && h->n_forced == 0 && c.csq_extra == 0) ? 1 : 0;
     P.rec_init = 1 + 6 * (c.tape_capacity + 1);
-    P.initdt = h->initdt; P.a6_part = h->a6_part; P.a6_sum = h->a6_sum; P.a6_u1bar = h->a6_buf; P.a6_f0 = h->a6_f0;
+    P.initdt = h->initdt; P.a6_part = h->a6_part; P.a6_sum = h->a6_sum; P.a6_u1bar = h->a6_buf; P.a6_f0 = h->a6_f0; P.a6_zb = h->a6_zb; P.a6_tau = h->a6_tau; P.a6_kc = h->a6_kc;
 }
 
 // shared-memory offsets of the chain region: right after the generic kernel's own layout
@@ -692,26 +710,44 @@ static int backward_impl(rnde_handle* h, const float* du_dev, const float* dusav
     // Their records sit behind the last step: 6N+1..6N+5 empty, 6N+6 the evaluation f(u0 + dt0 f0, t0 + dt0).
     const bool a6 = P.a6 && s.naccept > 0;
     P.a6 = a6 ? 1 : 0;
-    // the tensor-core contraction takes the extra record in the spare K slot of the first step's group, where it lies;
+    // the tensor-core contraction takes the extra record in a spare K slot (of the second step's group), where it lies;
     // the other contractions see it as stage 7 of a pseudo-step behind the last one (records 6N+1..6N+5 empty)
     static const bool force_ffma = getenv("RNDE_WGRAD_FFMA") != nullptr;
     const bool wg_tc = h->NP == 16 && !force_ffma && h->cfg.n_layers == 0;
+    const bool wg_slot = wg_tc && s.naccept >= 2;      // ... in the spare K slot of the SECOND step's group
+    // the cluster-4 sweeps differentiate the heuristic themselves (one more VJP between two grid-wide sums, a6.cuh); the other
+    // variants, and the reference-exact mode whose sums run over all ranks, launch the generic kernel twice after the sweep
+    static const bool a6_external = getenv("RNDE_A6_EXTERNAL") != nullptr;      // developer switch: always the separate launches
+    const bool a6_inkernel = a6 && !a6_external && h->variant == RNDE_KERNEL_CLUSTER4 && !(h->cfg.nranks > 1 && h->cfg.dist_mode == RNDE_DIST_EXACT);
+    if (a6_inkernel) { P.a6 = (h->detach == RNDE_DETACH_FIRST_TERM_ONLY) ? 3 : 2; P.rec_x = wg_slot ? P.rec_init : 6 * s.naccept + 6; }
     const size_t tileN = (size_t)h->Q * h->NP;
     const size_t recD = tileN * h->cfg.state_dim;
     const size_t recH = tileN * (h->cfg.n_layers > 0 ? (size_t)chain_hrows(h->cfg) : (size_t)h->cfg.hidden_dim);
-    if (a6) CUDA_TRY(h, cudaMemcpyAsync(h->a6_f0, h->tapeK, sizeof(float) * recD, cudaMemcpyDeviceToDevice, st));      // f0, before delta2 replaces it
-    if (a6 && !wg_tc) {
+    if (a6 && !a6_inkernel) CUDA_TRY(h, cudaMemcpyAsync(h->a6_f0, h->tapeK, sizeof(float) * recD, cudaMemcpyDeviceToDevice, st));      // f0, before delta2 replaces it
+    if (a6 && !wg_slot) {
         const size_t rx = (size_t)6 * s.naccept + 6, ri = (size_t)P.rec_init;
         CUDA_TRY(h, cudaMemcpyAsync(h->tapeZ + rx * recD, h->tapeZ + ri * recD, sizeof(float) * recD, cudaMemcpyDeviceToDevice, st));
         CUDA_TRY(h, cudaMemcpyAsync(h->tapeK + rx * recD, h->tapeK + ri * recD, sizeof(float) * recD, cudaMemcpyDeviceToDevice, st));
         CUDA_TRY(h, cudaMemcpyAsync(h->tapeH + rx * recH, h->tapeH + ri * recH, sizeof(float) * recH, cudaMemcpyDeviceToDevice, st));
         CUDA_TRY(h, cudaMemsetAsync(h->tapeK + (rx - 5) * recD, 0, sizeof(float) * 5 * recD, st));
         CUDA_TRY(h, cudaMemsetAsync(h->tapeD1 + (rx - 5) * recH, 0, sizeof(float) * 5 * recH, st));
+        // ... and their inputs too: the contraction multiplies them by the zero deltas, and stale memory may hold NaN
+        CUDA_TRY(h, cudaMemsetAsync(h->tapeZ + (rx - 5) * recD, 0, sizeof(float) * 5 * recD, st));
+        CUDA_TRY(h, cudaMemsetAsync(h->tapeH + (rx - 5) * recH, 0, sizeof(float) * 5 * recH, st));
+    }
+    if (a6 && h->a6_kc) {      // k_1..k_6 of the first and of the last step, before the sweep replaces them by delta2 (a6.cuh)
+        CUDA_TRY(h, cudaMemcpyAsync(h->a6_kc, h->tapeK, sizeof(float) * 6 * recD, cudaMemcpyDeviceToDevice, st));
+        if (s.naccept > 1)
+            CUDA_TRY(h, cudaMemcpyAsync(h->a6_kc + 6 * recD, h->tapeK + (size_t)6 * (s.naccept - 1) * recD, sizeof(float) * 6 * recD, cudaMemcpyDeviceToDevice, st));
     }
     CUDA_TRY(h, cudaMemsetAsync(h->bar, 0, sizeof(unsigned) * 4, st));
-    int rc = launch(h, bwd_kernel_for(h->variant, h->cfg.state_dim, h->cfg.hidden_dim), P, h->smem_bwd, st);
+    int rc = launch(h, bwd_kernel_for(h->variant, h->cfg.state_dim, h->cfg.hidden_dim, P.a6 != 0), P, h->smem_bwd, st);
     if (rc != RNDE_OK) return rc;
-    if (a6) {
+    if (a6_inkernel && h->detach == RNDE_DETACH_FIRST_TERM_ONLY) {      // diagnostic: only record 0 and the extra record keep their deltas
+        CUDA_TRY(h, cudaMemsetAsync(h->tapeK + recD, 0, sizeof(float) * (size_t)6 * s.naccept * recD, st));
+        CUDA_TRY(h, cudaMemsetAsync(h->tapeD1 + recH, 0, sizeof(float) * (size_t)6 * s.naccept * recH, st));
+    }
+    if (a6 && !a6_inkernel) {
         const int nparts = h->Q * h->G;
         auto reduce = [&](int slot) -> int {
             a6_reduce_kernel<<<1, 256, 0, st>>>(h->a6_part, nparts, h->a6_sum, slot);
@@ -722,7 +758,7 @@ static int backward_impl(rnde_handle* h, const float* du_dev, const float* dusav
             return RNDE_OK;
         };
         KParams PA = P;
-        PA.du = nullptr; PA.dusave = nullptr; PA.n_saveat = 0; PA.rec_x = wg_tc ? P.rec_init : 6 * s.naccept + 6;
+        PA.du = nullptr; PA.dusave = nullptr; PA.n_saveat = 0; PA.rec_x = wg_slot ? P.rec_init : 6 * s.naccept + 6;
         if (h->variant == RNDE_KERNEL_CLUSTER4) { PA.n_layers = 0; }
         if ((rc = reduce(0)) != RNDE_OK) return rc;
         if (h->detach == RNDE_DETACH_FIRST_TERM_ONLY) {      // diagnostic: drop what the sweep produced, keep only the first-dt term
@@ -737,7 +773,7 @@ static int backward_impl(rnde_handle* h, const float* du_dev, const float* dusav
         PA.a6_mode = 2;
         if ((rc = launch(h, a6_kernel_for(h->variant), PA, h->smem_a6, st)) != RNDE_OK) return rc;
     }
-    const int nsteps_w = s.naccept + ((a6 && !wg_tc) ? 1 : 0);      // steps the weight-gradient contraction runs over
+    const int nsteps_w = s.naccept + ((a6 && !wg_slot) ? 1 : 0);      // steps the weight-gradient contraction runs over
     if (h->cfg.n_layers > 0) {      // chain field: per-layer contractions over the tape, FP64 across stages
         const int nrec_c = 1 + 6 * nsteps_w;
         WgDesc desc; memset(&desc, 0, sizeof(desc));
@@ -761,7 +797,7 @@ static int backward_impl(rnde_handle* h, const float* du_dev, const float* dusav
     // tensor-core (tcgen05 3xTF32) contraction for the 16-column tape layout; RNDE_WGRAD_FFMA=1 selects the FFMA kernel
     if (wg_tc) {
         rc = launch_wgrad_tc(h->cfg.state_dim, h->cfg.hidden_dim, h->cfg.time_dep ? 1 : 0, nrec, h->Q, h->tapeZ, h->tapeK, h->tapeH, h->tapeD1,
-                             h->steps, h->cfg.t0, h->wg_ws, dp_dev, st, &h->launches, a6 ? P.rec_init : -1);
+                             h->steps, h->cfg.t0, h->wg_ws, dp_dev, st, &h->launches, (a6 && wg_slot) ? P.rec_init : -1);
         if (rc != 0) return set_err(h, RNDE_ERR_CUDA, std::string("wgrad (tcgen05) launch: ") + cudaGetErrorString((cudaError_t)rc));
         return RNDE_OK;
     }

@@ -73,8 +73,9 @@ __device__ __forceinline__ void mbar_arrive_local(uint32_t bar) { asm volatile("
 
 // A: [tiles][M][16], Bm: [tiles][Nrows][16] (physical tile = rec*Q + q); partial: [split][chunk][Naug][M] floats.
 // Stage sg = ((s*Q + q) << 2) | cq : step s, column tile q, columns [4cq, 4cq+4) of the tile; K slot j of a column = record
-// 1+6s+j (j < 6), record 0 (j = 6, s = 0 only), record rec_extra (j = 7, s = 0 only, when rec_extra >= 0: the evaluation of the
-// initial-dt heuristic, a6.cuh; its time is t + dt of the pseudo-step steps[nsteps]), zero otherwise.
+// 1+6s+j (j < 6); slot 6 holds record 0 in the first step's group and, when rec_extra >= 0, record rec_extra in the second
+// step's (the evaluation of the initial-dt heuristic, a6.cuh; its time is t + dt of the pseudo-step steps[nsteps]); slot 7 and
+// every other slot 6 are zero.
 __global__ void __launch_bounds__(WGT_THREADS, 1) wgrad_tc_kernel(const float* __restrict__ A, int M, const float* __restrict__ Bm, int Nrows,
                                                                  int nsteps, int Q, const StepRec* __restrict__ steps, float t0, int td,
                                                                  int flush, float* __restrict__ partial, int rec_extra) {
@@ -122,14 +123,14 @@ __global__ void __launch_bounds__(WGT_THREADS, 1) wgrad_tc_kernel(const float* _
         const bool aug_t = opnd && grow == Nrows, aug_1 = opnd && grow == Nrows + 1;
         const uint32_t dst_off = (uint32_t)((opnd ? 2 * WGT_PART_BYTES : 0) + (row >> 3) * WGT_SBO + (row & 7) * 16);
         auto tf32_rn = [](float v) -> float { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v)); return __uint_as_float(r); };
-        auto issue = [&](int g, float4 (&buf)[8]) {
+        auto issue = [&](int g, float4 (&buf)[7]) {
             const int sg = stage0 + g;
             const int grp = sg >> 2, cq = sg & 3;
             const int s = grp / Q, q = grp - s * Q;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int rec = (j < 6) ? 1 + 6 * s + j : (j == 6 ? 0 : rec_extra);
-                const bool have = (j < 6) ? (s < nsteps) : (j == 6 ? (s == 0) : (s == 0 && rec_extra >= 0));
+            for (int j = 0; j < 7; ++j) {
+                const int rec = (j < 6) ? 1 + 6 * s + j : (s == 0 ? 0 : rec_extra);
+                const bool have = (j < 6) ? (s < nsteps) : (s == 0 || (s == 1 && rec_extra >= 0));
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (have) {
                     if (real_row) v = __ldg(reinterpret_cast<const float4*>(gsrc + (((size_t)rec * Q + q) * nrows_src + grow) * NP + cq * 4));
@@ -141,28 +142,29 @@ __global__ void __launch_bounds__(WGT_THREADS, 1) wgrad_tc_kernel(const float* _
             // formed from it in convert_store (a dependent load here would stall this thread, and with it the stage, once per stage)
             if (aug_t && td) {
                 buf[0] = (s < nsteps) ? __ldg(reinterpret_cast<const float4*>(steps + s)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                buf[1] = make_float4((s < nsteps) ? 1.f : 0.f, (s == 0) ? 1.f : 0.f, (s == 0 && rec_extra >= 0) ? 1.f : 0.f, 0.f);      // which slots are live
-                buf[2] = (s == 0 && rec_extra >= 0) ? __ldg(reinterpret_cast<const float4*>(steps + nsteps)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float tx = 0.f;      // time of slot 6: t0 for record 0, t + dt of the pseudo-step for the extra record
+                if (s == 0) tx = t0;
+                else if (s == 1 && rec_extra >= 0) { const float4 ps = __ldg(reinterpret_cast<const float4*>(steps + nsteps)); tx = ps.x + ps.y; }
+                buf[1] = make_float4((s < nsteps) ? 1.f : 0.f, tx, 0.f, 0.f);      // slots 0-5 live; time of slot 6 (0 when empty)
             }
         };
-        auto time_row = [&](float4 (&buf)[8]) {      // expand (t, dt) of the step into the 8 slot times (same arithmetic as rec_time)
+        auto time_row = [&](float4 (&buf)[7]) {      // expand (t, dt) of the step into the 7 slot times (same arithmetic as rec_time)
             const float st = buf[0].x, sdt = buf[0].y;
-            const bool live6 = buf[1].x != 0.f, live0 = buf[1].y != 0.f;
-            const float tx = (buf[1].z != 0.f) ? buf[2].x + buf[2].y : 0.f;      // stage 7 of the pseudo-step: t + dt
+            const bool live6 = buf[1].x != 0.f;
+            const float tz = buf[1].y;
 #pragma unroll
             for (int j = 0; j < 6; ++j) { const float tv = live6 ? stage_time(st, sdt, j + 2) : 0.f; buf[j] = make_float4(tv, tv, tv, tv); }
-            const float tz = live0 ? t0 : 0.f;
             buf[6] = make_float4(tz, tz, tz, tz);
-            buf[7] = make_float4(tx, tx, tx, tx);
         };
         // x = hi + lo (+ <= 2^-24 |x|), both rounded to nearest TF32; column c of the quad -> K-block c, slots 0-3 | 4-7
-        auto convert_store = [&](int g, const float4 (&buf)[8]) {
+        auto convert_store = [&](int g, const float4 (&buf)[7]) {
             unsigned char* st = tsm + (size_t)(g % WGT_STAGES) * WGT_STAGE_BYTES + dst_off;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 float v[8], hi[8], lo[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = (c == 0) ? buf[j].x : (c == 1) ? buf[j].y : (c == 2) ? buf[j].z : buf[j].w;
+                for (int j = 0; j < 7; ++j) v[j] = (c == 0) ? buf[j].x : (c == 1) ? buf[j].y : (c == 2) ? buf[j].z : buf[j].w;
+                v[7] = 0.f;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { hi[j] = tf32_rn(v[j]); lo[j] = tf32_rn(v[j] - hi[j]); }
                 *reinterpret_cast<float4*>(st + c * 256) = make_float4(hi[0], hi[1], hi[2], hi[3]);
@@ -171,7 +173,7 @@ __global__ void __launch_bounds__(WGT_THREADS, 1) wgrad_tc_kernel(const float* _
                 *reinterpret_cast<float4*>(st + WGT_PART_BYTES + c * 256 + 128) = make_float4(lo[4], lo[5], lo[6], lo[7]);
             }
         };
-        auto publish = [&](int g, float4 (&buf)[8]) {
+        auto publish = [&](int g, float4 (&buf)[7]) {
             const int b = g % WGT_STAGES;
             if (aug_t && td) time_row(buf);
             if (g >= WGT_STAGES) mbar_wait(bar_empty(b), (uint32_t)((g / WGT_STAGES - 1) & 1));
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(WGT_THREADS, 1) wgrad_tc_kernel(const float* _
             mbar_arrive_local(bar_ready(b));
         };
         // software pipeline over three register buffers: the loads of stages g+1 and g+2 are in flight while stage g is converted
-        float4 bufA[8], bufB[8], bufC[8];
+        float4 bufA[7], bufB[7], bufC[7];
         if (nstage > 0) issue(0, bufA);
         if (nstage > 1) issue(1, bufB);
         for (int g = 0; g < nstage; g += 3) {

@@ -670,9 +670,11 @@ def test_first_dt_gradient_term(oracle_built, name, D, H, B, act_out, auto, func
     (initial-dt heuristic) stays on the tape.  The extra term -- gradient with detach_dt = "all_but_first" minus the
     frozen-step gradient -- is 1e-7 ... 1e-3 of the gradient, below the Float32 noise of the regulariser part, so it is
     checked on its own: the library's diagnostic mode returns the term alone, and so does the oracle (Float64 cotangents
-    over the Float32 forward).  The term is dL/d(dt_1) * d(dt_1)/d(theta, x); dL/d(dt_1) is a sum of the same cancelling
-    cotangents as the regulariser gradient, so the bar is the one of the gradient tests: <= 1e-3, or 1.5x the CPU Float32
-    adjoint's own error on the term."""
+    over the Float32 forward).  The term is a scalar, dL/d(dt_1), times the direction d(dt_1)/d(theta, x):
+      * the direction (two field VJPs through the Hairer-Wanner heuristic) must agree to 1e-3 after the best rescaling;
+      * the scalar is a sum of the same cancelling O(10) cotangents as the regulariser gradient (a CPU Float32 adjoint gets it
+        to 0.03 ... 27 % on these cases): within 10 %, and -- what matters for the gradient -- the term's absolute error must
+        stay below 1e-5 of the gradient, a tenth of north_star's 1e-4 bar."""
     r = R()
     rng = np.random.default_rng(11)
     p_np = orc.glorot_params(rng, D, H)
@@ -696,6 +698,50 @@ def test_first_dt_gradient_term(oracle_built, name, D, H, B, act_out, auto, func
     full, _, _, _ = o.backward(w, ws, hi=True)
     assert np.abs(tp).max() > 0 and np.abs(tx).max() > 0
     rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()
-    e_p, e_x, c_p, c_x = rel(p.grad.cpu().numpy(), tp), rel(x.grad.cpu().numpy(), tx), rel(cp, tp), rel(cx, tx)
-    note = (e_p, e_x, c_p, c_x, np.abs(tp).max() / np.abs(full).max())
-    assert e_p <= max(1e-3, GRAD_BAR * c_p) and e_x <= max(1e-3, GRAD_BAR * c_x), note
+    gp, gx = p.grad.cpu().numpy().astype(np.float64), x.grad.cpu().numpy().astype(np.float64)
+    tp64, tx64 = tp.astype(np.float64), tx.astype(np.float64)
+    scale = float((gp * tp64).sum() / (tp64 * tp64).sum())
+    note = (scale, rel(gp, tp64), rel(gx, tx64), rel(cp, tp), np.abs(tp).max() / np.abs(full).max())
+    assert rel(gp / scale, tp64) <= 1e-3 and rel(gx / scale, tx64) <= 1e-3, note       # direction
+    assert abs(scale - 1.0) <= 0.1, note                                                # dL/d(dt_1)
+    assert np.abs(gp - tp64).max() <= 1e-5 * np.abs(full).max(), note                   # what reaches the gradient
+
+
+def test_first_dt_gradient_term_chain_saveat(oracle_built):
+    """The same term on the Latent-ODE path (experiments/latent_ode.jl:137-147): Chain field without time input, saveat,
+    AutoTsit5, error + stiffness regulariser.  Here the term also collects the explicit dt of states interpolated inside
+    the first and the last step (u(theta) = uprev + dt * sum_j b_j(theta) k_j, theta frozen)."""
+    r = R()
+    rng = np.random.default_rng(77)
+    D, widths, acts, B = 20, (50, 50, 20), (1, 1, 0), 70
+    p_np = orc.glorot_chain_params(rng, D, widths, bias_scale=0.05)
+    x_np = rng.standard_normal((D, B)).astype(np.float32)
+    saveat = np.unique(np.concatenate([[0.0], np.sort(rng.random(11)), [1.0]]).astype(np.float32))
+    layers, K = [], D
+    for M, a in zip(widths, acts):
+        layers.append(r.Dense(K, M, "tanh" if a else None)); K = M
+    node = r.TrackedNeuralODE(r.Chain("tanh", *layers), [0.0, 1.0], False, True, r.AutoTsit5(), reltol=1.4e-8, abstol=1.4e-8,
+                              saveat=saveat.tolist(), detach_dt="first_term_only")
+    x = torch.from_numpy(x_np).cuda().requires_grad_(True)
+    p = torch.from_numpy(p_np).cuda().requires_grad_(True)
+    res, nfe, sv = node(x, p, func=r.ERROR_PLUS_STIFFNESS)
+    o = orc.Oracle(orc.OracleConfig(D=D, H=max(widths), B=B, alg=1, reg_kind=r.ERROR_PLUS_STIFFNESS.kind, kblock1=D, widths=widths, acts=acts,
+                                    pre_act=1, saveat=saveat.astype(np.float64)))
+    ref = o.forward(x_np, p_np)
+    assert np.array_equal(bits(res.detach().permute(1, 0, 2).cpu().numpy()), bits(ref.usave))
+    w = rng.standard_normal(ref.usave.shape).astype(np.float32)
+    ws = rng.standard_normal(len(ref.saveval)).astype(np.float32)
+    ((res * torch.from_numpy(np.ascontiguousarray(w.transpose(1, 0, 2))).cuda()).sum() + (sv.saveval * torch.from_numpy(ws).cuda()).sum()).backward()
+    torch.cuda.synchronize()
+    zeros = np.zeros((D, B), np.float32)
+    tp, tx, _, _ = o.backward(zeros, ws, hi=True, dusave=w, first_dt_tracked="term")
+    full, _, _, _ = o.backward(zeros, ws, hi=True, dusave=w)
+    gp, gx = p.grad.cpu().numpy().astype(np.float64), x.grad.cpu().numpy().astype(np.float64)
+    tp64, tx64 = tp.astype(np.float64), tx.astype(np.float64)
+    assert np.abs(tp64).max() > 0
+    rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()
+    scale = float((gp * tp64).sum() / (tp64 * tp64).sum())
+    note = (scale, rel(gp, tp64), rel(gx, tx64), np.abs(tp).max() / np.abs(full).max())
+    assert rel(gp / scale, tp64) <= 1e-3 and rel(gx / scale, tx64) <= 1e-3, note
+    assert abs(scale - 1.0) <= 0.1, note
+    assert np.abs(gp - tp64).max() <= 1e-5 * np.abs(full).max(), note
