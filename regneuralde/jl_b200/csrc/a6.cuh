@@ -75,8 +75,13 @@ __device__ __forceinline__ void a6_block_sum(double v, float* scratch_f, double*
 
 // Sum of `v` over the whole (co-resident) grid, returned to every thread: per-CTA partials, a grid barrier, then every CTA
 // adds the partials in the same fixed order.  `slot` selects one of the two partial arrays (two sums per launch).
+// Reference-exact data parallel (P.nranks > 1): the sum runs over all ranks' columns -- block 0 writes this rank's total (as a
+// hi + lo pair of floats) into every rank's exchange buffer, the clusters' lead CTAs arrive on every rank's counter like after a
+// norm of the forward solve (xrank_arrive_wait; xseq continues the sequence number kept in the exchange buffer),
+// and every CTA adds the ranks' totals in rank order.  cluster_lead: this CTA is rank 0 of its cluster; G: CTAs per cluster.
 template <int NT>
-__device__ __forceinline__ double a6_grid_sum(double v, float* scratch_f, const KParams& P, unsigned& bar_gen, int slot) {
+__device__ __forceinline__ double a6_grid_sum(double v, float* scratch_f, const KParams& P, unsigned& bar_gen, int slot,
+                                              const bool cluster_lead = false, const int G = 1, const unsigned xseq = 0) {
     double* part = P.a6_part + (size_t)slot * gridDim.x;
     a6_block_sum<NT>(v, scratch_f, part);
     grid_barrier(P.bar, gridDim.x, bar_gen);
@@ -89,8 +94,27 @@ __device__ __forceinline__ double a6_grid_sum(double v, float* scratch_f, const 
         if (threadIdx.x == 0) scratch[0] = s;
     }
     __syncthreads();
-    const double tot = scratch[0];
+    double tot = scratch[0];
     __syncthreads();
+    if (P.nranks > 1) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            const float hi = (float)tot, lo = (float)(tot - (double)hi);
+            for (int r = 0; r < P.nranks; ++r) {
+                float* dst = reinterpret_cast<float*>(P.peers[r]) + 16 * slot + 2 * P.rank;      // the column-sum area is idle during the backward
+                dst[0] = hi; dst[1] = lo;
+            }
+        }
+        xrank_arrive_wait(P, cluster_lead, xseq, gridDim.x / G);
+        if (threadIdx.x == 0) {
+            const volatile float* src = reinterpret_cast<const volatile float*>(P.peers[P.rank]) + 16 * slot;
+            double s = 0.0;
+            for (int r = 0; r < P.nranks; ++r) s += (double)src[2 * r] + (double)src[2 * r + 1];
+            scratch[0] = s;
+        }
+        __syncthreads();
+        tot = scratch[0];
+        __syncthreads();
+    }
     return tot;
 }
 
@@ -156,7 +180,7 @@ __device__ __forceinline__ double a6_sweep_partial(const KParams& P, const bool 
                 }
             }
         }
-        if (blockIdx.x == 0 && threadIdx.x == 0 && P.dsaveval) {
+        if (blockIdx.x == 0 && threadIdx.x == 0 && P.dsaveval && P.a6_scalar) {
             const float sbar = __ldg(P.dsaveval + s + 1);
             if (P.reg_kind == RNDE_REG_ERR_DT) part += (double)(2.f * w * sbar * sr.eest);
             else if (P.reg_kind == RNDE_REG_STIFF_DT_ABS && P.alg == RNDE_ALG_AUTO_TSIT5) part += (double)(w * sbar * ((sr.eig * sr.dt) >= 0.f ? 1.f : -1.f) * sr.eig);
@@ -186,7 +210,10 @@ __device__ __forceinline__ double a6_sweep_partial(const KParams& P, const bool 
 #define RNDE_A6_TASK_PRE(SA6, CUR, SCR, PARTIAL)                                                                                       \
     do {                                                                                                                               \
         unsigned a6_gen = 0;                                                                                                           \
-        const double a6_tot = a6_grid_sum<NT>((PARTIAL), SCR, P, a6_gen, 0);                                                           \
+        /* sequence number of the cross-rank rounds: read before the first grid barrier, i.e. before anybody can have advanced it */ \
+        const unsigned a6_xb = (P.nranks > 1) ? *(reinterpret_cast<const unsigned*>(P.peers[P.rank]) + P.flag_off + 32) : 0u;           \
+        if (tid == 0) SA6[8] = __uint_as_float(a6_xb);                                                                                 \
+        const double a6_tot = a6_grid_sum<NT>((PARTIAL), SCR, P, a6_gen, 0, rank == 0, G, a6_xb + 1u);                                                           \
         const A6Scal a6_sc = a6_scalars(P, (float)a6_tot);                                                                             \
         if (tid == 0) { SA6[0] = a6_sc.d2bar; SA6[1] = a6_sc.d1bar; SA6[2] = a6_sc.dt0bar; SA6[3] = a6_sc.dt0_free ? 1.f : 0.f; }      \
         const float a6_d2 = P.initdt[2], a6_dt0 = P.initdt[3];                                                                         \
@@ -235,7 +262,10 @@ __device__ __forceinline__ double a6_sweep_partial(const KParams& P, const bool 
             P.steps[P.nsteps] = sr;                                                                                                    \
         }                                                                                                                              \
         unsigned a6_gen = 1;                                                                                                           \
-        const double a6_tot2 = a6_grid_sum<NT>(a6_part, SCR, P, a6_gen, 1);                                                            \
+        const unsigned a6_xb = __float_as_uint(SA6[8]);                                                                                \
+        const double a6_tot2 = a6_grid_sum<NT>(a6_part, SCR, P, a6_gen, 1, rank == 0, G, a6_xb + 2u);                                  \
+        if (P.nranks > 1 && blockIdx.x == 0 && tid == 0)      /* two more cross-rank rounds happened: keep the sequence number */  \
+            *(reinterpret_cast<unsigned*>(P.peers[P.rank]) + P.flag_off + 32) = a6_xb + 2u;                                                            \
         float a6_dt0bar = SA6[2] + (float)a6_tot2, a6_d0bar = 0.f, a6_d1bar = SA6[1];                                                  \
         if (SA6[3] != 0.f) { a6_d0bar = a6_dt0bar * a6_dt0 / a6_d0; a6_d1bar -= a6_dt0bar * a6_dt0 / a6_d1; }                           \
         const float a6_c1 = (a6_d1bar != 0.f && a6_d1 > 0.f) ? a6_d1bar / (cntf * a6_d1) : 0.f;                                         \

@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4_kernel(const KParams P) {
             // weight of this step's explicit dt in dL/d(dt_1) (first step: +1, last step when it was cut: -1) and of its start time
             wdir = P.a6 ? ((s == 0 ? 1.f : 0.f) - (s == P.nsteps - 1 ? P.initdt[5] : 0.f)) : 0.f;
             wshift = (P.a6 && s >= 1) ? 1.f : 0.f;
-            if (wdir != 0.f && sbar != 0.f && blockIdx.x == 0 && tid == 0) {
+            if (wdir != 0.f && sbar != 0.f && blockIdx.x == 0 && tid == 0 && P.a6_scalar) {
                 if (P.reg_kind == RNDE_REG_ERR_DT) dacc += wdir * sbar * EEst;
                 else if (P.reg_kind == RNDE_REG_STIFF_DT_ABS && P.alg == RNDE_ALG_AUTO_TSIT5) dacc += wdir * sbar * ((eig * dt) >= 0.f ? 1.f : -1.f) * eig;
                 else if (P.reg_kind == RNDE_REG_ERR_PLUS_STIFF) { const float e = EEst * dt; if (!(e == 0.f || e != e)) dacc += wdir * sbar * EEst; }

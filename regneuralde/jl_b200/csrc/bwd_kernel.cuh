@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(NT, 1) bwd_kernel(const KParams P) {
         // weight of this step's explicit dt in dL/d(dt_1): the first step takes dt_1, the last one shrinks by it when it was cut
         const float wdir = P.a6 ? ((s == 0 ? 1.f : 0.f) - (s == P.nsteps - 1 ? clampN : 0.f)) : 0.f;
         const float wshift = (P.a6 && s >= 1) ? 1.f : 0.f;      // ... and every later step starts dt_1 later
-        if (wdir != 0.f && sbar != 0.f && blockIdx.x == 0 && tid == 0) {
+        if (wdir != 0.f && sbar != 0.f && blockIdx.x == 0 && tid == 0 && P.a6_scalar) {
             if (P.reg_kind == RNDE_REG_ERR_DT) dacc += (double)(wdir * sbar * EEst);
             else if (P.reg_kind == RNDE_REG_STIFF_DT_ABS && P.alg == RNDE_ALG_AUTO_TSIT5) dacc += wdir * sbar * ((eig * dt) >= 0.f ? 1.f : -1.f) * eig;
             else if (P.reg_kind == RNDE_REG_ERR_PLUS_STIFF) { const float e = EEst * dt; if (!(e == 0.f || e != e)) dacc += wdir * sbar * EEst; }

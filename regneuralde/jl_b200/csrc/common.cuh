@@ -52,6 +52,7 @@ struct KParams {
     const float* forced_dt; int n_forced;
     // Appendix A.6 with the first dt on the tape (rnde_set_detach, a6.cuh): dt_1 = initial_dt(theta, x) is differentiated
     int a6;                 // forward: tape the evaluation of the initial-dt heuristic; sweep: accumulate dL/d(dt_1)
+    int a6_scalar;          // this rank adds the terms that exist once per solve (saved-value cotangent x explicit dt): rank 0 in the exact mode
     int a6_mode;            // bwd_kernel: 0 = sweep, 1 = VJP of f(u0 + dt0 f0, t0 + dt0), 2 = VJP of f0 added to record 0
     int rec_init;           // tape record the forward writes the initial-dt evaluation to (copied behind the last step for wgrad)
     int rec_x;              // record the adjoint of that evaluation is written to: 6 * nsteps + 6 (stage 7 of a pseudo-step)

@@ -579,6 +579,7 @@ static void fill_params(const rnde_handle* h, KParams& P) {
     P.forced_dt = h->forced_dev; P.n_forced = h->n_forced;
     P.a6 = (c.need_backward && h->detach != RNDE_DETACH_ALL && h->n_forced == 0 && c.csq_extra == 0) ? 1 : 0;
     P.rec_init = 1 + 6 * (c.tape_capacity + 1);
+    P.a6_scalar = (c.dist_mode == RNDE_DIST_EXACT && c.nranks > 1 && c.rank != 0) ? 0 : 1;
     P.initdt = h->initdt; P.a6_part = h->a6_part; P.a6_sum = h->a6_sum; P.a6_u1bar = h->a6_buf; P.a6_f0 = h->a6_f0; P.a6_zb = h->a6_zb; P.a6_tau = h->a6_tau; P.a6_kc = h->a6_kc;
 }
 
@@ -715,10 +716,10 @@ static int backward_impl(rnde_handle* h, const float* du_dev, const float* dusav
     static const bool force_ffma = getenv("RNDE_WGRAD_FFMA") != nullptr;
     const bool wg_tc = h->NP == 16 && !force_ffma && h->cfg.n_layers == 0;
     const bool wg_slot = wg_tc && s.naccept >= 2;      // ... in the spare K slot of the SECOND step's group
-    // the cluster-4 sweeps differentiate the heuristic themselves (one more VJP between two grid-wide sums, a6.cuh); the other
-    // variants, and the reference-exact mode whose sums run over all ranks, launch the generic kernel twice after the sweep
+    // the cluster-4 sweeps differentiate the heuristic themselves (one more VJP between two grid-wide sums -- over all ranks in the
+    // reference-exact mode --, a6.cuh); the other variants launch the generic kernel twice after the sweep
     static const bool a6_external = getenv("RNDE_A6_EXTERNAL") != nullptr;      // developer switch: always the separate launches
-    const bool a6_inkernel = a6 && !a6_external && h->variant == RNDE_KERNEL_CLUSTER4 && !(h->cfg.nranks > 1 && h->cfg.dist_mode == RNDE_DIST_EXACT);
+    const bool a6_inkernel = a6 && !a6_external && h->variant == RNDE_KERNEL_CLUSTER4;
     if (a6_inkernel) { P.a6 = (h->detach == RNDE_DETACH_FIRST_TERM_ONLY) ? 3 : 2; P.rec_x = wg_slot ? P.rec_init : 6 * s.naccept + 6; }
     const size_t tileN = (size_t)h->Q * h->NP;
     const size_t recD = tileN * h->cfg.state_dim;

@@ -41,9 +41,10 @@ def count(text, mnemonic):
 
 
 def test_reverse_sweep_and_weight_gradients_run_on_tcgen05(sass):
-    b = body(sass, "bwd4tc_kernel")
-    assert count(b, "UTCHMMA") >= 8 and "LDTM" in b and "UTCBAR" in b          # tcgen05.mma kind::f16, tcgen05.ld, tcgen05.commit
-    assert "UBLKCP" in b                                                       # delta tiles leave as bulk stores
+    for inst in ("bwd4tc_kernelILb1E", "bwd4tc_kernelILb0E"):                  # with / without the first-dt additions (a6.cuh)
+        b = body(sass, inst)
+        assert count(b, "UTCHMMA") >= 8 and "LDTM" in b and "UTCBAR" in b      # tcgen05.mma kind::f16, tcgen05.ld, tcgen05.commit
+        assert "UBLKCP" in b                                                   # delta tiles leave as bulk stores
     w = body(sass, "wgrad_tc_kernelE")
     assert count(w, "UTCHMMA") >= 3 and "LDTM" in w                            # 3xTF32 split products
     for k, v in sass.items():                                                  # no legacy warp-level MMA anywhere

@@ -27,7 +27,8 @@ for it in range(3):
     res, nfe, sv = node(x, p, func=R.ERROR_ESTIMATE)
     torch.cuda.synchronize(); t1 = time.time()
     ws = torch.ones_like(sv.saveval)
-    loss = (res * torch.from_numpy(np.ascontiguousarray(w_np[:, rank * Bl:(rank + 1) * Bl])).cuda()).sum() + (sv.saveval * ws).sum() / world
+    # the saved values are shared by all ranks: every rank applies their FULL cotangent to its own columns, the gradients are summed
+    loss = (res * torch.from_numpy(np.ascontiguousarray(w_np[:, rank * Bl:(rank + 1) * Bl])).cuda()).sum() + (sv.saveval * ws).sum()
     loss.backward()
     g = p.grad.clone(); dist.all_reduce(g)
     torch.cuda.synchronize(); t2 = time.time()
@@ -43,4 +44,18 @@ if rank == 0:
           "| u bit-equal", np.array_equal(bits(u), bits(ref.u)), "| saveval bit-equal", np.array_equal(bits(sv.saveval.detach().cpu().numpy()), bits(ref.saveval)))
     dp, _, _, _ = o.backward(w_np, np.ones(len(ref.saveval), np.float32), hi=True)
     print("gradient (sum over ranks) vs oracle: relerr %.3e" % (np.abs(g.cpu().numpy() - dp).max() / np.abs(dp).max()))
+    dp0, _, _, _ = o.backward(w_np, np.ones(len(ref.saveval), np.float32), hi=True, first_dt_tracked=False)
+    print("   (against the frozen-step gradient: %.3e; first-dt term / gradient %.1e)" % (np.abs(g.cpu().numpy() - dp0).max() / np.abs(dp0).max(), np.abs(dp - dp0).max() / np.abs(dp).max()))
+# the first-dt term alone (rnde_set_detach diagnostic mode): its scalar dL/d(dt_1) is a sum over ALL ranks' columns
+node2 = R.TrackedNeuralODE(model, [0.0, 1.0], True, True, R.Tsit5(), reltol=1.4e-8, abstol=1.4e-8, dist_mode=L.DIST_EXACT, rank=rank, world=world,
+                           detach_dt="first_term_only")
+p2 = torch.from_numpy(p_np).cuda().requires_grad_(True)
+res2, _, sv2 = node2(x, p2, func=R.ERROR_ESTIMATE)
+((res2 * torch.from_numpy(np.ascontiguousarray(w_np[:, rank * Bl:(rank + 1) * Bl])).cuda()).sum() + sv2.saveval.sum()).backward()
+g2 = p2.grad.clone(); dist.all_reduce(g2)
+if rank == 0:
+    tp, _, _, _ = o.backward(w_np, np.ones(len(ref.saveval), np.float32), hi=True, first_dt_tracked="term")
+    a, b = g2.cpu().numpy().astype(np.float64), tp.astype(np.float64)
+    sc = float((a * b).sum() / (b * b).sum())
+    print("first-dt term alone (sum over ranks) vs oracle: scale %.5f, direction relerr %.2e" % (sc, np.abs(a / sc - b).max() / np.abs(b).max()))
 dist.destroy_process_group()
