@@ -137,7 +137,7 @@ __device__ __noinline__ double a6_direct_term(const float* kbase, size_t rstride
 
 // This thread's part of dL/d(dt_1) for the tensor-core sweep, which keeps its hot loop free of it: the sweep only leaves
 //   a6_zb  : the cotangent of every stage input z_i of the first and of the last step ([slot 0-5 | 6-11][tile][row][NP]), and
-//   a6_tau : per record and CTA the time cotangents sum W2[:, t] . delta2 (this CTA's rows) and sum W1[:, t] . delta1, which the
+//   a6_tau : per record, CTA and column the time cotangents sum W2[:, t] . delta2 (this CTA's rows) and sum W1[:, t] . delta1, which the
 //            tensor cores produce in one spare accumulator row each;
 // everything else follows from the tape:
 //   a6_kc  : copies of k_1..k_6 of those two steps, taken by the host before the sweep replaces k by delta2 on the tape
@@ -189,12 +189,13 @@ __device__ __forceinline__ double a6_sweep_partial(const KParams& P, const bool 
     }
     if (P.td) {
 #pragma unroll 1
-        for (int rec = 1 + (int)threadIdx.x; rec <= 6 * N; rec += (int)blockDim.x) {
+        for (int it = (int)threadIdx.x; it < 6 * N * 16; it += (int)blockDim.x) {      // (record, column) pairs
+            const int rec = 1 + (it >> 4), c = it & 15;
             const int s = (rec - 1) / 6, i = (rec - 1) % 6 + 2;
             const float wdir = (s == 0 ? 1.f : 0.f) - (s == N - 1 ? clampN : 0.f);
             const float wt = (s >= 1 ? 1.f : 0.f) + wdir * ts_c(i);
-            const float* tp = P.a6_tau + (((size_t)rec * P.Q + q) * G + rank) * 2;
-            part += (double)(wt * (__ldcg(tp) + (rank == 0 ? __ldcg(tp + 1) : 0.f)));
+            const float* tp = P.a6_tau + (((size_t)rec * P.Q + q) * G + rank) * 32;
+            part += (double)(wt * (__ldcg(tp + c) + (rank == 0 ? __ldcg(tp + 16 + c) : 0.f)));
         }
     }
     return part;

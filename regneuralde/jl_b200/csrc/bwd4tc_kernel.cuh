@@ -108,7 +108,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #ifdef RNDE_A6_COMPILED_OUT      // developer switch (tools/sweep_variants.py): what the first-dt additions cost the hot loop
 #define A6ON false
 #else
-#define A6ON (A6C && P.a6 != 0)
+#define A6ON A6C      // the <true> instantiation is only launched with P.a6 != 0
 #endif
 #ifdef RNDE_A6_NO_TAU
 #define A6TAU false
@@ -340,11 +340,10 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
                     }
                 }
             const int m = quad * 32 + lane;
-            if (m == H && A6TAU) {      // time cotangent of layer 2, this CTA's rows (a6.cuh): kept per record, summed in the a6 task
-                float t = 0.f;
+            if (m == H && A6TAU) {      // time cotangent of layer 2, this CTA's rows (a6.cuh): kept per record and column, summed in the a6 task
+                float4* tp = reinterpret_cast<float4*>(P.a6_tau + (((size_t)rec * P.Q + q) * G + rank) * 32);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) t += v[j];
-                P.a6_tau[(((size_t)rec * P.Q + q) * G + rank) * 2] = t;
+                for (int c4 = 0; c4 < 4; ++c4) tp[c4] = make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
             }
             if (m < H) {
                 const int d = m / HS, ml = m - d * HS;
@@ -448,10 +447,9 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
                     }
                 }
             if (row == R && A6TAU) {      // time cotangent of layer 1 (the same in every CTA of the cluster)
-                float t = 0.f;
+                float4* tp = reinterpret_cast<float4*>(P.a6_tau + (((size_t)rec * P.Q + q) * G + rank) * 32 + 16);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) t += v[j];
-                P.a6_tau[(((size_t)rec * P.Q + q) * G + rank) * 2 + 1] = t;
+                for (int c4 = 0; c4 < 4; ++c4) tp[c4] = make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
             }
             if (row < R) {
 #pragma unroll
@@ -622,8 +620,8 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
         }
         vjp(cur, zb, rec, rec_next);
         if (a6task) {      // its time cotangent: the two sums the tensor cores left for this CTA
-            const float* tp = P.a6_tau + (((size_t)rec * P.Q + q) * G + rank) * 2;
-            RNDE_A6_TASK_POST(sA6, zb, sPart, (tid == 0 && td) ? (double)(__ldcg(tp) + (rank == 0 ? __ldcg(tp + 1) : 0.f)) : 0.0);
+            const float* tp = P.a6_tau + (((size_t)rec * P.Q + q) * G + rank) * 32;
+            RNDE_A6_TASK_POST(sA6, zb, sPart, (tid < 16 && td) ? (double)(__ldcg(tp + tid) + (rank == 0 ? __ldcg(tp + 16 + tid) : 0.f)) : 0.0);
             continue;
         }
         if (last) {

@@ -63,7 +63,7 @@ struct KParams {
     const float* a6_f0;     // [tile][row][NP] copy of record 0's k = f0, taken before the sweep replaces it by delta2
     float* a6_zb;           // tensor-core sweep: cotangents of the stage inputs of the first / last step, [12][tile][row][NP]
     const float* a6_kc;     // tensor-core sweep: copies of k_1..k_6 of the first / last step, [12][tile][row][NP]
-    float* a6_tau;          // tensor-core sweep: per record and CTA the two time cotangents, [rec][Q][G][2]
+    float* a6_tau;          // tensor-core sweep: per record and CTA the two time cotangents, [rec][Q][G][2][16]
     // chain field (chain.cuh): layer widths / activations, pre-activation, tape rows per column, shared-memory offsets (floats)
     int n_layers; int lw[8]; int la[8]; int pre_act; int hrows; int chain_np; int oCW, oCA, oCB, oCH;
     // FFJORD field (csq.cuh): Hutchinson noise ((D - csq_extra) x B, column-major), augmented rows, shared-memory offset of its region

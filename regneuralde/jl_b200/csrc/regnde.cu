@@ -456,7 +456,7 @@ extern "C" int rnde_create(const rnde_config* cfg, rnde_handle** out) {
         if (h->variant == RNDE_KERNEL_CLUSTER4) {      // what the tensor-core sweep leaves for the first-dt term (a6.cuh)
             if (cudaMalloc(&h->a6_zb, sizeof(float) * 12 * tile * D) != cudaSuccess) return fail("cudaMalloc a6_zb");
             if (cudaMalloc(&h->a6_kc, sizeof(float) * 12 * tile * D) != cudaSuccess) return fail("cudaMalloc a6_kc");
-            if (cudaMalloc(&h->a6_tau, sizeof(float) * nrec * h->Q * h->G * 2) != cudaSuccess) return fail("cudaMalloc a6_tau");
+            if (cudaMalloc(&h->a6_tau, sizeof(float) * nrec * h->Q * h->G * 32) != cudaSuccess) return fail("cudaMalloc a6_tau");
         }
         if (cudaMalloc(&h->tapeZ, sizeof(float) * nrec * tile * D) != cudaSuccess) return fail("cudaMalloc tapeZ (lower tape_capacity?)");
         if (cudaMalloc(&h->tapeK, sizeof(float) * nrec * tile * D) != cudaSuccess) return fail("cudaMalloc tapeK (lower tape_capacity?)");
