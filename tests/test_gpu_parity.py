@@ -745,3 +745,34 @@ def test_first_dt_gradient_term_chain_saveat(oracle_built):
     assert rel(gp / scale, tp64) <= 1e-3 and rel(gx / scale, tx64) <= 1e-3, note
     assert abs(scale - 1.0) <= 0.1, note
     assert np.abs(gp - tp64).max() <= 1e-5 * np.abs(full).max(), note
+
+
+@pytest.mark.parametrize("seed,scale,tol", [(20, 6.0, 1e-3), (6, 8.0, 1e-4)])
+def test_first_dt_gradient_term_after_a_rejected_first_attempt(oracle_built, seed, scale, tol):
+    """A rejected attempt divides dt by a detached factor: after rejected FIRST attempts the first accepted step is
+    kappa * initial_dt(theta, x), kappa != 1 (a6.cuh takes kappa = dt of the first accepted step / dt_init)."""
+    r = R()
+    rng = np.random.default_rng(seed)
+    D, H, B = 3, 8, 2
+    p_np = (orc.glorot_params(rng, D, H, dtype=np.float64) * scale).astype(np.float32)
+    x_np = (rng.random((D, B)) * 2).astype(np.float32)
+    model = r.TDChain(r.Dense(D + 1, H, "tanh"), r.Dense(H + 1, D, None))
+    node = r.TrackedNeuralODE(model, [0.0, 1.0], True, True, r.Tsit5(), reltol=tol, abstol=tol, detach_dt="first_term_only")
+    p = torch.from_numpy(p_np).cuda().requires_grad_(True)
+    x = torch.from_numpy(x_np).cuda().requires_grad_(True)
+    res, nfe, sv = node(x, p, func=r.ERROR_ESTIMATE)
+    o = orc.Oracle(orc.OracleConfig(D=D, H=H, B=B, act2=orc.ACT_ID, alg=0, reg_kind=orc.REG_ERR_DT, kblock1=D, abstol=tol, reltol=tol, arith=node.arith))
+    ref = o.forward(x_np, p_np)
+    assert ref.accept_log[0] == 0 and ref.nreject >= 1                      # the case this test exists for
+    assert (nfe, node.last_stats.naccept, node.last_stats.nreject) == (ref.nf, ref.naccept, ref.nreject)
+    assert np.array_equal(bits(res.detach().cpu().numpy()), bits(ref.u))
+    w = rng.standard_normal((D, B)).astype(np.float32)
+    ws = rng.standard_normal(len(ref.saveval)).astype(np.float32)
+    ((res * torch.from_numpy(w).cuda()).sum() + (sv.saveval * torch.from_numpy(ws).cuda()).sum()).backward()
+    torch.cuda.synchronize()
+    tp, tx, _, _ = o.backward(w, ws, hi=True, first_dt_tracked="term")
+    gp, tp64 = p.grad.cpu().numpy().astype(np.float64), tp.astype(np.float64)
+    scale_ = float((gp * tp64).sum() / (tp64 * tp64).sum())
+    rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()
+    assert rel(gp / scale_, tp64) <= 1e-3 and abs(scale_ - 1.0) <= 0.1, (scale_, rel(gp, tp64))
+    assert rel(x.grad.cpu().numpy() / scale_, tx.astype(np.float64)) <= 1e-3

@@ -174,3 +174,33 @@ def test_fixed24_arithmetic_is_a_rounding_of_the_same_field(oracle_built):
     r1 = orc.Oracle(orc.OracleConfig(D=D, H=H, B=B, reg_kind=orc.REG_ERR_DT, kblock1=98, arith=1)).forward(x, p)
     assert np.abs(r1.u - r0.u).max() <= 2e-6 * np.abs(r0.u).max()
     assert abs(r1.nf - r0.nf) <= 0.1 * r0.nf
+
+
+@pytest.mark.parametrize("seed,scale,tol", [(20, 6.0, 1e-3), (6, 8.0, 1e-4), (34, 8.0, 1e-4)])
+def test_first_dt_term_with_a_rejected_first_attempt(oracle_built, seed, scale, tol):
+    """Appendix A.6: a rejected attempt divides dt by a detached factor, so after rejected FIRST attempts the first accepted step
+    is kappa * initial_dt(theta, x) with a constant kappa != 1 -- the C oracle's first-dt term (kappa = dt_accepted / dt_init)
+    against autograd through the torch oracle, which simply keeps the tracked dt through its retries."""
+    torch.set_default_dtype(torch.float64)
+    try:
+        rng = np.random.default_rng(seed)
+        D, H, B = 3, 8, 2
+        cfg = orc.OracleConfig(D=D, H=H, B=B, act2=orc.ACT_ID, alg=0, reg_kind=orc.REG_ERR_DT, abstol=tol, reltol=tol)
+        p = orc.glorot_params(rng, D, H, dtype=np.float64) * scale
+        x = rng.random((D, B)) * 2
+        o = orc.Oracle(cfg, f64=True)
+        r = o.forward(x, p)
+        assert r.accept_log[0] == 0 and r.nreject >= 1                      # the case this test exists for
+        pt = torch.tensor(p, requires_grad=True); xt = torch.tensor(x, requires_grad=True)
+        tr = to.solve(xt, pt, D=D, H=H, act2_tanh=False, reg_kind=orc.REG_ERR_DT, abstol=tol, reltol=tol, detach="all_but_first")
+        assert (r.nf, r.naccept, r.nreject) == (tr.nf, tr.naccept, tr.nreject)
+        w = rng.standard_normal((D, B)); ws = rng.standard_normal(len(r.saveval))
+        loss = (tr.u * torch.tensor(w)).sum() + (torch.stack(tr.saveval) * torch.tensor(ws)).sum()
+        gp, gx = torch.autograd.grad(loss, [pt, xt])
+        dp, dx, _, _ = o.backward(w, ws, first_dt_tracked=True)
+        term, _, _, _ = o.backward(w, ws, first_dt_tracked="term")
+        assert np.abs(term).max() > 1e-6 * np.abs(dp).max()                 # the term is not negligible here
+        assert np.abs(dp - gp.numpy()).max() <= 1e-7 * np.abs(gp.numpy()).max()
+        assert np.abs(dx - gx.numpy()).max() <= 1e-7 * np.abs(gx.numpy()).max()
+    finally:
+        torch.set_default_dtype(torch.float32)
