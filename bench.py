@@ -443,6 +443,30 @@ def run_ours(args):
             extra["strong_scaling"] = dict(summarise(ts, rs, K), global_batch=B, per_gpu_batch=Bl,
                                            note="reference-exact mode on the columns of one global batch of 512")
             del ts
+            # what "reference-exact" claims, checked where the driver sees it: the same global batch of 512 solved once on rank 0
+            # alone and by all ranks together (rank r: columns [r*B/R, (r+1)*B/R)), initial weights, one loss + gradient call each
+            tc = Trainer("strong", Bl, [xs0[0][:, sl]], [ys0[0][:, sl]])
+            oc = tc.clf.loss_and_gradient(tc.xs[0], tc.ys[0], lam=LAMBDA, func=R.ERROR_ESTIMATE, agg="mean", ce_scale=1.0 / world)
+            tc.node.allreduce_(oc["g2"], oc["g3"])
+            nfe_x, nacc_x = int(tc.node.last_stats.nf), int(tc.node.last_stats.naccept)
+            lg = oc["logits"].t().contiguous()                          # (Bl, classes): this rank's columns
+            lgs = [torch.empty_like(lg) for _ in range(world)]
+            dist.all_gather(lgs, lg)
+            if rank == 0:
+                t1 = Trainer("single", B, [xs0[0]], [ys0[0]])
+                o1 = t1.clf.loss_and_gradient(t1.xs[0], t1.ys[0], lam=LAMBDA, func=R.ERROR_ESTIMATE, agg="mean")
+                rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+                extra["exact_check"] = {
+                    "global_batch": B, "nfe": [nfe_x, int(t1.node.last_stats.nf)], "naccept": [nacc_x, int(t1.node.last_stats.naccept)],
+                    "steps_identical": nfe_x == int(t1.node.last_stats.nf) and nacc_x == int(t1.node.last_stats.naccept),
+                    "regulariser_bit_identical": bool(torch.equal(oc["reg"], o1["reg"])),
+                    "logits_bit_identical": bool(torch.equal(torch.cat(lgs, 0), o1["logits"].t().contiguous())),
+                    "grad_relerr_vs_single_solve": {"node": rel(oc["g2"], o1["g2"]), "head": rel(oc["g3"], o1["g3"])},
+                    "note": "all ranks together (reference-exact mode, summed gradients) against rank 0 solving the 512 batch alone; the node gradient "
+                            "differs by the Float32 summation noise of the regulariser part (grad_check.c_cpu32 is its size); "
+                            "tools/dist_exact_check.py compares states and saved values bit by bit and the gradient with the oracle"}
+                del t1
+            del tc
 
     if rank == 0:
         main = summarise(tr, res, K)
