@@ -281,7 +281,14 @@ __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, int ns
         const int stage0 = sp * per, stage1 = min(NS, stage0 + per);
         const int nstage = max(stage1 - stage0, 0);
         const int nchunk = (nstage + flush - 1) / flush;
-        for (int ch = 0; ch < nchunk; ++ch) s += (double)partial[(((size_t)sp * WGT_MAXCHUNK + ch) * Naug + n) * M + m];
+        // all chunk loads of a split in flight at once; the additions keep their order.  (Two splits at once -- 32 values -- spill
+        // and triple the time: measured.)
+        const float* pp = partial + (((size_t)sp * WGT_MAXCHUNK) * Naug + n) * M + m;
+        float v[WGT_MAXCHUNK];
+#pragma unroll
+        for (int ch = 0; ch < WGT_MAXCHUNK; ++ch) v[ch] = (ch < nchunk) ? __ldcs(pp + (size_t)ch * Naug * M) : 0.f;
+#pragma unroll
+        for (int ch = 0; ch < WGT_MAXCHUNK; ++ch) if (ch < nchunk) s += (double)v[ch];
     }
     if (n < Nrows) outW[(size_t)M * n + m] = (float)s;
     else if (n == Nrows) { if (td) outW[(size_t)M * Nrows + m] = (float)s; }
