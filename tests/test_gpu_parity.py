@@ -776,3 +776,45 @@ def test_first_dt_gradient_term_after_a_rejected_first_attempt(oracle_built, see
     rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()
     assert rel(gp / scale_, tp64) <= 1e-3 and abs(scale_ - 1.0) <= 0.1, (scale_, rel(gp, tp64))
     assert rel(x.grad.cpu().numpy() / scale_, tx.astype(np.float64)) <= 1e-3
+
+
+SHORT_CASES = [
+    # name, D, H, B, act_out, variant, tol: two accepted steps (both instrumented by the first-dt term) and ONE (dt_1 = t1 - t0: a constant)
+    ("toy, 2 steps", 2, 10, 5, 0, 0, 0.3),
+    ("toy, 1 step", 2, 10, 5, 0, 0, 100.0),
+    ("mnist cluster4, 2 steps", 784, 100, 16, 1, 4, 0.5),
+    ("mnist cluster4, 1 step", 784, 100, 16, 1, 4, 1000.0),
+]
+
+
+@pytest.mark.parametrize("name,D,H,B,act_out,variant,tol", SHORT_CASES, ids=[c[0] for c in SHORT_CASES])
+def test_gradient_of_very_short_solves(oracle_built, name, D, H, B, act_out, variant, tol):
+    """Edge cases of the first-dt term (a6.cuh): the first step is also the last one, or the only one (then dt_1 is the whole
+    interval, a constant, and the term vanishes); the extra record must still find its place in the weight-gradient kernels."""
+    r = R()
+    rng = np.random.default_rng(5)
+    p_np = orc.glorot_params(rng, D, H)
+    x_np = rng.random((D, B), dtype=np.float32)
+    model = r.TDChain(r.Dense(D + 1, H, "tanh"), r.Dense(H + 1, D, "tanh" if act_out else None))
+    node = r.TrackedNeuralODE(model, [0.0, 1.0], True, True, r.Tsit5(), reltol=tol, abstol=tol, kernel_variant=variant)
+    p = torch.from_numpy(p_np).cuda().requires_grad_(True)
+    x = torch.from_numpy(x_np).cuda().requires_grad_(True)
+    res, nfe, sv = node(x, p, func=r.ERROR_ESTIMATE)
+    cfg = oracle_cfg(D, H, B, act_out, 0, r.ERROR_ESTIMATE.kind, arith=node.arith)
+    cfg.abstol = cfg.reltol = tol
+    o = orc.Oracle(cfg)
+    ref = o.forward(x_np, p_np)
+    assert ref.naccept == (1 if "1 step" in name else 2) and node.last_stats.naccept == ref.naccept
+    assert np.array_equal(bits(res.detach().cpu().numpy()), bits(ref.u))
+    w = rng.standard_normal((D, B)).astype(np.float32)
+    ws = rng.standard_normal(len(ref.saveval)).astype(np.float32)
+    ((res * torch.from_numpy(w).cuda()).sum() + (sv.saveval * torch.from_numpy(ws).cuda()).sum()).backward()
+    torch.cuda.synchronize()
+    dp_hi, dx_hi, _, _ = o.backward(w, ws, hi=True)
+    term, _, _, _ = o.backward(w, ws, hi=True, first_dt_tracked="term")
+    if "1 step" in name:
+        assert np.abs(term).max() == 0.0
+    rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()
+    c_p, c_x = cpu32_noise(o, w, ws, n=3)
+    e_p, e_x = rel(p.grad.cpu().numpy(), dp_hi), rel(x.grad.cpu().numpy(), dx_hi)
+    assert e_p <= max(1e-4, GRAD_BAR * c_p) and e_x <= max(1e-4, GRAD_BAR * c_x), (e_p, c_p, e_x, c_x, np.abs(term).max() / np.abs(dp_hi).max())
