@@ -1,6 +1,7 @@
 """Small end-to-end cases for compute-sanitizer (memcheck / racecheck / synccheck):
     compute-sanitizer --tool memcheck python tools/sanitize_cases.py [case ...]
-cases: toy (CTA variant), stream, mnist (cluster-4 forward, tensor-core sweep, tcgen05 weight gradients), cluster8, chain (chain field + saveat), gru."""
+cases: toy (CTA variant), stream, mnist (cluster-4 forward, tensor-core sweep, tcgen05 weight gradients), ffma4 (FFMA sweep),
+cluster8, chain (chain field + saveat), gru, sde.  All backward passes include the first-dt term (a6.cuh), the default."""
 import sys
 import numpy as np
 import torch
@@ -8,7 +9,7 @@ sys.path.insert(0, ".")
 import regneuralde.jl_b200 as r
 from oracle import orc
 
-cases = sys.argv[1:] or ["toy", "stream", "mnist", "cluster8", "chain", "gru"]
+cases = sys.argv[1:] or ["toy", "stream", "mnist", "ffma4", "cluster8", "chain", "gru", "sde"]
 rng = np.random.default_rng(0)
 
 
@@ -30,6 +31,8 @@ for c in cases:
         print(c, tdchain(2, 10, 9, 2, r.AutoTsit5(), r.ERROR_PLUS_STIFFNESS, act_out=False))
     elif c == "mnist":
         print(c, tdchain(784, 100, 20, 4, r.AutoTsit5(), r.ERROR_PLUS_STIFFNESS))
+    elif c == "ffma4":      # cluster-4 forward with the FFMA sweep (shape outside the tensor-core sweep's range)
+        print(c, tdchain(200, 37, 20, 4, r.AutoTsit5(), r.STIFFNESS_ESTIMATE, act_out=False))
     elif c == "cluster8":
         print(c, tdchain(784, 100, 33, 3, r.Tsit5(), r.ERROR_ESTIMATE))
     elif c == "chain":
@@ -42,6 +45,14 @@ for c in cases:
         res, nfe, sv = node(x, p, func=r.ERROR_ESTIMATE)
         (res.sum() + sv.saveval.sum()).backward(); torch.cuda.synchronize()
         print(c, nfe)
+    elif c == "sde":
+        D, H, B = 32, 64, 24
+        nsde = r.TrackedNeuralDSDE(r.Chain(r.Dense(D, H, "tanh"), r.Dense(H, D, None)), r.Dense(D, D, None), [0.0, 0.2], True, r.SOSRI())
+        x = torch.randn(D, B, device="cuda")
+        with torch.no_grad():
+            out = nsde(x, nsde.p, func=r.ERROR_ESTIMATE)
+        torch.cuda.synchronize()
+        print(c, out[1], out[2])
     elif c == "gru":
         gru = r.LatentGRU(5, 6, 4)
         x = torch.randn(11, 5, 6, device="cuda"); p = gru.p.clone().requires_grad_(True)
