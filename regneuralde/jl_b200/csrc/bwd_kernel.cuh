@@ -14,6 +14,8 @@
 #include "common.cuh"
 #include "chain.cuh"
 #include "a6.cuh"
+#include "csq_bwd.cuh"
+#include "wgrad_kernel.cuh"      // rec_time
 
 namespace rnde {
 
@@ -38,7 +40,8 @@ __host__ __device__ inline BwdLayout make_bwd_layout(int G, int NP, bool WS, int
     return L;
 }
 
-template <int G, int NP, int TM, bool WS, int NT>
+// FIELD: 0 = the 2-layer time-concatenated field or a chain field; 1 = the FFJORD field (csq_bwd.cuh)
+template <int G, int NP, int TM, bool WS, int NT, int FIELD = 0>
 __global__ void __launch_bounds__(NT, 1) bwd_kernel(const KParams P) {
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -79,7 +82,15 @@ __global__ void __launch_bounds__(NT, 1) bwd_kernel(const KParams P) {
     cv.L = P.n_layers; cv.D = D; cv.NP = NP; cv.hrows = P.hrows; cv.w = P.lw; cv.a = P.la; cv.pre = P.pre_act;
     cv.sW = smem + P.oCW; cv.sA = smem + P.oCA; cv.sB = smem + P.oCB; cv.sH = smem + P.oCH;
     if (chain) for (int e = tid; e < P.chain_np; e += NT) smem[P.oCW + e] = __ldg(P.p + e);
-    if constexpr (WS) if (!chain) {
+    if constexpr (FIELD == 1) {      // noise tile of this CTA's columns, [row][NP] like the state (as in fwd_kernel)
+        const int Dz = D - P.csq_extra;
+        float* sE = smem + P.oCS;
+        for (int e = tid; e < Dz * NP; e += NT) {
+            const int n = e / Dz, i = e - n * Dz;
+            sE[i * NP + n] = (n < Nloc) ? __ldg(P.noise + (size_t)Dz * (c0 + n) + i) : 0.f;
+        }
+    }
+    if constexpr (WS && FIELD == 0) if (!chain) {
         for (int e = tid; e < R * HP; e += NT) {       // W2T[k][m] = W2[r0+k, m]
             const int k = e / HP, m = e - k * HP;
             sW2T[e] = (k < Rloc && m < H) ? __ldg(gW2 + (size_t)D * m + r0 + k) : 0.f;
@@ -106,6 +117,22 @@ __global__ void __launch_bounds__(NT, 1) bwd_kernel(const KParams P) {
     // `accum` adds the deltas to the record instead of replacing k (second VJP of record 0, k taken from the copy a6_f0)
     double dacc = 0.0;
     auto vjp = [&](float* sKbar, const int rec, const float wt, const bool accum, auto epi) {
+        if constexpr (FIELD == 1) {      // FFJORD field: recompute the evaluation from the taped stage input and reverse it
+            const int Dz = D - P.csq_extra;
+            float* sE = smem + P.oCS;
+            float* sZc = sE + Dz * NP;
+            const size_t base = ((size_t)rec * P.Q + q) * (size_t)D * NP;
+            for (int e = tid; e < D * NP; e += NT) sZc[e] = __ldcg(P.tapeZ + base + e);
+            __syncthreads();
+            const float* zb = csq_vjp<NP, NT>(P.p, Dz, H, P.csq_extra, rec_time(P.steps, P.t0, rec), sZc, sE, sKbar,
+                                              P.tapeH + ((size_t)rec * P.Q + q) * (size_t)P.hrows * NP, csq_bwd_carve(sZc + D * NP, Dz, H, NP));
+            for (int e = tid; e < Rloc * (NP / 4); e += NT) {
+                const int m = e / (NP / 4), nn = (e - m * (NP / 4)) * 4;
+                epi(m, nn, zb + m * NP + nn);
+            }
+            __syncthreads();
+            return;
+        }
         if constexpr (G == 1 && WS) {
             if (chain) {
                 const float* zb = chain_vjp<NP, NT>(P, cv, sKbar, rec, q, accum ? P.a6_f0 + (size_t)q * tileD : nullptr);

@@ -194,8 +194,9 @@ struct WgLayer {
     int dstride, astride;                     // floats per (record, tile) block of each tape
     int doff, aoff;                           // first row of this layer's delta / input inside a block
     int M, K, poff;                           // out, in, offset of W in the parameter vector (bias follows W)
+    int nobias;                               // 1: no bias row (a second outer product into the same W: the FFJORD transposed chain)
 };
-struct WgDesc { WgLayer l[8]; int nl; };
+struct WgDesc { WgLayer l[12]; int nl; };
 
 // rows x 64 columns of a tape into shared memory as float4 (tile-major items: consecutive threads read consecutive rows of one
 // (record, tile) block = contiguous memory); `ones` appends a row of 1 (the bias input)
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(CW_NT) dense_wgrad_kernel(const WgDesc desc, c
         const long long t0 = s * tiles_per_stage;
         __syncthreads();
         wg_stage(sDel, Ld.dptr, Ld.dstride, Ld.doff, M, false, NPt, t0, ntile);
-        wg_stage(sAct, Ld.aptr, Ld.astride, Ld.aoff, K, true, NPt, t0, ntile);
+        wg_stage(sAct, Ld.aptr, Ld.astride, Ld.aoff, K, !Ld.nobias, NPt, t0, ntile);
         __syncthreads();
 #pragma unroll
         for (int t = 0; t < CW_TPT; ++t) {
@@ -278,7 +279,7 @@ __global__ void __launch_bounds__(CW_NT) dense_wgrad_kernel(const WgDesc desc, c
 #pragma unroll
                 for (int o = 0; o < 4; ++o) {
                     const int in = it * 4 + i, on = mt * 4 + o;
-                    if (in <= K && on < M) atomicAdd(acc_out + Ld.poff + in * M + on, acc[t][i * 4 + o]);   // Flux order: W column-major, bias (in == K) behind it
+                    if (in < K + (Ld.nobias ? 0 : 1) && on < M) atomicAdd(acc_out + Ld.poff + in * M + on, acc[t][i * 4 + o]);   // Flux order: W column-major, bias (in == K) behind it
                 }
         }
     }

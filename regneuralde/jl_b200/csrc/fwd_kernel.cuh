@@ -307,6 +307,10 @@ __global__ void __launch_bounds__(NT, 1) fwd_kernel(const KParams P) {
             const int Dz = D - P.csq_extra;
             float* sE = smem + P.oCS;
             csq_rhs<NP, NT>(P.p, Dz, H, P.csq_extra, tstage, sIn, sE, sOut, csq_carve(sE + Dz * NP, Dz, H, NP));
+            if (rec >= 0) {      // tape: stage input and k (the reverse pass recomputes everything else, csq_bwd.cuh)
+                const size_t base = ((size_t)rec * P.Q + q) * D * NP;
+                for (int e = tid; e < D * NP; e += NT) { P.tapeZ[base + e] = sIn[e]; P.tapeK[base + e] = sOut[e]; }
+            }
             return;
         }
         if constexpr (G == 1 && WS) {

@@ -150,7 +150,8 @@ static bool bwd4_use_tc(int D, int H) {
     return !force_ffma && D > 0 && H > 0 && b4t_shape_ok(D, H);
 }
 // a6: the instantiation that also serves the first-dt term (a6.cuh); the plain one keeps the hot loop free of it
-static kern_t bwd_kernel_for(int variant, int D = 0, int H = 0, bool a6 = true) {
+static kern_t bwd_kernel_for(int variant, int D = 0, int H = 0, bool a6 = true, int csq = 0) {
+    if (csq > 0) return variant == RNDE_KERNEL_CHAIN ? bwd_kernel<1, 4, 1, true, NT_FWD, 1> : nullptr;
     switch (variant) {
         case RNDE_KERNEL_CTA: return bwd_kernel<1, 32, 4, true, NT_FWD>;
         case RNDE_KERNEL_STREAM: return bwd_kernel<1, 4, 1, false, NT_FWD>;
@@ -259,6 +260,12 @@ static size_t chain_smem_floats(const rnde_config& c, int NP, bool backward) {
     return (size_t)round_up((int)rnde_num_params(&c), 4) + 2 * (size_t)round_up(chain_maxw(c), 4) * NP + (backward ? (size_t)chain_hrows(c) * NP : 0);
 }
 
+// the same for the reverse pass: noise tile, stage-input tile, the tiles of csq_bwd.cuh
+static size_t csq_bwd_smem_floats(const rnde_config& c, int NP) {
+    if (c.csq_extra <= 0) return 0;
+    const int Dz = c.state_dim - c.csq_extra;
+    return (size_t)Dz * NP + (size_t)c.state_dim * NP + (size_t)csq_bwd_tile_floats(Dz, c.hidden_dim, c.csq_extra, NP) + 4;
+}
 // extra shared memory of the FFJORD field: the noise tile and the tiles of one evaluation (csq.cuh)
 static size_t csq_smem_floats(const rnde_config& c, int NP) {
     if (c.csq_extra <= 0) return 0;
@@ -306,7 +313,7 @@ static int try_variant(rnde_handle* h, int variant, size_t smem_limit, std::stri
     if (c.n_layers > 0 && variant != RNDE_KERNEL_CHAIN && variant != RNDE_KERNEL_CTA) { *why = "chain fields run on the CHAIN / CTA variants"; return 0; }
     if (c.csq_extra > 0 && variant != RNDE_KERNEL_CHAIN) { *why = "the FFJORD field runs on the CHAIN variant (4-column tiles)"; return 0; }
     const size_t sf = smem_bytes_fwd(variant, D, H, R, HS, h->kblock, c.arith) + sizeof(float) * (chain_smem_floats(c, NP, false) + csq_smem_floats(c, NP));
-    const size_t sb = c.need_backward ? smem_bytes_bwd(variant, D, H, R, HS, h->kblock) + sizeof(float) * chain_smem_floats(c, NP, true) : 0;
+    const size_t sb = c.need_backward ? smem_bytes_bwd(variant, D, H, R, HS, h->kblock) + sizeof(float) * (chain_smem_floats(c, NP, true) + csq_bwd_smem_floats(c, NP)) : 0;
     if (sf > smem_limit || sb > smem_limit) { *why = "shared memory: need " + std::to_string(std::max(sf, sb)) + " B"; return 0; }
     // all CTAs must be co-resident (persistent grid with a grid barrier)
     if (c.arith == RNDE_ARITH_SPLITK && variant != RNDE_KERNEL_CLUSTER4) { *why = "RNDE_ARITH_SPLITK is implemented by the cluster-4 variant"; return 0; }
@@ -318,7 +325,7 @@ static int try_variant(rnde_handle* h, int variant, size_t smem_limit, std::stri
     size_t sa = sb;
     if (c.need_backward) {
         for (int a = 0; a < 2; ++a) {      // both instantiations (with / without the first-dt additions)
-            kern_t kb = bwd_kernel_for(variant, D, H, a != 0);
+            kern_t kb = bwd_kernel_for(variant, D, H, a != 0, c.csq_extra);
             if (cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb) != cudaSuccess) { cudaGetLastError(); *why = "cudaFuncSetAttribute(bwd) failed"; return 0; }
         }
         if (variant == RNDE_KERNEL_CLUSTER4) {
@@ -334,7 +341,7 @@ static int try_variant(rnde_handle* h, int variant, size_t smem_limit, std::stri
         max_cta = per_sm * h->num_sms;
         if (c.need_backward) {
             int per_sm_b = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, bwd_kernel_for(variant, D, H), NT_FWD, sb);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, bwd_kernel_for(variant, D, H, true, c.csq_extra), NT_FWD, sb);
             max_cta = std::min(max_cta, per_sm_b * h->num_sms);
         }
     } else {
@@ -379,7 +386,7 @@ extern "C" int rnde_create(const rnde_config* cfg, rnde_handle** out) {
     if (cfg->csq_extra != 0) {
         if ((cfg->csq_extra != 1 && cfg->csq_extra != 3) || cfg->state_dim <= cfg->csq_extra || cfg->n_layers != 0 || cfg->hidden_dim <= 0 ||
             cfg->arith != RNDE_ARITH_FMA_CHAIN || cfg->max_saveat > 0) return RNDE_ERR_ARG;
-        if (cfg->need_backward || cfg->dist_mode == RNDE_DIST_EXACT) return RNDE_ERR_UNSUPPORTED;      // forward solves only so far
+        if (cfg->dist_mode == RNDE_DIST_EXACT) return RNDE_ERR_UNSUPPORTED;
     }
     if (cfg->reg_kind < 0 || cfg->reg_kind > RNDE_REG_ERR_PLUS_STIFF || cfg->alg < 0 || cfg->alg > 1) return RNDE_ERR_ARG;
     if (!(cfg->t1 > cfg->t0) || !(cfg->abstol > 0.f) || !(cfg->reltol > 0.f)) return RNDE_ERR_ARG;
@@ -460,9 +467,9 @@ extern "C" int rnde_create(const rnde_config* cfg, rnde_handle** out) {
         }
         if (cudaMalloc(&h->tapeZ, sizeof(float) * nrec * tile * D) != cudaSuccess) return fail("cudaMalloc tapeZ (lower tape_capacity?)");
         if (cudaMalloc(&h->tapeK, sizeof(float) * nrec * tile * D) != cudaSuccess) return fail("cudaMalloc tapeK (lower tape_capacity?)");
-        const size_t hrows = c.n_layers > 0 ? (size_t)chain_hrows(c) : (size_t)H;
+        const size_t hrows = c.csq_extra > 0 ? (size_t)csq_tape_rows(D - c.csq_extra, H).total : (c.n_layers > 0 ? (size_t)chain_hrows(c) : (size_t)H);
         if (cudaMalloc(&h->tapeH, sizeof(float) * nrec * tile * hrows) != cudaSuccess) return fail("cudaMalloc tapeH");
-        if (cudaMalloc(&h->tapeD1, sizeof(float) * nrec * tile * hrows) != cudaSuccess) return fail("cudaMalloc tapeD1");
+        if (cudaMalloc(&h->tapeD1, sizeof(float) * nrec * tile * (c.csq_extra > 0 ? 1 : hrows)) != cudaSuccess) return fail("cudaMalloc tapeD1");      // FFJORD: unused
         h->wg_ws_floats = std::max(wgrad_workspace_floats(D, H), (size_t)2 * h->np + 8);
         if (cudaMalloc(&h->wg_ws, sizeof(float) * h->wg_ws_floats) != cudaSuccess) return fail("cudaMalloc wgrad workspace");
         if (cudaMalloc(&h->scal, sizeof(float) * 2 * c.tape_capacity) != cudaSuccess) return fail("cudaMalloc scal");
@@ -573,7 +580,7 @@ static void fill_params(const rnde_handle* h, KParams& P) {
     for (int i = 0; i < 8; ++i) P.peers[i] = h->peers[i];
     P.colsum = h->colsum; P.colsum_stride = h->colsum_stride; P.bar = h->bar; P.steps = h->steps; P.stats = h->stats;
     P.dbg = h->dbg;
-    P.n_layers = c.n_layers; P.pre_act = c.pre_act; P.hrows = c.n_layers > 0 ? chain_hrows(c) : 0; P.chain_np = c.n_layers > 0 ? (int)h->np : 0;
+    P.n_layers = c.n_layers; P.pre_act = c.pre_act; P.hrows = c.csq_extra > 0 ? csq_tape_rows(c.state_dim - c.csq_extra, c.hidden_dim).total : (c.n_layers > 0 ? chain_hrows(c) : 0); P.chain_np = c.n_layers > 0 ? (int)h->np : 0;
     for (int l = 0; l < 8; ++l) { P.lw[l] = c.layer_width[l]; P.la[l] = c.layer_act[l]; }
     P.tapeZ = h->tapeZ; P.tapeK = h->tapeK; P.tapeH = h->tapeH; P.tapeD1 = h->tapeD1; P.scal = h->scal;
     P.forced_dt = h->forced_dev; P.n_forced = h->n_forced;
@@ -707,6 +714,13 @@ static int backward_impl(rnde_handle* h, const float* du_dev, const float* dusav
         bool WS; int G, NP; variant_shape(h->variant, &G, &NP, &WS);
         set_chain_offsets(h, P, make_bwd_layout(G, NP, WS, h->cfg.state_dim, h->cfg.hidden_dim, h->R, h->HS).total);
     }
+    if (h->cfg.csq_extra > 0) {
+        if (!h->noise) return set_err(h, RNDE_ERR_STATE, "FFJORD handle: call rnde_set_noise first");
+        if (dusave_dev) return set_err(h, RNDE_ERR_UNSUPPORTED, "FFJORD handles have no saveat path");
+        bool WS; int G, NP; variant_shape(h->variant, &G, &NP, &WS);
+        P.noise = h->noise; P.csq_extra = h->cfg.csq_extra;
+        P.oCS = round_up(make_bwd_layout(G, NP, WS, h->cfg.state_dim, h->cfg.hidden_dim, h->R, h->HS).total, 4);
+    }
     // Appendix A.6 (a6.cuh): the sweep also accumulates dL/d(dt_1); two more VJPs then differentiate the initial-dt heuristic.
     // Their records sit behind the last step: 6N+1..6N+5 empty, 6N+6 the evaluation f(u0 + dt0 f0, t0 + dt0).
     const bool a6 = P.a6 && s.naccept > 0;
@@ -742,7 +756,7 @@ static int backward_impl(rnde_handle* h, const float* du_dev, const float* dusav
             CUDA_TRY(h, cudaMemcpyAsync(h->a6_kc + 6 * recD, h->tapeK + (size_t)6 * (s.naccept - 1) * recD, sizeof(float) * 6 * recD, cudaMemcpyDeviceToDevice, st));
     }
     CUDA_TRY(h, cudaMemsetAsync(h->bar, 0, sizeof(unsigned) * 4, st));
-    int rc = launch(h, bwd_kernel_for(h->variant, h->cfg.state_dim, h->cfg.hidden_dim, P.a6 != 0), P, h->smem_bwd, st);
+    int rc = launch(h, bwd_kernel_for(h->variant, h->cfg.state_dim, h->cfg.hidden_dim, P.a6 != 0, h->cfg.csq_extra), P, h->smem_bwd, st);
     if (rc != RNDE_OK) return rc;
     if (a6_inkernel && h->detach == RNDE_DETACH_FIRST_TERM_ONLY) {      // diagnostic: only record 0 and the extra record keep their deltas
         CUDA_TRY(h, cudaMemsetAsync(h->tapeK + recD, 0, sizeof(float) * (size_t)6 * s.naccept * recD, st));
@@ -775,6 +789,43 @@ static int backward_impl(rnde_handle* h, const float* du_dev, const float* dusav
         if ((rc = launch(h, a6_kernel_for(h->variant), PA, h->smem_a6, st)) != RNDE_OK) return rc;
     }
     const int nsteps_w = s.naccept + ((a6 && !wg_slot) ? 1 : 0);      // steps the weight-gradient contraction runs over
+    if (h->cfg.csq_extra > 0) {      // FFJORD field (csq_bwd.cuh): every W receives two outer products per record, the bias / gate vectors a sum
+        const int Dd = h->cfg.state_dim, Dz = Dd - h->cfg.csq_extra, Hh = h->cfg.hidden_dim;
+        const CsqTapeRows R = csq_tape_rows(Dz, Hh);
+        WgDesc desc; memset(&desc, 0, sizeof(desc));
+        const int Ms[3] = {Hh, Hh, Dz}, Ks[3] = {Dz, Hh, Hh};
+        const int linb[3] = {R.linb1, R.linb2, R.linb3}, us[3] = {R.u1, R.u2, R.u3}, vbs[3] = {R.vb1, R.vb2, R.vb3}, vecs[3] = {R.vec1, R.vec2, R.vec3};
+        const int ain[3] = {0, R.a1, R.a2};
+        int poff = 0;
+        auto add = [&](const float* dptr, int dstride, int doff, const float* aptr, int astride, int aoff, int M, int K, int po, int nobias) {
+            if (desc.nl >= 12) { desc.nl = 13; return; }      // reported below
+            WgLayer& w = desc.l[desc.nl++];
+            w.dptr = dptr; w.dstride = dstride; w.doff = doff; w.aptr = aptr; w.astride = astride; w.aoff = aoff; w.M = M; w.K = K; w.poff = po; w.nobias = nobias;
+        };
+        const int hs = R.total * h->NP, ds = Dd * h->NP;
+        for (int l = 0; l < 3; ++l) {
+            const int M = Ms[l], K = Ks[l];
+            // the contraction kernel holds at most 512 4x4 output tiles per pseudo-layer: split the input index
+            const int kmax = std::max(4, ((512 / ((M + 3) / 4)) * 4 - 4) / 4 * 4);
+            for (int k0 = 0; k0 < K; k0 += kmax) {
+                const int kc = std::min(kmax, K - k0);
+                const bool lastc = k0 + kc >= K;
+                // forward chain: dW += linb x^T (x = z on the state tape for layer 1), dB = sum linb through the bias row of the LAST chunk.
+                // A chunk that is not the last must not add a bias row: it would land inside W.
+                if (l == 0) add(h->tapeH, hs, linb[l], h->tapeZ, ds, k0, M, kc, poff + k0 * M, lastc ? 0 : 1);
+                else add(h->tapeH, hs, linb[l], h->tapeH, hs, ain[l] + k0, M, kc, poff + k0 * M, lastc ? 0 : 1);
+                // transposed chain: dW += u vbar^T
+                add(h->tapeH, hs, us[l], h->tapeH, hs, vbs[l] + k0, M, kc, poff + k0 * M, 1);
+            }
+            add(h->tapeH, hs, vecs[l], h->tapeH, hs, 0, 3 * M, 0, poff + M * K + M, 0);      // [bias_W | bias_B | gate_W] = sums of the three vectors
+            poff += M * K + 4 * M;
+        }
+        if (desc.nl > 12) return set_err(h, RNDE_ERR_UNSUPPORTED, "FFJORD weight gradients: layer too large for the contraction kernel");
+        const int nrec_c = 1 + 6 * s.naccept;
+        cudaError_t ce = launch_dense_wgrad(desc, h->NP, (long long)nrec_c * h->Q, (int)h->np, h->num_sms, reinterpret_cast<double*>(h->wg_ws), dp_dev, st, &h->launches);
+        if (ce != cudaSuccess) return set_err(h, RNDE_ERR_CUDA, std::string("FFJORD wgrad launch: ") + cudaGetErrorString(ce));
+        return RNDE_OK;
+    }
     if (h->cfg.n_layers > 0) {      // chain field: per-layer contractions over the tape, FP64 across stages
         const int nrec_c = 1 + 6 * nsteps_w;
         WgDesc desc; memset(&desc, 0, sizeof(desc));

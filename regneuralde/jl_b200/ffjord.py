@@ -1,12 +1,14 @@
-"""FFJORD model surface over libregnde.so -- FORWARD (log-density) ONLY so far.
+"""FFJORD model surface over libregnde.so: log-density and, since round 2, its gradient.
 
     TrackedFFJORD(model, tspan, time_dep, regularize, solver; dynamics, reltol, abstol, ...)   src/models/ffjord.jl:1-51
     ffjord(x, p, e; regularize=false) -> (logpx, lambda1, lambda2, nfe, sv)                    src/models/ffjord.jl:68-137
     ConcatSquashLinear / MLPDynamics(in, hidden)                                               experiments/ffjord_tabular.jl:47-90
 
 The augmented-state solve (z; delta_logp (; ||f||^2; ||e^T J||^2)) runs in the CUDA library (csrc/csq.cuh inside the generic
-Tsit5 stepper); the standard-normal log-density of z(1) is the host glue the reference keeps in Julia.  There is no backward
-yet: calling with gradients enabled on p raises."""
+Tsit5 stepper); the standard-normal log-density of z(1) is the host glue the reference keeps in Julia.  With gradients enabled
+the solve is taped and torch autograd reaches it through node._Solve: the reverse sweep differentiates the field by hand
+(csrc/csq_bwd.cuh: reverse mode through forw_n_back, i.e. the second-order terms Tracker would produce) and the parameter
+gradients are contracted from the tape in Float64 (dense_wgrad_kernel).  The step sizes are frozen (detach_dt = "all")."""
 from __future__ import annotations
 
 import ctypes as C
@@ -16,7 +18,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib as L
-from .node import ERROR_ESTIMATE, SavedValues, Tsit5, _Handle, _stream_ptr, colmajor, from_colmajor
+from .node import ERROR_ESTIMATE, SavedValues, Tsit5, _Handle, _Solve, _stream_ptr, colmajor, from_colmajor
 
 
 class ConcatSquashLinear:
@@ -65,14 +67,14 @@ class TrackedFFJORD:
         self._handles: dict = {}
         self.last_stats = None
 
-    def _handle(self, B: int, extra: int, reg_kind: int) -> _Handle:
-        key = (B, extra, reg_kind)
+    def _handle(self, B: int, extra: int, reg_kind: int, need_backward: bool = False) -> _Handle:
+        key = (B, extra, reg_kind, need_backward)
         if key not in self._handles:
             cfg = L.Config()
             cfg.struct_bytes = C.sizeof(L.Config)
             cfg.state_dim, cfg.hidden_dim, cfg.batch = self.model.D + extra, self.model.H, B
             cfg.time_dep, cfg.alg, cfg.reg_kind = 1, self.solver.alg, reg_kind
-            cfg.max_steps, cfg.tape_capacity, cfg.need_backward = self.maxiters, self.tape_capacity, 0
+            cfg.max_steps, cfg.tape_capacity, cfg.need_backward = self.maxiters, self.tape_capacity, (1 if need_backward else 0)
             cfg.t0, cfg.t1 = self.tspan
             cfg.abstol, cfg.reltol = self.abstol, self.reltol
             cfg.global_batch, cfg.csq_extra = B, extra
@@ -88,21 +90,26 @@ class TrackedFFJORD:
             raise ValueError(f"x must be ({D}, B)")
         if not x.is_cuda or not p.is_cuda:
             raise RuntimeError("regneuralde.jl_b200 runs on CUDA tensors only (no CPU fallback)")
-        if torch.is_grad_enabled() and (p.requires_grad or x.requires_grad):
-            raise NotImplementedError("the FFJORD backward is not built yet (DESIGN.md section 9); call under torch.no_grad()")
+        need_bwd = torch.is_grad_enabled() and (p.requires_grad or x.requires_grad)
         B = x.shape[1]
         e = torch.randn(D, B, device=x.device) if e is None else e          # CUDA.randn(Float32, size(x)...)  (ffjord.jl:71)
         extra = 3 if (regularize and not self.regularize) else 1
-        hd = self._handle(B, extra, ERROR_ESTIMATE.kind if self.regularize else L.REG_NONE)
+        hd = self._handle(B, extra, ERROR_ESTIMATE.kind if self.regularize else L.REG_NONE, need_bwd)
         ebuf = colmajor(e.to(torch.float32))
         ubuf0 = colmajor(torch.cat([x.to(torch.float32), torch.zeros(extra, B, device=x.device)], 0))
         u = torch.empty((D + extra) * B, device=x.device, dtype=torch.float32)
         sv = torch.zeros(hd.cfg.tape_capacity + 1, device=x.device, dtype=torch.float32)
         st = L.Stats()
         hd.check(hd.lib.rnde_set_noise(hd.h, ebuf.data_ptr()), "rnde_set_noise")
-        rc = hd.lib.rnde_forward(hd.h, ubuf0.data_ptr(), p.contiguous().data_ptr(), u.data_ptr(), sv.data_ptr(), C.byref(st), _stream_ptr())
-        self.last_stats = st
-        hd.check(rc, "rnde_forward")
+        self._noise_keepalive = ebuf          # the library keeps the pointer until the backward pass has run
+        if need_bwd:
+            u, sv_all = _Solve.apply(ubuf0, p.contiguous(), self, hd)      # sets self.last_stats
+            st = self.last_stats
+            sv = sv_all
+        else:
+            rc = hd.lib.rnde_forward(hd.h, ubuf0.data_ptr(), p.contiguous().data_ptr(), u.data_ptr(), sv.data_ptr(), C.byref(st), _stream_ptr())
+            self.last_stats = st
+            hd.check(rc, "rnde_forward")
         pred = from_colmajor(u, D + extra, B)
         z, delta_logp = pred[:D], pred[D]
         zero = torch.zeros(B, device=x.device)

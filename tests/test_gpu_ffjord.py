@@ -65,3 +65,54 @@ def test_ffjord_solve_bit_identical(oracle_built, Dz, H, B, regf, kinetic):
         assert np.array_equal(sv.saveval.cpu().numpy().view(np.uint32), ref.saveval.view(np.uint32))
     else:
         assert sv is None
+
+
+# ---- the gradient (round 2): reverse sweep through the hand-differentiated field (csrc/csq_bwd.cuh) -------------------------------
+
+
+@pytest.mark.parametrize("Dz,H,B,regf,kinetic", [(5, 9, 10, False, False), (5, 9, 130, True, False), (43, 100, 8, False, True), (43, 100, 24, True, False)])
+def test_ffjord_gradient_matches_oracle(oracle_built, Dz, H, B, regf, kinetic):
+    """Tracker.gradient of the tabular loss terms (experiments/ffjord_tabular.jl:137-141): random cotangents on logpx, on the kinetic
+    regulariser rows and on the saved values; CUDA against the C oracle's adjoint with Float64 cotangents over the same Float32
+    forward (which is itself checked against torch autograd through the same field, tests/test_ffjord_oracle.py).  The step sizes
+    are frozen on both sides."""
+    import regneuralde.jl_b200 as R
+    sys_path_tests = __import__("gradbar")
+    rng = np.random.default_rng(29)
+    p_np = F.glorot_params(rng, Dz, H, dtype=np.float32, bias_scale=0.1)
+    x_np = rng.standard_normal((Dz, B)).astype(np.float32)
+    e_np = rng.standard_normal((Dz, B)).astype(np.float32)
+    extra = 3 if kinetic else 1
+    o = orc.Oracle(orc.OracleConfig(D=Dz + extra, H=H, B=B, csq_extra=extra, csq_noise=e_np, kblock1=Dz + extra,
+                                    reg_kind=orc.REG_ERR_DT if regf else orc.REG_NONE))
+    ref = o.forward(np.concatenate([x_np, np.zeros((extra, B), np.float32)], 0), p_np)
+    ff = R.TrackedFFJORD(R.CSQDynamics(Dz, H), [0.0, 1.0], True, regf, R.Tsit5(), reltol=1.4e-8, abstol=1.4e-8, tape_capacity=64)
+    p = torch.from_numpy(p_np).cuda().requires_grad_(True)
+    x = torch.from_numpy(x_np).cuda().requires_grad_(True)
+    logpx, l1, l2, nfe, sv = ff(x, p, torch.from_numpy(e_np).cuda(), regularize=kinetic)
+    assert nfe == ref.nf and ff.last_stats.naccept == ref.naccept
+    # loss = sum(w_l .* (logpz - delta_logp)) + sum(w1 .* l1) + sum(w2 .* l2) + sum(ws .* saveval)
+    w_l = rng.standard_normal(B).astype(np.float32)
+    w1, w2 = rng.standard_normal(B).astype(np.float32), rng.standard_normal(B).astype(np.float32)
+    ws = rng.standard_normal(len(ref.saveval) if regf else 1).astype(np.float32)
+    loss = (logpx * torch.from_numpy(w_l).cuda()).sum()
+    if kinetic:
+        loss = loss + (l1 * torch.from_numpy(w1).cuda()).sum() + (l2 * torch.from_numpy(w2).cuda()).sum()
+    if regf:
+        loss = loss + (sv.saveval * torch.from_numpy(ws).cuda()).sum()
+    loss.backward()
+    torch.cuda.synchronize()
+    # the same cotangent on the augmented final state: d logpz/dz = -z
+    du = np.zeros((Dz + extra, B), np.float32)
+    du[:Dz] = -ref.u[:Dz] * w_l
+    du[Dz] = -w_l
+    if kinetic:
+        du[Dz + 1], du[Dz + 2] = w1, w2
+    dp_hi, dx_hi, _, _ = o.backward(du, ws if regf else None, hi=True, first_dt_tracked=False)
+    dp_32, dx_32, _, _ = o.backward(du, ws if regf else None, first_dt_tracked=False)
+    rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()
+    e_p, e_x = rel(p.grad.cpu().numpy(), dp_hi), rel(x.grad.cpu().numpy(), dx_hi[:Dz])
+    c_p, c_x = rel(dp_32, dp_hi), rel(dx_32[:Dz], dx_hi[:Dz])
+    print(f"ffjord grad Dz={Dz} H={H} B={B} regf={regf} kinetic={kinetic}: e_p {e_p:.2e} (cpu32 {c_p:.2e})  e_x {e_x:.2e} (cpu32 {c_x:.2e})  |dp| {np.abs(dp_hi).max():.2e}")
+    assert np.abs(dp_hi).max() > 0 and np.abs(dx_hi).max() > 0
+    assert e_p <= max(1e-4, sys_path_tests.GRAD_BAR * c_p) and e_x <= max(1e-4, sys_path_tests.GRAD_BAR * c_x), (e_p, c_p, e_x, c_x)
