@@ -508,8 +508,9 @@ def run_ours(args):
 
 def secondary_workloads(torch, R, peak) -> dict:
     """The widened rows on the record: one Latent-ODE training step (N1: GRU encoder + chain-field solve with 49
-    save times + decoder, PhysioNet-shaped synthetic batch 37 x 49 x 512, error-estimate regulariser) and one Neural-SDE
-    forward solve (N2: SOSRI, 32-dim state, batch 512, tol 1.4e-1, supplied noise); device times, CUDA events."""
+    save times + decoder, PhysioNet-shaped synthetic batch 37 x 49 x 512, error-estimate regulariser), one Neural-SDE
+    forward solve (N2: SOSRI, 32-dim state, batch 512, tol 1.4e-1, supplied noise) and one FFJORD training step (N4: MINIBOONE
+    shape, batch 1024, forward + reverse sweep + WeightDecay/ADAM update); device times, CUDA events."""
     out = {}
 
     def timed(fn, iters=10, warm=3):
@@ -576,6 +577,29 @@ def secondary_workloads(torch, R, peak) -> dict:
                              "nreject": int(node.last_stats.nreject)}
     except Exception as ex:
         out["neural_sde"] = {"error": repr(ex)[:200]}
+    try:
+        # ---- row N4: FFJORD training step (experiments/ffjord_tabular.jl:112-141: MLPDynamics(43, 100), batch 1024, Tsit5 1.4e-8,
+        #      loss = -mean(logpx), Optimiser(WeightDecay(1e-5), ADAM(1e-2)); configs/ffjord_tabular.yml: regularize false) ----
+        Dz, Hf, B = 43, 100, 1024
+        g = torch.Generator().manual_seed(SEED)
+        ff = R.TrackedFFJORD(R.CSQDynamics(Dz, Hf, generator=g), [0.0, 1.0], True, False, R.Tsit5(), reltol=1.4e-8, abstol=1.4e-8, tape_capacity=96)
+        x = torch.randn(Dz, B, generator=g).cuda()
+        e = torch.randn(Dz, B, generator=g).cuda()
+        opt = R.ADAMOptimiser(1e-5, 1e-2)
+        res = {}
+
+        def train():
+            o = R.ffjord.loss_and_gradient(ff, x, ff.p, e)
+            R.update_parameters_((ff.p,), (o["g"],), opt)
+            res.update(o)
+
+        ms = timed(train, 5, 2)
+        with torch.no_grad():
+            ms_fwd = timed(lambda: ff(x, ff.p, e), 3, 1)
+        out["ffjord"] = {"workload": f"ffjord_tabular train step (MINIBOONE shape: MLPDynamics({Dz},{Hf}), batch {B}, Tsit5 tol 1.4e-8, -mean(logpx), WeightDecay+ADAM)",
+                         "ms_per_step": ms, "samples_per_s": B / (ms * 1e-3), "nfe": int(res["nfe"]), "nll": float(res["nll"]), "forward_ms": ms_fwd}
+    except Exception as ex:      # secondary rows never break the headline line
+        out["ffjord"] = {"error": repr(ex)[:200]}
     return out
 
 

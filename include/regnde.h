@@ -71,7 +71,8 @@ enum { RNDE_REG_NONE = 0, RNDE_REG_ERR_DT = 1, RNDE_REG_STIFF_DT_ABS = 2, RNDE_R
  * STREAM: weights streamed from L2 (any size, slow fallback); CLUSTER: 8-CTA clusters, state in
  * distributed shared memory; CLUSTER4: 4-CTA clusters, state in registers (MNIST-shaped fields). */
 enum { RNDE_KERNEL_AUTO = 0, RNDE_KERNEL_CTA = 1, RNDE_KERNEL_STREAM = 2, RNDE_KERNEL_CLUSTER = 3, RNDE_KERNEL_CLUSTER4 = 4,
-       RNDE_KERNEL_CHAIN = 5 /* CTA variant with 4-column tiles: chain fields, one CTA per SM at batch 512 */ };
+       RNDE_KERNEL_CHAIN = 5 /* CTA variant with 4-column tiles: chain fields, one CTA per SM at batch 512 */,
+       RNDE_KERNEL_CHAIN8 = 6 /* the same with 8-column tiles: FFJORD handles whose batch needs more than one 4-column CTA per SM */ };
 enum { RNDE_DIST_SINGLE = 0, RNDE_DIST_EXACT = 1, RNDE_DIST_INDEPENDENT = 2 };
 /* FMA_CHAIN: blocked fma chains in a fixed order (every kernel variant).
  * FIXED24: exact truncated fixed-point products, order-independent, run as integer tensor-core MMAs by the cluster-4
@@ -200,6 +201,10 @@ int rnde_set_saveat(rnde_handle* h, const float* saveat_host, int32_t n);
  * column-major, caller-owned device memory that must stay valid until the solve has run (the `e` argument of the
  * TrackedFFJORD functors, src/models/ffjord.jl:68-72). */
 int rnde_set_noise(rnde_handle* h, const float* e_dev);
+/* FFJORD handles: integrate the flow backwards, tspan[1] -> tspan[0] -- `sample` of the reference solves its ODEProblem over
+ * [n.tspan[2], n.tspan[1]] (src/models/ffjord.jl:160-167).  With reverse != 0 the following forward solves integrate
+ * dz/ds = -f(z, t0 + t1 - s) over s in [t0, t1], i.e. they return z(t0) for the state given at t1.  Forward solves only. */
+int rnde_set_reverse_time(rnde_handle* h, int32_t reverse);
 int rnde_forward_saveat(rnde_handle* h, const float* x_dev, const float* p_dev, float* u_out_dev, float* usave_dev, float* saveval_dev,
                         rnde_stats* stats_host, void* stream);
 int rnde_backward_saveat(rnde_handle* h, const float* du_dev, const float* dusave_dev, const float* dsaveval_dev, float* dp_dev,
@@ -309,6 +314,13 @@ int rnde_reg_agg(rnde_handle* h, int32_t agg, float lam, float cot_scale, const 
  * `h` may be NULL (no handle state is used). */
 int rnde_opt_update(rnde_handle* h, float* p_dev, const float* g_dev, float* v_dev, int64_t n, float inv_decay_scale, float eta, float rho,
                     void* stream);
+/* Flux.Optimise.Optimiser(WeightDecay(wd), ADAM(eta, (beta1, beta2))) on raw arrays (experiments/ffjord_tabular.jl:128):
+ *   delta = g + wd * p ;  m = beta1 m + (1 - beta1) delta ;  v = beta2 v + (1 - beta2) delta^2
+ *   p = p - eta * m / (1 - beta1_pow) / (sqrt(v / (1 - beta2_pow)) + eps)        [Flux 0.11.6 ADAM, eps = 1e-8]
+ * beta*_pow: the running powers beta^t of this update (t = 1-based), kept by the caller like Flux keeps them in its state.
+ * `h` may be NULL. */
+int rnde_adam_update(rnde_handle* h, float* p_dev, const float* g_dev, float* m_dev, float* v_dev, int64_t n, float eta, float beta1, float beta2,
+                     float beta1_pow, float beta2_pow, float eps, float weight_decay, void* stream);
 
 /* Reference-exact data-parallel mode (RNDE_DIST_EXACT): all ranks take the step sequence of the single batched
  * solve over the global batch.  The per-column sums of squares of every norm are written by each rank straight into

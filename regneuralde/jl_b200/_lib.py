@@ -29,7 +29,7 @@ OK, ERR_MAXITERS, ERR_DTMIN, ERR_NAN, ERR_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_TA
 ACT_IDENTITY, ACT_TANH = 0, 1
 ALG_TSIT5, ALG_AUTO_TSIT5 = 0, 1
 REG_NONE, REG_ERR_DT, REG_STIFF_DT_ABS, REG_STIFF_SCALED, REG_ERR_PLUS_STIFF = range(5)
-KERNEL_AUTO, KERNEL_CTA, KERNEL_STREAM, KERNEL_CLUSTER, KERNEL_CLUSTER4, KERNEL_CHAIN = range(6)
+KERNEL_AUTO, KERNEL_CTA, KERNEL_STREAM, KERNEL_CLUSTER, KERNEL_CLUSTER4, KERNEL_CHAIN, KERNEL_CHAIN8 = range(7)
 DIST_SINGLE, DIST_EXACT, DIST_INDEPENDENT = range(3)
 ARITH_FMA_CHAIN, ARITH_FIXED24, ARITH_SPLITK = 0, 1, 2
 DETACH_ALL, DETACH_ALL_BUT_FIRST, DETACH_FIRST_TERM_ONLY = 0, 1, 2
@@ -37,7 +37,7 @@ SDE_SOSRI, SDE_AUTO_SOSRI2 = 0, 1
 
 EXPORTS = [
     "rnde_version", "rnde_status_string", "rnde_device_count", "rnde_create", "rnde_destroy", "rnde_last_error",
-    "rnde_num_params", "rnde_default_kblock", "rnde_kernel_variant", "rnde_launch_count", "rnde_set_tspan", "rnde_set_forced_steps", "rnde_set_detach",
+    "rnde_num_params", "rnde_default_kblock", "rnde_kernel_variant", "rnde_launch_count", "rnde_set_tspan", "rnde_set_forced_steps", "rnde_set_detach", "rnde_set_reverse_time", "rnde_adam_update",
     "rnde_forward", "rnde_backward", "rnde_forward_host", "rnde_backward_host", "rnde_head_loss_grad", "rnde_get_steps",
     "rnde_opt_update", "rnde_test_tanh", "rnde_test_tanh_bits", "rnde_test_pow", "rnde_test_unary_bits", "rnde_test_csq_rhs", "rnde_debug_timeline", "rnde_debug_a6", "rnde_dist_export", "rnde_dist_import",
     "rnde_set_saveat", "rnde_forward_saveat", "rnde_backward_saveat", "rnde_set_noise",
@@ -153,6 +153,8 @@ def lib() -> C.CDLL:
     L.rnde_set_tspan.argtypes = [vp, C.c_float, C.c_float]
     L.rnde_set_forced_steps.argtypes = [vp, fp, C.c_int32]
     L.rnde_set_detach.argtypes = [vp, C.c_int32]
+    L.rnde_set_reverse_time.argtypes = [vp, C.c_int32]
+    L.rnde_adam_update.argtypes = [vp, vp, vp, vp, vp, C.c_int64] + [C.c_float] * 7 + [vp]
     L.rnde_forward.argtypes = [vp, vp, vp, vp, vp, C.POINTER(Stats), vp]
     L.rnde_backward.argtypes = [vp, vp, vp, vp, vp, vp]
     L.rnde_forward_host.argtypes = [vp, vp, vp, vp, vp, C.POINTER(Stats)]

@@ -128,12 +128,35 @@ class Optimiser:
         return self.state[k]
 
 
-def update_parameters_(ps, gs, opt: Optimiser) -> None:
+class ADAMOptimiser:
+    """Flux.Optimise.Optimiser(WeightDecay(wd), ADAM(eta, beta)) -- experiments/ffjord_tabular.jl:128 (Flux 0.11.6: eps = 1e-8, the
+    running powers beta^t live in the per-parameter state)."""
+
+    def __init__(self, weight_decay: float = 1.0e-5, eta: float = 1.0e-2, beta=(0.9, 0.999), eps: float = 1.0e-8):
+        self.weight_decay, self.eta, self.beta, self.eps = weight_decay, eta, (float(beta[0]), float(beta[1])), eps
+        self.state: dict = {}
+
+    def slot(self, p: torch.Tensor):
+        k = p.data_ptr()
+        if k not in self.state:
+            self.state[k] = {"m": torch.zeros_like(p), "v": torch.zeros_like(p), "bp": [self.beta[0], self.beta[1]]}
+        return self.state[k]
+
+
+def update_parameters_(ps, gs, opt) -> None:
     """update_parameters!(ps, gs, opt): in-place on raw arrays, skipping empty parameter vectors
     (src/utils.jl:149-156)."""
     lib = L.lib()
     for p, g in zip(ps, gs):
         if p.numel() == 0:
+            continue
+        if isinstance(opt, ADAMOptimiser):
+            s = opt.slot(p)
+            rc = lib.rnde_adam_update(None, p.data_ptr(), g.data_ptr(), s["m"].data_ptr(), s["v"].data_ptr(), p.numel(), opt.eta, opt.beta[0],
+                                      opt.beta[1], s["bp"][0], s["bp"][1], opt.eps, opt.weight_decay, _stream_ptr())
+            if rc != L.OK:
+                raise L.RndeError(rc, "rnde_adam_update")
+            s["bp"][0] *= opt.beta[0]; s["bp"][1] *= opt.beta[1]
             continue
         s = opt.slot(p)
         scale = 1.0 / (1.0 + opt.gamma * s["n"])

@@ -306,7 +306,11 @@ __global__ void __launch_bounds__(NT, 1) fwd_kernel(const KParams P) {
         if constexpr (FIELD == 1) {
             const int Dz = D - P.csq_extra;
             float* sE = smem + P.oCS;
-            csq_rhs<NP, NT>(P.p, Dz, H, P.csq_extra, tstage, sIn, sE, sOut, csq_carve(sE + Dz * NP, Dz, H, NP));
+            csq_rhs<NP, NT>(P.p, Dz, H, P.csq_extra, P.csq_reverse ? (P.t0 + P.t1) - tstage : tstage, sIn, sE, sOut, csq_carve(sE + Dz * NP, Dz, H, NP));
+            if (P.csq_reverse) {      // the flow backwards (`sample`, ffjord.jl:160-167)
+                for (int e = tid; e < D * NP; e += NT) sOut[e] = -sOut[e];
+                __syncthreads();
+            }
             if (rec >= 0) {      // tape: stage input and k (the reverse pass recomputes everything else, csq_bwd.cuh)
                 const size_t base = ((size_t)rec * P.Q + q) * D * NP;
                 for (int e = tid; e < D * NP; e += NT) { P.tapeZ[base + e] = sIn[e]; P.tapeK[base + e] = sOut[e]; }

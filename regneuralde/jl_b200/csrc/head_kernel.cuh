@@ -225,4 +225,17 @@ __global__ void opt_update_kernel(float* __restrict__ p, const float* __restrict
     p[i] = p[i] + vn;
 }
 
+// Flux.Optimise.Optimiser(WeightDecay(wd), ADAM(eta, beta)) (experiments/ffjord_tabular.jl:128; Flux 0.11.6 apply!)
+__global__ void adam_update_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+                                   float eta, float b1, float b2, float b1p, float b2p, float eps, float wd) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float pi = p[i];
+    const float d = g[i] + wd * pi;
+    const float mn = b1 * m[i] + (1.f - b1) * d;
+    const float vn = b2 * v[i] + (1.f - b2) * d * d;
+    m[i] = mn; v[i] = vn;
+    p[i] = pi - mn / (1.f - b1p) / (sqrtf(vn / (1.f - b2p)) + eps) * eta;
+}
+
 }  // namespace rnde

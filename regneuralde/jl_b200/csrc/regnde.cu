@@ -56,6 +56,7 @@ struct rnde_handle {
     float* a6_zb = nullptr; float* a6_tau = nullptr; float* a6_kc = nullptr;
     size_t smem_a6 = 0;
     const float* noise = nullptr;       // FFJORD: caller-owned Hutchinson noise (rnde_set_noise)
+    int csq_reverse = 0;                // FFJORD: integrate the flow backwards (rnde_set_reverse_time)
     long long* dbg = nullptr;
     // host-path staging
     float *hx = nullptr, *hp = nullptr, *hu = nullptr, *hsv = nullptr, *hdu = nullptr, *hdsv = nullptr, *hdp = nullptr, *hdx = nullptr;
@@ -130,7 +131,7 @@ constexpr int NT_FWD = 256;
 typedef void (*kern_t)(const KParams);
 
 static kern_t fwd_kernel_for(int variant, int D = 0, int H = 0, int arith = 0, int csq = 0) {
-    if (csq > 0) return variant == RNDE_KERNEL_CHAIN ? fwd_kernel<1, 4, 1, true, NT_FWD, 1> : nullptr;
+    if (csq > 0) return variant == RNDE_KERNEL_CHAIN ? fwd_kernel<1, 4, 1, true, NT_FWD, 1> : (variant == RNDE_KERNEL_CHAIN8 ? fwd_kernel<1, 8, 1, true, NT_FWD, 1> : nullptr);
     switch (variant) {
         case RNDE_KERNEL_CTA: return fwd_kernel<1, 32, 4, true, NT_FWD>;
         case RNDE_KERNEL_STREAM: return fwd_kernel<1, 4, 1, false, NT_FWD>;
@@ -151,7 +152,7 @@ static bool bwd4_use_tc(int D, int H) {
 }
 // a6: the instantiation that also serves the first-dt term (a6.cuh); the plain one keeps the hot loop free of it
 static kern_t bwd_kernel_for(int variant, int D = 0, int H = 0, bool a6 = true, int csq = 0) {
-    if (csq > 0) return variant == RNDE_KERNEL_CHAIN ? bwd_kernel<1, 4, 1, true, NT_FWD, 1> : nullptr;
+    if (csq > 0) return variant == RNDE_KERNEL_CHAIN ? bwd_kernel<1, 4, 1, true, NT_FWD, 1> : (variant == RNDE_KERNEL_CHAIN8 ? bwd_kernel<1, 8, 1, true, NT_FWD, 1> : nullptr);
     switch (variant) {
         case RNDE_KERNEL_CTA: return bwd_kernel<1, 32, 4, true, NT_FWD>;
         case RNDE_KERNEL_STREAM: return bwd_kernel<1, 4, 1, false, NT_FWD>;
@@ -174,6 +175,7 @@ static void variant_shape(int variant, int* G, int* NP, bool* WS) {
         case RNDE_KERNEL_CTA: *G = 1; *NP = 32; *WS = true; break;
         case RNDE_KERNEL_STREAM: *G = 1; *NP = 4; *WS = false; break;
         case RNDE_KERNEL_CHAIN: *G = 1; *NP = 4; *WS = true; break;
+        case RNDE_KERNEL_CHAIN8: *G = 1; *NP = 8; *WS = true; break;
         case RNDE_KERNEL_CLUSTER4: *G = V2_G; *NP = V2_NP; *WS = true; break;
         default: *G = 8; *NP = 32; *WS = true; break;
     }
@@ -311,7 +313,8 @@ static int try_variant(rnde_handle* h, int variant, size_t smem_limit, std::stri
     const int nbl = (D + h->kblock - 1) / h->kblock;
     if (nbl > 64) { *why = "more than 64 canonical K-blocks"; return 0; }
     if (c.n_layers > 0 && variant != RNDE_KERNEL_CHAIN && variant != RNDE_KERNEL_CTA) { *why = "chain fields run on the CHAIN / CTA variants"; return 0; }
-    if (c.csq_extra > 0 && variant != RNDE_KERNEL_CHAIN) { *why = "the FFJORD field runs on the CHAIN variant (4-column tiles)"; return 0; }
+    if (c.csq_extra > 0 && variant != RNDE_KERNEL_CHAIN && variant != RNDE_KERNEL_CHAIN8) { *why = "the FFJORD field runs on the CHAIN variants (4- or 8-column tiles)"; return 0; }
+    if (c.csq_extra == 0 && variant == RNDE_KERNEL_CHAIN8) { *why = "the 8-column CHAIN variant serves FFJORD handles"; return 0; }
     const size_t sf = smem_bytes_fwd(variant, D, H, R, HS, h->kblock, c.arith) + sizeof(float) * (chain_smem_floats(c, NP, false) + csq_smem_floats(c, NP));
     const size_t sb = c.need_backward ? smem_bytes_bwd(variant, D, H, R, HS, h->kblock) + sizeof(float) * (chain_smem_floats(c, NP, true) + csq_bwd_smem_floats(c, NP)) : 0;
     if (sf > smem_limit || sb > smem_limit) { *why = "shared memory: need " + std::to_string(std::max(sf, sb)) + " B"; return 0; }
@@ -418,8 +421,9 @@ extern "C" int rnde_create(const rnde_config* cfg, rnde_handle** out) {
     } else {
         // chain fields: 4-column tiles while they give every SM at most one CTA, else 32-column tiles
         const bool chain4 = (cfg->n_layers > 0 && (cfg->batch + 3) / 4 <= h->num_sms) || cfg->csq_extra > 0;
-        const int order[4] = {chain4 ? RNDE_KERNEL_CHAIN : RNDE_KERNEL_CTA, chain4 ? RNDE_KERNEL_CTA : RNDE_KERNEL_CLUSTER4, RNDE_KERNEL_CLUSTER, RNDE_KERNEL_STREAM};
-        for (int i = 0; i < 4 && !ok; ++i) {
+        const int order[5] = {chain4 ? RNDE_KERNEL_CHAIN : RNDE_KERNEL_CTA, chain4 ? RNDE_KERNEL_CTA : RNDE_KERNEL_CLUSTER4, RNDE_KERNEL_CLUSTER, RNDE_KERNEL_STREAM,
+                              RNDE_KERNEL_CHAIN8};
+        for (int i = 0; i < 5 && !ok; ++i) {
             ok = try_variant(h, order[i], smem_limit, &why);
             if (!ok) all += "[variant " + std::to_string(order[i]) + ": " + why + "] ";
         }
@@ -559,6 +563,14 @@ extern "C" int rnde_set_forced_steps(rnde_handle* h, const float* dt_host, int32
     return RNDE_OK;
 }
 
+extern "C" int rnde_set_reverse_time(rnde_handle* h, int32_t reverse) {
+    if (!h) return RNDE_ERR_ARG;
+    if (h->cfg.csq_extra <= 0) return set_err(h, RNDE_ERR_STATE, "rnde_set_reverse_time: FFJORD handles only");
+    if (reverse && h->cfg.need_backward) return set_err(h, RNDE_ERR_UNSUPPORTED, "reverse-time solves are forward only");
+    h->csq_reverse = reverse ? 1 : 0;
+    return RNDE_OK;
+}
+
 extern "C" int rnde_set_noise(rnde_handle* h, const float* e_dev) {
     if (!h || !e_dev) return RNDE_ERR_ARG;
     if (h->cfg.csq_extra <= 0) return set_err(h, RNDE_ERR_STATE, "rnde_set_noise: the handle was not created with csq_extra");
@@ -637,7 +649,7 @@ static int forward_impl(rnde_handle* h, const float* x_dev, const float* p_dev, 
     if (h->cfg.csq_extra > 0) {
         if (!h->noise) return set_err(h, RNDE_ERR_STATE, "FFJORD handle: call rnde_set_noise first");
         bool WS; int G, NP; variant_shape(h->variant, &G, &NP, &WS);
-        P.noise = h->noise; P.csq_extra = h->cfg.csq_extra;
+        P.noise = h->noise; P.csq_extra = h->cfg.csq_extra; P.csq_reverse = h->csq_reverse;
         P.oCS = round_up(make_layout(G, NP, WS, h->cfg.state_dim, h->cfg.hidden_dim, h->R, h->HS, h->kblock).total, 4);
     }
     CUDA_TRY(h, cudaMemsetAsync(h->bar, 0, sizeof(unsigned) * 4, st));
@@ -980,6 +992,18 @@ extern "C" int rnde_opt_update(rnde_handle* h, float* p_dev, const float* g_dev,
     if (h) h->launches += 1;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_err(h, RNDE_ERR_CUDA, std::string("opt_update: ") + cudaGetErrorString(e));
+    return RNDE_OK;
+}
+
+extern "C" int rnde_adam_update(rnde_handle* h, float* p_dev, const float* g_dev, float* m_dev, float* v_dev, int64_t n, float eta, float beta1,
+                                float beta2, float beta1_pow, float beta2_pow, float eps, float weight_decay, void* stream) {
+    if (!p_dev || !g_dev || !m_dev || !v_dev || n < 0) return RNDE_ERR_ARG;
+    if (n == 0) return RNDE_OK;
+    adam_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p_dev, g_dev, m_dev, v_dev, (long long)n, eta, beta1, beta2,
+                                                                                     beta1_pow, beta2_pow, eps, weight_decay);
+    if (h) h->launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_err(h, RNDE_ERR_CUDA, std::string("adam_update: ") + cudaGetErrorString(e));
     return RNDE_OK;
 }
 

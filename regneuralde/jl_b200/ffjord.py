@@ -117,3 +117,43 @@ class TrackedFFJORD:
         logpz = (-(math.log(2 * math.pi) + z * z) / 2).sum(0)
         svals = SavedValues(torch.zeros(0), sv[: st.n_saved]) if self.regularize else None
         return logpz - delta_logp, lam1, lam2, int(st.nf), svals
+
+
+def sample(n: TrackedFFJORD, indims: int, p: Optional[torch.Tensor] = None, *, nsamples: int = 1, z: Optional[torch.Tensor] = None):
+    """sample(n, indims, p; nsamples) (src/models/ffjord.jl:160-167): draw z ~ N(0, I) and integrate the flow BACKWARDS over
+    [tspan[2], tspan[1]] -> generated data (indims, nsamples).  The reference integrates the deterministic augmented field
+    (exact trace) and drops the last row; the data rows do not depend on the trace row, so the library solves the same z-dynamics
+    with the trace estimator switched off (zero noise) through rnde_set_reverse_time.  ``z`` overrides the draw (tests)."""
+    p = n.p if p is None else p
+    if indims != n.model.D:
+        raise ValueError(f"indims must be {n.model.D}")
+    dev = p.device
+    zs = torch.randn(indims, nsamples, device=dev) if z is None else z.to(dev)
+    B = zs.shape[1]
+    hd = n._handle(B, 1, L.REG_NONE, False)
+    e0 = torch.zeros(indims * B, device=dev)
+    ubuf0 = colmajor(torch.cat([zs.to(torch.float32), torch.zeros(1, B, device=dev)], 0))
+    u = torch.empty((indims + 1) * B, device=dev, dtype=torch.float32)
+    sv = torch.zeros(hd.cfg.tape_capacity + 1, device=dev, dtype=torch.float32)
+    st = L.Stats()
+    hd.check(hd.lib.rnde_set_noise(hd.h, e0.data_ptr()), "rnde_set_noise")
+    hd.check(hd.lib.rnde_set_reverse_time(hd.h, 1), "rnde_set_reverse_time")
+    try:
+        rc = hd.lib.rnde_forward(hd.h, ubuf0.data_ptr(), p.detach().contiguous().data_ptr(), u.data_ptr(), sv.data_ptr(), C.byref(st), _stream_ptr())
+    finally:
+        hd.lib.rnde_set_reverse_time(hd.h, 0)
+    n.last_stats = st
+    hd.check(rc, "rnde_forward")
+    return from_colmajor(u, indims + 1, B)[:indims]
+
+
+def loss_and_gradient(n: TrackedFFJORD, x: torch.Tensor, p: torch.Tensor, e: Optional[torch.Tensor] = None, *, lam: float = 1.0e2):
+    """loss_function of experiments/ffjord_tabular.jl:137-141 and its Tracker.gradient: -mean(logpx) (+ lam * mean(sv.saveval) for the
+    regularised model).  Returns dict(loss, nll, reg, nfe, g)."""
+    pg = p.detach().requires_grad_(True)
+    logpx, _, _, nfe, sv = n(x, pg, e)
+    nll = -logpx.mean()
+    reg = lam * sv.saveval.mean() if n.regularize else torch.zeros((), device=x.device)
+    loss = nll + reg
+    (g,) = torch.autograd.grad(loss, [pg])
+    return {"loss": loss.detach(), "nll": nll.detach(), "reg": reg.detach(), "nfe": nfe, "g": g}

@@ -75,7 +75,7 @@ def test_ffjord_mirror_parameter_order_and_validation():
     h = C.c_void_p()
     cfg.csq_extra = 2
     assert L.lib().rnde_create(C.byref(cfg), C.byref(h)) == L.ERR_ARG
-    cfg.csq_extra, cfg.need_backward = 1, 1
+    cfg.csq_extra, cfg.dist_mode, cfg.nranks = 1, L.DIST_EXACT, 2      # the FFJORD field has no reference-exact data-parallel mode
     assert L.lib().rnde_create(C.byref(cfg), C.byref(h)) == L.ERR_UNSUPPORTED
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError):

@@ -9,7 +9,7 @@ sys.path.insert(0, ".")
 import regneuralde.jl_b200 as r
 from oracle import orc
 
-cases = sys.argv[1:] or ["toy", "stream", "mnist", "ffma4", "cluster8", "chain", "gru", "sde"]
+cases = sys.argv[1:] or ["toy", "stream", "mnist", "ffma4", "cluster8", "chain", "gru", "sde", "ffjord"]
 rng = np.random.default_rng(0)
 
 
@@ -53,6 +53,13 @@ for c in cases:
             out = nsde(x, nsde.p, func=r.ERROR_ESTIMATE)
         torch.cuda.synchronize()
         print(c, out[1], out[2])
+    elif c == "ffjord":     # forward + reverse sweep through the hand-differentiated ConcatSquash field, then the sampler
+        ff = r.TrackedFFJORD(r.CSQDynamics(6, 12), [0.0, 0.1], True, True, r.Tsit5(), tape_capacity=16)
+        x = torch.randn(6, 9, device="cuda"); p = ff.p.clone().requires_grad_(True)
+        logpx, l1, l2, nfe, sv = ff(x, p, torch.randn(6, 9, device="cuda"))
+        (logpx.sum() + sv.saveval.sum()).backward(); torch.cuda.synchronize()
+        r.ffjord.sample(ff, 6, ff.p, nsamples=5); torch.cuda.synchronize()
+        print(c, nfe)
     elif c == "gru":
         gru = r.LatentGRU(5, 6, 4)
         x = torch.randn(11, 5, 6, device="cuda"); p = gru.p.clone().requires_grad_(True)
