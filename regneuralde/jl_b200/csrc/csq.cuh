@@ -2,8 +2,8 @@
 // between them, evaluated together with the transposed-Jacobian product e^T J for a fixed Hutchinson noise column
 //   /root/reference/experiments/ffjord_tabular.jl:47-105 (ConcatSquashLinear, MLPDynamics, forw_n_back)
 //   /root/reference/src/models/ffjord.jl:53-66           (_ffjord: rows [f; -sum(eJ .* e) (; ||f||^2; ||eJ||^2)])
-// STATUS: the field evaluation only, reachable through the test hook rnde_test_csq_rhs and bit-identical to the C oracle on
-// a B200 (tests/test_gpu_ffjord.py); it is NOT yet wired into a stepper -- DESIGN.md section 9.
+// Runs inside the generic Tsit5 stepper (fwd_kernel<1,4|8,1,true,NT,FIELD=1>) and behind the test hook rnde_test_csq_rhs; bit-identical
+// to the C oracle on a B200 (tests/test_gpu_ffjord.py).  Its reverse pass is csq_bwd.cuh.
 // Canonical arithmetic = oracle/rnde_oracle.c csq_column: all six products through quad_dense (contraction index in four
 // contiguous quarters, (q0+q1)+(q2+q3)); layer r = fma(W x + B, g, fma(bW, t, bB)), g = canon_sigmoidf(G*t); the transposed
 // chain multiplies by the gate first; row sums are ascending fma chains from 0.
