@@ -366,4 +366,67 @@ function sde_forward(s::Ptr{Cvoid}, x::CuMatrix{Float32}, p::CuVector{Float32}, 
     u, Int(st.nfe1), Int(st.nfe2), sv[1:st.n_saved]
 end
 
+# ---- TrackedFFJORD (src/models/ffjord.jl:1-137, experiments/ffjord_tabular.jl:47-141) ----------------------------------
+# The model is the tabular experiment's MLPDynamics of three ConcatSquashLinear layers with its forw_n_back; p = destructure(model)
+# (per layer: layer_W, layer_B, bias_W, bias_B, gate_W -- the order the library expects).  The augmented state [z; delta_logp
+# (; |f|^2; |e^T J|^2)] is solved on the device; logpz stays in Julia as in the reference.
+struct TrackedFFJORD{R,P}
+    p::P
+    D::Int; H::Int
+    tspan::Vector{Float32}; alg::Int32; reltol::Float32; abstol::Float32
+    handles::Dict{Tuple{Int,Int32,Bool},Ptr{Cvoid}}
+end
+TrackedFFJORD(p, D, H, tspan, regularize, solver = :Tsit5; reltol = 1.4f-8, abstol = 1.4f-8) =
+    TrackedFFJORD{regularize,typeof(p)}(p, D, H, Float32.(tspan), _alg(solver), reltol, abstol, Dict())
+
+function handle!(n::TrackedFFJORD{R}, B, extra, need_backward) where {R}
+    get!(n.handles, (B, Int32(extra), need_backward)) do
+        cfg = Ref(RndeConfig(sizeof(RndeConfig), n.D + extra, n.H, B, 0, 0, 1, 0, n.alg, R ? REG_ERR_DT : REG_NONE, 0, 256, need_backward, 0, 0, 0, 1,
+                             n.tspan[1], n.tspan[2], n.abstol, n.reltol, 0f0, 0, 0, B, 0, ntuple(_ -> Int32(0), 8), ntuple(_ -> Int32(0), 8), ARITH_FMA_CHAIN, extra, 0))
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:rnde_create, LIB), Cint, (Ref{RndeConfig}, Ref{Ptr{Cvoid}}), cfg, h))
+        h[]
+    end
+end
+
+# (n::TrackedFFJORD{R})(x, p, e; regularize) -> (logpx, lambda1, lambda2, nfe, sv)       ffjord.jl:68-137
+function (n::TrackedFFJORD{R})(x, p = n.p, e = CUDA.randn(Float32, size(x)...); regularize = false) where {R}
+    extra = (regularize && !R) ? 3 : 1                                   # the {true} functor ignores the keyword (ffjord.jl:121)
+    B = size(x, 2)
+    h = handle!(n, B, extra, istracked(p) || istracked(x))
+    ed = data(e)
+    GC.@preserve ed check(ccall((:rnde_set_noise, LIB), Cint, (Ptr{Cvoid}, CuPtr{Float32}), h, ed), h)
+    u0 = vcat(x, CUDA.zeros(Float32, extra, B))
+    stub = (model = nothing, alg = n.alg)                                 # _solve / _solve_tracked only use the handle
+    pred, sv, st = (istracked(p) || istracked(x)) ? _solve_tracked(stub, h, u0, p) : _solve(stub, h, data(u0), data(p))
+    z, delta_logp = pred[1:n.D, :], pred[n.D+1, :]
+    logpz = vec(sum(-(log(2f0 * Float32(pi)) .+ z .* z) ./ 2, dims = 1))
+    l1, l2 = extra == 3 ? (pred[n.D+2, :], pred[n.D+3, :]) : (CUDA.zeros(Float32, B), CUDA.zeros(Float32, B))
+    logpz .- delta_logp, l1, l2, Int(st.nf), R ? SavedValuesB200(Float32[], sv) : nothing
+end
+
+# sample(n, indims, p; nsamples) (ffjord.jl:160-167): the flow integrated backwards over [tspan[2], tspan[1]]
+function sample(n::TrackedFFJORD, indims::Int, p = n.p; nsamples::Int = 1)
+    h = handle!(n, nsamples, 1, false)
+    e0 = CUDA.zeros(Float32, indims, nsamples)
+    GC.@preserve e0 check(ccall((:rnde_set_noise, LIB), Cint, (Ptr{Cvoid}, CuPtr{Float32}), h, e0), h)
+    check(ccall((:rnde_set_reverse_time, LIB), Cint, (Ptr{Cvoid}, Int32), h, 1), h)
+    u, _, _ = try
+        _solve((model = nothing, alg = n.alg), h, vcat(CUDA.randn(Float32, indims, nsamples), CUDA.zeros(Float32, 1, nsamples)), data(p))
+    finally
+        ccall((:rnde_set_reverse_time, LIB), Cint, (Ptr{Cvoid}, Int32), h, 0)
+    end
+    u[1:indims, :]
+end
+
+# update_parameters!(ps, gs, opt) with opt = Optimiser(WeightDecay(wd), ADAM(η, β)) on raw arrays (ffjord_tabular.jl:128); βp: the running
+# powers β.^t of this update, kept by the caller as Flux keeps them in the optimiser state
+function adam_update!(p::CuVector{Float32}, g::CuVector{Float32}, m::CuVector{Float32}, v::CuVector{Float32}, βp; wd = 1f-5, η = 1f-2, β = (0.9f0, 0.999f0), ϵ = 1f-8)
+    isempty(p) && return p
+    GC.@preserve p g m v check(ccall((:rnde_adam_update, LIB), Cint,
+        (Ptr{Cvoid}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, Int64, Cfloat, Cfloat, Cfloat, Cfloat, Cfloat, Cfloat, Cfloat, Ptr{Cvoid}),
+        C_NULL, p, g, m, v, length(p), η, β[1], β[2], βp[1], βp[2], ϵ, wd, CUDA.stream().handle))
+    p
+end
+
 end # module
