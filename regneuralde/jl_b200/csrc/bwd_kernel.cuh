@@ -89,6 +89,10 @@ __global__ void __launch_bounds__(NT, 1) bwd_kernel(const KParams P) {
             const int n = e / Dz, i = e - n * Dz;
             sE[i * NP + n] = (n < Nloc) ? __ldg(P.noise + (size_t)Dz * (c0 + n) + i) : 0.f;
         }
+        if (P.oCSP > 0) {
+            const int npar = csq_num_params(Dz, H);
+            for (int e = tid; e < npar; e += NT) smem[P.oCSP + e] = __ldg(P.p + e);
+        }
     }
     if constexpr (WS && FIELD == 0) if (!chain) {
         for (int e = tid; e < R * HP; e += NT) {       // W2T[k][m] = W2[r0+k, m]
@@ -124,7 +128,7 @@ __global__ void __launch_bounds__(NT, 1) bwd_kernel(const KParams P) {
             const size_t base = ((size_t)rec * P.Q + q) * (size_t)D * NP;
             for (int e = tid; e < D * NP; e += NT) sZc[e] = __ldcg(P.tapeZ + base + e);
             __syncthreads();
-            const float* zb = csq_vjp<NP, NT>(P.p, Dz, H, P.csq_extra, rec_time(P.steps, P.t0, rec), sZc, sE, sKbar,
+            const float* zb = csq_vjp<NP, NT>(P.oCSP > 0 ? smem + P.oCSP : P.p, Dz, H, P.csq_extra, rec_time(P.steps, P.t0, rec), sZc, sE, sKbar,
                                               P.tapeH + ((size_t)rec * P.Q + q) * (size_t)P.hrows * NP, csq_bwd_carve(sZc + D * NP, Dz, H, NP));
             for (int e = tid; e < Rloc * (NP / 4); e += NT) {
                 const int m = e / (NP / 4), nn = (e - m * (NP / 4)) * 4;

@@ -68,6 +68,7 @@ struct KParams {
     int n_layers; int lw[8]; int la[8]; int pre_act; int hrows; int chain_np; int oCW, oCA, oCB, oCH;
     // FFJORD field (csq.cuh): Hutchinson noise ((D - csq_extra) x B, column-major), augmented rows, shared-memory offset of its region
     const float* noise; int csq_extra; int oCS;
+    int oCSP;               // > 0: the FFJORD parameters are staged in shared memory at this offset (floats)
     int csq_reverse;        // 1: the field is -f(z, t0 + t1 - t): the flow integrated backwards (rnde_set_reverse_time, `sample`)
 };
 

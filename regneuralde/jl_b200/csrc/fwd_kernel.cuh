@@ -249,6 +249,10 @@ __global__ void __launch_bounds__(NT, 1) fwd_kernel(const KParams P) {
             const int n = e / Dz, i = e - n * Dz;
             sE[i * NP + n] = (n < Nloc) ? __ldg(P.noise + (size_t)Dz * (c0 + n) + i) : 0.f;
         }
+        if (P.oCSP > 0) {      // all parameters (78 KB for MLPDynamics(43, 100)) stay in shared memory for the whole solve
+            const int npar = csq_num_params(Dz, H);
+            for (int e = tid; e < npar; e += NT) smem[P.oCSP + e] = __ldg(P.p + e);
+        }
     } else if (!chain) {
         for (int m = tid; m < HP; m += NT) {
             sW1t[m] = (td && m < H) ? __ldg(gW1 + (size_t)H * D + m) : 0.f;
@@ -306,7 +310,7 @@ __global__ void __launch_bounds__(NT, 1) fwd_kernel(const KParams P) {
         if constexpr (FIELD == 1) {
             const int Dz = D - P.csq_extra;
             float* sE = smem + P.oCS;
-            csq_rhs<NP, NT>(P.p, Dz, H, P.csq_extra, P.csq_reverse ? (P.t0 + P.t1) - tstage : tstage, sIn, sE, sOut, csq_carve(sE + Dz * NP, Dz, H, NP));
+            csq_rhs<NP, NT>(P.oCSP > 0 ? smem + P.oCSP : P.p, Dz, H, P.csq_extra, P.csq_reverse ? (P.t0 + P.t1) - tstage : tstage, sIn, sE, sOut, csq_carve(sE + Dz * NP, Dz, H, NP));
             if (P.csq_reverse) {      // the flow backwards (`sample`, ffjord.jl:160-167)
                 for (int e = tid; e < D * NP; e += NT) sOut[e] = -sOut[e];
                 __syncthreads();

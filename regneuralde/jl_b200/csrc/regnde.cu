@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 #include <mutex>
@@ -57,6 +58,7 @@ struct rnde_handle {
     size_t smem_a6 = 0;
     const float* noise = nullptr;       // FFJORD: caller-owned Hutchinson noise (rnde_set_noise)
     int csq_reverse = 0;                // FFJORD: integrate the flow backwards (rnde_set_reverse_time)
+    int csq_stage = 0;                  // FFJORD: the parameters are staged in shared memory (one CTA per SM suffices and they fit)
     long long* dbg = nullptr;
     // host-path staging
     float *hx = nullptr, *hp = nullptr, *hu = nullptr, *hsv = nullptr, *hdu = nullptr, *hdsv = nullptr, *hdp = nullptr, *hdx = nullptr;
@@ -69,6 +71,22 @@ struct rnde_handle {
     int64_t launches = 0;
     std::string err;
 };
+
+// The opt-in dynamic shared-memory limit is a property of the KERNEL, shared by all handles that launch it: only ever raise it
+// (a later, smaller handle must not pull it below what an earlier handle still launches with).
+static std::mutex g_smem_mutex;
+static std::map<const void*, size_t> g_smem_attr;
+static cudaError_t raise_smem_limit(const void* kern, size_t bytes) {
+    std::lock_guard<std::mutex> lk(g_smem_mutex);
+    // per device: the attribute is per (function, device); key on both
+    int dev = 0; cudaGetDevice(&dev);
+    const void* key = reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(kern) ^ ((uintptr_t)(dev + 1) << 52));
+    size_t& cur = g_smem_attr[key];
+    if (bytes <= cur) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) cur = bytes;
+    return e;
+}
 
 static bool g_const_init[64] = {false};
 static std::mutex g_const_mutex;      // handles may be created from several host threads
@@ -315,8 +333,13 @@ static int try_variant(rnde_handle* h, int variant, size_t smem_limit, std::stri
     if (c.n_layers > 0 && variant != RNDE_KERNEL_CHAIN && variant != RNDE_KERNEL_CTA) { *why = "chain fields run on the CHAIN / CTA variants"; return 0; }
     if (c.csq_extra > 0 && variant != RNDE_KERNEL_CHAIN && variant != RNDE_KERNEL_CHAIN8) { *why = "the FFJORD field runs on the CHAIN variants (4- or 8-column tiles)"; return 0; }
     if (c.csq_extra == 0 && variant == RNDE_KERNEL_CHAIN8) { *why = "the 8-column CHAIN variant serves FFJORD handles"; return 0; }
-    const size_t sf = smem_bytes_fwd(variant, D, H, R, HS, h->kblock, c.arith) + sizeof(float) * (chain_smem_floats(c, NP, false) + csq_smem_floats(c, NP));
-    const size_t sb = c.need_backward ? smem_bytes_bwd(variant, D, H, R, HS, h->kblock) + sizeof(float) * (chain_smem_floats(c, NP, true) + csq_bwd_smem_floats(c, NP)) : 0;
+    size_t sf = smem_bytes_fwd(variant, D, H, R, HS, h->kblock, c.arith) + sizeof(float) * (chain_smem_floats(c, NP, false) + csq_smem_floats(c, NP));
+    size_t sb = c.need_backward ? smem_bytes_bwd(variant, D, H, R, HS, h->kblock) + sizeof(float) * (chain_smem_floats(c, NP, true) + csq_bwd_smem_floats(c, NP)) : 0;
+    int csq_stage = 0;
+    if (c.csq_extra > 0 && Q <= h->num_sms) {      // FFJORD: keep the parameters in shared memory when one CTA per SM is enough and they fit
+        const size_t pbytes = sizeof(float) * (size_t)round_up(csq_num_params(D - c.csq_extra, H), 4);
+        if (sf + pbytes <= smem_limit && (sb == 0 || sb + pbytes <= smem_limit)) { sf += pbytes; if (sb) sb += pbytes; csq_stage = 1; }
+    }
     if (sf > smem_limit || sb > smem_limit) { *why = "shared memory: need " + std::to_string(std::max(sf, sb)) + " B"; return 0; }
     // all CTAs must be co-resident (persistent grid with a grid barrier)
     if (c.arith == RNDE_ARITH_SPLITK && variant != RNDE_KERNEL_CLUSTER4) { *why = "RNDE_ARITH_SPLITK is implemented by the cluster-4 variant"; return 0; }
@@ -324,17 +347,17 @@ static int try_variant(rnde_handle* h, int variant, size_t smem_limit, std::stri
         *why = "RNDE_ARITH_FIXED24 is implemented by the cluster-4 variant for 128 < D/4 <= 256, H <= 128"; return 0;
     }
     kern_t kf = fwd_kernel_for(variant, D, H, c.arith, c.csq_extra);
-    if (cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sf) != cudaSuccess) { cudaGetLastError(); *why = "cudaFuncSetAttribute(fwd) failed"; return 0; }
+    if (raise_smem_limit((const void*)kf, sf) != cudaSuccess) { cudaGetLastError(); *why = "cudaFuncSetAttribute(fwd) failed"; return 0; }
     size_t sa = sb;
     if (c.need_backward) {
         for (int a = 0; a < 2; ++a) {      // both instantiations (with / without the first-dt additions)
             kern_t kb = bwd_kernel_for(variant, D, H, a != 0, c.csq_extra);
-            if (cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb) != cudaSuccess) { cudaGetLastError(); *why = "cudaFuncSetAttribute(bwd) failed"; return 0; }
+            if (raise_smem_limit((const void*)kb, sb) != cudaSuccess) { cudaGetLastError(); *why = "cudaFuncSetAttribute(bwd) failed"; return 0; }
         }
         if (variant == RNDE_KERNEL_CLUSTER4) {
             sa = (size_t)make_bwd_layout(4, 16, false, D, H, R, HS).total * sizeof(float);
             if (sa > smem_limit) { *why = "shared memory (initial-dt adjoint): need " + std::to_string(sa) + " B"; return 0; }
-            if (cudaFuncSetAttribute(a6_kernel_for(variant), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa) != cudaSuccess) { cudaGetLastError(); *why = "cudaFuncSetAttribute(a6) failed"; return 0; }
+            if (raise_smem_limit((const void*)a6_kernel_for(variant), sa) != cudaSuccess) { cudaGetLastError(); *why = "cudaFuncSetAttribute(a6) failed"; return 0; }
         }
     }
     int max_cta = 0;
@@ -364,7 +387,7 @@ static int try_variant(rnde_handle* h, int variant, size_t smem_limit, std::stri
         }
     }
     if (Q * G > max_cta) { *why = "grid of " + std::to_string(Q * G) + " CTAs exceeds co-resident capacity " + std::to_string(max_cta); return 0; }
-    h->variant = variant; h->G = G; h->NP = NP; h->R = R; h->HS = HS; h->Q = Q; h->smem_fwd = sf; h->smem_bwd = sb; h->smem_a6 = sa;
+    h->variant = variant; h->G = G; h->NP = NP; h->R = R; h->HS = HS; h->Q = Q; h->smem_fwd = sf; h->smem_bwd = sb; h->smem_a6 = sa; h->csq_stage = csq_stage;
     return 1;
 }
 
@@ -651,6 +674,7 @@ static int forward_impl(rnde_handle* h, const float* x_dev, const float* p_dev, 
         bool WS; int G, NP; variant_shape(h->variant, &G, &NP, &WS);
         P.noise = h->noise; P.csq_extra = h->cfg.csq_extra; P.csq_reverse = h->csq_reverse;
         P.oCS = round_up(make_layout(G, NP, WS, h->cfg.state_dim, h->cfg.hidden_dim, h->R, h->HS, h->kblock).total, 4);
+        if (h->csq_stage) P.oCSP = round_up(P.oCS + (int)csq_smem_floats(h->cfg, NP), 4);
     }
     CUDA_TRY(h, cudaMemsetAsync(h->bar, 0, sizeof(unsigned) * 4, st));
     int rc = launch(h, fwd_kernel_for(h->variant, h->cfg.state_dim, h->cfg.hidden_dim, h->cfg.arith, h->cfg.csq_extra), P, h->smem_fwd, st);
@@ -732,6 +756,7 @@ static int backward_impl(rnde_handle* h, const float* du_dev, const float* dusav
         bool WS; int G, NP; variant_shape(h->variant, &G, &NP, &WS);
         P.noise = h->noise; P.csq_extra = h->cfg.csq_extra;
         P.oCS = round_up(make_bwd_layout(G, NP, WS, h->cfg.state_dim, h->cfg.hidden_dim, h->R, h->HS).total, 4);
+        if (h->csq_stage) P.oCSP = round_up(P.oCS + (int)csq_bwd_smem_floats(h->cfg, NP), 4);
     }
     // Appendix A.6 (a6.cuh): the sweep also accumulates dL/d(dt_1); two more VJPs then differentiate the initial-dt heuristic.
     // Their records sit behind the last step: 6N+1..6N+5 empty, 6N+6 the evaluation f(u0 + dt0 f0, t0 + dt0).
@@ -1102,8 +1127,8 @@ extern "C" int rnde_gru_create(const rnde_gru_config* cfg, rnde_gru** out) {
         fprintf(stderr, "regnde: GRU weights (%d floats) do not fit shared memory\n", g->off.np);
         delete g; return RNDE_ERR_UNSUPPORTED;
     }
-    if (cudaFuncSetAttribute(gru_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_fwd) != cudaSuccess ||
-        cudaFuncSetAttribute(gru_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_bwd) != cudaSuccess) { cudaGetLastError(); delete g; return RNDE_ERR_CUDA; }
+    if (raise_smem_limit((const void*)gru_fwd_kernel, g->smem_fwd) != cudaSuccess ||
+        raise_smem_limit((const void*)gru_bwd_kernel, g->smem_bwd) != cudaSuccess) { cudaGetLastError(); delete g; return RNDE_ERR_CUDA; }
     if (cfg->need_backward) {
         const size_t blocks = (size_t)cfg->seq_len * g->Q * GRU_NP;
         if (cudaMalloc(&g->tapeA, sizeof(float) * blocks * g->off.arows) != cudaSuccess ||
@@ -1226,7 +1251,7 @@ extern "C" int64_t rnde_sde_launch_count(const rnde_sde* s) { return s ? s->laun
 
 template <int NP>
 static int sde_capacity(size_t smem, int num_sms, int* out) {
-    if (cudaFuncSetAttribute(sde_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (raise_smem_limit((const void*)sde_kernel<NP>, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sde_kernel<NP>, SDE_NT, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
     *out = per_sm * num_sms;
