@@ -275,6 +275,14 @@ const char* rnde_sde_last_error(const rnde_sde* s);
 int rnde_sde_forward(rnde_sde* s, const float* x_dev, const float* p_dev, const float* normals_dev, int32_t n_draws, float* u_out_dev,
                      float* saveval_dev, rnde_sde_stats* stats_host, void* stream);
 /* introspection for tests: (dt, EEst, accepted) of the first `cap` attempts of the last solve, host array of 3*cap floats */
+/* Reverse sweep of the solve (Tracker.gradient through solve(SDEProblem, SOSRI(); sensealg = SensitivityADPassThrough()),
+ * src/models/neural_sde.jl:84-146, experiments/mnist_nsde.jl:201-204): the discrete adjoint of the accepted steps with the step sizes
+ * and the Wiener increments frozen.  rnde_sde_enable_tape makes the following forward solves record their accepted steps (state,
+ * dW, dZ, dt, EEst; at most tape_capacity of them, RNDE_ERR_TAPE_FULL beyond); rnde_sde_backward then takes the cotangents of the
+ * final state (D x B, may be NULL) and of the saved values (rnde_sde_stats.n_saved entries, error-estimate regulariser only; may be
+ * NULL) and writes dp (num_params) and dx (D x B, may be NULL). */
+int rnde_sde_enable_tape(rnde_sde* s, int32_t tape_capacity);
+int rnde_sde_backward(rnde_sde* s, const float* du_dev, const float* dsaveval_dev, float* dp_dev, float* dx_dev, void* stream);
 int rnde_sde_get_log(rnde_sde* s, float* log_host, int32_t cap);
 int64_t rnde_sde_launch_count(const rnde_sde* s);
 

@@ -186,6 +186,7 @@ class SdeResult:
     eests: list = field(default_factory=list)
     draws: int = 0
     dt_init: float = 0.0
+    steps: list = field(default_factory=list)        # accepted steps: (dt, dW, dZ, EEst) -- what the discrete adjoint replays
 
 
 def rms(x):
@@ -302,6 +303,7 @@ def solve(x, f, g, normals, *, alg=ALG_SOSRI, reg_kind=REG_NONE, t0=0.0, t1=1.0,
         res.dts.append(dt); res.accepted.append(accept); res.eests.append(EEst)
         if accept:
             res.naccept += 1
+            res.steps.append((float(dt), np.array(dW, copy=True), np.array(dZ, copy=True), float(EEst)))
             qold = max(EEst, qoldinit)
             t = t + dt
             if abs(t1 - t) < 10 * np.finfo(dtype).eps * max(abs(t1), 1.0):
@@ -344,3 +346,56 @@ def classifier_nsde(x, p1, p2, p3, normals, *, trajectories=1, **kw):
     z = Wq @ r.u + bq[:, None]
     z = z.reshape(10, trajectories, B).mean(axis=1)
     return z, r
+
+
+def replay_torch(x, p, steps, *, alg=ALG_SOSRI, reg_kind=REG_NONE, abstol=0.14, reltol=0.14, D=32, H=64):
+    """The accepted steps of a solve replayed in torch (Float64) with the step sizes and the noise increments frozen: what
+    Tracker.gradient through solve(SDEProblem, SOSRI(); sensealg = SensitivityADPassThrough()) differentiates
+    (src/models/neural_sde.jl:84-146, experiments/mnist_nsde.jl:201-204; the proposed dt are detached like in the ODE path, the
+    Wiener increments come from the untracked RNG).  x: (D, B) tensor, p: flat tensor (vcat(p_drift, p_diffusion)), both may
+    require grad.  Returns (u_final, saved values as a tensor incl. the initial entry)."""
+    import torch
+    tab = SOSRI if alg == ALG_SOSRI else SOSRI2
+    T = {k: float(v) for k, v in tab.items()}
+    o = 0
+    W1 = p[o:o + H * D].reshape(D, H).T; o += H * D
+    b1 = p[o:o + H]; o += H
+    W2 = p[o:o + D * H].reshape(H, D).T; o += D * H
+    b2 = p[o:o + D]; o += D
+    Wg = p[o:o + D * D].reshape(D, D).T; o += D * D
+    bg = p[o:o + D]
+    F = lambda u: W2 @ torch.tanh(W1 @ u + b1[:, None]) + b2[:, None]
+    G = lambda u: Wg @ u + bg[:, None]
+    u = x
+    saved = [torch.zeros((), dtype=x.dtype)] if reg_kind != REG_NONE else []
+    delta = 1.0 / 26.0
+    for dt, dW, dZ, _ in steps:
+        dW = torch.as_tensor(np.asarray(dW, dtype=np.float64)); dZ = torch.as_tensor(np.asarray(dZ, dtype=np.float64))
+        sqdt = math.sqrt(dt)
+        chi1 = (dW * dW - dt) / (2 * sqdt)
+        chi2 = (dW + dZ / math.sqrt(3.0)) / 2
+        chi3 = (dW * dW * dW - 3 * dW * dt) / (6 * dt)
+        k1 = F(u); g1 = G(u)
+        H01 = u + dt * T["a021"] * k1 + T["b021"] * chi2 * g1
+        H11 = u + dt * T["a121"] * k1 + sqdt * T["b121"] * g1
+        k2 = F(H01); g2 = G(H11)
+        H02 = u + dt * (T["a031"] * k1 + T["a032"] * k2) + chi2 * (T["b031"] * g1 + T["b032"] * g2)
+        H12 = u + dt * (T["a131"] * k1 + T["a132"] * k2) + sqdt * (T["b131"] * g1 + T["b132"] * g2)
+        k3 = F(H02); g3 = G(H12)
+        H03 = u + dt * (T["a041"] * k1 + T["a042"] * k2 + T["a043"] * k3) + chi2 * (T["b041"] * g1 + T["b042"] * g2 + T["b043"] * g3)
+        H13 = u + dt * (T["a141"] * k1 + T["a142"] * k2 + T["a143"] * k3) + sqdt * (T["b141"] * g1 + T["b142"] * g2 + T["b143"] * g3)
+        k4 = F(H03); g4 = G(H13)
+        E2 = chi2 * (T["beta31"] * g1 + T["beta32"] * g2 + T["beta33"] * g3 + T["beta34"] * g4) + \
+            chi3 * (T["beta41"] * g1 + T["beta42"] * g2 + T["beta43"] * g3 + T["beta44"] * g4)
+        unew = u + dt * (T["al1"] * k1 + T["al2"] * k2 + T["al3"] * k3 + T["al4"] * k4) + E2 + \
+            dW * (T["beta11"] * g1 + T["beta12"] * g2 + T["beta13"] * g3 + T["beta14"] * g4) + \
+            chi1 * (T["beta21"] * g1 + T["beta22"] * g2 + T["beta23"] * g3 + T["beta24"] * g4)
+        if reg_kind == REG_ERR_DT:
+            E1 = dt * (k1 + k2 + k3 + k4)
+            resid = (delta * E1 + E2) / (abstol + torch.maximum(torch.abs(u), torch.abs(unew)) * reltol)
+            saved.append(torch.sqrt(torch.mean(resid * resid)) * dt)
+        elif reg_kind == REG_STIFF_SCALED:
+            eig = torch.sqrt(torch.mean((k4 - k3) ** 2)) / torch.sqrt(torch.mean((H03 - H02) ** 2))
+            saved.append(torch.abs(eig) / SOSRI2_STABILITY_SIZE)
+        u = unew
+    return u, (torch.stack(saved) if saved else None)

@@ -43,7 +43,7 @@ EXPORTS = [
     "rnde_set_saveat", "rnde_forward_saveat", "rnde_backward_saveat", "rnde_set_noise",
     "rnde_gru_num_params", "rnde_gru_create", "rnde_gru_destroy", "rnde_gru_last_error", "rnde_gru_forward", "rnde_gru_backward",
     "rnde_gru_launch_count", "rnde_reg_agg", "rnde_last_stats", "rnde_allreduce_grads",
-    "rnde_sde_num_params", "rnde_sde_create", "rnde_sde_destroy", "rnde_sde_last_error", "rnde_sde_forward", "rnde_sde_get_log", "rnde_sde_launch_count",
+    "rnde_sde_num_params", "rnde_sde_create", "rnde_sde_destroy", "rnde_sde_last_error", "rnde_sde_forward", "rnde_sde_enable_tape", "rnde_sde_backward", "rnde_sde_get_log", "rnde_sde_launch_count",
 ]
 
 
@@ -195,6 +195,8 @@ def lib() -> C.CDLL:
     L.rnde_sde_last_error.argtypes = [vp]
     L.rnde_sde_last_error.restype = C.c_char_p
     L.rnde_sde_forward.argtypes = [vp, vp, vp, vp, C.c_int32, vp, vp, C.POINTER(SdeStats), vp]
+    L.rnde_sde_enable_tape.argtypes = [vp, C.c_int32]
+    L.rnde_sde_backward.argtypes = [vp, vp, vp, vp, vp, vp]
     L.rnde_sde_get_log.argtypes = [vp, fp, C.c_int32]
     L.rnde_sde_launch_count.argtypes = [vp]
     L.rnde_sde_launch_count.restype = C.c_int64

@@ -25,6 +25,7 @@
 #include "gru_kernel.cuh"
 #include "csq.cuh"
 #include "sde_kernel.cuh"
+#include "sde_bwd.cuh"
 
 using namespace rnde;
 
@@ -1197,6 +1198,9 @@ struct rnde_sde {
     size_t smem = 0;
     double* partial = nullptr; float* stacks = nullptr; unsigned* bar = nullptr; SdeStats* stats = nullptr; float* log = nullptr; float* saveval_int = nullptr;
     int log_cap = 4096;
+    // reverse sweep (rnde_sde_enable_tape / rnde_sde_backward)
+    float* tape = nullptr; float* tape_steps = nullptr; float* gpart = nullptr; int tape_cap = 0; size_t smem_bwd = 0;
+    const float* last_p = nullptr; bool have_tape = false;
     int64_t launches = 0;
     std::string err;
 };
@@ -1299,6 +1303,7 @@ extern "C" void rnde_sde_destroy(rnde_sde* s) {
     if (!s) return;
     DeviceScope scope(s->device);
     cudaFree(s->partial); cudaFree(s->stacks); cudaFree(s->bar); cudaFree(s->stats); cudaFree(s->log); cudaFree(s->saveval_int);
+    cudaFree(s->tape); cudaFree(s->tape_steps); cudaFree(s->gpart);
     delete s;
 }
 
@@ -1315,6 +1320,8 @@ extern "C" int rnde_sde_forward(rnde_sde* s, const float* x_dev, const float* p_
     P.max_saved = c.max_saved; P.n_draws = n_draws; P.t0 = c.t0; P.t1 = c.t1; P.abstol = c.abstol; P.reltol = c.reltol;
     P.x = x_dev; P.p = p_dev; P.normals = normals_dev; P.u_out = u_out_dev; P.saveval = saveval_dev ? saveval_dev : s->saveval_int;
     P.partial = s->partial; P.stacks = s->stacks; P.bar = s->bar; P.stats = s->stats; P.log = s->log; P.log_cap = s->log_cap;
+    P.tape = s->tape; P.tape_steps = s->tape_steps; P.tape_cap = s->tape_cap;
+    s->last_p = p_dev; s->have_tape = s->tape != nullptr;
     if (cudaMemsetAsync(s->bar, 0, sizeof(unsigned) * 4, st) != cudaSuccess) return sde_err(s, RNDE_ERR_CUDA, "cudaMemsetAsync");
     if (s->NP == 4) sde_kernel<4><<<s->Q, SDE_NT, s->smem, st>>>(P);
     else if (s->NP == 8) sde_kernel<8><<<s->Q, SDE_NT, s->smem, st>>>(P);
@@ -1331,6 +1338,53 @@ extern "C" int rnde_sde_forward(rnde_sde* s, const float* x_dev, const float* p_
         stats_host->t_final = h.t_final; stats_host->dt_init = h.dt_init; stats_host->dt_last = h.dt_last; stats_host->reserved2 = 0.f;
         if (h.retcode != RNDE_OK) return sde_err(s, h.retcode, h.retcode == RNDE_ERR_ARG ? "the supplied normals ran out" : rnde_status_string(h.retcode));
     }
+    return RNDE_OK;
+}
+
+extern "C" int rnde_sde_enable_tape(rnde_sde* s, int32_t tape_capacity) {
+    if (!s || tape_capacity <= 0) return RNDE_ERR_ARG;
+    DeviceScope scope(s->device);
+    if (scope.err != cudaSuccess) return sde_err(s, RNDE_ERR_CUDA, "selecting the handle's device");
+    const rnde_sde_config& c = s->cfg;
+    const int D = c.state_dim, H = c.hidden_dim;
+    const int np = H * D + H + D * H + D + D * D + D;
+    cudaFree(s->tape); cudaFree(s->tape_steps); cudaFree(s->gpart);
+    s->tape = nullptr; s->tape_steps = nullptr; s->gpart = nullptr; s->tape_cap = 0; s->have_tape = false;
+    const size_t smem = sizeof(float) * (size_t)sde_bwd_smem_floats(D, H, np, s->NP);
+    int dev = 0, smem_limit = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (smem > (size_t)smem_limit) return sde_err(s, RNDE_ERR_UNSUPPORTED, "reverse sweep: shared memory");
+    const void* k = s->NP == 4 ? (const void*)sde_bwd_kernel<4> : (s->NP == 8 ? (const void*)sde_bwd_kernel<8> : (const void*)sde_bwd_kernel<16>);
+    if (raise_smem_limit(k, smem) != cudaSuccess) { cudaGetLastError(); return sde_err(s, RNDE_ERR_CUDA, "cudaFuncSetAttribute(sde_bwd)"); }
+    const size_t T = (size_t)D * s->NP;
+    if (cudaMalloc(&s->tape, sizeof(float) * (size_t)tape_capacity * s->Q * 3 * T) != cudaSuccess ||
+        cudaMalloc(&s->tape_steps, sizeof(float) * 2 * (size_t)tape_capacity) != cudaSuccess ||
+        cudaMalloc(&s->gpart, sizeof(float) * (size_t)s->Q * np) != cudaSuccess) { cudaGetLastError(); return sde_err(s, RNDE_ERR_CUDA, "cudaMalloc (tape)"); }
+    s->tape_cap = tape_capacity; s->smem_bwd = smem;
+    return RNDE_OK;
+}
+
+extern "C" int rnde_sde_backward(rnde_sde* s, const float* du_dev, const float* dsaveval_dev, float* dp_dev, float* dx_dev, void* stream) {
+    if (!s || !dp_dev || (!du_dev && !dsaveval_dev)) return RNDE_ERR_ARG;
+    if (!s->have_tape) return sde_err(s, RNDE_ERR_STATE, "rnde_sde_backward needs rnde_sde_enable_tape and a forward solve on this handle first");
+    if (s->cfg.reg_kind == RNDE_REG_STIFF_SCALED && dsaveval_dev) return sde_err(s, RNDE_ERR_UNSUPPORTED, "the stiffness-estimate regulariser has no reverse sweep yet");
+    DeviceScope scope(s->device);
+    if (scope.err != cudaSuccess) return sde_err(s, RNDE_ERR_CUDA, "selecting the handle's device");
+    cudaStream_t st = (cudaStream_t)stream;
+    const rnde_sde_config& c = s->cfg;
+    SdeBwdParams P; memset(&P, 0, sizeof(P));
+    P.D = c.state_dim; P.H = c.hidden_dim; P.B = c.batch; P.Q = s->Q; P.alg = c.alg; P.reg_kind = c.reg_kind; P.tape_cap = s->tape_cap;
+    P.abstol = c.abstol; P.reltol = c.reltol; P.p = s->last_p; P.tape = s->tape; P.tape_steps = s->tape_steps; P.stats = s->stats;
+    P.du = du_dev; P.dsaveval = (c.reg_kind == RNDE_REG_ERR_DT) ? dsaveval_dev : nullptr; P.dx = dx_dev; P.gpart = s->gpart;
+    if (s->NP == 4) sde_bwd_kernel<4><<<s->Q, SDE_NT, s->smem_bwd, st>>>(P);
+    else if (s->NP == 8) sde_bwd_kernel<8><<<s->Q, SDE_NT, s->smem_bwd, st>>>(P);
+    else sde_bwd_kernel<16><<<s->Q, SDE_NT, s->smem_bwd, st>>>(P);
+    const int np = c.hidden_dim * c.state_dim + c.hidden_dim + c.state_dim * c.hidden_dim + c.state_dim + c.state_dim * c.state_dim + c.state_dim;
+    sde_grad_reduce_kernel<<<(np + 255) / 256, 256, 0, st>>>(s->gpart, s->Q, np, dp_dev);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return sde_err(s, RNDE_ERR_CUDA, std::string("sde_bwd_kernel launch: ") + cudaGetErrorString(e));
+    s->launches += 2;
     return RNDE_OK;
 }
 

@@ -37,6 +37,8 @@ struct SdeParams {
     unsigned* bar;
     SdeStats* stats;
     float* log; int log_cap;      // per attempt: dt, EEst, accepted
+    // tape of the accepted steps for the reverse sweep (sde_bwd.cuh): [step][Q][3][D * NP] = state at the step's start, dW, dZ; [step][2] = dt, EEst
+    float* tape; float* tape_steps; int tape_cap;
 };
 
 // the 51 coefficients of a four-stage SRI tableau (filled by the host from the same Float64 literals as the oracle)
@@ -414,6 +416,14 @@ __global__ void __launch_bounds__(SDE_NT) sde_kernel(const SdeParams P) {
             qold = fmax(EEst, qoldinit);
             t = t + dt;
             if (fabs((double)P.t1 - t) < 10.0 * 1.1920928955078125e-07 * fmax(fabs((double)P.t1), 1.0)) t = (double)P.t1;
+            if (P.tape) {
+                if (naccept <= P.tape_cap) {
+                    float* tp = P.tape + (((size_t)(naccept - 1) * P.Q + q) * 3) * T;
+                    for (int e = tid; e < T; e += NT) { tp[e] = sU[e]; tp[T + e] = sdW[e]; tp[2 * T + e] = sdZ[e]; }
+                    if (q == 0 && tid == 0) { P.tape_steps[2 * (naccept - 1)] = dtc; P.tape_steps[2 * (naccept - 1) + 1] = (float)EEst; }
+                } else retcode = RNDE_ERR_TAPE_FULL;
+                __syncthreads();
+            }
             for (int e = tid; e < T; e += NT) sU[e] = sUn[e];
             dt_last = (float)dt;
             if (P.reg_kind != RNDE_REG_NONE) {

@@ -1,4 +1,4 @@
-"""Neural-SDE model surface over libregnde.so -- FORWARD SOLVES ONLY.
+"""Neural-SDE model surface over libregnde.so: forward solves and, since the end of round 2, their gradient.
 
     TrackedNeuralDSDE(model1, model2, tspan, regularize, solver; reltol, abstol, ...)      src/models/neural_sde.jl:1-42
     (n::TrackedNeuralDSDE{R,false})(x, p; func) -> (res, nfe1, nfe2, sv)                   src/models/neural_sde.jl:84-146
@@ -11,7 +11,10 @@ The adaptive SOSRI / SOSRI2 solve with the RSwM3 noise bookkeeping is ONE persis
 (csrc/sde_kernel.cuh).  The reference draws its Wiener increments from Julia's MersenneTwister, which cannot be reproduced:
 the functor takes the standard normals as the ``noise`` keyword ((n_draws, D, B) tensor; default: torch.randn on the device) and
 consumes them in the order documented in include/regnde.h.  The pre / post Dense layers and the mean over trajectories are the
-host glue the reference keeps in Flux.  There is no backward: calling with gradients enabled on p raises."""
+host glue the reference keeps in Flux.  With gradients enabled the solve tapes its accepted steps and torch autograd reaches it
+through _SdeSolve: the reverse sweep (csrc/sde_bwd.cuh) is the discrete adjoint of those steps with step sizes and Wiener
+increments frozen -- Tracker.gradient through solve(...; sensealg = SensitivityADPassThrough()) (mnist_nsde.jl:201-204).  The
+error-estimate regulariser is differentiated; the stiffness-estimate one (AutoSOSRI2) is forward only."""
 from __future__ import annotations
 
 import ctypes as C
@@ -55,13 +58,47 @@ class _SdeHandle:
             pass
 
 
+class _SdeSolve(torch.autograd.Function):
+    """Glue between torch autograd and rnde_sde_forward / rnde_sde_backward."""
+
+    @staticmethod
+    def forward(ctx, xbuf: torch.Tensor, p: torch.Tensor, node, hd, nz: torch.Tensor):
+        D, B = node.D, hd.cfg.batch
+        u = torch.empty(D * B, device=xbuf.device, dtype=torch.float32)
+        sv = torch.zeros(hd.cfg.max_saved if hd.cfg.max_saved > 0 else 1024, device=xbuf.device, dtype=torch.float32)
+        st = L.SdeStats()
+        rc = hd.lib.rnde_sde_forward(hd.h, xbuf.data_ptr(), p.data_ptr(), nz.data_ptr(), nz.shape[0], u.data_ptr(), sv.data_ptr(), C.byref(st), _stream_ptr())
+        node.last_stats, node.last_handle = st, hd
+        hd.check(rc, "rnde_sde_forward")
+        hd.serial = getattr(hd, "serial", 0) + 1
+        ctx.serial, ctx.hd, ctx.n_saved, ctx.p_ref, ctx.shape = hd.serial, hd, int(st.n_saved), p, (D, B)
+        return u, sv[: st.n_saved]
+
+    @staticmethod
+    def backward(ctx, du, dsv):
+        hd = ctx.hd
+        if ctx.serial != hd.serial:
+            raise RuntimeError("the tape of this SDE solve was overwritten by a later solve on the same handle")
+        D, B = ctx.shape
+        dev = ctx.p_ref.device
+        du = du.contiguous() if du is not None else torch.zeros(D * B, device=dev)
+        dsv_full = torch.zeros(max(ctx.n_saved, 1), device=dev, dtype=torch.float32)
+        if dsv is not None and ctx.n_saved > 0:
+            dsv_full[: ctx.n_saved] = dsv
+        dp = torch.empty(ctx.p_ref.numel(), device=dev, dtype=torch.float32)
+        dx = torch.empty(D * B, device=dev, dtype=torch.float32)
+        hd.check(hd.lib.rnde_sde_backward(hd.h, du.data_ptr(), dsv_full.data_ptr() if ctx.n_saved > 0 else None, dp.data_ptr(), dx.data_ptr(), _stream_ptr()),
+                 "rnde_sde_backward")
+        return dx, dp, None, None, None
+
+
 class TrackedNeuralDSDE:
     """src/models/neural_sde.jl:1-42.  model1 = drift Chain(Dense(D,H,tanh), Dense(H,D)), model2 = diffusion Dense(D,D);
     p = vcat(p1, p2) (neural_sde.jl:16-18)."""
 
     def __init__(self, model1: Chain, model2: Dense, tspan: Sequence[float], regularize: bool, solver=SOSRI(), *, reltol: float = 1.4e-1,
                  abstol: float = 1.4e-1, save_everystep: bool = False, save_start: bool = False, maxiters: int = 0, max_saved: int = 1024,
-                 device: str = "cuda"):
+                 device: str = "cuda", tape_capacity: int = 1024):
         if save_everystep:
             raise NotImplementedError("the multi-save functors {R,true} have no call site in the reference experiments")
         if not (isinstance(model1, Chain) and len(model1.layers) == 2 and model1.pre_act == 0 and model1.layers[0].act == L.ACT_TANH
@@ -80,12 +117,13 @@ class TrackedNeuralDSDE:
         self.tspan = (float(tspan[0]), float(tspan[1]))
         self.regularize, self.solver = bool(regularize), solver
         self.reltol, self.abstol, self.maxiters, self.max_saved = float(reltol), float(abstol), maxiters, max_saved
+        self.tape_capacity = int(tape_capacity)
         self._handles: dict = {}
         self.last_stats: Optional[L.SdeStats] = None
         self.last_handle: Optional[_SdeHandle] = None
 
-    def _handle(self, B: int, reg_kind: int) -> _SdeHandle:
-        key = (B, reg_kind)
+    def _handle(self, B: int, reg_kind: int, need_backward: bool = False) -> _SdeHandle:
+        key = (B, reg_kind, need_backward)
         if key not in self._handles:
             cfg = L.SdeConfig()
             cfg.struct_bytes = C.sizeof(L.SdeConfig)
@@ -93,7 +131,10 @@ class TrackedNeuralDSDE:
             cfg.alg, cfg.reg_kind, cfg.max_steps, cfg.max_saved = self.solver.alg, reg_kind, self.maxiters, self.max_saved
             cfg.t0, cfg.t1 = self.tspan
             cfg.abstol, cfg.reltol = self.abstol, self.reltol
-            self._handles[key] = _SdeHandle(cfg)
+            hd = _SdeHandle(cfg)
+            if need_backward:
+                hd.check(hd.lib.rnde_sde_enable_tape(hd.h, self.tape_capacity), "rnde_sde_enable_tape")
+            self._handles[key] = hd
         return self._handles[key]
 
     def __call__(self, x: torch.Tensor, p: Optional[torch.Tensor] = None, *, func: Optional[SaveFunc] = None, noise: Optional[torch.Tensor] = None):
@@ -103,8 +144,7 @@ class TrackedNeuralDSDE:
             raise ValueError(f"x must be ({self.D}, B)")
         if not x.is_cuda or not p.is_cuda:
             raise RuntimeError("regneuralde.jl_b200 runs on CUDA tensors only (no CPU fallback)")
-        if torch.is_grad_enabled() and (p.requires_grad or x.requires_grad):
-            raise NotImplementedError("the Neural-SDE path is forward only so far (no Tracker.gradient through the SDE solve); use torch.no_grad()")
+        need_bwd = torch.is_grad_enabled() and (p.requires_grad or x.requires_grad)
         B = x.shape[1]
         if self.regularize:
             func = ERROR_ESTIMATE if func is None else func          # default of neural_sde.jl:119
@@ -117,8 +157,17 @@ class TrackedNeuralDSDE:
             noise = torch.randn(256, self.D, B, device=x.device, dtype=torch.float32)
         if tuple(noise.shape[1:]) != (self.D, B) or noise.dtype != torch.float32 or not noise.is_cuda:
             raise ValueError(f"noise must be a CUDA Float32 tensor of shape (n_draws, {self.D}, {B})")
-        hd = self._handle(B, reg_kind)
+        if need_bwd and reg_kind == L.REG_STIFF_SCALED:
+            raise NotImplementedError("the stiffness-estimate regulariser of the SDE path has no reverse sweep; the error-estimate one has")
+        hd = self._handle(B, reg_kind, need_bwd)
         xbuf = colmajor(x.to(torch.float32))
+        if need_bwd:
+            ubuf, saveval = _SdeSolve.apply(xbuf, p.contiguous(), self, hd, noise.contiguous())
+            st = self.last_stats
+            res = from_colmajor(ubuf, self.D, B)
+            if not self.regularize:
+                return res, int(st.nfe1), int(st.nfe2), None
+            return res, int(st.nfe1), int(st.nfe2), SavedValues(torch.zeros(0), saveval)
         u = torch.empty(self.D * B, device=x.device, dtype=torch.float32)
         sv = torch.zeros(hd.cfg.max_saved if hd.cfg.max_saved > 0 else 1024, device=x.device, dtype=torch.float32)
         st = L.SdeStats()

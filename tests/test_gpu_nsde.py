@@ -100,3 +100,54 @@ def test_classifier_nsde_and_errors():
     pp = torch.from_numpy(p2).cuda().requires_grad_(True)
     with pytest.raises(NotImplementedError):
         node(torch.zeros(32, B * traj, device="cuda"), pp, noise=torch.from_numpy(z).cuda())
+
+
+# ---- the gradient (round 2): csrc/sde_bwd.cuh against torch autograd through the replayed accepted steps -------------------------
+
+GRAD_CASES = [
+    # name, D, H, B, tol, regularize, weight scale
+    ("mnist_nsde shape B=48 error_est", 32, 64, 48, 0.14, True, 1.0),
+    ("unregularised, ragged tile", 32, 64, 33, 0.14, False, 1.0),
+    ("tight tolerance, inflated weights (rejections on the way)", 32, 64, 7, 0.02, True, 3.0),
+    ("generic dims D=12 H=20", 12, 20, 9, 0.05, True, 3.0),
+    ("8-column tiles", 32, 64, 3000, 0.14, True, 1.0),
+]
+
+
+@pytest.mark.parametrize("name,D,H,B,tol,regularize,scale", GRAD_CASES, ids=[c[0] for c in GRAD_CASES])
+def test_sde_gradient_matches_the_replayed_adjoint(name, D, H, B, tol, regularize, scale):
+    """Tracker.gradient through the SDE solve (experiments/mnist_nsde.jl:201-204): random cotangents on the final state and on the
+    saved values EEst * dt.  Yardstick: torch autograd (Float64) through oracle/sde_oracle.py replay_torch -- the accepted steps of
+    the ORACLE's solve with its step sizes and Wiener increments frozen; the CUDA solve takes the same accept/reject decisions
+    (asserted), so both differentiate the same discrete map.  Bar: 1e-4 relative (Float32 sweep against a Float64 replay)."""
+    import regneuralde.jl_b200 as r
+    p_np, x_np, z_np = make(1999, D, H, B, ndraw=120 if B > 1000 else 400, scale=scale)
+    node = node_for(D, H, regularize, r.SOSRI(), tol)
+    p = torch.from_numpy(p_np).cuda().requires_grad_(True)
+    x = torch.from_numpy(x_np).cuda().requires_grad_(True)
+    func = r.ERROR_ESTIMATE if regularize else None
+    res, nfe1, nfe2, sv = node(x, p, func=func, noise=torch.from_numpy(z_np).cuda())
+    f, g = S.drift_diffusion(p_np, np.float32, D, H)
+    ref = S.solve(x_np, f, g, z_np, alg=S.ALG_SOSRI, reg_kind=S.REG_ERR_DT if regularize else S.REG_NONE, abstol=tol, reltol=tol)
+    st = node.last_stats
+    assert (st.naccept, st.nreject, nfe1, nfe2) == (ref.naccept, ref.nreject, ref.nfe1, ref.nfe2)
+    rng = np.random.default_rng(5)
+    w = rng.standard_normal((D, B)).astype(np.float32)
+    loss = (res * torch.from_numpy(w).cuda()).sum()
+    ws = None
+    if regularize:
+        ws = rng.standard_normal(len(ref.saveval)).astype(np.float32)
+        loss = loss + (sv.saveval * torch.from_numpy(ws).cuda()).sum()
+    loss.backward()
+    torch.cuda.synchronize()
+    pt = torch.tensor(p_np.astype(np.float64), requires_grad=True)
+    xt = torch.tensor(x_np.astype(np.float64), requires_grad=True)
+    u64, sv64 = S.replay_torch(xt, pt, ref.steps, alg=S.ALG_SOSRI, reg_kind=S.REG_ERR_DT if regularize else S.REG_NONE, abstol=tol, reltol=tol, D=D, H=H)
+    l64 = (u64 * torch.tensor(w.astype(np.float64))).sum()
+    if regularize:
+        l64 = l64 + (sv64 * torch.tensor(ws.astype(np.float64))).sum()
+    gp, gx = torch.autograd.grad(l64, [pt, xt])
+    rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()
+    e_p, e_x = rel(p.grad.cpu().numpy(), gp.numpy()), rel(x.grad.cpu().numpy(), gx.numpy())
+    print(f"sde grad {name}: e_p {e_p:.2e} e_x {e_x:.2e} naccept {ref.naccept} nreject {ref.nreject}")
+    assert e_p <= 1e-4 and e_x <= 1e-4, (e_p, e_x)
