@@ -575,6 +575,20 @@ def secondary_workloads(torch, R, peak) -> dict:
         out["neural_sde"] = {"workload": f"mnist_nsde forward solve (SOSRI, {D}-dim state, batch {B}, tol 1.4e-1, supplied noise)", "ms_per_solve": ms,
                              "samples_per_s": B / (ms * 1e-3), "nfe1": info["nfe"][0], "nfe2": info["nfe"][1], "naccept": int(node.last_stats.naccept),
                              "nreject": int(node.last_stats.nreject)}
+        # the training step of experiments/mnist_nsde.jl:89-110,191-204: Dense(784,32) -> SDE solve -> Dense(32,10), logitcrossentropy +
+        # lam * mean(EEst dt), Tracker.gradient, Optimiser(InvDecay(1e-5), ADAM(0.01)); trajectories = 1 as in training
+        gen = torch.Generator().manual_seed(SEED)
+        clf = R.ClassifierNSDE(R.Dense(784, D, generator=gen), node, R.Dense(D, 10, generator=gen))
+        xi = torch.rand(784, B, generator=gen).cuda()
+        yi = torch.nn.functional.one_hot(torch.randint(0, 10, (B,), generator=gen), 10).T.float().cuda()
+        opt = R.ADAMOptimiser(0.0, 0.01, inv_decay=1e-5)
+
+        def train():
+            o = clf.loss_and_gradient(xi, yi, lam=1.0e2, trajectories=1, func=R.ERROR_ESTIMATE, noise=z)
+            R.update_parameters_((clf.p1, clf.p2, clf.p3), (o["g1"], o["g2"], o["g3"]), opt)
+
+        out["neural_sde"]["train_ms_per_step"] = timed(train, 5, 2)
+        out["neural_sde"]["train_samples_per_s"] = B / (out["neural_sde"]["train_ms_per_step"] * 1e-3)
     except Exception as ex:
         out["neural_sde"] = {"error": repr(ex)[:200]}
     try:

@@ -366,6 +366,18 @@ function sde_forward(s::Ptr{Cvoid}, x::CuMatrix{Float32}, p::CuVector{Float32}, 
     u, Int(st.nfe1), Int(st.nfe2), sv[1:st.n_saved]
 end
 
+# Tracker.gradient through the SDE solve (mnist_nsde.jl:201-204): sde_enable_tape once per handle, then sde_backward after a forward
+sde_enable_tape(s::Ptr{Cvoid}, cap = 1024) = (ccall((:rnde_sde_enable_tape, LIB), Cint, (Ptr{Cvoid}, Int32), s, cap) == 0 || error("regnde: tape"); s)
+function sde_backward(s::Ptr{Cvoid}, du::CuMatrix{Float32}, dsv::CuVector{Float32}, np::Int)
+    dp = CUDA.zeros(Float32, np); dx = similar(du)
+    GC.@preserve du dsv dp dx begin
+        rc = ccall((:rnde_sde_backward, LIB), Cint, (Ptr{Cvoid}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, Ptr{Cvoid}),
+                   s, du, dsv, dp, dx, CUDA.stream().handle)
+        rc == 0 || error("regnde: ", unsafe_string(ccall((:rnde_sde_last_error, LIB), Cstring, (Ptr{Cvoid},), s)))
+    end
+    dx, dp
+end
+
 # ---- TrackedFFJORD (src/models/ffjord.jl:1-137, experiments/ffjord_tabular.jl:47-141) ----------------------------------
 # The model is the tabular experiment's MLPDynamics of three ConcatSquashLinear layers with its forw_n_back; p = destructure(model)
 # (per layer: layer_W, layer_B, bias_W, bias_B, gate_W -- the order the library expects).  The augmented state [z; delta_logp

@@ -132,14 +132,15 @@ class ADAMOptimiser:
     """Flux.Optimise.Optimiser(WeightDecay(wd), ADAM(eta, beta)) -- experiments/ffjord_tabular.jl:128 (Flux 0.11.6: eps = 1e-8, the
     running powers beta^t live in the per-parameter state)."""
 
-    def __init__(self, weight_decay: float = 1.0e-5, eta: float = 1.0e-2, beta=(0.9, 0.999), eps: float = 1.0e-8):
-        self.weight_decay, self.eta, self.beta, self.eps = weight_decay, eta, (float(beta[0]), float(beta[1])), eps
+    def __init__(self, weight_decay: float = 1.0e-5, eta: float = 1.0e-2, beta=(0.9, 0.999), eps: float = 1.0e-8, inv_decay: float = 0.0):
+        """inv_decay > 0: Optimiser(InvDecay(inv_decay), ADAM(eta)) of experiments/mnist_nsde.jl:87 (use weight_decay = 0 there)."""
+        self.weight_decay, self.eta, self.beta, self.eps, self.inv_decay = weight_decay, eta, (float(beta[0]), float(beta[1])), eps, inv_decay
         self.state: dict = {}
 
     def slot(self, p: torch.Tensor):
         k = p.data_ptr()
         if k not in self.state:
-            self.state[k] = {"m": torch.zeros_like(p), "v": torch.zeros_like(p), "bp": [self.beta[0], self.beta[1]]}
+            self.state[k] = {"m": torch.zeros_like(p), "v": torch.zeros_like(p), "bp": [self.beta[0], self.beta[1]], "n": 1}
         return self.state[k]
 
 
@@ -152,6 +153,9 @@ def update_parameters_(ps, gs, opt) -> None:
             continue
         if isinstance(opt, ADAMOptimiser):
             s = opt.slot(p)
+            if opt.inv_decay > 0:          # InvDecay: delta / (1 + gamma n), n = 1-based update count (Flux 0.11.6)
+                g = g * (1.0 / (1.0 + opt.inv_decay * s["n"]))
+            s["n"] += 1
             rc = lib.rnde_adam_update(None, p.data_ptr(), g.data_ptr(), s["m"].data_ptr(), s["v"].data_ptr(), p.numel(), opt.eta, opt.beta[0],
                                       opt.beta[1], s["bp"][0], s["bp"][1], opt.eps, opt.weight_decay, _stream_ptr())
             if rc != L.OK:

@@ -224,3 +224,17 @@ class ClassifierNSDE:
         z = self._dense(p3, self.postsde.out, self.postsde.inp, u)
         z = z.reshape(z.shape[0], trajectories, bsize).mean(dim=1)
         return z, nfe1, nfe2, sv
+
+    def loss_and_gradient(self, x: torch.Tensor, y_onehot: torch.Tensor, *, lam: float = 1.0e2, trajectories: int = 1, func: Optional[SaveFunc] = None,
+                          noise: Optional[torch.Tensor] = None):
+        """loss_function of experiments/mnist_nsde.jl:89-110 and its Tracker.gradient (:191-204): logitcrossentropy(model(x), y) +
+        lam * mean(sv.saveval).  The pre / post Dense layers and the trajectory mean are torch operations; the SDE solve and its
+        reverse sweep run in the library.  Returns dict(loss, ce, reg, nfe1, nfe2, g1, g2, g3)."""
+        ps = [q.detach().requires_grad_(True) for q in (self.p1, self.p2, self.p3)]
+        kw = {} if noise is None else {"noise": noise}
+        z, nfe1, nfe2, sv = self(x, *ps, trajectories=trajectories, func=func, **kw)
+        ce = -(torch.log_softmax(z, dim=0) * y_onehot).sum(0).mean()          # Flux.Losses.logitcrossentropy: mean over the batch
+        reg = lam * sv.saveval.mean() if sv is not None else torch.zeros((), device=x.device)
+        loss = ce + reg
+        g1, g2, g3 = torch.autograd.grad(loss, ps)
+        return {"loss": loss.detach(), "ce": ce.detach(), "reg": reg.detach(), "nfe1": nfe1, "nfe2": nfe2, "g1": g1, "g2": g2, "g3": g3}

@@ -151,3 +151,44 @@ def test_sde_gradient_matches_the_replayed_adjoint(name, D, H, B, tol, regulariz
     e_p, e_x = rel(p.grad.cpu().numpy(), gp.numpy()), rel(x.grad.cpu().numpy(), gx.numpy())
     print(f"sde grad {name}: e_p {e_p:.2e} e_x {e_x:.2e} naccept {ref.naccept} nreject {ref.nreject}")
     assert e_p <= 1e-4 and e_x <= 1e-4, (e_p, e_x)
+
+
+def test_classifier_nsde_training_gradient():
+    """ClassifierNSDE (supervised_classification.jl:50-103) loss and gradient as experiments/mnist_nsde.jl:89-110,191-204 take them:
+    Dense(784,32) -> SDE solve -> Dense(32,10), logitcrossentropy + lam * mean(EEst * dt); all three parameter groups against a
+    Float64 torch restatement around the replayed SDE steps."""
+    import regneuralde.jl_b200 as r
+    rng = np.random.default_rng(77)
+    D, H, B, C_, I = 32, 64, 24, 10, 784
+    g = torch.Generator().manual_seed(3)
+    nsde = r.TrackedNeuralDSDE(r.Chain(r.Dense(D, H, "tanh", generator=g), r.Dense(H, D, generator=g)), r.Dense(D, D, generator=g), [0.0, 1.0], True, r.SOSRI(),
+                               reltol=0.14, abstol=0.14)
+    clf = r.ClassifierNSDE(r.Dense(I, D, generator=g), nsde, r.Dense(D, C_, generator=g))
+    x = torch.from_numpy(rng.random((I, B)).astype(np.float32)).cuda()
+    y = torch.nn.functional.one_hot(torch.from_numpy(rng.integers(0, C_, B)), C_).T.float().cuda()
+    z = torch.from_numpy(rng.standard_normal((300, D, B)).astype(np.float32)).cuda()
+    lam = 100.0
+    out = clf.loss_and_gradient(x, y, lam=lam, trajectories=1, func=r.ERROR_ESTIMATE, noise=z)
+    # Float64 restatement: pre-net, oracle solve from the SAME Float32 pre-net output (step sequence), replay, post-net, loss
+    p1, p2, p3 = (q.detach().cpu().double().requires_grad_(True) for q in (clf.p1, clf.p2, clf.p3))
+    dense = lambda p, o, i, v: p[: o * i].view(i, o).t() @ v + p[o * i:][:, None]
+    h64 = dense(p1, D, I, x.cpu().double())
+    h32 = clf._dense(clf.p1, D, I, x).detach().cpu().numpy()
+    f, gd = S.drift_diffusion(clf.p2.detach().cpu().numpy(), np.float32, D, H)
+    ref = S.solve(h32, f, gd, z.cpu().numpy(), alg=S.ALG_SOSRI, reg_kind=S.REG_ERR_DT, abstol=0.14, reltol=0.14)
+    assert (nsde.last_stats.naccept, nsde.last_stats.nreject) == (ref.naccept, ref.nreject)
+    u64, sv64 = S.replay_torch(h64, p2, ref.steps, alg=S.ALG_SOSRI, reg_kind=S.REG_ERR_DT, abstol=0.14, reltol=0.14, D=D, H=H)
+    logits = dense(p3, C_, D, u64)
+    ce = -(torch.log_softmax(logits, dim=0) * y.cpu().double()).sum(0).mean()
+    loss = ce + lam * sv64.mean()
+    g1, g2, g3 = torch.autograd.grad(loss, [p1, p2, p3])
+    rel = lambda a, b: float((a.cpu().double() - b).abs().max() / b.abs().max())
+    assert abs(float(out["loss"]) - float(loss)) <= 1e-5 * abs(float(loss))
+    errs = (rel(out["g1"], g1), rel(out["g2"], g2), rel(out["g3"], g3))
+    print("ClassifierNSDE gradient errors (pre, sde, post):", errs)
+    assert max(errs) <= 1e-4, errs
+    # and one optimiser step of Optimiser(InvDecay(1e-5), ADAM(0.01)) (mnist_nsde.jl:87) runs
+    opt = r.ADAMOptimiser(0.0, 0.01, inv_decay=1e-5)
+    before = clf.p2.clone()
+    r.update_parameters_((clf.p1, clf.p2, clf.p3), (out["g1"], out["g2"], out["g3"]), opt)
+    assert float((clf.p2 - before).abs().max()) > 0

@@ -134,3 +134,34 @@ def test_experiment_shape_runs_and_is_deterministic():
     r64 = S.solve(x, f, g, z, reg_kind=S.REG_ERR_DT, dtype=np.float64)
     if r64.accepted == r1.accepted:      # same decisions: the Float32 and Float64 paths agree to rounding
         assert np.abs(r1.u - r64.u).max() < 1e-4 * max(1.0, np.abs(r64.u).max())
+
+
+def test_replay_reproduces_the_solve_and_its_gradient_is_the_finite_difference():
+    """oracle/sde_oracle.py replay_torch (the yardstick of the CUDA reverse sweep, tests/test_gpu_nsde.py): the accepted steps
+    replayed in torch give the solve's state and saved values back, and autograd through them agrees with central finite
+    differences of the replay (step sizes and increments frozen) in a few random parameter directions."""
+    import torch
+    rng = np.random.default_rng(4)
+    D, H, B = 6, 9, 3
+    npar = H * D + H + D * H + D + D * D + D
+    p = 0.4 * rng.standard_normal(npar)
+    x = rng.standard_normal((D, B))
+    z = rng.standard_normal((300, D, B))
+    f, g = S.drift_diffusion(p, np.float64, D, H)
+    r = S.solve(x, f, g, z, alg=S.ALG_SOSRI, reg_kind=S.REG_ERR_DT, abstol=0.05, reltol=0.05, dtype=np.float64)
+    assert r.naccept == len(r.steps) and r.naccept > 5
+    w = rng.standard_normal((D, B)); ws = rng.standard_normal(len(r.saveval))
+
+    def loss_of(pv, xv):
+        u, sv = S.replay_torch(xv, pv, r.steps, alg=S.ALG_SOSRI, reg_kind=S.REG_ERR_DT, abstol=0.05, reltol=0.05, D=D, H=H)
+        return (u * torch.tensor(w)).sum() + (sv * torch.tensor(ws)).sum(), u, sv
+
+    pt = torch.tensor(p, requires_grad=True); xt = torch.tensor(x, requires_grad=True)
+    loss, u, sv = loss_of(pt, xt)
+    assert np.abs(u.detach().numpy() - r.u).max() < 1e-12 and np.abs(sv.detach().numpy() - r.saveval).max() < 1e-12
+    gp, gx = torch.autograd.grad(loss, [pt, xt])
+    for k in range(4):
+        d = rng.standard_normal(npar); h = 1e-6
+        lp = loss_of(torch.tensor(p + h * d), torch.tensor(x))[0]; lm = loss_of(torch.tensor(p - h * d), torch.tensor(x))[0]
+        fd = float(lp - lm) / (2 * h)
+        assert abs(fd - float(gp.numpy() @ d)) <= 1e-6 * max(abs(fd), 1.0)

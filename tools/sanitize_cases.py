@@ -49,8 +49,9 @@ for c in cases:
         D, H, B = 32, 64, 24
         nsde = r.TrackedNeuralDSDE(r.Chain(r.Dense(D, H, "tanh"), r.Dense(H, D, None)), r.Dense(D, D, None), [0.0, 0.2], True, r.SOSRI())
         x = torch.randn(D, B, device="cuda")
-        with torch.no_grad():
-            out = nsde(x, nsde.p, func=r.ERROR_ESTIMATE)
+        p = nsde.p.clone().requires_grad_(True)
+        out = nsde(x, p, func=r.ERROR_ESTIMATE)
+        (out[0].sum() + out[3].saveval.sum()).backward()          # forward with the tape, then the reverse sweep (sde_bwd.cuh)
         torch.cuda.synchronize()
         print(c, out[1], out[2])
     elif c == "ffjord":     # forward + reverse sweep through the hand-differentiated ConcatSquash field, then the sampler
