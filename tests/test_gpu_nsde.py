@@ -1,7 +1,8 @@
 """GPU parity of the Neural-SDE stepper (csrc/sde_kernel.cuh through the C ABI / the TrackedNeuralDSDE mirror) against
 oracle/sde_oracle.py WITH SUPPLIED NOISE (the reference's random stream cannot be reproduced).
 Bars: accepted / rejected attempts, nfe1, nfe2 and the number of consumed draws identical; final state, saved values and the
-saved-value sum within 1e-5 relative (the oracle's matrix products run through BLAS, so not bit for bit)."""
+saved-value sum within 1e-5 relative (the oracle's matrix products run through BLAS, so not bit for bit); gradients (reverse
+sweep csrc/sde_bwd.cuh) within 1e-4 of torch autograd through the oracle's replayed steps."""
 import numpy as np
 import pytest
 
@@ -96,10 +97,11 @@ def test_classifier_nsde_and_errors():
     with pytest.raises(L.RndeError) as ei, torch.no_grad():
         node(torch.zeros(32, B * traj, device="cuda"), torch.from_numpy(p2).cuda(), noise=torch.from_numpy(z[:3]).cuda())
     assert ei.value.code == L.ERR_ARG
-    # no backward yet: loud
+    # the stiffness-estimate regulariser has no reverse sweep: loud, not silently without its gradient
     pp = torch.from_numpy(p2).cuda().requires_grad_(True)
+    auto = node_for(32, 64, True, r.AutoSOSRI2(), 0.14)
     with pytest.raises(NotImplementedError):
-        node(torch.zeros(32, B * traj, device="cuda"), pp, noise=torch.from_numpy(z).cuda())
+        auto(torch.zeros(32, B * traj, device="cuda"), pp, func=r.STIFFNESS_SCALED, noise=torch.from_numpy(z).cuda())
 
 
 # ---- the gradient (round 2): csrc/sde_bwd.cuh against torch autograd through the replayed accepted steps -------------------------
