@@ -1359,7 +1359,7 @@ extern "C" int rnde_sde_enable_tape(rnde_sde* s, int32_t tape_capacity) {
     if (raise_smem_limit(k, smem) != cudaSuccess) { cudaGetLastError(); return sde_err(s, RNDE_ERR_CUDA, "cudaFuncSetAttribute(sde_bwd)"); }
     const size_t T = (size_t)D * s->NP;
     if (cudaMalloc(&s->tape, sizeof(float) * (size_t)tape_capacity * s->Q * 3 * T) != cudaSuccess ||
-        cudaMalloc(&s->tape_steps, sizeof(float) * 2 * (size_t)tape_capacity) != cudaSuccess ||
+        cudaMalloc(&s->tape_steps, sizeof(float) * 4 * (size_t)tape_capacity) != cudaSuccess ||
         cudaMalloc(&s->gpart, sizeof(float) * (size_t)s->Q * np) != cudaSuccess) { cudaGetLastError(); return sde_err(s, RNDE_ERR_CUDA, "cudaMalloc (tape)"); }
     s->tape_cap = tape_capacity; s->smem_bwd = smem;
     return RNDE_OK;
@@ -1368,7 +1368,6 @@ extern "C" int rnde_sde_enable_tape(rnde_sde* s, int32_t tape_capacity) {
 extern "C" int rnde_sde_backward(rnde_sde* s, const float* du_dev, const float* dsaveval_dev, float* dp_dev, float* dx_dev, void* stream) {
     if (!s || !dp_dev || (!du_dev && !dsaveval_dev)) return RNDE_ERR_ARG;
     if (!s->have_tape) return sde_err(s, RNDE_ERR_STATE, "rnde_sde_backward needs rnde_sde_enable_tape and a forward solve on this handle first");
-    if (s->cfg.reg_kind == RNDE_REG_STIFF_SCALED && dsaveval_dev) return sde_err(s, RNDE_ERR_UNSUPPORTED, "the stiffness-estimate regulariser has no reverse sweep yet");
     DeviceScope scope(s->device);
     if (scope.err != cudaSuccess) return sde_err(s, RNDE_ERR_CUDA, "selecting the handle's device");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1376,7 +1375,7 @@ extern "C" int rnde_sde_backward(rnde_sde* s, const float* du_dev, const float* 
     SdeBwdParams P; memset(&P, 0, sizeof(P));
     P.D = c.state_dim; P.H = c.hidden_dim; P.B = c.batch; P.Q = s->Q; P.alg = c.alg; P.reg_kind = c.reg_kind; P.tape_cap = s->tape_cap;
     P.abstol = c.abstol; P.reltol = c.reltol; P.p = s->last_p; P.tape = s->tape; P.tape_steps = s->tape_steps; P.stats = s->stats;
-    P.du = du_dev; P.dsaveval = (c.reg_kind == RNDE_REG_ERR_DT) ? dsaveval_dev : nullptr; P.dx = dx_dev; P.gpart = s->gpart;
+    P.du = du_dev; P.dsaveval = (c.reg_kind != RNDE_REG_NONE) ? dsaveval_dev : nullptr; P.dx = dx_dev; P.gpart = s->gpart;
     if (s->NP == 4) sde_bwd_kernel<4><<<s->Q, SDE_NT, s->smem_bwd, st>>>(P);
     else if (s->NP == 8) sde_bwd_kernel<8><<<s->Q, SDE_NT, s->smem_bwd, st>>>(P);
     else sde_bwd_kernel<16><<<s->Q, SDE_NT, s->smem_bwd, st>>>(P);

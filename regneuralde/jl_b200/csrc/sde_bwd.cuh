@@ -18,7 +18,7 @@ namespace rnde {
 struct SdeBwdParams {
     int D, H, B, Q, alg, reg_kind, tape_cap;
     float abstol, reltol;
-    const float* p; const float* tape; const float* tape_steps;      // tape: [step][Q][3][D * NP] (u at step start, dW, dZ); steps: [step][2] (dt, EEst)
+    const float* p; const float* tape; const float* tape_steps;      // tape: [step][Q][3][D * NP] (u at step start, dW, dZ); steps: [step][4] (dt, EEst, rms(k4 - k3), rms(H03 - H02))
     const SdeStats* stats;                                           // naccept of the forward solve, read on the device
     const float* du; const float* dsaveval;                          // cotangents of the final state (D x B) and of the saved values
     float* dx; float* gpart;                                         // dx: D x B; gpart: [Q][np] per-tile parameter gradients
@@ -153,7 +153,8 @@ __global__ void __launch_bounds__(SDE_NT) sde_bwd_kernel(const SdeBwdParams P) {
     for (int s = nsteps - 1; s >= 0; --s) {
         const float* tp = P.tape + (((size_t)s * P.Q + q) * 3) * T;
         for (int e = tid; e < T; e += NT) { sU[e] = __ldcg(tp + e); sdW[e] = __ldcg(tp + T + e); sdZ[e] = __ldcg(tp + 2 * T + e); }
-        const float dtc = __ldg(P.tape_steps + 2 * s), EEst = __ldg(P.tape_steps + 2 * s + 1);
+        const float dtc = __ldg(P.tape_steps + 4 * s), EEst = __ldg(P.tape_steps + 4 * s + 1);
+        const float n1 = __ldg(P.tape_steps + 4 * s + 2), n2 = __ldg(P.tape_steps + 4 * s + 3);
         const float sqdt = (float)sqrt((double)dtc), sqrt3 = (float)sqrt(3.0);
         __syncthreads();
         auto chi1 = [&](int e) { const float w = sdW[e]; return (w * w - dtc) / (2.f * sqdt); };
@@ -184,6 +185,14 @@ __global__ void __launch_bounds__(SDE_NT) sde_bwd_kernel(const SdeBwdParams P) {
         eval_fg(sH0[2], sK[3], sHid[3], sH1[2], sG[3]);
         // ---- cotangents of the update formula and of the error estimate ----
         const float sbar = (P.dsaveval && P.reg_kind == RNDE_REG_ERR_DT) ? __ldg(P.dsaveval + s + 1) : 0.f;
+        // stiffness-estimate regulariser of AutoSOSRI2 (mnist_nsde.jl:52-56): saved = |eig| / 10.6, eig = rms(k4 - k3) / rms(H03 - H02)
+        // -> cotangents on k4, k3 and directly on the stage inputs H03, H02 (added where those inputs' cotangents are distributed)
+        float cK = 0.f, cH = 0.f;
+        if (P.dsaveval && P.reg_kind == RNDE_REG_STIFF_SCALED && P.alg == 1 && n1 > 0.f && n2 > 0.f) {
+            const float eigbar = __ldg(P.dsaveval + s + 1) * (1.f / 10.6f);       // eig = n1 / n2 >= 0
+            cK = (eigbar / n2) / (cnt * n1);                                      // multiplies (k4 - k3)
+            cH = (-eigbar * n1 / (n2 * n2)) / (cnt * n2);                         // multiplies (H03 - H02)
+        }
         const float gE = (sbar != 0.f && EEst > 0.f) ? sbar * dtc / (cnt * EEst) : 0.f;      // d(EEst dt)/d(resid_e) = dt resid_e / (cnt EEst)
         for (int e = tid; e < T; e += NT) {
             const int n = e % NP;
@@ -207,7 +216,8 @@ __global__ void __launch_bounds__(SDE_NT) sde_bwd_kernel(const SdeBwdParams P) {
             sUb[e] = unb + (1.f - wn) * denb * rtol * sgu;                 // direct path u' = u + ... and the |u| branch
             const float kcommon = dtc * delta * Eb;
             sKb[0][e] = dtc * tb.al1 * unb + kcommon; sKb[1][e] = dtc * tb.al2 * unb + kcommon;
-            sKb[2][e] = dtc * tb.al3 * unb + kcommon; sKb[3][e] = dtc * tb.al4 * unb + kcommon;
+            const float dk = (n < Nloc) ? cK * (k4 - k3) : 0.f;
+            sKb[2][e] = dtc * tb.al3 * unb + kcommon - dk; sKb[3][e] = dtc * tb.al4 * unb + kcommon + dk;
             const float ue = unb + Eb;                                     // E2 sits in u' and in the residual
             sGb[0][e] = (w * tb.be11 + c1 * tb.be21) * unb + (c2 * tb.be31 + c3 * tb.be41) * ue;
             sGb[1][e] = (w * tb.be12 + c1 * tb.be22) * unb + (c2 * tb.be32 + c3 * tb.be42) * ue;
@@ -218,7 +228,8 @@ __global__ void __launch_bounds__(SDE_NT) sde_bwd_kernel(const SdeBwdParams P) {
         // ---- the stages in reverse ----
         vjp_fg(sH0[2], sHid[3], sKb[3], sH1[2], sGb[3]);      // k4 = f(H03), g4 = g(H13)
         for (int e = tid; e < T; e += NT) {
-            const float a = sA[e], b = sBv[e], c2 = chi2(e);
+            const float dh = ((e % NP) < Nloc) ? cH * (sH0[2][e] - sH0[1][e]) : 0.f;
+            const float a = sA[e] + dh, b = sBv[e], c2 = chi2(e);
             sUb[e] += a + b;
             sKb[0][e] += dtc * (tb.a041 * a + tb.a141 * b); sKb[1][e] += dtc * (tb.a042 * a + tb.a142 * b); sKb[2][e] += dtc * (tb.a043 * a + tb.a143 * b);
             sGb[0][e] += c2 * tb.b041 * a + sqdt * tb.b141 * b; sGb[1][e] += c2 * tb.b042 * a + sqdt * tb.b142 * b; sGb[2][e] += c2 * tb.b043 * a + sqdt * tb.b143 * b;
@@ -226,7 +237,8 @@ __global__ void __launch_bounds__(SDE_NT) sde_bwd_kernel(const SdeBwdParams P) {
         __syncthreads();
         vjp_fg(sH0[1], sHid[2], sKb[2], sH1[1], sGb[2]);      // k3 = f(H02), g3 = g(H12)
         for (int e = tid; e < T; e += NT) {
-            const float a = sA[e], b = sBv[e], c2 = chi2(e);
+            const float dh = ((e % NP) < Nloc) ? cH * (sH0[2][e] - sH0[1][e]) : 0.f;
+            const float a = sA[e] - dh, b = sBv[e], c2 = chi2(e);
             sUb[e] += a + b;
             sKb[0][e] += dtc * (tb.a031 * a + tb.a131 * b); sKb[1][e] += dtc * (tb.a032 * a + tb.a132 * b);
             sGb[0][e] += c2 * tb.b031 * a + sqdt * tb.b131 * b; sGb[1][e] += c2 * tb.b032 * a + sqdt * tb.b132 * b;

@@ -37,7 +37,7 @@ struct SdeParams {
     unsigned* bar;
     SdeStats* stats;
     float* log; int log_cap;      // per attempt: dt, EEst, accepted
-    // tape of the accepted steps for the reverse sweep (sde_bwd.cuh): [step][Q][3][D * NP] = state at the step's start, dW, dZ; [step][2] = dt, EEst
+    // tape of the accepted steps for the reverse sweep (sde_bwd.cuh): [step][Q][3][D * NP] = state at the step's start, dW, dZ; [step][4] = dt, EEst, rms(k4 - k3), rms(H03 - H02)
     float* tape; float* tape_steps; int tape_cap;
 };
 
@@ -420,7 +420,10 @@ __global__ void __launch_bounds__(SDE_NT) sde_kernel(const SdeParams P) {
                 if (naccept <= P.tape_cap) {
                     float* tp = P.tape + (((size_t)(naccept - 1) * P.Q + q) * 3) * T;
                     for (int e = tid; e < T; e += NT) { tp[e] = sU[e]; tp[T + e] = sdW[e]; tp[2 * T + e] = sdZ[e]; }
-                    if (q == 0 && tid == 0) { P.tape_steps[2 * (naccept - 1)] = dtc; P.tape_steps[2 * (naccept - 1) + 1] = (float)EEst; }
+                    if (q == 0 && tid == 0) {
+                        float* ts = P.tape_steps + 4 * (naccept - 1);
+                        ts[0] = dtc; ts[1] = (float)EEst; ts[2] = (P.alg == 1) ? (float)nv[1] : 0.f; ts[3] = (P.alg == 1) ? (float)nv[2] : 0.f;
+                    }
                 } else retcode = RNDE_ERR_TAPE_FULL;
                 __syncthreads();
             }

@@ -13,8 +13,8 @@ the functor takes the standard normals as the ``noise`` keyword ((n_draws, D, B)
 consumes them in the order documented in include/regnde.h.  The pre / post Dense layers and the mean over trajectories are the
 host glue the reference keeps in Flux.  With gradients enabled the solve tapes its accepted steps and torch autograd reaches it
 through _SdeSolve: the reverse sweep (csrc/sde_bwd.cuh) is the discrete adjoint of those steps with step sizes and Wiener
-increments frozen -- Tracker.gradient through solve(...; sensealg = SensitivityADPassThrough()) (mnist_nsde.jl:201-204).  The
-error-estimate regulariser is differentiated; the stiffness-estimate one (AutoSOSRI2) is forward only."""
+increments frozen -- Tracker.gradient through solve(...; sensealg = SensitivityADPassThrough()) (mnist_nsde.jl:201-204), with both
+regularisers of the experiment (EEst * dt, and the scaled stiffness estimate of AutoSOSRI2) differentiated."""
 from __future__ import annotations
 
 import ctypes as C
@@ -157,8 +157,6 @@ class TrackedNeuralDSDE:
             noise = torch.randn(256, self.D, B, device=x.device, dtype=torch.float32)
         if tuple(noise.shape[1:]) != (self.D, B) or noise.dtype != torch.float32 or not noise.is_cuda:
             raise ValueError(f"noise must be a CUDA Float32 tensor of shape (n_draws, {self.D}, {B})")
-        if need_bwd and reg_kind == L.REG_STIFF_SCALED:
-            raise NotImplementedError("the stiffness-estimate regulariser of the SDE path has no reverse sweep; the error-estimate one has")
         hd = self._handle(B, reg_kind, need_bwd)
         xbuf = colmajor(x.to(torch.float32))
         if need_bwd:

@@ -97,18 +97,15 @@ def test_classifier_nsde_and_errors():
     with pytest.raises(L.RndeError) as ei, torch.no_grad():
         node(torch.zeros(32, B * traj, device="cuda"), torch.from_numpy(p2).cuda(), noise=torch.from_numpy(z[:3]).cuda())
     assert ei.value.code == L.ERR_ARG
-    # the stiffness-estimate regulariser has no reverse sweep: loud, not silently without its gradient
-    pp = torch.from_numpy(p2).cuda().requires_grad_(True)
-    auto = node_for(32, 64, True, r.AutoSOSRI2(), 0.14)
-    with pytest.raises(NotImplementedError):
-        auto(torch.zeros(32, B * traj, device="cuda"), pp, func=r.STIFFNESS_SCALED, noise=torch.from_numpy(z).cuda())
 
 
 # ---- the gradient (round 2): csrc/sde_bwd.cuh against torch autograd through the replayed accepted steps -------------------------
 
 GRAD_CASES = [
-    # name, D, H, B, tol, regularize, weight scale
+    # name, D, H, B, tol, regularize (True: EEst * dt; "stiff": AutoSOSRI2 with the scaled stiffness estimate), weight scale
     ("mnist_nsde shape B=48 error_est", 32, 64, 48, 0.14, True, 1.0),
+    ("AutoSOSRI2 stiff_est", 32, 64, 40, 0.14, "stiff", 1.0),
+    ("AutoSOSRI2 stiff_est, inflated weights (rejections)", 32, 64, 40, 0.06, "stiff", 3.0),
     ("unregularised, ragged tile", 32, 64, 33, 0.14, False, 1.0),
     ("tight tolerance, inflated weights (rejections on the way)", 32, 64, 7, 0.02, True, 3.0),
     ("generic dims D=12 H=20", 12, 20, 9, 0.05, True, 3.0),
@@ -124,13 +121,17 @@ def test_sde_gradient_matches_the_replayed_adjoint(name, D, H, B, tol, regulariz
     (asserted), so both differentiate the same discrete map.  Bar: 1e-4 relative (Float32 sweep against a Float64 replay)."""
     import regneuralde.jl_b200 as r
     p_np, x_np, z_np = make(1999, D, H, B, ndraw=120 if B > 1000 else 400, scale=scale)
-    node = node_for(D, H, regularize, r.SOSRI(), tol)
+    stiff = regularize == "stiff"
+    regularize = bool(regularize)
+    alg = S.ALG_AUTO_SOSRI2 if stiff else S.ALG_SOSRI
+    regk = (S.REG_STIFF_SCALED if stiff else S.REG_ERR_DT) if regularize else S.REG_NONE
+    node = node_for(D, H, regularize, r.AutoSOSRI2() if stiff else r.SOSRI(), tol)
     p = torch.from_numpy(p_np).cuda().requires_grad_(True)
     x = torch.from_numpy(x_np).cuda().requires_grad_(True)
-    func = r.ERROR_ESTIMATE if regularize else None
+    func = (r.STIFFNESS_SCALED if stiff else r.ERROR_ESTIMATE) if regularize else None
     res, nfe1, nfe2, sv = node(x, p, func=func, noise=torch.from_numpy(z_np).cuda())
     f, g = S.drift_diffusion(p_np, np.float32, D, H)
-    ref = S.solve(x_np, f, g, z_np, alg=S.ALG_SOSRI, reg_kind=S.REG_ERR_DT if regularize else S.REG_NONE, abstol=tol, reltol=tol)
+    ref = S.solve(x_np, f, g, z_np, alg=alg, reg_kind=regk, abstol=tol, reltol=tol)
     st = node.last_stats
     assert (st.naccept, st.nreject, nfe1, nfe2) == (ref.naccept, ref.nreject, ref.nfe1, ref.nfe2)
     rng = np.random.default_rng(5)
@@ -144,7 +145,7 @@ def test_sde_gradient_matches_the_replayed_adjoint(name, D, H, B, tol, regulariz
     torch.cuda.synchronize()
     pt = torch.tensor(p_np.astype(np.float64), requires_grad=True)
     xt = torch.tensor(x_np.astype(np.float64), requires_grad=True)
-    u64, sv64 = S.replay_torch(xt, pt, ref.steps, alg=S.ALG_SOSRI, reg_kind=S.REG_ERR_DT if regularize else S.REG_NONE, abstol=tol, reltol=tol, D=D, H=H)
+    u64, sv64 = S.replay_torch(xt, pt, ref.steps, alg=alg, reg_kind=regk, abstol=tol, reltol=tol, D=D, H=H)
     l64 = (u64 * torch.tensor(w.astype(np.float64))).sum()
     if regularize:
         l64 = l64 + (sv64 * torch.tensor(ws.astype(np.float64))).sum()
