@@ -486,9 +486,12 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
     float dt = 0.f, gB = 0.f;
     bool use_eig = false;
     int recU1 = 0, recG6 = 0;
-    for (int task = 0; task < ntask; ++task) {
-        const bool last = (task == ntask - 1);
-        const bool a6task = na6 && (task == ntask - 2);
+    // With the first-dt additions compiled in, the loop runs the steps only and the tail tasks (the a6 task, record 0) follow it with
+    // a second inlined copy of the VJP: branches on them inside the loop cost every record (profiles/r2p_a6_sweep_variants.txt).
+    const int nloop = A6C ? 6 * P.nsteps : ntask;
+    for (int task = 0; task < nloop; ++task) {
+        const bool last = !A6C && (task == ntask - 1);
+        const bool a6task = false;
         const bool tail = last || a6task;
         const int s = tail ? 0 : P.nsteps - 1 - task / 6;
         const int i = tail ? 7 : 7 - task % 6;
@@ -592,8 +595,7 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
         TLB(9);
         // kbar of this evaluation
         float cur[16], zb[16];
-        if (a6task) RNDE_A6_TASK_PRE(sA6, cur, sPart, a6_sweep_partial(P, own, cvalid, offD(0, 0), (size_t)P.Q * tileD, NP, q, rank, G));
-        else switch (i) {
+        switch (i) {
 #define RNDE_CUR(J) case J: _Pragma("unroll") for (int e = 0; e < 16; ++e) cur[e] = kb[J - 1][e]; break;
             RNDE_CUR(2) RNDE_CUR(3) RNDE_CUR(4) RNDE_CUR(5) RNDE_CUR(6)
             default: _Pragma("unroll") for (int e = 0; e < 16; ++e) cur[e] = kb[6][e]; break;
@@ -619,11 +621,6 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
             }
         }
         vjp(cur, zb, rec, rec_next);
-        if (a6task) {      // its time cotangent: the two sums the tensor cores left for this CTA
-            const float* tp = P.a6_tau + (((size_t)rec * P.Q + q) * G + rank) * 32;
-            RNDE_A6_TASK_POST(sA6, zb, sPart, (tid < 16 && td) ? (double)(__ldcg(tp + tid) + (rank == 0 ? __ldcg(tp + 16 + tid) : 0.f)) : 0.0);
-            continue;
-        }
         if (last) {
             // initial fsalfirst = f(u0, t0): dx = ubar + zbar
             if (P.dx && own) {
@@ -675,6 +672,34 @@ __global__ void __launch_bounds__(V2_NT, 1) bwd4tc_kernel(const KParams P) {
             // hand over to the previous step: u_new(prev) = uprev, k7(prev) = k1
 #pragma unroll
             for (int e = 0; e < 16; ++e) { ubar[e] = upb[e]; kb[6][e] = kb[0][e]; }
+        }
+    }
+    if constexpr (A6C) {
+        for (int tt = 0; tt < 1 + na6; ++tt) {
+            const bool a6task = na6 && tt == 0;
+            const int rec = a6task ? P.rec_x : 0;
+            float cur[16], zb[16];
+            if (a6task) RNDE_A6_TASK_PRE(sA6, cur, sPart, a6_sweep_partial(P, own, cvalid, offD(0, 0), (size_t)P.Q * tileD, NP, q, rank, G));
+            else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) cur[e] = kb[6][e];
+            }
+            vjp(cur, zb, rec, a6task ? 0 : -1);
+            if (a6task) {      // its time cotangent: the two sums the tensor cores left for this CTA
+                const float* tp = P.a6_tau + (((size_t)rec * P.Q + q) * G + rank) * 32;
+                RNDE_A6_TASK_POST(sA6, zb, sPart, (tid < 16 && td) ? (double)(__ldcg(tp + tid) + (rank == 0 ? __ldcg(tp + 16 + tid) : 0.f)) : 0.0);
+                continue;
+            }
+            // initial fsalfirst = f(u0, t0): dx = ubar + zbar
+            if (P.dx && own) {
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int n = cn0 + jj;
+                        if (ii < cvalid && n < Nloc) P.dx[(size_t)D * (c0 + n) + r0 + crow0 + ii] = ubar[ii * 4 + jj] + zb[ii * 4 + jj];
+                    }
+            }
         }
     }
 #ifdef RNDE_TIMELINE
