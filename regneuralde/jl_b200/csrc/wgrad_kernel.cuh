@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_gemm_kernel(const float* __restr
         cp_async_commit();
     };
 
+    const bool all_double = (long long)M * Nrows <= 16384;      // uniform: small fields afford Float64 products
     double accd[8][4];
     float acc[8][4];
 #pragma unroll
@@ -142,10 +143,15 @@ __global__ void __launch_bounds__(256, 1) wgrad_gemm_kernel(const float* __restr
             for (int i = 0; i < 8; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    acc[i][j] = rn_fmaf(a4[i].x, b4[j].x, acc[i][j]);
-                    acc[i][j] = rn_fmaf(a4[i].y, b4[j].y, acc[i][j]);
-                    acc[i][j] = rn_fmaf(a4[i].z, b4[j].z, acc[i][j]);
-                    acc[i][j] = rn_fmaf(a4[i].w, b4[j].w, acc[i][j]);
+                    if (all_double) {      // small fields: every product in Float64 (the toy shapes' stiffness-estimate gradient needs it to stay within
+                        // 1.5x of a CPU Float32 adjoint: 1.2x, against 2.5x with Float32 products and 7x with a Float32 partial per stage)
+                        accd[i][j] = fma((double)a4[i].x, (double)b4[j].x, accd[i][j]); accd[i][j] = fma((double)a4[i].y, (double)b4[j].y, accd[i][j]);
+                        accd[i][j] = fma((double)a4[i].z, (double)b4[j].z, accd[i][j]); accd[i][j] = fma((double)a4[i].w, (double)b4[j].w, accd[i][j]);
+                    } else {
+                        // four entries of ONE record (no cancellation among them) in Float32, then Float64: a Float32 partial over a whole
+                        // stage mixes the records of a step, whose +-O(10) cotangents cancel (found at the end of round 2, tools/stiff_probe.py)
+                        accd[i][j] += (double)rn_fmaf(a4[i].w, b4[j].w, rn_fmaf(a4[i].z, b4[j].z, rn_fmaf(a4[i].y, b4[j].y, a4[i].x * b4[j].x)));
+                    }
                 }
         }
         if ((s % WG_FLUSH) == WG_FLUSH - 1 || s == nstage - 1) {

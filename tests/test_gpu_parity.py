@@ -142,11 +142,9 @@ def test_gradient_matches_oracle(oracle_built, name, D, H, B, act_out, auto, fun
     if tol is not None:
         assert e_p <= tol and e_x <= tol, (e_p, e_x)
     assert e_x <= max(1e-4, GRAD_BAR * c_x), (e_x, c_x)
-    # OPEN ISSUE: on the toy shape the PARAMETER gradient of the stiffness-estimate regulariser from the
-    # generic sweep is measured 7x further from the yardstick than the CPU Float32 adjoint (every block W1, b1, W2, b2 alike,
-    # profiles/r2i_grad_blocks.txt), cause not found; the same regulariser at the flagship shape is 0.3x (test_flagship_gradient_both_sweeps)
-    bar_p = 8.0 if name == "test_node stiffreg grad" else GRAD_BAR
-    assert e_p <= max(1e-4, bar_p * c_p), (e_p, c_p)
+    # (until the end of round 2 the stiffness-estimate case needed an 8x bar here: the FFMA weight-gradient contraction kept a
+    # Float32 partial per 64-entry stage, which mixes the cancelling records of a step; fixed in wgrad_kernel.cuh)
+    assert e_p <= max(1e-4, GRAD_BAR * c_p), (e_p, c_p)
 
 
 def test_mnist_training_step_against_oracle(oracle_built):
