@@ -7,6 +7,8 @@
 // Canonical arithmetic (oracle/rnde_oracle.c chain_column): one fma chain over the inputs in ascending order starting
 // from 0, then + bias, then the activation.
 #pragma once
+#include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace rnde {
@@ -184,11 +186,24 @@ __device__ __forceinline__ const float* chain_vjp(const KParams& P, const ChainV
 
 // Parameter gradients of Dense layers from a tape: for every layer dW = sum over (record, column) of delta a^T and
 // db = sum delta.  Tapes are [record][tile][row][NP]; a layer is described by where its delta and its input rows live.
-// grid = (splits, layers, output chunks); a CTA walks a contiguous range of (record, tile) pairs, stages 64 columns at
-// a time and every thread owns up to CW_OUT (output, input) pairs of its chunk; partial sums are FP32 over one stage
-// and FP64 across stages (the regulariser cotangents cancel between records: DESIGN.md section 5).
-constexpr int CW_NT = 256, CW_COLS = 64, CW_LD = 68;   // CW_LD: padded row stride (conflict-free LDS.128)
-constexpr int CW_TPT = 2;                              // 4 x 4 output tiles per thread: 512 tiles >= 10 x 44 (the 40 x 176 GRU layers)
+// grid = (splits, layers); a CTA walks a contiguous range of (record, tile) pairs 64 columns (a "stage") at a time and every
+// thread owns one 4 x 4 tile of (output, input) pairs.  Every product is a Float64 fma (the regulariser cotangents cancel
+// between records: DESIGN.md section 5; a 64-column Float32 partial made the parameter gradient of the regularised toy /
+// chain cases 2-2.5x noisier than the CPU Float32 adjoint).  What round 2 measured on the FFJORD step and changed
+// (profiles/r2zz_next_rows_ncu.txt):
+//   * converting float -> double in the inner loop put 32 F2F per 64 DFMA on the XU pipe (16 lanes/clk/SM against 64 for DFMA): the
+//     XU pipe sat at 100 %.  The operands are now converted ONCE per stage; shared memory holds doubles.
+//   * the float rows 272 B apart made the delta reads 4-way bank conflicted.  A tile's four outputs are now MT rows apart, the
+//     lanes of a warp read consecutive rows, CW_LD = 66 doubles = 16 B mod 128 B apart: conflict-free LDS.128.
+//   * the loads of a stage were exposed (26 % of the warp samples waited on them, 29 % at the barrier behind them): the next stage's
+//     rows now travel as cp.async into a raw Float32 buffer while this stage's products run, and are converted after them.
+//   * 512 threads with one tile each instead of 256 with up to two (the second pass occupied 3 of 8 warps).
+#ifndef RNDE_CW_NT
+#define RNDE_CW_NT 512
+#endif
+constexpr int CW_NT = RNDE_CW_NT, CW_COLS = 64, CW_LD = 66;   // CW_LD: row stride in doubles
+constexpr int CW_MAXTILES = 512;                               // 4 x 4 output tiles per pseudo-layer (>= 10 x 44: the 40 x 176 GRU layers)
+constexpr int CW_TPT = CW_MAXTILES / CW_NT;
 struct WgLayer {
     const float* dptr; const float* aptr;     // delta tape, input-activation tape
     int dstride, astride;                     // floats per (record, tile) block of each tape
@@ -196,73 +211,108 @@ struct WgLayer {
     int M, K, poff;                           // out, in, offset of W in the parameter vector (bias follows W)
     int nobias;                               // 1: no bias row (a second outer product into the same W: the FFJORD transposed chain)
 };
-struct WgDesc { WgLayer l[12]; int nl; };
+struct WgDesc { WgLayer l[16]; int nl; int cta0[17]; };      // cta0: first CTA of every layer (filled by launch_dense_wgrad)
 
-// rows x 64 columns of a tape into shared memory as float4 (tile-major items: consecutive threads read consecutive rows of one
-// (record, tile) block = contiguous memory); `ones` appends a row of 1 (the bias input)
-__device__ __forceinline__ void wg_stage(float* dst, const float* __restrict__ src, const int stride, const int row0, const int rows, const bool ones,
-                                         const int NPt, const long long t0, const long long ntile) {
-    const int v4 = NPt / 4, tiles = CW_COLS / NPt;
-    const int per_tile = rows * v4;
-    for (int item = threadIdx.x; item < tiles * per_tile; item += CW_NT) {
-        const int tl = item / per_tile, rem = item - tl * per_tile;
-        const int row = rem / v4, v = rem - row * v4;
-        const long long tile = t0 + tl;
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (tile < ntile) x = __ldcg(reinterpret_cast<const float4*>(src + (size_t)tile * stride + (size_t)(row0 + row) * NPt + v * 4));
-        *reinterpret_cast<float4*>(dst + row * CW_LD + tl * NPt + v * 4) = x;
-    }
-    if (ones) {
-        for (int c = threadIdx.x; c < CW_COLS; c += CW_NT) dst[rows * CW_LD + c] = (t0 + c / NPt < ntile) ? 1.f : 0.f;
+__device__ __forceinline__ void cw_cp16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+// Item enumeration of a stage, shared by the asynchronous copy and the conversion: NPt is a power of two (4..64), so a
+// (record, tile) block of a layer is per = rows * NPt / 4 consecutive float4; items are dealt as (tile of the stage, float4 of
+// the block) with the block length padded to a power of two (shifts, no divisions).  visit(isA, tl, e, idx): idx = compact index.
+struct WgGeom { int lv4, ltiles, perD, perA, lpD, lpA, nD2, n2; };
+__device__ __forceinline__ WgGeom wg_geom(const WgLayer& Ld, const int NPt) {
+    WgGeom g;
+    g.lv4 = __ffs(NPt) - 3; g.ltiles = 6 - (g.lv4 + 2);
+    g.perD = Ld.M << g.lv4; g.perA = Ld.K << g.lv4;
+    g.lpD = 32 - __clz(max(g.perD, 1) - 1); g.lpA = 32 - __clz(max(g.perA, 1) - 1);
+    g.nD2 = 1 << (g.lpD + g.ltiles); g.n2 = g.nD2 + (1 << (g.lpA + g.ltiles));
+    return g;
+}
+template <class V>
+__device__ __forceinline__ void wg_items(const WgGeom& g, V visit) {
+    for (int e2 = threadIdx.x; e2 < g.n2; e2 += CW_NT) {
+        const bool isA = e2 >= g.nD2;
+        const int u = isA ? e2 - g.nD2 : e2, lp = isA ? g.lpA : g.lpD, per = isA ? g.perA : g.perD;
+        const int tl = u >> lp, e = u & ((1 << lp) - 1);
+        if (e < per) visit(isA, tl, e, (isA ? (g.perD << g.ltiles) : 0) + tl * per + e);
     }
 }
 
 __global__ void __launch_bounds__(CW_NT) dense_wgrad_kernel(const WgDesc desc, const int NPt, const long long ntile, double* __restrict__ acc_out) {
-    extern __shared__ __align__(16) float csm[];
+    extern __shared__ __align__(16) double csm[];
     const int tid = threadIdx.x;
-    const WgLayer& Ld = desc.l[blockIdx.y];
+    int layer = 0;
+    while (layer + 1 < desc.nl && (int)blockIdx.x >= desc.cta0[layer + 1]) ++layer;
+    const WgLayer& Ld = desc.l[layer];
+    const int split = (int)blockIdx.x - desc.cta0[layer], nsplit = desc.cta0[layer + 1] - desc.cta0[layer];
     const int M = Ld.M, K = Ld.K;
-    const int MT = (M + 3) / 4, IT = (K + 1 + 3) / 4;        // 4 x 4 output tiles: 4 outputs x 4 inputs (input K = bias)
+    const int MT = (M + 3) / 4, IT = (K + 1 + 3) / 4;        // 4 x 4 output tiles: outputs {mt, mt+MT, mt+2MT, mt+3MT} x inputs 4it..4it+3 (input K = bias)
     const int ntiles_out = MT * IT;
-    float* sDel = csm;                                       // round_up(M,4) x CW_LD
-    float* sAct = csm + MT * 4 * CW_LD;                      // round_up(K+1,4) x CW_LD, row K = 1 (bias)
-    for (int e = tid; e < (MT * 4 + IT * 4) * CW_LD; e += CW_NT) csm[e] = 0.f;      // padding rows stay zero
+    double* sDel = csm;                                      // 4*MT x CW_LD
+    double* sAct = csm + MT * 4 * CW_LD;                     // 4*IT x CW_LD, row K = 1 (bias)
+    float* sRaw = reinterpret_cast<float*>(csm + (MT * 4 + IT * 4) * CW_LD);      // (M + K) rows x 64 columns as they lie on the tapes
+    for (int e = tid; e < (MT * 4 + IT * 4) * CW_LD; e += CW_NT) csm[e] = 0.0;      // padding rows stay zero
+    const WgGeom g = wg_geom(Ld, NPt);
     const int tiles_per_stage = CW_COLS / NPt;
     const long long nstage = (ntile + tiles_per_stage - 1) / tiles_per_stage;
-    const long long s0 = nstage * blockIdx.x / gridDim.x, s1 = nstage * (blockIdx.x + 1) / gridDim.x;
+    const long long s0 = nstage * split / nsplit, s1 = nstage * (split + 1) / nsplit;
+    auto issue = [&](const long long s) {
+        const long long t0 = s * tiles_per_stage;
+        wg_items(g, [&](const bool isA, const int tl, const int e, const int idx) {
+            const long long tile = t0 + tl;
+            float* dst = sRaw + (size_t)idx * 4;
+            if (tile < ntile) {
+                const float* src = isA ? Ld.aptr + (size_t)tile * Ld.astride + (size_t)Ld.aoff * NPt : Ld.dptr + (size_t)tile * Ld.dstride + (size_t)Ld.doff * NPt;
+                cw_cp16(dst, src + (size_t)e * 4);
+            } else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+        });
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto convert = [&](const long long s) {
+        const long long t0 = s * tiles_per_stage;
+        wg_items(g, [&](const bool isA, const int tl, const int e, const int idx) {
+            const float4 x = *reinterpret_cast<const float4*>(sRaw + (size_t)idx * 4);
+            const int row = e >> g.lv4;
+            double2* d2 = reinterpret_cast<double2*>((isA ? sAct : sDel) + row * CW_LD + tl * NPt + ((e - (row << g.lv4)) << 2));
+            d2[0] = make_double2((double)x.x, (double)x.y);
+            d2[1] = make_double2((double)x.z, (double)x.w);
+        });
+        if (!Ld.nobias)
+            for (int c = tid; c < CW_COLS; c += CW_NT) sAct[K * CW_LD + c] = (t0 + c / NPt < ntile) ? 1.0 : 0.0;
+    };
     double acc[CW_TPT][16];
 #pragma unroll
     for (int t = 0; t < CW_TPT; ++t)
 #pragma unroll
         for (int r = 0; r < 16; ++r) acc[t][r] = 0.0;
+    if (s0 < s1) issue(s0);
     for (long long s = s0; s < s1; ++s) {
-        const long long t0 = s * tiles_per_stage;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                 // stage s has landed in sRaw; every thread is done with the doubles of stage s - 1
+        convert(s);
         __syncthreads();
-        wg_stage(sDel, Ld.dptr, Ld.dstride, Ld.doff, M, false, NPt, t0, ntile);
-        wg_stage(sAct, Ld.aptr, Ld.astride, Ld.aoff, K, !Ld.nobias, NPt, t0, ntile);
-        __syncthreads();
+        if (s + 1 < s1) issue(s + 1);    // travels while the products of stage s run
 #pragma unroll
         for (int t = 0; t < CW_TPT; ++t) {
             const int ot = tid + t * CW_NT;
             if (ot < ntiles_out) {
                 const int it = ot / MT, mt = ot - it * MT;
-                const float* dp = sDel + mt * 4 * CW_LD;
-                const float* ap = sAct + it * 4 * CW_LD;
-                // Float32 partial sums over FOUR columns only, then Float64 (round 2: a 64-column Float32 partial made the parameter
-                // gradient of the regularised toy / chain cases 2-2.5x noisier than the CPU Float32 adjoint; the products of the
-                // cancelling O(10) cotangents must not pile up in Float32)
+                const double* dp = sDel + mt * CW_LD;
+                const double* ap = sAct + it * 4 * CW_LD;
 #pragma unroll 4
-                for (int c4 = 0; c4 < CW_COLS / 4; ++c4) {
-                    float4 d[4], a[4];
+                for (int c2 = 0; c2 < CW_COLS / 2; ++c2) {
+                    double2 d[4], a[4];
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) { d[r] = *reinterpret_cast<const float4*>(dp + r * CW_LD + c4 * 4); a[r] = *reinterpret_cast<const float4*>(ap + r * CW_LD + c4 * 4); }
+                    for (int r = 0; r < 4; ++r) {
+                        d[r] = *reinterpret_cast<const double2*>(dp + r * MT * CW_LD + c2 * 2);
+                        a[r] = *reinterpret_cast<const double2*>(ap + r * CW_LD + c2 * 2);
+                    }
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
 #pragma unroll
                         for (int o = 0; o < 4; ++o) {
                             double v = acc[t][i * 4 + o];
-                            v = fma((double)d[o].x, (double)a[i].x, v); v = fma((double)d[o].y, (double)a[i].y, v);
-                            v = fma((double)d[o].z, (double)a[i].z, v); v = fma((double)d[o].w, (double)a[i].w, v);
+                            v = fma(d[o].x, a[i].x, v); v = fma(d[o].y, a[i].y, v);
                             acc[t][i * 4 + o] = v;
                         }
                 }
@@ -278,7 +328,7 @@ __global__ void __launch_bounds__(CW_NT) dense_wgrad_kernel(const WgDesc desc, c
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int o = 0; o < 4; ++o) {
-                    const int in = it * 4 + i, on = mt * 4 + o;
+                    const int in = it * 4 + i, on = mt + o * MT;
                     if (in < K + (Ld.nobias ? 0 : 1) && on < M) atomicAdd(acc_out + Ld.poff + in * M + on, acc[t][i * 4 + o]);   // Flux order: W column-major, bias (in == K) behind it
                 }
         }
@@ -291,26 +341,38 @@ __global__ void wgrad_finish_kernel(const double* __restrict__ acc, float* __res
 }
 
 // host helper: launch the contraction for all layers of `desc` and convert the FP64 sums to dp (overwritten)
+inline size_t dense_wgrad_smem(int M, int K) {
+    const size_t rows = (size_t)(M + 3) / 4 * 4 + (size_t)(K + 1 + 3) / 4 * 4;
+    return sizeof(double) * rows * CW_LD + sizeof(float) * (size_t)(M + K) * CW_COLS;
+}
+constexpr size_t CW_SMEM_MAX = 227 * 1024;
 inline cudaError_t launch_dense_wgrad(const WgDesc& desc, int NPt, long long ntile, int np, int num_sms, double* acc, float* dp,
                                       cudaStream_t st, int64_t* launches) {
+    if (NPt < 4 || NPt > CW_COLS || (NPt & (NPt - 1)) != 0) return cudaErrorInvalidValue;      // wg_items shifts by log2(NPt)
     cudaError_t e = cudaMemsetAsync(acc, 0, sizeof(double) * np, st);
     if (e != cudaSuccess) return e;
-    int maxrows = 0;
+    size_t smem = 0;
     for (int l = 0; l < desc.nl; ++l) {
-        const int rows = (desc.l[l].M + 3) / 4 * 4 + (desc.l[l].K + 1 + 3) / 4 * 4;
-        maxrows = maxrows > rows ? maxrows : rows;
-        if (((desc.l[l].M + 3) / 4) * ((desc.l[l].K + 1 + 3) / 4) > CW_TPT * CW_NT) return cudaErrorInvalidValue;
+        smem = std::max(smem, dense_wgrad_smem(desc.l[l].M, desc.l[l].K));
+        if (((desc.l[l].M + 3) / 4) * ((desc.l[l].K + 1 + 3) / 4) > CW_MAXTILES) return cudaErrorInvalidValue;
     }
+    if (smem > CW_SMEM_MAX) return cudaErrorInvalidValue;
+    // CTAs per layer: the layers differ 10x in work per stage (output tiles) and a CTA fills the SM's shared memory, so the grid is
+    // several CTAs per SM and layer for the block scheduler to balance.  Measured on the FFJORD step (profiles/r2zz_next_rows_ncu.txt):
+    // 2 / 3 / 4 / 6 / 8 CTAs per SM in total: 2.72 / 2.30 / 2.21 / 2.07 / 2.12 ms; one wave of CTAs dealt to the layers by a cost model
+    // (tiles + a fixed share): 3.6 - 4.5 ms.
     const long long nstage = (ntile * NPt + CW_COLS - 1) / CW_COLS;
-    long long splits = 2LL * num_sms / desc.nl;
+    WgDesc d = desc;
+    static const int oversub = [] { const char* v = getenv("RNDE_CW_OVERSUB"); const int n = v ? atoi(v) : 0; return n > 0 ? n : 6; }();
+    long long splits = (long long)oversub * num_sms / d.nl;
     if (splits > nstage) splits = nstage;
     if (splits < 1) splits = 1;
-    const size_t smem = sizeof(float) * (size_t)maxrows * CW_LD;
+    for (int l = 0; l <= d.nl; ++l) d.cta0[l] = (int)(l * splits);
     if (smem > 48 * 1024) {
         e = cudaFuncSetAttribute(dense_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    dense_wgrad_kernel<<<dim3((unsigned)splits, desc.nl), CW_NT, smem, st>>>(desc, NPt, ntile, acc);
+    dense_wgrad_kernel<<<d.cta0[d.nl], CW_NT, smem, st>>>(d, NPt, ntile, acc);
     wgrad_finish_kernel<<<(np + 255) / 256, 256, 0, st>>>(acc, dp, np);
     if (launches) *launches += 2;
     return cudaGetLastError();

@@ -404,8 +404,8 @@ extern "C" int rnde_create(const rnde_config* cfg, rnde_handle** out) {
         for (int l = 0; l < cfg->n_layers; ++l) {
             const int M = cfg->layer_width[l];
             if (M <= 0 || M > 1024 || cfg->layer_act[l] < 0 || cfg->layer_act[l] > 1) return RNDE_ERR_ARG;
-            // dense_wgrad_kernel: every thread owns at most CW_TPT 4x4 tiles of a layer's (out x (in + bias)) gradient
-            if (cfg->need_backward && ((M + 3) / 4) * ((K + 1 + 3) / 4) > CW_TPT * CW_NT) return RNDE_ERR_UNSUPPORTED;
+            // dense_wgrad_kernel: at most CW_MAXTILES 4x4 tiles of a layer's (out x (in + bias)) gradient, and its stage in shared memory
+            if (cfg->need_backward && (((M + 3) / 4) * ((K + 1 + 3) / 4) > CW_MAXTILES || dense_wgrad_smem(M, K) > CW_SMEM_MAX)) return RNDE_ERR_UNSUPPORTED;
             K = M;
         }
     }
@@ -836,7 +836,7 @@ static int backward_impl(rnde_handle* h, const float* du_dev, const float* dusav
         const int ain[3] = {0, R.a1, R.a2};
         int poff = 0;
         auto add = [&](const float* dptr, int dstride, int doff, const float* aptr, int astride, int aoff, int M, int K, int po, int nobias) {
-            if (desc.nl >= 12) { desc.nl = 13; return; }      // reported below
+            if (desc.nl >= 16) { desc.nl = 17; return; }      // reported below
             WgLayer& w = desc.l[desc.nl++];
             w.dptr = dptr; w.dstride = dstride; w.doff = doff; w.aptr = aptr; w.astride = astride; w.aoff = aoff; w.M = M; w.K = K; w.poff = po; w.nobias = nobias;
         };
@@ -855,10 +855,11 @@ static int backward_impl(rnde_handle* h, const float* du_dev, const float* dusav
                 // transposed chain: dW += u vbar^T
                 add(h->tapeH, hs, us[l], h->tapeH, hs, vbs[l] + k0, M, kc, poff + k0 * M, 1);
             }
-            add(h->tapeH, hs, vecs[l], h->tapeH, hs, 0, 3 * M, 0, poff + M * K + M, 0);      // [bias_W | bias_B | gate_W] = sums of the three vectors
+            // [bias_W | bias_B | gate_W] = sums of the three vectors (K = 0: only the bias row), in chunks that fit the kernel's shared memory
+            for (int m0 = 0; m0 < 3 * M; m0 += 160) add(h->tapeH, hs, vecs[l] + m0, h->tapeH, hs, 0, std::min(160, 3 * M - m0), 0, poff + M * K + M + m0, 0);
             poff += M * K + 4 * M;
         }
-        if (desc.nl > 12) return set_err(h, RNDE_ERR_UNSUPPORTED, "FFJORD weight gradients: layer too large for the contraction kernel");
+        if (desc.nl > 16) return set_err(h, RNDE_ERR_UNSUPPORTED, "FFJORD weight gradients: layer too large for the contraction kernel");
         const int nrec_c = 1 + 6 * s.naccept;
         cudaError_t ce = launch_dense_wgrad(desc, h->NP, (long long)nrec_c * h->Q, (int)h->np, h->num_sms, reinterpret_cast<double*>(h->wg_ws), dp_dev, st, &h->launches);
         if (ce != cudaSuccess) return set_err(h, RNDE_ERR_CUDA, std::string("FFJORD wgrad launch: ") + cudaGetErrorString(ce));
