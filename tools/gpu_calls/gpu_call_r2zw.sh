@@ -1,5 +1,7 @@
 #!/bin/bash
 # ncu --set full of one dense_wgrad_kernel variant: where the time goes (stall reasons, hottest SASS lines)
+# (record of what ran: build_variants/lib_*.so were whole-library builds of intermediate revisions of chain.cuh with -DRNDE_CW_BATCH / _MINB / _NT / _TPT;
+#  the directory is not kept -- results in profiles/r2zz_next_rows_ncu.txt)
 mkdir -p gpurun_out
 V=${1:-b4t512}
 cp build_variants/lib_$V.so regneuralde/jl_b200/libregnde.so
