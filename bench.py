@@ -589,6 +589,11 @@ def secondary_workloads(torch, R, peak) -> dict:
 
         out["neural_sde"]["train_ms_per_step"] = timed(train, 5, 2)
         out["neural_sde"]["train_samples_per_s"] = B / (out["neural_sde"]["train_ms_per_step"] * 1e-3)
+        # algorithmic rate of the solve: drift Chain(Dense(D,H,tanh), Dense(H,D)) per f evaluation, diffusion Dense(D,D) per g evaluation
+        fl = float((int(info["nfe"][0]) * 2 * (D * H + H * D) + int(info["nfe"][1]) * 2 * D * D) * B)
+        out["neural_sde"]["solve_tflops"] = fl / (float(ms) * 1e-3) / 1e12
+        out["neural_sde"]["solve_frac_of_ffma_peak"] = fl / (float(ms) * 1e-3) / 1e12 / float(peak)
+        out["neural_sde"]["note"] = "5 248 weights in shared memory, 128 CTAs x 4 columns, 8 warps per SM: latency bound (profiles/r2zz_next_rows_ncu.txt)"
     except Exception as ex:
         out["neural_sde"] = {"error": repr(ex)[:200]}
     try:
@@ -612,6 +617,11 @@ def secondary_workloads(torch, R, peak) -> dict:
             ms_fwd = timed(lambda: ff(x, ff.p, e), 3, 1)
         out["ffjord"] = {"workload": f"ffjord_tabular train step (MINIBOONE shape: MLPDynamics({Dz},{Hf}), batch {B}, Tsit5 tol 1.4e-8, -mean(logpx), WeightDecay+ADAM)",
                          "ms_per_step": ms, "samples_per_s": B / (ms * 1e-3), "nfe": int(res["nfe"]), "nll": float(res["nll"]), "forward_ms": ms_fwd}
+        # algorithmic rate of the forward solve: the three ConcatSquash layers and their e^T J product per evaluation
+        fl = float(int(res["nfe"]) * 2 * 2 * (Dz * Hf + Hf * Hf + Hf * Dz) * B)
+        out["ffjord"]["forward_tflops"] = fl / (float(ms_fwd) * 1e-3) / 1e12
+        out["ffjord"]["forward_frac_of_ffma_peak"] = fl / (float(ms_fwd) * 1e-3) / 1e12 / float(peak)
+        out["ffjord"]["note"] = "18.6 k weights in shared memory, 128 CTAs x 8 columns, 8 warps per SM: latency bound (profiles/r2zz_next_rows_ncu.txt)"
     except Exception as ex:      # secondary rows never break the headline line
         out["ffjord"] = {"error": repr(ex)[:200]}
     return out
@@ -636,8 +646,8 @@ def grad_check(tr, torch, R) -> dict:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=512, help="samples per GPU")
     ap.add_argument("--tape-capacity", type=int, default=128)
